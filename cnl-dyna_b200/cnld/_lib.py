@@ -1,0 +1,238 @@
+"""
+ctypes binding of libcnld_b200.so (C ABI in include/cnld_b200.h).
+
+This is the binding a cnl-dyna maintainer would drop next to cnld/h2lib/*.pyx (see
+INTEGRATION.md).  The library is the product: if it is missing or no CUDA device is
+present every compute call raises -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libcnld_b200.so')
+
+_lib = None
+
+u32 = C.c_uint
+f64 = C.c_double
+vp = C.c_void_p
+
+
+class Cnldb200Error(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Cnldb200Error(
+                f'{LIB_PATH} not found: build it with `make -C cnl-dyna_b200` '
+                '(or __graft_entry__.build()); libcnld_b200 has no CPU fallback')
+        L = C.CDLL(LIB_PATH)
+        L.cnld_b200_last_error.restype = C.c_char_p
+        L.cnld_b200_version.restype = C.c_char_p
+        L.cnld_b200_launch_count.restype = C.c_ulonglong
+        L.cnld_b200_create.restype = vp
+        L.cnld_b200_create.argtypes = [C.c_int, u32, u32, vp, vp, u32, u32]
+        L.cnld_b200_destroy.argtypes = [vp]
+        L.cnld_b200_set_streams.argtypes = [vp, C.c_int]
+        L.cnld_b200_get_geometry.argtypes = [vp, vp, vp]
+        L.cnld_b200_assemble_slp_ll.argtypes = [vp, f64, f64, vp, u32]
+        L.cnld_b200_lrdecomp.argtypes = [C.c_int, u32, vp, u32, vp]
+        L.cnld_b200_lrsolve.argtypes = [C.c_int, u32, vp, u32, vp, u32, u32]
+        L.cnld_b200_zgemm.argtypes = [C.c_int, u32, u32, u32, f64, vp, u32, vp, u32, f64, vp, u32]
+        L.cnld_b200_set_mbk.argtypes = [vp] * 6
+        L.cnld_b200_set_loads.argtypes = [vp, u32] + [vp] * 7
+        L.cnld_b200_sweep_run.argtypes = [vp, vp, u32, f64, f64, vp, vp, vp]
+        L.cnld_b200_sweep_run_device.argtypes = [vp, vp, u32, f64, f64]
+        L.cnld_b200_sweep_fetch.argtypes = [vp, u32, vp, vp]
+        L.cnld_b200_sweep_stage_times.argtypes = [vp, vp]
+        L.cnld_b200_set_profile.argtypes = [vp, C.c_int]
+        L.cnld_b200_sweep_kernel_stats.argtypes = [vp, vp]
+        L.cnld_b200_pres_vector.argtypes = [vp, vp, u32, f64, f64, f64, vp]
+        L.cnld_b200_pressure.argtypes = [vp, vp, u32, vp, u32, f64, f64, vp, u32, vp]
+        L.cnld_b200_bench_zgemm.argtypes = [C.c_int, u32, u32, u32, C.c_int, vp]
+        L.cnld_b200_bench_dfma.argtypes = [C.c_int, C.c_int, vp]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise Cnldb200Error(lib().cnld_b200_last_error().decode())
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(vp)
+
+
+def device_count():
+    return lib().cnld_b200_device_count()
+
+
+def launch_count():
+    return int(lib().cnld_b200_launch_count())
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class Context:
+    """Mesh + quadrature + FEM data resident on one GPU (opaque cnld_ctx)."""
+
+    def __init__(self, vertices, triangles, q_reg=2, q_sing=4, device=0):
+        self.vertices = _c(vertices, np.float64)
+        self.triangles = _c(triangles, np.uint32)
+        self.nv, self.nt = len(self.vertices), len(self.triangles)
+        self.device = device
+        self.npatch = 0
+        self._h = lib().cnld_b200_create(device, self.nv, self.nt, ptr(self.vertices),
+                                         ptr(self.triangles), q_reg, q_sing)
+        if not self._h:
+            raise Cnldb200Error(lib().cnld_b200_last_error().decode())
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().cnld_b200_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_streams(self, n):
+        check(lib().cnld_b200_set_streams(self._h, int(n)))
+
+    def geometry(self):
+        g = np.zeros(self.nt)
+        n = np.zeros((self.nt, 3))
+        check(lib().cnld_b200_get_geometry(self._h, ptr(g), ptr(n)))
+        return g, n
+
+    def assemble_z(self, k):
+        """Z[i, j] (mathematical indexing) of the Helmholtz SLP, linear basis."""
+        k = complex(k)
+        buf = np.zeros((self.nv, self.nv), dtype=np.complex128)  # column-major => buf = Z^T
+        check(lib().cnld_b200_assemble_slp_ll(self._h, k.real, k.imag, ptr(buf), self.nv))
+        return buf.T
+
+    def set_mbk(self, K, M, B):
+        """K, M, B: scipy sparse (any format) or dense, real, N x N, same shape."""
+        from scipy import sparse as sps
+        K, M, B = (sps.csr_matrix(a) for a in (K, M, B))
+        pat = (abs(K) + abs(M) + abs(B)).tocsr()
+        pat.sort_indices()
+        rows = np.repeat(np.arange(self.nv), np.diff(pat.indptr))
+        cols = pat.indices
+        vals = [np.asarray(a[rows, cols]).ravel().astype(np.float64) for a in (K, M, B)]
+        self._mbk = (_c(pat.indptr, np.int64), _c(cols, np.uint32)) + tuple(_c(v, np.float64) for v in vals)
+        check(lib().cnld_b200_set_mbk(self._h, *[ptr(a) for a in self._mbk]))
+
+    def set_loads(self, F, AVG, on_boundary):
+        from scipy import sparse as sps
+        F, AVG = sps.csc_matrix(F), sps.csc_matrix(AVG)
+        F.sort_indices()
+        AVG.sort_indices()
+        self.npatch = F.shape[1]
+        self._loads = (_c(F.indptr, np.int64), _c(F.indices, np.uint32), _c(F.data, np.float64),
+                       _c(AVG.indptr, np.int64), _c(AVG.indices, np.uint32), _c(AVG.data, np.float64),
+                       _c(on_boundary, np.uint8))
+        check(lib().cnld_b200_set_loads(self._h, self.npatch, *[ptr(a) for a in self._loads]))
+
+    def sweep(self, freqs, c=1500., rho=1000., want_nodes=True):
+        """-> x_patch[nf, P(src), P(dst)], x_node[nf, P(src), N] or None, t[nf]."""
+        freqs = _c(freqs, np.float64)
+        nf, P = len(freqs), self.npatch
+        xp = np.zeros((nf, P, P), dtype=np.complex128)
+        xn = np.zeros((nf, P, self.nv), dtype=np.complex128) if want_nodes else None
+        t = np.zeros(nf)
+        check(lib().cnld_b200_sweep_run(self._h, ptr(freqs), nf, c, rho, ptr(xp), ptr(xn), ptr(t)))
+        return xp, xn, t
+
+    def sweep_device(self, freqs, c=1500., rho=1000.):
+        freqs = _c(freqs, np.float64)
+        check(lib().cnld_b200_sweep_run_device(self._h, ptr(freqs), len(freqs), c, rho))
+
+    def sweep_fetch(self, nf):
+        xp = np.zeros((nf, self.npatch, self.npatch), dtype=np.complex128)
+        check(lib().cnld_b200_sweep_fetch(self._h, nf, ptr(xp), None))
+        return xp
+
+    def stage_times(self):
+        out = np.zeros(4)
+        check(lib().cnld_b200_sweep_stage_times(self._h, ptr(out)))
+        return dict(assemble=out[0], factor=out[1], solve=out[2], launches=int(out[3]))
+
+    def set_profile(self, on=True):
+        check(lib().cnld_b200_set_profile(self._h, int(on)))
+
+    def kernel_stats(self):
+        out = np.zeros(3)
+        check(lib().cnld_b200_sweep_kernel_stats(self._h, ptr(out)))
+        return dict(flops=out[0], seconds=out[1], launches=int(out[2]))
+
+    def pres_vector(self, obs, k, c=1500., rho=1000.):
+        obs = _c(np.atleast_2d(obs), np.float64)
+        out = np.zeros((len(obs), self.nv), dtype=np.complex128)
+        check(lib().cnld_b200_pres_vector(self._h, ptr(obs), len(obs), float(k), c, rho, ptr(out)))
+        return out
+
+    def pressure(self, obs, ks, disp, c=1500., rho=1000.):
+        """disp[nk, nsrc, N] -> p[nk, nsrc, nobs]."""
+        obs = _c(np.atleast_2d(obs), np.float64)
+        ks = _c(np.atleast_1d(ks), np.float64)
+        disp = _c(disp, np.complex128)
+        nk, nsrc, nv = disp.shape
+        assert nk == len(ks) and nv == self.nv
+        out = np.zeros((nk, nsrc, len(obs)), dtype=np.complex128)
+        check(lib().cnld_b200_pressure(self._h, ptr(obs), len(obs), ptr(ks), nk, c, rho, ptr(disp), nsrc,
+                                       ptr(out)))
+        return out
+
+
+def lrdecomp(G, device=0):
+    """Unpivoted LU of G (mathematical indexing); raises like FullFormat._lu
+    (cnld/compressed_formats.py:247-252) on a zero pivot."""
+    n = G.shape[0]
+    a = np.array(np.asarray(G).T, dtype=np.complex128, order='C', copy=True)
+    info = C.c_uint(0)
+    check(lib().cnld_b200_lrdecomp(device, n, ptr(a), n, C.byref(info)))
+    if info.value != 0:
+        raise RuntimeError('failed to calculate LU decomposition')
+    return a.T
+
+
+def lrsolve(LU, b, device=0):
+    n = LU.shape[0]
+    a = np.ascontiguousarray(np.asarray(LU, dtype=np.complex128).T)
+    b = np.asarray(b, dtype=np.complex128)
+    x = np.array(b.reshape(n, -1).T, dtype=np.complex128, order='C', copy=True)  # [nrhs][n]
+    check(lib().cnld_b200_lrsolve(device, n, ptr(a), n, ptr(x), x.shape[0], n))
+    return x.T.reshape(b.shape)
+
+
+def zgemm(A, B, Cm=None, alpha=1.0, device=0):
+    """alpha*A@B (+ Cm) through the DMMA kernel; mathematical indexing."""
+    A = np.asarray(A, dtype=np.complex128)
+    B = np.asarray(B, dtype=np.complex128)
+    m, k = A.shape
+    n = B.shape[1]
+    a, b = np.ascontiguousarray(A.T), np.ascontiguousarray(B.T)
+    c = np.zeros((n, m), dtype=np.complex128) if Cm is None else np.array(np.asarray(Cm).T, dtype=np.complex128, order='C', copy=True)
+    check(lib().cnld_b200_zgemm(device, m, n, k, alpha, ptr(a), m, ptr(b), k, 0.0 if Cm is None else 1.0,
+                                ptr(c), m))
+    return c.T
+
+
+def bench_zgemm(m, n, k, reps=5, device=0):
+    out = C.c_double(0)
+    check(lib().cnld_b200_bench_zgemm(device, m, n, k, reps, C.byref(out)))
+    return out.value
+
+
+def bench_dfma(reps=5, device=0):
+    out = C.c_double(0)
+    check(lib().cnld_b200_bench_dfma(device, reps, C.byref(out)))
+    return out.value

@@ -1,0 +1,277 @@
+// Galerkin assembly of the Helmholtz single-layer operator with linear hat
+// functions, kernel exp(i k r)/(4 pi r):  Z_ij = int int phi_i(x) g(x,y) phi_j(y).
+// Replaces assemble_bem3d_amatrix -> bem->nearfield = assemble_ll_near_bem3d
+// (include/bem3d.h:3028, :1728-1735; kernel form include/helmholtzbem3d.h:32-35 and
+// scratch/demo_zmatrix_hmatrix.c:97-121; call site cnld/compressed_formats.py:629-634).
+//
+// Two kernels accumulate alpha * Z into a pre-initialised matrix (the sweep
+// initialises it with K - w^2 M - j w B and passes alpha = -2 rho w^2, so G is formed
+// without an extra pass over HBM -- cnld/scripts/generate_db.py:54-59):
+//   k_regular : every disjoint triangle pair, q^4 tensor Duffy-Gauss points.  One
+//               thread owns a row triangle (lanes run along rows = the contiguous
+//               direction of the column-major matrix), a CTA streams a chunk of
+//               column triangles through shared memory.  FP64 sincos + rsqrt.
+//   k_singular: one warp per touching pair (identical / common edge / common vertex),
+//               lanes stride the Sauter-Schwab points, warp-shuffle reduction.
+#include "bem.cuh"
+
+namespace cnld {
+
+namespace {
+constexpr int MAXNQ = 16;
+
+constexpr double INV4PI = 0.0795774715459476678844418816863;
+
+// per-triangle setup: Gram determinant g = |(B-A)x(C-A)| = 2*area, unit normal, and the
+// regular rule's points in global coordinates (H2Lib USE_TRIQUADPOINTS, singquad2d.h:120-135)
+__global__ void k_tri_setup(uint nt, uint nq, const __grid_constant__ RegRule R,
+                            const double *__restrict__ x, const uint *__restrict__ t, double *g,
+                            double *nrm, double *qp) {
+  uint i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nt) return;
+  const double *A = x + 3 * (size_t)t[3 * i], *B = x + 3 * (size_t)t[3 * i + 1],
+               *C = x + 3 * (size_t)t[3 * i + 2];
+  double u0 = B[0] - A[0], u1 = B[1] - A[1], u2 = B[2] - A[2];
+  double v0 = C[0] - A[0], v1 = C[1] - A[1], v2 = C[2] - A[2];
+  double c0 = u1 * v2 - u2 * v1, c1 = u2 * v0 - u0 * v2, c2 = u0 * v1 - u1 * v0;
+  double nn = sqrt(c0 * c0 + c1 * c1 + c2 * c2);
+  g[i] = nn;
+  nrm[3 * i] = c0 / nn; nrm[3 * i + 1] = c1 / nn; nrm[3 * i + 2] = c2 / nn;
+  for (uint p = 0; p < nq; p++)
+    for (int d = 0; d < 3; d++)
+      qp[((size_t)i * nq + p) * 3 + d] = A[d] * R.phi[p][0] + B[d] * R.phi[p][1] + C[d] * R.phi[p][2];
+}
+
+// exp(i kr r) * exp(-ki r) / r  for squared distance r2
+template <bool CPLXK>
+__device__ __forceinline__ cplx helmholtz(double r2, double kr, double ki) {
+  double rinv = rsqrt(r2);
+  double r = r2 * rinv;
+  if (CPLXK) rinv *= exp(-ki * r);
+  double s, c;
+  sincos(kr * r, &s, &c);
+  return make_double2(c * rinv, s * rinv);
+}
+
+constexpr int REG_THREADS = 128;
+constexpr int REG_CHUNK = 64;
+
+template <int NQ, bool CPLXK>
+__global__ void __launch_bounds__(REG_THREADS)
+k_regular(uint nt, const __grid_constant__ RegRule R, const uint *__restrict__ tri,
+          const double *__restrict__ qp, const double *__restrict__ g, double kr, double ki,
+          cplx alpha, cplx *Z, size_t ld) {
+  __shared__ double s_qp[REG_CHUNK][NQ][3];
+  __shared__ uint s_tv[REG_CHUNK][3];
+  __shared__ double s_g[REG_CHUNK];
+  const uint t = blockIdx.x * REG_THREADS + threadIdx.x;
+  const uint s0 = blockIdx.y * REG_CHUNK;
+  const uint ns = min((uint)REG_CHUNK, nt - s0);
+  for (uint i = threadIdx.x; i < ns * NQ * 3; i += REG_THREADS)
+    (&s_qp[0][0][0])[i] = qp[(size_t)s0 * NQ * 3 + i];
+  for (uint i = threadIdx.x; i < ns * 3; i += REG_THREADS) (&s_tv[0][0])[i] = tri[(size_t)s0 * 3 + i];
+  for (uint i = threadIdx.x; i < ns; i += REG_THREADS) s_g[i] = g[s0 + i];
+  __syncthreads();
+  if (t >= nt) return;
+  uint tv[3] = {tri[3 * (size_t)t], tri[3 * (size_t)t + 1], tri[3 * (size_t)t + 2]};
+  double xp[NQ][3];
+#pragma unroll
+  for (int p = 0; p < NQ; p++)
+#pragma unroll
+    for (int d = 0; d < 3; d++) xp[p][d] = qp[((size_t)t * NQ + p) * 3 + d];
+  const double gt = g[t] * INV4PI;
+
+  for (uint sl = 0; sl < ns; sl++) {
+    const uint sv0 = s_tv[sl][0], sv1 = s_tv[sl][1], sv2 = s_tv[sl][2];
+    bool touch = (tv[0] == sv0) | (tv[0] == sv1) | (tv[0] == sv2) | (tv[1] == sv0) | (tv[1] == sv1) |
+                 (tv[1] == sv2) | (tv[2] == sv0) | (tv[2] == sv1) | (tv[2] == sv2);
+    if (touch) continue;  // handled by k_singular
+    cplx loc[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) loc[i][j] = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int p = 0; p < NQ; p++) {
+      cplx a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        double dx = xp[p][0] - s_qp[sl][q][0], dy = xp[p][1] - s_qp[sl][q][1],
+               dz = xp[p][2] - s_qp[sl][q][2];
+        cplx kv = helmholtz<CPLXK>(dx * dx + dy * dy + dz * dz, kr, ki);
+        double w0 = R.w[q] * R.phi[q][0], w1 = R.w[q] * R.phi[q][1], w2 = R.w[q] * R.phi[q][2];
+        a0.x = fma(w0, kv.x, a0.x); a0.y = fma(w0, kv.y, a0.y);
+        a1.x = fma(w1, kv.x, a1.x); a1.y = fma(w1, kv.y, a1.y);
+        a2.x = fma(w2, kv.x, a2.x); a2.y = fma(w2, kv.y, a2.y);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        double wi = R.w[p] * R.phi[p][i];
+        loc[i][0].x = fma(wi, a0.x, loc[i][0].x); loc[i][0].y = fma(wi, a0.y, loc[i][0].y);
+        loc[i][1].x = fma(wi, a1.x, loc[i][1].x); loc[i][1].y = fma(wi, a1.y, loc[i][1].y);
+        loc[i][2].x = fma(wi, a2.x, loc[i][2].x); loc[i][2].y = fma(wi, a2.y, loc[i][2].y);
+      }
+    }
+    const double sc = gt * s_g[sl];
+    const cplx f = make_double2(alpha.x * sc, alpha.y * sc);
+    const uint sv[3] = {sv0, sv1, sv2};
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        cplx v = cmul(loc[i][j], f);
+        double *dst = reinterpret_cast<double *>(Z + (size_t)sv[j] * ld + tv[i]);
+        atomicAdd(dst, v.x);
+        atomicAdd(dst + 1, v.y);
+      }
+  }
+}
+
+constexpr int SING_WARPS = 8;
+
+template <bool CPLXK>
+__global__ void __launch_bounds__(SING_WARPS * 32)
+k_singular(size_t npairs, const TouchPair *__restrict__ pairs, const double *__restrict__ x,
+           const double *__restrict__ g, SingTables tab, double kr, double ki, cplx alpha, cplx *Z,
+           size_t ld) {
+  const size_t pid = (size_t)blockIdx.x * SING_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pid >= npairs) return;
+  const TouchPair P = pairs[pid];
+  double V[6][3];
+#pragma unroll
+  for (int v = 0; v < 3; v++)
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      V[v][d] = x[3 * (size_t)P.rv[v] + d];
+      V[3 + v][d] = x[3 * (size_t)P.cv[v] + d];
+    }
+  const uint n = tab.n[P.family];
+  const double *xt = tab.p[P.family], *xs = xt + n, *yt = xs + n, *ys = yt + n, *w = ys + n;
+  double acc[18];
+#pragma unroll
+  for (int i = 0; i < 18; i++) acc[i] = 0.0;
+  for (uint q = lane; q < n; q += 32) {
+    double a[3] = {1.0 - xt[q], xt[q] - xs[q], xs[q]};
+    double b[3] = {1.0 - yt[q], yt[q] - ys[q], ys[q]};
+    double dx = V[0][0] * a[0] + V[1][0] * a[1] + V[2][0] * a[2] - (V[3][0] * b[0] + V[4][0] * b[1] + V[5][0] * b[2]);
+    double dy = V[0][1] * a[0] + V[1][1] * a[1] + V[2][1] * a[2] - (V[3][1] * b[0] + V[4][1] * b[1] + V[5][1] * b[2]);
+    double dz = V[0][2] * a[0] + V[1][2] * a[1] + V[2][2] * a[2] - (V[3][2] * b[0] + V[4][2] * b[1] + V[5][2] * b[2]);
+    cplx kv = helmholtz<CPLXK>(dx * dx + dy * dy + dz * dz, kr, ki);
+    double wq = w[q];
+    kv.x *= wq; kv.y *= wq;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        double ab = a[i] * b[j];
+        acc[2 * (3 * i + j)] = fma(ab, kv.x, acc[2 * (3 * i + j)]);
+        acc[2 * (3 * i + j) + 1] = fma(ab, kv.y, acc[2 * (3 * i + j) + 1]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 18; i++)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+  if (lane == 0) {
+    double sc = g[P.t] * g[P.s] * INV4PI;
+    cplx f = make_double2(alpha.x * sc, alpha.y * sc);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        cplx v = cmul(make_double2(acc[2 * (3 * i + j)], acc[2 * (3 * i + j) + 1]), f);
+        double *dst = reinterpret_cast<double *>(Z + (size_t)P.cv[j] * ld + P.rv[i]);
+        atomicAdd(dst, v.x);
+        atomicAdd(dst + 1, v.y);
+      }
+  }
+}
+
+template <int NQ>
+int launch_regular(cudaStream_t st, const BemDev &b, double kr, double ki, cplx alpha, cplx *Z, size_t ld) {
+  dim3 grid((b.nt + REG_THREADS - 1) / REG_THREADS, (b.nt + REG_CHUNK - 1) / REG_CHUNK);
+  if (ki != 0.0)
+    k_regular<NQ, true><<<grid, REG_THREADS, 0, st>>>(b.nt, b.rule, b.t, b.qp, b.g, kr, ki, alpha, Z, ld);
+  else
+    k_regular<NQ, false><<<grid, REG_THREADS, 0, st>>>(b.nt, b.rule, b.t, b.qp, b.g, kr, ki, alpha, Z, ld);
+  CNLD_CK_LAUNCH();
+  return 0;
+}
+}  // namespace
+
+int bem_create(BemDev &b, int device, uint nv, uint nt, const double *x, const uint *t, uint q, uint q2) {
+  if (q < 1 || q > 4) { set_error("q_reg must be 1..4 (got %u)", q); return -1; }
+  if (q2 < 1 || q2 > 12) { set_error("q_sing must be 1..12 (got %u)", q2); return -1; }
+  b = BemDev();
+  b.device = device; b.nv = nv; b.nt = nt; b.q = q; b.q2 = q2; b.nq = q * q;
+  CNLD_CK(cudaSetDevice(device));
+  CNLD_CK(cudaMalloc(&b.x, sizeof(double) * 3 * (size_t)nv));
+  CNLD_CK(cudaMalloc(&b.t, sizeof(uint) * 3 * (size_t)nt));
+  CNLD_CK(cudaMalloc(&b.g, sizeof(double) * nt));
+  CNLD_CK(cudaMalloc(&b.n, sizeof(double) * 3 * (size_t)nt));
+  CNLD_CK(cudaMalloc(&b.qp, sizeof(double) * 3 * (size_t)nt * b.nq));
+  CNLD_CK(cudaMemcpy(b.x, x, sizeof(double) * 3 * (size_t)nv, cudaMemcpyHostToDevice));
+  CNLD_CK(cudaMemcpy(b.t, t, sizeof(uint) * 3 * (size_t)nt, cudaMemcpyHostToDevice));
+  // regular rule (kernel parameter, lands in the constant bank)
+  std::vector<double> rt, rs, rw;
+  build_triangle_rule(q, rt, rs, rw);
+  memset(&b.rule, 0, sizeof(b.rule));
+  for (uint p = 0; p < b.nq && p < MAXNQ; p++) {
+    b.rule.w[p] = rw[p];
+    b.rule.phi[p][0] = 1.0 - rt[p]; b.rule.phi[p][1] = rt[p] - rs[p]; b.rule.phi[p][2] = rs[p];
+  }
+  // singular families
+  for (int f = FAM_VERT; f <= FAM_ID; f++) {
+    PairRule R;
+    build_pair_rule(f, q, q2, R);
+    size_t n = R.size();
+    std::vector<double> flat;
+    flat.reserve(5 * n);
+    flat.insert(flat.end(), R.xt.begin(), R.xt.end());
+    flat.insert(flat.end(), R.xs.begin(), R.xs.end());
+    flat.insert(flat.end(), R.yt.begin(), R.yt.end());
+    flat.insert(flat.end(), R.ys.begin(), R.ys.end());
+    flat.insert(flat.end(), R.w.begin(), R.w.end());
+    double *d = nullptr;
+    CNLD_CK(cudaMalloc(&d, sizeof(double) * 5 * n));
+    CNLD_CK(cudaMemcpy(d, flat.data(), sizeof(double) * 5 * n, cudaMemcpyHostToDevice));
+    b.sing.p[f] = d;
+    b.sing.n[f] = (uint)n;
+  }
+  std::vector<TouchPair> pairs;
+  build_touching_pairs(nv, nt, t, pairs);
+  b.npairs = pairs.size();
+  CNLD_CK(cudaMalloc(&b.pairs, sizeof(TouchPair) * pairs.size()));
+  CNLD_CK(cudaMemcpy(b.pairs, pairs.data(), sizeof(TouchPair) * pairs.size(), cudaMemcpyHostToDevice));
+  k_tri_setup<<<(nt + 127) / 128, 128>>>(nt, b.nq, b.rule, b.x, b.t, b.g, b.n, b.qp);
+  CNLD_CK_LAUNCH();
+  CNLD_CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+void bem_free(BemDev &b) {
+  cudaFree(b.x); cudaFree(b.t); cudaFree(b.g); cudaFree(b.n); cudaFree(b.qp); cudaFree(b.pairs);
+  for (int f = 0; f < 4; f++) cudaFree(const_cast<double *>(b.sing.p[f]));
+  b = BemDev();
+}
+
+int bem_assemble(cudaStream_t st, const BemDev &b, double kr, double ki, cplx alpha, cplx *Z, size_t ld) {
+  int rc;
+  switch (b.nq) {
+  case 1: rc = launch_regular<1>(st, b, kr, ki, alpha, Z, ld); break;
+  case 4: rc = launch_regular<4>(st, b, kr, ki, alpha, Z, ld); break;
+  case 9: rc = launch_regular<9>(st, b, kr, ki, alpha, Z, ld); break;
+  default: rc = launch_regular<16>(st, b, kr, ki, alpha, Z, ld); break;
+  }
+  if (rc) return rc;
+  unsigned grid = (unsigned)((b.npairs + SING_WARPS - 1) / SING_WARPS);
+  if (ki != 0.0)
+    k_singular<true><<<grid, SING_WARPS * 32, 0, st>>>(b.npairs, b.pairs, b.x, b.g, b.sing, kr, ki, alpha, Z, ld);
+  else
+    k_singular<false><<<grid, SING_WARPS * 32, 0, st>>>(b.npairs, b.pairs, b.x, b.g, b.sing, kr, ki, alpha, Z, ld);
+  CNLD_CK_LAUNCH();
+  return 0;
+}
+
+}  // namespace cnld

@@ -1,0 +1,46 @@
+// Device-side BEM context (mesh + quadrature tables), see assembly.cu.
+#pragma once
+#include "common.cuh"
+#include "quadrature.h"
+
+namespace cnld {
+
+struct SingTables {
+  const double *p[4] = {nullptr, nullptr, nullptr, nullptr};  // per family: xt|xs|yt|ys|w, n each
+  uint n[4] = {0, 0, 0, 0};
+};
+
+struct RegRule {        // single-triangle Duffy-Gauss rule, passed by value to kernels
+  double w[16];         // weights (sum 1/2)
+  double phi[16][3];    // hat values (1-t, t-s, s) at the points
+};
+
+struct BemDev {
+  int device = 0;
+  uint nv = 0, nt = 0, q = 0, q2 = 0, nq = 0;
+  double *x = nullptr;   // [nv][3]
+  uint *t = nullptr;     // [nt][3]
+  double *g = nullptr;   // [nt]   Gram determinant = 2*area
+  double *n = nullptr;   // [nt][3] unit normals
+  double *qp = nullptr;  // [nt][nq][3] regular-rule points in global coordinates
+  RegRule rule;
+  SingTables sing;
+  TouchPair *pairs = nullptr;
+  size_t npairs = 0;
+};
+
+int bem_create(BemDev &b, int device, uint nv, uint nt, const double *x, const uint *t, uint q, uint q2);
+void bem_free(BemDev &b);
+// Z += alpha * Z_slp(k); Z must be initialised by the caller.
+int bem_assemble(cudaStream_t st, const BemDev &b, double kr, double ki, cplx alpha, cplx *Z, size_t ld);
+
+}  // namespace cnld
+
+namespace cnld {
+// pressure.cu
+int pres_vector(cudaStream_t st, const BemDev &b, const double *d_obs, uint nobs, double k, double c,
+                double rho, cplx *d_pvec);
+int pres_points(cudaStream_t st, const BemDev &b, double *d_sp);
+int pressure_field(cudaStream_t st, const BemDev &b, const double *d_obs, uint nobs, const double *d_sp,
+                   double k, double c, double rho, const cplx *d_disp, uint nsrc, cplx *d_D, cplx *d_out);
+}  // namespace cnld

@@ -1,0 +1,517 @@
+// C ABI of libcnld_b200.so (see include/cnld_b200.h) and the per-frequency sweep
+// pipeline: init G with K - w^2 M - j w B -> accumulate (-2 rho w^2) Z(k) -> unpivoted LU
+// -> solve all source patches -> conj / boundary mask / patch average
+// (cnld/scripts/generate_db.py:30-130).
+#include "../../include/cnld_b200.h"
+
+#include <cmath>
+#include <mutex>
+
+#include "bem.cuh"
+
+namespace cnld {
+std::atomic<unsigned long long> g_launches{0};
+static thread_local std::string t_err;
+static std::string g_err;
+static std::mutex g_err_mu;
+void set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_err = buf;
+}
+
+namespace sweep {
+constexpr int MAX_SLOTS = 8;
+constexpr double TWO_PI = 6.283185307179586476925286766559;
+
+struct Slot {
+  cudaStream_t st = nullptr;
+  cplx *G = nullptr;      // nv x nv
+  cplx *X = nullptr;      // nv x P
+  cplx *hX = nullptr;     // pinned staging for x_node
+  LuWork lu;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  long pending = -1;      // frequency index whose x_node sits in hX
+};
+}  // namespace sweep
+}  // namespace cnld
+
+using namespace cnld;
+using namespace cnld::sweep;
+
+struct cnld_ctx {
+  BemDev bem;
+  int nslots = 2;
+  Slot slots[MAX_SLOTS];
+  bool ws_ready = false;
+  // FEM operators, one CSR pattern
+  size_t nnz = 0;
+  int64_t *d_indptr = nullptr;
+  uint *d_indices = nullptr;
+  double *d_K = nullptr, *d_M = nullptr, *d_B = nullptr;
+  // loads
+  uint P = 0;
+  int64_t *d_f_indptr = nullptr, *d_a_indptr = nullptr;
+  uint *d_f_idx = nullptr, *d_a_idx = nullptr;
+  double *d_f_val = nullptr, *d_a_val = nullptr;
+  uint8_t *d_ob = nullptr;
+  // results of the last sweep
+  cplx *d_xpatch = nullptr;
+  size_t xpatch_cap = 0;
+  cplx *d_xnode = nullptr;  // only for run_device with keep_node
+  double stage[4] = {0, 0, 0, 0};
+  bool profile = false;
+  double kstat[3] = {0, 0, 0};  // trailing ZGEMM: flops, seconds, launches (last sweep)
+  // pressure scratch
+  double *d_sp = nullptr;
+};
+
+namespace cnld_capi {
+
+__global__ void k_scatter_mbk(uint nv, const int64_t *__restrict__ indptr, const uint *__restrict__ indices,
+                              const double *__restrict__ K, const double *__restrict__ M,
+                              const double *__restrict__ B, double omega, cplx *G, size_t ld) {
+  // one warp per row: G[i,j] = K - w^2 M - j w B   (cnld/fem.py:1305)
+  uint row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint lane = threadIdx.x & 31;
+  if (row >= nv) return;
+  double w2 = omega * omega;
+  for (int64_t p = indptr[row] + lane; p < indptr[row + 1]; p += 32) {
+    G[(size_t)indices[p] * ld + row] = make_double2(K[p] - w2 * M[p], -omega * B[p]);
+  }
+}
+
+__global__ void k_build_rhs(uint P, const int64_t *__restrict__ indptr, const uint *__restrict__ idx,
+                            const double *__restrict__ val, cplx *X, size_t ldx) {
+  uint col = blockIdx.x;
+  if (col >= P) return;
+  for (int64_t p = indptr[col] + threadIdx.x; p < indptr[col + 1]; p += blockDim.x)
+    X[(size_t)col * ldx + idx[p]] = make_double2(val[p], 0.0);
+}
+
+// x = conj(x); x[ob] = 0; x_patch[src][dst] = sum_i AVG[i,dst] x[i]   (generate_db.py:89-99)
+__global__ void __launch_bounds__(256)
+k_epilogue(uint nv, uint P, cplx *X, size_t ldx, const uint8_t *__restrict__ ob,
+           const int64_t *__restrict__ a_indptr, const uint *__restrict__ a_idx,
+           const double *__restrict__ a_val, cplx *xpatch) {
+  const uint src = blockIdx.x;
+  cplx *x = X + (size_t)src * ldx;
+  for (uint i = threadIdx.x; i < nv; i += blockDim.x) {
+    cplx v = x[i];
+    v.y = -v.y;
+    if (ob[i]) v = make_double2(0.0, 0.0);
+    x[i] = v;
+  }
+  __syncthreads();
+  const uint warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (uint dst = warp; dst < P; dst += nw) {
+    double sr = 0.0, si = 0.0;
+    for (int64_t p = a_indptr[dst] + lane; p < a_indptr[dst + 1]; p += 32) {
+      cplx v = x[a_idx[p]];
+      sr = fma(a_val[p], v.x, sr);
+      si = fma(a_val[p], v.y, si);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      sr += __shfl_xor_sync(0xffffffffu, sr, off);
+      si += __shfl_xor_sync(0xffffffffu, si, off);
+    }
+    if (lane == 0) xpatch[(size_t)src * P + dst] = make_double2(sr, si);
+  }
+}
+
+template <typename T>
+int upload(T *&d, const T *h, size_t n) {
+  if (d) { cudaFree(d); d = nullptr; }
+  CNLD_CK(cudaMalloc(&d, sizeof(T) * (n ? n : 1)));
+  if (n) CNLD_CK(cudaMemcpy(d, h, sizeof(T) * n, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int ensure_workspace(cnld_ctx *c, bool need_host_stage) {
+  const size_t nv = c->bem.nv;
+  CNLD_CK(cudaSetDevice(c->bem.device));
+  for (int s = 0; s < c->nslots; s++) {
+    Slot &S = c->slots[s];
+    if (!S.st) CNLD_CK(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+    if (!S.G) CNLD_CK(cudaMalloc(&S.G, sizeof(cplx) * nv * nv));
+    if (!S.X) CNLD_CK(cudaMalloc(&S.X, sizeof(cplx) * nv * (c->P ? c->P : 1)));
+    if (!S.lu.linv && lu_work_alloc(S.lu, (uint)nv)) return -1;
+    lu_profile(S.lu, c->profile);
+    for (int e = 0; e < 4; e++)
+      if (!S.ev[e]) CNLD_CK(cudaEventCreate(&S.ev[e]));
+    if (need_host_stage && !S.hX) CNLD_CK(cudaMallocHost(&S.hX, sizeof(cplx) * nv * c->P));
+  }
+  c->ws_ready = true;
+  return 0;
+}
+
+void free_workspace(cnld_ctx *c) {
+  for (int s = 0; s < MAX_SLOTS; s++) {
+    Slot &S = c->slots[s];
+    if (S.st) cudaStreamSynchronize(S.st);
+    cudaFree(S.G); cudaFree(S.X);
+    if (S.hX) cudaFreeHost(S.hX);
+    lu_work_free(S.lu);
+    for (int e = 0; e < 4; e++) if (S.ev[e]) cudaEventDestroy(S.ev[e]);
+    if (S.st) cudaStreamDestroy(S.st);
+    S = Slot();
+  }
+  c->ws_ready = false;
+}
+
+// enqueue one frequency on a slot; results: xpatch slice (device), X holds x_node
+int enqueue_frequency(cnld_ctx *c, Slot &S, double f, double cs, double rho, cplx *d_xpatch_f) {
+  const uint nv = c->bem.nv, P = c->P;
+  const double omega = TWO_PI * f, k = omega / cs;
+  CNLD_CK(cudaEventRecord(S.ev[0], S.st));
+  CNLD_CK(cudaMemsetAsync(S.G, 0, sizeof(cplx) * (size_t)nv * nv, S.st));
+  k_scatter_mbk<<<(nv * 32 + 255) / 256, 256, 0, S.st>>>(nv, c->d_indptr, c->d_indices, c->d_K, c->d_M,
+                                                      c->d_B, omega, S.G, nv);
+  CNLD_CK_LAUNCH();
+  if (f != 0.0) {
+    // Gbe = -omg^2 * 2 * rho * Z   (generate_db.py:55-56)
+    if (bem_assemble(S.st, c->bem, k, 0.0, make_double2(-omega * omega * 2.0 * rho, 0.0), S.G, nv)) return -1;
+  }
+  CNLD_CK(cudaEventRecord(S.ev[1], S.st));
+  if (lu_factor(S.st, S.lu, S.G, nv)) return -1;
+  CNLD_CK(cudaEventRecord(S.ev[2], S.st));
+  CNLD_CK(cudaMemsetAsync(S.X, 0, sizeof(cplx) * (size_t)nv * P, S.st));
+  k_build_rhs<<<P, 128, 0, S.st>>>(P, c->d_f_indptr, c->d_f_idx, c->d_f_val, S.X, nv);
+  CNLD_CK_LAUNCH();
+  if (lu_solve(S.st, S.lu, S.G, nv, S.X, P, nv)) return -1;
+  k_epilogue<<<P, 256, 0, S.st>>>(nv, P, S.X, nv, c->d_ob, c->d_a_indptr, c->d_a_idx, c->d_a_val,
+                                  d_xpatch_f);
+  CNLD_CK_LAUNCH();
+  CNLD_CK(cudaEventRecord(S.ev[3], S.st));
+  return 0;
+}
+
+int check_ready(cnld_ctx *c) {
+  if (!c) { set_error("null context"); return -1; }
+  if (!c->d_indptr) { set_error("cnld_b200_set_mbk has not been called"); return -1; }
+  if (!c->d_f_indptr) { set_error("cnld_b200_set_loads has not been called"); return -1; }
+  return 0;
+}
+
+int sweep_impl(cnld_ctx *c, const double *freqs, uint nf, double cs, double rho, cnld_field *x_patch,
+               cnld_field *x_node, double *t_freq, bool device_only) {
+  if (check_ready(c)) return -1;
+  const size_t nv = c->bem.nv, P = c->P;
+  if (ensure_workspace(c, x_node != nullptr)) return -1;
+  if (c->xpatch_cap < nf) {
+    cudaFree(c->d_xpatch);
+    c->d_xpatch = nullptr;
+    CNLD_CK(cudaMalloc(&c->d_xpatch, sizeof(cplx) * (size_t)nf * P * P));
+    c->xpatch_cap = nf;
+  }
+  for (int s = 0; s < c->nslots; s++) c->slots[s].pending = -1;
+  c->kstat[0] = c->kstat[1] = c->kstat[2] = 0.0;
+  double acc[3] = {0, 0, 0};
+  unsigned long long l0 = g_launches.load();
+  auto drain = [&](Slot &S) -> int {
+    if (S.pending < 0) return 0;
+    CNLD_CK(cudaEventSynchronize(S.ev[3]));
+    float ms[3];
+    for (int e = 0; e < 3; e++) { CNLD_CK(cudaEventElapsedTime(&ms[e], S.ev[e], S.ev[e + 1])); acc[e] += ms[e] * 1e-3; }
+    if (t_freq) t_freq[S.pending] = (ms[0] + ms[1] + ms[2]) * 1e-3;
+    if (x_node) memcpy(reinterpret_cast<cplx *>(x_node) + (size_t)S.pending * P * nv, S.hX, sizeof(cplx) * P * nv);
+    if (c->profile) {
+      double sec, fl, nl;
+      if (lu_trailing_stats(S.lu, &sec, &fl, &nl)) return -1;
+      c->kstat[0] += fl; c->kstat[1] += sec; c->kstat[2] += nl;
+    }
+    uint info = 0;
+    CNLD_CK(cudaMemcpy(&info, S.lu.info, sizeof(uint), cudaMemcpyDeviceToHost));
+    if (info) { set_error("failed to calculate LU decomposition (pivot %u, frequency index %ld)", info - 1, S.pending); return -2; }
+    S.pending = -1;
+    return 0;
+  };
+  for (uint i = 0; i < nf; i++) {
+    Slot &S = c->slots[i % c->nslots];
+    int rc = drain(S);
+    if (rc) return rc;
+    if (enqueue_frequency(c, S, freqs[i], cs, rho, c->d_xpatch + (size_t)i * P * P)) return -1;
+    if (x_node) CNLD_CK(cudaMemcpyAsync(S.hX, S.X, sizeof(cplx) * P * nv, cudaMemcpyDeviceToHost, S.st));
+    if (x_node) CNLD_CK(cudaEventRecord(S.ev[3], S.st));
+    S.pending = i;
+  }
+  for (int s = 0; s < c->nslots; s++) {
+    int rc = drain(c->slots[(nf + s) % c->nslots]);
+    if (rc) return rc;
+  }
+  if (!device_only && x_patch)
+    CNLD_CK(cudaMemcpy(x_patch, c->d_xpatch, sizeof(cplx) * (size_t)nf * P * P, cudaMemcpyDeviceToHost));
+  c->stage[0] = acc[0]; c->stage[1] = acc[1]; c->stage[2] = acc[2];
+  c->stage[3] = (double)(g_launches.load() - l0);
+  return 0;
+}
+}  // namespace cnld_capi
+using namespace cnld_capi;
+
+extern "C" {
+
+const char *cnld_b200_last_error(void) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  t_err = g_err;
+  return t_err.c_str();
+}
+const char *cnld_b200_version(void) { return "cnld_b200 0.1 (sm_100a)"; }
+int cnld_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+unsigned long long cnld_b200_launch_count(void) { return g_launches.load(); }
+
+cnld_ctx *cnld_b200_create(int device, cnld_uint nv, cnld_uint nt, const double *x, const cnld_uint *t,
+                           cnld_uint q_reg, cnld_uint q_sing) {
+  if (cnld_b200_device_count() <= device) {
+    set_error("no CUDA device %d (libcnld_b200 has no CPU fallback)", device);
+    return nullptr;
+  }
+  for (size_t i = 0; i < 3 * (size_t)nt; i++)
+    if (t[i] >= nv) { set_error("triangle vertex index out of range"); return nullptr; }
+  cnld_ctx *c = new cnld_ctx();
+  if (bem_create(c->bem, device, nv, nt, x, t, q_reg, q_sing)) { delete c; return nullptr; }
+  return c;
+}
+
+void cnld_b200_destroy(cnld_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->bem.device);
+  free_workspace(c);
+  cudaFree(c->d_indptr); cudaFree(c->d_indices); cudaFree(c->d_K); cudaFree(c->d_M); cudaFree(c->d_B);
+  cudaFree(c->d_f_indptr); cudaFree(c->d_a_indptr); cudaFree(c->d_f_idx); cudaFree(c->d_a_idx);
+  cudaFree(c->d_f_val); cudaFree(c->d_a_val); cudaFree(c->d_ob); cudaFree(c->d_xpatch); cudaFree(c->d_xnode);
+  cudaFree(c->d_sp);
+  bem_free(c->bem);
+  delete c;
+}
+
+int cnld_b200_set_streams(cnld_ctx *c, int n) {
+  if (!c || n < 1 || n > MAX_SLOTS) { set_error("nstreams must be 1..%d", MAX_SLOTS); return -1; }
+  if (n != c->nslots) { cudaSetDevice(c->bem.device); free_workspace(c); c->nslots = n; }
+  return 0;
+}
+
+int cnld_b200_get_geometry(cnld_ctx *c, double *g, double *n) {
+  if (!c) { set_error("null context"); return -1; }
+  CNLD_CK(cudaSetDevice(c->bem.device));
+  if (g) CNLD_CK(cudaMemcpy(g, c->bem.g, sizeof(double) * c->bem.nt, cudaMemcpyDeviceToHost));
+  if (n) CNLD_CK(cudaMemcpy(n, c->bem.n, sizeof(double) * 3 * c->bem.nt, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int cnld_b200_assemble_slp_ll(cnld_ctx *c, double k_re, double k_im, cnld_field *Z, cnld_uint ld) {
+  if (!c) { set_error("null context"); return -1; }
+  const size_t nv = c->bem.nv;
+  if (ld < nv) { set_error("ld < rows"); return -1; }
+  CNLD_CK(cudaSetDevice(c->bem.device));
+  cplx *dZ = nullptr;
+  CNLD_CK(cudaMalloc(&dZ, sizeof(cplx) * nv * nv));
+  int rc = 0;
+  do {
+    if (cudaMemsetAsync(dZ, 0, sizeof(cplx) * nv * nv, 0) != cudaSuccess) { set_error("memset failed"); rc = -1; break; }
+    if (bem_assemble(0, c->bem, k_re, k_im, make_double2(1.0, 0.0), dZ, nv)) { rc = -1; break; }
+    cudaError_t e = cudaMemcpy2D(Z, sizeof(cplx) * ld, dZ, sizeof(cplx) * nv, sizeof(cplx) * nv, nv,
+                                 cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("copy back: %s", cudaGetErrorString(e)); rc = -1; }
+  } while (0);
+  cudaFree(dZ);
+  return rc;
+}
+
+int cnld_b200_nearfield_slp_ll(cnld_ctx *c, double, double, const cnld_uint *, cnld_uint, const cnld_uint *,
+                               cnld_uint, cnld_field *, cnld_uint) {
+  (void)c;
+  set_error("cnld_b200_nearfield_slp_ll: not available in this build");
+  return -1;
+}
+
+int cnld_b200_lrdecomp(int device, cnld_uint n, cnld_field *a, cnld_uint ld, cnld_uint *info) {
+  if (cnld_b200_device_count() <= device) { set_error("no CUDA device %d (no CPU fallback)", device); return -1; }
+  CNLD_CK(cudaSetDevice(device));
+  cplx *dA = nullptr;
+  CNLD_CK(cudaMalloc(&dA, sizeof(cplx) * (size_t)n * n));
+  LuWork w;
+  int rc = 0;
+  do {
+    if (cudaMemcpy2D(dA, sizeof(cplx) * n, a, sizeof(cplx) * ld, sizeof(cplx) * n, n, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); rc = -1; break; }
+    if (lu_work_alloc(w, n) || lu_factor(0, w, dA, n)) { rc = -1; break; }
+    uint inf = 0;
+    if (cudaMemcpy(&inf, w.info, sizeof(uint), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); rc = -1; break; }
+    if (info) *info = inf;
+    if (cudaMemcpy2D(a, sizeof(cplx) * ld, dA, sizeof(cplx) * n, sizeof(cplx) * n, n, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); rc = -1; }
+  } while (0);
+  lu_work_free(w);
+  cudaFree(dA);
+  return rc;
+}
+
+int cnld_b200_lrsolve(int device, cnld_uint n, const cnld_field *lu, cnld_uint ld, cnld_field *x,
+                      cnld_uint nrhs, cnld_uint ldx) {
+  if (cnld_b200_device_count() <= device) { set_error("no CUDA device %d (no CPU fallback)", device); return -1; }
+  CNLD_CK(cudaSetDevice(device));
+  cplx *dA = nullptr, *dX = nullptr;
+  CNLD_CK(cudaMalloc(&dA, sizeof(cplx) * (size_t)n * n));
+  CNLD_CK(cudaMalloc(&dX, sizeof(cplx) * (size_t)n * nrhs));
+  LuWork w;
+  int rc = 0;
+  do {
+    if (cudaMemcpy2D(dA, sizeof(cplx) * n, lu, sizeof(cplx) * ld, sizeof(cplx) * n, n, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy2D(dX, sizeof(cplx) * n, x, sizeof(cplx) * ldx, sizeof(cplx) * n, nrhs, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); rc = -1; break; }
+    if (lu_work_alloc(w, n) || lu_invert_diag(0, w, dA, n) || lu_solve(0, w, dA, n, dX, nrhs, n)) { rc = -1; break; }
+    if (cudaMemcpy2D(x, sizeof(cplx) * ldx, dX, sizeof(cplx) * n, sizeof(cplx) * n, nrhs, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); rc = -1; }
+  } while (0);
+  lu_work_free(w);
+  cudaFree(dA);
+  cudaFree(dX);
+  return rc;
+}
+
+int cnld_b200_zgemm(int device, cnld_uint m, cnld_uint n, cnld_uint k, double alpha, const cnld_field *A,
+                    cnld_uint lda, const cnld_field *B, cnld_uint ldb, double beta, cnld_field *C,
+                    cnld_uint ldc) {
+  if (cnld_b200_device_count() <= device) { set_error("no CUDA device %d (no CPU fallback)", device); return -1; }
+  if (!((alpha == 1.0 || alpha == -1.0) && (beta == 0.0 || beta == 1.0))) { set_error("alpha must be +-1, beta 0 or 1"); return -1; }
+  CNLD_CK(cudaSetDevice(device));
+  cplx *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  CNLD_CK(cudaMalloc(&dA, sizeof(cplx) * (size_t)m * k + 16));
+  CNLD_CK(cudaMalloc(&dB, sizeof(cplx) * (size_t)k * n + 16));
+  CNLD_CK(cudaMalloc(&dC, sizeof(cplx) * (size_t)m * n + 16));
+  int rc = 0;
+  do {
+    if (cudaMemcpy2D(dA, sizeof(cplx) * m, A, sizeof(cplx) * lda, sizeof(cplx) * m, k, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy2D(dB, sizeof(cplx) * k, B, sizeof(cplx) * ldb, sizeof(cplx) * k, n, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy2D(dC, sizeof(cplx) * m, C, sizeof(cplx) * ldc, sizeof(cplx) * m, n, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); rc = -1; break; }
+    if (zgemm(0, m, n, k, alpha, dA, m, dB, k, beta, dC, m)) { rc = -1; break; }
+    cudaError_t e = cudaMemcpy2D(C, sizeof(cplx) * ldc, dC, sizeof(cplx) * m, sizeof(cplx) * m, n, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("zgemm: %s", cudaGetErrorString(e)); rc = -1; }
+  } while (0);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  return rc;
+}
+
+int cnld_b200_set_mbk(cnld_ctx *c, const int64_t *indptr, const cnld_uint *indices, const double *K,
+                      const double *M, const double *B) {
+  if (!c) { set_error("null context"); return -1; }
+  CNLD_CK(cudaSetDevice(c->bem.device));
+  const size_t nv = c->bem.nv;
+  size_t nnz = (size_t)indptr[nv];
+  for (size_t i = 0; i < nnz; i++) if (indices[i] >= nv) { set_error("MBK column index out of range"); return -1; }
+  c->nnz = nnz;
+  if (upload(c->d_indptr, indptr, nv + 1) || upload(c->d_indices, indices, nnz) || upload(c->d_K, K, nnz) ||
+      upload(c->d_M, M, nnz) || upload(c->d_B, B, nnz)) return -1;
+  return 0;
+}
+
+int cnld_b200_set_loads(cnld_ctx *c, cnld_uint P, const int64_t *f_indptr, const cnld_uint *f_idx,
+                        const double *f_val, const int64_t *a_indptr, const cnld_uint *a_idx,
+                        const double *a_val, const uint8_t *ob) {
+  if (!c) { set_error("null context"); return -1; }
+  CNLD_CK(cudaSetDevice(c->bem.device));
+  const size_t nv = c->bem.nv;
+  for (int64_t i = 0; i < f_indptr[P]; i++) if (f_idx[i] >= nv) { set_error("F row index out of range"); return -1; }
+  for (int64_t i = 0; i < a_indptr[P]; i++) if (a_idx[i] >= nv) { set_error("AVG row index out of range"); return -1; }
+  if (P != c->P) { free_workspace(c); c->xpatch_cap = 0; }
+  c->P = P;
+  if (upload(c->d_f_indptr, f_indptr, (size_t)P + 1) || upload(c->d_f_idx, f_idx, (size_t)f_indptr[P]) ||
+      upload(c->d_f_val, f_val, (size_t)f_indptr[P]) || upload(c->d_a_indptr, a_indptr, (size_t)P + 1) ||
+      upload(c->d_a_idx, a_idx, (size_t)a_indptr[P]) || upload(c->d_a_val, a_val, (size_t)a_indptr[P]) ||
+      upload(c->d_ob, ob, nv)) return -1;
+  return 0;
+}
+
+int cnld_b200_sweep_run(cnld_ctx *c, const double *freqs, cnld_uint nf, double cs, double rho,
+                        cnld_field *x_patch, cnld_field *x_node, double *t_freq) {
+  return sweep_impl(c, freqs, nf, cs, rho, x_patch, x_node, t_freq, false);
+}
+
+int cnld_b200_sweep_run_device(cnld_ctx *c, const double *freqs, cnld_uint nf, double cs, double rho) {
+  return sweep_impl(c, freqs, nf, cs, rho, nullptr, nullptr, nullptr, true);
+}
+
+int cnld_b200_sweep_fetch(cnld_ctx *c, cnld_uint nf, cnld_field *x_patch, cnld_field *x_node) {
+  if (!c || !c->d_xpatch || nf > c->xpatch_cap) { set_error("no sweep results to fetch"); return -1; }
+  if (x_node) { set_error("x_node is not retained by sweep_run_device; use cnld_b200_sweep_run"); return -1; }
+  CNLD_CK(cudaSetDevice(c->bem.device));
+  CNLD_CK(cudaMemcpy(x_patch, c->d_xpatch, sizeof(cplx) * (size_t)nf * c->P * c->P, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int cnld_b200_sweep_stage_times(cnld_ctx *c, double *out) {
+  if (!c) { set_error("null context"); return -1; }
+  for (int i = 0; i < 4; i++) out[i] = c->stage[i];
+  return 0;
+}
+
+int cnld_b200_set_profile(cnld_ctx *c, int on) {
+  if (!c) { set_error("null context"); return -1; }
+  c->profile = on != 0;
+  for (int s = 0; s < c->nslots; s++)
+    if (c->slots[s].lu.linv) lu_profile(c->slots[s].lu, c->profile);
+  return 0;
+}
+
+int cnld_b200_sweep_kernel_stats(cnld_ctx *c, double *out) {
+  if (!c) { set_error("null context"); return -1; }
+  for (int i = 0; i < 3; i++) out[i] = c->kstat[i];
+  return 0;
+}
+
+int cnld_b200_pres_vector(cnld_ctx *c, const double *obs, cnld_uint nobs, double k, double cs, double rho,
+                          cnld_field *pvec) {
+  if (!c) { set_error("null context"); return -1; }
+  CNLD_CK(cudaSetDevice(c->bem.device));
+  double *d_obs = nullptr;
+  cplx *d_p = nullptr;
+  CNLD_CK(cudaMalloc(&d_obs, sizeof(double) * 3 * (size_t)nobs));
+  CNLD_CK(cudaMalloc(&d_p, sizeof(cplx) * (size_t)nobs * c->bem.nv));
+  int rc = 0;
+  do {
+    if (cudaMemcpy(d_obs, obs, sizeof(double) * 3 * (size_t)nobs, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); rc = -1; break; }
+    if (pres_vector(0, c->bem, d_obs, nobs, k, cs, rho, d_p)) { rc = -1; break; }
+    cudaError_t e = cudaMemcpy(pvec, d_p, sizeof(cplx) * (size_t)nobs * c->bem.nv, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("pres_vector: %s", cudaGetErrorString(e)); rc = -1; }
+  } while (0);
+  cudaFree(d_obs);
+  cudaFree(d_p);
+  return rc;
+}
+
+int cnld_b200_pressure(cnld_ctx *c, const double *obs, cnld_uint nobs, const double *ks, cnld_uint nk,
+                       double cs, double rho, const cnld_field *disp, cnld_uint nsrc, cnld_field *p) {
+  if (!c) { set_error("null context"); return -1; }
+  CNLD_CK(cudaSetDevice(c->bem.device));
+  const size_t nv = c->bem.nv, nt = c->bem.nt;
+  double *d_obs = nullptr;
+  cplx *d_disp = nullptr, *d_D = nullptr, *d_out = nullptr;
+  if (!c->d_sp) {
+    CNLD_CK(cudaMalloc(&c->d_sp, sizeof(double) * 2 * 3 * nt));
+    if (pres_points(0, c->bem, c->d_sp)) return -1;
+  }
+  CNLD_CK(cudaMalloc(&d_obs, sizeof(double) * 3 * (size_t)nobs));
+  CNLD_CK(cudaMalloc(&d_disp, sizeof(cplx) * nsrc * nv));
+  CNLD_CK(cudaMalloc(&d_D, sizeof(cplx) * nsrc * 3 * nt));
+  CNLD_CK(cudaMalloc(&d_out, sizeof(cplx) * (size_t)nsrc * nobs));
+  int rc = 0;
+  do {
+    if (cudaMemcpy(d_obs, obs, sizeof(double) * 3 * (size_t)nobs, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); rc = -1; break; }
+    for (uint ik = 0; ik < nk && !rc; ik++) {
+      const cplx *hd = reinterpret_cast<const cplx *>(disp) + (size_t)ik * nsrc * nv;
+      if (cudaMemcpyAsync(d_disp, hd, sizeof(cplx) * nsrc * nv, cudaMemcpyHostToDevice, 0) != cudaSuccess) { set_error("H2D failed"); rc = -1; break; }
+      if (pressure_field(0, c->bem, d_obs, nobs, c->d_sp, ks[ik], cs, rho, d_disp, nsrc, d_D, d_out)) { rc = -1; break; }
+      cudaError_t e = cudaMemcpy(reinterpret_cast<cplx *>(p) + (size_t)ik * nsrc * nobs, d_out,
+                                 sizeof(cplx) * (size_t)nsrc * nobs, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) { set_error("pressure: %s", cudaGetErrorString(e)); rc = -1; }
+    }
+  } while (0);
+  cudaFree(d_obs); cudaFree(d_disp); cudaFree(d_D); cudaFree(d_out);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// Shared declarations for libcnld_b200 (sm_100a).  Complex numbers are double2
+// (re, im), layout-identical to C99 double _Complex / H2Lib `field`.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+typedef double2 cplx;
+typedef unsigned int uint;
+
+namespace cnld {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<unsigned long long> g_launches;
+inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define CNLD_CK(call)                                                                     \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      cnld::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return -1;                                                                          \
+    }                                                                                     \
+  } while (0)
+
+#define CNLD_CK_LAUNCH()                                                                  \
+  do {                                                                                    \
+    cnld::count_launch();                                                                 \
+    cudaError_t e__ = cudaGetLastError();                                                 \
+    if (e__ != cudaSuccess) {                                                             \
+      cnld::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return -1;                                                                          \
+    }                                                                                     \
+  } while (0)
+
+__host__ __device__ inline cplx cmul(cplx a, cplx b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ inline cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__host__ __device__ inline cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__host__ __device__ inline cplx cinv(cplx a) {
+  double d = 1.0 / (a.x * a.x + a.y * a.y);
+  return make_double2(a.x * d, -a.y * d);
+}
+// c += a*b
+__device__ __forceinline__ void cfma(cplx &c, cplx a, cplx b) {
+  c.x = fma(a.x, b.x, c.x);
+  c.x = fma(-a.y, b.y, c.x);
+  c.y = fma(a.x, b.y, c.y);
+  c.y = fma(a.y, b.x, c.y);
+}
+// c -= a*b
+__device__ __forceinline__ void cfms(cplx &c, cplx a, cplx b) {
+  c.x = fma(-a.x, b.x, c.x);
+  c.x = fma(a.y, b.y, c.x);
+  c.y = fma(-a.x, b.y, c.y);
+  c.y = fma(-a.y, b.x, c.y);
+}
+
+// ---- dense kernels (zgemm.cu / lu.cu) --------------------------------------
+// C(MxN) = beta*C + alpha*A(MxK)*B(KxN); alpha in {+1,-1}, beta in {0,1};
+// column-major, interleaved complex.  In-place (C aliasing A or B) is safe only
+// when one CTA tile spans the full extent that is re-read (see lu.cu).
+int zgemm(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
+          const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc);
+
+struct LuWork {
+  uint n = 0, nb = 0, nblk = 0;
+  cplx *linv = nullptr;  // [nblk][nb*nb]
+  cplx *uinv = nullptr;  // [nblk][nb*nb]
+  uint *info = nullptr;  // device flag: 0 ok else first failing pivot + 1
+  cplx *panel = nullptr; // scratch for out-of-place panel updates
+  bool prof = false;     // record events around every trailing-update ZGEMM
+  std::vector<cudaEvent_t> pe;
+};
+int lu_work_alloc(LuWork &w, uint n);
+void lu_work_free(LuWork &w);
+// form inv(L_kk), inv(R_kk) of an already factored matrix (stand-alone lrsolve entry)
+int lu_invert_diag(cudaStream_t st, LuWork &w, cplx *a, size_t lda);
+void lu_profile(LuWork &w, bool on);
+int lu_trailing_stats(const LuWork &w, double *seconds, double *flops, double *launches);
+// unpivoted LU in place on device matrix a (n x n, lda); keeps block inverses in w
+int lu_factor(cudaStream_t st, LuWork &w, cplx *a, size_t lda);
+// X (n x nrhs, ldx) <- (LU)^-1 X
+int lu_solve(cudaStream_t st, const LuWork &w, const cplx *a, size_t lda, cplx *x, uint nrhs,
+             size_t ldx);
+
+}  // namespace cnld

@@ -1,0 +1,213 @@
+// Blocked UNPIVOTED complex-FP64 LU and multi-RHS triangular solves.
+// Replaces lrdecomp_amatrix / lrsolve_amatrix_avector
+// (include/factorizations.h:173-182, :233; call sites
+// cnld/compressed_formats.py:247-252, :259-262).  Like the reference there is
+// no pivoting: A = L R with unit-lower L, in place; a zero / non-finite pivot is
+// reported through `info` (index + 1) exactly as lrdecomp_amatrix's return value.
+//
+// Right-looking, block size 64.  The diagonal block is factored by one CTA in
+// shared memory, which also forms inv(L_kk) and inv(R_kk); both panel updates
+// and all triangular solves then become DMMA ZGEMMs (zgemm.cu), as does the
+// rank-64 trailing update that carries ~99% of the flops.
+#include "common.cuh"
+
+namespace cnld {
+namespace {
+constexpr int NB = 64;
+constexpr int LD = NB + 1;  // odd leading dimension (in 16-byte elements): conflict free both ways
+constexpr int DIAG_THREADS = 512;
+constexpr int DIAG_SMEM = 2 * NB * LD * (int)sizeof(cplx);
+
+// FACTOR=true : factor diagonal block `b0` (grid = 1).
+// FACTOR=false: the matrix already holds L\R; only form the block inverses, one CTA per
+//               diagonal block (grid = nblk) -- used by the stand-alone lrsolve entry.
+template <bool FACTOR>
+__global__ void __launch_bounds__(DIAG_THREADS, 1)
+k_diag(cplx *a0, size_t lda, uint n, uint b0, cplx *linv0, cplx *uinv0, uint *info) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx *S = reinterpret_cast<cplx *>(smem_raw);
+  cplx *X = S + NB * LD;
+  const int tid = threadIdx.x;
+  const uint b = b0 + blockIdx.x, base = b * NB;
+  const uint nbk = (n - base < (uint)NB) ? n - base : NB;
+  cplx *a = a0 + (size_t)base * lda + base;
+  cplx *linv = linv0 + (size_t)b * NB * NB, *uinv = uinv0 + (size_t)b * NB * NB;
+  for (uint idx = tid; idx < nbk * nbk; idx += DIAG_THREADS) {
+    uint i = idx % nbk, j = idx / nbk;
+    S[j * LD + i] = a[(size_t)j * lda + i];
+  }
+  __syncthreads();
+  for (uint k = 0; FACTOR && k < nbk; k++) {
+    cplx piv = S[k * LD + k];
+    double mag = piv.x * piv.x + piv.y * piv.y;
+    if (tid == 0 && !(mag > 0.0 && mag < 1.79e308)) atomicCAS(info, 0u, base + k + 1);
+    cplx pinv = cinv(piv);
+    for (uint i = k + 1 + tid; i < nbk; i += DIAG_THREADS) S[k * LD + i] = cmul(S[k * LD + i], pinv);
+    __syncthreads();
+    uint m = nbk - k - 1;
+    for (uint idx = tid; idx < m * m; idx += DIAG_THREADS) {
+      uint i = k + 1 + idx % m, j = k + 1 + idx / m;
+      cfms(S[j * LD + i], S[k * LD + i], S[j * LD + k]);
+    }
+    __syncthreads();
+  }
+  if (FACTOR)
+    for (uint idx = tid; idx < nbk * nbk; idx += DIAG_THREADS) {
+      uint i = idx % nbk, j = idx / nbk;
+      a[(size_t)j * lda + i] = S[j * LD + i];
+    }
+  // X = inv(L), L unit lower: forward elimination on the identity
+  for (uint idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
+    uint i = idx % NB, j = idx / NB;
+    X[j * LD + i] = make_double2(i == j ? 1.0 : 0.0, 0.0);
+  }
+  __syncthreads();
+  for (uint k = 0; k + 1 < nbk; k++) {
+    uint m = nbk - k - 1, w = k + 1;
+    for (uint idx = tid; idx < m * w; idx += DIAG_THREADS) {
+      uint i = k + 1 + idx % m, c = idx / m;
+      cfms(X[c * LD + i], S[k * LD + i], X[c * LD + k]);
+    }
+    __syncthreads();
+  }
+  for (uint idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
+    uint i = idx % NB, j = idx / NB;
+    linv[j * NB + i] = X[j * LD + i];
+  }
+  __syncthreads();
+  // X = inv(R), R upper: backward elimination on the identity
+  for (uint idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
+    uint i = idx % NB, j = idx / NB;
+    X[j * LD + i] = make_double2(i == j ? 1.0 : 0.0, 0.0);
+  }
+  __syncthreads();
+  for (uint kk = nbk; kk-- > 0;) {
+    cplx pinv = cinv(S[kk * LD + kk]);
+    for (uint c = kk + tid; c < nbk; c += DIAG_THREADS) X[c * LD + kk] = cmul(X[c * LD + kk], pinv);
+    __syncthreads();
+    uint w = nbk - kk;  // columns kk..nbk-1
+    for (uint idx = tid; idx < kk * w; idx += DIAG_THREADS) {
+      uint i = idx % kk, c = kk + idx / kk;
+      cfms(X[c * LD + i], S[kk * LD + i], X[c * LD + kk]);
+    }
+    __syncthreads();
+  }
+  for (uint idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
+    uint i = idx % NB, j = idx / NB;
+    uinv[j * NB + i] = X[j * LD + i];
+  }
+}
+}  // namespace
+
+int lu_work_alloc(LuWork &w, uint n) {
+  w.n = n;
+  w.nb = NB;
+  w.nblk = (n + NB - 1) / NB;
+  CNLD_CK(cudaMalloc(&w.linv, sizeof(cplx) * (size_t)w.nblk * NB * NB));
+  CNLD_CK(cudaMalloc(&w.uinv, sizeof(cplx) * (size_t)w.nblk * NB * NB));
+  CNLD_CK(cudaMalloc(&w.info, sizeof(uint)));
+  return 0;
+}
+
+void lu_work_free(LuWork &w) {
+  cudaFree(w.linv);
+  cudaFree(w.uinv);
+  cudaFree(w.info);
+  cudaFree(w.panel);
+  for (auto &e : w.pe) cudaEventDestroy(e);
+  w = LuWork();
+}
+
+static int diag_attr() {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CNLD_CK(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    CNLD_CK(cudaFuncSetAttribute(k_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+    CNLD_CK(cudaFuncSetAttribute(k_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+    attr_set[dev & 63] = true;
+  }
+  return 0;
+}
+
+int lu_invert_diag(cudaStream_t st, LuWork &w, cplx *a, size_t lda) {
+  if (diag_attr()) return -1;
+  k_diag<false><<<w.nblk, DIAG_THREADS, DIAG_SMEM, st>>>(a, lda, w.n, 0, w.linv, w.uinv, w.info);
+  CNLD_CK_LAUNCH();
+  return 0;
+}
+
+void lu_profile(LuWork &w, bool on) {
+  if (on && w.pe.empty()) {
+    w.pe.resize(2 * (size_t)w.nblk);
+    for (auto &e : w.pe) cudaEventCreate(&e);
+  }
+  w.prof = on;
+}
+
+// seconds and flops spent in the trailing-update ZGEMMs of the last lu_factor on this work
+int lu_trailing_stats(const LuWork &w, double *seconds, double *flops, double *launches) {
+  *seconds = *flops = *launches = 0.0;
+  if (!w.prof) return 0;
+  for (uint b = 0; b + 1 < w.nblk; b++) {
+    uint o = b * NB;
+    double rem = (double)w.n - o - NB;
+    if (rem <= 0) break;
+    float ms = 0.f;
+    CNLD_CK(cudaEventElapsedTime(&ms, w.pe[2 * b], w.pe[2 * b + 1]));
+    *seconds += ms * 1e-3;
+    *flops += 8.0 * rem * rem * NB;
+    *launches += 1.0;
+  }
+  return 0;
+}
+
+int lu_factor(cudaStream_t st, LuWork &w, cplx *a, size_t lda) {
+  if (diag_attr()) return -1;
+  const uint n = w.n;
+  CNLD_CK(cudaMemsetAsync(w.info, 0, sizeof(uint), st));
+  for (uint b = 0, o = 0; o < n; b++, o += NB) {
+    uint nbk = (n - o < (uint)NB) ? n - o : NB;
+    uint rem = n - o - nbk;
+    cplx *akk = a + (size_t)o * lda + o;
+    cplx *li = w.linv + (size_t)b * NB * NB, *ui = w.uinv + (size_t)b * NB * NB;
+    k_diag<true><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(a, lda, n, b, w.linv, w.uinv, w.info);
+    CNLD_CK_LAUNCH();
+    if (rem) {
+      cplx *a21 = akk + nbk, *a12 = akk + (size_t)nbk * lda, *a22 = a12 + nbk;
+      // in place: one CTA tile (128x64) spans the whole 64-wide panel it re-reads
+      if (zgemm(st, rem, nbk, nbk, 1.0, a21, lda, ui, NB, 0.0, a21, lda)) return -1;
+      if (zgemm(st, nbk, rem, nbk, 1.0, li, NB, a12, lda, 0.0, a12, lda)) return -1;
+      if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * b], st));
+      if (zgemm(st, rem, rem, nbk, -1.0, a21, lda, a12, lda, 1.0, a22, lda)) return -1;
+      if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * b + 1], st));
+    }
+  }
+  return 0;
+}
+
+int lu_solve(cudaStream_t st, const LuWork &w, const cplx *a, size_t lda, cplx *x, uint nrhs,
+             size_t ldx) {
+  const uint n = w.n;
+  for (uint b = 0, o = 0; o < n; b++, o += NB) {  // L y = b
+    uint nbk = (n - o < (uint)NB) ? n - o : NB;
+    uint rem = n - o - nbk;
+    cplx *xb = x + o;
+    if (zgemm(st, nbk, nrhs, nbk, 1.0, w.linv + (size_t)b * NB * NB, NB, xb, ldx, 0.0, xb, ldx))
+      return -1;
+    if (rem &&
+        zgemm(st, rem, nrhs, nbk, -1.0, a + (size_t)o * lda + o + nbk, lda, xb, ldx, 1.0, xb + nbk, ldx))
+      return -1;
+  }
+  for (uint b = w.nblk; b-- > 0;) {  // R x = y
+    uint o = b * NB;
+    uint nbk = (n - o < (uint)NB) ? n - o : NB;
+    cplx *xb = x + o;
+    if (zgemm(st, nbk, nrhs, nbk, 1.0, w.uinv + (size_t)b * NB * NB, NB, xb, ldx, 0.0, xb, ldx))
+      return -1;
+    if (o && zgemm(st, o, nrhs, nbk, -1.0, a + (size_t)o * lda, lda, xb, ldx, 1.0, x, ldx)) return -1;
+  }
+  return 0;
+}
+
+}  // namespace cnld

@@ -1,0 +1,166 @@
+// Complex-FP64 GEMM on the FP64 tensor pipe (DMMA.8x8x4 via mma.sync.m8n8k4.f64;
+// tcgen05 has no f64 kind, and every larger f64 mma shape lowers to DMMA.8x8x4 on
+// sm_100a -- checked with cuobjdump).  This is the one dense contraction of the
+// hot path: the trailing update of the blocked unpivoted LU
+// (lrdecomp_amatrix, include/factorizations.h:173-182), plus the triangular
+// panel/solve products (lrsolve_amatrix_avector, :233).
+//
+// C(MxN) = beta*C + alpha*A(MxK)*B(KxN), column-major interleaved complex.
+// Complex product as 4 real DMMAs per 8x8x4 tile:
+//   Cre += Are*Bre + (-Aim)*Bim ;  Cim += Are*Bim + Aim*Bre
+// CTA tile 128x64, 8 warps (4x2), warp tile 32x32 (128 accumulator registers),
+// K chunks of 8 through a 4-stage cp.async ring.  Shared-memory leading dimensions
+// are chosen so the 16-byte fragment loads are bank-conflict free:
+//   A tile [k][i], ld = 130 (== 2 mod 8);  B tile [j][k], ld = 12 (== 4 mod 8).
+#include "common.cuh"
+
+namespace cnld {
+
+namespace {
+constexpr int BM = 128, BN = 64, BK = 8, STAGES = 4, NT = 256;
+constexpr int AS_LD = BM + 2;
+constexpr int BS_LD = BK + 4;
+constexpr int A_STAGE = BK * AS_LD;  // cplx elements
+constexpr int B_STAGE = BN * BS_LD;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(cplx);
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(NT, 1)
+zgemm_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A, size_t lda,
+             const cplx *__restrict__ B, size_t ldb, double beta, cplx *C, size_t ldc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx *As = reinterpret_cast<cplx *>(smem_raw);
+  cplx *Bs = As + STAGES * A_STAGE;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;
+  const uint m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int nk = (K + BK - 1) / BK;
+
+  auto load_stage = [&](int kc, int stage) {
+    const uint k0 = kc * BK;
+    cplx *as = As + stage * A_STAGE;
+    cplx *bs = Bs + stage * B_STAGE;
+    const int i = tid & 127;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      int kk = (tid >> 7) + 2 * r;
+      bool ok = (m0 + i < M) && (k0 + kk < K);
+      const cplx *src = ok ? (A + (size_t)(k0 + kk) * lda + (m0 + i)) : A;
+      cp_async16(as + kk * AS_LD + i, src, ok);
+    }
+    const int kb = tid & 7;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      int j = (tid >> 3) + 32 * r;
+      bool ok = (n0 + j < N) && (k0 + kb < K);
+      const cplx *src = ok ? (B + (size_t)(n0 + j) * ldb + (k0 + kb)) : B;
+      cp_async16(bs + j * BS_LD + kb, src, ok);
+    }
+  };
+
+  double cre[4][4][2], cim[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) cre[a][b][0] = cre[a][b][1] = cim[a][b][0] = cim[a][b][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < nk) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  const int fr = lane >> 2, fc = lane & 3;
+  for (int kc = 0; kc < nk; kc++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      int nx = kc + STAGES - 1;
+      if (nx < nk) load_stage(nx, nx % STAGES);
+      cp_async_commit();
+    }
+    const cplx *as = As + (kc % STAGES) * A_STAGE + wm * 32 + fr;
+    const cplx *bs = Bs + (kc % STAGES) * B_STAGE + (wn * 32 + fr) * BS_LD + fc;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ks++) {
+      double are[4], aim[4], nai[4], bre[4], bim[4];
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++) {
+        cplx v = as[(ks * 4 + fc) * AS_LD + mi * 8];
+        are[mi] = v.x; aim[mi] = v.y; nai[mi] = -v.y;
+      }
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) {
+        cplx v = bs[ni * 8 * BS_LD + ks * 4];
+        bre[ni] = v.x; bim[ni] = v.y;
+      }
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+          dmma(cre[mi][ni][0], cre[mi][ni][1], are[mi], bre[ni]);
+          dmma(cim[mi][ni][0], cim[mi][ni][1], are[mi], bim[ni]);
+          dmma(cre[mi][ni][0], cre[mi][ni][1], nai[mi], bim[ni]);
+          dmma(cim[mi][ni][0], cim[mi][ni][1], aim[mi], bre[ni]);
+        }
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: lane holds C[fr][2*fc + e] of each 8x8 block
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++) {
+    uint row = m0 + wm * 32 + mi * 8 + fr;
+    if (row >= M) continue;
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        uint col = n0 + wn * 32 + ni * 8 + fc * 2 + e;
+        if (col >= N) continue;
+        cplx *p = C + (size_t)col * ldc + row;
+        cplx r = make_double2(alpha * cre[mi][ni][e], alpha * cim[mi][ni][e]);
+        if (beta != 0.0) {
+          cplx o = *p;
+          r.x += o.x; r.y += o.y;
+        }
+        *p = r;
+      }
+  }
+}
+}  // namespace
+
+int zgemm(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
+          const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc) {
+  if (M == 0 || N == 0) return 0;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CNLD_CK(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    CNLD_CK(cudaFuncSetAttribute(zgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 SMEM_BYTES));
+    attr_set[dev & 63] = true;
+  }
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
+  zgemm_kernel<<<grid, NT, SMEM_BYTES, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  CNLD_CK_LAUNCH();
+  return 0;
+}
+
+}  // namespace cnld

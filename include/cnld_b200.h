@@ -1,0 +1,158 @@
+/* ============================================================================
+ * cnld_b200.h -- C ABI of libcnld_b200.so
+ *
+ * B200-native (sm_100a) implementation of cnl-dyna's frequency-response hot
+ * path: assemble Z(k) (Galerkin single-layer Helmholtz, linear hats) -> form
+ * G = K - w^2 M - j w B - 2 rho w^2 Z -> unpivoted LU -> solve all source
+ * patches -> conj / boundary mask / patch average -> field pressure.
+ *
+ * Two groups of entry points:
+ *   (A) cnld_b200_*  : batched, device-resident entry points for a frequency
+ *       shard (not in the reference; this is what the sweep driver calls).
+ *   (B) H2Lib-named  : the symbols cnl-dyna's Cython layer binds
+ *       (cnld/h2lib/_*.pxd), same prototypes, host-visible struct prefixes
+ *       identical to the ones Cython dereferences.  Declared in
+ *       cnld_b200_h2lib.h.
+ *
+ * Conventions (both groups): real = double, field = C99 double _Complex
+ * (two doubles re,im), uint = unsigned int (cnld/h2lib/_basic.pxd:3-6);
+ * dense matrices column-major with leading dimension ld (include/amatrix.h:42-48);
+ * all pointers are HOST pointers owned by the caller; the library owns device
+ * memory until *_destroy.  Functions return 0 on success, non-zero on error
+ * (message through cnld_b200_last_error()); no exceptions cross the ABI.
+ * There is NO CPU fallback: without a CUDA device every compute entry fails.
+ * ========================================================================== */
+#ifndef CNLD_B200_H
+#define CNLD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__cplusplus)
+typedef struct { double re, im; } cnld_field; /* layout-identical to double _Complex */
+#else
+typedef double _Complex cnld_field;
+#endif
+typedef unsigned int cnld_uint;
+
+typedef struct cnld_ctx cnld_ctx; /* opaque: mesh, quadrature tables, FEM data, device workspaces */
+
+/* ---- library ---------------------------------------------------------- */
+const char *cnld_b200_last_error(void);
+const char *cnld_b200_version(void);
+int cnld_b200_device_count(void);
+/* number of kernel launches issued by this library since load (bench: gpu_launches) */
+unsigned long long cnld_b200_launch_count(void);
+
+/* ---- context: mesh + quadrature (frequency independent) ---------------
+ * Replaces: Mesh.from_abstract -> Surface3d + prepare_surface3d
+ *           (cnld/mesh.py:182-222,148; include/surface3d.h:45-71,101) and
+ *           new_slp_helmholtz_bem3d(k, gr, q_reg, q_sing, LINEAR, LINEAR) ->
+ *           build_singquad2d (include/helmholtzbem3d.h:81-83, singquad2d.h:179;
+ *           call sites cnld/compressed_formats.py:629,675).
+ * x[nv][3] vertex coordinates, t[nt][3] triangle vertex ids. */
+cnld_ctx *cnld_b200_create(int device, cnld_uint nv, cnld_uint nt, const double *x,
+                           const cnld_uint *t, cnld_uint q_reg, cnld_uint q_sing);
+void cnld_b200_destroy(cnld_ctx *ctx);
+int cnld_b200_set_streams(cnld_ctx *ctx, int nstreams); /* frequencies in flight, default 2 */
+
+/* Gram determinants g[nt] (= 2*area) and normals n[nt][3] as computed on device
+ * (prepare_surface3d, include/surface3d.h:101). Either pointer may be NULL. */
+int cnld_b200_get_geometry(cnld_ctx *ctx, double *g, double *n);
+
+/* ---- stage entry points (each mirrors one reference call) ----------------- */
+
+/* assemble_bem3d_amatrix(bem, Z) (include/bem3d.h:3028; compressed_formats.py:634):
+ * dense nv x nv Galerkin matrix of the Helmholtz SLP for wavenumber k = k_re + i k_im,
+ * kernel exp(i k r)/(4 pi r).  Z is a host buffer, column-major, ld >= nv. */
+int cnld_b200_assemble_slp_ll(cnld_ctx *ctx, double k_re, double k_im, cnld_field *Z,
+                              cnld_uint ld);
+
+/* bem->nearfield(ridx, cidx, bem, false, N) (include/bem3d.h:370-385): the
+ * rows x cols sub-block of Z for the given vertex index sets. */
+int cnld_b200_nearfield_slp_ll(cnld_ctx *ctx, double k_re, double k_im, const cnld_uint *ridx,
+                               cnld_uint rows, const cnld_uint *cidx, cnld_uint cols,
+                               cnld_field *N, cnld_uint ld);
+
+/* lrdecomp_amatrix(a) (include/factorizations.h:173-182; compressed_formats.py:249):
+ * in-place UNPIVOTED LU, L unit lower.  *info = 0 ok, k+1 if pivot k is zero/non-finite. */
+int cnld_b200_lrdecomp(int device, cnld_uint n, cnld_field *a, cnld_uint ld, cnld_uint *info);
+
+/* lrsolve_amatrix_avector(false, LU, x) (include/factorizations.h:233;
+ * compressed_formats.py:259-262) for nrhs right-hand sides at once. */
+int cnld_b200_lrsolve(int device, cnld_uint n, const cnld_field *lu, cnld_uint ld,
+                      cnld_field *x, cnld_uint nrhs, cnld_uint ldx);
+
+/* addmul_amatrix(alpha, false, A, false, B, C) (cnld/h2lib/_amatrix.pxd:34) restricted to
+ * alpha = +-1 and C = beta*C + alpha*A*B with beta in {0,1}: the FP64 tensor-core ZGEMM the
+ * LU is built from, exposed so it can be parity-tested on its own. */
+int cnld_b200_zgemm(int device, cnld_uint m, cnld_uint n, cnld_uint k, double alpha,
+                    const cnld_field *A, cnld_uint lda, const cnld_field *B, cnld_uint ldb,
+                    double beta, cnld_field *C, cnld_uint ldc);
+
+/* ---- frequency sweep (the metric's unit of work) -----------------------
+ * FEM operators of the whole array as ONE CSR pattern with three value arrays
+ * (fem.array_mbk_spmatrix, cnld/fem.py:1289-1315: block = -(w^2) M - 1j w B + K). */
+int cnld_b200_set_mbk(cnld_ctx *ctx, const int64_t *indptr, const cnld_uint *indices,
+                      const double *K, const double *M, const double *B);
+/* Patch loads F[nv x P] and patch averaging AVG[nv x P] in CSC
+ * (fem.array_f_spmatrix / array_avg_spmatrix, cnld/fem.py:1255-1286) and the
+ * boundary-node mask ob[nv] (mesh.on_boundary, cnld/mesh.py:262-266). */
+int cnld_b200_set_loads(cnld_ctx *ctx, cnld_uint npatch, const int64_t *f_indptr,
+                        const cnld_uint *f_idx, const double *f_val, const int64_t *a_indptr,
+                        const cnld_uint *a_idx, const double *a_val, const uint8_t *ob);
+
+/* generate_db.process for nf frequencies (cnld/scripts/generate_db.py:30-130):
+ *   k = 2 pi f / c;  G = MBK(f) + (-(2 pi f)^2 * 2 rho) Z(k);  LU;  for every
+ *   source patch s: x = conj(LU \ F[:,s]); x[ob] = 0; x_patch = AVG^T x.
+ * x_patch[nf][P(src)][P(dst)], x_node[nf][P(src)][nv] (nullable), t_freq[nf]
+ * device seconds per frequency (nullable). */
+int cnld_b200_sweep_run(cnld_ctx *ctx, const double *freqs, cnld_uint nf, double c, double rho,
+                        cnld_field *x_patch, cnld_field *x_node, double *t_freq);
+
+/* Same work, inputs/outputs stay in HBM (device-resident timing for the bench's
+ * `value`); results are kept in an internal device buffer and can be fetched with
+ * cnld_b200_sweep_fetch afterwards. */
+int cnld_b200_sweep_run_device(cnld_ctx *ctx, const double *freqs, cnld_uint nf, double c,
+                               double rho);
+int cnld_b200_sweep_fetch(cnld_ctx *ctx, cnld_uint nf, cnld_field *x_patch, cnld_field *x_node);
+
+/* per-stage device time (seconds, CUDA events) accumulated over the last sweep_run*:
+ * out[0]=assemble, [1]=factor, [2]=solve+epilogue, [3]=launch count */
+int cnld_b200_sweep_stage_times(cnld_ctx *ctx, double *out);
+
+/* Dominant-kernel timing for the roofline: when profiling is on, every trailing-update
+ * ZGEMM launch of the LU is bracketed by CUDA events on its own stream.
+ * out[0] = algorithmic flops (8 m n k summed), out[1] = seconds (sum of launch durations),
+ * out[2] = number of launches, all over the last sweep_run*. */
+int cnld_b200_set_profile(cnld_ctx *ctx, int on);
+int cnld_b200_sweep_kernel_stats(cnld_ctx *ctx, double *out);
+
+/* ---- field pressure ------------------------------------------------------
+ * bem_pressure.mesh_pres_vector (cnld/bem_pressure.pyx:54-88) for nobs points and
+ * one wavenumber: pvec[nobs][nv].  Kernel exp(-j k r)/(4 pi r), 3-point rule,
+ * source z forced to 0, scale -(k c)^2 * 2 rho. */
+int cnld_b200_pres_vector(cnld_ctx *ctx, const double *obs, cnld_uint nobs, double k, double c,
+                          double rho, cnld_field *pvec);
+/* Fused p[ik][isrc][iobs] = pvec(obs, ks[ik]) . disp[ik][isrc][:]  -- the loop of
+ * array_patch_pres_imp_resp (cnld/bem_pressure.pyx:103-112) for all points at once. */
+int cnld_b200_pressure(cnld_ctx *ctx, const double *obs, cnld_uint nobs, const double *ks,
+                       cnld_uint nk, double c, double rho, const cnld_field *disp,
+                       cnld_uint nsrc, cnld_field *p);
+
+/* ---- microbenchmarks used for roofline denominators ----------------------- */
+/* FP64 DMMA ZGEMM C(m x n) -= A(m x k) B(k x n) on device-resident random data;
+ * returns achieved TFLOP/s (8 m n k flop) averaged over reps. */
+int cnld_b200_bench_zgemm(int device, cnld_uint m, cnld_uint n, cnld_uint k, int reps,
+                          double *tflops);
+/* FP64 FMA-pipe peak probe (dependent-free DFMA chains), TFLOP/s */
+int cnld_b200_bench_dfma(int device, int reps, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNLD_B200_H */

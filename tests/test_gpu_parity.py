@@ -1,0 +1,111 @@
+"""GPU parity: the CUDA path (through the C ABI, via cnld._lib) against the CPU oracle on the
+same inputs.  Tolerances: Z entries 1e-10 relative to max|Z| (same quadrature rules, only
+rounding / libm differences); displacements, patch averages and pressure 1e-6 relative l2
+(the north-star tolerance; observed values are far smaller)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300)
+
+
+@pytest.fixture(scope='module')
+def L():
+    from cnld import _lib
+    assert _lib.device_count() > 0, 'no CUDA device: libcnld_b200 has no CPU fallback'
+    return _lib
+
+
+@pytest.mark.parametrize('n,nrhs', [(37, 1), (64, 3), (200, 5), (517, 144)])
+def test_lu_and_solve_vs_oracle(L, po, n, nrhs):
+    rng = np.random.default_rng(n)
+    G = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)) + n * 0.7 * np.eye(n)
+    B = rng.standard_normal((n, nrhs)) + 1j * rng.standard_normal((n, nrhs))
+    LU = L.lrdecomp(G)
+    LUo, st = po.lrdecomp(G)
+    assert st == 0
+    assert np.abs(LU - LUo).max() / np.abs(LUo).max() < 1e-12
+    X = L.lrsolve(LU, B)
+    Xo = np.stack([po.lrsolve(LUo, B[:, j]) for j in range(nrhs)], axis=1)
+    assert _rel(X, Xo) < 1e-12
+    assert _rel(G @ X, B) < 1e-11
+
+
+def test_lu_zero_pivot_raises(L):
+    G = np.eye(70, dtype=np.complex128)
+    G[5, 5] = 0.0
+    with pytest.raises(RuntimeError, match='failed to calculate LU decomposition'):
+        L.lrdecomp(G)
+
+
+@pytest.mark.parametrize('nelem,refn,k', [((1, 1), 3, 2 * np.pi * 1e6 / 1500), ((2, 1), 4, 3.1e4),
+                                          ((1, 1), 5, 0.0), ((2, 1), 3, 2.0e4 + 3.0e3j)])
+def test_assemble_z_vs_oracle(L, po, nelem, refn, k):
+    arr = po.matrix_array(nelem=nelem)
+    am = po.array_mesh(arr, refn)
+    ctx = L.Context(am.vertices, am.triangles)
+    g, nrm = ctx.geometry()
+    assert np.allclose(g, am.g, rtol=1e-14)
+    assert np.allclose(nrm, am.normals, atol=1e-14)
+    Z = ctx.assemble_z(k)
+    Zo = po.assemble_z(am, k)
+    assert np.abs(Z - Zo).max() / np.abs(Zo).max() < 1e-10
+    ctx.close()
+
+
+@pytest.mark.parametrize('q_reg,q_sing', [(1, 2), (3, 3), (4, 5)])
+def test_assemble_z_other_orders(L, po, q_reg, q_sing):
+    am = po.array_mesh(po.matrix_array(nelem=(1, 1)), 3)
+    ctx = L.Context(am.vertices, am.triangles, q_reg=q_reg, q_sing=q_sing)
+    Z = ctx.assemble_z(5.0e4)
+    Zo = po.assemble_z(am, 5.0e4, q_reg, q_sing)
+    assert np.abs(Z - Zo).max() / np.abs(Zo).max() < 1e-10
+    ctx.close()
+
+
+def _setup_sweep(L, po, nelem, refn):
+    from scipy.linalg import block_diag
+    arr = po.matrix_array(nelem=nelem)
+    am = po.array_mesh(arr, refn)
+    blocks = po.array_fem(arr, refn)
+    ctx = L.Context(am.vertices, am.triangles)
+    ctx.set_mbk(block_diag(*[b[0] for b in blocks]), block_diag(*[b[1] for b in blocks]),
+                block_diag(*[b[2] for b in blocks]))
+    ctx.set_loads(block_diag(*[b[3] for b in blocks]), block_diag(*[b[4] for b in blocks]),
+                  am.on_boundary)
+    return arr, am, blocks, ctx
+
+
+@pytest.mark.parametrize('nstreams', [1, 3])
+def test_sweep_vs_oracle(L, po, nstreams):
+    arr, am, blocks, ctx = _setup_sweep(L, po, (2, 1), 4)
+    ctx.set_streams(nstreams)
+    freqs = np.array([0.0, 1e6, 7.3e6, 20e6, 50e6])
+    xp, xn, t = ctx.sweep(freqs)
+    for i, f in enumerate(freqs):
+        Xo, XPo = po.solve_frequency(am, blocks, f)
+        assert _rel(xn[i].T, Xo) < 1e-6, (f, _rel(xn[i].T, Xo))
+        assert _rel(xp[i].T, XPo) < 1e-6
+        assert _rel(xn[i].T, Xo) < 1e-9     # what the same-rule comparison actually achieves
+    ctx.sweep_device(freqs)
+    assert np.array_equal(ctx.sweep_fetch(len(freqs)), xp) or _rel(ctx.sweep_fetch(len(freqs)), xp) < 1e-12
+    ctx.close()
+
+
+def test_pressure_vs_oracle(L, po):
+    arr, am, blocks, ctx = _setup_sweep(L, po, (2, 1), 3)
+    rng = np.random.default_rng(1)
+    obs = np.c_[rng.uniform(-1e-3, 1e-3, 300), rng.uniform(-1e-3, 1e-3, 300), rng.uniform(1e-4, 2.1e-3, 300)]
+    ks = np.array([2 * np.pi * 1e6 / 1500, 2 * np.pi * 17e6 / 1500])
+    for k in ks:
+        assert _rel(ctx.pres_vector(obs[:7], k), po.pres_vector(am, obs[:7], k)) < 1e-12
+    disp = rng.standard_normal((2, 5, am.nvertices)) + 1j * rng.standard_normal((2, 5, am.nvertices))
+    p = ctx.pressure(obs, ks, disp)
+    for ik, k in enumerate(ks):
+        pv = po.pres_vector(am, obs, k)          # [nobs, nv]
+        ref = disp[ik] @ pv.T                    # [nsrc, nobs]   (p_vector.dot(disp))
+        assert _rel(p[ik], ref) < 1e-11
+    ctx.close()
