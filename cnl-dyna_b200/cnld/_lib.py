@@ -161,9 +161,9 @@ class Context:
         return xp
 
     def stage_times(self):
-        out = np.zeros(4)
+        out = np.zeros(5)
         check(lib().cnld_b200_sweep_stage_times(self._h, ptr(out)))
-        return dict(assemble=out[0], factor=out[1], solve=out[2], launches=int(out[3]))
+        return dict(assemble=out[0], factor=out[1], solve=out[2], launches=int(out[3]), device_seconds=out[4])
 
     def set_profile(self, on=True):
         check(lib().cnld_b200_set_profile(self._h, int(on)))

@@ -1,0 +1,166 @@
+"""
+cnld.sweep -- frequency-sweep driver on top of libcnld_b200 (one process per GPU).
+
+What generate_db.process does for ONE frequency in ONE forked process
+(/root/reference/cnld/scripts/generate_db.py:30-130) -- re-mesh, re-assemble FEM, build Z, form
+G, LU, loop over source patches -- is split here into a frequency-independent part done once
+(mesh, quadrature tables, K/M/B, F, AVG, boundary mask -> GPU) and a per-frequency part that
+runs entirely on the device for a whole shard of frequencies.
+
+Multi-GPU: frequencies are independent jobs (generate_db.py:229-242), so they are
+block-distributed over ranks with no collective inside a frequency; rank 0's setup is
+broadcast once and the patch responses are gathered at the end (`run_distributed`).
+"""
+import numpy as np
+
+from . import _lib, fem, mesh
+
+
+class SweepSetup:
+    """Frequency-independent host data of a sweep (plain arrays: cheap to broadcast)."""
+
+    def __init__(self, vertices, triangles, on_boundary, K, M, B, F, AVG, c, rho, q_reg, q_sing):
+        from scipy import sparse as sps
+        self.vertices = np.ascontiguousarray(vertices, dtype=np.float64)
+        self.triangles = np.ascontiguousarray(triangles, dtype=np.uint32)
+        self.on_boundary = np.ascontiguousarray(on_boundary, dtype=np.uint8)
+        self.K, self.M, self.B = (sps.csr_matrix(a) for a in (K, M, B))
+        self.F, self.AVG = sps.csc_matrix(F), sps.csc_matrix(AVG)
+        self.c, self.rho, self.q_reg, self.q_sing = float(c), float(rho), int(q_reg), int(q_sing)
+
+    @classmethod
+    def from_abstract(cls, array, refn, c=1500., rho=1000., q_reg=2, q_sing=4):
+        am = mesh.Mesh.from_abstract(array, refn)
+        K, M, B = fem.array_kmb_spmatrices(array, refn)
+        return cls(np.array(am.vertices), np.array(am.triangles), np.array(am.on_boundary), K, M, B,
+                   fem.array_f_spmatrix(array, refn), fem.array_avg_spmatrix(array, refn), c, rho,
+                   q_reg, q_sing)
+
+    @property
+    def nnodes(self):
+        return len(self.vertices)
+
+    @property
+    def npatch(self):
+        return self.F.shape[1]
+
+    # flat arrays <-> object, for torch.distributed broadcast
+    def pack(self):
+        out = {'vertices': self.vertices, 'triangles': self.triangles, 'on_boundary': self.on_boundary,
+               'scalars': np.array([self.c, self.rho, self.q_reg, self.q_sing, self.nnodes, self.npatch],
+                                   dtype=np.float64)}
+        for name in ('K', 'M', 'B', 'F', 'AVG'):
+            m = getattr(self, name)
+            out[name + '_indptr'] = m.indptr.astype(np.int64)
+            out[name + '_indices'] = m.indices.astype(np.int64)
+            out[name + '_data'] = m.data.astype(np.float64)
+        return out
+
+    @classmethod
+    def unpack(cls, d):
+        from scipy import sparse as sps
+        c, rho, q_reg, q_sing, n, P = d['scalars']
+        n, P = int(n), int(P)
+        mats = {}
+        for name in ('K', 'M', 'B'):
+            mats[name] = sps.csr_matrix((d[name + '_data'], d[name + '_indices'], d[name + '_indptr']), shape=(n, n))
+        for name in ('F', 'AVG'):
+            mats[name] = sps.csc_matrix((d[name + '_data'], d[name + '_indices'], d[name + '_indptr']), shape=(n, P))
+        return cls(d['vertices'], d['triangles'], d['on_boundary'], mats['K'], mats['M'], mats['B'], mats['F'],
+                   mats['AVG'], c, rho, int(q_reg), int(q_sing))
+
+
+class FrequencySweep:
+    """Device-resident sweep on one GPU."""
+
+    def __init__(self, setup, device=0, nstreams=2):
+        self.setup = setup
+        self.ctx = _lib.Context(setup.vertices, setup.triangles, q_reg=setup.q_reg, q_sing=setup.q_sing,
+                                device=device)
+        self.ctx.set_streams(nstreams)
+        self.upload()
+
+    def upload(self):
+        """Host -> device copy of the FEM operators, loads and boundary mask."""
+        s = self.setup
+        self.ctx.set_mbk(s.K, s.M, s.B)
+        self.ctx.set_loads(s.F, s.AVG, s.on_boundary)
+        return self.upload_bytes
+
+    @property
+    def upload_bytes(self):
+        return int(sum(a.nbytes for a in self.ctx._mbk) + sum(a.nbytes for a in self.ctx._loads))
+
+    def run(self, freqs, want_nodes=True):
+        """-> x_patch[nf, P(src), P(dst)], x_node[nf, P(src), N] | None, seconds[nf]."""
+        return self.ctx.sweep(freqs, self.setup.c, self.setup.rho, want_nodes=want_nodes)
+
+    def run_device(self, freqs):
+        self.ctx.sweep_device(freqs, self.setup.c, self.setup.rho)
+
+    def close(self):
+        self.ctx.close()
+
+
+def shard(n, rank, world):
+    """Contiguous block distribution of n jobs: [lo, hi) of `rank` (sizes differ by at most 1)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def broadcast_setup(setup, rank, device=None):
+    """Rank 0's SweepSetup to every rank through torch.distributed (NCCL over NVLink on GPUs,
+    gloo on CPU).  One collective per array, once per sweep."""
+    import torch
+    import torch.distributed as dist
+    dev = device if device is not None else 'cpu'
+    names = ['vertices', 'triangles', 'on_boundary', 'scalars'] + [
+        f'{m}_{p}' for m in ('K', 'M', 'B', 'F', 'AVG') for p in ('indptr', 'indices', 'data')]
+    packed = setup.pack() if rank == 0 else None
+    meta = [[(k, packed[k].shape, str(packed[k].dtype)) for k in names]] if rank == 0 else [None]
+    dist.broadcast_object_list(meta, src=0)
+    out = {}
+    for k, shape, dtype in meta[0]:
+        if rank == 0:
+            t = torch.from_numpy(np.ascontiguousarray(packed[k]).view(np.uint8).reshape(-1).copy()).to(dev)
+        else:
+            nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        out[k] = t.cpu().numpy().view(np.dtype(dtype)).reshape(shape)
+    return SweepSetup.unpack(out)
+
+
+def run_distributed(setup_or_none, freqs, rank, world, device=0, torch_device=None, nstreams=2,
+                    solver=None):
+    """Block-distributed sweep: returns (x_patch[nf, P, P] on rank 0 else None, local seconds).
+    `solver(setup, freqs) -> x_patch[nf_local, P, P]` defaults to the GPU sweep; tests inject a
+    CPU stand-in to exercise the sharding / broadcast / gather logic under gloo."""
+    import torch
+    import torch.distributed as dist
+    freqs = np.asarray(freqs, dtype=np.float64)
+    setup = broadcast_setup(setup_or_none, rank, torch_device) if world > 1 else setup_or_none
+    lo, hi = shard(len(freqs), rank, world)
+    if solver is None:
+        sw = FrequencySweep(setup, device=device, nstreams=nstreams)
+        xp, _, t = sw.run(freqs[lo:hi], want_nodes=False)
+        sw.close()
+    else:
+        xp = solver(setup, freqs[lo:hi])
+        t = np.zeros(hi - lo)
+    if world == 1:
+        return xp, t
+    P = setup.npatch
+    counts = [shard(len(freqs), r, world) for r in range(world)]
+    nmax = max(h - l for l, h in counts)
+    buf = np.zeros((nmax, P, P), dtype=np.complex128)
+    buf[:hi - lo] = xp
+    dev = torch_device if torch_device is not None else 'cpu'
+    mine = torch.from_numpy(buf.view(np.float64)).to(dev)
+    gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, gathered, dst=0)
+    if rank != 0:
+        return None, t
+    parts = [g.cpu().numpy().view(np.complex128)[:h - l] for g, (l, h) in zip(gathered, counts)]
+    return np.concatenate(parts, axis=0), t

@@ -87,3 +87,6 @@ extern "C" int cnld_b200_bench_dfma(int device, int reps, double *tflops) {
   cudaFree(out);
   return 0;
 }
+
+extern "C" int cnld_b200_set_zgemm_variant(int v) { cnld::g_zgemm_variant = v; return 0; }
+extern "C" int cnld_b200_set_lu_outer(int v) { cnld::g_lu_outer = v; return 0; }

@@ -63,7 +63,8 @@ struct cnld_ctx {
   cplx *d_xpatch = nullptr;
   size_t xpatch_cap = 0;
   cplx *d_xnode = nullptr;  // only for run_device with keep_node
-  double stage[4] = {0, 0, 0, 0};
+  double stage[5] = {0, 0, 0, 0, 0};
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   bool profile = false;
   double kstat[3] = {0, 0, 0};  // trailing ZGEMM: flops, seconds, launches (last sweep)
   // pressure scratch
@@ -209,6 +210,10 @@ int sweep_impl(cnld_ctx *c, const double *freqs, uint nf, double cs, double rho,
     c->xpatch_cap = nf;
   }
   for (int s = 0; s < c->nslots; s++) c->slots[s].pending = -1;
+  // whole-sweep device time: begin event gates every slot stream, end event joins them
+  if (!c->ev_begin) { CNLD_CK(cudaEventCreate(&c->ev_begin)); CNLD_CK(cudaEventCreate(&c->ev_end)); }
+  CNLD_CK(cudaEventRecord(c->ev_begin, c->slots[0].st));
+  for (int s = 1; s < c->nslots; s++) CNLD_CK(cudaStreamWaitEvent(c->slots[s].st, c->ev_begin, 0));
   c->kstat[0] = c->kstat[1] = c->kstat[2] = 0.0;
   double acc[3] = {0, 0, 0};
   unsigned long long l0 = g_launches.load();
@@ -239,9 +244,18 @@ int sweep_impl(cnld_ctx *c, const double *freqs, uint nf, double cs, double rho,
     if (x_node) CNLD_CK(cudaEventRecord(S.ev[3], S.st));
     S.pending = i;
   }
+  for (int s = 1; s < c->nslots; s++)
+    if (c->slots[s].pending >= 0) CNLD_CK(cudaStreamWaitEvent(c->slots[0].st, c->slots[s].ev[3], 0));
+  CNLD_CK(cudaEventRecord(c->ev_end, c->slots[0].st));
   for (int s = 0; s < c->nslots; s++) {
     int rc = drain(c->slots[(nf + s) % c->nslots]);
     if (rc) return rc;
+  }
+  CNLD_CK(cudaEventSynchronize(c->ev_end));
+  {
+    float ms = 0.f;
+    CNLD_CK(cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end));
+    c->stage[4] = ms * 1e-3;
   }
   if (!device_only && x_patch)
     CNLD_CK(cudaMemcpy(x_patch, c->d_xpatch, sizeof(cplx) * (size_t)nf * P * P, cudaMemcpyDeviceToHost));
@@ -288,6 +302,7 @@ void cnld_b200_destroy(cnld_ctx *c) {
   cudaFree(c->d_f_indptr); cudaFree(c->d_a_indptr); cudaFree(c->d_f_idx); cudaFree(c->d_a_idx);
   cudaFree(c->d_f_val); cudaFree(c->d_a_val); cudaFree(c->d_ob); cudaFree(c->d_xpatch); cudaFree(c->d_xnode);
   cudaFree(c->d_sp);
+  if (c->ev_begin) { cudaEventDestroy(c->ev_begin); cudaEventDestroy(c->ev_end); }
   bem_free(c->bem);
   delete c;
 }
@@ -445,7 +460,7 @@ int cnld_b200_sweep_fetch(cnld_ctx *c, cnld_uint nf, cnld_field *x_patch, cnld_f
 
 int cnld_b200_sweep_stage_times(cnld_ctx *c, double *out) {
   if (!c) { set_error("null context"); return -1; }
-  for (int i = 0; i < 4; i++) out[i] = c->stage[i];
+  for (int i = 0; i < 5; i++) out[i] = c->stage[i];
   return 0;
 }
 

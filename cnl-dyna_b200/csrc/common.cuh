@@ -63,6 +63,8 @@ __device__ __forceinline__ void cfms(cplx &c, cplx a, cplx b) {
   c.y = fma(-a.y, b.x, c.y);
 }
 
+extern int g_zgemm_variant;
+extern int g_lu_outer;
 // ---- dense kernels (zgemm.cu / lu.cu) --------------------------------------
 // C(MxN) = beta*C + alpha*A(MxK)*B(KxN); alpha in {+1,-1}, beta in {0,1};
 // column-major, interleaved complex.  In-place (C aliasing A or B) is safe only
@@ -71,7 +73,7 @@ int zgemm(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, 
           const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc);
 
 struct LuWork {
-  uint n = 0, nb = 0, nblk = 0;
+  uint n = 0, nb = 0, nblk = 0, nouter = 0, nbo = 0;
   cplx *linv = nullptr;  // [nblk][nb*nb]
   cplx *uinv = nullptr;  // [nblk][nb*nb]
   uint *info = nullptr;  // device flag: 0 ok else first failing pivot + 1

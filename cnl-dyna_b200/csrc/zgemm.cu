@@ -17,12 +17,16 @@
 namespace cnld {
 
 namespace {
-constexpr int BM = 128, BN = 64, BK = 8, STAGES = 4, NT = 256;
-constexpr int AS_LD = BM + 2;
+constexpr int BK = 8;
 constexpr int BS_LD = BK + 4;
-constexpr int A_STAGE = BK * AS_LD;  // cplx elements
-constexpr int B_STAGE = BN * BS_LD;
-constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(cplx);
+template <int WM, int WN, int STAGES_>
+struct Cfg {
+  static constexpr int BM = 32 * WM, BN = 32 * WN, STAGES = STAGES_, NT = 32 * WM * WN;
+  static constexpr int AS_LD = BM + 2;
+  static constexpr int A_STAGE = BK * AS_LD;  // cplx elements
+  static constexpr int B_STAGE = BN * BS_LD;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * (int)sizeof(cplx);
+};
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -40,15 +44,19 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(NT, 1)
+template <class CF, int MINB>
+__global__ void __launch_bounds__(CF::NT, MINB)
 zgemm_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A, size_t lda,
              const cplx *__restrict__ B, size_t ldb, double beta, cplx *C, size_t ldc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx *As = reinterpret_cast<cplx *>(smem_raw);
+  constexpr int BM = CF::BM, BN = CF::BN, STAGES = CF::STAGES, NT = CF::NT, AS_LD = CF::AS_LD,
+                A_STAGE = CF::A_STAGE, B_STAGE = CF::B_STAGE;
+  constexpr int WMC = BM / 32;
   cplx *Bs = As + STAGES * A_STAGE;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp & 3, wn = warp >> 2;
+  const int wm = warp % WMC, wn = warp / WMC;
   const uint m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int nk = (K + BK - 1) / BK;
 
@@ -56,18 +64,18 @@ zgemm_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A, s
     const uint k0 = kc * BK;
     cplx *as = As + stage * A_STAGE;
     cplx *bs = Bs + stage * B_STAGE;
-    const int i = tid & 127;
+    const int i = tid % BM;
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-      int kk = (tid >> 7) + 2 * r;
+    for (int r = 0; r < BM * BK / NT; r++) {
+      int kk = tid / BM + (NT / BM) * r;
       bool ok = (m0 + i < M) && (k0 + kk < K);
       const cplx *src = ok ? (A + (size_t)(k0 + kk) * lda + (m0 + i)) : A;
       cp_async16(as + kk * AS_LD + i, src, ok);
     }
     const int kb = tid & 7;
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
-      int j = (tid >> 3) + 32 * r;
+    for (int r = 0; r < BN * BK / NT; r++) {
+      int j = (tid >> 3) + (NT / 8) * r;
       bool ok = (n0 + j < N) && (k0 + kb < K);
       const cplx *src = ok ? (B + (size_t)(n0 + j) * ldb + (k0 + kb)) : B;
       cp_async16(bs + j * BS_LD + kb, src, ok);
@@ -124,43 +132,58 @@ zgemm_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A, s
   cp_async_wait<0>();
 
   // epilogue: lane holds C[fr][2*fc + e] of each 8x8 block
+  // (all loads of a row-group are issued before its stores: C is not restrict-qualified, so a
+  //  naive load/add/store chain would serialise 32 HBM round trips per thread)
 #pragma unroll
   for (int mi = 0; mi < 4; mi++) {
-    uint row = m0 + wm * 32 + mi * 8 + fr;
-    if (row >= M) continue;
+    const uint row = m0 + wm * 32 + mi * 8 + fr;
+    const bool rok = row < M;
+    cplx old[4][2];
 #pragma unroll
     for (int ni = 0; ni < 4; ni++)
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         uint col = n0 + wn * 32 + ni * 8 + fc * 2 + e;
-        if (col >= N) continue;
-        cplx *p = C + (size_t)col * ldc + row;
-        cplx r = make_double2(alpha * cre[mi][ni][e], alpha * cim[mi][ni][e]);
-        if (beta != 0.0) {
-          cplx o = *p;
-          r.x += o.x; r.y += o.y;
-        }
-        *p = r;
+        old[ni][e] = make_double2(0.0, 0.0);
+        if (beta != 0.0 && rok && col < N) old[ni][e] = __ldcg(C + (size_t)col * ldc + row);
+      }
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        uint col = n0 + wn * 32 + ni * 8 + fc * 2 + e;
+        if (rok && col < N)
+          C[(size_t)col * ldc + row] = make_double2(fma(alpha, cre[mi][ni][e], old[ni][e].x),
+                                                    fma(alpha, cim[mi][ni][e], old[ni][e].y));
       }
   }
 }
 }  // namespace
 
-int zgemm(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
-          const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc) {
-  if (M == 0 || N == 0) return 0;
+int g_zgemm_variant = 1;  // 0: 128x64 tile, 1 CTA/SM;  1: 64x64 tile, 2 CTAs/SM
+
+template <class CF, int MINB>
+static int launch(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
+                  const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc) {
   static bool attr_set[64] = {false};
   int dev = 0;
   CNLD_CK(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    CNLD_CK(cudaFuncSetAttribute(zgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 SMEM_BYTES));
+    CNLD_CK(cudaFuncSetAttribute(zgemm_kernel<CF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 CF::SMEM_BYTES));
     attr_set[dev & 63] = true;
   }
-  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-  zgemm_kernel<<<grid, NT, SMEM_BYTES, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  dim3 grid((M + CF::BM - 1) / CF::BM, (N + CF::BN - 1) / CF::BN);
+  zgemm_kernel<CF, MINB><<<grid, CF::NT, CF::SMEM_BYTES, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
   CNLD_CK_LAUNCH();
   return 0;
+}
+
+int zgemm(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
+          const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc) {
+  if (M == 0 || N == 0) return 0;
+  if (g_zgemm_variant == 0) return launch<Cfg<4, 2, 4>, 1>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  return launch<Cfg<2, 2, 4>, 2>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
 }
 
 }  // namespace cnld

@@ -122,7 +122,9 @@ int cnld_b200_sweep_run_device(cnld_ctx *ctx, const double *freqs, cnld_uint nf,
 int cnld_b200_sweep_fetch(cnld_ctx *ctx, cnld_uint nf, cnld_field *x_patch, cnld_field *x_node);
 
 /* per-stage device time (seconds, CUDA events) accumulated over the last sweep_run*:
- * out[0]=assemble, [1]=factor, [2]=solve+epilogue, [3]=launch count */
+ * out[0]=assemble, [1]=factor, [2]=solve+epilogue (each summed over frequencies; they overlap
+ * when several streams are in flight), [3]=kernel launches, [4]=device seconds of the whole
+ * sweep (begin/end events joined across all streams).  out must hold 5 doubles. */
 int cnld_b200_sweep_stage_times(cnld_ctx *ctx, double *out);
 
 /* Dominant-kernel timing for the roofline: when profiling is on, every trailing-update

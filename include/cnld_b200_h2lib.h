@@ -1,0 +1,174 @@
+/* ============================================================================
+ * cnld_b200_h2lib.h -- the H2Lib-named part of libcnld_b200.so's C ABI.
+ *
+ * These are the symbols cnl-dyna's Cython layer binds (`cdef extern` blocks in
+ * /root/reference/cnld/h2lib/_*.pxd), with identical prototypes, so that
+ * cnld/h2lib/*.pyx can be re-pointed at libcnld_b200.so instead of libh2.a
+ * (setup.py:15-16).  Struct members that Cython (or Python through numpy views)
+ * dereferences keep H2Lib's names, types and order; private members follow them.
+ * All `a`, `v`, `x`, ... buffers are HOST memory (numpy views alias them,
+ * cnld/h2lib/amatrix.pyx:34-37); the arithmetic entry points move the data
+ * to the GPU, run the sm_100a kernels and copy the result back.  For a whole
+ * frequency sweep use the device-resident entry points in cnld_b200.h instead.
+ *
+ * real = double, field = double _Complex, uint = unsigned (settings.h:62,89,163).
+ * ========================================================================== */
+#ifndef CNLD_B200_H2LIB_H
+#define CNLD_B200_H2LIB_H
+
+#include <stdbool.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+typedef struct { double re, im; } field;
+#else
+typedef double _Complex field;
+#endif
+typedef double real;
+typedef unsigned int uint;
+typedef field *pfield;
+typedef real *preal;
+
+/* ---- basic (cnld/h2lib/_basic.pxd:20-25; include/basic.h) ------------------ */
+void init_h2lib(int *argc, char ***argv);
+void uninit_h2lib(void);
+void freemem(void *ptr);
+
+/* ---- avector (cnld/h2lib/_avector.pxd:8-23; include/avector.h:39-48) ------- */
+typedef struct _avector {
+  field *v;
+  uint dim;
+  void *owner;
+} avector, *pavector;
+typedef const avector *pcavector;
+pavector new_avector(uint dim);
+pavector new_zero_avector(uint dim);
+void del_avector(pavector v);
+void clear_avector(pavector v);
+void copy_avector(pcavector v, pavector w);
+void random_avector(pavector v);
+
+/* ---- amatrix (cnld/h2lib/_amatrix.pxd:8-34; include/amatrix.h:42-57) ------- */
+typedef struct _amatrix {
+  field *a;   /* column-major, a[i + j*ld] */
+  uint ld;
+  uint rows;
+  uint cols;
+  void *owner;
+} amatrix, *pamatrix;
+typedef const amatrix *pcamatrix;
+pamatrix new_amatrix(uint rows, uint cols);
+pamatrix new_zero_amatrix(uint rows, uint cols);
+void del_amatrix(pamatrix a);
+pamatrix clone_amatrix(pcamatrix src);
+void scale_amatrix(field alpha, pamatrix a);
+void conjugate_amatrix(pamatrix a);
+void addeval_amatrix_avector(field alpha, pcamatrix a, pcavector src, pavector trg);
+void add_amatrix(field alpha, bool atrans, pcamatrix a, pamatrix b);
+size_t getsize_amatrix(pcamatrix a);
+void addmul_amatrix(field alpha, bool atrans, pcamatrix a, bool btrans, pcamatrix b, pamatrix c);
+
+/* ---- sparsematrix (cnld/h2lib/_sparsematrix.pxd:12-30; sparsematrix.h:41-57) */
+typedef struct _sparsematrix {
+  uint rows;
+  uint cols;
+  uint nz;
+  uint *row;    /* CRS row starts, rows+1 entries */
+  uint *col;
+  pfield coeff;
+} sparsematrix, *psparsematrix;
+typedef const sparsematrix *pcsparsematrix;
+psparsematrix new_raw_sparsematrix(uint rows, uint cols, uint nz);
+psparsematrix new_identity_sparsematrix(uint rows, uint cols);
+void del_sparsematrix(psparsematrix a);
+field addentry_sparsematrix(psparsematrix a, uint row, uint col, field x);
+void setentry_sparsematrix(psparsematrix a, uint row, uint col, field x);
+size_t getsize_sparsematrix(pcsparsematrix a);
+void sort_sparsematrix(psparsematrix a);
+void clear_sparsematrix(psparsematrix a);
+void add_sparsematrix_amatrix(field alpha, bool atrans, pcsparsematrix a, pamatrix b);
+void addeval_sparsematrix_avector(field alpha, pcsparsematrix a, pcavector x, pavector y);
+
+/* ---- surface3d (cnld/h2lib/_surface3d.pxd:9-34; include/surface3d.h:45-71) -- */
+typedef struct _surface3d {
+  uint vertices;
+  uint edges;
+  uint triangles;
+  real (*x)[3];
+  uint (*e)[2];
+  uint (*t)[3];
+  uint (*s)[3];   /* s[i][j] lies opposite t[i][j] */
+  real (*n)[3];
+  preal g;        /* Gram determinant = 2*area */
+  real hmin;
+  real hmax;
+} surface3d, *psurface3d;
+typedef const surface3d *pcsurface3d;
+psurface3d new_surface3d(uint vertices, uint edges, uint triangles);
+void del_surface3d(psurface3d gr);
+void prepare_surface3d(psurface3d gr);
+psurface3d merge_surface3d(pcsurface3d gr1, pcsurface3d gr2);
+psurface3d refine_red_surface3d(psurface3d gr);
+void translate_surface3d(psurface3d gr, real *t);
+uint check_surface3d(pcsurface3d gr);
+bool isclosed_surface3d(pcsurface3d gr);
+bool isoriented_surface3d(pcsurface3d gr);
+
+/* ---- macrosurface3d (_macrosurface3d.pxd:8-26; macrosurface3d.h:48-101,187-199) */
+typedef struct _macrosurface3d {
+  uint vertices;
+  uint edges;
+  uint triangles;
+  real (*x)[3];
+  uint (*e)[2];
+  uint (*t)[3];
+  uint (*s)[3];
+  void (*phi)(uint i, real xr1, real xr2, void *phidata, real xt[3]);
+  void *phidata;
+} macrosurface3d, *pmacrosurface3d;
+typedef const macrosurface3d *pcmacrosurface3d;
+pmacrosurface3d new_macrosurface3d(uint vertices, uint edges, uint triangles);
+void del_macrosurface3d(pmacrosurface3d mg);
+psurface3d build_from_macrosurface3d_surface3d(pcmacrosurface3d mg, uint split);
+pmacrosurface3d new_sphere_macrosurface3d(void);
+/* the parametrizations cnl-dyna implements in Cython (macrosurface3d.pyx:83-172),
+ * provided natively so a ctypes host does not need callbacks */
+void cnld_b200_phi_affine(uint i, real xr1, real xr2, void *phidata, real xt[3]);
+void cnld_b200_phi_circle(uint i, real xr1, real xr2, void *phidata, real xt[3]);
+void cnld_b200_phi_sphere(uint i, real xr1, real xr2, void *phidata, real xt[3]);
+
+/* ---- bem3d / helmholtzbem3d (_bem3d.pxd:10-37, _helmholtzbem3d.pxd:11-14) --- */
+typedef enum {
+  BASIS_NONE_BEM3D = 0,
+  BASIS_CONSTANT_BEM3D = 'c',
+  BASIS_LINEAR_BEM3D = 'l'
+} basisfunctionbem3d;
+typedef struct _bem3d {
+  pcsurface3d gr;
+  void *sq;                       /* quadrature tables (device + host), private */
+  basisfunctionbem3d row_basis;
+  basisfunctionbem3d col_basis;
+  real *mass;
+  field alpha;
+  field k;                        /* wavenumber (bem3d.h:338) */
+  field kernel_const;             /* 1/(4 pi) (helmholtzbem3d.h:35) */
+  void *priv;                     /* cnld_ctx of the device-side state */
+  uint q_regular, q_singular;
+} bem3d, *pbem3d;
+typedef const bem3d *pcbem3d;
+pbem3d new_bem3d(pcsurface3d gr, basisfunctionbem3d row_basis, basisfunctionbem3d col_basis);
+void del_bem3d(pbem3d bem);
+pbem3d new_slp_helmholtz_bem3d(field k, pcsurface3d gr, uint q_regular, uint q_singular,
+                               basisfunctionbem3d row_basis, basisfunctionbem3d col_basis);
+void assemble_bem3d_amatrix(pbem3d bem, pamatrix G);
+
+/* ---- factorizations (_factorizations.pxd:13-19; factorizations.h:173-233) --- */
+uint lrdecomp_amatrix(pamatrix a);
+void lrsolve_amatrix_avector(bool atrans, pcamatrix a, pavector x);
+void triangularsolve_amatrix_avector(bool alower, bool aunit, bool atrans, pcamatrix a, pavector x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNLD_B200_H2LIB_H */

@@ -1,5 +1,10 @@
-import sys; sys.path.insert(0,'cnl-dyna_b200')
+import sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'cnl-dyna_b200'))
 from cnld import _lib
+L = _lib.lib()
 print('dfma TF', _lib.bench_dfma(5))
-for (m,n,k) in [(4096,4096,4096),(8192,8192,64),(14736,14736,64),(14736,14736,128),(14736,144,64),(8192,8192,1024)]:
-    print((m,n,k), 'zgemm TF', _lib.bench_zgemm(m,n,k,3))
+for v in (0, 1):
+    L.cnld_b200_set_zgemm_variant(v)
+    for (m, n, k) in [(14736, 14736, 64), (14736, 14736, 128), (14736, 14736, 256), (14736, 14736, 512),
+                      (8192, 8192, 4096), (14736, 144, 64), (14736, 64, 64), (64, 14736, 64)]:
+        print('variant', v, (m, n, k), 'zgemm TF %.2f' % _lib.bench_zgemm(m, n, k, 3))
