@@ -128,6 +128,10 @@ class Context:
         cols = pat.indices
         vals = [np.asarray(a[rows, cols]).ravel().astype(np.float64) for a in (K, M, B)]
         self._mbk = (_c(pat.indptr, np.int64), _c(cols, np.uint32)) + tuple(_c(v, np.float64) for v in vals)
+        self.upload_mbk()
+
+    def upload_mbk(self):
+        """(re-)copy the prepared K/M/B arrays host -> device"""
         check(lib().cnld_b200_set_mbk(self._h, *[ptr(a) for a in self._mbk]))
 
     def set_loads(self, F, AVG, on_boundary):
@@ -139,14 +143,21 @@ class Context:
         self._loads = (_c(F.indptr, np.int64), _c(F.indices, np.uint32), _c(F.data, np.float64),
                        _c(AVG.indptr, np.int64), _c(AVG.indices, np.uint32), _c(AVG.data, np.float64),
                        _c(on_boundary, np.uint8))
+        self.upload_loads()
+
+    def upload_loads(self):
         check(lib().cnld_b200_set_loads(self._h, self.npatch, *[ptr(a) for a in self._loads]))
 
-    def sweep(self, freqs, c=1500., rho=1000., want_nodes=True):
-        """-> x_patch[nf, P(src), P(dst)], x_node[nf, P(src), N] or None, t[nf]."""
+    def sweep(self, freqs, c=1500., rho=1000., want_nodes=True, out_nodes=None):
+        """-> x_patch[nf, P(src), P(dst)], x_node[nf, P(src), N] or None, t[nf].
+        `out_nodes` lets a caller reuse a preallocated [nf, P, N] complex128 buffer."""
         freqs = _c(freqs, np.float64)
         nf, P = len(freqs), self.npatch
-        xp = np.zeros((nf, P, P), dtype=np.complex128)
-        xn = np.zeros((nf, P, self.nv), dtype=np.complex128) if want_nodes else None
+        xp = np.empty((nf, P, P), dtype=np.complex128)
+        xn = None
+        if want_nodes:
+            xn = out_nodes if out_nodes is not None else np.empty((nf, P, self.nv), dtype=np.complex128)
+            assert xn.shape == (nf, P, self.nv) and xn.dtype == np.complex128 and xn.flags.c_contiguous
         t = np.zeros(nf)
         check(lib().cnld_b200_sweep_run(self._h, ptr(freqs), nf, c, rho, ptr(xp), ptr(xn), ptr(t)))
         return xp, xn, t

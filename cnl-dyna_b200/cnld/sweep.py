@@ -78,22 +78,23 @@ class FrequencySweep:
         self.ctx = _lib.Context(setup.vertices, setup.triangles, q_reg=setup.q_reg, q_sing=setup.q_sing,
                                 device=device)
         self.ctx.set_streams(nstreams)
-        self.upload()
-
-    def upload(self):
-        """Host -> device copy of the FEM operators, loads and boundary mask."""
         s = self.setup
         self.ctx.set_mbk(s.K, s.M, s.B)
         self.ctx.set_loads(s.F, s.AVG, s.on_boundary)
+
+    def upload(self):
+        """Host -> device copy of the FEM operators, loads and boundary mask."""
+        self.ctx.upload_mbk()
+        self.ctx.upload_loads()
         return self.upload_bytes
 
     @property
     def upload_bytes(self):
         return int(sum(a.nbytes for a in self.ctx._mbk) + sum(a.nbytes for a in self.ctx._loads))
 
-    def run(self, freqs, want_nodes=True):
+    def run(self, freqs, want_nodes=True, out_nodes=None):
         """-> x_patch[nf, P(src), P(dst)], x_node[nf, P(src), N] | None, seconds[nf]."""
-        return self.ctx.sweep(freqs, self.setup.c, self.setup.rho, want_nodes=want_nodes)
+        return self.ctx.sweep(freqs, self.setup.c, self.setup.rho, want_nodes=want_nodes, out_nodes=out_nodes)
 
     def run_device(self, freqs):
         self.ctx.sweep_device(freqs, self.setup.c, self.setup.rho)

@@ -110,3 +110,51 @@ def test_abstract_json_roundtrip(tmp_path):
     assert '"__name__": "SquareCmutMembrane"' in abstract.dumps(arr)
     m0, m1 = arr.elements[0].membranes[0], arr.elements[3].membranes[0]
     assert m0._memoize() == m1._memoize()        # id / position / patches excluded
+
+
+def test_fir_mirror_matches_reference_golden():
+    from cnld import impulse_response
+    g = np.load(os.path.join(GOLDEN, 'fir.npz'))
+    for interp in (1, 2, 3):
+        for kkr in (1, 0):
+            t, h = impulse_response.fft_to_fir(g['f'], g['s'], interp=interp, use_kkr=bool(kkr), axis=-1)
+            assert np.allclose(t, g[f't_{interp}_{kkr}'], rtol=1e-13, atol=0)
+            assert _rel(h, g[f'h_{interp}_{kkr}']) < 1e-11
+    t, h = impulse_response.fft_to_sir(g['f'], g['s'][0], interp=2, use_kkr=False, axis=1)
+    assert _rel(h, g['sir_h']) < 1e-11
+    # axis handling: frequency on axis 0
+    s0 = np.moveaxis(g['s'], -1, 0)
+    t0, h0 = impulse_response.fft_to_fir(g['f'], s0, interp=2, use_kkr=True, axis=0)
+    assert _rel(np.moveaxis(h0, 0, -1), g['h_2_1']) < 1e-11
+
+
+def test_database_roundtrip(tmp_path):
+    from cnld import database
+    from cnld.scripts.generate_db import Config
+    f = str(tmp_path / 'x.db')
+    cfg = Config()
+    database.create_db(f, **cfg._asdict())
+    assert database.read_metadata(f, as_dict=True)['mesh_refn'] == '11'
+    rng = np.random.default_rng(0)
+    P, N, nf = 3, 7, 4
+    nodes = rng.standard_normal((N, 3))
+    database.append_node(f, node_id=range(N), x=nodes[:, 0], y=nodes[:, 1], z=nodes[:, 2])
+    assert np.allclose(database.read_node(f), nodes.T)
+    freqs = np.array([1e6, 2e6, 3e6, 4e6])
+    xp = rng.standard_normal((nf, P, P)) + 1j * rng.standard_normal((nf, P, P))
+    xn = rng.standard_normal((nf, P, N)) + 1j * rng.standard_normal((nf, P, N))
+    database.create_progress_table(f, nf)
+    database.append_frequency_block(f, freqs[:2], freqs[:2] / 1500, xp[:2], xn[:2], nodes)
+    database.update_progress(f, [1, 2])
+    done, ijob = database.get_progress(f)
+    assert done.tolist() == [True, True, False, False] and ijob == 3
+    database.append_frequency_block(f, freqs[2:], freqs[2:] / 1500, xp[2:], xn[2:], nodes)
+    fr, pp = database.read_patch_to_patch_freq_resp(f)
+    assert np.allclose(fr, freqs) and np.allclose(pp, np.transpose(xp, (1, 2, 0)))
+    fr, pn, nd = database.read_patch_to_node_freq_resp(f)
+    assert np.allclose(pn, np.transpose(xn, (1, 2, 0))) and np.allclose(nd, nodes)
+    # the reference's one-source-patch-at-a-time writer signature still works
+    from itertools import repeat
+    database.append_patch_to_patch_freq_resp(f, frequency=repeat(5e6), wavenumber=repeat(1.0), source_patch=repeat(0),
+                                             dest_patch=np.arange(P), displacement_real=np.ones(P),
+                                             displacement_imag=np.zeros(P), time_solve=repeat(0.1))
