@@ -20,6 +20,11 @@ f64 = C.c_double
 vp = C.c_void_p
 
 
+class cfield(C.Structure):
+    """cnld_field by value (two doubles)."""
+    _fields_ = [('re', C.c_double), ('im', C.c_double)]
+
+
 class Cnldb200Error(RuntimeError):
     pass
 
@@ -54,6 +59,15 @@ def lib():
         L.cnld_b200_sweep_kernel_stats.argtypes = [vp, vp]
         L.cnld_b200_pres_vector.argtypes = [vp, vp, u32, f64, f64, f64, vp]
         L.cnld_b200_pressure.argtypes = [vp, vp, u32, vp, u32, f64, f64, vp, u32, vp]
+        L.cnld_b200_hmat_create.restype = vp
+        L.cnld_b200_hmat_create.argtypes = [vp, u32, f64, C.c_int, C.c_int, u32]
+        L.cnld_b200_hmat_destroy.argtypes = [vp]
+        L.cnld_b200_hmat_info.argtypes = [vp, vp]
+        L.cnld_b200_hmat_tree.argtypes = [vp] * 12
+        L.cnld_b200_hmat_assemble.argtypes = [vp, f64, f64, f64]
+        L.cnld_b200_hmat_matvec.argtypes = [vp, cfield, vp, vp, u32]
+        L.cnld_b200_hmat_todense.argtypes = [vp, vp, u32]
+        L.cnld_b200_hsweep_run.argtypes = [vp, vp, vp, u32, f64, f64, f64, f64, u32, u32, u32, vp, vp, vp, vp]
         L.cnld_b200_bench_zgemm.argtypes = [C.c_int, u32, u32, u32, C.c_int, vp]
         L.cnld_b200_bench_dfma.argtypes = [C.c_int, C.c_int, vp]
         _lib = L
@@ -201,6 +215,74 @@ class Context:
         check(lib().cnld_b200_pressure(self._h, ptr(obs), len(obs), ptr(ks), nk, c, rho, ptr(disp), nsrc,
                                        ptr(out)))
         return out
+
+
+ADMIS = {'2': 0, 'max': 1, 'sphere': 2, '2min': 3, '2_min': 3}
+
+
+class HMatrix:
+    """Device H-matrix of the Helmholtz SLP operator bound to a Context (opaque cnld_hmat)."""
+
+    def __init__(self, ctx, clf=16, eta=0.8, admis='2', strict=True, kmax=64):
+        self.ctx = ctx
+        self._h = lib().cnld_b200_hmat_create(ctx._h, clf, float(eta), ADMIS[str(admis).lower()], int(bool(strict)), kmax)
+        if not self._h:
+            raise Cnldb200Error(lib().cnld_b200_last_error().decode())
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().cnld_b200_hmat_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def info(self):
+        out = np.zeros(8)
+        check(lib().cnld_b200_hmat_info(self._h, ptr(out)))
+        keys = ('clusters', 'leaves', 'admissible', 'inadmissible', 'capacity', 'stored', 'maxrank', 'n')
+        return {k: int(v) for k, v in zip(keys, out)}
+
+    def tree(self):
+        i = self.info()
+        ncl, nl, n = i['clusters'], i['leaves'], i['n']
+        t = dict(perm=np.zeros(n, np.uint32), son0=np.zeros(ncl, np.int32), son1=np.zeros(ncl, np.int32),
+                 start=np.zeros(ncl, np.uint32), size=np.zeros(ncl, np.uint32), bmin=np.zeros((ncl, 3)),
+                 bmax=np.zeros((ncl, 3)), leaf_rc=np.zeros(nl, np.uint32), leaf_cc=np.zeros(nl, np.uint32),
+                 leaf_adm=np.zeros(nl, np.uint8), leaf_rank=np.zeros(nl, np.uint32))
+        check(lib().cnld_b200_hmat_tree(self._h, *[ptr(a) for a in t.values()]))
+        return t
+
+    def assemble(self, k, eps_aca=1e-2):
+        k = complex(k)
+        check(lib().cnld_b200_hmat_assemble(self._h, k.real, k.imag, float(eps_aca)))
+
+    def matvec(self, x, alpha=1.0):
+        """alpha * Z @ x for x[n] or x[n, nrhs]."""
+        x = np.asarray(x, dtype=np.complex128)
+        X = np.ascontiguousarray(x.reshape(x.shape[0], -1).T)      # [nrhs][n]
+        Y = np.zeros_like(X)
+        a = complex(alpha)
+        check(lib().cnld_b200_hmat_matvec(self._h, cfield(a.real, a.imag), ptr(X), ptr(Y), X.shape[0]))
+        return Y.T.reshape(x.shape)
+
+    def todense(self):
+        n = self.ctx.nv
+        buf = np.zeros((n, n), dtype=np.complex128)
+        check(lib().cnld_b200_hmat_todense(self._h, ptr(buf), n))
+        return buf.T
+
+    def sweep(self, freqs, c=1500., rho=1000., eps_aca=1e-2, tol=1e-6, restart=50, maxiter=500, batch=32,
+              want_nodes=True):
+        """H-matrix + GMRES sweep -> x_patch[nf, P, P], x_node[nf, P, N] | None, iters[nf, P], t[nf]."""
+        freqs = _c(freqs, np.float64)
+        nf, P, n = len(freqs), self.ctx.npatch, self.ctx.nv
+        xp = np.zeros((nf, P, P), dtype=np.complex128)
+        xn = np.zeros((nf, P, n), dtype=np.complex128) if want_nodes else None
+        it = np.zeros((nf, P), dtype=np.uint32)
+        t = np.zeros(nf)
+        check(lib().cnld_b200_hsweep_run(self.ctx._h, self._h, ptr(freqs), nf, c, rho, eps_aca, tol, restart, maxiter,
+                                         batch, ptr(xp), ptr(xn), ptr(it), ptr(t)))
+        return xp, xn, it, t
 
 
 def lrdecomp(G, device=0):

@@ -13,14 +13,13 @@
 //               column triangles through shared memory.  FP64 sincos + rsqrt.
 //   k_singular: one warp per touching pair (identical / common edge / common vertex),
 //               lanes stride the Sauter-Schwab points, warp-shuffle reduction.
-#include "bem.cuh"
+#include "pair.cuh"
 
 namespace cnld {
 
 namespace {
 constexpr int MAXNQ = 16;
 
-constexpr double INV4PI = 0.0795774715459476678844418816863;
 
 // per-triangle setup: Gram determinant g = |(B-A)x(C-A)| = 2*area, unit normal, and the
 // regular rule's points in global coordinates (H2Lib USE_TRIQUADPOINTS, singquad2d.h:120-135)
@@ -40,17 +39,6 @@ __global__ void k_tri_setup(uint nt, uint nq, const __grid_constant__ RegRule R,
   for (uint p = 0; p < nq; p++)
     for (int d = 0; d < 3; d++)
       qp[((size_t)i * nq + p) * 3 + d] = A[d] * R.phi[p][0] + B[d] * R.phi[p][1] + C[d] * R.phi[p][2];
-}
-
-// exp(i kr r) * exp(-ki r) / r  for squared distance r2
-template <bool CPLXK>
-__device__ __forceinline__ cplx helmholtz(double r2, double kr, double ki) {
-  double rinv = rsqrt(r2);
-  double r = r2 * rinv;
-  if (CPLXK) rinv *= exp(-ki * r);
-  double s, c;
-  sincos(kr * r, &s, &c);
-  return make_double2(c * rinv, s * rinv);
 }
 
 constexpr int REG_THREADS = 128;
@@ -87,31 +75,7 @@ k_regular(uint nt, const __grid_constant__ RegRule R, const uint *__restrict__ t
                  (tv[1] == sv2) | (tv[2] == sv0) | (tv[2] == sv1) | (tv[2] == sv2);
     if (touch) continue;  // handled by k_singular
     cplx loc[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-      for (int j = 0; j < 3; j++) loc[i][j] = make_double2(0.0, 0.0);
-#pragma unroll
-    for (int p = 0; p < NQ; p++) {
-      cplx a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0;
-#pragma unroll
-      for (int q = 0; q < NQ; q++) {
-        double dx = xp[p][0] - s_qp[sl][q][0], dy = xp[p][1] - s_qp[sl][q][1],
-               dz = xp[p][2] - s_qp[sl][q][2];
-        cplx kv = helmholtz<CPLXK>(dx * dx + dy * dy + dz * dz, kr, ki);
-        double w0 = R.w[q] * R.phi[q][0], w1 = R.w[q] * R.phi[q][1], w2 = R.w[q] * R.phi[q][2];
-        a0.x = fma(w0, kv.x, a0.x); a0.y = fma(w0, kv.y, a0.y);
-        a1.x = fma(w1, kv.x, a1.x); a1.y = fma(w1, kv.y, a1.y);
-        a2.x = fma(w2, kv.x, a2.x); a2.y = fma(w2, kv.y, a2.y);
-      }
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        double wi = R.w[p] * R.phi[p][i];
-        loc[i][0].x = fma(wi, a0.x, loc[i][0].x); loc[i][0].y = fma(wi, a0.y, loc[i][0].y);
-        loc[i][1].x = fma(wi, a1.x, loc[i][1].x); loc[i][1].y = fma(wi, a1.y, loc[i][1].y);
-        loc[i][2].x = fma(wi, a2.x, loc[i][2].x); loc[i][2].y = fma(wi, a2.y, loc[i][2].y);
-      }
-    }
+    regular_pair<NQ, CPLXK>(xp, &s_qp[sl][0][0], R, kr, ki, loc);
     const double sc = gt * s_g[sl];
     const cplx f = make_double2(alpha.x * sc, alpha.y * sc);
     const uint sv[3] = {sv0, sv1, sv2};
@@ -146,33 +110,8 @@ k_singular(size_t npairs, const TouchPair *__restrict__ pairs, const double *__r
       V[v][d] = x[3 * (size_t)P.rv[v] + d];
       V[3 + v][d] = x[3 * (size_t)P.cv[v] + d];
     }
-  const uint n = tab.n[P.family];
-  const double *xt = tab.p[P.family], *xs = xt + n, *yt = xs + n, *ys = yt + n, *w = ys + n;
   double acc[18];
-#pragma unroll
-  for (int i = 0; i < 18; i++) acc[i] = 0.0;
-  for (uint q = lane; q < n; q += 32) {
-    double a[3] = {1.0 - xt[q], xt[q] - xs[q], xs[q]};
-    double b[3] = {1.0 - yt[q], yt[q] - ys[q], ys[q]};
-    double dx = V[0][0] * a[0] + V[1][0] * a[1] + V[2][0] * a[2] - (V[3][0] * b[0] + V[4][0] * b[1] + V[5][0] * b[2]);
-    double dy = V[0][1] * a[0] + V[1][1] * a[1] + V[2][1] * a[2] - (V[3][1] * b[0] + V[4][1] * b[1] + V[5][1] * b[2]);
-    double dz = V[0][2] * a[0] + V[1][2] * a[1] + V[2][2] * a[2] - (V[3][2] * b[0] + V[4][2] * b[1] + V[5][2] * b[2]);
-    cplx kv = helmholtz<CPLXK>(dx * dx + dy * dy + dz * dz, kr, ki);
-    double wq = w[q];
-    kv.x *= wq; kv.y *= wq;
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        double ab = a[i] * b[j];
-        acc[2 * (3 * i + j)] = fma(ab, kv.x, acc[2 * (3 * i + j)]);
-        acc[2 * (3 * i + j) + 1] = fma(ab, kv.y, acc[2 * (3 * i + j) + 1]);
-      }
-  }
-#pragma unroll
-  for (int i = 0; i < 18; i++)
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+  singular_pair_warp<CPLXK>(V, tab, P.family, kr, ki, lane, acc);
   if (lane == 0) {
     double sc = g[P.t] * g[P.s] * INV4PI;
     cplx f = make_double2(alpha.x * sc, alpha.y * sc);

@@ -24,52 +24,11 @@ void set_error(const char *fmt, ...) {
   g_err = buf;
 }
 
-namespace sweep {
-constexpr int MAX_SLOTS = 8;
-constexpr double TWO_PI = 6.283185307179586476925286766559;
-
-struct Slot {
-  cudaStream_t st = nullptr;
-  cplx *G = nullptr;      // nv x nv
-  cplx *X = nullptr;      // nv x P
-  cplx *hX = nullptr;     // pinned staging for x_node
-  LuWork lu;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  long pending = -1;      // frequency index whose x_node sits in hX
-};
-}  // namespace sweep
 }  // namespace cnld
 
+#include "ctx.cuh"
 using namespace cnld;
 using namespace cnld::sweep;
-
-struct cnld_ctx {
-  BemDev bem;
-  int nslots = 2;
-  Slot slots[MAX_SLOTS];
-  bool ws_ready = false;
-  // FEM operators, one CSR pattern
-  size_t nnz = 0;
-  int64_t *d_indptr = nullptr;
-  uint *d_indices = nullptr;
-  double *d_K = nullptr, *d_M = nullptr, *d_B = nullptr;
-  // loads
-  uint P = 0;
-  int64_t *d_f_indptr = nullptr, *d_a_indptr = nullptr;
-  uint *d_f_idx = nullptr, *d_a_idx = nullptr;
-  double *d_f_val = nullptr, *d_a_val = nullptr;
-  uint8_t *d_ob = nullptr;
-  // results of the last sweep
-  cplx *d_xpatch = nullptr;
-  size_t xpatch_cap = 0;
-  cplx *d_xnode = nullptr;  // only for run_device with keep_node
-  double stage[5] = {0, 0, 0, 0, 0};
-  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-  bool profile = false;
-  double kstat[3] = {0, 0, 0};  // trailing ZGEMM: flops, seconds, launches (last sweep)
-  // pressure scratch
-  double *d_sp = nullptr;
-};
 
 namespace cnld_capi {
 
@@ -290,6 +249,8 @@ cnld_ctx *cnld_b200_create(int device, cnld_uint nv, cnld_uint nt, const double 
   for (size_t i = 0; i < 3 * (size_t)nt; i++)
     if (t[i] >= nv) { set_error("triangle vertex index out of range"); return nullptr; }
   cnld_ctx *c = new cnld_ctx();
+  c->h_x.assign(x, x + 3 * (size_t)nv);
+  c->h_t.assign(t, t + 3 * (size_t)nt);
   if (bem_create(c->bem, device, nv, nt, x, t, q_reg, q_sing)) { delete c; return nullptr; }
   return c;
 }
@@ -419,6 +380,9 @@ int cnld_b200_set_mbk(cnld_ctx *c, const int64_t *indptr, const cnld_uint *indic
   size_t nnz = (size_t)indptr[nv];
   for (size_t i = 0; i < nnz; i++) if (indices[i] >= nv) { set_error("MBK column index out of range"); return -1; }
   c->nnz = nnz;
+  c->h_indptr.assign(indptr, indptr + nv + 1);
+  c->h_indices.assign(indices, indices + nnz);
+  c->h_K.assign(K, K + nnz); c->h_M.assign(M, M + nnz); c->h_B.assign(B, B + nnz);
   if (upload(c->d_indptr, indptr, nv + 1) || upload(c->d_indices, indices, nnz) || upload(c->d_K, K, nnz) ||
       upload(c->d_M, M, nnz) || upload(c->d_B, B, nnz)) return -1;
   return 0;

@@ -1,0 +1,59 @@
+// Private definition of cnld_ctx (shared by capi.cu and hapi.cu).
+#pragma once
+#include "../../include/cnld_b200.h"
+#include "bem.cuh"
+
+namespace cnld {
+namespace sweep {
+constexpr int MAX_SLOTS = 8;
+constexpr double TWO_PI = 6.283185307179586476925286766559;
+
+struct Slot {
+  cudaStream_t st = nullptr;
+  cplx *G = nullptr;      // nv x nv
+  cplx *X = nullptr;      // nv x P
+  cplx *hX = nullptr;     // pinned staging for x_node
+  LuWork lu;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  long pending = -1;      // frequency index whose x_node sits in hX
+};
+}  // namespace sweep
+}  // namespace cnld
+
+using namespace cnld;
+using namespace cnld::sweep;
+
+struct cnld_ctx {
+  BemDev bem;
+  int nslots = 2;
+  Slot slots[MAX_SLOTS];
+  bool ws_ready = false;
+  // FEM operators, one CSR pattern
+  size_t nnz = 0;
+  int64_t *d_indptr = nullptr;
+  uint *d_indices = nullptr;
+  double *d_K = nullptr, *d_M = nullptr, *d_B = nullptr;
+  // host copies (block detection for the GMRES preconditioner, hapi.cu)
+  std::vector<int64_t> h_indptr;
+  std::vector<uint> h_indices;
+  std::vector<double> h_K, h_M, h_B;
+  std::vector<double> h_x;   // mesh kept for the cluster tree
+  std::vector<uint> h_t;
+  // loads
+  uint P = 0;
+  int64_t *d_f_indptr = nullptr, *d_a_indptr = nullptr;
+  uint *d_f_idx = nullptr, *d_a_idx = nullptr;
+  double *d_f_val = nullptr, *d_a_val = nullptr;
+  uint8_t *d_ob = nullptr;
+  // results of the last sweep
+  cplx *d_xpatch = nullptr;
+  size_t xpatch_cap = 0;
+  cplx *d_xnode = nullptr;  // only for run_device with keep_node
+  double stage[5] = {0, 0, 0, 0, 0};
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  bool profile = false;
+  double kstat[3] = {0, 0, 0};  // trailing ZGEMM: flops, seconds, launches (last sweep)
+  // pressure scratch
+  double *d_sp = nullptr;
+};
+

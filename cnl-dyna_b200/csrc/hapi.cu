@@ -1,0 +1,521 @@
+// C ABI of the H-matrix path (include/cnld_b200.h, "cnld_b200_hmat_*" / "cnld_b200_hsweep_run")
+// and the GPU GMRES that replaces the reference's H-LU for arrays too large to factor densely
+// (BASELINE.json north_star; Krylov formulation of scratch/freq_resp_db_krylov.py:38-79 and
+// solve_gmres_hmatrix_avector, include/krylovsolvers.h:283).
+//
+// Per frequency:  G x = F[:, s]  with  G = (K - w^2 M - j w B) + (-2 rho w^2) Z_H(k),
+// left-preconditioned by the block-diagonal inverse of the FEM operator (one dense inverse per
+// membrane type and frequency, the `Gfe_inv` of the reference's Krylov driver), restarted
+// GMRES with classical Gram-Schmidt + re-orthogonalisation, all right-hand sides of a batch
+// iterated in lock-step so every H-matrix leaf is streamed from HBM once per iteration for the
+// whole batch.
+#include <cmath>
+#include <complex>
+
+#include "ctx.cuh"
+#include "hmat.cuh"
+
+struct cnld_hmat {
+  cnld_ctx *ctx = nullptr;
+  HMat H;
+};
+
+namespace cnld_hapi {
+typedef std::complex<double> zc;
+constexpr double H_TWO_PI = 6.283185307179586476925286766559;
+
+// ---- batched vector kernels; vectors are [r][n] with stride n --------------------------------
+__global__ void k_spmv_mbk(uint n, uint nb, const int64_t *__restrict__ indptr, const uint *__restrict__ indices,
+                           const double *__restrict__ K, const double *__restrict__ M, const double *__restrict__ B,
+                           double omega, const cplx *__restrict__ X, cplx *Y) {
+  // Y[r][i] = sum_j (K - w^2 M - j w B)[i,j] X[r][j]; one warp per (row, rhs)
+  const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint lane = threadIdx.x & 31;
+  if (w >= (size_t)n * nb) return;
+  const uint r = w / n, i = w % n;
+  const double w2 = omega * omega;
+  cplx s = make_double2(0.0, 0.0);
+  for (int64_t p = indptr[i] + lane; p < indptr[i + 1]; p += 32) {
+    cplx a = make_double2(K[p] - w2 * M[p], -omega * B[p]);
+    cfma(s, a, X[(size_t)r * n + indices[p]]);
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, off);
+    s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
+  }
+  if (lane == 0) Y[(size_t)r * n + i] = s;
+}
+
+__global__ void k_block_dense(uint nb_, uint r0, const int64_t *__restrict__ indptr, const uint *__restrict__ indices,
+                              const double *__restrict__ K, const double *__restrict__ M, const double *__restrict__ B,
+                              double omega, cplx *D) {
+  // dense copy of one diagonal block of the FEM operator (column-major nb_ x nb_, zero-initialised)
+  uint i = blockIdx.x;
+  const double w2 = omega * omega;
+  for (int64_t p = indptr[r0 + i] + threadIdx.x; p < indptr[r0 + i + 1]; p += blockDim.x) {
+    uint j = indices[p] - r0;
+    if (j < nb_) D[(size_t)j * nb_ + i] = make_double2(K[p] - w2 * M[p], -omega * B[p]);
+  }
+}
+__global__ void k_identity(uint n, cplx *D) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)n * n) D[i] = make_double2((i % n) == (i / n) ? 1.0 : 0.0, 0.0);
+}
+
+// Hd[i][r] = <V_i[r], W[r]>, i = 0..nv-1 (conjugate-linear in V); grid (nb, nv)
+__global__ void __launch_bounds__(256) k_dots(uint n, uint nb, const cplx *__restrict__ Vb, const cplx *__restrict__ W, cplx *Hd) {
+  __shared__ double sr[8], si[8];
+  const uint r = blockIdx.x, i = blockIdx.y;
+  const cplx *v = Vb + ((size_t)i * nb + r) * n, *w = W + (size_t)r * n;
+  double ar = 0.0, ai = 0.0;
+  for (uint e = threadIdx.x; e < n; e += 256) {
+    cplx a = v[e], b = w[e];
+    ar += a.x * b.x + a.y * b.y;
+    ai += a.x * b.y - a.y * b.x;
+  }
+  for (int off = 16; off > 0; off >>= 1) { ar += __shfl_xor_sync(0xffffffffu, ar, off); ai += __shfl_xor_sync(0xffffffffu, ai, off); }
+  if ((threadIdx.x & 31) == 0) { sr[threadIdx.x >> 5] = ar; si[threadIdx.x >> 5] = ai; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; k++) { ar += sr[k]; ai += si[k]; }
+    Hd[(size_t)i * nb + r] = make_double2(ar, ai);
+  }
+}
+// W[r] -= sum_i Hd[i][r] V_i[r]
+__global__ void k_project(uint n, uint nb, uint nv, const cplx *__restrict__ Vb, const cplx *__restrict__ Hd, cplx *W) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint r = blockIdx.y;
+  if (e >= n) return;
+  cplx w = W[(size_t)r * n + e];
+  for (uint i = 0; i < nv; i++) cfms(w, Hd[(size_t)i * nb + r], Vb[((size_t)i * nb + r) * n + e]);
+  W[(size_t)r * n + e] = w;
+}
+// out[r] = W[r] * s[r]   (s real)
+__global__ void k_scale_to(uint n, const cplx *__restrict__ W, const double *__restrict__ s, cplx *out) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint r = blockIdx.y;
+  if (e >= n) return;
+  cplx w = W[(size_t)r * n + e];
+  out[(size_t)r * n + e] = make_double2(w.x * s[r], w.y * s[r]);
+}
+// X[r] += sum_j y[j][r] V_j[r]
+__global__ void k_combine(uint n, uint nb, uint nv, const cplx *__restrict__ Vb, const cplx *__restrict__ y, cplx *X) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint r = blockIdx.y;
+  if (e >= n) return;
+  cplx x = X[(size_t)r * n + e];
+  for (uint j = 0; j < nv; j++) cfma(x, y[(size_t)j * nb + r], Vb[((size_t)j * nb + r) * n + e]);
+  X[(size_t)r * n + e] = x;
+}
+__global__ void k_sub(size_t tot, const cplx *__restrict__ A, const cplx *__restrict__ Bv, cplx *C) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < tot) C[e] = make_double2(A[e].x - Bv[e].x, A[e].y - Bv[e].y);
+}
+__global__ void k_rhs_batch(uint n, uint s0, const int64_t *__restrict__ indptr, const uint *__restrict__ idx,
+                            const double *__restrict__ val, cplx *X) {
+  uint col = s0 + blockIdx.x;
+  for (int64_t p = indptr[col] + threadIdx.x; p < indptr[col + 1]; p += blockDim.x)
+    X[(size_t)blockIdx.x * n + idx[p]] = make_double2(val[p], 0.0);
+}
+__global__ void __launch_bounds__(256)
+k_epilogue_batch(uint nv, uint P, uint s0, cplx *X, const uint8_t *__restrict__ ob, const int64_t *__restrict__ a_indptr,
+                 const uint *__restrict__ a_idx, const double *__restrict__ a_val, cplx *xpatch) {
+  // x = conj(x); x[ob] = 0; x_patch[src][dst] = AVG[:, dst] . x   (generate_db.py:89-99)
+  const uint src = s0 + blockIdx.x;
+  cplx *x = X + (size_t)blockIdx.x * nv;
+  for (uint i = threadIdx.x; i < nv; i += blockDim.x) {
+    cplx v = x[i];
+    v.y = -v.y;
+    if (ob[i]) v = make_double2(0.0, 0.0);
+    x[i] = v;
+  }
+  __syncthreads();
+  const uint warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (uint dst = warp; dst < P; dst += nw) {
+    double sr = 0.0, si = 0.0;
+    for (int64_t p = a_indptr[dst] + lane; p < a_indptr[dst + 1]; p += 32) {
+      cplx v = x[a_idx[p]];
+      sr = fma(a_val[p], v.x, sr);
+      si = fma(a_val[p], v.y, si);
+    }
+    for (int off = 16; off > 0; off >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, off); si += __shfl_xor_sync(0xffffffffu, si, off); }
+    if (lane == 0) xpatch[(size_t)src * P + dst] = make_double2(sr, si);
+  }
+}
+
+struct Blocks {  // diagonal blocks of the FEM operator and their types (identical membranes share one)
+  std::vector<uint> r0, sz, type;
+  std::vector<uint> rep;  // representative block of each type
+};
+
+// block-diagonal structure from the CSR pattern; blocks with identical K, M, B get one type
+void detect_blocks(const cnld_ctx *c, Blocks &B) {
+  const uint n = c->bem.nv;
+  uint start = 0, reach = 0;
+  for (uint i = 0; i < n; i++) {
+    for (int64_t p = c->h_indptr[i]; p < c->h_indptr[i + 1]; p++) reach = std::max(reach, c->h_indices[p]);
+    // tiny blocks (clamped boundary nodes have identity rows) are merged into the block that follows
+    if (reach <= i && (i + 1 - start >= 8 || i + 1 == n)) {
+      B.r0.push_back(start); B.sz.push_back(i + 1 - start); start = i + 1; reach = i + 1;
+    }
+  }
+  auto same = [&](uint a, uint b) {
+    if (B.sz[a] != B.sz[b]) return false;
+    int64_t pa = c->h_indptr[B.r0[a]], pb = c->h_indptr[B.r0[b]];
+    int64_t na = c->h_indptr[B.r0[a] + B.sz[a]] - pa, nb = c->h_indptr[B.r0[b] + B.sz[b]] - pb;
+    if (na != nb) return false;
+    for (int64_t q = 0; q < na; q++) {
+      if (c->h_indices[pa + q] - B.r0[a] != c->h_indices[pb + q] - B.r0[b]) return false;
+      if (c->h_K[pa + q] != c->h_K[pb + q] || c->h_M[pa + q] != c->h_M[pb + q] || c->h_B[pa + q] != c->h_B[pb + q]) return false;
+    }
+    return true;
+  };
+  for (uint b = 0; b < B.r0.size(); b++) {
+    uint t = (uint)B.rep.size();
+    for (uint k = 0; k < B.rep.size(); k++) if (same(B.rep[k], b)) { t = k; break; }
+    if (t == B.rep.size()) B.rep.push_back(b);
+    B.type.push_back(t);
+  }
+}
+
+struct Gmres {
+  cnld_ctx *c;
+  HMat *H;
+  cudaStream_t st;
+  uint n, nb, restart;
+  double omega, coef;
+  Blocks blk;
+  std::vector<cplx *> d_inv;  // per block type: dense inverse
+  cplx *Vb = nullptr, *W = nullptr, *T = nullptr, *X = nullptr, *Bp = nullptr, *Hd = nullptr, *yd = nullptr;
+  double *sd = nullptr;
+
+  int apply_G(const cplx *x, cplx *y, uint nr) {  // y = MBK x + coef Z x
+    k_spmv_mbk<<<(unsigned)(((size_t)n * nr * 32 + 255) / 256), 256, 0, st>>>(n, nr, c->d_indptr, c->d_indices, c->d_K,
+                                                                            c->d_M, c->d_B, omega, x, y);
+    CNLD_CK_LAUNCH();
+    if (coef != 0.0 && hmat_matvec(st, *H, make_double2(coef, 0.0), x, y, nr)) return -1;
+    return 0;
+  }
+  int apply_P(const cplx *x, cplx *y, uint nr) {  // y = blockdiag(MBK)^-1 x
+    for (size_t b = 0; b < blk.r0.size(); b++)
+      if (zgemm(st, blk.sz[b], nr, blk.sz[b], 1.0, d_inv[blk.type[b]], blk.sz[b], x + blk.r0[b], n, 0.0, y + blk.r0[b], n))
+        return -1;
+    return 0;
+  }
+  int setup_precond() {
+    for (uint t = 0; t < blk.rep.size(); t++) {
+      const uint b = blk.rep[t], sz = blk.sz[b];
+      if (sz > 8192) { set_error("FEM diagonal block of %u DOFs is too large for the block preconditioner", sz); return -1; }
+      cplx *D = nullptr, *I = nullptr;
+      CNLD_CK(cudaMalloc(&D, sizeof(cplx) * (size_t)sz * sz));
+      CNLD_CK(cudaMalloc(&I, sizeof(cplx) * (size_t)sz * sz));
+      CNLD_CK(cudaMemsetAsync(D, 0, sizeof(cplx) * (size_t)sz * sz, st));
+      k_block_dense<<<sz, 128, 0, st>>>(sz, blk.r0[b], c->d_indptr, c->d_indices, c->d_K, c->d_M, c->d_B, omega, D);
+      CNLD_CK_LAUNCH();
+      k_identity<<<(unsigned)(((size_t)sz * sz + 255) / 256), 256, 0, st>>>(sz, I);
+      CNLD_CK_LAUNCH();
+      LuWork w;
+      if (lu_work_alloc(w, sz) || lu_factor(st, w, D, sz) || lu_solve(st, w, D, sz, I, sz, sz)) return -1;
+      CNLD_CK(cudaStreamSynchronize(st));
+      lu_work_free(w);
+      cudaFree(D);
+      if (t < d_inv.size()) { cudaFree(d_inv[t]); d_inv[t] = I; } else d_inv.push_back(I);
+    }
+    return 0;
+  }
+  int alloc() {
+    const size_t v = (size_t)n * nb;
+    CNLD_CK(cudaMalloc(&Vb, sizeof(cplx) * v * (restart + 1)));
+    CNLD_CK(cudaMalloc(&W, sizeof(cplx) * v));
+    CNLD_CK(cudaMalloc(&T, sizeof(cplx) * v));
+    CNLD_CK(cudaMalloc(&X, sizeof(cplx) * v));
+    CNLD_CK(cudaMalloc(&Bp, sizeof(cplx) * v));
+    CNLD_CK(cudaMalloc(&Hd, sizeof(cplx) * (size_t)(restart + 2) * nb));
+    CNLD_CK(cudaMalloc(&yd, sizeof(cplx) * (size_t)(restart + 1) * nb));
+    CNLD_CK(cudaMalloc(&sd, sizeof(double) * nb));
+    return 0;
+  }
+  void release() {
+    cudaFree(Vb); cudaFree(W); cudaFree(T); cudaFree(X); cudaFree(Bp); cudaFree(Hd); cudaFree(yd); cudaFree(sd);
+    for (auto p : d_inv) cudaFree(p);
+    d_inv.clear();
+  }
+
+  // Solve P G X = P B for nr right-hand sides held in B (device, [r][n]); result in X.
+  int solve(const cplx *Bdev, uint nr, double tol, uint maxiter, uint *iters) {
+    const size_t v = (size_t)n * nr;
+    const unsigned gv = (unsigned)((v + 255) / 256);
+    dim3 ge((n + 255) / 256, nr);
+    std::vector<double> bnorm(nr), resid(nr), scal(nr);
+    std::vector<zc> hh((size_t)(restart + 2) * nb);
+    std::vector<char> done(nr, 0);
+    std::vector<uint> it(nr, 0);
+    CNLD_CK(cudaMemsetAsync(X, 0, sizeof(cplx) * v, st));
+    if (apply_P(Bdev, Bp, nr)) return -1;
+    auto norms = [&](const cplx *vec, std::vector<double> &out) -> int {
+      dim3 g(nr, 1);
+      k_dots<<<g, 256, 0, st>>>(n, nr, vec, vec, Hd);   // Vb index 0 -> vec itself (stride nb*n unused for i = 0)
+      CNLD_CK_LAUNCH();
+      CNLD_CK(cudaMemcpyAsync(hh.data(), Hd, sizeof(cplx) * nr, cudaMemcpyDeviceToHost, st));
+      CNLD_CK(cudaStreamSynchronize(st));
+      for (uint r = 0; r < nr; r++) out[r] = std::sqrt(std::max(hh[r].real(), 0.0));
+      return 0;
+    };
+    if (norms(Bp, bnorm)) return -1;
+    for (uint r = 0; r < nr; r++) if (bnorm[r] == 0.0) done[r] = 1;
+    uint total = 0;
+    while (total < maxiter) {
+      // residual of the preconditioned system
+      if (total == 0) {
+        CNLD_CK(cudaMemcpyAsync(W, Bp, sizeof(cplx) * v, cudaMemcpyDeviceToDevice, st));
+      } else {
+        if (apply_G(X, T, nr) || apply_P(T, W, nr)) return -1;
+        k_sub<<<gv, 256, 0, st>>>(v, Bp, W, W);
+        CNLD_CK_LAUNCH();
+      }
+      if (norms(W, resid)) return -1;
+      bool all = true;
+      for (uint r = 0; r < nr; r++) {
+        if (!done[r] && resid[r] <= tol * bnorm[r]) done[r] = 1;
+        all &= (bool)done[r];
+        scal[r] = resid[r] > 0.0 ? 1.0 / resid[r] : 0.0;
+      }
+      if (all) break;
+      CNLD_CK(cudaMemcpyAsync(sd, scal.data(), sizeof(double) * nr, cudaMemcpyHostToDevice, st));
+      k_scale_to<<<ge, 256, 0, st>>>(n, W, sd, Vb);
+      CNLD_CK_LAUNCH();
+      // per-rhs Hessenberg least squares by Givens rotations (host, tiny)
+      const uint m = restart;
+      std::vector<zc> Hm((size_t)nr * (m + 1) * m, zc(0)), gvec((size_t)nr * (m + 1), zc(0)), cs((size_t)nr * m), sn((size_t)nr * m);
+      for (uint r = 0; r < nr; r++) gvec[(size_t)r * (m + 1)] = resid[r];
+      uint j = 0;
+      for (; j < m && total < maxiter; j++, total++) {
+        const cplx *vj = Vb + (size_t)j * nb * n;
+        if (apply_G(vj, T, nr) || apply_P(T, W, nr)) return -1;
+        std::vector<zc> hcol((size_t)(j + 2) * nr, zc(0));
+        for (int pass = 0; pass < 2; pass++) {  // classical Gram-Schmidt, twice
+          dim3 gd(nr, j + 1);
+          k_dots<<<gd, 256, 0, st>>>(n, nb, Vb, W, Hd);
+          CNLD_CK_LAUNCH();
+          k_project<<<ge, 256, 0, st>>>(n, nb, j + 1, Vb, Hd, W);
+          CNLD_CK_LAUNCH();
+          CNLD_CK(cudaMemcpyAsync(hh.data(), Hd, sizeof(cplx) * (size_t)(j + 1) * nb, cudaMemcpyDeviceToHost, st));
+          CNLD_CK(cudaStreamSynchronize(st));
+          for (uint i = 0; i <= j; i++)
+            for (uint r = 0; r < nr; r++) hcol[(size_t)i * nr + r] += hh[(size_t)i * nb + r];
+        }
+        std::vector<double> wn(nr);
+        if (norms(W, wn)) return -1;
+        bool alldone = true;
+        for (uint r = 0; r < nr; r++) {
+          scal[r] = wn[r] > 0.0 ? 1.0 / wn[r] : 0.0;
+          if (done[r]) continue;
+          zc *Hr = Hm.data() + (size_t)r * (m + 1) * m, *gr = gvec.data() + (size_t)r * (m + 1);
+          zc *c_ = cs.data() + (size_t)r * m, *s_ = sn.data() + (size_t)r * m;
+          std::vector<zc> col(j + 2);
+          for (uint i = 0; i <= j; i++) col[i] = hcol[(size_t)i * nr + r];
+          col[j + 1] = wn[r];
+          for (uint i = 0; i < j; i++) {
+            zc t0 = std::conj(c_[i]) * col[i] + std::conj(s_[i]) * col[i + 1];
+            col[i + 1] = -s_[i] * col[i] + c_[i] * col[i + 1];
+            col[i] = t0;
+          }
+          double d = std::sqrt(std::norm(col[j]) + std::norm(col[j + 1]));
+          if (d == 0.0) { c_[j] = 1.0; s_[j] = 0.0; }
+          else { c_[j] = col[j] / d; s_[j] = col[j + 1] / d; }
+          // rotation G = [conj(c) conj(s); -s c] maps (col_j, col_{j+1}) -> (d, 0)
+          col[j] = d;
+          col[j + 1] = 0.0;
+          zc g0 = std::conj(c_[j]) * gr[j] + std::conj(s_[j]) * gr[j + 1];
+          gr[j + 1] = -s_[j] * gr[j] + c_[j] * gr[j + 1];
+          gr[j] = g0;
+          for (uint i = 0; i <= j + 1 && i <= m; i++) if (i <= j) Hr[(size_t)i * m + j] = col[i];
+          it[r]++;
+          if (std::abs(gr[j + 1]) <= tol * bnorm[r]) done[r] = 2;  // converged inside this cycle
+        }
+        for (uint r = 0; r < nr; r++) alldone &= (done[r] != 0);
+        CNLD_CK(cudaMemcpyAsync(sd, scal.data(), sizeof(double) * nr, cudaMemcpyHostToDevice, st));
+        k_scale_to<<<ge, 256, 0, st>>>(n, W, sd, Vb + (size_t)(j + 1) * nb * n);
+        CNLD_CK_LAUNCH();
+        CNLD_CK(cudaStreamSynchronize(st));
+        if (alldone) { j++; total++; break; }
+      }
+      // back substitution per rhs with the number of columns that rhs actually used
+      std::vector<zc> yh((size_t)m * nb, zc(0));
+      for (uint r = 0; r < nr; r++) {
+        if (done[r] == 1) continue;  // was already converged before this cycle: no update
+        zc *Hr = Hm.data() + (size_t)r * (m + 1) * m, *gr = gvec.data() + (size_t)r * (m + 1);
+        uint kk = j;
+        std::vector<zc> y(kk, zc(0));
+        for (uint ii = kk; ii-- > 0;) {
+          zc s = gr[ii];
+          for (uint l = ii + 1; l < kk; l++) s -= Hr[(size_t)ii * m + l] * y[l];
+          y[ii] = (Hr[(size_t)ii * m + ii] != zc(0)) ? s / Hr[(size_t)ii * m + ii] : zc(0);
+        }
+        for (uint l = 0; l < kk; l++) yh[(size_t)l * nb + r] = y[l];
+        if (done[r] == 2) done[r] = 1;
+      }
+      CNLD_CK(cudaMemcpyAsync(yd, yh.data(), sizeof(cplx) * (size_t)m * nb, cudaMemcpyHostToDevice, st));
+      k_combine<<<ge, 256, 0, st>>>(n, nb, j, Vb, yd, X);
+      CNLD_CK_LAUNCH();
+      CNLD_CK(cudaStreamSynchronize(st));
+    }
+    if (iters) for (uint r = 0; r < nr; r++) iters[r] = it[r];
+    return 0;
+  }
+};
+}  // namespace cnld_hapi
+using namespace cnld_hapi;
+
+extern "C" {
+
+cnld_hmat *cnld_b200_hmat_create(cnld_ctx *c, cnld_uint clf, double eta, int admis, int strict, cnld_uint kmax) {
+  if (!c) { set_error("null context"); return nullptr; }
+  if (clf < 1 || !(eta > 0.0) || admis < 0 || admis > 3) { set_error("bad cluster / admissibility parameters"); return nullptr; }
+  cnld_hmat *h = new cnld_hmat();
+  h->ctx = c;
+  if (hmat_create(h->H, c->bem, c->h_x.data(), c->h_t.data(), clf, eta, admis, strict != 0, kmax ? kmax : 64)) {
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+
+void cnld_b200_hmat_destroy(cnld_hmat *h) {
+  if (!h) return;
+  cudaSetDevice(h->ctx->bem.device);
+  hmat_free(h->H);
+  delete h;
+}
+
+int cnld_b200_hmat_info(cnld_hmat *h, double *out) {
+  if (!h) { set_error("null H-matrix"); return -1; }
+  HMat &H = h->H;
+  double used = (double)H.near_entries, maxrank = 0;
+  if (H.assembled) {
+    if (hmat_fetch_leaves(H)) return -1;
+    for (auto &L : H.leaf)
+      if (L.adm) { used += (double)L.k * (L.m + L.n); maxrank = std::max(maxrank, (double)L.k); }
+  }
+  out[0] = (double)H.tree.node.size(); out[1] = (double)H.leaf.size(); out[2] = H.nfar; out[3] = H.nnear;
+  out[4] = (double)H.pool_size; out[5] = used; out[6] = maxrank; out[7] = H.n;
+  return 0;
+}
+
+int cnld_b200_hmat_tree(cnld_hmat *h, cnld_uint *perm, int *son0, int *son1, cnld_uint *start, cnld_uint *size,
+                        double *bmin, double *bmax, cnld_uint *leaf_rc, cnld_uint *leaf_cc, uint8_t *leaf_adm,
+                        cnld_uint *leaf_rank) {
+  if (!h) { set_error("null H-matrix"); return -1; }
+  HMat &H = h->H;
+  if (perm) memcpy(perm, H.tree.perm.data(), sizeof(uint) * H.n);
+  for (size_t i = 0; i < H.tree.node.size(); i++) {
+    const ClusterNode &N = H.tree.node[i];
+    if (son0) son0[i] = N.son[0];
+    if (son1) son1[i] = N.son[1];
+    if (start) start[i] = N.start;
+    if (size) size[i] = N.size;
+    for (int d = 0; d < 3; d++) { if (bmin) bmin[3 * i + d] = N.bmin[d]; if (bmax) bmax[3 * i + d] = N.bmax[d]; }
+  }
+  if (leaf_rank && H.assembled && hmat_fetch_leaves(H)) return -1;
+  for (size_t b = 0; b < H.blocks.size(); b++) {
+    if (leaf_rc) leaf_rc[b] = H.blocks[b].rc;
+    if (leaf_cc) leaf_cc[b] = H.blocks[b].cc;
+    if (leaf_adm) leaf_adm[b] = H.blocks[b].admissible;
+    if (leaf_rank) leaf_rank[b] = H.leaf[b].adm ? H.leaf[b].k : 0;
+  }
+  return 0;
+}
+
+int cnld_b200_hmat_assemble(cnld_hmat *h, double k_re, double k_im, double eps_aca) {
+  if (!h) { set_error("null H-matrix"); return -1; }
+  CNLD_CK(cudaSetDevice(h->ctx->bem.device));
+  return hmat_assemble(0, h->H, k_re, k_im, eps_aca);
+}
+
+int cnld_b200_hmat_matvec(cnld_hmat *h, cnld_field alpha, const cnld_field *x, cnld_field *y, cnld_uint nrhs) {
+  if (!h) { set_error("null H-matrix"); return -1; }
+  CNLD_CK(cudaSetDevice(h->ctx->bem.device));
+  const size_t tot = (size_t)h->H.n * nrhs;
+  cplx *dx = nullptr, *dy = nullptr;
+  CNLD_CK(cudaMalloc(&dx, sizeof(cplx) * tot));
+  CNLD_CK(cudaMalloc(&dy, sizeof(cplx) * tot));
+  int rc = 0;
+  do {
+    if (cudaMemcpy(dx, x, sizeof(cplx) * tot, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(dy, y, sizeof(cplx) * tot, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); rc = -1; break; }
+    if (hmat_matvec(0, h->H, make_double2(alpha.re, alpha.im), dx, dy, nrhs)) { rc = -1; break; }
+    cudaError_t e = cudaMemcpy(y, dy, sizeof(cplx) * tot, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("hmat_matvec: %s", cudaGetErrorString(e)); rc = -1; }
+  } while (0);
+  cudaFree(dx); cudaFree(dy);
+  return rc;
+}
+
+int cnld_b200_hmat_todense(cnld_hmat *h, cnld_field *Z, cnld_uint ld) {
+  if (!h) { set_error("null H-matrix"); return -1; }
+  CNLD_CK(cudaSetDevice(h->ctx->bem.device));
+  const size_t n = h->H.n;
+  cplx *dZ = nullptr;
+  CNLD_CK(cudaMalloc(&dZ, sizeof(cplx) * n * n));
+  int rc = 0;
+  do {
+    if (hmat_expand(0, h->H, dZ, n)) { rc = -1; break; }
+    cudaError_t e = cudaMemcpy2D(Z, sizeof(cplx) * ld, dZ, sizeof(cplx) * n, sizeof(cplx) * n, n, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("hmat_todense: %s", cudaGetErrorString(e)); rc = -1; }
+  } while (0);
+  cudaFree(dZ);
+  return rc;
+}
+
+int cnld_b200_hsweep_run(cnld_ctx *c, cnld_hmat *h, const double *freqs, cnld_uint nf, double cs, double rho,
+                         double eps_aca, double tol, cnld_uint restart, cnld_uint maxiter, cnld_uint batch,
+                         cnld_field *x_patch, cnld_field *x_node, cnld_uint *iters, double *t_freq) {
+  if (!c || !h || h->ctx != c) { set_error("hsweep: context / H-matrix mismatch"); return -1; }
+  if (!c->d_indptr || !c->d_f_indptr) { set_error("cnld_b200_set_mbk / set_loads have not been called"); return -1; }
+  CNLD_CK(cudaSetDevice(c->bem.device));
+  const uint n = c->bem.nv, P = c->P;
+  Gmres G;
+  G.c = c; G.H = &h->H; G.st = 0; G.n = n;
+  G.nb = std::min(batch ? batch : 32u, P);
+  G.restart = restart ? restart : 50;
+  detect_blocks(c, G.blk);
+  if (G.alloc()) return -1;
+  cplx *dB = nullptr, *dxp = nullptr;
+  CNLD_CK(cudaMalloc(&dB, sizeof(cplx) * (size_t)n * G.nb));
+  CNLD_CK(cudaMalloc(&dxp, sizeof(cplx) * (size_t)P * P));
+  cudaEvent_t e0, e1;
+  CNLD_CK(cudaEventCreate(&e0));
+  CNLD_CK(cudaEventCreate(&e1));
+  int rc = 0;
+  for (uint i = 0; i < nf && !rc; i++) {
+    const double f = freqs[i], omega = H_TWO_PI * f;
+    G.omega = omega;
+    G.coef = -omega * omega * 2.0 * rho;
+    cudaEventRecord(e0, 0);
+    if (f != 0.0 && hmat_assemble(0, h->H, omega / cs, 0.0, eps_aca)) { rc = -1; break; }
+    if (G.setup_precond()) { rc = -1; break; }
+    for (uint s0 = 0; s0 < P && !rc; s0 += G.nb) {
+      const uint nr = std::min(G.nb, P - s0);
+      cudaMemsetAsync(dB, 0, sizeof(cplx) * (size_t)n * nr, 0);
+      k_rhs_batch<<<nr, 128>>>(n, s0, c->d_f_indptr, c->d_f_idx, c->d_f_val, dB);
+      cnld::count_launch();
+      if (G.solve(dB, nr, tol, maxiter ? maxiter : 500, iters ? iters + (size_t)i * P + s0 : nullptr)) { rc = -1; break; }
+      k_epilogue_batch<<<nr, 256>>>(n, P, s0, G.X, c->d_ob, c->d_a_indptr, c->d_a_idx, c->d_a_val, dxp);
+      cnld::count_launch();
+      if (x_node && cudaMemcpy(reinterpret_cast<cplx *>(x_node) + ((size_t)i * P + s0) * n, G.X, sizeof(cplx) * (size_t)n * nr,
+                               cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); rc = -1; }
+    }
+    cudaEventRecord(e1, 0);
+    if (cudaMemcpy(reinterpret_cast<cplx *>(x_patch) + (size_t)i * P * P, dxp, sizeof(cplx) * (size_t)P * P,
+                   cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); rc = -1; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (t_freq) t_freq[i] = ms * 1e-3;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(dB); cudaFree(dxp);
+  G.release();
+  return rc;
+}
+
+}  // extern "C"

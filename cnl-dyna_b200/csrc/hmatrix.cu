@@ -1,0 +1,524 @@
+// H-matrix path for arrays too large to factor densely: host-built cluster / block tree
+// (cluster.cpp), device-side leaf builders and the batched H-matrix matvec.
+//   inadmissible leaf -> dense block          = bem->nearfield        (include/bem3d.h:370-385)
+//   admissible leaf   -> partial-pivot ACA    = decomp_partialaca_rkmatrix with entry =
+//                                               bem->nearfield_far    (include/aca.h:79-117, bem3d.h:405)
+//   y += alpha Z x                            = addeval_hmatrix_avector (include/hmatrix.h:392-419)
+// Replaces setup_hmatrix_aprx_paca_bem3d + assemble_bem3d_hmatrix (bem3d.h:2627, :3056; call
+// sites cnld/compressed_formats.py:675-694).
+//
+// Layout in HBM: all leaves live in one pool of complex doubles; DOFs are permuted into cluster
+// order so every leaf is a contiguous (row range) x (column range).  A dense leaf is an m x n
+// column-major tile; a low-rank leaf stores U (m x kcap) then V (n x kcap), block ~ U V^T.
+//   k_near  : one CTA per inadmissible leaf, one thread per disjoint triangle pair, touching pairs
+//             queued in shared memory and evaluated one warp per pair (Sauter-Schwab rules).
+//   k_aca   : one CTA per admissible leaf; residual rows / columns generated on demand, entry by
+//             entry, from the vertex -> triangle fans with the regular rule.
+//   k_hmv_* : leaf-parallel matvec, HBM-bound streaming of the pool.
+#include "hmat.cuh"
+
+#include <algorithm>
+#include <map>
+
+#include "pair.cuh"
+
+namespace cnld {
+
+namespace {
+
+__device__ __forceinline__ void red_add(cplx *p, cplx v) {
+  atomicAdd(reinterpret_cast<double *>(p), v.x);
+  atomicAdd(reinterpret_cast<double *>(p) + 1, v.y);
+}
+
+constexpr int NEAR_THREADS = 128;
+constexpr int NEAR_QCAP = 3072;
+
+template <int NQ, bool CPLXK>
+__global__ void __launch_bounds__(NEAR_THREADS)
+k_near(const HLeafDev *__restrict__ leaves, const uint *__restrict__ near_ids, const __grid_constant__ RegRule R,
+       const SingTables tab, const double *__restrict__ x, const uint *__restrict__ tri,
+       const double *__restrict__ qp, const double *__restrict__ g, const uint *__restrict__ pos,
+       const uint *__restrict__ ctri_ptr, const uint *__restrict__ ctri, double kr, double ki, cplx *pool,
+       uint *err) {
+  __shared__ uint2 queue[NEAR_QCAP];
+  __shared__ uint qn;
+  const HLeafDev L = leaves[near_ids[blockIdx.x]];
+  const uint *rt = ctri + ctri_ptr[L.rtl], *ct = ctri + ctri_ptr[L.ctl];
+  const uint nr = ctri_ptr[L.rtl + 1] - ctri_ptr[L.rtl], nc = ctri_ptr[L.ctl + 1] - ctri_ptr[L.ctl];
+  cplx *D = pool + L.off;
+  if (threadIdx.x == 0) qn = 0;
+  __syncthreads();
+  for (uint p = threadIdx.x; p < nr * nc; p += NEAR_THREADS) {
+    const uint t = rt[p / nc], s = ct[p % nc];
+    const uint tv[3] = {tri[3 * (size_t)t], tri[3 * (size_t)t + 1], tri[3 * (size_t)t + 2]};
+    const uint sv[3] = {tri[3 * (size_t)s], tri[3 * (size_t)s + 1], tri[3 * (size_t)s + 2]};
+    bool touch = false;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) touch |= (tv[i] == sv[j]);
+    if (touch) {
+      uint slot = atomicAdd(&qn, 1u);
+      if (slot < NEAR_QCAP) queue[slot] = make_uint2(t, s);
+      else atomicExch(err, 1u);
+      continue;
+    }
+    double xp[NQ][3];
+#pragma unroll
+    for (int a = 0; a < NQ; a++)
+#pragma unroll
+      for (int d = 0; d < 3; d++) xp[a][d] = qp[((size_t)t * NQ + a) * 3 + d];
+    cplx loc[3][3];
+    regular_pair<NQ, CPLXK>(xp, qp + (size_t)s * NQ * 3, R, kr, ki, loc);
+    const double sc = g[t] * g[s] * INV4PI;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      uint pr = pos[tv[i]] - L.r0;
+      if (pr >= L.m) continue;
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        uint pc = pos[sv[j]] - L.c0;
+        if (pc < L.n) red_add(D + (size_t)pc * L.m + pr, make_double2(loc[i][j].x * sc, loc[i][j].y * sc));
+      }
+    }
+  }
+  __syncthreads();
+  const uint nq = min(qn, (uint)NEAR_QCAP);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint e = warp; e < nq; e += NEAR_THREADS / 32) {
+    const uint t = queue[e].x, s = queue[e].y;
+    uint tv[3] = {tri[3 * (size_t)t], tri[3 * (size_t)t + 1], tri[3 * (size_t)t + 2]};
+    uint sv[3] = {tri[3 * (size_t)s], tri[3 * (size_t)s + 1], tri[3 * (size_t)s + 2]};
+    // shared vertices to the front, same slot in both (select_quadrature_singquad2d)
+    uint tp[3], sp[3], c = 0;
+    bool tu[3] = {false, false, false}, su[3] = {false, false, false};
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        if (tv[i] == sv[j]) { tp[c] = i; sp[c] = j; tu[i] = su[j] = true; c++; break; }
+    uint a = c, b = c;
+    for (int i = 0; i < 3; i++) { if (!tu[i]) tp[a++] = i; if (!su[i]) sp[b++] = i; }
+    uint rv[3] = {tv[tp[0]], tv[tp[1]], tv[tp[2]]}, cv[3] = {sv[sp[0]], sv[sp[1]], sv[sp[2]]};
+    double V[6][3];
+#pragma unroll
+    for (int v = 0; v < 3; v++)
+#pragma unroll
+      for (int d = 0; d < 3; d++) { V[v][d] = x[3 * (size_t)rv[v] + d]; V[3 + v][d] = x[3 * (size_t)cv[v] + d]; }
+    double acc[18];
+    singular_pair_warp<CPLXK>(V, tab, c, kr, ki, lane, acc);
+    if (lane == 0) {
+      const double sc = g[t] * g[s] * INV4PI;
+      for (int i = 0; i < 3; i++) {
+        uint pr = pos[rv[i]] - L.r0;
+        if (pr >= L.m) continue;
+        for (int j = 0; j < 3; j++) {
+          uint pc = pos[cv[j]] - L.c0;
+          if (pc < L.n) red_add(D + (size_t)pc * L.m + pr, make_double2(acc[2 * (3 * i + j)] * sc, acc[2 * (3 * i + j) + 1] * sc));
+        }
+      }
+    }
+  }
+}
+
+// Galerkin entry Z[vi, vj] for well separated vertices (every triangle pair disjoint):
+// sum over the two triangle fans with the regular rule (bem->nearfield_far)
+template <int NQ, bool CPLXK>
+__device__ cplx far_entry(uint vi, uint vj, const RegRule &R, const double *__restrict__ qp,
+                          const double *__restrict__ g, const uint *__restrict__ v2t_ptr,
+                          const uint *__restrict__ v2t, double kr, double ki) {
+  cplx sum = make_double2(0.0, 0.0);
+  for (uint a = v2t_ptr[vi]; a < v2t_ptr[vi + 1]; a++) {
+    const uint t = v2t[a] >> 2, li = v2t[a] & 3;
+    double xp[NQ][3];
+#pragma unroll
+    for (int p = 0; p < NQ; p++)
+#pragma unroll
+      for (int d = 0; d < 3; d++) xp[p][d] = qp[((size_t)t * NQ + p) * 3 + d];
+    for (uint b = v2t_ptr[vj]; b < v2t_ptr[vj + 1]; b++) {
+      const uint s = v2t[b] >> 2, lj = v2t[b] & 3;
+      const double *yq = qp + (size_t)s * NQ * 3;
+      cplx acc = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int p = 0; p < NQ; p++) {
+        cplx ap = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+          double dx = xp[p][0] - yq[3 * q], dy = xp[p][1] - yq[3 * q + 1], dz = xp[p][2] - yq[3 * q + 2];
+          cplx kv = helmholtz<CPLXK>(dx * dx + dy * dy + dz * dz, kr, ki);
+          double wq = R.w[q] * R.phi[q][lj];
+          ap.x = fma(wq, kv.x, ap.x);
+          ap.y = fma(wq, kv.y, ap.y);
+        }
+        double wp = R.w[p] * R.phi[p][li];
+        acc.x = fma(wp, ap.x, acc.x);
+        acc.y = fma(wp, ap.y, acc.y);
+      }
+      double sc = g[t] * g[s] * INV4PI;
+      sum.x = fma(acc.x, sc, sum.x);
+      sum.y = fma(acc.y, sc, sum.y);
+    }
+  }
+  return sum;
+}
+
+constexpr int ACA_THREADS = 256;
+
+// block-wide argmax of (value, index); result broadcast to all threads
+__device__ void block_argmax(double &val, uint &idx, double *sv, uint *si) {
+  for (int off = 16; off > 0; off >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, val, off);
+    uint oi = __shfl_xor_sync(0xffffffffu, idx, off);
+    if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) { sv[warp] = val; si[warp] = idx; }
+  __syncthreads();
+  val = sv[0]; idx = si[0];
+  for (int w = 1; w < ACA_THREADS / 32; w++)
+    if (sv[w] > val || (sv[w] == val && si[w] < idx)) { val = sv[w]; idx = si[w]; }
+}
+__device__ double block_sum(double v, double *sv) {
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sv[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < ACA_THREADS / 32; w++) s += sv[w];
+  return s;
+}
+
+template <int NQ, bool CPLXK>
+__global__ void __launch_bounds__(ACA_THREADS)
+k_aca(HLeafDev *leaves, const uint *__restrict__ far_ids, const __grid_constant__ RegRule R,
+      const double *__restrict__ qp, const double *__restrict__ g, const uint *__restrict__ perm,
+      const uint *__restrict__ v2t_ptr, const uint *__restrict__ v2t, double kr, double ki, double accur,
+      cplx *pool, unsigned char *flags) {
+  __shared__ double s_val[ACA_THREADS / 32];
+  __shared__ uint s_idx[ACA_THREADS / 32];
+  const uint lid = far_ids[blockIdx.x];
+  const HLeafDev L = leaves[lid];
+  const uint m = L.m, n = L.n, kcap = L.kcap;
+  cplx *U = pool + L.off, *V = U + (size_t)m * kcap;
+  unsigned char *rused = flags + L.foff, *cused = rused + m;
+  const uint *ridx = perm + L.r0, *cidx = perm + L.c0;
+  for (uint i = threadIdx.x; i < m + n; i += ACA_THREADS) rused[i] = 0;
+  __syncthreads();
+  uint k = 0, ik = 0;
+  double start = 0.0;
+  while (k < kcap) {
+    // residual row ik -> V[:, k]
+    const uint vi = ridx[ik];
+    double best = -1.0;
+    uint bj = 0xffffffffu;
+    for (uint j = threadIdx.x; j < n; j += ACA_THREADS) {
+      cplx r = far_entry<NQ, CPLXK>(vi, cidx[j], R, qp, g, v2t_ptr, v2t, kr, ki);
+      for (uint l = 0; l < k; l++) cfms(r, U[(size_t)l * m + ik], V[(size_t)l * n + j]);
+      V[(size_t)k * n + j] = r;
+      double a = r.x * r.x + r.y * r.y;
+      if (!cused[j] && a > best) { best = a; bj = j; }
+    }
+    if (threadIdx.x == 0) rused[ik] = 1;
+    block_argmax(best, bj, s_val, s_idx);
+    if (!(best > 0.0)) {
+      // zero residual row: continue with the first unused row, if any
+      double nb = -1.0;
+      uint nx = 0xffffffffu;
+      for (uint i = threadIdx.x; i < m; i += ACA_THREADS)
+        if (!rused[i] && i < nx) { nx = i; nb = 1.0; }
+      // argmax breaks ties towards the smaller index -> picks the smallest unused row
+      block_argmax(nb, nx, s_val, s_idx);
+      if (!(nb > 0.0)) break;
+      ik = nx;
+      continue;
+    }
+    const uint jk = bj;
+    const cplx piv = cinv(V[(size_t)k * n + jk]);
+    __syncthreads();
+    double nv2 = 0.0;
+    for (uint j = threadIdx.x; j < n; j += ACA_THREADS) {
+      cplx v = cmul(V[(size_t)k * n + j], piv);
+      V[(size_t)k * n + j] = v;
+      nv2 += v.x * v.x + v.y * v.y;
+    }
+    if (threadIdx.x == 0) cused[jk] = 1;
+    // residual column jk -> U[:, k]
+    const uint vj = cidx[jk];
+    double nu2 = 0.0;
+    best = -1.0;
+    uint bi = 0xffffffffu;
+    __syncthreads();
+    for (uint i = threadIdx.x; i < m; i += ACA_THREADS) {
+      cplx c = far_entry<NQ, CPLXK>(ridx[i], vj, R, qp, g, v2t_ptr, v2t, kr, ki);
+      for (uint l = 0; l < k; l++) cfms(c, U[(size_t)l * m + i], V[(size_t)l * n + jk]);
+      U[(size_t)k * m + i] = c;
+      double a = c.x * c.x + c.y * c.y;
+      nu2 += a;
+      if (!rused[i] && a > best) { best = a; bi = i; }
+    }
+    nu2 = block_sum(nu2, s_val);
+    nv2 = block_sum(nv2, s_val);
+    block_argmax(best, bi, s_val, s_idx);
+    const double e = sqrt(nu2) * sqrt(nv2);
+    if (k == 0) start = e;
+    k++;
+    if (e <= accur * start) break;
+    if (bi == 0xffffffffu) break;
+    ik = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) leaves[lid].k = k;
+}
+
+// ---- matvec: y_perm += alpha * Z * x_perm over the leaves --------------------------------
+constexpr int MV_THREADS = 128;
+
+__global__ void k_permute_in(uint n, uint nrhs, const uint *__restrict__ perm, const cplx *__restrict__ x,
+                             cplx *xp) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * nrhs) return;
+  uint r = i / n, p = i % n;
+  xp[i] = x[(size_t)r * n + perm[p]];
+}
+__global__ void k_permute_out(uint n, uint nrhs, const uint *__restrict__ perm, cplx alpha, const cplx *__restrict__ yp,
+                              cplx *y) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * nrhs) return;
+  uint r = i / n, p = i % n;
+  cplx v = cmul(alpha, yp[i]);
+  cplx *d = y + (size_t)r * n + perm[p];
+  d->x += v.x;
+  d->y += v.y;
+}
+
+// one CTA per leaf; vectors in cluster order, nrhs right-hand sides (stride n)
+__global__ void __launch_bounds__(MV_THREADS)
+k_hmv_leaf(const HLeafDev *__restrict__ leaves, uint ntot, const cplx *__restrict__ pool, const cplx *__restrict__ xp,
+           cplx *yp, uint nrhs) {
+  __shared__ cplx s_t[64];
+  const HLeafDev L = leaves[blockIdx.x];
+  const cplx *base = pool + L.off;
+  for (uint r = 0; r < nrhs; r++) {
+    const cplx *x = xp + (size_t)r * ntot + L.c0;
+    cplx *y = yp + (size_t)r * ntot + L.r0;
+    if (!L.adm) {
+      for (uint i = threadIdx.x; i < L.m; i += MV_THREADS) {
+        cplx s = make_double2(0.0, 0.0);
+        for (uint j = 0; j < L.n; j++) cfma(s, base[(size_t)j * L.m + i], x[j]);
+        red_add(y + i, s);
+      }
+    } else {
+      const cplx *U = base, *V = base + (size_t)L.m * L.kcap;
+      for (uint l0 = 0; l0 < L.k; l0 += 64) {
+        const uint kk = min(64u, L.k - l0);
+        __syncthreads();
+        // t[l] = V[:, l] . x  -- one warp per column l
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (uint l = warp; l < kk; l += MV_THREADS / 32) {
+          cplx s = make_double2(0.0, 0.0);
+          const cplx *v = V + (size_t)(l0 + l) * L.n;
+          for (uint j = lane; j < L.n; j += 32) cfma(s, v[j], x[j]);
+          for (int off = 16; off > 0; off >>= 1) {
+            s.x += __shfl_xor_sync(0xffffffffu, s.x, off);
+            s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
+          }
+          if (lane == 0) s_t[l] = s;
+        }
+        __syncthreads();
+        for (uint i = threadIdx.x; i < L.m; i += MV_THREADS) {
+          cplx s = make_double2(0.0, 0.0);
+          for (uint l = 0; l < kk; l++) cfma(s, U[(size_t)(l0 + l) * L.m + i], s_t[l]);
+          red_add(y + i, s);
+        }
+      }
+    }
+  }
+}
+
+__global__ void k_expand(const HLeafDev *__restrict__ leaves, const cplx *__restrict__ pool,
+                         const uint *__restrict__ perm, cplx *Z, size_t ld) {
+  const HLeafDev L = leaves[blockIdx.x];
+  const cplx *base = pool + L.off;
+  for (size_t e = threadIdx.x; e < (size_t)L.m * L.n; e += blockDim.x) {
+    uint i = e % L.m, j = e / L.m;
+    cplx v;
+    if (!L.adm) v = base[e];
+    else {
+      v = make_double2(0.0, 0.0);
+      const cplx *U = base, *V = base + (size_t)L.m * L.kcap;
+      for (uint l = 0; l < L.k; l++) cfma(v, U[(size_t)l * L.m + i], V[(size_t)l * L.n + j]);
+    }
+    Z[(size_t)perm[L.c0 + j] * ld + perm[L.r0 + i]] = v;
+  }
+}
+
+template <typename T>
+int to_device(T *&d, const std::vector<T> &h) {
+  CNLD_CK(cudaMalloc(&d, sizeof(T) * (h.size() ? h.size() : 1)));
+  if (!h.empty()) CNLD_CK(cudaMemcpy(d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+}  // namespace
+
+int hmat_create(HMat &H, const BemDev &bem, const double *hx, const uint *htri, uint clf, double eta, int admis,
+                bool strict, uint kmax) {
+  H.bem = &bem;
+  H.n = bem.nv;
+  H.kmax = kmax;
+  build_vertex_cluster_tree(bem.nv, bem.nt, hx, htri, clf, H.tree);
+  build_block_leaves(H.tree, eta, (Admis)admis, strict, H.blocks);
+  // cluster -> triangles touching it (only for clusters of inadmissible leaves)
+  std::vector<uint> vstart(bem.nv + 1, 0), vadj(3 * (size_t)bem.nt), v2t(3 * (size_t)bem.nt);
+  for (size_t i = 0; i < 3 * (size_t)bem.nt; i++) vstart[htri[i] + 1]++;
+  for (uint v = 0; v < bem.nv; v++) vstart[v + 1] += vstart[v];
+  {
+    std::vector<uint> fill(vstart.begin(), vstart.end() - 1);
+    for (uint t = 0; t < bem.nt; t++)
+      for (uint d = 0; d < 3; d++) { uint e = fill[htri[3 * (size_t)t + d]]++; vadj[e] = t; v2t[e] = t * 4 + d; }
+  }
+  std::map<uint, uint> list_of;  // cluster id -> triangle list id
+  std::vector<uint> ctri_ptr(1, 0), ctri;
+  auto tri_list = [&](uint c) -> uint {
+    auto it = list_of.find(c);
+    if (it != list_of.end()) return it->second;
+    const ClusterNode &C = H.tree.node[c];
+    std::vector<uint> ts;
+    for (uint i = 0; i < C.size; i++) {
+      uint v = H.tree.perm[C.start + i];
+      for (uint e = vstart[v]; e < vstart[v + 1]; e++) ts.push_back(vadj[e]);
+    }
+    std::sort(ts.begin(), ts.end());
+    ts.erase(std::unique(ts.begin(), ts.end()), ts.end());
+    ctri.insert(ctri.end(), ts.begin(), ts.end());
+    ctri_ptr.push_back((uint)ctri.size());
+    uint id = (uint)ctri_ptr.size() - 2;
+    list_of[c] = id;
+    return id;
+  };
+  H.leaf.clear();
+  std::vector<uint> near_ids, far_ids;
+  size_t off = 0, foff = 0;
+  for (size_t b = 0; b < H.blocks.size(); b++) {
+    const BlockLeaf &B = H.blocks[b];
+    const ClusterNode &Rn = H.tree.node[B.rc], &Cn = H.tree.node[B.cc];
+    HLeafDev L;
+    memset(&L, 0, sizeof(L));
+    L.r0 = Rn.start; L.m = Rn.size; L.c0 = Cn.start; L.n = Cn.size;
+    L.adm = B.admissible ? 1 : 0;
+    L.off = off;
+    if (B.admissible) {
+      L.kcap = std::min(std::min(L.m, L.n), kmax);
+      L.foff = foff;
+      foff += (size_t)L.m + L.n;
+      off += (size_t)(L.m + L.n) * L.kcap;
+      far_ids.push_back((uint)b);
+    } else {
+      L.rtl = tri_list(B.rc);
+      L.ctl = tri_list(B.cc);
+      off += (size_t)L.m * L.n;
+      near_ids.push_back((uint)b);
+    }
+    H.leaf.push_back(L);
+  }
+  H.pool_size = off;
+  H.nnear = (uint)near_ids.size();
+  H.nfar = (uint)far_ids.size();
+  H.near_entries = 0;
+  for (uint b : near_ids) H.near_entries += (size_t)H.leaf[b].m * H.leaf[b].n;
+  CNLD_CK(cudaSetDevice(bem.device));
+  if (to_device(H.d_leaf, H.leaf) || to_device(H.d_near, near_ids) || to_device(H.d_far, far_ids) ||
+      to_device(H.d_perm, H.tree.perm) || to_device(H.d_pos, H.tree.pos) || to_device(H.d_ctri_ptr, ctri_ptr) ||
+      to_device(H.d_ctri, ctri) || to_device(H.d_v2t_ptr, vstart) || to_device(H.d_v2t, v2t))
+    return -1;
+  CNLD_CK(cudaMalloc(&H.d_pool, sizeof(cplx) * (off ? off : 1)));
+  CNLD_CK(cudaMalloc(&H.d_flags, foff ? foff : 1));
+  CNLD_CK(cudaMalloc(&H.d_err, sizeof(uint)));
+  return 0;
+}
+
+void hmat_free(HMat &H) {
+  cudaFree(H.d_leaf); cudaFree(H.d_near); cudaFree(H.d_far); cudaFree(H.d_perm); cudaFree(H.d_pos);
+  cudaFree(H.d_ctri_ptr); cudaFree(H.d_ctri); cudaFree(H.d_v2t_ptr); cudaFree(H.d_v2t); cudaFree(H.d_pool);
+  cudaFree(H.d_flags); cudaFree(H.d_err); cudaFree(H.d_xp); cudaFree(H.d_yp);
+  H = HMat();
+}
+
+template <int NQ>
+static int assemble_nq(cudaStream_t st, HMat &H, double kr, double ki, double accur) {
+  const BemDev &b = *H.bem;
+  if (H.nnear) {
+    if (ki != 0.0)
+      k_near<NQ, true><<<H.nnear, NEAR_THREADS, 0, st>>>(H.d_leaf, H.d_near, b.rule, b.sing, b.x, b.t, b.qp, b.g,
+                                                          H.d_pos, H.d_ctri_ptr, H.d_ctri, kr, ki, H.d_pool, H.d_err);
+    else
+      k_near<NQ, false><<<H.nnear, NEAR_THREADS, 0, st>>>(H.d_leaf, H.d_near, b.rule, b.sing, b.x, b.t, b.qp, b.g,
+                                                           H.d_pos, H.d_ctri_ptr, H.d_ctri, kr, ki, H.d_pool, H.d_err);
+    CNLD_CK_LAUNCH();
+  }
+  if (H.nfar) {
+    if (ki != 0.0)
+      k_aca<NQ, true><<<H.nfar, ACA_THREADS, 0, st>>>(H.d_leaf, H.d_far, b.rule, b.qp, b.g, H.d_perm, H.d_v2t_ptr,
+                                                       H.d_v2t, kr, ki, accur, H.d_pool, H.d_flags);
+    else
+      k_aca<NQ, false><<<H.nfar, ACA_THREADS, 0, st>>>(H.d_leaf, H.d_far, b.rule, b.qp, b.g, H.d_perm, H.d_v2t_ptr,
+                                                        H.d_v2t, kr, ki, accur, H.d_pool, H.d_flags);
+    CNLD_CK_LAUNCH();
+  }
+  return 0;
+}
+
+int hmat_assemble(cudaStream_t st, HMat &H, double kr, double ki, double accur) {
+  CNLD_CK(cudaMemsetAsync(H.d_pool, 0, sizeof(cplx) * H.pool_size, st));
+  CNLD_CK(cudaMemsetAsync(H.d_err, 0, sizeof(uint), st));
+  int rc;
+  switch (H.bem->nq) {
+  case 1: rc = assemble_nq<1>(st, H, kr, ki, accur); break;
+  case 4: rc = assemble_nq<4>(st, H, kr, ki, accur); break;
+  case 9: rc = assemble_nq<9>(st, H, kr, ki, accur); break;
+  default: set_error("H-matrix path supports q_reg <= 3"); return -1;
+  }
+  if (rc) return rc;
+  uint err = 0;
+  CNLD_CK(cudaMemcpyAsync(&err, H.d_err, sizeof(uint), cudaMemcpyDeviceToHost, st));
+  CNLD_CK(cudaStreamSynchronize(st));
+  if (err) { set_error("H-matrix near-field: touching-pair queue overflow (leaf too large; raise NEAR_QCAP)"); return -1; }
+  H.assembled = true;
+  return 0;
+}
+
+// device vectors in ORIGINAL DOF order, nrhs of them with stride n:  y += alpha * Z x
+int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y, uint nrhs) {
+  if (!H.assembled) { set_error("H-matrix has not been assembled"); return -1; }
+  if (H.vec_cap < nrhs) {
+    cudaFree(H.d_xp); cudaFree(H.d_yp);
+    H.d_xp = H.d_yp = nullptr;
+    CNLD_CK(cudaMalloc(&H.d_xp, sizeof(cplx) * (size_t)H.n * nrhs));
+    CNLD_CK(cudaMalloc(&H.d_yp, sizeof(cplx) * (size_t)H.n * nrhs));
+    H.vec_cap = nrhs;
+  }
+  const size_t tot = (size_t)H.n * nrhs;
+  const unsigned gb = (unsigned)((tot + 255) / 256);
+  k_permute_in<<<gb, 256, 0, st>>>(H.n, nrhs, H.d_perm, d_x, H.d_xp);
+  CNLD_CK_LAUNCH();
+  CNLD_CK(cudaMemsetAsync(H.d_yp, 0, sizeof(cplx) * tot, st));
+  k_hmv_leaf<<<(unsigned)H.leaf.size(), MV_THREADS, 0, st>>>(H.d_leaf, H.n, H.d_pool, H.d_xp, H.d_yp, nrhs);
+  CNLD_CK_LAUNCH();
+  k_permute_out<<<gb, 256, 0, st>>>(H.n, nrhs, H.d_perm, alpha, H.d_yp, d_y);
+  CNLD_CK_LAUNCH();
+  return 0;
+}
+
+int hmat_expand(cudaStream_t st, HMat &H, cplx *d_Z, size_t ld) {
+  if (!H.assembled) { set_error("H-matrix has not been assembled"); return -1; }
+  k_expand<<<(unsigned)H.leaf.size(), 256, 0, st>>>(H.d_leaf, H.d_pool, H.d_perm, d_Z, ld);
+  CNLD_CK_LAUNCH();
+  return 0;
+}
+
+int hmat_fetch_leaves(HMat &H) {
+  CNLD_CK(cudaMemcpy(H.leaf.data(), H.d_leaf, sizeof(HLeafDev) * H.leaf.size(), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // namespace cnld

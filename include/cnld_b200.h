@@ -146,6 +146,42 @@ int cnld_b200_pressure(cnld_ctx *ctx, const double *obs, cnld_uint nobs, const d
                        cnld_uint nk, double c, double rho, const cnld_field *disp,
                        cnld_uint nsrc, cnld_field *p);
 
+/* ---- H-matrix path (arrays too large to factor densely) ---------------------------------
+ * Replaces build_bem3d_cluster(bem, clf, LINEAR) (include/bem3d.h:1493), build_strict_block /
+ * build_nonstrict_block(root, root, &eta, admissible_*) (include/block.h:216-248, :78-140),
+ * build_from_block_hmatrix (include/hmatrix.h:358), setup_hmatrix_aprx_paca_bem3d +
+ * assemble_bem3d_hmatrix (include/bem3d.h:2627, :3056), addeval_hmatrix_avector
+ * (include/hmatrix.h:419) and the Krylov solve (include/krylovsolvers.h:283;
+ * scratch/freq_resp_db_krylov.py:38-79).  Call sites: cnld/compressed_formats.py:652-703. */
+typedef struct cnld_hmat cnld_hmat;
+/* admis: 0 = '2' (max diam <= eta dist, euclidean), 1 = 'max', 2 = 'sphere', 3 = '2min';
+ * kmax: rank capacity of a low-rank leaf (0 -> 64). */
+cnld_hmat *cnld_b200_hmat_create(cnld_ctx *ctx, cnld_uint clf, double eta, int admis, int strict,
+                                 cnld_uint kmax);
+void cnld_b200_hmat_destroy(cnld_hmat *h);
+/* out[8]: clusters, leaves, admissible leaves, inadmissible leaves, pool capacity (entries),
+ * stored entries (dense + k(m+n), after assembly), max rank, n */
+int cnld_b200_hmat_info(cnld_hmat *h, double *out);
+/* tree export (any pointer may be NULL): perm[n] (cluster order -> DOF), per cluster son0/son1
+ * (-1 = leaf), start/size into perm, bmin/bmax[.][3]; per leaf row/col cluster, admissibility, rank */
+int cnld_b200_hmat_tree(cnld_hmat *h, cnld_uint *perm, int *son0, int *son1, cnld_uint *start,
+                        cnld_uint *size, double *bmin, double *bmax, cnld_uint *leaf_rc,
+                        cnld_uint *leaf_cc, uint8_t *leaf_adm, cnld_uint *leaf_rank);
+/* fill every leaf for wavenumber k: dense near field, partial-pivot ACA (accuracy eps_aca) far field */
+int cnld_b200_hmat_assemble(cnld_hmat *h, double k_re, double k_im, double eps_aca);
+/* y[r][:] += alpha * Z x[r][:] for nrhs host vectors of length n (original DOF order) */
+int cnld_b200_hmat_matvec(cnld_hmat *h, cnld_field alpha, const cnld_field *x, cnld_field *y,
+                          cnld_uint nrhs);
+int cnld_b200_hmat_todense(cnld_hmat *h, cnld_field *Z, cnld_uint ld);
+/* generate_db.process with the H-matrix + GMRES path: per frequency assemble Z_H(k), then solve
+ * (MBK + (-2 rho w^2) Z_H) x = F[:, s] for all source patches by left-preconditioned restarted
+ * GMRES (block-diagonal MBK^-1), `batch` right-hand sides in lock-step; residual tolerance tol.
+ * Outputs as cnld_b200_sweep_run; iters[nf][P] (nullable) = Arnoldi steps per right-hand side. */
+int cnld_b200_hsweep_run(cnld_ctx *ctx, cnld_hmat *h, const double *freqs, cnld_uint nf, double c,
+                         double rho, double eps_aca, double tol, cnld_uint restart,
+                         cnld_uint maxiter, cnld_uint batch, cnld_field *x_patch,
+                         cnld_field *x_node, cnld_uint *iters, double *t_freq);
+
 /* ---- microbenchmarks used for roofline denominators ----------------------- */
 /* FP64 DMMA ZGEMM C(m x n) -= A(m x k) B(k x n) on device-resident random data;
  * returns achieved TFLOP/s (8 m n k flop) averaged over reps. */

@@ -1,0 +1,97 @@
+"""GPU parity of the H-matrix path: trees identical to the oracle's, dense leaves exact, ACA leaves
+and the H-matvec within eps_aca of the dense operator, GMRES sweep against the dense-LU sweep."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300)
+
+
+@pytest.fixture(scope='module')
+def L():
+    from cnld import _lib
+    assert _lib.device_count() > 0
+    return _lib
+
+
+@pytest.mark.parametrize('nelem,refn,clf,eta,strict', [((2, 2), 6, 16, 0.8, True), ((2, 1), 7, 8, 1.2, False)])
+def test_trees_match_oracle(L, po, nelem, refn, clf, eta, strict):
+    am = po.array_mesh(po.matrix_array(nelem=nelem), refn)
+    ctx = L.Context(am.vertices, am.triangles)
+    H = L.HMatrix(ctx, clf=clf, eta=eta, strict=strict)
+    t = H.tree()
+    ct = po.ClusterTree(am, clf)
+    assert np.array_equal(t['perm'], ct.perm)
+    assert np.array_equal(t['son0'], ct.son0) and np.array_equal(t['son1'], ct.son1)
+    assert np.array_equal(t['start'], ct.start) and np.array_equal(t['size'], ct.size)
+    assert np.array_equal(t['bmin'], ct.bmin) and np.array_equal(t['bmax'], ct.bmax)
+    rc, cc, adm = po.build_block(ct, eta, strict)
+    assert np.array_equal(t['leaf_rc'], rc) and np.array_equal(t['leaf_cc'], cc)
+    assert np.array_equal(t['leaf_adm'].astype(bool), adm)
+    # the leaves tile the matrix exactly once
+    cover = np.zeros((am.nvertices, am.nvertices), dtype=np.int32)
+    for r, c in zip(rc, cc):
+        cover[np.ix_(ct.idx(r), ct.idx(c))] += 1
+    assert cover.min() == 1 and cover.max() == 1
+    H.close()
+    ctx.close()
+
+
+@pytest.mark.parametrize('eps', [1e-2, 1e-4, 1e-6])
+def test_hmatrix_vs_dense_and_oracle(L, po, eps):
+    am = po.array_mesh(po.matrix_array(nelem=(2, 2)), 6)
+    k = 2 * np.pi * 5e6 / 1500
+    ctx = L.Context(am.vertices, am.triangles)
+    Z = ctx.assemble_z(k)
+    H = L.HMatrix(ctx, clf=16, eta=0.8, strict=True)
+    H.assemble(k, eps)
+    Zh = H.todense()
+    t = H.tree()
+    ct = po.ClusterTree(am, 16)
+    # inadmissible leaves reproduce the dense assembly (same rules, different summation order)
+    for r, c, a in zip(t['leaf_rc'], t['leaf_cc'], t['leaf_adm']):
+        if not a:
+            ix = np.ix_(ct.idx(r), ct.idx(c))
+            assert np.abs(Zh[ix] - Z[ix]).max() / np.abs(Z).max() < 1e-10
+    err = _rel(Zh, Z)
+    assert err < 0.2 * eps, err
+    Ho = po.HMatrix(am, k, clf=16, eta=0.8, eps_aca=eps)
+    # same pivoting rule -> same ranks and (up to rounding) the same low-rank factors
+    ranks_o = np.array([d[0].shape[1] if isinstance(d, tuple) else 0 for _, _, d in Ho.leaves])
+    assert np.array_equal(t['leaf_rank'], ranks_o)
+    assert _rel(Zh, Ho.todense()) < 1e-9
+    x = np.random.default_rng(0).standard_normal((am.nvertices, 3)) + 1j * np.random.default_rng(1).standard_normal((am.nvertices, 3))
+    assert _rel(H.matvec(x), Zh @ x) < 1e-12
+    assert _rel(H.matvec(x[:, 0], alpha=2 - 1j), (2 - 1j) * (Zh @ x[:, 0])) < 1e-12
+    info = H.info()
+    assert info['stored'] == Ho.size_entries
+    H.close()
+    ctx.close()
+
+
+def test_gmres_sweep_vs_dense_lu(L, po):
+    from scipy.linalg import block_diag
+    arr = po.matrix_array(nelem=(2, 2))
+    am = po.array_mesh(arr, 5)
+    blocks = po.array_fem(arr, 5)
+    ctx = L.Context(am.vertices, am.triangles)
+    ctx.set_mbk(block_diag(*[b[0] for b in blocks]), block_diag(*[b[1] for b in blocks]), block_diag(*[b[2] for b in blocks]))
+    ctx.set_loads(block_diag(*[b[3] for b in blocks]), block_diag(*[b[4] for b in blocks]), am.on_boundary)
+    freqs = np.array([0.0, 2e6, 9e6, 30e6])
+    xp, xn, _ = ctx.sweep(freqs)
+    H = L.HMatrix(ctx, clf=16, eta=0.8, strict=True)
+    # tight ACA + tight GMRES: the two solvers must agree to the north-star 1e-6
+    xph, xnh, it, t = H.sweep(freqs, eps_aca=1e-8, tol=1e-10, restart=40, maxiter=400, batch=16)
+    for i in range(len(freqs)):
+        assert _rel(xnh[i], xn[i]) < 1e-6, (freqs[i], _rel(xnh[i], xn[i]))
+        assert _rel(xph[i], xp[i]) < 1e-6
+    assert it.max() < 400
+    # the reference's default eps_aca = 1e-2: tolerance max(1e-6, eps_aca)
+    xph2, xnh2, it2, _ = H.sweep(freqs[1:3], eps_aca=1e-2, tol=1e-6, batch=36)
+    for i in range(2):
+        assert _rel(xnh2[i], xn[i + 1]) < 1e-2
+    H.close()
+    ctx.close()
