@@ -1,0 +1,3 @@
+/* Shim so that `cdef extern from 'amatrix.h'` in cnl-dyna's cnld/h2lib/_amatrix.pxd resolves against
+ * libcnld_b200 instead of H2Lib: put include/h2lib_compat first on the include path. */
+#include "../cnld_b200_h2lib.h"
