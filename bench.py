@@ -252,7 +252,10 @@ def main():
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                          'frac': (ach / fp64_peak) if ach else None, 'traffic': None,
-                         'kernel': 'zgemm_kernel (DMMA.8x8x4 trailing update of the LU)',
+                         'kernel': 'zgemm3m_kernel (DMMA.8x8x4 rank-512 trailing updates of the LU; 3M complex '
+                                   'product = 6 m n k executed real flops per launch, i.e. 8 m n k conventional '
+                                   'complex-GEMM flops at 4/3 of this rate)',
+                         'achieved_conventional_8mnk': (ach * 4.0 / 3.0) if ach else None,
                          'launches_timed': int(klaunch),
                          'peak_source': 'FP64 FMA-pipe peak measured live with cnld_b200_bench_dfma '
                                         '(MEASURED_PEAKS.json carries no FP64 figure; DMMA and DFMA share it)'},

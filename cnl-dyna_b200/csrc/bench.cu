@@ -50,10 +50,10 @@ extern "C" int cnld_b200_bench_zgemm(int device, cnld_uint m, cnld_uint n, cnld_
   CNLD_CK(cudaEventCreate(&e0));
   CNLD_CK(cudaEventCreate(&e1));
   int rc = 0;
-  for (int w = 0; w < 2 && !rc; w++) rc = zgemm(0, m, n, k, -1.0, A, m, B, k, 1.0, C, m);
+  for (int w = 0; w < 2 && !rc; w++) rc = zgemm3m(0, m, n, k, -1.0, A, m, B, k, 1.0, C, m);
   if (!rc) {
     CNLD_CK(cudaEventRecord(e0, 0));
-    for (int r = 0; r < reps && !rc; r++) rc = zgemm(0, m, n, k, -1.0, A, m, B, k, 1.0, C, m);
+    for (int r = 0; r < reps && !rc; r++) rc = zgemm3m(0, m, n, k, -1.0, A, m, B, k, 1.0, C, m);
     CNLD_CK(cudaEventRecord(e1, 0));
     CNLD_CK(cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -90,3 +90,4 @@ extern "C" int cnld_b200_bench_dfma(int device, int reps, double *tflops) {
 
 extern "C" int cnld_b200_set_zgemm_variant(int v) { cnld::g_zgemm_variant = v; return 0; }
 extern "C" int cnld_b200_set_lu_outer(int v) { cnld::g_lu_outer = v; return 0; }
+extern "C" int cnld_b200_set_zgemm_3m(int v) { cnld::g_zgemm_3m = v; return 0; }

@@ -72,6 +72,11 @@ extern int g_lu_outer;
 int zgemm(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
           const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc);
 
+// same contract, 3M complex product (C must not alias A or B)
+int zgemm3m(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
+            const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc);
+extern int g_zgemm_3m;
+
 struct LuWork {
   uint n = 0, nb = 0, nblk = 0, nouter = 0, nbo = 0;
   cplx *linv = nullptr;  // [nblk][nb*nb]

@@ -157,7 +157,7 @@ int lu_trailing_stats(const LuWork &w, double *seconds, double *flops, double *l
     float ms = 0.f;
     CNLD_CK(cudaEventElapsedTime(&ms, w.pe[2 * ob], w.pe[2 * ob + 1]));
     *seconds += ms * 1e-3;
-    *flops += 8.0 * rem * rem * W;
+    *flops += (g_zgemm_3m ? 6.0 : 8.0) * rem * rem * W;  // executed real flops (3M: three real products)
     *launches += 1.0;
   }
   return 0;
@@ -195,10 +195,10 @@ int lu_factor(cudaStream_t st, LuWork &w, cplx *a, size_t lda) {
       const uint in_cols = OE - o - nbk;  // columns (and rows) left inside the outer block
       if (in_cols) {
         // block column: all rows below x remaining columns of the outer block
-        if (zgemm(st, below, in_cols, nbk, -1.0, a21, lda, a12, lda, 1.0, a22, lda)) return -1;
+        if (zgemm3m(st, below, in_cols, nbk, -1.0, a21, lda, a12, lda, 1.0, a22, lda)) return -1;
         // block row: remaining rows of the outer block x columns right of the outer block
         const uint right = n - OE;
-        if (right && zgemm(st, in_cols, right, nbk, -1.0, a21, lda, a12 + (size_t)in_cols * lda, lda, 1.0,
+        if (right && zgemm3m(st, in_cols, right, nbk, -1.0, a21, lda, a12 + (size_t)in_cols * lda, lda, 1.0,
                            a22 + (size_t)in_cols * lda, lda)) return -1;
       }
     }
@@ -206,7 +206,7 @@ int lu_factor(cudaStream_t st, LuWork &w, cplx *a, size_t lda) {
     if (rem) {
       cplx *l = a + (size_t)O * lda + OE, *u = a + (size_t)OE * lda + O, *t = a + (size_t)OE * lda + OE;
       if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * ob], st));
-      if (zgemm(st, rem, rem, W, -1.0, l, lda, u, lda, 1.0, t, lda)) return -1;
+      if (zgemm3m(st, rem, rem, W, -1.0, l, lda, u, lda, 1.0, t, lda)) return -1;
       if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * ob + 1], st));
     }
   }
@@ -225,7 +225,7 @@ int lu_solve(cudaStream_t st, const LuWork &w, const cplx *a, size_t lda, cplx *
     if (zgemm(st, nbk, nrhs, nbk, 1.0, w.linv + (size_t)b * NB * NB, NB, xb, ldx, 0.0, xb, ldx))
       return -1;
     if (rem &&
-        zgemm(st, rem, nrhs, nbk, -1.0, a + (size_t)o * lda + o + nbk, lda, xb, ldx, 1.0, xb + nbk, ldx))
+        zgemm3m(st, rem, nrhs, nbk, -1.0, a + (size_t)o * lda + o + nbk, lda, xb, ldx, 1.0, xb + nbk, ldx))
       return -1;
   }
   for (uint b = w.nblk; b-- > 0;) {  // R x = y
@@ -234,7 +234,7 @@ int lu_solve(cudaStream_t st, const LuWork &w, const cplx *a, size_t lda, cplx *
     cplx *xb = x + o;
     if (zgemm(st, nbk, nrhs, nbk, 1.0, w.uinv + (size_t)b * NB * NB, NB, xb, ldx, 0.0, xb, ldx))
       return -1;
-    if (o && zgemm(st, o, nrhs, nbk, -1.0, a + (size_t)o * lda, lda, xb, ldx, 1.0, x, ldx)) return -1;
+    if (o && zgemm3m(st, o, nrhs, nbk, -1.0, a + (size_t)o * lda, lda, xb, ldx, 1.0, x, ldx)) return -1;
   }
   return 0;
 }

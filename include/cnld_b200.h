@@ -129,7 +129,7 @@ int cnld_b200_sweep_stage_times(cnld_ctx *ctx, double *out);
 
 /* Dominant-kernel timing for the roofline: when profiling is on, every trailing-update
  * ZGEMM launch of the LU is bracketed by CUDA events on its own stream.
- * out[0] = algorithmic flops (8 m n k summed), out[1] = seconds (sum of launch durations),
+ * out[0] = executed real flops (6 m n k per launch: 3M complex product), out[1] = seconds (sum of launch durations),
  * out[2] = number of launches, all over the last sweep_run*. */
 int cnld_b200_set_profile(cnld_ctx *ctx, int on);
 int cnld_b200_sweep_kernel_stats(cnld_ctx *ctx, double *out);

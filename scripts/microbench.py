@@ -4,7 +4,7 @@ from cnld import _lib
 L = _lib.lib()
 print('dfma TF', _lib.bench_dfma(5))
 for v in (0, 1):
-    L.cnld_b200_set_zgemm_variant(v)
-    for (m, n, k) in [(14736, 14736, 64), (14736, 14736, 128), (14736, 14736, 256), (14736, 14736, 512),
-                      (8192, 8192, 4096), (14736, 144, 64), (14736, 64, 64), (64, 14736, 64)]:
-        print('variant', v, (m, n, k), 'zgemm TF %.2f' % _lib.bench_zgemm(m, n, k, 3))
+    L.cnld_b200_set_zgemm_3m(v)
+    for (m, n, k) in [(14736, 14736, 64), (14736, 14736, 256), (14736, 14736, 512), (8192, 8192, 4096),
+                      (14736, 144, 64), (14736, 448, 64), (448, 14288, 64)]:
+        print('3M' if v else '4M', (m, n, k), 'zgemm "4M-equivalent" TF %.2f' % _lib.bench_zgemm(m, n, k, 3))

@@ -20,7 +20,8 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     names = []
     for h in sorted(os.listdir(os.path.join(ROOT, 'include'))):
-        names += _declared(h)
+        if h.endswith('.h'):
+            names += _declared(h)
     assert len(names) >= 20
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
