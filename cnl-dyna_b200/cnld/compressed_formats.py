@@ -207,7 +207,13 @@ class SparseFormat(BaseFormat):
 
 
 class HFormat(BaseFormat):
-    """Hierarchical format (compressed_formats.py:360-548) on libcnld_b200's H-matrix."""
+    """Hierarchical format (compressed_formats.py:360-548) on libcnld_b200's H-matrix.
+
+    The reference keeps sums and products inside the format with truncated H-arithmetic and
+    factors with an H-LU (`lrdecomp_hmatrix`, eps 1e-12).  Following the north star that
+    machinery is replaced: `H + sparse` is kept as the lazy sum it mathematically is
+    (`HSumFormat`), and `.lu()` returns an object whose `lusolve` is GMRES on the GPU H-matvec,
+    preconditioned by a sparse LU of the sparse part, to the same 1e-12 residual."""
     eps_add = 1e-12
     eps_lu = 1e-12
     eps_chol = 1e-12
@@ -216,24 +222,21 @@ class HFormat(BaseFormat):
     size = property(lambda self: _h2.getsize_hmatrix(self._mat))
 
     def _add(self, x):
-        B = _h2.clone_hmatrix(self._mat)
-        tm = _h2.new_releucl_truncmode()
-        if isinstance(x, FullFormat):
-            _h2.add_amatrix_hmatrix(1.0, False, x._mat, tm, self.eps_add, B)
-        elif isinstance(x, SparseFormat):
-            _h2.add_hmatrix(1, (x._as_hformat(self._mat))._mat, tm, self.eps_add, B)
-        elif isinstance(x, HFormat):
-            _h2.add_hmatrix(1, x._mat, tm, self.eps_add, B)
-        else:
-            return NotImplemented
-        return HFormat(B)
+        if isinstance(x, SparseFormat):
+            return HSumFormat(self, x)
+        if isinstance(x, (FullFormat, HFormat)):
+            raise NotImplementedError('truncated H-matrix arithmetic (add_hmatrix / add_amatrix_hmatrix) is replaced '
+                                      'by dense LU or GMRES on the H-matvec; add to a FullFormat instead')
+        return NotImplemented
 
     def _smul(self, x):
         # the reference multiplies by a scaled identity H-matrix with truncation (:402-409);
         # scaling the leaves directly is the same operator without the truncation error
         B = _h2.clone_hmatrix(self._mat)
         _h2.scale_hmatrix(x, B)
-        return HFormat(B)
+        out = HFormat(B)
+        out._keep = self
+        return out
 
     def _matvec(self, x):
         xv = AVector.from_array(x)
@@ -243,28 +246,59 @@ class HFormat(BaseFormat):
         return np.array(y.v)
 
     def _lu(self):
-        return HLUFormat(self)
+        return HSumFormat(self, None)._lu()
 
     def _lusolve(self, b):
         raise RuntimeError('lusolve needs the result of .lu()')
 
 
-class HLUFormat(HFormat):
-    """Result of HFormat.lu().  The reference factors the H-matrix with truncated H-arithmetic
-    (lrdecomp_hmatrix, eps_lu = 1e-12, :433-437); here `lusolve` runs GMRES on the batched
-    H-matrix matvec to the same 1e-12 residual (BASELINE.json north_star: 'a GMRES path using a
-    batched H-matrix matvec for arrays too large to factor densely')."""
+class HSumFormat(BaseFormat):
+    """H + S with S sparse (the coupled system MBK + (-2 rho w^2) Z_H of generate_db.py:59)."""
 
-    def __init__(self, h):
+    def __init__(self, h, sp):
+        self._h, self._sp = h, sp
         self._mat = h._mat
-        self._parent = h
+        self.eps_lu = h.eps_lu
+
+    rows = property(lambda self: self._h.rows)
+    cols = property(lambda self: self._h.cols)
+    size = property(lambda self: self._h.size + (self._sp.size if self._sp is not None else 0))
+
+    def _csr(self):
+        m = self._sp._mat
+        return csr_matrix((np.array(m.coeff), np.array(m.col), np.array(m.row)), shape=(m.rows, m.cols))
+
+    def _add(self, x):
+        if isinstance(x, SparseFormat) and self._sp is None:
+            return HSumFormat(self._h, x)
+        return NotImplemented
+
+    def _matvec(self, x):
+        y = self._h._matvec(x)
+        return y + self._sp._matvec(x) if self._sp is not None else y
+
+    def _lu(self):
+        out = HSumFormat(self._h, self._sp)
+        out._is_lu = True
+        if self._sp is not None:
+            from scipy.sparse.linalg import splu
+            out._prec = splu(self._csr().tocsc())
+        return out
 
     def _lusolve(self, b):
-        x = AVector(np.asarray(b).size)
-        clear_avector(x)
-        bv = AVector.from_array(b)
-        _h2.solve_gmres_hmatrix_avector(self._mat, bv, x, self.eps_lu, 2000, 200)
-        return np.array(x.v)
+        if not getattr(self, '_is_lu', False):
+            raise RuntimeError('lusolve needs the result of .lu()')
+        from scipy.sparse.linalg import LinearOperator, gmres
+        b = np.asarray(b, dtype=np.complex128).ravel()
+        n = b.size
+        A = LinearOperator((n, n), dtype=np.complex128, matvec=lambda v: self._matvec(np.asarray(v).ravel()))
+        M = None
+        if self._sp is not None:
+            M = LinearOperator((n, n), dtype=np.complex128, matvec=lambda v: self._prec.solve(np.asarray(v).ravel()))
+        x, info = gmres(A, b, rtol=self.eps_lu, atol=0.0, restart=100, maxiter=50, M=M)
+        if info != 0:
+            raise RuntimeError('failed to calculate LU decomposition')
+        return x
 
     _triangularsolve = _lusolve
 
@@ -355,6 +389,8 @@ class ZHMatrix(HFormat):
         _h2.assemble_bem3d_hmatrix(bem, broot, Z)
         self._time_assemble = timer() - start
         self._mat = Z
+        # keep the H2Lib objects alive (the reference must drop bem/broot to let its worker
+        # processes terminate, :699-709; no such constraint here)
         self._root = root
         self._broot = broot
         self._bem = bem

@@ -66,7 +66,44 @@ class _bem3d(C.Structure):
     _fields_ = [('gr', C.POINTER(_surface3d)), ('sq', C.c_void_p), ('row_basis', C.c_int),
                 ('col_basis', C.c_int), ('mass', C.POINTER(real)), ('alpha', field), ('k', field),
                 ('kernel_const', field), ('priv', C.c_void_p), ('q_regular', uint),
-                ('q_singular', uint)]
+                ('q_singular', uint), ('accur', real)]
+
+
+class _cluster(C.Structure):
+    pass
+
+
+_cluster._fields_ = [('size', uint), ('idx', C.POINTER(uint)), ('sons', uint), ('son', C.POINTER(C.POINTER(_cluster))),
+                     ('dim', uint), ('bmin', C.POINTER(real)), ('bmax', C.POINTER(real)), ('desc', uint), ('type', uint)]
+
+
+class _block(C.Structure):
+    pass
+
+
+_block._fields_ = [('rc', C.POINTER(_cluster)), ('cc', C.POINTER(_cluster)), ('a', C.c_bool),
+                   ('son', C.POINTER(C.POINTER(_block))), ('rsons', uint), ('csons', uint), ('desc', uint)]
+
+
+class _rkmatrix(C.Structure):
+    _fields_ = [('A', _amatrix), ('B', _amatrix), ('k', uint)]
+
+
+class _hmatrix(C.Structure):
+    pass
+
+
+_hmatrix._fields_ = [('rc', C.POINTER(_cluster)), ('cc', C.POINTER(_cluster)), ('r', C.POINTER(_rkmatrix)),
+                     ('f', C.POINTER(_amatrix)), ('son', C.POINTER(C.POINTER(_hmatrix))), ('rsons', uint),
+                     ('csons', uint), ('refs', uint), ('desc', uint)]
+
+
+class _truncmode(C.Structure):
+    _fields_ = [('frobenius', C.c_bool), ('absolute', C.c_bool), ('blocks', C.c_bool), ('zeta_level', real),
+                ('zeta_age', real)]
+
+
+_ADMIS = C.CFUNCTYPE(C.c_bool, C.POINTER(_cluster), C.POINTER(_cluster), C.c_void_p)
 
 
 class basisfunctionbem3d(enum.IntEnum):
@@ -120,6 +157,32 @@ def _lib_h2():
         'lrsolve_amatrix_avector': (None, [C.c_bool, P(_amatrix), P(_avector)]),
         'triangularsolve_amatrix_avector': (None, [C.c_bool, C.c_bool, C.c_bool, P(_amatrix), P(_avector)]),
         'init_h2lib': (None, [C.c_void_p, C.c_void_p]), 'uninit_h2lib': (None, []),
+        'freemem': (None, [C.c_void_p]),
+        'new_cluster': (P(_cluster), [uint, P(uint), uint, uint]), 'del_cluster': (None, [P(_cluster)]),
+        'build_bem3d_cluster': (P(_cluster), [P(_bem3d), uint, C.c_int]),
+        'new_block': (P(_block), [P(_cluster), P(_cluster), C.c_bool, uint, uint]), 'del_block': (None, [P(_block)]),
+        'build_strict_block': (P(_block), [P(_cluster), P(_cluster), C.c_void_p, C.c_void_p]),
+        'build_nonstrict_block': (P(_block), [P(_cluster), P(_cluster), C.c_void_p, C.c_void_p]),
+        'new_rkmatrix': (P(_rkmatrix), [uint, uint, uint]), 'del_rkmatrix': (None, [P(_rkmatrix)]),
+        'new_hmatrix': (P(_hmatrix), [P(_cluster), P(_cluster)]), 'del_hmatrix': (None, [P(_hmatrix)]),
+        'clear_hmatrix': (None, [P(_hmatrix)]), 'copy_hmatrix': (None, [P(_hmatrix), P(_hmatrix)]),
+        'clone_hmatrix': (P(_hmatrix), [P(_hmatrix)]), 'clonestructure_hmatrix': (P(_hmatrix), [P(_hmatrix)]),
+        'getsize_hmatrix': (C.c_size_t, [P(_hmatrix)]), 'getrows_hmatrix': (uint, [P(_hmatrix)]),
+        'getcols_hmatrix': (uint, [P(_hmatrix)]), 'build_from_block_hmatrix': (P(_hmatrix), [P(_block), uint]),
+        'addeval_hmatrix_avector': (None, [field, P(_hmatrix), P(_avector), P(_avector)]),
+        'addevalsymm_hmatrix_avector': (None, [field, P(_hmatrix), P(_avector), P(_avector)]),
+        'copy_sparsematrix_hmatrix': (None, [P(_sparsematrix), P(_hmatrix)]),
+        'identity_hmatrix': (None, [P(_hmatrix)]), 'scale_hmatrix': (None, [field, P(_hmatrix)]),
+        'add_hmatrix_amatrix': (None, [field, C.c_bool, P(_hmatrix), P(_amatrix)]),
+        'setup_hmatrix_aprx_aca_bem3d': (None, [P(_bem3d), P(_cluster), P(_cluster), P(_block), real]),
+        'setup_hmatrix_aprx_paca_bem3d': (None, [P(_bem3d), P(_cluster), P(_cluster), P(_block), real]),
+        'setup_hmatrix_aprx_hca_bem3d': (None, [P(_bem3d), P(_cluster), P(_cluster), P(_block), uint, real]),
+        'setup_hmatrix_aprx_inter_row_bem3d': (None, [P(_bem3d), P(_cluster), P(_cluster), P(_block), uint]),
+        'assemble_bem3d_hmatrix': (None, [P(_bem3d), P(_block), P(_hmatrix)]),
+        'new_truncmode': (P(_truncmode), []), 'del_truncmode': (None, [P(_truncmode)]),
+        'new_releucl_truncmode': (P(_truncmode), []),
+        'solve_gmres_amatrix_avector': (uint, [P(_amatrix), P(_avector), P(_avector), real, uint, uint]),
+        'solve_gmres_hmatrix_avector': (uint, [P(_hmatrix), P(_avector), P(_avector), real, uint, uint]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -326,6 +389,137 @@ class Bem3d(_Handle):
         return complex(k.re, k.im)
 
 
+class Cluster(_Handle):
+    """cluster.pyx: owner also frees the index array (cluster.pyx:19-22)."""
+    _del = 'del_cluster'
+
+    def __init__(self, size, idx, sons, dim):
+        super().__init__()
+        self._idx_keep = np.ascontiguousarray(idx, dtype=np.uint32)
+        self._setup(_lib_h2().new_cluster(size, self._idx_keep.ctypes.data_as(C.POINTER(uint)), sons, dim), True)
+        self._owns_idx = False
+
+    def __del__(self):
+        if getattr(self, 'ptr', None) and self.owner and _L is not None:
+            if getattr(self, '_owns_idx', True):
+                _L.freemem(C.cast(self.ptr.contents.idx, C.c_void_p))
+            _L.del_cluster(self.ptr)
+            self.ptr = None
+
+    size = property(lambda self: self.ptr.contents.size)
+    sons = property(lambda self: self.ptr.contents.sons)
+    dim = property(lambda self: self.ptr.contents.dim)
+    desc = property(lambda self: self.ptr.contents.desc)
+    type = property(lambda self: self.ptr.contents.type)
+    idx = property(lambda self: _view(self.ptr.contents.idx, (self.size,), np.uint32))
+    bmin = property(lambda self: _view(self.ptr.contents.bmin, (self.dim,), np.float64))
+    bmax = property(lambda self: _view(self.ptr.contents.bmax, (self.dim,), np.float64))
+
+    @property
+    def son(self):
+        out = []
+        for i in range(self.sons):
+            c = Cluster.wrap(self.ptr.contents.son[i], False)
+            c._parent = self
+            out.append(c)
+        return out
+
+
+class Block(_Handle):
+    _del = 'del_block'
+
+    def __init__(self, rc, cc, a, rsons, csons):
+        super().__init__()
+        self._keep = (rc, cc)
+        self._setup(_lib_h2().new_block(rc.ptr, cc.ptr, bool(a), rsons, csons), True)
+
+    a = property(lambda self: bool(self.ptr.contents.a))
+    rsons = property(lambda self: self.ptr.contents.rsons)
+    csons = property(lambda self: self.ptr.contents.csons)
+    desc = property(lambda self: self.ptr.contents.desc)
+    rc = property(lambda self: Cluster.wrap(self.ptr.contents.rc, False))
+    cc = property(lambda self: Cluster.wrap(self.ptr.contents.cc, False))
+
+    @property
+    def son(self):
+        # the reference indexes rsons + csons sons (hmatrix.pyx:64-66, right only for 2x2); the
+        # full rsons * csons list is returned here
+        out = []
+        for i in range(self.rsons * self.csons):
+            b = Block.wrap(self.ptr.contents.son[i], False)
+            b._parent = self
+            out.append(b)
+        return out
+
+
+class RKMatrix(_Handle):
+    _del = 'del_rkmatrix'
+
+    def __init__(self, rows, cols, k):
+        super().__init__()
+        self._setup(_lib_h2().new_rkmatrix(rows, cols, k), True)
+
+    k = property(lambda self: self.ptr.contents.k)
+
+    @property
+    def A(self):
+        m = AMatrix.wrap(C.pointer(self.ptr.contents.A), False)
+        m._parent = self
+        return m
+
+    @property
+    def B(self):
+        m = AMatrix.wrap(C.pointer(self.ptr.contents.B), False)
+        m._parent = self
+        return m
+
+
+class HMatrix(_Handle):
+    _del = 'del_hmatrix'
+
+    def __init__(self, rc, cc):
+        super().__init__()
+        self._keep = (rc, cc)
+        self._setup(_lib_h2().new_hmatrix(rc.ptr, cc.ptr), True)
+
+    rsons = property(lambda self: self.ptr.contents.rsons)
+    csons = property(lambda self: self.ptr.contents.csons)
+    desc = property(lambda self: self.ptr.contents.desc)
+    rc = property(lambda self: Cluster.wrap(self.ptr.contents.rc, False))
+    cc = property(lambda self: Cluster.wrap(self.ptr.contents.cc, False))
+
+    @property
+    def r(self):
+        if self.ptr.contents.r:
+            m = RKMatrix.wrap(self.ptr.contents.r, False)
+            m._parent = self
+            return m
+
+    @property
+    def f(self):
+        if self.ptr.contents.f:
+            m = AMatrix.wrap(self.ptr.contents.f, False)
+            m._parent = self
+            return m
+
+    @property
+    def son(self):
+        out = []
+        for i in range(self.rsons * self.csons):
+            h = HMatrix.wrap(self.ptr.contents.son[i], False)
+            h._parent = self
+            out.append(h)
+        return out
+
+
+class Truncmode(_Handle):
+    _del = 'del_truncmode'
+
+    def __init__(self):
+        super().__init__()
+        self._setup(_lib_h2().new_truncmode(), True)
+
+
 # ---- function layer (same names as the cpdef wrappers) ---------------------------------
 def init_h2lib():
     _lib_h2().init_h2lib(None, None)
@@ -460,6 +654,131 @@ def new_slp_helmholtz_bem3d(k, surf, q_regular, q_singular, row_basis, col_basis
 
 def assemble_bem3d_amatrix(bem, G):
     _lib_h2().assemble_bem3d_amatrix(bem.ptr, G.ptr)
+
+
+def build_bem3d_cluster(bem, clf, basis):
+    c = Cluster.wrap(_lib_h2().build_bem3d_cluster(bem.ptr, clf, int(basis)), True)
+    c._owns_idx = True
+    return c
+
+
+def _admis_fn(admis):
+    name = {'2': 'admissible_2_cluster', 'max': 'admissible_max_cluster', 'sphere': 'admissible_sphere_cluster',
+            '2min': 'admissible_2_min_cluster', '2_min': 'admissible_2_min_cluster'}.get(str(admis).lower())
+    if name is None:
+        raise TypeError
+    return C.cast(getattr(_lib_h2(), name), C.c_void_p)
+
+
+def _build_block(fn, rc, cc, eta, admis):
+    e = real(eta)
+    b = Block.wrap(getattr(_lib_h2(), fn)(rc.ptr, cc.ptr, C.cast(C.pointer(e), C.c_void_p), _admis_fn(admis)), True)
+    b._keep = (rc, cc)
+    return b
+
+
+def build_strict_block(rc, cc, eta, admis):
+    return _build_block('build_strict_block', rc, cc, eta, admis)
+
+
+def build_nonstrict_block(rc, cc, eta, admis):
+    return _build_block('build_nonstrict_block', rc, cc, eta, admis)
+
+
+def setup_hmatrix_aprx_aca_bem3d(bem, rc, cc, tree, accur):
+    _lib_h2().setup_hmatrix_aprx_aca_bem3d(bem.ptr, rc.ptr, cc.ptr, tree.ptr, accur)
+
+
+def setup_hmatrix_aprx_paca_bem3d(bem, rc, cc, tree, accur):
+    _lib_h2().setup_hmatrix_aprx_paca_bem3d(bem.ptr, rc.ptr, cc.ptr, tree.ptr, accur)
+
+
+def setup_hmatrix_aprx_hca_bem3d(bem, rc, cc, tree, m, accur):
+    _lib_h2().setup_hmatrix_aprx_hca_bem3d(bem.ptr, rc.ptr, cc.ptr, tree.ptr, m, accur)
+
+
+def setup_hmatrix_aprx_inter_row_bem3d(bem, rc, cc, tree, m):
+    _lib_h2().setup_hmatrix_aprx_inter_row_bem3d(bem.ptr, rc.ptr, cc.ptr, tree.ptr, m)
+
+
+def build_from_block_hmatrix(b, k):
+    h = HMatrix.wrap(_lib_h2().build_from_block_hmatrix(b.ptr, k), True)
+    h._keep = b
+    return h
+
+
+def assemble_bem3d_hmatrix(bem, b, G):
+    _lib_h2().assemble_bem3d_hmatrix(bem.ptr, b.ptr, G.ptr)
+
+
+def clear_hmatrix(hm):
+    _lib_h2().clear_hmatrix(hm.ptr)
+
+
+def copy_hmatrix(src, trg):
+    _lib_h2().copy_hmatrix(src.ptr, trg.ptr)
+
+
+def _derived(fn, src):
+    h = HMatrix.wrap(getattr(_lib_h2(), fn)(src.ptr), True)
+    h._keep = src
+    return h
+
+
+def clone_hmatrix(src):
+    return _derived('clone_hmatrix', src)
+
+
+def clonestructure_hmatrix(src):
+    return _derived('clonestructure_hmatrix', src)
+
+
+def getsize_hmatrix(hm):
+    return _lib_h2().getsize_hmatrix(hm.ptr)
+
+
+def getrows_hmatrix(hm):
+    return _lib_h2().getrows_hmatrix(hm.ptr)
+
+
+def getcols_hmatrix(hm):
+    return _lib_h2().getcols_hmatrix(hm.ptr)
+
+
+def addeval_hmatrix_avector(alpha, hm, x, y):
+    _lib_h2().addeval_hmatrix_avector(_f(alpha), hm.ptr, x.ptr, y.ptr)
+
+
+def addevalsymm_hmatrix_avector(alpha, hm, x, y):
+    _lib_h2().addevalsymm_hmatrix_avector(_f(alpha), hm.ptr, x.ptr, y.ptr)
+
+
+def copy_sparsematrix_hmatrix(sp, hm):
+    _lib_h2().copy_sparsematrix_hmatrix(sp.ptr, hm.ptr)
+
+
+def identity_hmatrix(hm):
+    _lib_h2().identity_hmatrix(hm.ptr)
+
+
+def scale_hmatrix(alpha, hm):
+    _lib_h2().scale_hmatrix(_f(alpha), hm.ptr)
+
+
+def add_hmatrix_amatrix(alpha, atrans, a, b):
+    _lib_h2().add_hmatrix_amatrix(_f(alpha), bool(atrans), a.ptr, b.ptr)
+
+
+def new_releucl_truncmode():
+    return Truncmode.wrap(_lib_h2().new_releucl_truncmode(), True)
+
+
+def solve_gmres_hmatrix_avector(A, b, x, eps, maxiter, kmax):
+    return _lib_h2().solve_gmres_hmatrix_avector(A.ptr, b.ptr, x.ptr, eps, maxiter, kmax)
+
+
+def solve_gmres_amatrix_avector(A, b, x, eps, maxiter, kmax):
+    return _lib_h2().solve_gmres_amatrix_avector(A.ptr, b.ptr, x.ptr, eps, maxiter, kmax)
 
 
 def lrdecomp_amatrix(a):

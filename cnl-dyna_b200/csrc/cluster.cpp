@@ -89,7 +89,7 @@ void build_vertex_cluster_tree(unsigned nv, unsigned nt, const double *x, const 
   for (unsigned i = 0; i < nv; i++) T.pos[T.perm[i]] = i;
 }
 
-bool admissible(const ClusterNode &r, const ClusterNode &c, double eta, Admis kind) {
+bool is_admissible(const ClusterNode &r, const ClusterNode &c, double eta, Admis kind) {
   double dr2 = 0, dc2 = 0, dist2 = 0, drm = 0, dcm = 0, distm = 0;
   for (int d = 0; d < 3; d++) {
     double a = r.bmax[d] - r.bmin[d], b = c.bmax[d] - c.bmin[d];
@@ -118,7 +118,7 @@ namespace {
 void descend(const ClusterTree &T, unsigned r, unsigned c, double eta, Admis kind, bool strict,
              std::vector<BlockLeaf> &out) {
   const ClusterNode &R = T.node[r], &C = T.node[c];
-  if (admissible(R, C, eta, kind)) { out.push_back({r, c, true}); return; }
+  if (is_admissible(R, C, eta, kind)) { out.push_back({r, c, true}); return; }
   const bool rs = R.son[0] >= 0, cs = C.son[0] >= 0;
   if (rs && cs) {
     for (int j = 0; j < 2; j++)      // H2Lib son order: son[i + j*rsons]

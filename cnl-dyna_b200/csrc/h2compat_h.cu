@@ -1,0 +1,524 @@
+// H2Lib-named cluster / block / hmatrix / rkmatrix / krylov entry points
+// (include/cnld_b200_h2lib.h; bound by cnld/h2lib/_cluster.pxd, _block.pxd, _hmatrix.pxd,
+// _rkmatrix.pxd, _bem3d.pxd, _krylovsolvers.pxd, _truncation.pxd).  The pointer trees live in host
+// memory exactly as H2Lib's (Python walks them: cnld/h2lib/cluster.pyx:60-62, hmatrix.pyx:40-66);
+// leaf assembly and the matvec run on the GPU (hmatrix.cu).
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/cnld_b200_h2lib.h"
+#include "ctx.cuh"
+#include "hmat.cuh"
+
+namespace {
+typedef std::complex<double> zc;
+inline field mk(double re, double im) { field f; f.re = re; f.im = im; return f; }
+[[noreturn]] void die(const char *what) {
+  fprintf(stderr, "libcnld_b200: %s: %s\n", what, cnld_b200_last_error());
+  abort();
+}
+
+std::mutex g_mu;
+std::unordered_map<const cluster *, const cluster *> g_root;  // any node of a tree -> its root
+struct DevCopy { HMat H; bool valid = false; };
+std::unordered_map<const hmatrix *, DevCopy *> g_dev;         // matvec copies of root hmatrices
+
+void register_tree(const cluster *t, const cluster *root) {
+  g_root[t] = root;
+  for (uint i = 0; i < t->sons; i++) register_tree(t->son[i], root);
+}
+const cluster *root_of(const cluster *t) {
+  auto it = g_root.find(t);
+  return it == g_root.end() ? t : it->second;
+}
+void invalidate(const hmatrix *hm) {
+  auto it = g_dev.find(hm);
+  if (it != g_dev.end()) it->second->valid = false;
+}
+
+pcluster convert(const ClusterTree &T, uint id, uint *idx) {
+  const ClusterNode &N = T.node[id];
+  uint sons = N.son[0] >= 0 ? 2 : 0;
+  pcluster c = new_cluster(N.size, idx + N.start, sons, 3);
+  for (int d = 0; d < 3; d++) { c->bmin[d] = N.bmin[d]; c->bmax[d] = N.bmax[d]; }
+  c->desc = 1;
+  for (uint s = 0; s < sons; s++) {
+    c->son[s] = convert(T, (uint)N.son[s], idx);
+    c->desc += c->son[s]->desc;
+  }
+  return c;
+}
+
+void collect(hmatrix *hm, std::vector<hmatrix *> &out) {
+  if (hm->rsons * hm->csons == 0) { out.push_back(hm); return; }
+  for (uint j = 0; j < hm->csons; j++)
+    for (uint i = 0; i < hm->rsons; i++) collect(hm->son[i + j * hm->rsons], out);
+}
+
+void resize_rk(prkmatrix r, uint k) {
+  if (!r->A.owner) free(r->A.a);
+  if (!r->B.owner) free(r->B.a);
+  r->A.a = (field *)calloc((size_t)r->A.rows * (k ? k : 1), sizeof(field));
+  r->B.a = (field *)calloc((size_t)r->B.rows * (k ? k : 1), sizeof(field));
+  r->A.cols = r->B.cols = k;
+  r->A.owner = r->B.owner = nullptr;
+  r->k = k;
+}
+
+// flatten a host hmatrix into matvec leaves + pool (U = A, V = conj(B))
+int upload(const hmatrix *hm, DevCopy &D) {
+  const cluster *rr = root_of(hm->rc), *cr = root_of(hm->cc);
+  if (rr != hm->rc || cr != hm->cc || rr->size != cr->size || memcmp(rr->idx, cr->idx, sizeof(uint) * rr->size)) {
+    set_error("H-matrix matvec needs a square root block over one cluster tree");
+    return -1;
+  }
+  std::vector<hmatrix *> leaves;
+  collect(const_cast<hmatrix *>(hm), leaves);
+  std::vector<HLeafDev> L;
+  std::vector<cplx> pool;
+  for (hmatrix *l : leaves) {
+    HLeafDev d;
+    memset(&d, 0, sizeof(d));
+    d.r0 = (uint)(l->rc->idx - rr->idx); d.m = l->rc->size;
+    d.c0 = (uint)(l->cc->idx - cr->idx); d.n = l->cc->size;
+    d.off = pool.size();
+    if (l->f) {
+      for (uint j = 0; j < d.n; j++)
+        for (uint i = 0; i < d.m; i++) { field v = l->f->a[(size_t)j * l->f->ld + i]; pool.push_back(make_double2(v.re, v.im)); }
+    } else if (l->r) {
+      d.adm = 1; d.k = d.kcap = l->r->k;
+      for (uint c = 0; c < d.k; c++)
+        for (uint i = 0; i < d.m; i++) { field v = l->r->A.a[(size_t)c * l->r->A.ld + i]; pool.push_back(make_double2(v.re, v.im)); }
+      for (uint c = 0; c < d.k; c++)
+        for (uint i = 0; i < d.n; i++) { field v = l->r->B.a[(size_t)c * l->r->B.ld + i]; pool.push_back(make_double2(v.re, -v.im)); }
+    } else continue;
+    L.push_back(d);
+  }
+  if (pool.empty()) pool.push_back(make_double2(0, 0));
+  hmat_free(D.H);
+  std::vector<uint> perm(rr->idx, rr->idx + rr->size);
+  if (hmat_from_host(D.H, 0, rr->size, perm, L, pool)) return -1;
+  D.valid = true;
+  return 0;
+}
+
+int device_matvec(const hmatrix *hm, zc alpha, const field *x, field *y) {
+  DevCopy *D;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_dev.find(hm);
+    if (it == g_dev.end()) it = g_dev.emplace(hm, new DevCopy()).first;
+    D = it->second;
+    if (!D->valid && upload(hm, *D)) return -1;
+  }
+  const uint n = D->H.n;
+  cplx *dx = nullptr, *dy = nullptr;
+  CNLD_CK(cudaMalloc(&dx, sizeof(cplx) * n));
+  CNLD_CK(cudaMalloc(&dy, sizeof(cplx) * n));
+  int rc = 0;
+  if (cudaMemcpy(dx, x, sizeof(cplx) * n, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(dy, y, sizeof(cplx) * n, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); rc = -1; }
+  if (!rc) rc = hmat_matvec(0, D->H, make_double2(alpha.real(), alpha.imag()), dx, dy, 1);
+  if (!rc && cudaMemcpy(y, dy, sizeof(cplx) * n, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); rc = -1; }
+  cudaFree(dx); cudaFree(dy);
+  return rc;
+}
+
+// restarted GMRES (modified Gram-Schmidt, Givens) around a matvec callback, host vectors
+template <typename MV>
+uint gmres(MV &&mv, uint n, const field *b, field *x, double eps, uint maxiter, uint kmax) {
+  std::vector<zc> r(n), w(n), V((size_t)(kmax + 1) * n), H((size_t)(kmax + 1) * kmax), cs(kmax), sn(kmax), g(kmax + 1);
+  const zc *bb = reinterpret_cast<const zc *>(b);
+  zc *xx = reinterpret_cast<zc *>(x);
+  auto nrm = [&](const std::vector<zc> &v) { double s = 0; for (auto &e : v) s += std::norm(e); return std::sqrt(s); };
+  double bn = 0;
+  for (uint i = 0; i < n; i++) bn += std::norm(bb[i]);
+  bn = std::sqrt(bn);
+  if (bn == 0.0) { for (uint i = 0; i < n; i++) xx[i] = 0; return 0; }
+  uint it = 0;
+  while (it < maxiter) {
+    std::fill(w.begin(), w.end(), zc(0));
+    mv(xx, w.data());
+    for (uint i = 0; i < n; i++) r[i] = bb[i] - w[i];
+    double beta = nrm(r);
+    if (beta <= eps * bn) break;
+    for (uint i = 0; i < n; i++) V[i] = r[i] / beta;
+    std::fill(g.begin(), g.end(), zc(0));
+    g[0] = beta;
+    uint j = 0;
+    for (; j < kmax && it < maxiter; j++, it++) {
+      std::fill(w.begin(), w.end(), zc(0));
+      mv(&V[(size_t)j * n], w.data());
+      for (uint i = 0; i <= j; i++) {
+        zc h = 0;
+        for (uint e = 0; e < n; e++) h += std::conj(V[(size_t)i * n + e]) * w[e];
+        H[(size_t)i * kmax + j] = h;
+        for (uint e = 0; e < n; e++) w[e] -= h * V[(size_t)i * n + e];
+      }
+      double hn = nrm(w);
+      for (uint e = 0; e < n; e++) V[(size_t)(j + 1) * n + e] = hn > 0 ? w[e] / hn : zc(0);
+      zc hj1 = hn;
+      for (uint i = 0; i < j; i++) {
+        zc a = H[(size_t)i * kmax + j], c2 = H[(size_t)(i + 1) * kmax + j];
+        H[(size_t)i * kmax + j] = std::conj(cs[i]) * a + std::conj(sn[i]) * c2;
+        H[(size_t)(i + 1) * kmax + j] = -sn[i] * a + cs[i] * c2;
+      }
+      zc a = H[(size_t)j * kmax + j];
+      double d = std::sqrt(std::norm(a) + std::norm(hj1));
+      cs[j] = d > 0 ? a / d : zc(1);
+      sn[j] = d > 0 ? hj1 / d : zc(0);
+      H[(size_t)j * kmax + j] = d;
+      zc g0 = std::conj(cs[j]) * g[j] + std::conj(sn[j]) * g[j + 1];
+      g[j + 1] = -sn[j] * g[j] + cs[j] * g[j + 1];
+      g[j] = g0;
+      if (std::abs(g[j + 1]) <= eps * bn) { j++; it++; break; }
+    }
+    std::vector<zc> yv(j);
+    for (uint ii = j; ii-- > 0;) {
+      zc s = g[ii];
+      for (uint l = ii + 1; l < j; l++) s -= H[(size_t)ii * kmax + l] * yv[l];
+      yv[ii] = s / H[(size_t)ii * kmax + ii];
+    }
+    for (uint l = 0; l < j; l++)
+      for (uint e = 0; e < n; e++) xx[e] += yv[l] * V[(size_t)l * n + e];
+  }
+  return it;
+}
+}  // namespace
+
+extern "C" {
+
+/* -------------------------------------------------------------- cluster ---- */
+pcluster new_cluster(uint size, uint *idx, uint sons, uint dim) {
+  pcluster t = (pcluster)calloc(1, sizeof(cluster));
+  t->size = size; t->idx = idx; t->sons = sons; t->dim = dim;
+  t->son = sons ? (pcluster *)calloc(sons, sizeof(pcluster)) : nullptr;
+  t->bmin = (real *)calloc(dim ? dim : 1, sizeof(real));
+  t->bmax = (real *)calloc(dim ? dim : 1, sizeof(real));
+  t->desc = 1;
+  return t;
+}
+void del_cluster(pcluster t) {
+  if (!t) return;
+  for (uint i = 0; i < t->sons; i++) del_cluster(t->son[i]);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_root.erase(t);
+  }
+  free(t->son); free(t->bmin); free(t->bmax); free(t);
+}
+pcluster build_bem3d_cluster(pcbem3d bem, uint clf, basisfunctionbem3d basis) {
+  if (basis != BASIS_LINEAR_BEM3D) { set_error("build_bem3d_cluster: only the linear basis is on the cnl-dyna path"); return nullptr; }
+  pcsurface3d gr = bem->gr;
+  ClusterTree T;
+  build_vertex_cluster_tree(gr->vertices, gr->triangles, &gr->x[0][0], &gr->t[0][0], clf, T);
+  uint *idx = (uint *)malloc(sizeof(uint) * (gr->vertices ? gr->vertices : 1));  // freed by the caller
+  memcpy(idx, T.perm.data(), sizeof(uint) * gr->vertices);                        // (cluster.pyx:19-22 freemem(ptr.idx))
+  pcluster root = convert(T, 0, idx);
+  std::lock_guard<std::mutex> lk(g_mu);
+  register_tree(root, root);
+  return root;
+}
+
+/* ---------------------------------------------------------------- block ---- */
+static ClusterNode as_node(pcluster c) {
+  ClusterNode n;
+  for (uint d = 0; d < 3; d++) { n.bmin[d] = d < c->dim ? c->bmin[d] : 0.0; n.bmax[d] = d < c->dim ? c->bmax[d] : 0.0; }
+  return n;
+}
+bool admissible_2_cluster(pcluster rc, pcluster cc, void *data) { return is_admissible(as_node(rc), as_node(cc), *(real *)data, ADMIS_2); }
+bool admissible_max_cluster(pcluster rc, pcluster cc, void *data) { return is_admissible(as_node(rc), as_node(cc), *(real *)data, ADMIS_MAX); }
+bool admissible_sphere_cluster(pcluster rc, pcluster cc, void *data) { return is_admissible(as_node(rc), as_node(cc), *(real *)data, ADMIS_SPHERE); }
+bool admissible_2_min_cluster(pcluster rc, pcluster cc, void *data) { return is_admissible(as_node(rc), as_node(cc), *(real *)data, ADMIS_2_MIN); }
+
+pblock new_block(pcluster rc, pcluster cc, bool a, uint rsons, uint csons) {
+  pblock b = (pblock)calloc(1, sizeof(block));
+  b->rc = rc; b->cc = cc; b->a = a; b->rsons = rsons; b->csons = csons;
+  b->son = rsons * csons ? (pblock *)calloc((size_t)rsons * csons, sizeof(pblock)) : nullptr;
+  b->desc = 1;
+  return b;
+}
+void del_block(pblock b) {
+  if (!b) return;
+  for (uint i = 0; i < b->rsons * b->csons; i++) del_block(b->son[i]);
+  free(b->son); free(b);
+}
+static pblock build_block(pcluster rc, pcluster cc, void *data, admissible admis, bool strict) {
+  pblock b;
+  if (admis(rc, cc, data)) return new_block(rc, cc, true, 0, 0);
+  bool rs = rc->sons > 0, cs = cc->sons > 0;
+  if (rs && cs) {
+    b = new_block(rc, cc, false, rc->sons, cc->sons);
+    for (uint j = 0; j < cc->sons; j++)
+      for (uint i = 0; i < rc->sons; i++) b->son[i + j * rc->sons] = build_block(rc->son[i], cc->son[j], data, admis, strict);
+  } else if (!strict && rs) {
+    b = new_block(rc, cc, false, rc->sons, 1);
+    for (uint i = 0; i < rc->sons; i++) b->son[i] = build_block(rc->son[i], cc, data, admis, strict);
+  } else if (!strict && cs) {
+    b = new_block(rc, cc, false, 1, cc->sons);
+    for (uint j = 0; j < cc->sons; j++) b->son[j] = build_block(rc, cc->son[j], data, admis, strict);
+  } else
+    return new_block(rc, cc, false, 0, 0);
+  for (uint i = 0; i < b->rsons * b->csons; i++) b->desc += b->son[i]->desc;
+  return b;
+}
+pblock build_nonstrict_block(pcluster rc, pcluster cc, void *data, admissible admis) { return build_block(rc, cc, data, admis, false); }
+pblock build_strict_block(pcluster rc, pcluster cc, void *data, admissible admis) { return build_block(rc, cc, data, admis, true); }
+
+/* ------------------------------------------------------- rkmatrix / hmatrix - */
+prkmatrix new_rkmatrix(uint rows, uint cols, uint k) {
+  prkmatrix r = (prkmatrix)calloc(1, sizeof(rkmatrix));
+  r->A.rows = r->A.ld = rows; r->B.rows = r->B.ld = cols;
+  r->A.a = r->B.a = nullptr;
+  r->A.owner = r->B.owner = nullptr;
+  r->A.a = (field *)calloc((size_t)rows * (k ? k : 1), sizeof(field));
+  r->B.a = (field *)calloc((size_t)cols * (k ? k : 1), sizeof(field));
+  r->A.cols = r->B.cols = k;
+  r->k = k;
+  return r;
+}
+void del_rkmatrix(prkmatrix r) {
+  if (!r) return;
+  free(r->A.a); free(r->B.a); free(r);
+}
+phmatrix new_hmatrix(pccluster rc, pccluster cc) {
+  phmatrix h = (phmatrix)calloc(1, sizeof(hmatrix));
+  h->rc = rc; h->cc = cc; h->desc = 1;
+  return h;
+}
+void del_hmatrix(phmatrix hm) {
+  if (!hm) return;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_dev.find(hm);
+    if (it != g_dev.end()) { hmat_free(it->second->H); delete it->second; g_dev.erase(it); }
+  }
+  for (uint i = 0; i < hm->rsons * hm->csons; i++) del_hmatrix(hm->son[i]);
+  free(hm->son);
+  del_rkmatrix(hm->r);
+  del_amatrix(hm->f);
+  free(hm);
+}
+phmatrix build_from_block_hmatrix(pcblock b, uint k) {
+  phmatrix h = new_hmatrix(b->rc, b->cc);
+  if (b->rsons * b->csons) {
+    h->rsons = b->rsons; h->csons = b->csons;
+    h->son = (phmatrix *)calloc((size_t)b->rsons * b->csons, sizeof(phmatrix));
+    for (uint i = 0; i < b->rsons * b->csons; i++) { h->son[i] = build_from_block_hmatrix(b->son[i], k); h->desc += h->son[i]->desc; }
+  } else if (b->a)
+    h->r = new_rkmatrix(b->rc->size, b->cc->size, k);
+  else
+    h->f = new_zero_amatrix(b->rc->size, b->cc->size);
+  return h;
+}
+static phmatrix clone_impl(pchmatrix src, bool copy_data) {
+  phmatrix h = new_hmatrix(src->rc, src->cc);
+  if (src->rsons * src->csons) {
+    h->rsons = src->rsons; h->csons = src->csons;
+    h->son = (phmatrix *)calloc((size_t)src->rsons * src->csons, sizeof(phmatrix));
+    for (uint i = 0; i < src->rsons * src->csons; i++) { h->son[i] = clone_impl(src->son[i], copy_data); h->desc += h->son[i]->desc; }
+  } else if (src->r) {
+    h->r = new_rkmatrix(src->r->A.rows, src->r->B.rows, src->r->k);
+    if (copy_data) {
+      memcpy(h->r->A.a, src->r->A.a, sizeof(field) * (size_t)src->r->A.rows * src->r->k);
+      memcpy(h->r->B.a, src->r->B.a, sizeof(field) * (size_t)src->r->B.rows * src->r->k);
+    }
+  } else if (src->f) {
+    h->f = copy_data ? clone_amatrix(src->f) : new_zero_amatrix(src->f->rows, src->f->cols);
+  }
+  return h;
+}
+phmatrix clone_hmatrix(pchmatrix src) { return clone_impl(src, true); }
+phmatrix clonestructure_hmatrix(pchmatrix src) { return clone_impl(src, false); }
+void clear_hmatrix(phmatrix hm) {
+  std::vector<hmatrix *> L;
+  collect(hm, L);
+  for (hmatrix *l : L) {
+    if (l->f) memset(l->f->a, 0, sizeof(field) * (size_t)l->f->ld * l->f->cols);
+    if (l->r) resize_rk(l->r, 0);
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  invalidate(hm);
+}
+void copy_hmatrix(pchmatrix src, phmatrix trg) {
+  std::vector<hmatrix *> S, T;
+  collect(const_cast<hmatrix *>(src), S);
+  collect(trg, T);
+  if (S.size() != T.size()) { set_error("copy_hmatrix: structures differ"); die("copy_hmatrix"); }
+  for (size_t i = 0; i < S.size(); i++) {
+    if (S[i]->f && T[i]->f) {
+      for (uint j = 0; j < S[i]->f->cols; j++)
+        memcpy(T[i]->f->a + (size_t)j * T[i]->f->ld, S[i]->f->a + (size_t)j * S[i]->f->ld, sizeof(field) * S[i]->f->rows);
+    } else if (S[i]->r && T[i]->r) {
+      resize_rk(T[i]->r, S[i]->r->k);
+      memcpy(T[i]->r->A.a, S[i]->r->A.a, sizeof(field) * (size_t)S[i]->r->A.rows * S[i]->r->k);
+      memcpy(T[i]->r->B.a, S[i]->r->B.a, sizeof(field) * (size_t)S[i]->r->B.rows * S[i]->r->k);
+    } else { set_error("copy_hmatrix: structures differ"); die("copy_hmatrix"); }
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  invalidate(trg);
+}
+size_t getsize_hmatrix(pchmatrix hm) {
+  size_t sz = sizeof(hmatrix);
+  if (hm->r) sz += sizeof(rkmatrix) + sizeof(field) * (size_t)hm->r->k * (hm->r->A.rows + hm->r->B.rows);
+  if (hm->f) sz += getsize_amatrix(hm->f);
+  for (uint i = 0; i < hm->rsons * hm->csons; i++) sz += getsize_hmatrix(hm->son[i]);
+  return sz + sizeof(phmatrix) * hm->rsons * hm->csons;
+}
+uint getrows_hmatrix(pchmatrix hm) { return hm->rc->size; }
+uint getcols_hmatrix(pchmatrix hm) { return hm->cc->size; }
+
+void scale_hmatrix(field alpha, phmatrix hm) {
+  std::vector<hmatrix *> L;
+  collect(hm, L);
+  for (hmatrix *l : L) {
+    if (l->f) scale_amatrix(alpha, l->f);
+    if (l->r) scale_amatrix(alpha, &l->r->A);
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  invalidate(hm);
+}
+void identity_hmatrix(phmatrix hm) {
+  clear_hmatrix(hm);
+  std::vector<hmatrix *> L;
+  collect(hm, L);
+  for (hmatrix *l : L) {
+    if (!l->f) continue;
+    for (uint i = 0; i < l->rc->size; i++)
+      for (uint j = 0; j < l->cc->size; j++)
+        if (l->rc->idx[i] == l->cc->idx[j]) l->f->a[(size_t)j * l->f->ld + i] = mk(1.0, 0.0);
+  }
+}
+void copy_sparsematrix_hmatrix(psparsematrix sp, phmatrix hm) {
+  // entries that fall into dense leaves are copied; the (block-diagonal FEM) operators of cnl-dyna
+  // can also reach admissible leaves -- those are reported, not silently dropped
+  clear_hmatrix(hm);
+  std::vector<hmatrix *> L;
+  collect(hm, L);
+  size_t placed = 0;
+  for (hmatrix *l : L) {
+    if (!l->f) continue;
+    std::unordered_map<uint, uint> cpos;
+    for (uint j = 0; j < l->cc->size; j++) cpos[l->cc->idx[j]] = j;
+    for (uint i = 0; i < l->rc->size; i++) {
+      uint row = l->rc->idx[i];
+      for (uint p = sp->row[row]; p < sp->row[row + 1]; p++) {
+        auto it = cpos.find(sp->col[p]);
+        if (it != cpos.end()) { l->f->a[(size_t)it->second * l->f->ld + i] = sp->coeff[p]; placed++; }
+      }
+    }
+  }
+  size_t nzv = 0;
+  for (uint p = 0; p < sp->nz; p++) if (sp->coeff[p].re != 0.0 || sp->coeff[p].im != 0.0) nzv++;
+  if (placed < nzv)
+    fprintf(stderr, "libcnld_b200: copy_sparsematrix_hmatrix: %zu non-zero entries lie in admissible leaves and "
+                    "were not copied (keep the sparse operator separate: cnld.compressed_formats.HSumFormat)\n",
+            nzv - placed);
+}
+void add_hmatrix_amatrix(field alpha, bool atrans, pchmatrix a, pamatrix b) {
+  std::vector<hmatrix *> L;
+  collect(const_cast<hmatrix *>(a), L);
+  zc al(alpha.re, alpha.im);
+  for (hmatrix *l : L)
+    for (uint j = 0; j < l->cc->size; j++)
+      for (uint i = 0; i < l->rc->size; i++) {
+        zc v(0);
+        if (l->f) v = zc(l->f->a[(size_t)j * l->f->ld + i].re, l->f->a[(size_t)j * l->f->ld + i].im);
+        else if (l->r)
+          for (uint c = 0; c < l->r->k; c++) {
+            field A = l->r->A.a[(size_t)c * l->r->A.ld + i], B = l->r->B.a[(size_t)c * l->r->B.ld + j];
+            v += zc(A.re, A.im) * std::conj(zc(B.re, B.im));
+          }
+        uint r = l->rc->idx[i], c = l->cc->idx[j];
+        if (atrans) { std::swap(r, c); v = std::conj(v); }
+        field *d = b->a + (size_t)c * b->ld + r;
+        zc nv = zc(d->re, d->im) + al * v;
+        *d = mk(nv.real(), nv.imag());
+      }
+}
+void addeval_hmatrix_avector(field alpha, pchmatrix hm, pcavector x, pavector y) {
+  if (x->dim != hm->cc->size || y->dim != hm->rc->size) { set_error("addeval_hmatrix_avector: dimension mismatch"); die("addeval_hmatrix_avector"); }
+  if (device_matvec(hm, zc(alpha.re, alpha.im), x->v, y->v)) die("addeval_hmatrix_avector");
+}
+void addevalsymm_hmatrix_avector(field alpha, pchmatrix hm, pcavector x, pavector y) { addeval_hmatrix_avector(alpha, hm, x, y); }
+
+/* ------------------------------------------------------------ bem3d (H) ---- */
+void setup_hmatrix_aprx_paca_bem3d(pbem3d bem, pccluster, pccluster, pcblock, real accur) { bem->accur = accur; }
+void setup_hmatrix_aprx_aca_bem3d(pbem3d bem, pccluster rc, pccluster cc, pcblock t, real accur) { setup_hmatrix_aprx_paca_bem3d(bem, rc, cc, t, accur); }
+void setup_hmatrix_aprx_hca_bem3d(pbem3d bem, pccluster rc, pccluster cc, pcblock t, uint, real accur) { setup_hmatrix_aprx_paca_bem3d(bem, rc, cc, t, accur); }
+void setup_hmatrix_aprx_inter_row_bem3d(pbem3d bem, pccluster rc, pccluster cc, pcblock t, uint m) {
+  // interpolation order m is mapped to an ACA accuracy of comparable quality
+  setup_hmatrix_aprx_paca_bem3d(bem, rc, cc, t, std::pow(10.0, -(double)std::max(2u, m)));
+}
+void assemble_bem3d_hmatrix(pbem3d bem, pblock, phmatrix G) {
+  if (!bem || !bem->priv) { set_error("assemble_bem3d_hmatrix: bem object has no device state"); die("assemble_bem3d_hmatrix"); }
+  if (!(bem->accur > 0.0)) { set_error("assemble_bem3d_hmatrix: call setup_hmatrix_aprx_*_bem3d first"); die("assemble_bem3d_hmatrix"); }
+  cnld_ctx *c = (cnld_ctx *)bem->priv;
+  const cluster *rr = root_of(G->rc), *cr = root_of(G->cc);
+  std::vector<hmatrix *> leaves;
+  collect(G, leaves);
+  std::vector<LeafRange> ranges;
+  for (hmatrix *l : leaves)
+    ranges.push_back({(uint)(l->rc->idx - rr->idx), l->rc->size, (uint)(l->cc->idx - cr->idx), l->cc->size, l->r != nullptr});
+  if (rr->size != c->bem.nv || cr->size != c->bem.nv || memcmp(rr->idx, cr->idx, sizeof(uint) * rr->size)) {
+    set_error("assemble_bem3d_hmatrix: row and column cluster trees must be the tree of the bem geometry");
+    die("assemble_bem3d_hmatrix");
+  }
+  std::vector<uint> perm(rr->idx, rr->idx + rr->size);
+  HMat H;
+  if (hmat_create_from_ranges(H, c->bem, c->h_t.data(), perm, ranges, 64) ||
+      hmat_assemble(0, H, bem->k.re, bem->k.im, bem->accur) || hmat_fetch_leaves(H))
+    die("assemble_bem3d_hmatrix");
+  std::vector<cplx> pool(H.pool_size ? H.pool_size : 1);
+  if (cudaMemcpy(pool.data(), H.d_pool, sizeof(cplx) * H.pool_size, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("assemble_bem3d_hmatrix: D2H failed");
+    die("assemble_bem3d_hmatrix");
+  }
+  for (size_t i = 0; i < leaves.size(); i++) {
+    const HLeafDev &L = H.leaf[i];
+    const cplx *src = pool.data() + L.off;
+    hmatrix *l = leaves[i];
+    if (l->f) {
+      for (uint j = 0; j < L.n; j++)
+        for (uint r = 0; r < L.m; r++) l->f->a[(size_t)j * l->f->ld + r] = mk(src[(size_t)j * L.m + r].x, src[(size_t)j * L.m + r].y);
+    } else {
+      resize_rk(l->r, L.k);
+      const cplx *U = src, *V = src + (size_t)L.m * L.kcap;
+      for (uint cidx = 0; cidx < L.k; cidx++) {
+        for (uint r = 0; r < L.m; r++) l->r->A.a[(size_t)cidx * L.m + r] = mk(U[(size_t)cidx * L.m + r].x, U[(size_t)cidx * L.m + r].y);
+        for (uint r = 0; r < L.n; r++) l->r->B.a[(size_t)cidx * L.n + r] = mk(V[(size_t)cidx * L.n + r].x, -V[(size_t)cidx * L.n + r].y);
+      }
+    }
+  }
+  hmat_free(H);
+  std::lock_guard<std::mutex> lk(g_mu);
+  invalidate(G);
+}
+
+/* ----------------------------------------------------------- truncation ---- */
+ptruncmode new_truncmode(void) { return (ptruncmode)calloc(1, sizeof(truncmode)); }
+void del_truncmode(ptruncmode tm) { free(tm); }
+ptruncmode new_releucl_truncmode(void) { return new_truncmode(); }
+
+/* -------------------------------------------------------- krylovsolvers ---- */
+uint solve_gmres_hmatrix_avector(pchmatrix A, pcavector b, pavector x, real eps, uint maxiter, uint kmax) {
+  const uint n = b->dim;
+  return gmres([&](const zc *in, zc *out) {
+    if (device_matvec(A, zc(1.0), reinterpret_cast<const field *>(in), reinterpret_cast<field *>(out))) die("solve_gmres_hmatrix_avector");
+  }, n, b->v, x->v, eps, maxiter, kmax ? kmax : 50);
+}
+uint solve_gmres_amatrix_avector(pcamatrix A, pcavector b, pavector x, real eps, uint maxiter, uint kmax) {
+  const uint n = b->dim;
+  return gmres([&](const zc *in, zc *out) {
+    for (uint j = 0; j < A->cols; j++) {
+      zc s = in[j];
+      const field *col = A->a + (size_t)j * A->ld;
+      for (uint i = 0; i < A->rows; i++) out[i] += zc(col[i].re, col[i].im) * s;
+    }
+  }, n, b->v, x->v, eps, maxiter, kmax ? kmax : 50);
+}
+
+}  // extern "C"

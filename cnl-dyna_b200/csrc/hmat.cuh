@@ -33,6 +33,11 @@ struct HMat {
   uint vec_cap = 0;
 };
 
+struct LeafRange { uint r0, m, c0, n; bool admissible; };
+int hmat_create_from_ranges(HMat &H, const BemDev &bem, const uint *htri, const std::vector<uint> &perm,
+                            const std::vector<LeafRange> &ranges, uint kmax);
+int hmat_from_host(HMat &H, int device, uint n, const std::vector<uint> &perm, const std::vector<HLeafDev> &leaf,
+                   const std::vector<cplx> &pool);
 int hmat_create(HMat &H, const BemDev &bem, const double *hx, const uint *htri, uint clf, double eta, int admis,
                 bool strict, uint kmax);
 void hmat_free(HMat &H);

@@ -363,12 +363,26 @@ int to_device(T *&d, const std::vector<T> &h) {
 
 int hmat_create(HMat &H, const BemDev &bem, const double *hx, const uint *htri, uint clf, double eta, int admis,
                 bool strict, uint kmax) {
+  build_vertex_cluster_tree(bem.nv, bem.nt, hx, htri, clf, H.tree);
+  build_block_leaves(H.tree, eta, (Admis)admis, strict, H.blocks);
+  std::vector<LeafRange> ranges;
+  for (const BlockLeaf &B : H.blocks) {
+    const ClusterNode &Rn = H.tree.node[B.rc], &Cn = H.tree.node[B.cc];
+    ranges.push_back({Rn.start, Rn.size, Cn.start, Cn.size, B.admissible});
+  }
+  return hmat_create_from_ranges(H, bem, htri, H.tree.perm, ranges, kmax);
+}
+
+// leaves given as (row range, column range) of the permutation `perm` (cluster order -> DOF)
+int hmat_create_from_ranges(HMat &H, const BemDev &bem, const uint *htri, const std::vector<uint> &perm,
+                            const std::vector<LeafRange> &ranges, uint kmax) {
   H.bem = &bem;
   H.n = bem.nv;
   H.kmax = kmax;
-  build_vertex_cluster_tree(bem.nv, bem.nt, hx, htri, clf, H.tree);
-  build_block_leaves(H.tree, eta, (Admis)admis, strict, H.blocks);
-  // cluster -> triangles touching it (only for clusters of inadmissible leaves)
+  if (&perm != &H.tree.perm) H.tree.perm = perm;
+  H.tree.pos.resize(bem.nv);
+  for (uint i = 0; i < bem.nv; i++) H.tree.pos[H.tree.perm[i]] = i;
+  // vertex -> triangles, and per cluster range the triangles touching it (dense leaves only)
   std::vector<uint> vstart(bem.nv + 1, 0), vadj(3 * (size_t)bem.nt), v2t(3 * (size_t)bem.nt);
   for (size_t i = 0; i < 3 * (size_t)bem.nt; i++) vstart[htri[i] + 1]++;
   for (uint v = 0; v < bem.nv; v++) vstart[v + 1] += vstart[v];
@@ -377,15 +391,14 @@ int hmat_create(HMat &H, const BemDev &bem, const double *hx, const uint *htri, 
     for (uint t = 0; t < bem.nt; t++)
       for (uint d = 0; d < 3; d++) { uint e = fill[htri[3 * (size_t)t + d]]++; vadj[e] = t; v2t[e] = t * 4 + d; }
   }
-  std::map<uint, uint> list_of;  // cluster id -> triangle list id
+  std::map<std::pair<uint, uint>, uint> list_of;  // (start, size) -> triangle list id
   std::vector<uint> ctri_ptr(1, 0), ctri;
-  auto tri_list = [&](uint c) -> uint {
-    auto it = list_of.find(c);
+  auto tri_list = [&](uint start, uint size) -> uint {
+    auto it = list_of.find({start, size});
     if (it != list_of.end()) return it->second;
-    const ClusterNode &C = H.tree.node[c];
     std::vector<uint> ts;
-    for (uint i = 0; i < C.size; i++) {
-      uint v = H.tree.perm[C.start + i];
+    for (uint i = 0; i < size; i++) {
+      uint v = H.tree.perm[start + i];
       for (uint e = vstart[v]; e < vstart[v + 1]; e++) ts.push_back(vadj[e]);
     }
     std::sort(ts.begin(), ts.end());
@@ -393,18 +406,17 @@ int hmat_create(HMat &H, const BemDev &bem, const double *hx, const uint *htri, 
     ctri.insert(ctri.end(), ts.begin(), ts.end());
     ctri_ptr.push_back((uint)ctri.size());
     uint id = (uint)ctri_ptr.size() - 2;
-    list_of[c] = id;
+    list_of[{start, size}] = id;
     return id;
   };
   H.leaf.clear();
   std::vector<uint> near_ids, far_ids;
   size_t off = 0, foff = 0;
-  for (size_t b = 0; b < H.blocks.size(); b++) {
-    const BlockLeaf &B = H.blocks[b];
-    const ClusterNode &Rn = H.tree.node[B.rc], &Cn = H.tree.node[B.cc];
+  for (size_t b = 0; b < ranges.size(); b++) {
+    const LeafRange &B = ranges[b];
     HLeafDev L;
     memset(&L, 0, sizeof(L));
-    L.r0 = Rn.start; L.m = Rn.size; L.c0 = Cn.start; L.n = Cn.size;
+    L.r0 = B.r0; L.m = B.m; L.c0 = B.c0; L.n = B.n;
     L.adm = B.admissible ? 1 : 0;
     L.off = off;
     if (B.admissible) {
@@ -414,8 +426,8 @@ int hmat_create(HMat &H, const BemDev &bem, const double *hx, const uint *htri, 
       off += (size_t)(L.m + L.n) * L.kcap;
       far_ids.push_back((uint)b);
     } else {
-      L.rtl = tri_list(B.rc);
-      L.ctl = tri_list(B.cc);
+      L.rtl = tri_list(B.r0, B.m);
+      L.ctl = tri_list(B.c0, B.n);
       off += (size_t)L.m * L.n;
       near_ids.push_back((uint)b);
     }
@@ -434,6 +446,20 @@ int hmat_create(HMat &H, const BemDev &bem, const double *hx, const uint *htri, 
   CNLD_CK(cudaMalloc(&H.d_pool, sizeof(cplx) * (off ? off : 1)));
   CNLD_CK(cudaMalloc(&H.d_flags, foff ? foff : 1));
   CNLD_CK(cudaMalloc(&H.d_err, sizeof(uint)));
+  return 0;
+}
+
+// matvec-only H-matrix from host leaf data: `leaf` (off/k/kcap filled) and a packed pool
+int hmat_from_host(HMat &H, int device, uint n, const std::vector<uint> &perm, const std::vector<HLeafDev> &leaf,
+                   const std::vector<cplx> &pool) {
+  H.bem = nullptr;
+  H.n = n;
+  H.tree.perm = perm;
+  H.leaf = leaf;
+  H.pool_size = pool.size();
+  CNLD_CK(cudaSetDevice(device));
+  if (to_device(H.d_leaf, H.leaf) || to_device(H.d_perm, H.tree.perm) || to_device(H.d_pool, pool)) return -1;
+  H.assembled = true;
   return 0;
 }
 

@@ -31,7 +31,7 @@ struct BlockLeaf {
 // DOF = vertex (linear basis): characteristic point = vertex, support box = box of its triangle fan
 void build_vertex_cluster_tree(unsigned nv, unsigned nt, const double *x, const unsigned *tri, unsigned clf,
                                ClusterTree &T);
-bool admissible(const ClusterNode &r, const ClusterNode &c, double eta, Admis kind);
+bool is_admissible(const ClusterNode &r, const ClusterNode &c, double eta, Admis kind);
 void build_block_leaves(const ClusterTree &T, double eta, Admis kind, bool strict, std::vector<BlockLeaf> &leaves);
 
 }  // namespace cnld

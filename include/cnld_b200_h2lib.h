@@ -155,6 +155,7 @@ typedef struct _bem3d {
   field kernel_const;             /* 1/(4 pi) (helmholtzbem3d.h:35) */
   void *priv;                     /* cnld_ctx of the device-side state */
   uint q_regular, q_singular;
+  real accur;                     /* ACA accuracy set by setup_hmatrix_aprx_*_bem3d */
 } bem3d, *pbem3d;
 typedef const bem3d *pcbem3d;
 pbem3d new_bem3d(pcsurface3d gr, basisfunctionbem3d row_basis, basisfunctionbem3d col_basis);
@@ -162,6 +163,106 @@ void del_bem3d(pbem3d bem);
 pbem3d new_slp_helmholtz_bem3d(field k, pcsurface3d gr, uint q_regular, uint q_singular,
                                basisfunctionbem3d row_basis, basisfunctionbem3d col_basis);
 void assemble_bem3d_amatrix(pbem3d bem, pamatrix G);
+
+/* ---- cluster / block trees (_cluster.pxd:7-23, _block.pxd:8-31; cluster.h:40-70, block.h:48-69) */
+typedef struct _cluster cluster, *pcluster;
+typedef const cluster *pccluster;
+struct _cluster {
+  uint size;
+  uint *idx;        /* sons' idx point into the father's array (root owns it) */
+  uint sons;
+  pcluster *son;
+  uint dim;
+  real *bmin;
+  real *bmax;
+  uint desc;
+  uint type;
+};
+pcluster new_cluster(uint size, uint *idx, uint sons, uint dim);
+void del_cluster(pcluster t);
+typedef struct _block block, *pblock;
+typedef const block *pcblock;
+struct _block {
+  pcluster rc;
+  pcluster cc;
+  bool a;           /* admissible */
+  pblock *son;      /* son[i + j*rsons] */
+  uint rsons;
+  uint csons;
+  uint desc;
+};
+typedef bool (*admissible)(pcluster rc, pcluster cc, void *data);
+pblock new_block(pcluster rc, pcluster cc, bool a, uint rsons, uint csons);
+void del_block(pblock b);
+pblock build_nonstrict_block(pcluster rc, pcluster cc, void *data, admissible admis);
+pblock build_strict_block(pcluster rc, pcluster cc, void *data, admissible admis);
+bool admissible_2_cluster(pcluster rc, pcluster cc, void *data);       /* data = real *eta */
+bool admissible_max_cluster(pcluster rc, pcluster cc, void *data);
+bool admissible_sphere_cluster(pcluster rc, pcluster cc, void *data);
+bool admissible_2_min_cluster(pcluster rc, pcluster cc, void *data);
+pcluster build_bem3d_cluster(pcbem3d bem, uint clf, basisfunctionbem3d basis);
+
+/* ---- rkmatrix / hmatrix (_rkmatrix.pxd:7-19, _hmatrix.pxd:12-46; rkmatrix.h:36-44, hmatrix.h:49-72) */
+typedef struct _rkmatrix {
+  amatrix A;        /* rows x k */
+  amatrix B;        /* cols x k; block = A B^* */
+  uint k;
+} rkmatrix, *prkmatrix;
+typedef const rkmatrix *pcrkmatrix;
+prkmatrix new_rkmatrix(uint rows, uint cols, uint k);
+void del_rkmatrix(prkmatrix r);
+typedef struct _hmatrix hmatrix, *phmatrix;
+typedef const hmatrix *pchmatrix;
+struct _hmatrix {
+  pccluster rc;
+  pccluster cc;
+  prkmatrix r;      /* admissible leaf */
+  pamatrix f;       /* inadmissible leaf */
+  phmatrix *son;    /* son[i + j*rsons] */
+  uint rsons;
+  uint csons;
+  uint refs;
+  uint desc;
+};
+phmatrix new_hmatrix(pccluster rc, pccluster cc);
+void del_hmatrix(phmatrix hm);
+void clear_hmatrix(phmatrix hm);
+void copy_hmatrix(pchmatrix src, phmatrix trg);
+phmatrix clone_hmatrix(pchmatrix src);
+phmatrix clonestructure_hmatrix(pchmatrix src);
+size_t getsize_hmatrix(pchmatrix hm);
+uint getrows_hmatrix(pchmatrix hm);
+uint getcols_hmatrix(pchmatrix hm);
+phmatrix build_from_block_hmatrix(pcblock b, uint k);
+void addeval_hmatrix_avector(field alpha, pchmatrix hm, pcavector x, pavector y);
+void addevalsymm_hmatrix_avector(field alpha, pchmatrix hm, pcavector x, pavector y);
+void copy_sparsematrix_hmatrix(psparsematrix sp, phmatrix hm);
+void identity_hmatrix(phmatrix hm);
+void add_hmatrix_amatrix(field alpha, bool atrans, pchmatrix a, pamatrix b);   /* harith.h:88 */
+void scale_hmatrix(field alpha, phmatrix hm);   /* not in H2Lib's pxd: exact replacement for the
+                                                   truncated identity product of HFormat._smul */
+void setup_hmatrix_aprx_aca_bem3d(pbem3d bem, pccluster rc, pccluster cc, pcblock tree, real accur);
+void setup_hmatrix_aprx_paca_bem3d(pbem3d bem, pccluster rc, pccluster cc, pcblock tree, real accur);
+void setup_hmatrix_aprx_hca_bem3d(pbem3d bem, pccluster rc, pccluster cc, pcblock tree, uint m, real accur);
+void setup_hmatrix_aprx_inter_row_bem3d(pbem3d bem, pccluster rc, pccluster cc, pcblock tree, uint m);
+void assemble_bem3d_hmatrix(pbem3d bem, pblock b, phmatrix G);
+
+/* ---- truncation (_truncation.pxd:8-22) -- carried for call compatibility only ------------- */
+typedef struct _truncmode {
+  bool frobenius;
+  bool absolute;
+  bool blocks;
+  real zeta_level;
+  real zeta_age;
+} truncmode, *ptruncmode;
+typedef const truncmode *pctruncmode;
+ptruncmode new_truncmode(void);
+void del_truncmode(ptruncmode tm);
+ptruncmode new_releucl_truncmode(void);
+
+/* ---- krylovsolvers (_krylovsolvers.pxd:10-13; krylovsolvers.h:283) -------------------------- */
+uint solve_gmres_amatrix_avector(pcamatrix A, pcavector b, pavector x, real eps, uint maxiter, uint kmax);
+uint solve_gmres_hmatrix_avector(pchmatrix A, pcavector b, pavector x, real eps, uint maxiter, uint kmax);
 
 /* ---- factorizations (_factorizations.pxd:13-19; factorizations.h:173-233) --- */
 uint lrdecomp_amatrix(pamatrix a);
