@@ -46,6 +46,7 @@ def lib():
         L.cnld_b200_set_streams.argtypes = [vp, C.c_int]
         L.cnld_b200_get_geometry.argtypes = [vp, vp, vp]
         L.cnld_b200_assemble_slp_ll.argtypes = [vp, f64, f64, vp, u32]
+        L.cnld_b200_nearfield_slp_ll.argtypes = [vp, f64, f64, vp, u32, vp, u32, vp, u32]
         L.cnld_b200_lrdecomp.argtypes = [C.c_int, u32, vp, u32, vp]
         L.cnld_b200_lrsolve.argtypes = [C.c_int, u32, vp, u32, vp, u32, u32]
         L.cnld_b200_zgemm.argtypes = [C.c_int, u32, u32, u32, f64, vp, u32, vp, u32, f64, vp, u32]
@@ -130,6 +131,15 @@ class Context:
         k = complex(k)
         buf = np.zeros((self.nv, self.nv), dtype=np.complex128)  # column-major => buf = Z^T
         check(lib().cnld_b200_assemble_slp_ll(self._h, k.real, k.imag, ptr(buf), self.nv))
+        return buf.T
+
+    def nearfield(self, k, ridx, cidx):
+        """Z[ridx, cidx] (bem->nearfield): Galerkin entries for arbitrary vertex index sets."""
+        k = complex(k)
+        ridx, cidx = _c(ridx, np.uint32), _c(cidx, np.uint32)
+        buf = np.zeros((len(cidx), len(ridx)), dtype=np.complex128)
+        check(lib().cnld_b200_nearfield_slp_ll(self._h, k.real, k.imag, ptr(ridx), len(ridx), ptr(cidx), len(cidx),
+                                               ptr(buf), max(len(ridx), 1)))
         return buf.T
 
     def set_mbk(self, K, M, B):

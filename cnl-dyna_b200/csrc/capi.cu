@@ -7,7 +7,7 @@
 #include <cmath>
 #include <mutex>
 
-#include "bem.cuh"
+#include "hmat.cuh"
 
 namespace cnld {
 std::atomic<unsigned long long> g_launches{0};
@@ -301,11 +301,21 @@ int cnld_b200_assemble_slp_ll(cnld_ctx *c, double k_re, double k_im, cnld_field 
   return rc;
 }
 
-int cnld_b200_nearfield_slp_ll(cnld_ctx *c, double, double, const cnld_uint *, cnld_uint, const cnld_uint *,
-                               cnld_uint, cnld_field *, cnld_uint) {
-  (void)c;
-  set_error("cnld_b200_nearfield_slp_ll: not available in this build");
-  return -1;
+int cnld_b200_nearfield_slp_ll(cnld_ctx *c, double k_re, double k_im, const cnld_uint *ridx, cnld_uint rows,
+                               const cnld_uint *cidx, cnld_uint cols, cnld_field *N, cnld_uint ld) {
+  if (!c) { set_error("null context"); return -1; }
+  if (ld < rows) { set_error("ld < rows"); return -1; }
+  if (rows == 0 || cols == 0) return 0;
+  CNLD_CK(cudaSetDevice(c->bem.device));
+  cplx *d = nullptr;
+  CNLD_CK(cudaMalloc(&d, sizeof(cplx) * (size_t)rows * cols));
+  int rc = nearfield_block(0, c->bem, c->h_t.data(), ridx, rows, cidx, cols, k_re, k_im, d);
+  if (!rc) {
+    cudaError_t e = cudaMemcpy2D(N, sizeof(cplx) * ld, d, sizeof(cplx) * rows, sizeof(cplx) * rows, cols, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("nearfield: %s", cudaGetErrorString(e)); rc = -1; }
+  }
+  cudaFree(d);
+  return rc;
 }
 
 int cnld_b200_lrdecomp(int device, cnld_uint n, cnld_field *a, cnld_uint ld, cnld_uint *info) {

@@ -24,7 +24,7 @@ struct HMat {
   size_t pool_size = 0, near_entries = 0;
   bool assembled = false;
   HLeafDev *d_leaf = nullptr;
-  uint *d_near = nullptr, *d_far = nullptr, *d_perm = nullptr, *d_pos = nullptr;
+  uint *d_near = nullptr, *d_far = nullptr, *d_perm = nullptr, *d_pos = nullptr, *d_cpos = nullptr;
   uint *d_ctri_ptr = nullptr, *d_ctri = nullptr, *d_v2t_ptr = nullptr, *d_v2t = nullptr;
   cplx *d_pool = nullptr;
   unsigned char *d_flags = nullptr;
@@ -45,5 +45,7 @@ int hmat_assemble(cudaStream_t st, HMat &H, double kr, double ki, double accur);
 int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y, uint nrhs);
 int hmat_expand(cudaStream_t st, HMat &H, cplx *d_Z, size_t ld);
 int hmat_fetch_leaves(HMat &H);
+int nearfield_block(cudaStream_t st, const BemDev &bem, const uint *htri, const uint *ridx, uint rows,
+                    const uint *cidx, uint cols, double kr, double ki, cplx *d_out);
 
 }  // namespace cnld

@@ -39,8 +39,8 @@ __global__ void __launch_bounds__(NEAR_THREADS)
 k_near(const HLeafDev *__restrict__ leaves, const uint *__restrict__ near_ids, const __grid_constant__ RegRule R,
        const SingTables tab, const double *__restrict__ x, const uint *__restrict__ tri,
        const double *__restrict__ qp, const double *__restrict__ g, const uint *__restrict__ pos,
-       const uint *__restrict__ ctri_ptr, const uint *__restrict__ ctri, double kr, double ki, cplx *pool,
-       uint *err) {
+       const uint *__restrict__ cposv, const uint *__restrict__ ctri_ptr, const uint *__restrict__ ctri, double kr,
+       double ki, cplx *pool, uint *err) {
   __shared__ uint2 queue[NEAR_QCAP];
   __shared__ uint qn;
   const HLeafDev L = leaves[near_ids[blockIdx.x]];
@@ -78,7 +78,7 @@ k_near(const HLeafDev *__restrict__ leaves, const uint *__restrict__ near_ids, c
       if (pr >= L.m) continue;
 #pragma unroll
       for (int j = 0; j < 3; j++) {
-        uint pc = pos[sv[j]] - L.c0;
+        uint pc = cposv[sv[j]] - L.c0;
         if (pc < L.n) red_add(D + (size_t)pc * L.m + pr, make_double2(loc[i][j].x * sc, loc[i][j].y * sc));
       }
     }
@@ -112,7 +112,7 @@ k_near(const HLeafDev *__restrict__ leaves, const uint *__restrict__ near_ids, c
         uint pr = pos[rv[i]] - L.r0;
         if (pr >= L.m) continue;
         for (int j = 0; j < 3; j++) {
-          uint pc = pos[cv[j]] - L.c0;
+          uint pc = cposv[cv[j]] - L.c0;
           if (pc < L.n) red_add(D + (size_t)pc * L.m + pr, make_double2(acc[2 * (3 * i + j)] * sc, acc[2 * (3 * i + j) + 1] * sc));
         }
       }
@@ -353,6 +353,12 @@ __global__ void k_expand(const HLeafDev *__restrict__ leaves, const cplx *__rest
   }
 }
 
+__global__ void k_untile(const HLeafDev *__restrict__ leaves, const cplx *__restrict__ pool, cplx *out, size_t ld) {
+  const HLeafDev L = leaves[blockIdx.x];
+  for (size_t e = threadIdx.x; e < (size_t)L.m * L.n; e += blockDim.x)
+    out[(size_t)(L.c0 + e / L.m) * ld + L.r0 + e % L.m] = pool[L.off + e];
+}
+
 template <typename T>
 int to_device(T *&d, const std::vector<T> &h) {
   CNLD_CK(cudaMalloc(&d, sizeof(T) * (h.size() ? h.size() : 1)));
@@ -466,7 +472,7 @@ int hmat_from_host(HMat &H, int device, uint n, const std::vector<uint> &perm, c
 void hmat_free(HMat &H) {
   cudaFree(H.d_leaf); cudaFree(H.d_near); cudaFree(H.d_far); cudaFree(H.d_perm); cudaFree(H.d_pos);
   cudaFree(H.d_ctri_ptr); cudaFree(H.d_ctri); cudaFree(H.d_v2t_ptr); cudaFree(H.d_v2t); cudaFree(H.d_pool);
-  cudaFree(H.d_flags); cudaFree(H.d_err); cudaFree(H.d_xp); cudaFree(H.d_yp);
+  cudaFree(H.d_flags); cudaFree(H.d_err); cudaFree(H.d_xp); cudaFree(H.d_yp); cudaFree(H.d_cpos);
   H = HMat();
 }
 
@@ -476,10 +482,12 @@ static int assemble_nq(cudaStream_t st, HMat &H, double kr, double ki, double ac
   if (H.nnear) {
     if (ki != 0.0)
       k_near<NQ, true><<<H.nnear, NEAR_THREADS, 0, st>>>(H.d_leaf, H.d_near, b.rule, b.sing, b.x, b.t, b.qp, b.g,
-                                                          H.d_pos, H.d_ctri_ptr, H.d_ctri, kr, ki, H.d_pool, H.d_err);
+                                                          H.d_pos, H.d_cpos ? H.d_cpos : H.d_pos, H.d_ctri_ptr,
+                                                          H.d_ctri, kr, ki, H.d_pool, H.d_err);
     else
       k_near<NQ, false><<<H.nnear, NEAR_THREADS, 0, st>>>(H.d_leaf, H.d_near, b.rule, b.sing, b.x, b.t, b.qp, b.g,
-                                                           H.d_pos, H.d_ctri_ptr, H.d_ctri, kr, ki, H.d_pool, H.d_err);
+                                                           H.d_pos, H.d_cpos ? H.d_cpos : H.d_pos, H.d_ctri_ptr,
+                                                           H.d_ctri, kr, ki, H.d_pool, H.d_err);
     CNLD_CK_LAUNCH();
   }
   if (H.nfar) {
@@ -540,6 +548,82 @@ int hmat_expand(cudaStream_t st, HMat &H, cplx *d_Z, size_t ld) {
   k_expand<<<(unsigned)H.leaf.size(), 256, 0, st>>>(H.d_leaf, H.d_pool, H.d_perm, d_Z, ld);
   CNLD_CK_LAUNCH();
   return 0;
+}
+
+// bem->nearfield(ridx, cidx): dense sub-block for arbitrary vertex index sets, tiled 32 x 256 so the
+// touching-pair queue of k_near cannot overflow.  d_out is rows x cols column-major (ld = rows).
+int nearfield_block(cudaStream_t st, const BemDev &bem, const uint *htri, const uint *ridx, uint rows,
+                    const uint *cidx, uint cols, double kr, double ki, cplx *d_out) {
+  const uint NONE = 0xffffffffu, TR = 32, TC = 256;
+  HMat H;
+  H.bem = &bem;
+  H.n = bem.nv;
+  std::vector<uint> rpos(bem.nv, NONE), cpos(bem.nv, NONE);
+  for (uint i = 0; i < rows; i++) {
+    if (ridx[i] >= bem.nv || rpos[ridx[i]] != NONE) { set_error("nearfield: bad or repeated row index"); return -1; }
+    rpos[ridx[i]] = i;
+  }
+  for (uint i = 0; i < cols; i++) {
+    if (cidx[i] >= bem.nv || cpos[cidx[i]] != NONE) { set_error("nearfield: bad or repeated column index"); return -1; }
+    cpos[cidx[i]] = i;
+  }
+  std::vector<uint> vstart(bem.nv + 1, 0), vadj(3 * (size_t)bem.nt);
+  for (size_t i = 0; i < 3 * (size_t)bem.nt; i++) vstart[htri[i] + 1]++;
+  for (uint v = 0; v < bem.nv; v++) vstart[v + 1] += vstart[v];
+  {
+    std::vector<uint> fill(vstart.begin(), vstart.end() - 1);
+    for (uint t = 0; t < bem.nt; t++)
+      for (uint d = 0; d < 3; d++) vadj[fill[htri[3 * (size_t)t + d]]++] = t;
+  }
+  std::vector<uint> ctri_ptr(1, 0), ctri;
+  auto tri_list = [&](const uint *idx, uint cnt) -> uint {
+    std::vector<uint> ts;
+    for (uint i = 0; i < cnt; i++)
+      for (uint e = vstart[idx[i]]; e < vstart[idx[i] + 1]; e++) ts.push_back(vadj[e]);
+    std::sort(ts.begin(), ts.end());
+    ts.erase(std::unique(ts.begin(), ts.end()), ts.end());
+    ctri.insert(ctri.end(), ts.begin(), ts.end());
+    ctri_ptr.push_back((uint)ctri.size());
+    return (uint)ctri_ptr.size() - 2;
+  };
+  std::vector<uint> rlist, clist;
+  for (uint r0 = 0; r0 < rows; r0 += TR) rlist.push_back(tri_list(ridx + r0, std::min(TR, rows - r0)));
+  for (uint c0 = 0; c0 < cols; c0 += TC) clist.push_back(tri_list(cidx + c0, std::min(TC, cols - c0)));
+  // tiles write straight into the strided output: leaf offset = element (r0, c0), "m" = tile rows.
+  // k_near addresses D[pc * L.m + pr]; with a strided target we need ld = rows, so every tile is
+  // assembled into a compact scratch tile and copied out afterwards.
+  std::vector<uint> near_ids;
+  size_t off = 0;
+  for (uint ci = 0, c0 = 0; c0 < cols; c0 += TC, ci++)
+    for (uint ri = 0, r0 = 0; r0 < rows; r0 += TR, ri++) {
+      HLeafDev L;
+      memset(&L, 0, sizeof(L));
+      L.r0 = r0; L.m = std::min(TR, rows - r0); L.c0 = c0; L.n = std::min(TC, cols - c0);
+      L.rtl = rlist[ri]; L.ctl = clist[ci];
+      L.off = off;
+      off += (size_t)L.m * L.n;
+      near_ids.push_back((uint)H.leaf.size());
+      H.leaf.push_back(L);
+    }
+  H.pool_size = off;
+  H.nnear = (uint)near_ids.size();
+  H.nfar = 0;
+  CNLD_CK(cudaSetDevice(bem.device));
+  std::vector<uint> perm(bem.nv);
+  for (uint i = 0; i < bem.nv; i++) perm[i] = i;
+  int rc = 0;
+  if (to_device(H.d_leaf, H.leaf) || to_device(H.d_near, near_ids) || to_device(H.d_pos, rpos) || to_device(H.d_cpos, cpos) ||
+      to_device(H.d_ctri_ptr, ctri_ptr) || to_device(H.d_ctri, ctri) || to_device(H.d_perm, perm)) rc = -1;
+  if (!rc && cudaMalloc(&H.d_pool, sizeof(cplx) * (off ? off : 1)) != cudaSuccess) { set_error("nearfield: out of memory"); rc = -1; }
+  if (!rc && cudaMalloc(&H.d_err, sizeof(uint)) != cudaSuccess) { set_error("nearfield: out of memory"); rc = -1; }
+  if (!rc) rc = hmat_assemble(st, H, kr, ki, 0.0);
+  if (!rc) {
+    k_untile<<<(unsigned)H.leaf.size(), 256, 0, st>>>(H.d_leaf, H.d_pool, d_out, rows);
+    CNLD_CK_LAUNCH();
+    CNLD_CK(cudaStreamSynchronize(st));
+  }
+  hmat_free(H);
+  return rc;
 }
 
 int hmat_fetch_leaves(HMat &H) {

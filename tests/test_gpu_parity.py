@@ -109,3 +109,21 @@ def test_pressure_vs_oracle(L, po):
         ref = disp[ik] @ pv.T                    # [nsrc, nobs]   (p_vector.dot(disp))
         assert _rel(p[ik], ref) < 1e-11
     ctx.close()
+
+
+def test_nearfield_subblock_vs_oracle_and_dense(L, po):
+    am = po.array_mesh(po.matrix_array(nelem=(2, 1)), 5)
+    k = 2 * np.pi * 9e6 / 1500
+    ctx = L.Context(am.vertices, am.triangles)
+    Z = ctx.assemble_z(k)
+    rng = np.random.default_rng(5)
+    for nr, nc in [(1, 1), (7, 122), (40, 3), (100, 100)]:
+        ri = rng.choice(am.nvertices, nr, replace=False).astype(np.uint32)
+        ci = rng.choice(am.nvertices, nc, replace=False).astype(np.uint32)
+        N = ctx.nearfield(k, ri, ci)
+        assert np.abs(N - Z[np.ix_(ri, ci)]).max() / np.abs(Z).max() < 1e-10
+        assert np.abs(N - po.nearfield(am, k, ri, ci)).max() / np.abs(Z).max() < 1e-10
+    assert ctx.nearfield(k, np.zeros(0, np.uint32), np.arange(4, dtype=np.uint32)).shape == (0, 4)     # empty input
+    with pytest.raises(L.Cnldb200Error):
+        ctx.nearfield(k, [1, 1], [2])          # repeated index
+    ctx.close()
