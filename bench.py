@@ -219,12 +219,15 @@ def main():
     value = args.steps * nfb * world / dt
 
     # ---- end to end through the public API (host buffers in, host buffers out) -------------
+    out_nodes = np.empty((nfb, P, N), dtype=np.complex128)
+    sweep.upload()
+    sweep.run(batch(0), want_nodes=True, out_nodes=out_nodes)     # untimed: pinned staging is allocated here
     barrier()
     t0 = time.perf_counter()
     d2h = 0
     for s in range(args.steps):
         h2d = sweep.upload() + 8 * nfb
-        xp, xn, _ = sweep.run(batch(args.warmup + s), want_nodes=True)
+        xp, xn, _ = sweep.run(batch(args.warmup + s), want_nodes=True, out_nodes=out_nodes)
         d2h = xp.nbytes + xn.nbytes
     barrier()
     dte = time.perf_counter() - t0

@@ -13,6 +13,7 @@ struct SingTables {
 struct RegRule {        // single-triangle Duffy-Gauss rule, passed by value to kernels
   double w[16];         // weights (sum 1/2)
   double phi[16][3];    // hat values (1-t, t-s, s) at the points
+  double wphi[16][3];   // w * phi
 };
 
 struct BemDev {

@@ -96,10 +96,25 @@ int ensure_workspace(cnld_ctx *c, bool need_host_stage) {
   CNLD_CK(cudaSetDevice(c->bem.device));
   for (int s = 0; s < c->nslots; s++) {
     Slot &S = c->slots[s];
-    if (!S.st) CNLD_CK(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+    if (!S.st) {
+      int lo_p = 0, hi_p = 0;
+      CNLD_CK(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));   // (least, greatest); greatest is numerically lowest
+      CNLD_CK(cudaStreamCreateWithPriority(&S.st, cudaStreamNonBlocking, hi_p));
+      CNLD_CK(cudaStreamCreateWithPriority(&S.st_lo, cudaStreamNonBlocking, (lo_p + hi_p) / 2));
+      CNLD_CK(cudaStreamCreateWithPriority(&S.st_asm, cudaStreamNonBlocking, lo_p));
+      CNLD_CK(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming));
+      CNLD_CK(cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming));
+    }
     if (!S.G) CNLD_CK(cudaMalloc(&S.G, sizeof(cplx) * nv * nv));
     if (!S.X) CNLD_CK(cudaMalloc(&S.X, sizeof(cplx) * nv * (c->P ? c->P : 1)));
-    if (!S.lu.linv && lu_work_alloc(S.lu, (uint)nv)) return -1;
+    if (!S.lu.linv) {
+      if (lu_work_alloc(S.lu, (uint)nv)) return -1;
+      if (c->nslots > 1) {
+        S.lu.lo = S.st_lo;
+        CNLD_CK(cudaEventCreateWithFlags(&S.lu.ev_fork, cudaEventDisableTiming));
+        CNLD_CK(cudaEventCreateWithFlags(&S.lu.ev_join, cudaEventDisableTiming));
+      }
+    }
     lu_profile(S.lu, c->profile);
     for (int e = 0; e < 4; e++)
       if (!S.ev[e]) CNLD_CK(cudaEventCreate(&S.ev[e]));
@@ -118,6 +133,10 @@ void free_workspace(cnld_ctx *c) {
     lu_work_free(S.lu);
     for (int e = 0; e < 4; e++) if (S.ev[e]) cudaEventDestroy(S.ev[e]);
     if (S.st) cudaStreamDestroy(S.st);
+    if (S.st_lo) cudaStreamDestroy(S.st_lo);
+    if (S.st_asm) cudaStreamDestroy(S.st_asm);
+    if (S.ev_fork) cudaEventDestroy(S.ev_fork);
+    if (S.ev_join) cudaEventDestroy(S.ev_join);
     S = Slot();
   }
   c->ws_ready = false;
@@ -134,7 +153,17 @@ int enqueue_frequency(cnld_ctx *c, Slot &S, double f, double cs, double rho, cpl
   CNLD_CK_LAUNCH();
   if (f != 0.0) {
     // Gbe = -omg^2 * 2 * rho * Z   (generate_db.py:55-56)
-    if (bem_assemble(S.st, c->bem, k, 0.0, make_double2(-omega * omega * 2.0 * rho, 0.0), S.G, nv)) return -1;
+    cudaStream_t as = S.st;
+    if (c->nslots > 1) {  // throughput kernel -> low-priority companion stream
+      CNLD_CK(cudaEventRecord(S.ev_fork, S.st));
+      CNLD_CK(cudaStreamWaitEvent(S.st_asm, S.ev_fork, 0));
+      as = S.st_asm;
+    }
+    if (bem_assemble(as, c->bem, k, 0.0, make_double2(-omega * omega * 2.0 * rho, 0.0), S.G, nv)) return -1;
+    if (c->nslots > 1) {
+      CNLD_CK(cudaEventRecord(S.ev_join, S.st_asm));
+      CNLD_CK(cudaStreamWaitEvent(S.st, S.ev_join, 0));
+    }
   }
   CNLD_CK(cudaEventRecord(S.ev[1], S.st));
   if (lu_factor(S.st, S.lu, S.G, nv)) return -1;

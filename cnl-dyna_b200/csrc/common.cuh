@@ -83,6 +83,8 @@ struct LuWork {
   cplx *uinv = nullptr;  // [nblk][nb*nb]
   uint *info = nullptr;  // device flag: 0 ok else first failing pivot + 1
   cplx *panel = nullptr; // scratch for out-of-place panel updates
+  cudaStream_t lo = nullptr;  // optional low-priority stream for the big trailing updates
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool prof = false;     // record events around every trailing-update ZGEMM
   std::vector<cudaEvent_t> pe;
 };

@@ -9,7 +9,10 @@ constexpr int MAX_SLOTS = 8;
 constexpr double TWO_PI = 6.283185307179586476925286766559;
 
 struct Slot {
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr;      // high priority: latency-bound kernels
+  cudaStream_t st_lo = nullptr;   // medium priority: trailing updates (DMMA tensor pipe)
+  cudaStream_t st_asm = nullptr;  // lowest priority: assembly (FP64 ALU pipe) fills what the LU leaves free
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cplx *G = nullptr;      // nv x nv
   cplx *X = nullptr;      // nv x P
   cplx *hX = nullptr;     // pinned staging for x_node

@@ -145,11 +145,11 @@ __device__ cplx far_entry(uint vi, uint vj, const RegRule &R, const double *__re
         for (int q = 0; q < NQ; q++) {
           double dx = xp[p][0] - yq[3 * q], dy = xp[p][1] - yq[3 * q + 1], dz = xp[p][2] - yq[3 * q + 2];
           cplx kv = helmholtz<CPLXK>(dx * dx + dy * dy + dz * dz, kr, ki);
-          double wq = R.w[q] * R.phi[q][lj];
+          double wq = R.wphi[q][lj];
           ap.x = fma(wq, kv.x, ap.x);
           ap.y = fma(wq, kv.y, ap.y);
         }
-        double wp = R.w[p] * R.phi[p][li];
+        double wp = R.wphi[p][li];
         acc.x = fma(wp, ap.x, acc.x);
         acc.y = fma(wp, ap.y, acc.y);
       }

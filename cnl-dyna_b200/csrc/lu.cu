@@ -115,6 +115,8 @@ void lu_work_free(LuWork &w) {
   cudaFree(w.info);
   cudaFree(w.panel);
   for (auto &e : w.pe) cudaEventDestroy(e);
+  if (w.ev_fork) cudaEventDestroy(w.ev_fork);
+  if (w.ev_join) cudaEventDestroy(w.ev_join);
   w = LuWork();
 }
 
@@ -205,9 +207,22 @@ int lu_factor(cudaStream_t st, LuWork &w, cplx *a, size_t lda) {
     const uint rem = n - OE;
     if (rem) {
       cplx *l = a + (size_t)O * lda + OE, *u = a + (size_t)OE * lda + O, *t = a + (size_t)OE * lda + OE;
-      if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * ob], st));
-      if (zgemm3m(st, rem, rem, W, -1.0, l, lda, u, lda, 1.0, t, lda)) return -1;
-      if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * ob + 1], st));
+      // The rank-W update is the throughput kernel; when a low-priority companion stream is set
+      // it runs there, so that the latency-bound panel kernels of OTHER frequencies (high-priority
+      // streams) get SM slots as soon as any of its CTAs retires.
+      cudaStream_t ts = st;
+      if (w.lo) {
+        CNLD_CK(cudaEventRecord(w.ev_fork, st));
+        CNLD_CK(cudaStreamWaitEvent(w.lo, w.ev_fork, 0));
+        ts = w.lo;
+      }
+      if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * ob], ts));
+      if (zgemm3m(ts, rem, rem, W, -1.0, l, lda, u, lda, 1.0, t, lda)) return -1;
+      if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * ob + 1], ts));
+      if (w.lo) {
+        CNLD_CK(cudaEventRecord(w.ev_join, w.lo));
+        CNLD_CK(cudaStreamWaitEvent(st, w.ev_join, 0));
+      }
     }
   }
   w.nouter = ob;

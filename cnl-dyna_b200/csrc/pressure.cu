@@ -10,13 +10,12 @@
 //   (D_g = scale * area/3/(4 pi) * sum_l N_l(xi_g) disp[v_l]) and every thread owns one
 //   observation point, streaming the 3*nt source points through shared memory:
 //   p(obs) = sum_g D_g * e^{-j k r}/r.  FP64 sincos/rsqrt bound.
-#include "bem.cuh"
+#include "pair.cuh"
 
 namespace cnld {
 namespace {
 __constant__ double c_xi[3] = {1.0 / 6, 2.0 / 3, 1.0 / 6};
 __constant__ double c_eta[3] = {1.0 / 6, 1.0 / 6, 2.0 / 3};
-constexpr double INV4PI = 0.0795774715459476678844418816863;
 
 __global__ void k_pres_vector(uint nt, const double *__restrict__ x, const uint *__restrict__ tri,
                               const double *__restrict__ g, const double *__restrict__ obs, double k,
@@ -34,7 +33,7 @@ __global__ void k_pres_vector(uint nt, const double *__restrict__ x, const uint 
       double xs = x1 * n0 + x2 * xi + x3 * eta, ys = y1 * n0 + y2 * xi + y3 * eta;
       double r2 = (ox - xs) * (ox - xs) + (oy - ys) * (oy - ys) + oz * oz;
       double rinv = rsqrt(r2), r = r2 * rinv, s, c;
-      sincos(k * r, &s, &c);
+      sincos_fast(k * r, s, c);
       double f = scale * (1.0 / 3) * INV4PI * rinv * da;
       double cr = f * c, ci = -f * s;
       atomicAdd(p + 2 * (size_t)v0, n0 * cr);  atomicAdd(p + 2 * (size_t)v0 + 1, n0 * ci);
@@ -105,7 +104,7 @@ k_pressure(uint nobs, const double *__restrict__ obs, uint npts, const double *_
       double dx = ox - s_xy[i][0], dy = oy - s_xy[i][1];
       double r2 = fma(dx, dx, fma(dy, dy, oz2));
       double rinv = rsqrt(r2), r = r2 * rinv, sn, cs;
-      sincos(k * r, &sn, &cs);
+      sincos_fast(k * r, sn, cs);
       double er = cs * rinv, ei = -sn * rinv;
 #pragma unroll
       for (int s = 0; s < NS; s++) {

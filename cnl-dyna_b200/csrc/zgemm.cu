@@ -165,7 +165,7 @@ zgemm_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A, s
 // 25 % fewer DMMAs on the FP64 tensor pipe, which is what bounds the trailing updates.  Three
 // accumulator sets per warp tile, so the warp tile is 32x24 (144 accumulator registers) and the
 // CTA tile 64x48 (4 warps), still 2 CTAs/SM.  Used for C = C - A*B with C not aliasing A or B.
-constexpr int T3_BM = 64, T3_BN = 48, T3_NT = 128, T3_STAGES = 4;
+constexpr int T3_BM = 64, T3_BN = 48, T3_NT = 128, T3_STAGES = 4, T3_GM = 16;
 constexpr int T3_AS_LD = T3_BM + 2;
 constexpr int T3_A_STAGE = BK * T3_AS_LD, T3_B_STAGE = T3_BN * BS_LD;
 constexpr int T3_SMEM = T3_STAGES * (T3_A_STAGE + T3_B_STAGE) * (int)sizeof(cplx);
@@ -178,7 +178,12 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
   cplx *Bs = As + T3_STAGES * T3_A_STAGE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 1, wn = warp >> 1;
-  const uint m0 = blockIdx.x * T3_BM, n0 = blockIdx.y * T3_BN;
+  // grouped rasterisation: consecutive CTAs walk T3_GM row tiles x all column tiles, so the
+  // ~300 CTAs in flight share a few MB of A/B panels in L2 instead of streaming a whole panel
+  const uint mt = (M + T3_BM - 1) / T3_BM, nt = (N + T3_BN - 1) / T3_BN;
+  const uint gsz_full = T3_GM * nt, grp = blockIdx.x / gsz_full, first = grp * T3_GM;
+  const uint gm = min((uint)T3_GM, mt - first), within = blockIdx.x % gsz_full;
+  const uint m0 = (first + within % gm) * T3_BM, n0 = (within / gm) * T3_BN;
   const int nk = (K + BK - 1) / BK;
 
   auto load_stage = [&](int kc, int stage) {
@@ -292,7 +297,7 @@ int zgemm3m(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A
     CNLD_CK(cudaFuncSetAttribute(zgemm3m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM));
     attr_set[dev & 63] = true;
   }
-  dim3 grid((M + T3_BM - 1) / T3_BM, (N + T3_BN - 1) / T3_BN);
+  dim3 grid(((M + T3_BM - 1) / T3_BM) * ((N + T3_BN - 1) / T3_BN));
   zgemm3m_kernel<<<grid, T3_NT, T3_SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
   CNLD_CK_LAUNCH();
   return 0;
