@@ -17,6 +17,7 @@ Multi-GPU (torchrun, one rank per GPU): frequencies are sharded, no collective i
 frequency ("weak" scaling: per-GPU batch fixed); setup broadcast once, results gathered.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -141,6 +142,7 @@ def main():
     ap.add_argument('--streams', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--lu-outer', type=int, default=0, help='debug: outer LU block (multiple of 64)')
+    ap.add_argument('--lu-reserve', type=int, default=-1, help='debug: SMs left free by the look-ahead trailing update')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -171,6 +173,8 @@ def main():
         setup = broadcast_setup(setup, rank, torch.device('cuda', local))
     if args.lu_outer:
         _lib.lib().cnld_b200_set_lu_outer(args.lu_outer)
+    if args.lu_reserve >= 0:
+        _lib.lib().cnld_b200_set_lu_reserve(args.lu_reserve)
     sweep = FrequencySweep(setup, device=local, nstreams=args.streams)
     sweep.ctx.set_profile(True)
     t_setup = time.perf_counter() - t_setup

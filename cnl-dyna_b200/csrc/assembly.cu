@@ -44,11 +44,8 @@ __global__ void k_tri_setup(uint nt, uint nq, const __grid_constant__ RegRule R,
 constexpr int REG_THREADS = 128;
 constexpr int REG_CHUNK = 64;
 
-// (NQ = 4: capped at 102 registers so that one CTA fits on an SM next to two zgemm3m CTAs -- the
-//  FP64 ALU pipe this kernel lives on is separate from the DMMA tensor pipe the LU lives on, so the
-//  assembly of one frequency can hide under the factorisation of another)
 template <int NQ, bool CPLXK>
-__global__ void __launch_bounds__(REG_THREADS, NQ <= 4 ? 5 : 1)
+__global__ void __launch_bounds__(REG_THREADS)
 k_regular(uint nt, const __grid_constant__ RegRule R, const uint *__restrict__ tri,
           const double *__restrict__ qp, const double *__restrict__ g, double kr, double ki,
           cplx alpha, cplx *Z, size_t ld) {

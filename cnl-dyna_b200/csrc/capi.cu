@@ -100,7 +100,12 @@ int ensure_workspace(cnld_ctx *c, bool need_host_stage) {
       int lo_p = 0, hi_p = 0;
       CNLD_CK(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));   // (least, greatest); greatest is numerically lowest
       CNLD_CK(cudaStreamCreateWithPriority(&S.st, cudaStreamNonBlocking, hi_p));
-      CNLD_CK(cudaStreamCreateWithPriority(&S.st_lo, cudaStreamNonBlocking, (lo_p + hi_p) / 2));
+      // trailing updates: a different priority per slot, so the slots cannot stay in lock-step
+      // (one factorisation owns the tensor pipe while the other slot assembles on the FP64 pipe)
+      int mid = hi_p + 1 + s;
+      if (mid > lo_p - 1) mid = lo_p - 1;
+      if (mid < hi_p) mid = hi_p;
+      CNLD_CK(cudaStreamCreateWithPriority(&S.st_lo, cudaStreamNonBlocking, mid));
       CNLD_CK(cudaStreamCreateWithPriority(&S.st_asm, cudaStreamNonBlocking, lo_p));
       CNLD_CK(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming));
       CNLD_CK(cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming));
@@ -109,11 +114,9 @@ int ensure_workspace(cnld_ctx *c, bool need_host_stage) {
     if (!S.X) CNLD_CK(cudaMalloc(&S.X, sizeof(cplx) * nv * (c->P ? c->P : 1)));
     if (!S.lu.linv) {
       if (lu_work_alloc(S.lu, (uint)nv)) return -1;
-      if (c->nslots > 1) {
-        S.lu.lo = S.st_lo;
-        CNLD_CK(cudaEventCreateWithFlags(&S.lu.ev_fork, cudaEventDisableTiming));
-        CNLD_CK(cudaEventCreateWithFlags(&S.lu.ev_join, cudaEventDisableTiming));
-      }
+      S.lu.lo = S.st_lo;   // companion stream for the look-ahead trailing updates
+      CNLD_CK(cudaEventCreateWithFlags(&S.lu.ev_fork, cudaEventDisableTiming));
+      CNLD_CK(cudaEventCreateWithFlags(&S.lu.ev_join, cudaEventDisableTiming));
     }
     lu_profile(S.lu, c->profile);
     for (int e = 0; e < 4; e++)

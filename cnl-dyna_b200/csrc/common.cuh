@@ -65,6 +65,7 @@ __device__ __forceinline__ void cfms(cplx &c, cplx a, cplx b) {
 
 extern int g_zgemm_variant;
 extern int g_lu_outer;
+extern int g_lu_reserve_sms;
 // ---- dense kernels (zgemm.cu / lu.cu) --------------------------------------
 // C(MxN) = beta*C + alpha*A(MxK)*B(KxN); alpha in {+1,-1}, beta in {0,1};
 // column-major, interleaved complex.  In-place (C aliasing A or B) is safe only
@@ -74,7 +75,7 @@ int zgemm(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, 
 
 // same contract, 3M complex product (C must not alias A or B)
 int zgemm3m(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
-            const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc);
+            const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, int reserve_sms = 0);
 extern int g_zgemm_3m;
 
 struct LuWork {
@@ -87,6 +88,7 @@ struct LuWork {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool prof = false;     // record events around every trailing-update ZGEMM
   std::vector<cudaEvent_t> pe;
+  std::vector<double> pflops;  // executed flops of the launch bracketed by pe[2i], pe[2i+1]
 };
 int lu_work_alloc(LuWork &w, uint n);
 void lu_work_free(LuWork &w);

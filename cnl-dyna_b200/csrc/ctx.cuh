@@ -11,7 +11,9 @@ constexpr double TWO_PI = 6.283185307179586476925286766559;
 struct Slot {
   cudaStream_t st = nullptr;      // high priority: latency-bound kernels
   cudaStream_t st_lo = nullptr;   // medium priority: trailing updates (DMMA tensor pipe)
-  cudaStream_t st_asm = nullptr;  // lowest priority: assembly (FP64 ALU pipe) fills what the LU leaves free
+  cudaStream_t st_asm = nullptr;  // lowest priority: assembly.  (Measured on B200: DMMA and DFMA share the
+                                  // FP64 units -- a co-resident assembly CTA slows the ZGEMM CTAs one for one --
+                                  // so the assembly is NOT hidden under another frequency's factorisation.)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cplx *G = nullptr;      // nv x nv
   cplx *X = nullptr;      // nv x P

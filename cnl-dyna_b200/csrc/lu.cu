@@ -106,6 +106,7 @@ int lu_work_alloc(LuWork &w, uint n) {
   CNLD_CK(cudaMalloc(&w.linv, sizeof(cplx) * (size_t)w.nblk * NB * NB));
   CNLD_CK(cudaMalloc(&w.uinv, sizeof(cplx) * (size_t)w.nblk * NB * NB));
   CNLD_CK(cudaMalloc(&w.info, sizeof(uint)));
+  w.pflops.assign(w.nblk + 1, 0.0);
   return 0;
 }
 
@@ -151,15 +152,12 @@ void lu_profile(LuWork &w, bool on) {
 int lu_trailing_stats(const LuWork &w, double *seconds, double *flops, double *launches) {
   *seconds = *flops = *launches = 0.0;
   if (!w.prof) return 0;
-  for (uint ob = 0; ob < w.nouter; ob++) {
-    double O = (double)ob * w.nbo;
-    double W = (w.n - O < w.nbo) ? w.n - O : w.nbo;
-    double rem = (double)w.n - O - W;
-    if (rem <= 0) break;
+  for (uint ob = 0; ob < w.nouter && ob < w.pflops.size(); ob++) {
+    if (w.pflops[ob] <= 0.0) continue;
     float ms = 0.f;
     CNLD_CK(cudaEventElapsedTime(&ms, w.pe[2 * ob], w.pe[2 * ob + 1]));
     *seconds += ms * 1e-3;
-    *flops += (g_zgemm_3m ? 6.0 : 8.0) * rem * rem * W;  // executed real flops (3M: three real products)
+    *flops += w.pflops[ob] * (g_zgemm_3m ? 1.0 : 4.0 / 3.0);  // executed real flops (3M: 6 m n k)
     *launches += 1.0;
   }
   return 0;
@@ -167,64 +165,92 @@ int lu_trailing_stats(const LuWork &w, double *seconds, double *flops, double *l
 
 // Two-level right-looking factorisation.  Outer blocks of NBO columns: inside an outer block
 // the 64-wide steps update only the block column (all rows below) and the block row (all columns
-// to the right); the rest of the matrix receives ONE rank-NBO update per outer block, so ~97% of
-// the flops run as K = NBO ZGEMMs (DMMA efficiency grows with K: 26.6 / 32.4 TFLOP/s at K = 64 /
-// 256 on B200).
+// to the right); the rest of the matrix receives ONE rank-NBO update per outer block, so ~95% of
+// the flops run as K = NBO ZGEMMs (DMMA efficiency grows with K: 26.6 / 32.4 / 33.7 TFLOP/s at
+// K = 64 / 256 / 512 on B200).
+//
+// Look-ahead (when a companion stream w.lo exists): the rank-NBO update of outer block O is split
+// into T1 = the strip that the NEXT outer block's panel work touches (its block column and block
+// row) and T2 = everything beyond.  T2(O) runs on the companion stream with a few SMs left free
+// while the latency-bound panel loop of block O+1 runs on the main stream:
+//     main : inner(O) -> [wait T2(O-1)] T1(O) -> inner(O+1) -> [wait T2(O)] T1(O+1) -> ...
+//     lo   :                      [wait T1(O)] T2(O)   ->            [wait T1(O+1)] T2(O+1) ...
 int g_lu_outer = 512;
+int g_lu_reserve_sms = 12;
+
+static int inner_loop(cudaStream_t st, LuWork &w, cplx *a, size_t lda, uint O, uint OE) {
+  const uint n = w.n;
+  for (uint o = O; o < OE; o += NB) {
+    const uint b = o / NB;
+    const uint nbk = (OE - o < (uint)NB) ? OE - o : NB;
+    const uint below = n - o - nbk;  // rows below / columns right of the diagonal block
+    cplx *akk = a + (size_t)o * lda + o;
+    cplx *li = w.linv + (size_t)b * NB * NB, *ui = w.uinv + (size_t)b * NB * NB;
+    k_diag<true><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(a, lda, n, b, w.linv, w.uinv, w.info);
+    CNLD_CK_LAUNCH();
+    if (!below) continue;
+    cplx *a21 = akk + nbk, *a12 = akk + (size_t)nbk * lda, *a22 = a12 + nbk;
+    // in place: one CTA tile (64x64) spans the whole 64-wide panel it re-reads
+    if (zgemm(st, below, nbk, nbk, 1.0, a21, lda, ui, NB, 0.0, a21, lda)) return -1;
+    if (zgemm(st, nbk, below, nbk, 1.0, li, NB, a12, lda, 0.0, a12, lda)) return -1;
+    const uint in_cols = OE - o - nbk;  // columns (and rows) left inside the outer block
+    if (in_cols) {
+      // block column: all rows below x remaining columns of the outer block
+      if (zgemm3m(st, below, in_cols, nbk, -1.0, a21, lda, a12, lda, 1.0, a22, lda)) return -1;
+      // block row: remaining rows of the outer block x columns right of the outer block
+      const uint right = n - OE;
+      if (right && zgemm3m(st, in_cols, right, nbk, -1.0, a21, lda, a12 + (size_t)in_cols * lda, lda, 1.0,
+                           a22 + (size_t)in_cols * lda, lda)) return -1;
+    }
+  }
+  return 0;
+}
 
 int lu_factor(cudaStream_t st, LuWork &w, cplx *a, size_t lda) {
   if (diag_attr()) return -1;
   const uint n = w.n;
   const uint NBO = (uint)((g_lu_outer / NB) * NB > 0 ? (g_lu_outer / NB) * NB : NB);
   CNLD_CK(cudaMemsetAsync(w.info, 0, sizeof(uint), st));
+  const bool ahead = w.lo != nullptr;
+  bool t2_pending = false;
   uint ob = 0;
   for (uint O = 0; O < n; O += NBO, ob++) {
     const uint W = (n - O < NBO) ? n - O : NBO;
     const uint OE = O + W;  // end of the outer block
-    for (uint o = O; o < OE; o += NB) {
-      const uint b = o / NB;
-      const uint nbk = (OE - o < (uint)NB) ? OE - o : NB;
-      const uint below = n - o - nbk;   // rows below / columns right of the diagonal block
-      cplx *akk = a + (size_t)o * lda + o;
-      cplx *li = w.linv + (size_t)b * NB * NB, *ui = w.uinv + (size_t)b * NB * NB;
-      k_diag<true><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(a, lda, n, b, w.linv, w.uinv, w.info);
-      CNLD_CK_LAUNCH();
-      if (!below) continue;
-      cplx *a21 = akk + nbk, *a12 = akk + (size_t)nbk * lda, *a22 = a12 + nbk;
-      // in place: one CTA tile (64x64) spans the whole 64-wide panel it re-reads
-      if (zgemm(st, below, nbk, nbk, 1.0, a21, lda, ui, NB, 0.0, a21, lda)) return -1;
-      if (zgemm(st, nbk, below, nbk, 1.0, li, NB, a12, lda, 0.0, a12, lda)) return -1;
-      const uint in_cols = OE - o - nbk;  // columns (and rows) left inside the outer block
-      if (in_cols) {
-        // block column: all rows below x remaining columns of the outer block
-        if (zgemm3m(st, below, in_cols, nbk, -1.0, a21, lda, a12, lda, 1.0, a22, lda)) return -1;
-        // block row: remaining rows of the outer block x columns right of the outer block
-        const uint right = n - OE;
-        if (right && zgemm3m(st, in_cols, right, nbk, -1.0, a21, lda, a12 + (size_t)in_cols * lda, lda, 1.0,
-                           a22 + (size_t)in_cols * lda, lda)) return -1;
-      }
-    }
+    if (inner_loop(st, w, a, lda, O, OE)) return -1;
     const uint rem = n - OE;
-    if (rem) {
-      cplx *l = a + (size_t)O * lda + OE, *u = a + (size_t)OE * lda + O, *t = a + (size_t)OE * lda + OE;
-      // The rank-W update is the throughput kernel; when a low-priority companion stream is set
-      // it runs there, so that the latency-bound panel kernels of OTHER frequencies (high-priority
-      // streams) get SM slots as soon as any of its CTAs retires.
-      cudaStream_t ts = st;
-      if (w.lo) {
-        CNLD_CK(cudaEventRecord(w.ev_fork, st));
-        CNLD_CK(cudaStreamWaitEvent(w.lo, w.ev_fork, 0));
-        ts = w.lo;
-      }
-      if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * ob], ts));
-      if (zgemm3m(ts, rem, rem, W, -1.0, l, lda, u, lda, 1.0, t, lda)) return -1;
-      if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * ob + 1], ts));
-      if (w.lo) {
-        CNLD_CK(cudaEventRecord(w.ev_join, w.lo));
-        CNLD_CK(cudaStreamWaitEvent(st, w.ev_join, 0));
-      }
+    if (!rem) break;
+    cplx *l = a + (size_t)O * lda + OE, *u = a + (size_t)OE * lda + O, *t = a + (size_t)OE * lda + OE;
+    if (!ahead) {
+      if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * ob], st));
+      if (zgemm3m(st, rem, rem, W, -1.0, l, lda, u, lda, 1.0, t, lda)) return -1;
+      if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * ob + 1], st));
+      w.pflops[ob] = 6.0 * rem * rem * W;
+      continue;
+    }
+    const uint W2 = (rem < NBO) ? rem : NBO;  // width of the next outer block
+    // T1: needs the previous T2 (it covered this strip)
+    if (t2_pending) CNLD_CK(cudaStreamWaitEvent(st, w.ev_join, 0));
+    if (zgemm3m(st, rem, W2, W, -1.0, l, lda, u, lda, 1.0, t, lda)) return -1;
+    const uint rest = rem - W2;
+    if (rest) {
+      if (zgemm3m(st, W2, rest, W, -1.0, l, lda, u + (size_t)W2 * lda, lda, 1.0, t + (size_t)W2 * lda, lda)) return -1;
+      // T2 on the companion stream, leaving a few SMs to the panel loop of the next block
+      CNLD_CK(cudaEventRecord(w.ev_fork, st));
+      CNLD_CK(cudaStreamWaitEvent(w.lo, w.ev_fork, 0));
+      if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * ob], w.lo));
+      if (zgemm3m(w.lo, rest, rest, W, -1.0, l + W2, lda, u + (size_t)W2 * lda, lda, 1.0,
+                  t + (size_t)W2 * lda + W2, lda, g_lu_reserve_sms)) return -1;
+      if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * ob + 1], w.lo));
+      CNLD_CK(cudaEventRecord(w.ev_join, w.lo));
+      t2_pending = true;
+      w.pflops[ob] = 6.0 * rest * rest * W;
+    } else {
+      t2_pending = false;
+      w.pflops[ob] = 0.0;
     }
   }
+  if (ahead && t2_pending) CNLD_CK(cudaStreamWaitEvent(st, w.ev_join, 0));
   w.nouter = ob;
   w.nbo = NBO;
   return 0;

@@ -12,6 +12,8 @@
 // K chunks of 8 through a 4-stage cp.async ring.  Shared-memory leading dimensions
 // are chosen so the 16-byte fragment loads are bank-conflict free:
 //   A tile [k][i], ld = 130 (== 2 mod 8);  B tile [j][k], ld = 12 (== 4 mod 8).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace cnld {
@@ -178,11 +180,17 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
   cplx *Bs = As + T3_STAGES * T3_A_STAGE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 1, wn = warp >> 1;
-  // grouped rasterisation: consecutive CTAs walk T3_GM row tiles x all column tiles, so the
-  // ~300 CTAs in flight share a few MB of A/B panels in L2 instead of streaming a whole panel
+  // Persistent CTAs (grid = 2 per SM): every CTA walks the tile list, so the kernel never has
+  // pending CTAs and the block scheduler can place a co-resident assembly CTA of another frequency
+  // (FP64 ALU pipe) next to the two GEMM CTAs (DMMA tensor pipe) of an SM.
+  // Grouped rasterisation: consecutive tiles walk T3_GM row tiles x all column tiles, so the CTAs
+  // in flight share a few MB of A/B panels in L2 instead of streaming a whole panel.
   const uint mt = (M + T3_BM - 1) / T3_BM, nt = (N + T3_BN - 1) / T3_BN;
-  const uint gsz_full = T3_GM * nt, grp = blockIdx.x / gsz_full, first = grp * T3_GM;
-  const uint gm = min((uint)T3_GM, mt - first), within = blockIdx.x % gsz_full;
+  const uint gsz_full = T3_GM * nt;
+  const int fr = lane >> 2, fc = lane & 3;
+  for (uint tile = blockIdx.x; tile < mt * nt; tile += gridDim.x) {
+  const uint grp = tile / gsz_full, first = grp * T3_GM;
+  const uint gm = min((uint)T3_GM, mt - first), within = tile % gsz_full;
   const uint m0 = (first + within % gm) * T3_BM, n0 = (within / gm) * T3_BN;
   const int nk = (K + BK - 1) / BK;
 
@@ -221,7 +229,6 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
     if (s < nk) load_stage(s, s);
     cp_async_commit();
   }
-  const int fr = lane >> 2, fc = lane & 3;
   for (int kc = 0; kc < nk; kc++) {
     cp_async_wait<T3_STAGES - 2>();
     __syncthreads();
@@ -281,13 +288,15 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
         }
       }
   }
+  __syncthreads();  // shared-memory ring is reused by the next tile
+  }  // tile loop
 }
 }  // namespace
 
 int g_zgemm_3m = 1;  // use the 3M kernel for non-aliased accumulating products
 
 int zgemm3m(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
-            const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc) {
+            const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, int reserve_sms) {
   if (M == 0 || N == 0) return 0;
   if (!g_zgemm_3m) return zgemm(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
   static bool attr_set[64] = {false};
@@ -297,7 +306,13 @@ int zgemm3m(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A
     CNLD_CK(cudaFuncSetAttribute(zgemm3m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM));
     attr_set[dev & 63] = true;
   }
-  dim3 grid(((M + T3_BM - 1) / T3_BM) * ((N + T3_BN - 1) / T3_BN));
+  static int nsm[64] = {0};
+  if (!nsm[dev & 63]) CNLD_CK(cudaDeviceGetAttribute(&nsm[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+  const uint tiles = ((M + T3_BM - 1) / T3_BM) * ((N + T3_BN - 1) / T3_BN);
+  // reserve_sms: leave that many SMs without a CTA of this (persistent) kernel, for concurrent
+  // latency-bound kernels on another stream
+  const int use_sms = std::max(1, nsm[dev & 63] - std::max(0, reserve_sms));
+  dim3 grid(std::min(tiles, (uint)(2 * use_sms)));
   zgemm3m_kernel<<<grid, T3_NT, T3_SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
   CNLD_CK_LAUNCH();
   return 0;
