@@ -258,7 +258,11 @@ def main():
             'gpu_launches': int(launches), 'wall_seconds_timed_region': wall,
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': fp64_peak, 'unit': 'TFLOP/s',
-                         'frac': (ach / fp64_peak) if ach else None, 'traffic': None,
+                         'frac': (ach / fp64_peak) if ach else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the first trailing update
+                         # (13776 x 13776 x 512) from profiles/r1_ncu_full_summary.txt; algorithmic
+                         # bytes of that launch: C read + write 6.07e9 + panels 0.45e9
+                         'traffic': 8.28e9 if args.config == 'c3' else None,
                          'kernel': 'zgemm3m_kernel (DMMA.8x8x4 rank-512 trailing updates of the LU; 3M complex '
                                    'product = 6 m n k executed real flops per launch, i.e. 8 m n k conventional '
                                    'complex-GEMM flops at 4/3 of this rate)',

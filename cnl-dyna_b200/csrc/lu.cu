@@ -256,26 +256,36 @@ int lu_factor(cudaStream_t st, LuWork &w, cplx *a, size_t lda) {
   return 0;
 }
 
+// Forward / backward substitution for nrhs right-hand sides, blocked like the factorisation: 64-wide
+// steps with the inverted diagonal blocks inside an outer block of NBO rows, one rank-NBO ZGEMM per
+// outer block for everything beyond it.
 int lu_solve(cudaStream_t st, const LuWork &w, const cplx *a, size_t lda, cplx *x, uint nrhs,
              size_t ldx) {
   const uint n = w.n;
-  for (uint b = 0, o = 0; o < n; b++, o += NB) {  // L y = b
-    uint nbk = (n - o < (uint)NB) ? n - o : NB;
-    uint rem = n - o - nbk;
-    cplx *xb = x + o;
-    if (zgemm(st, nbk, nrhs, nbk, 1.0, w.linv + (size_t)b * NB * NB, NB, xb, ldx, 0.0, xb, ldx))
-      return -1;
-    if (rem &&
-        zgemm3m(st, rem, nrhs, nbk, -1.0, a + (size_t)o * lda + o + nbk, lda, xb, ldx, 1.0, xb + nbk, ldx))
+  const uint NBO = (uint)((g_lu_outer / NB) * NB > 0 ? (g_lu_outer / NB) * NB : NB);
+  for (uint O = 0; O < n; O += NBO) {  // L y = b
+    const uint OE = (n - O < NBO) ? n : O + NBO;
+    for (uint o = O; o < OE; o += NB) {
+      const uint b = o / NB, nbk = (OE - o < (uint)NB) ? OE - o : NB, in_rows = OE - o - nbk;
+      cplx *xb = x + o;
+      if (zgemm(st, nbk, nrhs, nbk, 1.0, w.linv + (size_t)b * NB * NB, NB, xb, ldx, 0.0, xb, ldx)) return -1;
+      if (in_rows && zgemm3m(st, in_rows, nrhs, nbk, -1.0, a + (size_t)o * lda + o + nbk, lda, xb, ldx, 1.0,
+                             xb + nbk, ldx)) return -1;
+    }
+    if (n > OE && zgemm3m(st, n - OE, nrhs, OE - O, -1.0, a + (size_t)O * lda + OE, lda, x + O, ldx, 1.0, x + OE, ldx))
       return -1;
   }
-  for (uint b = w.nblk; b-- > 0;) {  // R x = y
-    uint o = b * NB;
-    uint nbk = (n - o < (uint)NB) ? n - o : NB;
-    cplx *xb = x + o;
-    if (zgemm(st, nbk, nrhs, nbk, 1.0, w.uinv + (size_t)b * NB * NB, NB, xb, ldx, 0.0, xb, ldx))
-      return -1;
-    if (o && zgemm3m(st, o, nrhs, nbk, -1.0, a + (size_t)o * lda, lda, xb, ldx, 1.0, x, ldx)) return -1;
+  const uint nouter = (n + NBO - 1) / NBO;
+  for (uint ob = nouter; ob-- > 0;) {  // R x = y
+    const uint O = ob * NBO, OE = (n - O < NBO) ? n : O + NBO;
+    const uint nin = (OE - O + NB - 1) / NB;
+    for (uint ib = nin; ib-- > 0;) {
+      const uint o = O + ib * NB, b = o / NB, nbk = (OE - o < (uint)NB) ? OE - o : NB;
+      cplx *xb = x + o;
+      if (zgemm(st, nbk, nrhs, nbk, 1.0, w.uinv + (size_t)b * NB * NB, NB, xb, ldx, 0.0, xb, ldx)) return -1;
+      if (o > O && zgemm3m(st, o - O, nrhs, nbk, -1.0, a + (size_t)o * lda + O, lda, xb, ldx, 1.0, x + O, ldx)) return -1;
+    }
+    if (O && zgemm3m(st, O, nrhs, OE - O, -1.0, a + (size_t)O * lda, lda, x + O, ldx, 1.0, x, ldx)) return -1;
   }
   return 0;
 }
