@@ -48,6 +48,7 @@ def lib():
         L.cnld_b200_assemble_slp_ll.argtypes = [vp, f64, f64, vp, u32]
         L.cnld_b200_nearfield_slp_ll.argtypes = [vp, f64, f64, vp, u32, vp, u32, vp, u32]
         L.cnld_b200_lrdecomp.argtypes = [C.c_int, u32, vp, u32, vp]
+        L.cnld_b200_lrdecomp_sym.argtypes = [C.c_int, u32, vp, u32, vp]
         L.cnld_b200_lrsolve.argtypes = [C.c_int, u32, vp, u32, vp, u32, u32]
         L.cnld_b200_zgemm.argtypes = [C.c_int, u32, u32, u32, f64, vp, u32, vp, u32, f64, vp, u32]
         L.cnld_b200_set_mbk.argtypes = [vp] * 6
@@ -57,6 +58,8 @@ def lib():
         L.cnld_b200_sweep_fetch.argtypes = [vp, u32, vp, vp]
         L.cnld_b200_sweep_stage_times.argtypes = [vp, vp]
         L.cnld_b200_set_profile.argtypes = [vp, C.c_int]
+        L.cnld_b200_set_symmetric.argtypes = [vp, C.c_int, C.c_int]
+        L.cnld_b200_get_symmetric.argtypes = [vp, vp]
         L.cnld_b200_sweep_kernel_stats.argtypes = [vp, vp]
         L.cnld_b200_pres_vector.argtypes = [vp, vp, u32, f64, f64, f64, vp]
         L.cnld_b200_pressure.argtypes = [vp, vp, u32, vp, u32, f64, f64, vp, u32, vp]
@@ -119,6 +122,10 @@ class Context:
 
     def set_streams(self, n):
         check(lib().cnld_b200_set_streams(self._h, int(n)))
+
+    def set_symmetric(self, mode, refine_steps=2):
+        """mode 1: factor the symmetric part at half the flops and refine with the sparse asymmetry."""
+        check(lib().cnld_b200_set_symmetric(self._h, int(mode), int(refine_steps)))
 
     def geometry(self):
         g = np.zeros(self.nt)
@@ -302,6 +309,17 @@ def lrdecomp(G, device=0):
     a = np.array(np.asarray(G).T, dtype=np.complex128, order='C', copy=True)
     info = C.c_uint(0)
     check(lib().cnld_b200_lrdecomp(device, n, ptr(a), n, C.byref(info)))
+    if info.value != 0:
+        raise RuntimeError('failed to calculate LU decomposition')
+    return a.T
+
+
+def lrdecomp_sym(G, device=0):
+    """Unpivoted LU of the complex symmetric matrix given by G's lower triangle (half the flops)."""
+    n = G.shape[0]
+    a = np.array(np.asarray(G).T, dtype=np.complex128, order='C', copy=True)
+    info = C.c_uint(0)
+    check(lib().cnld_b200_lrdecomp_sym(device, n, ptr(a), n, C.byref(info)))
     if info.value != 0:
         raise RuntimeError('failed to calculate LU decomposition')
     return a.T

@@ -127,6 +127,123 @@ k_singular(size_t npairs, const TouchPair *__restrict__ pairs, const double *__r
   }
 }
 
+
+// ---- symmetric path ---------------------------------------------------------------------------
+// Only pairs with s < t are evaluated; the 3x3 block goes to the LOWER triangle: entry
+// (max(row, col), min(row, col)).  For a disjoint pair the transposed pair (s, t) has exactly the
+// transposed block (the tensor rule and the kernel are symmetric), so this fills the lower
+// triangle completely with half the kernel evaluations.
+template <int NQ, bool CPLXK>
+__global__ void __launch_bounds__(REG_THREADS)
+k_regular_sym(uint nt, const __grid_constant__ RegRule R, const uint *__restrict__ tri,
+              const double *__restrict__ qp, const double *__restrict__ g, double kr, double ki,
+              cplx alpha, cplx *Z, size_t ld) {
+  __shared__ double s_qp[REG_CHUNK][NQ][3];
+  __shared__ uint s_tv[REG_CHUNK][3];
+  __shared__ double s_g[REG_CHUNK];
+  const uint t = blockIdx.x * REG_THREADS + threadIdx.x;
+  const uint s0 = blockIdx.y * REG_CHUNK;
+  if (s0 >= min(nt, (blockIdx.x + 1) * REG_THREADS)) return;  // whole chunk has s >= every t of the block
+  const uint ns = min((uint)REG_CHUNK, nt - s0);
+  for (uint i = threadIdx.x; i < ns * NQ * 3; i += REG_THREADS)
+    (&s_qp[0][0][0])[i] = qp[(size_t)s0 * NQ * 3 + i];
+  for (uint i = threadIdx.x; i < ns * 3; i += REG_THREADS) (&s_tv[0][0])[i] = tri[(size_t)s0 * 3 + i];
+  for (uint i = threadIdx.x; i < ns; i += REG_THREADS) s_g[i] = g[s0 + i];
+  __syncthreads();
+  if (t >= nt) return;
+  uint tv[3] = {tri[3 * (size_t)t], tri[3 * (size_t)t + 1], tri[3 * (size_t)t + 2]};
+  double xp[NQ][3];
+#pragma unroll
+  for (int p = 0; p < NQ; p++)
+#pragma unroll
+    for (int d = 0; d < 3; d++) xp[p][d] = qp[((size_t)t * NQ + p) * 3 + d];
+  const double gt = g[t] * INV4PI;
+  const uint smax = min(ns, t > s0 ? t - s0 : 0u);  // s < t
+  for (uint sl = 0; sl < smax; sl++) {
+    const uint sv0 = s_tv[sl][0], sv1 = s_tv[sl][1], sv2 = s_tv[sl][2];
+    bool touch = (tv[0] == sv0) | (tv[0] == sv1) | (tv[0] == sv2) | (tv[1] == sv0) | (tv[1] == sv1) |
+                 (tv[1] == sv2) | (tv[2] == sv0) | (tv[2] == sv1) | (tv[2] == sv2);
+    if (touch) continue;
+    cplx loc[3][3];
+    regular_pair<NQ, CPLXK>(xp, &s_qp[sl][0][0], R, kr, ki, loc);
+    const double sc = gt * s_g[sl];
+    const cplx f = make_double2(alpha.x * sc, alpha.y * sc);
+    const uint sv[3] = {sv0, sv1, sv2};
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        cplx v = cmul(loc[i][j], f);
+        const uint r = max(tv[i], sv[j]), c = min(tv[i], sv[j]);
+        double *dst = reinterpret_cast<double *>(Z + (size_t)c * ld + r);
+        atomicAdd(dst, v.x);
+        atomicAdd(dst + 1, v.y);
+      }
+  }
+}
+
+// touching pairs -> sparse slots (no alpha: it is applied when the slots are folded in)
+template <bool CPLXK>
+__global__ void __launch_bounds__(SING_WARPS * 32)
+k_singular_slots(size_t npairs, const TouchPair *__restrict__ pairs, const uint *__restrict__ pair_slot,
+                 const double *__restrict__ x, const double *__restrict__ g, SingTables tab, double kr,
+                 double ki, cplx *sval) {
+  const size_t pid = (size_t)blockIdx.x * SING_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pid >= npairs) return;
+  const TouchPair P = pairs[pid];
+  double V[6][3];
+#pragma unroll
+  for (int v = 0; v < 3; v++)
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      V[v][d] = x[3 * (size_t)P.rv[v] + d];
+      V[3 + v][d] = x[3 * (size_t)P.cv[v] + d];
+    }
+  double acc[18];
+  singular_pair_warp<CPLXK>(V, tab, P.family, kr, ki, lane, acc);
+  if (lane < 9) {
+    const double sc = g[P.t] * g[P.s] * INV4PI;
+    double re = 0.0, im = 0.0;
+#pragma unroll
+    for (int e = 0; e < 9; e++)
+      if (lane == e) { re = acc[2 * e]; im = acc[2 * e + 1]; }
+    double *dst = reinterpret_cast<double *>(sval + pair_slot[9 * pid + lane]);
+    atomicAdd(dst, re * sc);
+    atomicAdd(dst + 1, im * sc);
+  }
+}
+
+__global__ void k_slots_fold(uint nslot, const uint *__restrict__ row, const uint *__restrict__ col,
+                             const uint *__restrict__ tr, const cplx *__restrict__ sval, cplx alpha, cplx *G,
+                             size_t ld, cplx *dval) {
+  uint s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslot) return;
+  const uint r = row[s], c = col[s];
+  cplx v = cmul(alpha, sval[s]);
+  if (r >= c) {
+    cplx *d = G + (size_t)c * ld + r;  // every lower slot is unique; the regular kernel has finished
+    d->x += v.x;
+    d->y += v.y;
+    dval[s] = make_double2(0.0, 0.0);
+  } else {
+    cplx w = cmul(alpha, sval[tr[s]]);
+    dval[s] = make_double2(v.x - w.x, v.y - w.y);
+  }
+}
+
+template <int NQ>
+int launch_regular_sym(cudaStream_t st, const BemDev &b, double kr, double ki, cplx alpha, cplx *Z, size_t ld) {
+  dim3 grid((b.nt + REG_THREADS - 1) / REG_THREADS, (b.nt + REG_CHUNK - 1) / REG_CHUNK);
+  if (ki != 0.0)
+    k_regular_sym<NQ, true><<<grid, REG_THREADS, 0, st>>>(b.nt, b.rule, b.t, b.qp, b.g, kr, ki, alpha, Z, ld);
+  else
+    k_regular_sym<NQ, false><<<grid, REG_THREADS, 0, st>>>(b.nt, b.rule, b.t, b.qp, b.g, kr, ki, alpha, Z, ld);
+  CNLD_CK_LAUNCH();
+  return 0;
+}
+
+
 template <int NQ>
 int launch_regular(cudaStream_t st, const BemDev &b, double kr, double ki, cplx alpha, cplx *Z, size_t ld) {
   dim3 grid((b.nt + REG_THREADS - 1) / REG_THREADS, (b.nt + REG_CHUNK - 1) / REG_CHUNK);
@@ -184,6 +301,24 @@ int bem_create(BemDev &b, int device, uint nv, uint nt, const double *x, const u
   b.npairs = pairs.size();
   CNLD_CK(cudaMalloc(&b.pairs, sizeof(TouchPair) * pairs.size()));
   CNLD_CK(cudaMemcpy(b.pairs, pairs.data(), sizeof(TouchPair) * pairs.size(), cudaMemcpyHostToDevice));
+  {
+    TouchSlots TS;
+    build_touch_slots(pairs, TS);
+    b.nslot = (uint)TS.row.size();
+    CNLD_CK(cudaMalloc(&b.pair_slot, sizeof(uint) * TS.pair_slot.size()));
+    CNLD_CK(cudaMalloc(&b.slot_row, sizeof(uint) * b.nslot));
+    CNLD_CK(cudaMalloc(&b.slot_col, sizeof(uint) * b.nslot));
+    CNLD_CK(cudaMalloc(&b.slot_tr, sizeof(uint) * b.nslot));
+    CNLD_CK(cudaMemcpy(b.pair_slot, TS.pair_slot.data(), sizeof(uint) * TS.pair_slot.size(), cudaMemcpyHostToDevice));
+    CNLD_CK(cudaMemcpy(b.slot_row, TS.row.data(), sizeof(uint) * b.nslot, cudaMemcpyHostToDevice));
+    CNLD_CK(cudaMemcpy(b.slot_col, TS.col.data(), sizeof(uint) * b.nslot, cudaMemcpyHostToDevice));
+    CNLD_CK(cudaMemcpy(b.slot_tr, TS.tr.data(), sizeof(uint) * b.nslot, cudaMemcpyHostToDevice));
+    std::vector<uint> rowptr(nv + 1, 0);
+    for (uint r : TS.row) rowptr[r + 1]++;
+    for (uint v = 0; v < nv; v++) rowptr[v + 1] += rowptr[v];
+    CNLD_CK(cudaMalloc(&b.slot_rowptr, sizeof(uint) * (nv + 1)));
+    CNLD_CK(cudaMemcpy(b.slot_rowptr, rowptr.data(), sizeof(uint) * (nv + 1), cudaMemcpyHostToDevice));
+  }
   k_tri_setup<<<(nt + 127) / 128, 128>>>(nt, b.nq, b.rule, b.x, b.t, b.g, b.n, b.qp);
   CNLD_CK_LAUNCH();
   CNLD_CK(cudaDeviceSynchronize());
@@ -192,6 +327,7 @@ int bem_create(BemDev &b, int device, uint nv, uint nt, const double *x, const u
 
 void bem_free(BemDev &b) {
   cudaFree(b.x); cudaFree(b.t); cudaFree(b.g); cudaFree(b.n); cudaFree(b.qp); cudaFree(b.pairs);
+  cudaFree(b.pair_slot); cudaFree(b.slot_row); cudaFree(b.slot_col); cudaFree(b.slot_tr); cudaFree(b.slot_rowptr);
   for (int f = 0; f < 4; f++) cudaFree(const_cast<double *>(b.sing.p[f]));
   b = BemDev();
 }
@@ -210,6 +346,28 @@ int bem_assemble(cudaStream_t st, const BemDev &b, double kr, double ki, cplx al
     k_singular<true><<<grid, SING_WARPS * 32, 0, st>>>(b.npairs, b.pairs, b.x, b.g, b.sing, kr, ki, alpha, Z, ld);
   else
     k_singular<false><<<grid, SING_WARPS * 32, 0, st>>>(b.npairs, b.pairs, b.x, b.g, b.sing, kr, ki, alpha, Z, ld);
+  CNLD_CK_LAUNCH();
+  return 0;
+}
+
+int bem_assemble_sym(cudaStream_t st, const BemDev &b, double kr, double ki, cplx alpha, cplx *G, size_t ld,
+                     cplx *sval, cplx *dval) {
+  CNLD_CK(cudaMemsetAsync(sval, 0, sizeof(cplx) * b.nslot, st));
+  int rc;
+  switch (b.nq) {
+  case 1: rc = launch_regular_sym<1>(st, b, kr, ki, alpha, G, ld); break;
+  case 4: rc = launch_regular_sym<4>(st, b, kr, ki, alpha, G, ld); break;
+  case 9: rc = launch_regular_sym<9>(st, b, kr, ki, alpha, G, ld); break;
+  default: rc = launch_regular_sym<16>(st, b, kr, ki, alpha, G, ld); break;
+  }
+  if (rc) return rc;
+  unsigned grid = (unsigned)((b.npairs + SING_WARPS - 1) / SING_WARPS);
+  if (ki != 0.0)
+    k_singular_slots<true><<<grid, SING_WARPS * 32, 0, st>>>(b.npairs, b.pairs, b.pair_slot, b.x, b.g, b.sing, kr, ki, sval);
+  else
+    k_singular_slots<false><<<grid, SING_WARPS * 32, 0, st>>>(b.npairs, b.pairs, b.pair_slot, b.x, b.g, b.sing, kr, ki, sval);
+  CNLD_CK_LAUNCH();
+  k_slots_fold<<<(b.nslot + 255) / 256, 256, 0, st>>>(b.nslot, b.slot_row, b.slot_col, b.slot_tr, sval, alpha, G, ld, dval);
   CNLD_CK_LAUNCH();
   return 0;
 }

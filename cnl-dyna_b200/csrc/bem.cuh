@@ -28,6 +28,10 @@ struct BemDev {
   SingTables sing;
   TouchPair *pairs = nullptr;
   size_t npairs = 0;
+  // sparse pattern of the entries fed by touching pairs (symmetric path, see quadrature.h)
+  uint nslot = 0;
+  uint *pair_slot = nullptr, *slot_row = nullptr, *slot_col = nullptr, *slot_tr = nullptr;
+  uint *slot_rowptr = nullptr;  // nv + 1: slots are sorted by (row, col)
 };
 
 int bem_create(BemDev &b, int device, uint nv, uint nt, const double *x, const uint *t, uint q, uint q2);
@@ -35,6 +39,12 @@ void bem_free(BemDev &b);
 // Z += alpha * Z_slp(k); Z must be initialised by the caller.
 int bem_assemble(cudaStream_t st, const BemDev &b, double kr, double ki, cplx alpha, cplx *Z, size_t ld);
 
+// Symmetric path: G_lower += alpha * Z_lower(k) where every disjoint pair is evaluated once (its
+// transposed contribution is identical), touching pairs are accumulated per sparse slot in `sval`
+// (caller-provided, nslot entries), folded into the lower triangle, and the asymmetry of the
+// Sauter-Schwab entries is returned in dval[slot] = alpha * (Z[r,c] - Z[c,r]) for slots with r < c.
+int bem_assemble_sym(cudaStream_t st, const BemDev &b, double kr, double ki, cplx alpha, cplx *G, size_t ld,
+                     cplx *sval, cplx *dval);
 }  // namespace cnld
 
 namespace cnld {

@@ -27,6 +27,7 @@ void set_error(const char *fmt, ...) {
 }  // namespace cnld
 
 #include "ctx.cuh"
+#include <algorithm>
 using namespace cnld;
 using namespace cnld::sweep;
 
@@ -112,6 +113,12 @@ int ensure_workspace(cnld_ctx *c, bool need_host_stage) {
     }
     if (!S.G) CNLD_CK(cudaMalloc(&S.G, sizeof(cplx) * nv * nv));
     if (!S.X) CNLD_CK(cudaMalloc(&S.X, sizeof(cplx) * nv * (c->P ? c->P : 1)));
+    if (c->symmetric && !S.E) {
+      CNLD_CK(cudaMalloc(&S.E, sizeof(cplx) * nv * (c->P ? c->P : 1)));
+      CNLD_CK(cudaMalloc(&S.E2, sizeof(cplx) * nv * (c->P ? c->P : 1)));
+      CNLD_CK(cudaMalloc(&S.sval, sizeof(cplx) * (c->bem.nslot + 1)));
+      CNLD_CK(cudaMalloc(&S.dval, sizeof(cplx) * (c->bem.nslot + 1)));
+    }
     if (!S.lu.linv) {
       if (lu_work_alloc(S.lu, (uint)nv)) return -1;
       S.lu.lo = S.st_lo;   // companion stream for the look-ahead trailing updates
@@ -131,7 +138,7 @@ void free_workspace(cnld_ctx *c) {
   for (int s = 0; s < MAX_SLOTS; s++) {
     Slot &S = c->slots[s];
     if (S.st) cudaStreamSynchronize(S.st);
-    cudaFree(S.G); cudaFree(S.X);
+    cudaFree(S.G); cudaFree(S.X); cudaFree(S.E); cudaFree(S.E2); cudaFree(S.sval); cudaFree(S.dval);
     if (S.hX) cudaFreeHost(S.hX);
     lu_work_free(S.lu);
     for (int e = 0; e < 4; e++) if (S.ev[e]) cudaEventDestroy(S.ev[e]);
@@ -145,15 +152,48 @@ void free_workspace(cnld_ctx *c) {
   c->ws_ready = false;
 }
 
+// R(:, p) = -Delta * E(:, p).  Delta is strictly upper and sparse: the Sauter-Schwab asymmetry sits in
+// dval at the slots with row < col (slots sorted by (row, col)), the asymmetry of the FEM operators (if
+// any) in a second CSR.  One CTA per row, one thread per right-hand side.
+__global__ void k_delta_apply(uint nv, uint P, const uint *__restrict__ rowptr, const uint *__restrict__ col,
+                              const cplx *__restrict__ dval, const uint *__restrict__ m_rowptr,
+                              const uint *__restrict__ m_col, const double *__restrict__ m_dK,
+                              const double *__restrict__ m_dM, const double *__restrict__ m_dB, double omega,
+                              const cplx *__restrict__ E, cplx *R, size_t ld) {
+  const uint r = blockIdx.x;
+  const uint s0 = rowptr[r], s1 = rowptr[r + 1];
+  const uint q0 = m_rowptr ? m_rowptr[r] : 0, q1 = m_rowptr ? m_rowptr[r + 1] : 0;
+  const double w2 = omega * omega;
+  for (uint p = threadIdx.x; p < P; p += blockDim.x) {
+    cplx acc = make_double2(0.0, 0.0);
+    for (uint s = s0; s < s1; s++) {
+      const uint cidx = col[s];
+      if (cidx > r) cfms(acc, dval[s], E[(size_t)p * ld + cidx]);
+    }
+    for (uint q = q0; q < q1; q++)
+      cfms(acc, make_double2(m_dK[q] - w2 * m_dM[q], -omega * m_dB[q]), E[(size_t)p * ld + m_col[q]]);
+    R[(size_t)p * ld + r] = acc;
+  }
+}
+__global__ void k_axpy(size_t n, const cplx *__restrict__ e, cplx *x) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { cplx v = x[i], w = e[i]; x[i] = make_double2(v.x + w.x, v.y + w.y); }
+}
+
 // enqueue one frequency on a slot; results: xpatch slice (device), X holds x_node
 int enqueue_frequency(cnld_ctx *c, Slot &S, double f, double cs, double rho, cplx *d_xpatch_f) {
   const uint nv = c->bem.nv, P = c->P;
   const double omega = TWO_PI * f, k = omega / cs;
+  // symmetric path: G = S + Delta with S symmetric (lower triangle of G mirrored) and Delta the sparse,
+  // strictly upper asymmetry of the Sauter-Schwab entries.  S is factored at half the cost and
+  // x = G^-1 f is recovered by the stationary iteration e <- -S^-1 Delta e, x <- x + e.
+  const bool sym = c->symmetric != 0;
   CNLD_CK(cudaEventRecord(S.ev[0], S.st));
   CNLD_CK(cudaMemsetAsync(S.G, 0, sizeof(cplx) * (size_t)nv * nv, S.st));
   k_scatter_mbk<<<(nv * 32 + 255) / 256, 256, 0, S.st>>>(nv, c->d_indptr, c->d_indices, c->d_K, c->d_M,
                                                       c->d_B, omega, S.G, nv);
   CNLD_CK_LAUNCH();
+  if (sym && f == 0.0) CNLD_CK(cudaMemsetAsync(S.dval, 0, sizeof(cplx) * (c->bem.nslot + 1), S.st));
   if (f != 0.0) {
     // Gbe = -omg^2 * 2 * rho * Z   (generate_db.py:55-56)
     cudaStream_t as = S.st;
@@ -162,19 +202,36 @@ int enqueue_frequency(cnld_ctx *c, Slot &S, double f, double cs, double rho, cpl
       CNLD_CK(cudaStreamWaitEvent(S.st_asm, S.ev_fork, 0));
       as = S.st_asm;
     }
-    if (bem_assemble(as, c->bem, k, 0.0, make_double2(-omega * omega * 2.0 * rho, 0.0), S.G, nv)) return -1;
+    const cplx alpha = make_double2(-omega * omega * 2.0 * rho, 0.0);
+    if (sym ? bem_assemble_sym(as, c->bem, k, 0.0, alpha, S.G, nv, S.sval, S.dval)
+            : bem_assemble(as, c->bem, k, 0.0, alpha, S.G, nv)) return -1;
     if (c->nslots > 1) {
       CNLD_CK(cudaEventRecord(S.ev_join, S.st_asm));
       CNLD_CK(cudaStreamWaitEvent(S.st, S.ev_join, 0));
     }
   }
   CNLD_CK(cudaEventRecord(S.ev[1], S.st));
-  if (lu_factor(S.st, S.lu, S.G, nv)) return -1;
+  if (sym ? lu_factor_sym(S.st, S.lu, S.G, nv) : lu_factor(S.st, S.lu, S.G, nv)) return -1;
   CNLD_CK(cudaEventRecord(S.ev[2], S.st));
   CNLD_CK(cudaMemsetAsync(S.X, 0, sizeof(cplx) * (size_t)nv * P, S.st));
   k_build_rhs<<<P, 128, 0, S.st>>>(P, c->d_f_indptr, c->d_f_idx, c->d_f_val, S.X, nv);
   CNLD_CK_LAUNCH();
   if (lu_solve(S.st, S.lu, S.G, nv, S.X, P, nv)) return -1;
+  {
+    const cplx *src = S.X;
+    cplx *dst = S.E, *other = S.E2;
+    for (int it = 0; sym && it < c->refine_steps; it++) {
+      k_delta_apply<<<nv, 160, 0, S.st>>>(nv, P, c->bem.slot_rowptr, c->bem.slot_col, S.dval, c->d_m_rowptr,
+                                          c->d_m_col, c->d_m_dK, c->d_m_dM, c->d_m_dB, omega, src, dst, nv);
+      CNLD_CK_LAUNCH();
+      if (lu_solve(S.st, S.lu, S.G, nv, dst, P, nv)) return -1;
+      const size_t tot = (size_t)nv * P;
+      k_axpy<<<(uint)((tot + 255) / 256), 256, 0, S.st>>>(tot, dst, S.X);
+      CNLD_CK_LAUNCH();
+      src = dst;
+      cplx *t = dst; dst = other; other = t;
+    }
+  }
   k_epilogue<<<P, 256, 0, S.st>>>(nv, P, S.X, nv, c->d_ob, c->d_a_indptr, c->d_a_idx, c->d_a_val,
                                   d_xpatch_f);
   CNLD_CK_LAUNCH();
@@ -295,6 +352,7 @@ void cnld_b200_destroy(cnld_ctx *c) {
   cudaFree(c->d_f_indptr); cudaFree(c->d_a_indptr); cudaFree(c->d_f_idx); cudaFree(c->d_a_idx);
   cudaFree(c->d_f_val); cudaFree(c->d_a_val); cudaFree(c->d_ob); cudaFree(c->d_xpatch); cudaFree(c->d_xnode);
   cudaFree(c->d_sp);
+  cudaFree(c->d_m_rowptr); cudaFree(c->d_m_col); cudaFree(c->d_m_dK); cudaFree(c->d_m_dM); cudaFree(c->d_m_dB);
   if (c->ev_begin) { cudaEventDestroy(c->ev_begin); cudaEventDestroy(c->ev_end); }
   bem_free(c->bem);
   delete c;
@@ -350,7 +408,7 @@ int cnld_b200_nearfield_slp_ll(cnld_ctx *c, double k_re, double k_im, const cnld
   return rc;
 }
 
-int cnld_b200_lrdecomp(int device, cnld_uint n, cnld_field *a, cnld_uint ld, cnld_uint *info) {
+static int lrdecomp_impl(int device, cnld_uint n, cnld_field *a, cnld_uint ld, cnld_uint *info, bool sym) {
   if (cnld_b200_device_count() <= device) { set_error("no CUDA device %d (no CPU fallback)", device); return -1; }
   CNLD_CK(cudaSetDevice(device));
   cplx *dA = nullptr;
@@ -359,7 +417,7 @@ int cnld_b200_lrdecomp(int device, cnld_uint n, cnld_field *a, cnld_uint ld, cnl
   int rc = 0;
   do {
     if (cudaMemcpy2D(dA, sizeof(cplx) * n, a, sizeof(cplx) * ld, sizeof(cplx) * n, n, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); rc = -1; break; }
-    if (lu_work_alloc(w, n) || lu_factor(0, w, dA, n)) { rc = -1; break; }
+    if (lu_work_alloc(w, n) || (sym ? lu_factor_sym(0, w, dA, n) : lu_factor(0, w, dA, n))) { rc = -1; break; }
     uint inf = 0;
     if (cudaMemcpy(&inf, w.info, sizeof(uint), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); rc = -1; break; }
     if (info) *info = inf;
@@ -368,6 +426,12 @@ int cnld_b200_lrdecomp(int device, cnld_uint n, cnld_field *a, cnld_uint ld, cnl
   lu_work_free(w);
   cudaFree(dA);
   return rc;
+}
+int cnld_b200_lrdecomp(int device, cnld_uint n, cnld_field *a, cnld_uint ld, cnld_uint *info) {
+  return lrdecomp_impl(device, n, a, ld, info, false);
+}
+int cnld_b200_lrdecomp_sym(int device, cnld_uint n, cnld_field *a, cnld_uint ld, cnld_uint *info) {
+  return lrdecomp_impl(device, n, a, ld, info, true);
 }
 
 int cnld_b200_lrsolve(int device, cnld_uint n, const cnld_field *lu, cnld_uint ld, cnld_field *x,
@@ -427,7 +491,54 @@ int cnld_b200_set_mbk(cnld_ctx *c, const int64_t *indptr, const cnld_uint *indic
   c->h_K.assign(K, K + nnz); c->h_M.assign(M, M + nnz); c->h_B.assign(B, B + nnz);
   if (upload(c->d_indptr, indptr, nv + 1) || upload(c->d_indices, indices, nnz) || upload(c->d_K, K, nnz) ||
       upload(c->d_M, M, nnz) || upload(c->d_B, B, nnz)) return -1;
+  // strictly upper asymmetry (symmetric path): Delta[r, c] = A[r, c] - A[c, r] for r < c, where the
+  // symmetric part S is defined by the LOWER triangle; an entry missing from the pattern counts as 0
+  {
+    struct Trip { uint r, c; double k, m, b; };
+    std::vector<Trip> trips;
+    auto find = [&](size_t r, uint col) -> int64_t {
+      for (int64_t p = indptr[r]; p < indptr[r + 1]; p++) if (indices[p] == col) return p;
+      return -1;
+    };
+    for (size_t r = 0; r < nv; r++)
+      for (int64_t p = indptr[r]; p < indptr[r + 1]; p++) {
+        const uint col = indices[p];
+        if (col > r) {  // upper entry: compare with its lower partner
+          int64_t q = find(col, (uint)r);
+          double a = K[p] - (q >= 0 ? K[q] : 0.0), b = M[p] - (q >= 0 ? M[q] : 0.0), d = B[p] - (q >= 0 ? B[q] : 0.0);
+          if (a != 0.0 || b != 0.0 || d != 0.0) trips.push_back({(uint)r, col, a, b, d});
+        } else if (col < r && find(col, (uint)r) < 0) {  // lower entry without an upper partner
+          trips.push_back({col, (uint)r, -K[p], -M[p], -B[p]});
+        }
+      }
+    std::stable_sort(trips.begin(), trips.end(), [](const Trip &x, const Trip &y) { return x.r < y.r; });
+    std::vector<uint> rp(nv + 1, 0), mc;
+    std::vector<double> dK, dM, dB;
+    for (const Trip &t : trips) { rp[t.r + 1]++; mc.push_back(t.c); dK.push_back(t.k); dM.push_back(t.m); dB.push_back(t.b); }
+    for (size_t r = 0; r < nv; r++) rp[r + 1] += rp[r];
+    c->m_nnz = (uint)mc.size();
+    cudaFree(c->d_m_rowptr); cudaFree(c->d_m_col); cudaFree(c->d_m_dK); cudaFree(c->d_m_dM); cudaFree(c->d_m_dB);
+    c->d_m_rowptr = nullptr; c->d_m_col = nullptr; c->d_m_dK = c->d_m_dM = c->d_m_dB = nullptr;
+    if (c->m_nnz) {
+      if (upload(c->d_m_rowptr, rp.data(), nv + 1) || upload(c->d_m_col, mc.data(), mc.size()) ||
+          upload(c->d_m_dK, dK.data(), dK.size()) || upload(c->d_m_dM, dM.data(), dM.size()) ||
+          upload(c->d_m_dB, dB.data(), dB.size())) return -1;
+    }
+  }
   return 0;
+}
+
+int cnld_b200_set_symmetric(cnld_ctx *c, int mode, int refine_steps) {
+  if (!c || mode < 0 || mode > 1 || refine_steps < 0 || refine_steps > 16) { set_error("set_symmetric: mode 0/1, refine_steps 0..16"); return -1; }
+  if (mode != c->symmetric) { cudaSetDevice(c->bem.device); free_workspace(c); }
+  c->symmetric = mode;
+  c->refine_steps = refine_steps;
+  return 0;
+}
+int cnld_b200_get_symmetric(const cnld_ctx *c, unsigned *mbk_asym_nnz) {
+  if (!c) return -1;
+  if (mbk_asym_nnz) *mbk_asym_nnz = c->m_nnz;
+  return c->symmetric;
 }
 
 int cnld_b200_set_loads(cnld_ctx *c, cnld_uint P, const int64_t *f_indptr, const cnld_uint *f_idx,

@@ -74,8 +74,11 @@ int zgemm(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, 
           const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc);
 
 // same contract, 3M complex product (C must not alias A or B)
+// lower_only: skip the tiles that lie entirely above the diagonal of C (M == N); *entries (optional)
+// returns the number of output entries actually computed.
 int zgemm3m(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
-            const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, int reserve_sms = 0);
+            const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, int reserve_sms = 0,
+            bool lower_only = false, double *entries = nullptr);
 extern int g_zgemm_3m;
 
 struct LuWork {
@@ -98,6 +101,8 @@ void lu_profile(LuWork &w, bool on);
 int lu_trailing_stats(const LuWork &w, double *seconds, double *flops, double *launches);
 // unpivoted LU in place on device matrix a (n x n, lda); keeps block inverses in w
 int lu_factor(cudaStream_t st, LuWork &w, cplx *a, size_t lda);
+// same result for a complex SYMMETRIC matrix given by its lower triangle, half the flops
+int lu_factor_sym(cudaStream_t st, LuWork &w, cplx *a, size_t lda);
 // X (n x nrhs, ldx) <- (LU)^-1 X
 int lu_solve(cudaStream_t st, const LuWork &w, const cplx *a, size_t lda, cplx *x, uint nrhs,
              size_t ldx);

@@ -18,6 +18,8 @@ struct Slot {
   cplx *G = nullptr;      // nv x nv
   cplx *X = nullptr;      // nv x P
   cplx *hX = nullptr;     // pinned staging for x_node
+  // symmetric path: sparse Sauter-Schwab slots, their asymmetry, refinement vectors (nv x P each)
+  cplx *sval = nullptr, *dval = nullptr, *E = nullptr, *E2 = nullptr;
   LuWork lu;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   long pending = -1;      // frequency index whose x_node sits in hX
@@ -57,6 +59,12 @@ struct cnld_ctx {
   double stage[5] = {0, 0, 0, 0, 0};
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   bool profile = false;
+  // symmetric path (cnld_b200_set_symmetric): factor the symmetric part, refine with the sparse asymmetry
+  int symmetric = 0, refine_steps = 2;
+  // strictly upper asymmetry of the FEM operators, CSR by row: (K, M, B)[r,c] - (K, M, B)[c,r]
+  uint m_nnz = 0;
+  uint *d_m_rowptr = nullptr, *d_m_col = nullptr;
+  double *d_m_dK = nullptr, *d_m_dM = nullptr, *d_m_dB = nullptr;
   double kstat[3] = {0, 0, 0};  // trailing ZGEMM: flops, seconds, launches (last sweep)
   // pressure scratch
   double *d_sp = nullptr;

@@ -21,7 +21,9 @@ constexpr int DIAG_SMEM = 2 * NB * LD * (int)sizeof(cplx);
 // FACTOR=true : factor diagonal block `b0` (grid = 1).
 // FACTOR=false: the matrix already holds L\R; only form the block inverses, one CTA per
 //               diagonal block (grid = nblk) -- used by the stand-alone lrsolve entry.
-template <bool FACTOR>
+// SYM=true: only the lower triangle of the block is valid on entry (symmetric path); the upper
+//           triangle is mirrored while loading.
+template <bool FACTOR, bool SYM = false>
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 k_diag(cplx *a0, size_t lda, uint n, uint b0, cplx *linv0, cplx *uinv0, uint *info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -34,7 +36,7 @@ k_diag(cplx *a0, size_t lda, uint n, uint b0, cplx *linv0, cplx *uinv0, uint *in
   cplx *linv = linv0 + (size_t)b * NB * NB, *uinv = uinv0 + (size_t)b * NB * NB;
   for (uint idx = tid; idx < nbk * nbk; idx += DIAG_THREADS) {
     uint i = idx % nbk, j = idx / nbk;
-    S[j * LD + i] = a[(size_t)j * lda + i];
+    S[j * LD + i] = (SYM && i < j) ? a[(size_t)i * lda + j] : a[(size_t)j * lda + i];
   }
   __syncthreads();
   for (uint k = 0; FACTOR && k < nbk; k++) {
@@ -127,6 +129,7 @@ static int diag_attr() {
   CNLD_CK(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
     CNLD_CK(cudaFuncSetAttribute(k_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+    CNLD_CK((cudaFuncSetAttribute(k_diag<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM)));
     CNLD_CK(cudaFuncSetAttribute(k_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
     attr_set[dev & 63] = true;
   }
@@ -251,6 +254,100 @@ int lu_factor(cudaStream_t st, LuWork &w, cplx *a, size_t lda) {
     }
   }
   if (ahead && t2_pending) CNLD_CK(cudaStreamWaitEvent(st, w.ev_join, 0));
+  w.nouter = ob;
+  w.nbo = NBO;
+  return 0;
+}
+
+// dst(r, c) = d(r) * src(c, r):  U block = D * L block^T  (G = L D L^T  =>  R = D L^T), 32x32 tiles
+__global__ void __launch_bounds__(256)
+k_ut(uint R, uint Cn, const cplx *__restrict__ src, const cplx *__restrict__ diag, cplx *dst, size_t lda) {
+  __shared__ cplx tile[32][33];
+  const uint r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const uint tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (uint k = ty; k < 32; k += 8) {
+    uint c = c0 + tx, r = r0 + k;  // src(c, r): c contiguous
+    if (c < Cn && r < R) tile[k][tx] = src[(size_t)r * lda + c];
+  }
+  __syncthreads();
+  for (uint k = ty; k < 32; k += 8) {
+    uint r = r0 + tx, c = c0 + k;  // dst(r, c): r contiguous
+    if (r < R && c < Cn) dst[(size_t)c * lda + r] = cmul(diag[(size_t)r * (lda + 1)], tile[tx][k]);
+  }
+}
+
+static int ut(cudaStream_t st, uint R, uint Cn, const cplx *src, const cplx *diag, cplx *dst, size_t lda) {
+  if (!R || !Cn) return 0;
+  dim3 grid((R + 31) / 32, (Cn + 31) / 32);
+  k_ut<<<grid, 256, 0, st>>>(R, Cn, src, diag, dst, lda);
+  CNLD_CK_LAUNCH();
+  return 0;
+}
+
+// Symmetric variant: a holds the LOWER triangle of a complex symmetric matrix S.  The unpivoted
+// elimination of S is S = L R with R = D L^T, so only L is computed by ZGEMMs; every block of R is
+// obtained from L by a scaled transposition, the block-row products disappear and the trailing
+// updates touch only the tiles on or below the diagonal: (4/3) n^3 conventional flops instead of
+// (8/3) n^3.  On exit the buffer holds L (unit lower) and R (upper) exactly like lu_factor's, so
+// lu_solve applies unchanged.  Look-ahead as in lu_factor.
+int lu_factor_sym(cudaStream_t st, LuWork &w, cplx *a, size_t lda) {
+  if (diag_attr()) return -1;
+  const uint n = w.n;
+  const uint NBO = (uint)((g_lu_outer / NB) * NB > 0 ? (g_lu_outer / NB) * NB : NB);
+  CNLD_CK(cudaMemsetAsync(w.info, 0, sizeof(uint), st));
+  const bool ahead = w.lo != nullptr;
+  bool t2_pending = false;
+  uint ob = 0;
+  for (uint O = 0; O < n; O += NBO, ob++) {
+    const uint W = (n - O < NBO) ? n - O : NBO;
+    const uint OE = O + W;
+    for (uint o = O; o < OE; o += NB) {
+      const uint b = o / NB;
+      const uint nbk = (OE - o < (uint)NB) ? OE - o : NB;
+      const uint below = n - o - nbk;
+      cplx *akk = a + (size_t)o * lda + o;
+      k_diag<true, true><<<1, DIAG_THREADS, DIAG_SMEM, st>>>(a, lda, n, b, w.linv, w.uinv, w.info);
+      CNLD_CK_LAUNCH();
+      if (!below) continue;
+      cplx *a21 = akk + nbk, *a12 = akk + (size_t)nbk * lda, *a22 = a12 + nbk;
+      if (zgemm(st, below, nbk, nbk, 1.0, a21, lda, w.uinv + (size_t)b * NB * NB, NB, 0.0, a21, lda)) return -1;
+      const uint in_cols = OE - o - nbk;
+      if (in_cols) {
+        if (ut(st, nbk, in_cols, a21, akk, a12, lda)) return -1;
+        if (zgemm3m(st, below, in_cols, nbk, -1.0, a21, lda, a12, lda, 1.0, a22, lda)) return -1;
+      }
+    }
+    const uint rem = n - OE;
+    if (!rem) break;
+    cplx *l = a + (size_t)O * lda + OE, *u = a + (size_t)OE * lda + O, *t = a + (size_t)OE * lda + OE;
+    if (ut(st, W, rem, l, a + (size_t)O * lda + O, u, lda)) return -1;
+    const uint W2 = (rem < NBO) ? rem : NBO;
+    if (t2_pending) CNLD_CK(cudaStreamWaitEvent(st, w.ev_join, 0));
+    // T1: the block column of the next outer block (all rows below)
+    if (zgemm3m(st, rem, W2, W, -1.0, l, lda, u, lda, 1.0, t, lda)) return -1;
+    const uint rest = rem - W2;
+    t2_pending = false;
+    w.pflops[ob] = 0.0;
+    if (rest) {
+      cudaStream_t ts = st;
+      if (ahead) {
+        CNLD_CK(cudaEventRecord(w.ev_fork, st));
+        CNLD_CK(cudaStreamWaitEvent(w.lo, w.ev_fork, 0));
+        ts = w.lo;
+      }
+      if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * ob], ts));
+      double tiles = 0.0;
+      if (zgemm3m(ts, rest, rest, W, -1.0, l + W2, lda, u + (size_t)W2 * lda, lda, 1.0, t + (size_t)W2 * lda + W2, lda,
+                  ahead ? g_lu_reserve_sms : 0, true, &tiles)) return -1;
+      if (w.prof) CNLD_CK(cudaEventRecord(w.pe[2 * ob + 1], ts));
+      if (ahead) {
+        CNLD_CK(cudaEventRecord(w.ev_join, w.lo));
+        t2_pending = true;
+      }
+      w.pflops[ob] = 6.0 * tiles * W;  // tiles = computed output entries
+    }
+  }
+  if (t2_pending) CNLD_CK(cudaStreamWaitEvent(st, w.ev_join, 0));
   w.nouter = ob;
   w.nbo = NBO;
   return 0;

@@ -177,4 +177,21 @@ void build_touching_pairs(unsigned nv, unsigned nt, const unsigned *tri, std::ve
   }
 }
 
+void build_touch_slots(const std::vector<TouchPair> &pairs, TouchSlots &S) {
+  std::vector<unsigned long long> keys;
+  keys.reserve(pairs.size() * 9);
+  for (const TouchPair &P : pairs)
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) keys.push_back(((unsigned long long)P.rv[i] << 32) | P.cv[j]);
+  std::vector<unsigned long long> uniq(keys);
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  auto find = [&](unsigned long long k) { return (unsigned)(std::lower_bound(uniq.begin(), uniq.end(), k) - uniq.begin()); };
+  S.row.resize(uniq.size()); S.col.resize(uniq.size()); S.tr.resize(uniq.size());
+  for (size_t s = 0; s < uniq.size(); s++) { S.row[s] = (unsigned)(uniq[s] >> 32); S.col[s] = (unsigned)(uniq[s] & 0xffffffffu); }
+  for (size_t s = 0; s < uniq.size(); s++) S.tr[s] = find(((unsigned long long)S.col[s] << 32) | S.row[s]);
+  S.pair_slot.resize(keys.size());
+  for (size_t k = 0; k < keys.size(); k++) S.pair_slot[k] = find(keys[k]);
+}
+
 }  // namespace cnld

@@ -28,4 +28,13 @@ void build_triangle_rule(unsigned q, std::vector<double> &t, std::vector<double>
 unsigned match_triangles(const unsigned *tv, const unsigned *sv, unsigned *tp, unsigned *sp);
 void build_touching_pairs(unsigned nv, unsigned nt, const unsigned *tri, std::vector<TouchPair> &out);
 
+// Sparse pattern of all matrix entries that receive contributions from touching pairs:
+// slot s = (row[s], col[s]), tr[s] = slot of the transposed entry, pair_slot[9*p + 3*i + j] = slot of
+// entry (rv[i], cv[j]) of pair p.  Used by the symmetric path: the Sauter-Schwab rules are not
+// symmetric under swapping the two triangles, so these entries carry the (tiny) asymmetry of Z.
+struct TouchSlots {
+  std::vector<unsigned> row, col, tr, pair_slot;
+};
+void build_touch_slots(const std::vector<TouchPair> &pairs, TouchSlots &S);
+
 }  // namespace cnld

@@ -174,7 +174,7 @@ constexpr int T3_SMEM = T3_STAGES * (T3_A_STAGE + T3_B_STAGE) * (int)sizeof(cplx
 
 __global__ void __launch_bounds__(T3_NT, 2)
 zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A, size_t lda,
-               const cplx *__restrict__ B, size_t ldb, double beta, cplx *C, size_t ldc) {
+               const cplx *__restrict__ B, size_t ldb, double beta, cplx *C, size_t ldc, int lower_only) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx *As = reinterpret_cast<cplx *>(smem_raw);
   cplx *Bs = As + T3_STAGES * T3_A_STAGE;
@@ -192,6 +192,7 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
   const uint grp = tile / gsz_full, first = grp * T3_GM;
   const uint gm = min((uint)T3_GM, mt - first), within = tile % gsz_full;
   const uint m0 = (first + within % gm) * T3_BM, n0 = (within / gm) * T3_BN;
+  if (lower_only && m0 + T3_BM <= n0) continue;  // tile entirely above the diagonal
   const int nk = (K + BK - 1) / BK;
 
   auto load_stage = [&](int kc, int stage) {
@@ -296,7 +297,15 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
 int g_zgemm_3m = 1;  // use the 3M kernel for non-aliased accumulating products
 
 int zgemm3m(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
-            const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, int reserve_sms) {
+            const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, int reserve_sms, bool lower_only,
+            double *entries) {
+  if (entries) {
+    double cnt = 0.0;
+    for (uint n0 = 0; n0 < N; n0 += T3_BN)
+      for (uint m0 = 0; m0 < M; m0 += T3_BM)
+        if (!lower_only || m0 + T3_BM > n0) cnt += (double)std::min((uint)T3_BM, M - m0) * std::min((uint)T3_BN, N - n0);
+    *entries = cnt;
+  }
   if (M == 0 || N == 0) return 0;
   if (!g_zgemm_3m) return zgemm(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
   static bool attr_set[64] = {false};
@@ -313,7 +322,7 @@ int zgemm3m(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A
   // latency-bound kernels on another stream
   const int use_sms = std::max(1, nsm[dev & 63] - std::max(0, reserve_sms));
   dim3 grid(std::min(tiles, (uint)(2 * use_sms)));
-  zgemm3m_kernel<<<grid, T3_NT, T3_SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  zgemm3m_kernel<<<grid, T3_NT, T3_SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower_only ? 1 : 0);
   CNLD_CK_LAUNCH();
   return 0;
 }

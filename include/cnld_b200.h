@@ -81,6 +81,9 @@ int cnld_b200_nearfield_slp_ll(cnld_ctx *ctx, double k_re, double k_im, const cn
 /* lrdecomp_amatrix(a) (include/factorizations.h:173-182; compressed_formats.py:249):
  * in-place UNPIVOTED LU, L unit lower.  *info = 0 ok, k+1 if pivot k is zero/non-finite. */
 int cnld_b200_lrdecomp(int device, cnld_uint n, cnld_field *a, cnld_uint ld, cnld_uint *info);
+/* Same elimination for a complex SYMMETRIC matrix of which only the lower triangle is read
+ * (a = L R with R = D L^T, half the flops); on exit a holds L and R exactly like lrdecomp's. */
+int cnld_b200_lrdecomp_sym(int device, cnld_uint n, cnld_field *a, cnld_uint ld, cnld_uint *info);
 
 /* lrsolve_amatrix_avector(false, LU, x) (include/factorizations.h:233;
  * compressed_formats.py:259-262) for nrhs right-hand sides at once. */
@@ -126,6 +129,15 @@ int cnld_b200_sweep_fetch(cnld_ctx *ctx, cnld_uint nf, cnld_field *x_patch, cnld
  * when several streams are in flight), [3]=kernel launches, [4]=device seconds of the whole
  * sweep (begin/end events joined across all streams).  out must hold 5 doubles. */
 int cnld_b200_sweep_stage_times(cnld_ctx *ctx, double *out);
+
+/* Symmetric path (mode 1; default 0 = the reference's general elimination, solve_cholesky=False /
+ * lrdecomp_amatrix in cnld/h2lib/factorizations_cy.pyx).  G = S + Delta, S = the complex symmetric
+ * matrix given by G's lower triangle, Delta = the sparse strictly-upper asymmetry (the Sauter-Schwab
+ * rules are not symmetric under swapping the two panels; plus any asymmetry of K, M, B).  S is
+ * eliminated as S = L (D L^T) at half the flops, and x = G^-1 f is recovered by `refine_steps`
+ * steps of x <- x - S^-1 Delta e.  Same results as mode 0 to the refinement's convergence. */
+int cnld_b200_set_symmetric(cnld_ctx *ctx, int mode, int refine_steps);
+int cnld_b200_get_symmetric(const cnld_ctx *ctx, unsigned *mbk_asym_nnz);
 
 /* Dominant-kernel timing for the roofline: when profiling is on, every trailing-update
  * ZGEMM launch of the LU is bracketed by CUDA events on its own stream.
