@@ -59,7 +59,8 @@ def lib():
         L.cnld_b200_sweep_stage_times.argtypes = [vp, vp]
         L.cnld_b200_set_profile.argtypes = [vp, C.c_int]
         L.cnld_b200_set_symmetric.argtypes = [vp, C.c_int, C.c_int]
-        L.cnld_b200_get_symmetric.argtypes = [vp, vp]
+        L.cnld_b200_set_symmetric_tol.argtypes = [vp, f64]
+        L.cnld_b200_symmetric_stats.argtypes = [vp, vp, vp, vp]
         L.cnld_b200_sweep_kernel_stats.argtypes = [vp, vp]
         L.cnld_b200_pres_vector.argtypes = [vp, vp, u32, f64, f64, f64, vp]
         L.cnld_b200_pressure.argtypes = [vp, vp, u32, vp, u32, f64, f64, vp, u32, vp]
@@ -123,9 +124,16 @@ class Context:
     def set_streams(self, n):
         check(lib().cnld_b200_set_streams(self._h, int(n)))
 
-    def set_symmetric(self, mode, refine_steps=2):
+    def set_symmetric(self, mode, refine_steps=1, tol=None):
         """mode 1: factor the symmetric part at half the flops and refine with the sparse asymmetry."""
         check(lib().cnld_b200_set_symmetric(self._h, int(mode), int(refine_steps)))
+        if tol is not None:
+            check(lib().cnld_b200_set_symmetric_tol(self._h, float(tol)))
+
+    def symmetric_stats(self):
+        a, r, m = C.c_uint(0), C.c_uint(0), C.c_double(0.0)
+        mode = lib().cnld_b200_symmetric_stats(self._h, C.byref(a), C.byref(r), C.byref(m))
+        return dict(mode=mode, mbk_asym_nnz=a.value, redone=r.value, max_ratio=m.value)
 
     def geometry(self):
         g = np.zeros(self.nt)

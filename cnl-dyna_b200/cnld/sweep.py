@@ -71,13 +71,20 @@ class SweepSetup:
 
 
 class FrequencySweep:
-    """Device-resident sweep on one GPU."""
+    """Device-resident sweep on one GPU.
 
-    def __init__(self, setup, device=0, nstreams=2):
+    symmetric=True (default) eliminates the symmetric part of G at half the flops and recovers the
+    reference's (non-symmetric) solution by `refine_steps` refinement steps with the sparse asymmetry;
+    every frequency's convergence is checked on the device and a frequency that misses 1e-11 is redone
+    with the general elimination.  symmetric=False is the reference's elimination order
+    (compressed_formats.py:247-252, lrdecomp_amatrix)."""
+
+    def __init__(self, setup, device=0, nstreams=2, symmetric=True, refine_steps=1):
         self.setup = setup
         self.ctx = _lib.Context(setup.vertices, setup.triangles, q_reg=setup.q_reg, q_sing=setup.q_sing,
                                 device=device)
         self.ctx.set_streams(nstreams)
+        self.ctx.set_symmetric(1 if symmetric else 0, refine_steps)
         s = self.setup
         self.ctx.set_mbk(s.K, s.M, s.B)
         self.ctx.set_loads(s.F, s.AVG, s.on_boundary)
@@ -134,7 +141,7 @@ def broadcast_setup(setup, rank, device=None):
 
 
 def run_distributed(setup_or_none, freqs, rank, world, device=0, torch_device=None, nstreams=2,
-                    solver=None):
+                    solver=None, symmetric=True):
     """Block-distributed sweep: returns (x_patch[nf, P, P] on rank 0 else None, local seconds).
     `solver(setup, freqs) -> x_patch[nf_local, P, P]` defaults to the GPU sweep; tests inject a
     CPU stand-in to exercise the sharding / broadcast / gather logic under gloo."""
@@ -144,7 +151,7 @@ def run_distributed(setup_or_none, freqs, rank, world, device=0, torch_device=No
     setup = broadcast_setup(setup_or_none, rank, torch_device) if world > 1 else setup_or_none
     lo, hi = shard(len(freqs), rank, world)
     if solver is None:
-        sw = FrequencySweep(setup, device=device, nstreams=nstreams)
+        sw = FrequencySweep(setup, device=device, nstreams=nstreams, symmetric=symmetric)
         xp, _, t = sw.run(freqs[lo:hi], want_nodes=False)
         sw.close()
     else:

@@ -117,6 +117,7 @@ int ensure_workspace(cnld_ctx *c, bool need_host_stage) {
       CNLD_CK(cudaMalloc(&S.E, sizeof(cplx) * nv * (c->P ? c->P : 1)));
       CNLD_CK(cudaMalloc(&S.E2, sizeof(cplx) * nv * (c->P ? c->P : 1)));
       CNLD_CK(cudaMalloc(&S.sval, sizeof(cplx) * (c->bem.nslot + 1)));
+      CNLD_CK(cudaMalloc(&S.norms, 2 * sizeof(double)));
       CNLD_CK(cudaMalloc(&S.dval, sizeof(cplx) * (c->bem.nslot + 1)));
     }
     if (!S.lu.linv) {
@@ -138,7 +139,7 @@ void free_workspace(cnld_ctx *c) {
   for (int s = 0; s < MAX_SLOTS; s++) {
     Slot &S = c->slots[s];
     if (S.st) cudaStreamSynchronize(S.st);
-    cudaFree(S.G); cudaFree(S.X); cudaFree(S.E); cudaFree(S.E2); cudaFree(S.sval); cudaFree(S.dval);
+    cudaFree(S.G); cudaFree(S.X); cudaFree(S.E); cudaFree(S.E2); cudaFree(S.norms); cudaFree(S.sval); cudaFree(S.dval);
     if (S.hX) cudaFreeHost(S.hX);
     lu_work_free(S.lu);
     for (int e = 0; e < 4; e++) if (S.ev[e]) cudaEventDestroy(S.ev[e]);
@@ -175,19 +176,35 @@ __global__ void k_delta_apply(uint nv, uint P, const uint *__restrict__ rowptr, 
     R[(size_t)p * ld + r] = acc;
   }
 }
-__global__ void k_axpy(size_t n, const cplx *__restrict__ e, cplx *x) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { cplx v = x[i], w = e[i]; x[i] = make_double2(v.x + w.x, v.y + w.y); }
+// x += e; norms[0] += |e|^2, norms[1] += |x|^2  (convergence estimate of the refinement)
+__global__ void __launch_bounds__(256) k_axpy(size_t n, const cplx *__restrict__ e, cplx *x, double *norms) {
+  double ne = 0.0, nx = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    cplx v = x[i], w = e[i];
+    v = make_double2(v.x + w.x, v.y + w.y);
+    x[i] = v;
+    ne += w.x * w.x + w.y * w.y;
+    nx += v.x * v.x + v.y * v.y;
+  }
+  for (int o = 16; o; o >>= 1) { ne += __shfl_xor_sync(0xffffffffu, ne, o); nx += __shfl_xor_sync(0xffffffffu, nx, o); }
+  __shared__ double sh[2][8];
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = ne; sh[1][threadIdx.x >> 5] = nx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++) { ne += sh[0][w]; nx += sh[1][w]; }
+    atomicAdd(norms, ne); atomicAdd(norms + 1, nx);
+  }
 }
 
 // enqueue one frequency on a slot; results: xpatch slice (device), X holds x_node
-int enqueue_frequency(cnld_ctx *c, Slot &S, double f, double cs, double rho, cplx *d_xpatch_f) {
+int enqueue_frequency(cnld_ctx *c, Slot &S, double f, double cs, double rho, cplx *d_xpatch_f, bool allow_sym = true) {
   const uint nv = c->bem.nv, P = c->P;
   const double omega = TWO_PI * f, k = omega / cs;
   // symmetric path: G = S + Delta with S symmetric (lower triangle of G mirrored) and Delta the sparse,
   // strictly upper asymmetry of the Sauter-Schwab entries.  S is factored at half the cost and
   // x = G^-1 f is recovered by the stationary iteration e <- -S^-1 Delta e, x <- x + e.
-  const bool sym = c->symmetric != 0;
+  const bool sym = c->symmetric != 0 && allow_sym;
+  S.was_sym = sym;
   CNLD_CK(cudaEventRecord(S.ev[0], S.st));
   CNLD_CK(cudaMemsetAsync(S.G, 0, sizeof(cplx) * (size_t)nv * nv, S.st));
   k_scatter_mbk<<<(nv * 32 + 255) / 256, 256, 0, S.st>>>(nv, c->d_indptr, c->d_indices, c->d_K, c->d_M,
@@ -226,7 +243,8 @@ int enqueue_frequency(cnld_ctx *c, Slot &S, double f, double cs, double rho, cpl
       CNLD_CK_LAUNCH();
       if (lu_solve(S.st, S.lu, S.G, nv, dst, P, nv)) return -1;
       const size_t tot = (size_t)nv * P;
-      k_axpy<<<(uint)((tot + 255) / 256), 256, 0, S.st>>>(tot, dst, S.X);
+      CNLD_CK(cudaMemsetAsync(S.norms, 0, 2 * sizeof(double), S.st));
+      k_axpy<<<1184, 256, 0, S.st>>>(tot, dst, S.X, S.norms);
       CNLD_CK_LAUNCH();
       src = dst;
       cplx *t = dst; dst = other; other = t;
@@ -265,9 +283,29 @@ int sweep_impl(cnld_ctx *c, const double *freqs, uint nf, double cs, double rho,
   c->kstat[0] = c->kstat[1] = c->kstat[2] = 0.0;
   double acc[3] = {0, 0, 0};
   unsigned long long l0 = g_launches.load();
+  c->sym_redone = 0;
+  c->sym_max_ratio = 0.0;
+  bool end_recorded = false;
   auto drain = [&](Slot &S) -> int {
     if (S.pending < 0) return 0;
     CNLD_CK(cudaEventSynchronize(S.ev[3]));
+    if (S.was_sym && c->refine_steps > 0) {
+      // convergence of x <- x + e: |e_last| / |x| estimates rho^steps, the remaining error rho^(steps+1)
+      double nr[2] = {0, 0};
+      CNLD_CK(cudaMemcpy(nr, S.norms, sizeof(nr), cudaMemcpyDeviceToHost));
+      double ratio = (nr[1] > 0.0) ? std::sqrt(nr[0] / nr[1]) : 0.0;
+      if (!(ratio == ratio)) ratio = 1.0;  // NaN
+      if (ratio > c->sym_max_ratio) c->sym_max_ratio = ratio;
+      double remaining = std::pow(ratio, (c->refine_steps + 1.0) / c->refine_steps);
+      if (remaining > c->sym_tol) {  // not converged: redo this frequency with the general elimination
+        c->sym_redone++;
+        if (enqueue_frequency(c, S, freqs[S.pending], cs, rho, c->d_xpatch + (size_t)S.pending * P * P, false)) return -1;
+        if (x_node) CNLD_CK(cudaMemcpyAsync(S.hX, S.X, sizeof(cplx) * P * nv, cudaMemcpyDeviceToHost, S.st));
+        if (x_node) CNLD_CK(cudaEventRecord(S.ev[3], S.st));
+        if (end_recorded) CNLD_CK(cudaEventRecord(c->ev_end, S.st));
+        CNLD_CK(cudaEventSynchronize(S.ev[3]));
+      }
+    }
     float ms[3];
     for (int e = 0; e < 3; e++) { CNLD_CK(cudaEventElapsedTime(&ms[e], S.ev[e], S.ev[e + 1])); acc[e] += ms[e] * 1e-3; }
     if (t_freq) t_freq[S.pending] = (ms[0] + ms[1] + ms[2]) * 1e-3;
@@ -295,6 +333,7 @@ int sweep_impl(cnld_ctx *c, const double *freqs, uint nf, double cs, double rho,
   for (int s = 1; s < c->nslots; s++)
     if (c->slots[s].pending >= 0) CNLD_CK(cudaStreamWaitEvent(c->slots[0].st, c->slots[s].ev[3], 0));
   CNLD_CK(cudaEventRecord(c->ev_end, c->slots[0].st));
+  end_recorded = true;
   for (int s = 0; s < c->nslots; s++) {
     int rc = drain(c->slots[(nf + s) % c->nslots]);
     if (rc) return rc;
@@ -535,10 +574,17 @@ int cnld_b200_set_symmetric(cnld_ctx *c, int mode, int refine_steps) {
   c->refine_steps = refine_steps;
   return 0;
 }
-int cnld_b200_get_symmetric(const cnld_ctx *c, unsigned *mbk_asym_nnz) {
+int cnld_b200_symmetric_stats(const cnld_ctx *c, unsigned *mbk_asym_nnz, unsigned *redone, double *max_ratio) {
   if (!c) return -1;
   if (mbk_asym_nnz) *mbk_asym_nnz = c->m_nnz;
+  if (redone) *redone = c->sym_redone;
+  if (max_ratio) *max_ratio = c->sym_max_ratio;
   return c->symmetric;
+}
+int cnld_b200_set_symmetric_tol(cnld_ctx *c, double tol) {
+  if (!c || !(tol > 0.0)) { set_error("set_symmetric_tol: tol > 0"); return -1; }
+  c->sym_tol = tol;
+  return 0;
 }
 
 int cnld_b200_set_loads(cnld_ctx *c, cnld_uint P, const int64_t *f_indptr, const cnld_uint *f_idx,

@@ -20,6 +20,8 @@ struct Slot {
   cplx *hX = nullptr;     // pinned staging for x_node
   // symmetric path: sparse Sauter-Schwab slots, their asymmetry, refinement vectors (nv x P each)
   cplx *sval = nullptr, *dval = nullptr, *E = nullptr, *E2 = nullptr;
+  double *norms = nullptr;  // [sum |e_last|^2, sum |x|^2] of the last refinement step
+  bool was_sym = false;
   LuWork lu;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   long pending = -1;      // frequency index whose x_node sits in hX
@@ -60,7 +62,10 @@ struct cnld_ctx {
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   bool profile = false;
   // symmetric path (cnld_b200_set_symmetric): factor the symmetric part, refine with the sparse asymmetry
-  int symmetric = 0, refine_steps = 2;
+  int symmetric = 0, refine_steps = 1;
+  double sym_tol = 1e-11;       // estimated remaining relative error above which a frequency is redone (general path)
+  unsigned sym_redone = 0;      // frequencies redone in the last sweep
+  double sym_max_ratio = 0.0;   // largest |e_last| / |x| of the last sweep
   // strictly upper asymmetry of the FEM operators, CSR by row: (K, M, B)[r,c] - (K, M, B)[c,r]
   uint m_nnz = 0;
   uint *d_m_rowptr = nullptr, *d_m_col = nullptr;

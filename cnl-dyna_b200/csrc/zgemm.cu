@@ -174,7 +174,8 @@ constexpr int T3_SMEM = T3_STAGES * (T3_A_STAGE + T3_B_STAGE) * (int)sizeof(cplx
 
 __global__ void __launch_bounds__(T3_NT, 2)
 zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A, size_t lda,
-               const cplx *__restrict__ B, size_t ldb, double beta, cplx *C, size_t ldc, int lower_only) {
+               const cplx *__restrict__ B, size_t ldb, double beta, cplx *C, size_t ldc, int lower_only,
+               uint ntiles) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx *As = reinterpret_cast<cplx *>(smem_raw);
   cplx *Bs = As + T3_STAGES * T3_A_STAGE;
@@ -188,11 +189,29 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
   const uint mt = (M + T3_BM - 1) / T3_BM, nt = (N + T3_BN - 1) / T3_BN;
   const uint gsz_full = T3_GM * nt;
   const int fr = lane >> 2, fc = lane & 3;
-  for (uint tile = blockIdx.x; tile < mt * nt; tile += gridDim.x) {
-  const uint grp = tile / gsz_full, first = grp * T3_GM;
-  const uint gm = min((uint)T3_GM, mt - first), within = tile % gsz_full;
+  for (uint tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  uint first, gm, within;
+  if (!lower_only) {
+    const uint grp = tile / gsz_full;
+    first = grp * T3_GM;
+    gm = min((uint)T3_GM, mt - first);
+    within = tile % gsz_full;
+  } else {
+    // compacted list: row group g keeps only the column tiles that reach its last row's diagonal,
+    // so every CTA of the persistent grid gets the same number of computed tiles
+    uint t = tile;
+    first = 0;
+    for (;;) {
+      gm = min((uint)T3_GM, mt - first);
+      const uint cols = min(nt, ((first + gm) * T3_BM + T3_BN - 1) / T3_BN);
+      if (t < gm * cols) break;
+      t -= gm * cols;
+      first += T3_GM;
+    }
+    within = t;
+  }
   const uint m0 = (first + within % gm) * T3_BM, n0 = (within / gm) * T3_BN;
-  if (lower_only && m0 + T3_BM <= n0) continue;  // tile entirely above the diagonal
+  if (lower_only && m0 + T3_BM <= n0) continue;  // tile entirely above the diagonal (inside a diagonal group)
   const int nk = (K + BK - 1) / BK;
 
   auto load_stage = [&](int kc, int stage) {
@@ -317,12 +336,20 @@ int zgemm3m(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A
   }
   static int nsm[64] = {0};
   if (!nsm[dev & 63]) CNLD_CK(cudaDeviceGetAttribute(&nsm[dev & 63], cudaDevAttrMultiProcessorCount, dev));
-  const uint tiles = ((M + T3_BM - 1) / T3_BM) * ((N + T3_BN - 1) / T3_BN);
+  const uint mt = (M + T3_BM - 1) / T3_BM, ntn = (N + T3_BN - 1) / T3_BN;
+  uint tiles = mt * ntn;
+  if (lower_only) {  // same enumeration as the kernel's compacted list
+    tiles = 0;
+    for (uint first = 0; first < mt; first += T3_GM) {
+      const uint gm = std::min((uint)T3_GM, mt - first);
+      tiles += gm * std::min(ntn, ((first + gm) * T3_BM + T3_BN - 1) / T3_BN);
+    }
+  }
   // reserve_sms: leave that many SMs without a CTA of this (persistent) kernel, for concurrent
   // latency-bound kernels on another stream
   const int use_sms = std::max(1, nsm[dev & 63] - std::max(0, reserve_sms));
   dim3 grid(std::min(tiles, (uint)(2 * use_sms)));
-  zgemm3m_kernel<<<grid, T3_NT, T3_SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower_only ? 1 : 0);
+  zgemm3m_kernel<<<grid, T3_NT, T3_SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower_only ? 1 : 0, tiles);
   CNLD_CK_LAUNCH();
   return 0;
 }

@@ -135,9 +135,14 @@ int cnld_b200_sweep_stage_times(cnld_ctx *ctx, double *out);
  * matrix given by G's lower triangle, Delta = the sparse strictly-upper asymmetry (the Sauter-Schwab
  * rules are not symmetric under swapping the two panels; plus any asymmetry of K, M, B).  S is
  * eliminated as S = L (D L^T) at half the flops, and x = G^-1 f is recovered by `refine_steps`
- * steps of x <- x - S^-1 Delta e.  Same results as mode 0 to the refinement's convergence. */
+ * steps of e <- -S^-1 Delta e, x <- x + e.  |e_last| / |x| is measured on the device for every
+ * frequency; a frequency whose estimated remaining relative error exceeds the tolerance
+ * (default 1e-11) is redone with mode 0, so both modes return the same results to that tolerance.
+ * symmetric_stats returns the mode and, for the last sweep, the number of frequencies redone and the
+ * largest |e_last| / |x|; mbk_asym_nnz = entries of K, M, B that differ from their transposes. */
 int cnld_b200_set_symmetric(cnld_ctx *ctx, int mode, int refine_steps);
-int cnld_b200_get_symmetric(const cnld_ctx *ctx, unsigned *mbk_asym_nnz);
+int cnld_b200_set_symmetric_tol(cnld_ctx *ctx, double tol);
+int cnld_b200_symmetric_stats(const cnld_ctx *ctx, unsigned *mbk_asym_nnz, unsigned *redone, double *max_ratio);
 
 /* Dominant-kernel timing for the roofline: when profiling is on, every trailing-update
  * ZGEMM launch of the LU is bracketed by CUDA events on its own stream.

@@ -13,11 +13,11 @@ def _rel(a, b):
     return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300)
 
 
-def _sweep(nelem, refn, nstreams=2):
+def _sweep(nelem, refn, nstreams=2, symmetric=True):
     from cnld import arrays
     from cnld.sweep import FrequencySweep, SweepSetup
     setup = SweepSetup.from_abstract(arrays.matrix_array(nelem=nelem), refn)
-    return setup, FrequencySweep(setup, nstreams=nstreams)
+    return setup, FrequencySweep(setup, nstreams=nstreams, symmetric=symmetric)
 
 
 def test_c1_single_membrane_vs_oracle(po):
@@ -34,9 +34,10 @@ def test_c1_single_membrane_vs_oracle(po):
     sw.close()
 
 
-def test_c2_2x2_array_vs_oracle(po):
+@pytest.mark.parametrize('symmetric', [True, False])
+def test_c2_2x2_array_vs_oracle(po, symmetric):
     """configs[1]: 2x2 array, refn 15 (N = 1 924, P = 36), dense LU on one GPU."""
-    setup, sw = _sweep((2, 2), 15)
+    setup, sw = _sweep((2, 2), 15, symmetric=symmetric)
     freqs = np.linspace(0.05e6, 50e6, 1000)[[3, 640]]
     xp, xn, _ = sw.run(freqs)
     oarr = po.matrix_array(nelem=(2, 2))

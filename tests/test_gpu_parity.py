@@ -34,6 +34,18 @@ def test_lu_and_solve_vs_oracle(L, po, n, nrhs):
     assert _rel(G @ X, B) < 1e-11
 
 
+@pytest.mark.parametrize('n', [37, 64, 200, 517, 1300])
+def test_symmetric_lu_equals_general_lu(L, n):
+    """lrdecomp_sym reads only the lower triangle and returns the same L and R as lrdecomp on the mirrored
+    matrix (R = D L^T is formed by transposition instead of block-row products)."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    A = A + A.T + n * 1.5 * np.eye(n)
+    LU = L.lrdecomp(A)
+    LUs = L.lrdecomp_sym(np.tril(A) + 1e3 * np.triu(np.ones((n, n)), 1))   # garbage above the diagonal is ignored
+    assert np.abs(LU - LUs).max() / np.abs(LU).max() < 1e-13
+
+
 def test_lu_zero_pivot_raises(L):
     G = np.eye(70, dtype=np.complex128)
     G[5, 5] = 0.0
@@ -79,10 +91,11 @@ def _setup_sweep(L, po, nelem, refn):
     return arr, am, blocks, ctx
 
 
-@pytest.mark.parametrize('nstreams', [1, 3])
-def test_sweep_vs_oracle(L, po, nstreams):
+@pytest.mark.parametrize('nstreams,symmetric', [(1, 0), (3, 0), (1, 1), (3, 1)])
+def test_sweep_vs_oracle(L, po, nstreams, symmetric):
     arr, am, blocks, ctx = _setup_sweep(L, po, (2, 1), 4)
     ctx.set_streams(nstreams)
+    ctx.set_symmetric(symmetric, 1)
     freqs = np.array([0.0, 1e6, 7.3e6, 20e6, 50e6])
     xp, xn, t = ctx.sweep(freqs)
     for i, f in enumerate(freqs):
@@ -92,6 +105,44 @@ def test_sweep_vs_oracle(L, po, nstreams):
         assert _rel(xn[i].T, Xo) < 1e-9     # what the same-rule comparison actually achieves
     ctx.sweep_device(freqs)
     assert np.array_equal(ctx.sweep_fetch(len(freqs)), xp) or _rel(ctx.sweep_fetch(len(freqs)), xp) < 1e-12
+    ctx.close()
+
+
+def test_symmetric_path_convergence_guard(L, po):
+    """Symmetric-part elimination + refinement: 0 steps leaves the Sauter-Schwab asymmetry (~1e-7) in
+    the result, 1 step removes it; an unreachable tolerance forces the general-path redo, which then
+    reproduces the general result; an asymmetric K, M or B goes into the correction too."""
+    arr, am, blocks, ctx = _setup_sweep(L, po, (2, 1), 4)
+    freqs = np.array([2e6, 11e6, 37e6])
+    xp0, xn0, _ = ctx.sweep(freqs)
+    ctx.set_symmetric(1, 0)
+    _, xn_raw, _ = ctx.sweep(freqs)
+    assert 1e-12 < _rel(xn_raw, xn0) < 1e-4, _rel(xn_raw, xn0)
+    ctx.set_symmetric(1, 1)
+    xp1, xn1, _ = ctx.sweep(freqs)
+    st = ctx.symmetric_stats()
+    assert st['mode'] == 1 and st['redone'] == 0 and 0 < st['max_ratio'] < 1e-5, st
+    assert _rel(xn1, xn0) < 1e-11 and _rel(xp1, xp0) < 1e-11, (_rel(xn1, xn0), _rel(xp1, xp0))
+    ctx.set_symmetric(1, 1, tol=1e-30)
+    xp2, xn2, _ = ctx.sweep(freqs)
+    assert ctx.symmetric_stats()['redone'] == len(freqs)
+    assert _rel(xn2, xn0) < 1e-13 and _rel(xp2, xp0) < 1e-13      # atomics: summation order differs between runs
+    ctx.close()
+    # asymmetric FEM operators
+    from scipy.linalg import block_diag
+    ctx = L.Context(am.vertices, am.triangles)
+    K, M, B = (block_diag(*[b[i] for b in blocks]) for i in range(3))
+    rng = np.random.default_rng(5)
+    K = K * (1 + 1e-6 * rng.standard_normal(K.shape))
+    B = B * (1 + 1e-6 * rng.standard_normal(B.shape))
+    ctx.set_mbk(K, M, B)
+    ctx.set_loads(block_diag(*[b[3] for b in blocks]), block_diag(*[b[4] for b in blocks]), am.on_boundary)
+    _, xg, _ = ctx.sweep(freqs)
+    ctx.set_symmetric(1, 2)
+    _, xs, _ = ctx.sweep(freqs)
+    st = ctx.symmetric_stats()
+    assert st['mbk_asym_nnz'] > 0
+    assert _rel(xs, xg) < 1e-10, (_rel(xs, xg), st)
     ctx.close()
 
 
