@@ -60,6 +60,8 @@ def lib():
         L.cnld_b200_set_profile.argtypes = [vp, C.c_int]
         L.cnld_b200_set_symmetric.argtypes = [vp, C.c_int, C.c_int]
         L.cnld_b200_set_symmetric_tol.argtypes = [vp, f64]
+        L.cnld_b200_set_translation_classes.argtypes = [vp, C.c_int]
+        L.cnld_b200_translation_info.argtypes = [vp, vp, vp]
         L.cnld_b200_symmetric_stats.argtypes = [vp, vp, vp, vp]
         L.cnld_b200_sweep_kernel_stats.argtypes = [vp, vp]
         L.cnld_b200_pres_vector.argtypes = [vp, vp, u32, f64, f64, f64, vp]
@@ -129,6 +131,15 @@ class Context:
         check(lib().cnld_b200_set_symmetric(self._h, int(mode), int(refine_steps)))
         if tol is not None:
             check(lib().cnld_b200_set_symmetric_tol(self._h, float(tol)))
+
+    def set_translation_classes(self, on=True):
+        """Integrate one block of Z per membrane-offset class and copy the rest (symmetric path)."""
+        check(lib().cnld_b200_set_translation_classes(self._h, int(bool(on))))
+
+    def translation_info(self):
+        nc, ncl = C.c_uint(0), C.c_uint(0)
+        used = lib().cnld_b200_translation_info(self._h, C.byref(nc), C.byref(ncl))
+        return dict(in_use=bool(used == 1), components=nc.value, offset_classes=ncl.value)
 
     def symmetric_stats(self):
         a, r, m = C.c_uint(0), C.c_uint(0), C.c_double(0.0)

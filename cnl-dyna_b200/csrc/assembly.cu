@@ -135,16 +135,17 @@ k_singular(size_t npairs, const TouchPair *__restrict__ pairs, const double *__r
 // triangle completely with half the kernel evaluations.
 template <int NQ, bool CPLXK>
 __global__ void __launch_bounds__(REG_THREADS)
-k_regular_sym(uint nt, const __grid_constant__ RegRule R, const uint *__restrict__ tri,
+k_regular_sym(const WorkItem *__restrict__ work, const __grid_constant__ RegRule R, const uint *__restrict__ tri,
               const double *__restrict__ qp, const double *__restrict__ g, double kr, double ki,
               cplx alpha, cplx *Z, size_t ld) {
   __shared__ double s_qp[REG_CHUNK][NQ][3];
   __shared__ uint s_tv[REG_CHUNK][3];
   __shared__ double s_g[REG_CHUNK];
-  const uint t = blockIdx.x * REG_THREADS + threadIdx.x;
-  const uint s0 = blockIdx.y * REG_CHUNK;
-  if (s0 >= min(nt, (blockIdx.x + 1) * REG_THREADS)) return;  // whole chunk has s >= every t of the block
-  const uint ns = min((uint)REG_CHUNK, nt - s0);
+  const WorkItem wi = work[blockIdx.x];   // row triangles [t_begin, t_end) x column chunk [s_begin, s_end)
+  const uint t = wi.t_begin + threadIdx.x;
+  const uint nt = wi.t_end;
+  const uint s0 = wi.s_begin;
+  const uint ns = wi.s_end - wi.s_begin;
   for (uint i = threadIdx.x; i < ns * NQ * 3; i += REG_THREADS)
     (&s_qp[0][0][0])[i] = qp[(size_t)s0 * NQ * 3 + i];
   for (uint i = threadIdx.x; i < ns * 3; i += REG_THREADS) (&s_tv[0][0])[i] = tri[(size_t)s0 * 3 + i];
@@ -214,31 +215,58 @@ k_singular_slots(size_t npairs, const TouchPair *__restrict__ pairs, const uint 
   }
 }
 
-__global__ void k_slots_fold(uint nslot, const uint *__restrict__ row, const uint *__restrict__ col,
+// replicate the integrated blocks: dst block = src block (or its transpose), blk x blk each
+__global__ void __launch_bounds__(256)
+k_block_copy(const CopyItem *__restrict__ items, uint blk, cplx *G, size_t ld) {
+  __shared__ cplx tile[32][33];
+  const CopyItem it = items[blockIdx.z];
+  const uint i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;   // tile of the destination block
+  const uint tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (!it.transposed) {
+    for (uint k = ty; k < 32; k += 8) {
+      const uint i = i0 + tx, j = j0 + k;
+      if (i < blk && j < blk) G[(size_t)(it.dst_c0 + j) * ld + it.dst_r0 + i] = G[(size_t)(it.src_c0 + j) * ld + it.src_r0 + i];
+    }
+    return;
+  }
+  for (uint k = ty; k < 32; k += 8) {   // src(j, i): rows j contiguous
+    const uint j = j0 + tx, i = i0 + k;
+    if (i < blk && j < blk) tile[k][tx] = G[(size_t)(it.src_c0 + i) * ld + it.src_r0 + j];
+  }
+  __syncthreads();
+  for (uint k = ty; k < 32; k += 8) {
+    const uint i = i0 + tx, j = j0 + k;
+    if (i < blk && j < blk) G[(size_t)(it.dst_c0 + j) * ld + it.dst_r0 + i] = tile[tx][k];
+  }
+}
+
+// nslot0: slots of the integrated component(s); slot s takes its value from slot s % nslot0
+__global__ void k_slots_fold(uint nslot, uint nslot0, const uint *__restrict__ row, const uint *__restrict__ col,
                              const uint *__restrict__ tr, const cplx *__restrict__ sval, cplx alpha, cplx *G,
                              size_t ld, cplx *dval) {
   uint s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nslot) return;
   const uint r = row[s], c = col[s];
-  cplx v = cmul(alpha, sval[s]);
+  cplx v = cmul(alpha, sval[s % nslot0]);
   if (r >= c) {
     cplx *d = G + (size_t)c * ld + r;  // every lower slot is unique; the regular kernel has finished
     d->x += v.x;
     d->y += v.y;
     dval[s] = make_double2(0.0, 0.0);
   } else {
-    cplx w = cmul(alpha, sval[tr[s]]);
+    cplx w = cmul(alpha, sval[tr[s] % nslot0]);
     dval[s] = make_double2(v.x - w.x, v.y - w.y);
   }
 }
 
 template <int NQ>
 int launch_regular_sym(cudaStream_t st, const BemDev &b, double kr, double ki, cplx alpha, cplx *Z, size_t ld) {
-  dim3 grid((b.nt + REG_THREADS - 1) / REG_THREADS, (b.nt + REG_CHUNK - 1) / REG_CHUNK);
+  const BemDev::SymPlan &pl = b.plan[(b.periodic && b.use_periodic) ? 1 : 0];
+  if (!pl.nwork) return 0;
   if (ki != 0.0)
-    k_regular_sym<NQ, true><<<grid, REG_THREADS, 0, st>>>(b.nt, b.rule, b.t, b.qp, b.g, kr, ki, alpha, Z, ld);
+    k_regular_sym<NQ, true><<<pl.nwork, REG_THREADS, 0, st>>>(pl.work, b.rule, b.t, b.qp, b.g, kr, ki, alpha, Z, ld);
   else
-    k_regular_sym<NQ, false><<<grid, REG_THREADS, 0, st>>>(b.nt, b.rule, b.t, b.qp, b.g, kr, ki, alpha, Z, ld);
+    k_regular_sym<NQ, false><<<pl.nwork, REG_THREADS, 0, st>>>(pl.work, b.rule, b.t, b.qp, b.g, kr, ki, alpha, Z, ld);
   CNLD_CK_LAUNCH();
   return 0;
 }
@@ -319,6 +347,29 @@ int bem_create(BemDev &b, int device, uint nv, uint nt, const double *x, const u
     CNLD_CK(cudaMalloc(&b.slot_rowptr, sizeof(uint) * (nv + 1)));
     CNLD_CK(cudaMemcpy(b.slot_rowptr, rowptr.data(), sizeof(uint) * (nv + 1), cudaMemcpyHostToDevice));
   }
+  for (int per = 0; per < 2; per++) {
+    TranslationPlan P;
+    build_translation_plan(nv, nt, x, t, REG_THREADS, REG_CHUNK, per == 1, P);
+    if (per == 1) {
+      if (!P.periodic) break;
+      // the sparse slots / touching pairs must repeat with the components too
+      if (b.nslot % P.ncomp || b.npairs % P.ncomp) break;
+      bool ok = true;
+      const uint ns0 = b.nslot / P.ncomp;
+      for (size_t i = 0; i < b.npairs / P.ncomp && ok; i++) ok = pairs[i].t < P.ntc && pairs[i].s < P.ntc;
+      if (!ok) break;
+      b.periodic = true; b.ncomp = P.ncomp; b.nclass = P.nclass;
+      b.plan[1].nslot0 = ns0; b.plan[1].npairs0 = b.npairs / P.ncomp; b.plan[1].blk = P.nvc;
+    } else {
+      b.plan[0].nslot0 = b.nslot; b.plan[0].npairs0 = b.npairs; b.plan[0].blk = nv;
+    }
+    BemDev::SymPlan &pl = b.plan[per];
+    pl.nwork = (uint)P.work.size(); pl.ncopy = (uint)P.copy.size();
+    CNLD_CK(cudaMalloc(&pl.work, sizeof(WorkItem) * (P.work.size() + 1)));
+    CNLD_CK(cudaMemcpy(pl.work, P.work.data(), sizeof(WorkItem) * P.work.size(), cudaMemcpyHostToDevice));
+    CNLD_CK(cudaMalloc(&pl.copy, sizeof(CopyItem) * (P.copy.size() + 1)));
+    CNLD_CK(cudaMemcpy(pl.copy, P.copy.data(), sizeof(CopyItem) * P.copy.size(), cudaMemcpyHostToDevice));
+  }
   k_tri_setup<<<(nt + 127) / 128, 128>>>(nt, b.nq, b.rule, b.x, b.t, b.g, b.n, b.qp);
   CNLD_CK_LAUNCH();
   CNLD_CK(cudaDeviceSynchronize());
@@ -329,6 +380,7 @@ void bem_free(BemDev &b) {
   cudaFree(b.x); cudaFree(b.t); cudaFree(b.g); cudaFree(b.n); cudaFree(b.qp); cudaFree(b.pairs);
   cudaFree(b.pair_slot); cudaFree(b.slot_row); cudaFree(b.slot_col); cudaFree(b.slot_tr); cudaFree(b.slot_rowptr);
   for (int f = 0; f < 4; f++) cudaFree(const_cast<double *>(b.sing.p[f]));
+  for (int per = 0; per < 2; per++) { cudaFree(b.plan[per].work); cudaFree(b.plan[per].copy); }
   b = BemDev();
 }
 
@@ -352,7 +404,8 @@ int bem_assemble(cudaStream_t st, const BemDev &b, double kr, double ki, cplx al
 
 int bem_assemble_sym(cudaStream_t st, const BemDev &b, double kr, double ki, cplx alpha, cplx *G, size_t ld,
                      cplx *sval, cplx *dval) {
-  CNLD_CK(cudaMemsetAsync(sval, 0, sizeof(cplx) * b.nslot, st));
+  const BemDev::SymPlan &pl = b.plan[(b.periodic && b.use_periodic) ? 1 : 0];
+  CNLD_CK(cudaMemsetAsync(sval, 0, sizeof(cplx) * pl.nslot0, st));
   int rc;
   switch (b.nq) {
   case 1: rc = launch_regular_sym<1>(st, b, kr, ki, alpha, G, ld); break;
@@ -361,14 +414,23 @@ int bem_assemble_sym(cudaStream_t st, const BemDev &b, double kr, double ki, cpl
   default: rc = launch_regular_sym<16>(st, b, kr, ki, alpha, G, ld); break;
   }
   if (rc) return rc;
-  unsigned grid = (unsigned)((b.npairs + SING_WARPS - 1) / SING_WARPS);
-  if (ki != 0.0)
-    k_singular_slots<true><<<grid, SING_WARPS * 32, 0, st>>>(b.npairs, b.pairs, b.pair_slot, b.x, b.g, b.sing, kr, ki, sval);
-  else
-    k_singular_slots<false><<<grid, SING_WARPS * 32, 0, st>>>(b.npairs, b.pairs, b.pair_slot, b.x, b.g, b.sing, kr, ki, sval);
-  CNLD_CK_LAUNCH();
-  k_slots_fold<<<(b.nslot + 255) / 256, 256, 0, st>>>(b.nslot, b.slot_row, b.slot_col, b.slot_tr, sval, alpha, G, ld, dval);
-  CNLD_CK_LAUNCH();
+  if (pl.ncopy) {  // blocks with the same offset between their components are equal (periodic.h)
+    dim3 grid((pl.blk + 31) / 32, (pl.blk + 31) / 32, pl.ncopy);
+    k_block_copy<<<grid, 256, 0, st>>>(pl.copy, pl.blk, G, ld);
+    CNLD_CK_LAUNCH();
+  }
+  if (pl.npairs0) {
+    unsigned grid = (unsigned)((pl.npairs0 + SING_WARPS - 1) / SING_WARPS);
+    if (ki != 0.0)
+      k_singular_slots<true><<<grid, SING_WARPS * 32, 0, st>>>(pl.npairs0, b.pairs, b.pair_slot, b.x, b.g, b.sing, kr, ki, sval);
+    else
+      k_singular_slots<false><<<grid, SING_WARPS * 32, 0, st>>>(pl.npairs0, b.pairs, b.pair_slot, b.x, b.g, b.sing, kr, ki, sval);
+    CNLD_CK_LAUNCH();
+  }
+  if (b.nslot) {
+    k_slots_fold<<<(b.nslot + 255) / 256, 256, 0, st>>>(b.nslot, pl.nslot0, b.slot_row, b.slot_col, b.slot_tr, sval, alpha, G, ld, dval);
+    CNLD_CK_LAUNCH();
+  }
   return 0;
 }
 

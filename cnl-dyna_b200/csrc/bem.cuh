@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "quadrature.h"
+#include "periodic.h"
 
 namespace cnld {
 
@@ -32,6 +33,18 @@ struct BemDev {
   uint nslot = 0;
   uint *pair_slot = nullptr, *slot_row = nullptr, *slot_col = nullptr, *slot_tr = nullptr;
   uint *slot_rowptr = nullptr;  // nv + 1: slots are sorted by (row, col)
+  // symmetric-path work lists (periodic.h): [0] integrate every pair s < t, [1] one block per
+  // translation class + copies (only when the mesh is translated copies of one component)
+  struct SymPlan {
+    uint nwork = 0, ncopy = 0, blk = 0;
+    WorkItem *work = nullptr;
+    CopyItem *copy = nullptr;
+    uint nslot0 = 0;       // slots of the integrated component(s)
+    size_t npairs0 = 0;    // touching pairs of the integrated component(s)
+  } plan[2];
+  bool periodic = false;   // plan[1] is valid
+  int use_periodic = 1;    // use it when valid
+  uint ncomp = 1, nclass = 0;
 };
 
 int bem_create(BemDev &b, int device, uint nv, uint nt, const double *x, const uint *t, uint q, uint q2);

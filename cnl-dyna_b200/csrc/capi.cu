@@ -33,6 +33,7 @@ using namespace cnld::sweep;
 
 namespace cnld_capi {
 
+template <bool ADD>
 __global__ void k_scatter_mbk(uint nv, const int64_t *__restrict__ indptr, const uint *__restrict__ indices,
                               const double *__restrict__ K, const double *__restrict__ M,
                               const double *__restrict__ B, double omega, cplx *G, size_t ld) {
@@ -42,7 +43,10 @@ __global__ void k_scatter_mbk(uint nv, const int64_t *__restrict__ indptr, const
   if (row >= nv) return;
   double w2 = omega * omega;
   for (int64_t p = indptr[row] + lane; p < indptr[row + 1]; p += 32) {
-    G[(size_t)indices[p] * ld + row] = make_double2(K[p] - w2 * M[p], -omega * B[p]);
+    cplx *d = G + (size_t)indices[p] * ld + row;
+    const cplx v = make_double2(K[p] - w2 * M[p], -omega * B[p]);
+    if (ADD) { d->x += v.x; d->y += v.y; }   // pattern entries are unique: no atomics needed
+    else *d = v;
   }
 }
 
@@ -207,9 +211,11 @@ int enqueue_frequency(cnld_ctx *c, Slot &S, double f, double cs, double rho, cpl
   S.was_sym = sym;
   CNLD_CK(cudaEventRecord(S.ev[0], S.st));
   CNLD_CK(cudaMemsetAsync(S.G, 0, sizeof(cplx) * (size_t)nv * nv, S.st));
-  k_scatter_mbk<<<(nv * 32 + 255) / 256, 256, 0, S.st>>>(nv, c->d_indptr, c->d_indices, c->d_K, c->d_M,
-                                                      c->d_B, omega, S.G, nv);
-  CNLD_CK_LAUNCH();
+  if (!sym) {
+    k_scatter_mbk<false><<<(nv * 32 + 255) / 256, 256, 0, S.st>>>(nv, c->d_indptr, c->d_indices, c->d_K, c->d_M,
+                                                               c->d_B, omega, S.G, nv);
+    CNLD_CK_LAUNCH();
+  }
   if (sym && f == 0.0) CNLD_CK(cudaMemsetAsync(S.dval, 0, sizeof(cplx) * (c->bem.nslot + 1), S.st));
   if (f != 0.0) {
     // Gbe = -omg^2 * 2 * rho * Z   (generate_db.py:55-56)
@@ -226,6 +232,11 @@ int enqueue_frequency(cnld_ctx *c, Slot &S, double f, double cs, double rho, cpl
       CNLD_CK(cudaEventRecord(S.ev_join, S.st_asm));
       CNLD_CK(cudaStreamWaitEvent(S.st, S.ev_join, 0));
     }
+  }
+  if (sym) {  // after the assembly: the translation-class copies overwrite whole blocks of G
+    k_scatter_mbk<true><<<(nv * 32 + 255) / 256, 256, 0, S.st>>>(nv, c->d_indptr, c->d_indices, c->d_K, c->d_M,
+                                                              c->d_B, omega, S.G, nv);
+    CNLD_CK_LAUNCH();
   }
   CNLD_CK(cudaEventRecord(S.ev[1], S.st));
   if (sym ? lu_factor_sym(S.st, S.lu, S.G, nv) : lu_factor(S.st, S.lu, S.G, nv)) return -1;
@@ -580,6 +591,17 @@ int cnld_b200_symmetric_stats(const cnld_ctx *c, unsigned *mbk_asym_nnz, unsigne
   if (redone) *redone = c->sym_redone;
   if (max_ratio) *max_ratio = c->sym_max_ratio;
   return c->symmetric;
+}
+int cnld_b200_set_translation_classes(cnld_ctx *c, int on) {
+  if (!c) { set_error("null context"); return -1; }
+  c->bem.use_periodic = on ? 1 : 0;
+  return 0;
+}
+int cnld_b200_translation_info(const cnld_ctx *c, unsigned *ncomp, unsigned *nclass) {
+  if (!c) return -1;
+  if (ncomp) *ncomp = c->bem.ncomp;
+  if (nclass) *nclass = c->bem.nclass;
+  return (c->bem.periodic && c->bem.use_periodic) ? 1 : 0;
 }
 int cnld_b200_set_symmetric_tol(cnld_ctx *c, double tol) {
   if (!c || !(tol > 0.0)) { set_error("set_symmetric_tol: tol > 0"); return -1; }

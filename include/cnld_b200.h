@@ -142,6 +142,17 @@ int cnld_b200_sweep_stage_times(cnld_ctx *ctx, double *out);
  * largest |e_last| / |x|; mbk_asym_nnz = entries of K, M, B that differ from their transposes. */
 int cnld_b200_set_symmetric(cnld_ctx *ctx, int mode, int refine_steps);
 int cnld_b200_set_symmetric_tol(cnld_ctx *ctx, double tol);
+
+/* Translation classes (symmetric path only).  A CMUT array mesh is one membrane mesh translated to
+ * every membrane position (cnld/mesh.py Mesh.from_abstract), and the kernel depends on x - y only:
+ * the block of Z coupling membranes a and b depends on their offset alone.  When the mesh is
+ * detected to be translated copies of its first connected component (identical connectivity,
+ * vertices equal up to a translation to 32 ulp), one block per distinct offset is integrated and the
+ * others are copied (opposite offsets: transposed).  Values differ from integrating every block only
+ * through the rounding of the translated coordinates.  on = 1 by default; translation_info returns
+ * whether the classes are in use, the number of components and of integrated off-diagonal blocks. */
+int cnld_b200_set_translation_classes(cnld_ctx *ctx, int on);
+int cnld_b200_translation_info(const cnld_ctx *ctx, unsigned *ncomp, unsigned *nclass);
 int cnld_b200_symmetric_stats(const cnld_ctx *ctx, unsigned *mbk_asym_nnz, unsigned *redone, double *max_ratio);
 
 /* Dominant-kernel timing for the roofline: when profiling is on, every trailing-update

@@ -146,6 +146,47 @@ def test_symmetric_path_convergence_guard(L, po):
     ctx.close()
 
 
+def test_translation_classes(L, po):
+    """A membrane array is one mesh translated to every membrane position, so Z's membrane blocks
+    depend on the offset only: integrating one block per offset class and copying the others must
+    reproduce integrating everything (to the rounding of the translated coordinates), and a mesh that
+    is not an exact set of translated copies must not be treated as one."""
+    from scipy.linalg import block_diag
+    arr = po.matrix_array(nelem=(3, 2))
+    am, blocks = po.array_mesh(arr, 3), po.array_fem(arr, 3)
+    mbk = [block_diag(*[b[i] for b in blocks]) for i in range(3)]
+    loads = (block_diag(*[b[3] for b in blocks]), block_diag(*[b[4] for b in blocks]), am.on_boundary)
+    freqs = np.array([1.5e6, 9e6, 41e6])
+
+    def run(vertices, classes):
+        ctx = L.Context(vertices, am.triangles)
+        ctx.set_mbk(*mbk)
+        ctx.set_loads(*loads)
+        ctx.set_symmetric(1, 1)
+        ctx.set_translation_classes(classes)
+        xp, xn, _ = ctx.sweep(freqs)
+        info = ctx.translation_info()
+        ctx.close()
+        return xn, info
+
+    x_all, info0 = run(am.vertices, False)
+    x_cls, info1 = run(am.vertices, True)
+    assert not info0['in_use'] and info1['in_use']
+    assert info1['components'] == 6
+    # 3 x 2 lattice: offsets (dx, dy) with dx in -2..2, dy in -1..1, up to sign -> 7 classes
+    assert info1['offset_classes'] == 7
+    assert _rel(x_cls, x_all) < 1e-11
+    Xo, _ = po.solve_frequency(am, blocks, freqs[1])
+    assert _rel(x_cls[1].T, Xo) < 1e-9
+    # one vertex moved by 1e-3 of an edge: not translated copies any more
+    V = am.vertices.copy()
+    V[am.nvertices // 2 + 3, 0] += 1e-9
+    x_ref, _ = run(V, False)
+    x_new, info2 = run(V, True)
+    assert not info2['in_use']
+    assert _rel(x_new, x_ref) < 1e-12
+
+
 def test_pressure_vs_oracle(L, po):
     arr, am, blocks, ctx = _setup_sweep(L, po, (2, 1), 3)
     rng = np.random.default_rng(1)
