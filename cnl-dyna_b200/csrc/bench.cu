@@ -92,4 +92,5 @@ extern "C" int cnld_b200_set_zgemm_variant(int v) { cnld::g_zgemm_variant = v; r
 extern "C" int cnld_b200_set_lu_outer(int v) { cnld::g_lu_outer = v; return 0; }
 extern "C" int cnld_b200_set_zgemm_3m(int v) { cnld::g_zgemm_3m = v; return 0; }
 
+extern "C" int cnld_b200_set_lu_outer_inverse(int v) { cnld::g_lu_outer_inverse = v; return 0; }
 extern "C" int cnld_b200_set_lu_reserve(int v) { cnld::g_lu_reserve_sms = v; return 0; }

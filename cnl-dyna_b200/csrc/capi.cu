@@ -546,7 +546,15 @@ int cnld_b200_set_mbk(cnld_ctx *c, const int64_t *indptr, const cnld_uint *indic
   {
     struct Trip { uint r, c; double k, m, b; };
     std::vector<Trip> trips;
+    bool sorted = true;   // scipy's canonical CSR: binary search; otherwise scan the row
+    for (size_t r = 0; r < nv && sorted; r++)
+      for (int64_t p = indptr[r] + 1; p < indptr[r + 1]; p++) if (indices[p - 1] >= indices[p]) { sorted = false; break; }
     auto find = [&](size_t r, uint col) -> int64_t {
+      if (sorted) {
+        const cnld_uint *b = indices + indptr[r], *e = indices + indptr[r + 1];
+        const cnld_uint *it = std::lower_bound(b, e, col);
+        return (it != e && *it == col) ? (int64_t)(it - indices) : -1;
+      }
       for (int64_t p = indptr[r]; p < indptr[r + 1]; p++) if (indices[p] == col) return p;
       return -1;
     };

@@ -66,6 +66,7 @@ __device__ __forceinline__ void cfms(cplx &c, cplx a, cplx b) {
 extern int g_zgemm_variant;
 extern int g_lu_outer;
 extern int g_lu_reserve_sms;
+extern int g_lu_outer_inverse;  // lu_solve through inverted outer diagonal blocks
 // ---- dense kernels (zgemm.cu / lu.cu) --------------------------------------
 // C(MxN) = beta*C + alpha*A(MxK)*B(KxN); alpha in {+1,-1}, beta in {0,1};
 // column-major, interleaved complex.  In-place (C aliasing A or B) is safe only
@@ -81,8 +82,23 @@ int zgemm3m(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A
             bool lower_only = false, double *entries = nullptr);
 extern int g_zgemm_3m;
 
+// Two-level batch of a ZGEMM: item q = o * per + j (blockIdx.z) shifts the operand pointers by
+// o * s?o + j * s?j elements.
+struct ZBatch {
+  uint per = 1;
+  long long sAo = 0, sAj = 0, sBo = 0, sBj = 0, sCo = 0, sCj = 0;
+};
+int zgemm_batched(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
+                  const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, uint nbatch, const ZBatch &bt);
+
 struct LuWork {
   uint n = 0, nb = 0, nblk = 0, nouter = 0, nbo = 0;
+  // inverses of the full nbo x nbo diagonal blocks of L and R (lu_invert_outer), used by lu_solve
+  cplx *linvO = nullptr, *uinvO = nullptr, *tmpO = nullptr;
+  uint inv_nbo = 0, inv_nfull = 0;   // geometry the buffers were allocated / filled for
+  bool inv_ready = false;
+  mutable cplx *ytmp = nullptr;      // nbo x nrhs scratch of lu_solve
+  mutable uint ytmp_cols = 0;
   cplx *linv = nullptr;  // [nblk][nb*nb]
   cplx *uinv = nullptr;  // [nblk][nb*nb]
   uint *info = nullptr;  // device flag: 0 ok else first failing pivot + 1
@@ -97,6 +113,8 @@ int lu_work_alloc(LuWork &w, uint n);
 void lu_work_free(LuWork &w);
 // form inv(L_kk), inv(R_kk) of an already factored matrix (stand-alone lrsolve entry)
 int lu_invert_diag(cudaStream_t st, LuWork &w, cplx *a, size_t lda);
+// inverses of the full outer diagonal blocks (recursive doubling from the nb-block inverses)
+int lu_invert_outer(cudaStream_t st, LuWork &w, const cplx *a, size_t lda);
 void lu_profile(LuWork &w, bool on);
 int lu_trailing_stats(const LuWork &w, double *seconds, double *flops, double *launches);
 // unpivoted LU in place on device matrix a (n x n, lda); keeps block inverses in w

@@ -113,6 +113,7 @@ int lu_work_alloc(LuWork &w, uint n) {
 }
 
 void lu_work_free(LuWork &w) {
+  cudaFree(w.linvO); cudaFree(w.uinvO); cudaFree(w.tmpO); cudaFree(w.ytmp);
   cudaFree(w.linv);
   cudaFree(w.uinv);
   cudaFree(w.info);
@@ -179,6 +180,7 @@ int lu_trailing_stats(const LuWork &w, double *seconds, double *flops, double *l
 //     main : inner(O) -> [wait T2(O-1)] T1(O) -> inner(O+1) -> [wait T2(O)] T1(O+1) -> ...
 //     lo   :                      [wait T1(O)] T2(O)   ->            [wait T1(O+1)] T2(O+1) ...
 int g_lu_outer = 512;
+int g_lu_outer_inverse = 1;
 int g_lu_reserve_sms = 12;
 
 static int inner_loop(cudaStream_t st, LuWork &w, cplx *a, size_t lda, uint O, uint OE) {
@@ -214,6 +216,7 @@ int lu_factor(cudaStream_t st, LuWork &w, cplx *a, size_t lda) {
   const uint n = w.n;
   const uint NBO = (uint)((g_lu_outer / NB) * NB > 0 ? (g_lu_outer / NB) * NB : NB);
   CNLD_CK(cudaMemsetAsync(w.info, 0, sizeof(uint), st));
+  w.inv_ready = false;
   const bool ahead = w.lo != nullptr;
   bool t2_pending = false;
   uint ob = 0;
@@ -256,7 +259,7 @@ int lu_factor(cudaStream_t st, LuWork &w, cplx *a, size_t lda) {
   if (ahead && t2_pending) CNLD_CK(cudaStreamWaitEvent(st, w.ev_join, 0));
   w.nouter = ob;
   w.nbo = NBO;
-  return 0;
+  return g_lu_outer_inverse ? lu_invert_outer(st, w, a, lda) : 0;
 }
 
 // dst(r, c) = d(r) * src(c, r):  U block = D * L block^T  (G = L D L^T  =>  R = D L^T), 32x32 tiles
@@ -295,6 +298,7 @@ int lu_factor_sym(cudaStream_t st, LuWork &w, cplx *a, size_t lda) {
   const uint n = w.n;
   const uint NBO = (uint)((g_lu_outer / NB) * NB > 0 ? (g_lu_outer / NB) * NB : NB);
   CNLD_CK(cudaMemsetAsync(w.info, 0, sizeof(uint), st));
+  w.inv_ready = false;
   const bool ahead = w.lo != nullptr;
   bool t2_pending = false;
   uint ob = 0;
@@ -350,18 +354,103 @@ int lu_factor_sym(cudaStream_t st, LuWork &w, cplx *a, size_t lda) {
   if (t2_pending) CNLD_CK(cudaStreamWaitEvent(st, w.ev_join, 0));
   w.nouter = ob;
   w.nbo = NBO;
+  return g_lu_outer_inverse ? lu_invert_outer(st, w, a, lda) : 0;
+}
+
+// ---- inverses of the outer diagonal blocks -----------------------------------------------------
+// zero the nbo x nbo inverse blocks and put the nb x nb block inverses (k_diag) on their diagonals
+__global__ void k_inv_init(uint nfull, uint nbo, const cplx *__restrict__ linv, const cplx *__restrict__ uinv,
+                           cplx *linvO, cplx *uinvO) {
+  const size_t tot = (size_t)nfull * nbo * nbo;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (size_t)gridDim.x * blockDim.x) {
+    const uint O = (uint)(idx / ((size_t)nbo * nbo));
+    const uint rem = (uint)(idx % ((size_t)nbo * nbo));
+    const uint i = rem % nbo, j = rem / nbo;
+    cplx l = make_double2(0.0, 0.0), u = l;
+    if (i / NB == j / NB) {
+      const size_t src = ((size_t)O * (nbo / NB) + i / NB) * NB * NB + (size_t)(j % NB) * NB + (i % NB);
+      l = linv[src];
+      u = uinv[src];
+    }
+    linvO[idx] = l;
+    uinvO[idx] = u;
+  }
+}
+
+// inv([A 0; C B]) = [A^-1 0; -B^-1 C A^-1  B^-1] (L) and inv([A C; 0 B]) = [A^-1  -A^-1 C B^-1; 0 B^-1] (R),
+// doubling the block size from nb to nbo, all outer blocks and all pairs of a level in one launch.
+int lu_invert_outer(cudaStream_t st, LuWork &w, const cplx *a, size_t lda) {
+  const uint nbo = w.nbo, nfull = w.n / (nbo ? nbo : 1);
+  w.inv_ready = false;
+  if (!nbo || nbo == (uint)NB || !nfull || (nbo & (nbo - 1)) || nbo % NB) return 0;  // needs nbo = nb * 2^k
+  if (w.inv_nbo != nbo || w.inv_nfull != nfull) {
+    cudaFree(w.linvO); cudaFree(w.uinvO); cudaFree(w.tmpO);
+    w.linvO = w.uinvO = w.tmpO = nullptr;
+    const size_t blk = (size_t)nbo * nbo;
+    CNLD_CK(cudaMalloc(&w.linvO, sizeof(cplx) * nfull * blk));
+    CNLD_CK(cudaMalloc(&w.uinvO, sizeof(cplx) * nfull * blk));
+    CNLD_CK(cudaMalloc(&w.tmpO, sizeof(cplx) * nfull * blk / 2));
+    w.inv_nbo = nbo; w.inv_nfull = nfull;
+  }
+  k_inv_init<<<1184, 256, 0, st>>>(nfull, nbo, w.linv, w.uinv, w.linvO, w.uinvO);
+  CNLD_CK_LAUNCH();
+  const long long blk = (long long)nbo * nbo;
+  for (uint s = NB; 2 * s <= nbo; s *= 2) {
+    const uint per = nbo / (2 * s), nbatch = nfull * per;
+    const long long dA = (long long)(lda + 1), dI = (long long)(nbo + 1);
+    ZBatch bt;
+    bt.per = per;
+    // L:  T = C * Ainv  (C = a[r0 + s, r0])
+    bt.sAo = nbo * dA; bt.sAj = 2 * s * dA;
+    bt.sBo = blk;      bt.sBj = 2 * s * dI;
+    bt.sCo = blk / 2;  bt.sCj = (long long)s * s;
+    if (zgemm_batched(st, s, s, s, 1.0, a + s, lda, w.linvO, nbo, 0.0, w.tmpO, s, nbatch, bt)) return -1;
+    //     new block = -Binv * T
+    bt.sAo = blk;      bt.sAj = 2 * s * dI;
+    bt.sBo = blk / 2;  bt.sBj = (long long)s * s;
+    bt.sCo = blk;      bt.sCj = 2 * s * dI;
+    if (zgemm_batched(st, s, s, s, -1.0, w.linvO + s * dI, nbo, w.tmpO, s, 0.0, w.linvO + s, nbo, nbatch, bt)) return -1;
+    // R:  T = C * Binv  (C = a[r0, r0 + s])
+    bt.sAo = nbo * dA; bt.sAj = 2 * s * dA;
+    bt.sBo = blk;      bt.sBj = 2 * s * dI;
+    bt.sCo = blk / 2;  bt.sCj = (long long)s * s;
+    if (zgemm_batched(st, s, s, s, 1.0, a + (size_t)s * lda, lda, w.uinvO + s * dI, nbo, 0.0, w.tmpO, s, nbatch, bt)) return -1;
+    //     new block = -Ainv * T
+    bt.sAo = blk;      bt.sAj = 2 * s * dI;
+    bt.sBo = blk / 2;  bt.sBj = (long long)s * s;
+    bt.sCo = blk;      bt.sCj = 2 * s * dI;
+    if (zgemm_batched(st, s, s, s, -1.0, w.uinvO, nbo, w.tmpO, s, 0.0, w.uinvO + (size_t)s * nbo, nbo, nbatch, bt)) return -1;
+  }
+  w.inv_ready = true;
   return 0;
 }
 
-// Forward / backward substitution for nrhs right-hand sides, blocked like the factorisation: 64-wide
-// steps with the inverted diagonal blocks inside an outer block of NBO rows, one rank-NBO ZGEMM per
-// outer block for everything beyond it.
+// Forward / backward substitution for nrhs right-hand sides (n x nrhs, ldx), in place.  Outer blocks
+// whose inverse is available (lu_invert_outer) take one product with the inverse and one rank-nbo
+// update of everything beyond; the others (a ragged last block, stand-alone lrsolve) go through
+// block steps with the inverted nb x nb diagonal blocks.
 int lu_solve(cudaStream_t st, const LuWork &w, const cplx *a, size_t lda, cplx *x, uint nrhs,
              size_t ldx) {
   const uint n = w.n;
-  const uint NBO = (uint)((g_lu_outer / NB) * NB > 0 ? (g_lu_outer / NB) * NB : NB);
-  for (uint O = 0; O < n; O += NBO) {  // L y = b
-    const uint OE = (n - O < NBO) ? n : O + NBO;
+  const bool inv = w.inv_ready && g_lu_outer_inverse;
+  const uint NBO = inv ? w.inv_nbo : (uint)((g_lu_outer / NB) * NB > 0 ? (g_lu_outer / NB) * NB : NB);
+  if (inv && w.ytmp_cols < nrhs) {
+    cudaFree(w.ytmp);
+    w.ytmp = nullptr;
+    CNLD_CK(cudaMalloc(&w.ytmp, sizeof(cplx) * (size_t)NBO * nrhs));
+    w.ytmp_cols = nrhs;
+  }
+  const uint nouter = (n + NBO - 1) / NBO;
+  for (uint ob = 0; ob < nouter; ob++) {  // L y = b
+    const uint O = ob * NBO, OE = (n - O < NBO) ? n : O + NBO;
+    if (inv && ob < w.inv_nfull) {
+      if (zgemm3m(st, NBO, nrhs, NBO, 1.0, w.linvO + (size_t)ob * NBO * NBO, NBO, x + O, ldx, 0.0, w.ytmp, NBO)) return -1;
+      CNLD_CK(cudaMemcpy2DAsync(x + O, sizeof(cplx) * ldx, w.ytmp, sizeof(cplx) * NBO, sizeof(cplx) * NBO, nrhs,
+                                cudaMemcpyDeviceToDevice, st));
+      if (n > OE && zgemm3m(st, n - OE, nrhs, NBO, -1.0, a + (size_t)O * lda + OE, lda, w.ytmp, NBO, 1.0, x + OE, ldx))
+        return -1;
+      continue;
+    }
     for (uint o = O; o < OE; o += NB) {
       const uint b = o / NB, nbk = (OE - o < (uint)NB) ? OE - o : NB, in_rows = OE - o - nbk;
       cplx *xb = x + o;
@@ -372,9 +461,15 @@ int lu_solve(cudaStream_t st, const LuWork &w, const cplx *a, size_t lda, cplx *
     if (n > OE && zgemm3m(st, n - OE, nrhs, OE - O, -1.0, a + (size_t)O * lda + OE, lda, x + O, ldx, 1.0, x + OE, ldx))
       return -1;
   }
-  const uint nouter = (n + NBO - 1) / NBO;
   for (uint ob = nouter; ob-- > 0;) {  // R x = y
     const uint O = ob * NBO, OE = (n - O < NBO) ? n : O + NBO;
+    if (inv && ob < w.inv_nfull) {
+      if (zgemm3m(st, NBO, nrhs, NBO, 1.0, w.uinvO + (size_t)ob * NBO * NBO, NBO, x + O, ldx, 0.0, w.ytmp, NBO)) return -1;
+      CNLD_CK(cudaMemcpy2DAsync(x + O, sizeof(cplx) * ldx, w.ytmp, sizeof(cplx) * NBO, sizeof(cplx) * NBO, nrhs,
+                                cudaMemcpyDeviceToDevice, st));
+      if (O && zgemm3m(st, O, nrhs, NBO, -1.0, a + (size_t)O * lda, lda, w.ytmp, NBO, 1.0, x, ldx)) return -1;
+      continue;
+    }
     const uint nin = (OE - O + NB - 1) / NB;
     for (uint ib = nin; ib-- > 0;) {
       const uint o = O + ib * NB, b = o / NB, nbk = (OE - o < (uint)NB) ? OE - o : NB;

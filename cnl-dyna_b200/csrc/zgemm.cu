@@ -48,8 +48,12 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 
 template <class CF, int MINB>
 __global__ void __launch_bounds__(CF::NT, MINB)
-zgemm_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A, size_t lda,
-             const cplx *__restrict__ B, size_t ldb, double beta, cplx *C, size_t ldc) {
+zgemm_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A0, size_t lda,
+             const cplx *__restrict__ B0, size_t ldb, double beta, cplx *C0, size_t ldc, const ZBatch bt) {
+  const long long bo = blockIdx.z / bt.per, bj = blockIdx.z % bt.per;
+  const cplx *__restrict__ A = A0 + bo * bt.sAo + bj * bt.sAj;
+  const cplx *__restrict__ B = B0 + bo * bt.sBo + bj * bt.sBj;
+  cplx *C = C0 + bo * bt.sCo + bj * bt.sCj;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx *As = reinterpret_cast<cplx *>(smem_raw);
   constexpr int BM = CF::BM, BN = CF::BN, STAGES = CF::STAGES, NT = CF::NT, AS_LD = CF::AS_LD,
@@ -189,32 +193,36 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
   const uint mt = (M + T3_BM - 1) / T3_BM, nt = (N + T3_BN - 1) / T3_BN;
   const uint gsz_full = T3_GM * nt;
   const int fr = lane >> 2, fc = lane & 3;
-  for (uint tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-  uint first, gm, within;
-  if (!lower_only) {
-    const uint grp = tile / gsz_full;
-    first = grp * T3_GM;
-    gm = min((uint)T3_GM, mt - first);
-    within = tile % gsz_full;
-  } else {
-    // compacted list: row group g keeps only the column tiles that reach its last row's diagonal,
-    // so every CTA of the persistent grid gets the same number of computed tiles
-    uint t = tile;
-    first = 0;
-    for (;;) {
-      gm = min((uint)T3_GM, mt - first);
-      const uint cols = min(nt, ((first + gm) * T3_BM + T3_BN - 1) / T3_BN);
-      if (t < gm * cols) break;
-      t -= gm * cols;
-      first += T3_GM;
-    }
-    within = t;
-  }
-  const uint m0 = (first + within % gm) * T3_BM, n0 = (within / gm) * T3_BN;
-  if (lower_only && m0 + T3_BM <= n0) continue;  // tile entirely above the diagonal (inside a diagonal group)
   const int nk = (K + BK - 1) / BK;
 
-  auto load_stage = [&](int kc, int stage) {
+  // tile index -> (m0, n0); false for a tile that lies entirely above the diagonal (lower_only)
+  auto coords = [&](uint tile, uint &m0, uint &n0) -> bool {
+    uint first, gm, within;
+    if (!lower_only) {
+      const uint grp = tile / gsz_full;
+      first = grp * T3_GM;
+      gm = min((uint)T3_GM, mt - first);
+      within = tile % gsz_full;
+    } else {
+      // compacted list: row group g keeps only the column tiles that reach its last row's diagonal,
+      // so every CTA of the persistent grid gets the same number of computed tiles
+      uint t = tile;
+      first = 0;
+      for (;;) {
+        gm = min((uint)T3_GM, mt - first);
+        const uint cols = min(nt, ((first + gm) * T3_BM + T3_BN - 1) / T3_BN);
+        if (t < gm * cols) break;
+        t -= gm * cols;
+        first += T3_GM;
+      }
+      within = t;
+    }
+    m0 = (first + within % gm) * T3_BM;
+    n0 = (within / gm) * T3_BN;
+    return !(lower_only && m0 + T3_BM <= n0);
+  };
+
+  auto load_stage = [&](uint m0, uint n0, int kc, int stage) {
     const uint k0 = kc * BK;
     cplx *as = As + stage * T3_A_STAGE;
     cplx *bs = Bs + stage * T3_B_STAGE;
@@ -235,7 +243,27 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
       cp_async16(bs + j * BS_LD + kb, src, ok);
     }
   };
+  auto prologue = [&](uint m0, uint n0) {
+#pragma unroll
+    for (int s = 0; s < T3_STAGES - 1; s++) {
+      if (s < nk) load_stage(m0, n0, s, s);
+      cp_async_commit();
+    }
+  };
 
+  uint tile = blockIdx.x, m0 = 0, n0 = 0;
+  while (tile < ntiles && !coords(tile, m0, n0)) tile += gridDim.x;
+  if (tile >= ntiles) return;
+  prologue(m0, n0);
+  for (;;) {
+  // the C tile is read ~70 us from now: pull its 384 lines into L2 while the main loop runs
+  if (beta != 0.0) {
+#pragma unroll
+    for (int r = 0; r < (T3_BN * T3_BM / 8) / T3_NT; r++) {
+      const uint l = tid + r * T3_NT, col = n0 + l / (T3_BM / 8), row = m0 + (l % (T3_BM / 8)) * 8;
+      if (col < N && row < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(C + (size_t)col * ldc + row));
+    }
+  }
   double X[4][3][2], Y[4][3][2], W[4][3][2];
 #pragma unroll
   for (int a = 0; a < 4; a++)
@@ -244,17 +272,12 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
 #pragma unroll
       for (int e = 0; e < 2; e++) X[a][b][e] = Y[a][b][e] = W[a][b][e] = 0.0;
 
-#pragma unroll
-  for (int s = 0; s < T3_STAGES - 1; s++) {
-    if (s < nk) load_stage(s, s);
-    cp_async_commit();
-  }
   for (int kc = 0; kc < nk; kc++) {
     cp_async_wait<T3_STAGES - 2>();
     __syncthreads();
     {
       int nx = kc + T3_STAGES - 1;
-      if (nx < nk) load_stage(nx, nx % T3_STAGES);
+      if (nx < nk) load_stage(m0, n0, nx, nx % T3_STAGES);
       cp_async_commit();
     }
     const cplx *as = As + (kc % T3_STAGES) * T3_A_STAGE + wm * 32 + fr;
@@ -283,32 +306,45 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
     }
   }
   cp_async_wait<0>();
+  __syncthreads();  // every warp is done with the shared-memory ring
+  // start the next tile's first stages now, so they fly while this tile's epilogue runs
+  uint ntile = tile + gridDim.x, nm0 = 0, nn0 = 0;
+  while (ntile < ntiles && !coords(ntile, nm0, nn0)) ntile += gridDim.x;
+  const bool more = ntile < ntiles;
+  if (more) prologue(nm0, nn0);
 #pragma unroll
-  for (int mi = 0; mi < 4; mi++) {
-    const uint row = m0 + wm * 32 + mi * 8 + fr;
-    const bool rok = row < M;
-    cplx old[3][2];
+  for (int mh = 0; mh < 2; mh++) {
+    cplx old[2][3][2];
 #pragma unroll
-    for (int ni = 0; ni < 3; ni++)
+    for (int mi = 0; mi < 2; mi++) {
+      const uint row = m0 + wm * 32 + (mh * 2 + mi) * 8 + fr;
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        uint col = n0 + wn * 24 + ni * 8 + fc * 2 + e;
-        old[ni][e] = make_double2(0.0, 0.0);
-        if (beta != 0.0 && rok && col < N) old[ni][e] = __ldcg(C + (size_t)col * ldc + row);
-      }
+      for (int ni = 0; ni < 3; ni++)
 #pragma unroll
-    for (int ni = 0; ni < 3; ni++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        uint col = n0 + wn * 24 + ni * 8 + fc * 2 + e;
-        if (rok && col < N) {
-          double cr = X[mi][ni][e] - Y[mi][ni][e];
-          double ci = W[mi][ni][e] - X[mi][ni][e] - Y[mi][ni][e];
-          C[(size_t)col * ldc + row] = make_double2(fma(alpha, cr, old[ni][e].x), fma(alpha, ci, old[ni][e].y));
+        for (int e = 0; e < 2; e++) {
+          uint col = n0 + wn * 24 + ni * 8 + fc * 2 + e;
+          old[mi][ni][e] = make_double2(0.0, 0.0);
+          if (beta != 0.0 && row < M && col < N) old[mi][ni][e] = __ldcg(C + (size_t)col * ldc + row);
         }
-      }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++) {
+      const uint row = m0 + wm * 32 + (mh * 2 + mi) * 8 + fr;
+#pragma unroll
+      for (int ni = 0; ni < 3; ni++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          uint col = n0 + wn * 24 + ni * 8 + fc * 2 + e;
+          if (row < M && col < N) {
+            double cr = X[mh * 2 + mi][ni][e] - Y[mh * 2 + mi][ni][e];
+            double ci = W[mh * 2 + mi][ni][e] - X[mh * 2 + mi][ni][e] - Y[mh * 2 + mi][ni][e];
+            C[(size_t)col * ldc + row] = make_double2(fma(alpha, cr, old[mi][ni][e].x), fma(alpha, ci, old[mi][ni][e].y));
+          }
+        }
+    }
   }
-  __syncthreads();  // shared-memory ring is reused by the next tile
+  if (!more) break;
+  tile = ntile; m0 = nm0; n0 = nn0;
   }  // tile loop
 }
 }  // namespace
@@ -361,7 +397,8 @@ int g_zgemm_variant = 1;  // 0: 128x64 tile, 1 CTA/SM;  1: 64x64 tile, 2 CTAs/SM
 
 template <class CF, int MINB>
 static int launch(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
-                  const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc) {
+                  const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, uint nbatch = 1,
+                  const ZBatch &bt = ZBatch()) {
   static bool attr_set[64] = {false};
   int dev = 0;
   CNLD_CK(cudaGetDevice(&dev));
@@ -370,8 +407,8 @@ static int launch(cudaStream_t st, uint M, uint N, uint K, double alpha, const c
                                  CF::SMEM_BYTES));
     attr_set[dev & 63] = true;
   }
-  dim3 grid((M + CF::BM - 1) / CF::BM, (N + CF::BN - 1) / CF::BN);
-  zgemm_kernel<CF, MINB><<<grid, CF::NT, CF::SMEM_BYTES, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  dim3 grid((M + CF::BM - 1) / CF::BM, (N + CF::BN - 1) / CF::BN, nbatch);
+  zgemm_kernel<CF, MINB><<<grid, CF::NT, CF::SMEM_BYTES, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bt);
   CNLD_CK_LAUNCH();
   return 0;
 }
@@ -381,6 +418,12 @@ int zgemm(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, 
   if (M == 0 || N == 0) return 0;
   if (g_zgemm_variant == 0) return launch<Cfg<4, 2, 4>, 1>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
   return launch<Cfg<2, 2, 4>, 2>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+
+int zgemm_batched(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
+                  const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, uint nbatch, const ZBatch &bt) {
+  if (M == 0 || N == 0 || nbatch == 0) return 0;
+  return launch<Cfg<2, 2, 4>, 2>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, nbatch, bt);
 }
 
 }  // namespace cnld
