@@ -30,6 +30,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, 'cnl-dyna_b200'))
 
+# dram bytes (read + write) of the first trailing update, ncu --set full: {general: ..., symmetric: ...}
+TRAFFIC_T2 = {True: 8.28e9, False: None}
 METRIC = 'frequencies solved/s (Z assemble+factor+solve), 4x4 CMUT array'
 UNIT = 'frequencies/s'
 CONFIGS = {  # name: (nelem, refn, nfreq of the full sweep, fmin, fmax)
@@ -138,8 +140,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default='c3', choices=sorted(CONFIGS))
-    ap.add_argument('--freqs-per-step', type=int, default=4)
-    ap.add_argument('--streams', type=int, default=2)
+    ap.add_argument('--freqs-per-step', type=int, default=6)
+    ap.add_argument('--streams', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--general', action='store_true', help='general unpivoted LU of G instead of the symmetric-part path')
     ap.add_argument('--lu-outer', type=int, default=0, help='debug: outer LU block (multiple of 64)')
@@ -177,7 +179,6 @@ def main():
     if args.lu_reserve >= 0:
         _lib.lib().cnld_b200_set_lu_reserve(args.lu_reserve)
     sweep = FrequencySweep(setup, device=local, nstreams=args.streams, symmetric=not args.general)
-    sweep.ctx.set_profile(True)
     t_setup = time.perf_counter() - t_setup
     N, P, T = setup.nnodes, setup.npatch, len(setup.triangles)
     nfb = args.freqs_per_step
@@ -200,15 +201,13 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count()
-    kflops = ksec = klaunch = 0.0
+    fl0 = _lib.dmma_flop_count()
     stage = np.zeros(3)
     dev_s = 0.0
     barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
         sweep.run_device(batch(args.warmup + s))
-        ks = sweep.ctx.kernel_stats()
-        kflops, ksec, klaunch = kflops + ks['flops'], ksec + ks['seconds'], klaunch + ks['launches']
         st = sweep.ctx.stage_times()
         stage += [st['assemble'], st['factor'], st['solve']]
         dev_s += st['device_seconds']       # CUDA events joined across the library's streams
@@ -216,6 +215,8 @@ def main():
     wall = time.perf_counter() - t0
     dt = dev_s
     launches = _lib.launch_count() - l0
+    step_flops = _lib.dmma_flop_count() - fl0      # executed DMMA flops of this rank's timed steps
+    step_tflops = step_flops / dev_s / 1e12
     clocks = sampler.finish() if rank == 0 else None
     tt = torch.tensor([dt], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -244,6 +245,21 @@ def main():
     assert np.isfinite(xp).all() and np.abs(xp).max() > 0
 
     sym_stats = sweep.ctx.symmetric_stats()
+    trans = sweep.ctx.translation_info()
+
+    # ---- roofline leg: the dominant kernel's launch durations, CUDA events on its own stream ----
+    # A dedicated single-stream pass of the same workload: with two frequencies in flight the other
+    # slot's kernels share the SMs with a trailing update and its event-bracketed duration would
+    # measure the sharing, not the kernel.
+    kflops = ksec = klaunch = 0.0
+    if rank == 0:
+        sweep.ctx.set_streams(1)
+        sweep.ctx.set_profile(True)
+        sweep.run_device(batch(0)[:1])
+        for s in range(2):
+            sweep.run_device(batch(1 + s)[:1])
+            ks = sweep.ctx.kernel_stats()
+            kflops, ksec, klaunch = kflops + ks['flops'], ksec + ks['seconds'], klaunch + ks['launches']
     line = None
     if rank == 0:
         ach = kflops / ksec / 1e12 if ksec > 0 else None
@@ -265,13 +281,20 @@ def main():
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                          'frac': (ach / fp64_peak) if ach else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of the first trailing update
-                         # (13776 x 13776 x 512) from profiles/r1_ncu_full_summary.txt; algorithmic
-                         # bytes of that launch: C read + write 6.07e9 + panels 0.45e9
-                         'traffic': 8.28e9 if args.config == 'c3' else None,
-                         'kernel': 'zgemm3m_kernel (DMMA.8x8x4 rank-512 trailing updates of the LU; 3M complex '
-                                   'product = 6 m n k executed real flops per launch, i.e. 8 m n k conventional '
-                                   'complex-GEMM flops at 4/3 of this rate)',
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the first trailing update from
+                         # profiles/r1_ncu_full_summary.txt.  General: 13776 x 13776 x 512, algorithmic bytes
+                         # C read + write 6.07e9 + panels 0.45e9.  Symmetric: the same update restricted to the
+                         # tiles on or below the diagonal, algorithmic C read + write 3.05e9 + panels 0.45e9.
+                         'traffic': (TRAFFIC_T2[bool(args.general)] if args.config == 'c3' else None),
+                         'kernel': 'zgemm3m_kernel (DMMA.8x8x4 rank-512 trailing updates of the LU'
+                                   + ('' if args.general else ', tiles on or below the diagonal only')
+                                   + '; 3M complex product = 6 m n k executed real flops per launch, i.e. 8 m n k '
+                                   'conventional complex-GEMM flops at 4/3 of this rate); durations from a dedicated '
+                                   'single-stream pass after the timed region',
+                         # every ZGEMM of the timed 2-stream steps (factor + solves), executed flops / device time:
+                         # how busy the FP64 units are over the whole step, not just inside the dominant kernel
+                         'whole_step_dmma_tflops': step_tflops,
+                         'whole_step_frac': step_tflops / fp64_peak,
                          'achieved_conventional_8mnk': (ach * 4.0 / 3.0) if ach else None,
                          'launches_timed': int(klaunch),
                          'peak_source': 'FP64 FMA-pipe peak measured live with cnld_b200_bench_dfma '

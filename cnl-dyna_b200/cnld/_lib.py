@@ -40,6 +40,7 @@ def lib():
         L.cnld_b200_last_error.restype = C.c_char_p
         L.cnld_b200_version.restype = C.c_char_p
         L.cnld_b200_launch_count.restype = C.c_ulonglong
+        L.cnld_b200_dmma_flop_count.restype = C.c_ulonglong
         L.cnld_b200_create.restype = vp
         L.cnld_b200_create.argtypes = [C.c_int, u32, u32, vp, vp, u32, u32]
         L.cnld_b200_destroy.argtypes = [vp]
@@ -370,6 +371,10 @@ def bench_zgemm(m, n, k, reps=5, device=0):
     out = C.c_double(0)
     check(lib().cnld_b200_bench_zgemm(device, m, n, k, reps, C.byref(out)))
     return out.value
+
+
+def dmma_flop_count():
+    return int(lib().cnld_b200_dmma_flop_count())
 
 
 def bench_dfma(reps=5, device=0):

@@ -79,7 +79,7 @@ class FrequencySweep:
     with the general elimination.  symmetric=False is the reference's elimination order
     (compressed_formats.py:247-252, lrdecomp_amatrix)."""
 
-    def __init__(self, setup, device=0, nstreams=2, symmetric=True, refine_steps=1):
+    def __init__(self, setup, device=0, nstreams=3, symmetric=True, refine_steps=1):
         self.setup = setup
         self.ctx = _lib.Context(setup.vertices, setup.triangles, q_reg=setup.q_reg, q_sing=setup.q_sing,
                                 device=device)
@@ -140,7 +140,7 @@ def broadcast_setup(setup, rank, device=None):
     return SweepSetup.unpack(out)
 
 
-def run_distributed(setup_or_none, freqs, rank, world, device=0, torch_device=None, nstreams=2,
+def run_distributed(setup_or_none, freqs, rank, world, device=0, torch_device=None, nstreams=3,
                     solver=None, symmetric=True):
     """Block-distributed sweep: returns (x_patch[nf, P, P] on rank 0 else None, local seconds).
     `solver(setup, freqs) -> x_patch[nf_local, P, P]` defaults to the GPU sweep; tests inject a

@@ -11,6 +11,7 @@
 
 namespace cnld {
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<unsigned long long> g_dmma_flops{0};
 static thread_local std::string t_err;
 static std::string g_err;
 static std::mutex g_err_mu;
@@ -378,6 +379,7 @@ int cnld_b200_device_count(void) {
   return n;
 }
 unsigned long long cnld_b200_launch_count(void) { return g_launches.load(); }
+unsigned long long cnld_b200_dmma_flop_count(void) { return g_dmma_flops.load(); }
 
 cnld_ctx *cnld_b200_create(int device, cnld_uint nv, cnld_uint nt, const double *x, const cnld_uint *t,
                            cnld_uint q_reg, cnld_uint q_sing) {

@@ -19,6 +19,8 @@ namespace cnld {
 void set_error(const char *fmt, ...);
 extern std::atomic<unsigned long long> g_launches;
 inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+// executed real flops of every ZGEMM launched so far (4M: 8 m n k, 3M: 6 m n k, skipped tiles excluded)
+extern std::atomic<unsigned long long> g_dmma_flops;
 
 #define CNLD_CK(call)                                                                     \
   do {                                                                                    \

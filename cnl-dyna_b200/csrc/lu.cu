@@ -27,76 +27,78 @@ template <bool FACTOR, bool SYM = false>
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 k_diag(cplx *a0, size_t lda, uint n, uint b0, cplx *linv0, cplx *uinv0, uint *info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ cplx P[NB];   // reciprocal pivots
   cplx *S = reinterpret_cast<cplx *>(smem_raw);
   cplx *X = S + NB * LD;
   const int tid = threadIdx.x;
+  const uint r = tid & (NB - 1), g = tid / NB;   // thread = (row r, column group g of NG)
+  constexpr uint NG = DIAG_THREADS / NB;
   const uint b = b0 + blockIdx.x, base = b * NB;
   const uint nbk = (n - base < (uint)NB) ? n - base : NB;
   cplx *a = a0 + (size_t)base * lda + base;
   cplx *linv = linv0 + (size_t)b * NB * NB, *uinv = uinv0 + (size_t)b * NB * NB;
-  for (uint idx = tid; idx < nbk * nbk; idx += DIAG_THREADS) {
-    uint i = idx % nbk, j = idx / nbk;
-    S[j * LD + i] = (SYM && i < j) ? a[(size_t)i * lda + j] : a[(size_t)j * lda + i];
-  }
+  for (uint j = g; j < nbk; j += NG)
+    if (r < nbk) S[j * LD + r] = (SYM && r < j) ? a[(size_t)r * lda + j] : a[(size_t)j * lda + r];
   __syncthreads();
-  for (uint k = 0; FACTOR && k < nbk; k++) {
-    cplx piv = S[k * LD + k];
+  // One barrier per elimination step: column k of L stays unscaled in S until the end (every thread
+  // multiplies by the reciprocal pivot itself -- the same two roundings as scaling first), and the
+  // thread that produces the next pivot also publishes its reciprocal.
+  auto publish = [&](uint k, cplx piv) {
     double mag = piv.x * piv.x + piv.y * piv.y;
-    if (tid == 0 && !(mag > 0.0 && mag < 1.79e308)) atomicCAS(info, 0u, base + k + 1);
-    cplx pinv = cinv(piv);
-    for (uint i = k + 1 + tid; i < nbk; i += DIAG_THREADS) S[k * LD + i] = cmul(S[k * LD + i], pinv);
+    if (FACTOR && !(mag > 0.0 && mag < 1.79e308)) atomicCAS(info, 0u, base + k + 1);
+    P[k] = cinv(piv);
+  };
+  if (FACTOR) {
+    if (tid == 0) publish(0, S[0]);
     __syncthreads();
-    uint m = nbk - k - 1;
-    for (uint idx = tid; idx < m * m; idx += DIAG_THREADS) {
-      uint i = k + 1 + idx % m, j = k + 1 + idx / m;
-      cfms(S[j * LD + i], S[k * LD + i], S[j * LD + k]);
+    for (uint k = 0; k + 1 < nbk; k++) {
+      if (r > k && r < nbk) {
+        const cplx l = cmul(S[k * LD + r], P[k]);
+        for (uint j = k + 1 + g; j < nbk; j += NG) {
+          cplx v = S[j * LD + r];
+          cfms(v, l, S[j * LD + k]);
+          S[j * LD + r] = v;
+          if (r == k + 1 && j == k + 1) publish(k + 1, v);
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
+    for (uint j = g; j < nbk; j += NG)   // scale L's columns, write the block back
+      if (r < nbk) {
+        cplx v = S[j * LD + r];
+        if (r > j) { v = cmul(v, P[j]); S[j * LD + r] = v; }
+        a[(size_t)j * lda + r] = v;
+      }
+  } else {
+    if (tid < (int)nbk) publish(tid, S[tid * LD + tid]);
   }
-  if (FACTOR)
-    for (uint idx = tid; idx < nbk * nbk; idx += DIAG_THREADS) {
-      uint i = idx % nbk, j = idx / nbk;
-      a[(size_t)j * lda + i] = S[j * LD + i];
-    }
   // X = inv(L), L unit lower: forward elimination on the identity
-  for (uint idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
-    uint i = idx % NB, j = idx / NB;
-    X[j * LD + i] = make_double2(i == j ? 1.0 : 0.0, 0.0);
-  }
+  for (uint j = g; j < NB; j += NG) X[j * LD + r] = make_double2(r == j ? 1.0 : 0.0, 0.0);
   __syncthreads();
   for (uint k = 0; k + 1 < nbk; k++) {
-    uint m = nbk - k - 1, w = k + 1;
-    for (uint idx = tid; idx < m * w; idx += DIAG_THREADS) {
-      uint i = k + 1 + idx % m, c = idx / m;
-      cfms(X[c * LD + i], S[k * LD + i], X[c * LD + k]);
+    if (r > k && r < nbk) {
+      const cplx l = S[k * LD + r];
+      for (uint c = g; c <= k; c += NG) cfms(X[c * LD + r], l, X[c * LD + k]);
     }
     __syncthreads();
   }
-  for (uint idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
-    uint i = idx % NB, j = idx / NB;
-    linv[j * NB + i] = X[j * LD + i];
-  }
+  for (uint j = g; j < NB; j += NG) linv[j * NB + r] = X[j * LD + r];
   __syncthreads();
-  // X = inv(R), R upper: backward elimination on the identity
-  for (uint idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
-    uint i = idx % NB, j = idx / NB;
-    X[j * LD + i] = make_double2(i == j ? 1.0 : 0.0, 0.0);
-  }
+  // X = inv(R), R upper: backward elimination on the identity; row kk is scaled by the reciprocal
+  // pivot on the fly and in place only at the end (one barrier per step again)
+  for (uint j = g; j < NB; j += NG) X[j * LD + r] = make_double2(r == j ? 1.0 : 0.0, 0.0);
   __syncthreads();
-  for (uint kk = nbk; kk-- > 0;) {
-    cplx pinv = cinv(S[kk * LD + kk]);
-    for (uint c = kk + tid; c < nbk; c += DIAG_THREADS) X[c * LD + kk] = cmul(X[c * LD + kk], pinv);
-    __syncthreads();
-    uint w = nbk - kk;  // columns kk..nbk-1
-    for (uint idx = tid; idx < kk * w; idx += DIAG_THREADS) {
-      uint i = idx % kk, c = kk + idx / kk;
-      cfms(X[c * LD + i], S[kk * LD + i], X[c * LD + kk]);
+  for (uint kk = nbk; kk-- > 1;) {
+    if (r < kk) {
+      const cplx u = S[kk * LD + r], pk = P[kk];
+      for (uint c = kk + g; c < nbk; c += NG) cfms(X[c * LD + r], u, cmul(X[c * LD + kk], pk));
     }
     __syncthreads();
   }
-  for (uint idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
-    uint i = idx % NB, j = idx / NB;
-    uinv[j * NB + i] = X[j * LD + i];
+  for (uint j = g; j < NB; j += NG) {
+    cplx v = X[j * LD + r];
+    if (r < nbk && j < nbk) v = cmul(v, P[r]);
+    uinv[j * NB + r] = v;
   }
 }
 }  // namespace

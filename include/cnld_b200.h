@@ -47,6 +47,9 @@ const char *cnld_b200_version(void);
 int cnld_b200_device_count(void);
 /* number of kernel launches issued by this library since load (bench: gpu_launches) */
 unsigned long long cnld_b200_launch_count(void);
+/* Real FP64 flops executed by every ZGEMM launched so far in this process (host-side count:
+ * 8 m n k for the 4M kernel, 6 m n k for the 3M kernel, tiles skipped by lower-only updates excluded). */
+unsigned long long cnld_b200_dmma_flop_count(void);
 
 /* ---- context: mesh + quadrature (frequency independent) ---------------
  * Replaces: Mesh.from_abstract -> Surface3d + prepare_surface3d
