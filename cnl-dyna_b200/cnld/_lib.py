@@ -373,6 +373,23 @@ def bench_zgemm(m, n, k, reps=5, device=0):
     return out.value
 
 
+def translation_plan(vertices, triangles, allow=True):
+    """Host-only: (info dict, work[nw, 4], copy[nc, 5]) of the symmetric-path assembly plan."""
+    x = np.ascontiguousarray(vertices, dtype=np.float64)
+    t = np.ascontiguousarray(triangles, dtype=np.uint32)
+    counts = np.zeros(6, dtype=np.uint32)
+    f = lib().cnld_b200_translation_plan
+    f.argtypes = [C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint,
+                  C.c_void_p, C.c_uint]
+    check(f(len(x), len(t), ptr(x), ptr(t), int(allow), ptr(counts), None, 0, None, 0))
+    work = np.zeros((int(counts[3]), 4), dtype=np.uint32)
+    copy = np.zeros((int(counts[4]), 5), dtype=np.uint32)
+    check(f(len(x), len(t), ptr(x), ptr(t), int(allow), ptr(counts), ptr(work), len(work), ptr(copy), len(copy)))
+    info = dict(periodic=bool(counts[0]), components=int(counts[1]), offset_classes=int(counts[2]),
+                vertices_per_component=int(counts[5]))
+    return info, work, copy
+
+
 def dmma_flop_count():
     return int(lib().cnld_b200_dmma_flop_count())
 

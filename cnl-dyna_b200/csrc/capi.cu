@@ -602,6 +602,23 @@ int cnld_b200_symmetric_stats(const cnld_ctx *c, unsigned *mbk_asym_nnz, unsigne
   if (max_ratio) *max_ratio = c->sym_max_ratio;
   return c->symmetric;
 }
+// Host-only: the work / copy lists the symmetric-path assembly would use for this mesh (no device needed).
+int cnld_b200_translation_plan(cnld_uint nv, cnld_uint nt, const double *x, const cnld_uint *t, int allow,
+                               cnld_uint *counts, cnld_uint *work, cnld_uint work_cap, cnld_uint *copy,
+                               cnld_uint copy_cap) {
+  for (size_t i = 0; i < 3 * (size_t)nt; i++)
+    if (t[i] >= nv) { set_error("triangle vertex index out of range"); return -1; }
+  TranslationPlan P;
+  build_translation_plan(nv, nt, x, t, 128, 64, allow != 0, P);
+  if (counts) {
+    counts[0] = P.periodic ? 1 : 0; counts[1] = P.ncomp; counts[2] = P.nclass;
+    counts[3] = (cnld_uint)P.work.size(); counts[4] = (cnld_uint)P.copy.size(); counts[5] = P.nvc;
+  }
+  if (work) for (size_t i = 0; i < P.work.size() && i < work_cap; i++) memcpy(work + 4 * i, &P.work[i], 16);
+  if (copy) for (size_t i = 0; i < P.copy.size() && i < copy_cap; i++) memcpy(copy + 5 * i, &P.copy[i], 20);
+  return 0;
+}
+
 int cnld_b200_set_translation_classes(cnld_ctx *c, int on) {
   if (!c) { set_error("null context"); return -1; }
   c->bem.use_periodic = on ? 1 : 0;

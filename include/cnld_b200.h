@@ -156,6 +156,13 @@ int cnld_b200_set_symmetric_tol(cnld_ctx *ctx, double tol);
  * whether the classes are in use, the number of components and of integrated off-diagonal blocks. */
 int cnld_b200_set_translation_classes(cnld_ctx *ctx, int on);
 int cnld_b200_translation_info(const cnld_ctx *ctx, unsigned *ncomp, unsigned *nclass);
+/* Host-only view of the plan (tests): counts = {periodic, components, offset classes, work items,
+ * copy items, vertices per component}; work items are {t_begin, t_end, s_begin, s_end} (row triangles
+ * x column-triangle chunk, pairs s < t are integrated), copy items {dst_r0, dst_c0, src_r0, src_c0,
+ * transposed} (vertex offsets of blocks of `vertices per component` rows and columns). */
+int cnld_b200_translation_plan(cnld_uint nv, cnld_uint nt, const double *x, const cnld_uint *t, int allow,
+                               cnld_uint *counts, cnld_uint *work, cnld_uint work_cap, cnld_uint *copy,
+                               cnld_uint copy_cap);
 int cnld_b200_symmetric_stats(const cnld_ctx *ctx, unsigned *mbk_asym_nnz, unsigned *redone, double *max_ratio);
 
 /* Dominant-kernel timing for the roofline: when profiling is on, every trailing-update

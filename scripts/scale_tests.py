@@ -93,7 +93,7 @@ def hsweep(nelem, refn, nfreq=1, batch=32, eps=1e-2, tol=1e-6):
     ctx.set_mbk(setup.K, setup.M, setup.B)
     ctx.set_loads(setup.F, setup.AVG, setup.on_boundary)
     H = _lib.HMatrix(ctx, clf=16, eta=0.8, strict=True, kmax=64)
-    freqs = np.linspace(2e6, 20e6, nfreq)
+    freqs = np.linspace(2e6, 20e6, nfreq) if nfreq > 1 else np.array([5e6])
     xp, _, it, t = H.sweep(freqs, eps_aca=eps, tol=tol, restart=50, maxiter=300, batch=batch, want_nodes=False)
     out = dict(n=setup.nnodes, P=setup.npatch, host_setup_seconds=t_setup, seconds_per_frequency=t.tolist(),
                iters_mean=float(it.mean()), iters_max=int(it.max()), finite=bool(np.isfinite(xp).all()),
@@ -107,6 +107,8 @@ if __name__ == '__main__' and any(a.startswith('sweep') for a in sys.argv[1:]):
     r = {}
     if 'sweep8' in sys.argv:
         r['hsweep_8x8_refn15'] = hsweep((8, 8), 15, nfreq=2, batch=64)
+    if 'sweep16' in sys.argv:      # configs[3]: 16x16 array, N = 194 816, P = 2 304 right-hand sides
+        r['hsweep_16x16_refn19'] = hsweep((16, 16), 19, nfreq=1, batch=96)
     if 'sweep4' in sys.argv:
         r['hsweep_4x4_refn21'] = hsweep((4, 4), 21, nfreq=2, batch=48)
     print(json.dumps(r, indent=1, default=float))

@@ -158,3 +158,48 @@ def test_database_roundtrip(tmp_path):
     database.append_patch_to_patch_freq_resp(f, frequency=repeat(5e6), wavenumber=repeat(1.0), source_patch=repeat(0),
                                              dest_patch=np.arange(P), displacement_real=np.ones(P),
                                              displacement_imag=np.zeros(P), time_solve=repeat(0.1))
+
+
+def test_translation_plan_covers_every_pair_once():
+    """Host logic of the symmetric-path assembly (csrc/periodic.cpp): the work list plus the block
+    copies must account for every lower-triangle membrane block exactly once, offsets with the same
+    class must really be equal, and a mesh that is not exact translated copies takes the full list."""
+    from cnld import _lib, arrays, mesh
+    am = mesh.Mesh.from_abstract(arrays.matrix_array(nelem=(4, 3)), 3)
+    V, T = np.array(am.vertices), np.array(am.triangles)
+    nt = len(T)
+    info, work, copy = _lib.translation_plan(V, T)
+    assert info['periodic'] and info['components'] == 12
+    # 4 x 3 lattice: offsets dx in -3..3, dy in -2..2, up to sign, minus zero -> (7*5 - 1) / 2 = 17 classes
+    assert info['offset_classes'] == 17
+    nvc, ntc = info['vertices_per_component'], nt // 12
+    assert nvc * 12 == len(V)
+    # integrated pairs: count (t, s) with s < t covered by the work items, per membrane block
+    cover = np.zeros((12, 12), dtype=np.int64)
+    for tb, te, sb, se in work.astype(np.int64):
+        assert tb // ntc == (te - 1) // ntc and sb // ntc == (se - 1) // ntc      # an item never straddles blocks
+        a, b = tb // ntc, sb // ntc
+        t = np.arange(tb, te)[:, None]
+        s = np.arange(sb, se)[None, :]
+        cover[a, b] += int((s < t).sum())
+    integrated = {(a, b) for a in range(12) for b in range(12) if cover[a, b]}
+    assert (0, 0) in integrated and cover[0, 0] == ntc * (ntc - 1) // 2
+    for (a, b) in integrated - {(0, 0)}:
+        assert a > b and cover[a, b] == ntc * ntc
+    assert len(integrated) == 1 + 17
+    # copies: every other lower block exactly once, from an integrated block with the same (or opposite) offset
+    org = V[::nvc][:12]                                  # first vertex of each membrane
+    seen = set(integrated)
+    for dr, dc, sr, sc, tr in copy.astype(np.int64):
+        a, b, ra, rb = dr // nvc, dc // nvc, sr // nvc, sc // nvc
+        assert (ra, rb) in integrated and (a, b) not in seen and a >= b
+        seen.add((a, b))
+        d, e = org[a] - org[b], org[ra] - org[rb]
+        assert np.allclose(d, -e if tr else e, rtol=0, atol=1e-15)
+    assert seen == {(a, b) for a in range(12) for b in range(a + 1)}
+    # without detection, or with one vertex nudged: one self rectangle over everything
+    for VV, allow in ((V, False), (V + 1e-9 * (np.arange(len(V)) == 7)[:, None], True)):
+        info2, work2, copy2 = _lib.translation_plan(VV, T, allow=allow)
+        assert not info2['periodic'] and len(copy2) == 0
+        tot = sum(int((np.arange(sb, se)[None, :] < np.arange(tb, te)[:, None]).sum()) for tb, te, sb, se in work2.astype(np.int64))
+        assert tot == nt * (nt - 1) // 2
