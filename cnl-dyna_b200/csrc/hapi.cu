@@ -146,6 +146,9 @@ k_epilogue_batch(uint nv, uint P, uint s0, cplx *X, const uint8_t *__restrict__ 
 struct Blocks {  // diagonal blocks of the FEM operator and their types (identical membranes share one)
   std::vector<uint> r0, sz, type;
   std::vector<uint> rep;  // representative block of each type
+  bool exact = true;      // every entry of a block's rows lies inside the block (FEM operator == its block diagonal)
+  struct Run { uint first, count; };   // consecutive blocks of one type: one batched ZGEMM
+  std::vector<Run> runs;
 };
 
 // block-diagonal structure from the CSR pattern; blocks with identical K, M, B get one type
@@ -176,6 +179,15 @@ void detect_blocks(const cnld_ctx *c, Blocks &B) {
     if (t == B.rep.size()) B.rep.push_back(b);
     B.type.push_back(t);
   }
+  for (uint b = 0; b < B.r0.size() && B.exact; b++)
+    for (int64_t p = c->h_indptr[B.r0[b]]; p < c->h_indptr[B.r0[b] + B.sz[b]]; p++)
+      if (c->h_indices[p] < B.r0[b] || c->h_indices[p] >= B.r0[b] + B.sz[b]) { B.exact = false; break; }
+  for (uint b = 0; b < B.r0.size();) {   // blocks partition [0, n) in order, so same-type neighbours are contiguous
+    uint e = b + 1;
+    while (e < B.r0.size() && B.type[e] == B.type[b]) e++;
+    B.runs.push_back({b, e - b});
+    b = e;
+  }
 }
 
 struct Gmres {
@@ -186,21 +198,35 @@ struct Gmres {
   double omega, coef;
   Blocks blk;
   std::vector<cplx *> d_inv;  // per block type: dense inverse
+  std::vector<cplx *> d_blk;  // per block type: the dense block K - w^2 M - j w B itself
   cplx *Vb = nullptr, *W = nullptr, *T = nullptr, *X = nullptr, *Bp = nullptr, *Hd = nullptr, *yd = nullptr;
   double *sd = nullptr;
 
+  // y|block = D_type x|block for every diagonal block: one batched ZGEMM per run of same-type blocks
+  int apply_blockdiag(const std::vector<cplx *> &mats, const cplx *x, cplx *y, uint nr) {
+    for (const Blocks::Run &R : blk.runs) {
+      const uint b = R.first, sz = blk.sz[b];
+      ZBatch bt;
+      bt.per = R.count;
+      bt.sBj = sz; bt.sCj = sz;   // operand A (the block) is shared by the run
+      if (zgemm_batched(st, sz, nr, sz, 1.0, mats[blk.type[b]], sz, x + blk.r0[b], n, 0.0, y + blk.r0[b], n, R.count, bt))
+        return -1;
+    }
+    return 0;
+  }
   int apply_G(const cplx *x, cplx *y, uint nr) {  // y = MBK x + coef Z x
-    k_spmv_mbk<<<(unsigned)(((size_t)n * nr * 32 + 255) / 256), 256, 0, st>>>(n, nr, c->d_indptr, c->d_indices, c->d_K,
-                                                                            c->d_M, c->d_B, omega, x, y);
-    CNLD_CK_LAUNCH();
+    if (blk.exact) {   // the FEM operator is its block diagonal: dense blocks on the tensor pipe
+      if (apply_blockdiag(d_blk, x, y, nr)) return -1;
+    } else {
+      k_spmv_mbk<<<(unsigned)(((size_t)n * nr * 32 + 255) / 256), 256, 0, st>>>(n, nr, c->d_indptr, c->d_indices, c->d_K,
+                                                                              c->d_M, c->d_B, omega, x, y);
+      CNLD_CK_LAUNCH();
+    }
     if (coef != 0.0 && hmat_matvec(st, *H, make_double2(coef, 0.0), x, y, nr)) return -1;
     return 0;
   }
   int apply_P(const cplx *x, cplx *y, uint nr) {  // y = blockdiag(MBK)^-1 x
-    for (size_t b = 0; b < blk.r0.size(); b++)
-      if (zgemm(st, blk.sz[b], nr, blk.sz[b], 1.0, d_inv[blk.type[b]], blk.sz[b], x + blk.r0[b], n, 0.0, y + blk.r0[b], n))
-        return -1;
-    return 0;
+    return apply_blockdiag(d_inv, x, y, nr);
   }
   int setup_precond() {
     for (uint t = 0; t < blk.rep.size(); t++) {
@@ -216,10 +242,17 @@ struct Gmres {
       CNLD_CK_LAUNCH();
       LuWork w;
       if (lu_work_alloc(w, sz) || lu_factor(st, w, D, sz) || lu_solve(st, w, D, sz, I, sz, sz)) return -1;
+      // keep an unfactored copy of the block for apply_G
+      cplx *Dc = nullptr;
+      CNLD_CK(cudaMalloc(&Dc, sizeof(cplx) * (size_t)sz * sz));
+      CNLD_CK(cudaMemsetAsync(Dc, 0, sizeof(cplx) * (size_t)sz * sz, st));
+      k_block_dense<<<sz, 128, 0, st>>>(sz, blk.r0[b], c->d_indptr, c->d_indices, c->d_K, c->d_M, c->d_B, omega, Dc);
+      CNLD_CK_LAUNCH();
       CNLD_CK(cudaStreamSynchronize(st));
       lu_work_free(w);
       cudaFree(D);
       if (t < d_inv.size()) { cudaFree(d_inv[t]); d_inv[t] = I; } else d_inv.push_back(I);
+      if (t < d_blk.size()) { cudaFree(d_blk[t]); d_blk[t] = Dc; } else d_blk.push_back(Dc);
     }
     return 0;
   }
@@ -239,6 +272,8 @@ struct Gmres {
     cudaFree(Vb); cudaFree(W); cudaFree(T); cudaFree(X); cudaFree(Bp); cudaFree(Hd); cudaFree(yd); cudaFree(sd);
     for (auto p : d_inv) cudaFree(p);
     d_inv.clear();
+    for (auto p : d_blk) cudaFree(p);
+    d_blk.clear();
   }
 
   // Solve P G X = P B for nr right-hand sides held in B (device, [r][n]); result in X.

@@ -31,6 +31,23 @@ struct HMat {
   uint *d_err = nullptr;
   cplx *d_xp = nullptr, *d_yp = nullptr;  // permuted work vectors
   uint vec_cap = 0;
+  // batched matvec (nrhs >= 4): bands of 16 rows in cluster order, each with the list of leaves that
+  // intersect it; low-rank leaves first contract t = V^T x into a scratch (k x nrhs per leaf)
+  uint nband = 0, nmvfar = 0;
+  uint *d_band_ptr = nullptr, *d_mvfar = nullptr;   // band -> dense rounds; low-rank leaf ids
+  // dense round = up to 16 columns of a dense leaf that intersects the band
+  struct DRound { unsigned long long a_off; uint r0, m, x_off, cnt; uint pad[2]; };
+  DRound *d_dround = nullptr;
+  // band -> packed (low-rank leaf, rank index) items, rebuilt after every assembly (ranks change)
+  struct FarItem { unsigned long long u_off, t_idx; uint r0, m; };   // U column at pool[u_off + row - r0]; t row index
+  uint *d_bfar_ptr = nullptr;
+  FarItem *d_bfar = nullptr;
+  size_t bfar_cap = 0;
+  unsigned long long *d_toff = nullptr;   // per leaf: offset (in rank indices) into the scratch
+  unsigned long long ksum = 0;
+  cplx *d_T = nullptr;
+  size_t T_cap = 0;
+  bool mv_ready = false;
 };
 
 struct LeafRange { uint r0, m, c0, n; bool admissible; };
@@ -45,6 +62,8 @@ int hmat_assemble(cudaStream_t st, HMat &H, double kr, double ki, double accur);
 int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y, uint nrhs);
 int hmat_expand(cudaStream_t st, HMat &H, cplx *d_Z, size_t ld);
 int hmat_fetch_leaves(HMat &H);
+// (re)build the band lists and rank offsets of the batched matvec from H.leaf (after the ranks changed)
+int hmat_prepare_batched(HMat &H, bool fetch);
 int nearfield_block(cudaStream_t st, const BemDev &bem, const uint *htri, const uint *ridx, uint rows,
                     const uint *cidx, uint cols, double kr, double ki, cplx *d_out);
 

@@ -336,6 +336,191 @@ k_hmv_leaf(const HLeafDev *__restrict__ leaves, uint ntot, const cplx *__restric
   }
 }
 
+// ---- batched matvec (several right-hand sides) ----------------------------------------------------
+// With nrhs vectors a leaf is a small GEMM.  Two passes, no atomics:
+//   1. every low-rank leaf:  t = V^T x|cols   (k x nrhs, into a scratch)
+//   2. every band of 16 rows (cluster order): y|band = sum over the leaves that intersect the band of
+//      A|band x|cols (dense) or U|band t (low rank); the band's CTA owns its rows of y.
+// A band's work is a list of rounds of up to 16 contraction indices: first the dense leaves that
+// intersect it (16 columns per round, static), then its (low-rank leaf, rank index) items 16 at a
+// time (rebuilt after every assembly because the ranks change).  Per round the operands are gathered
+// into shared memory with cp.async, software-pipelined (round c is contracted while round c+1 is in
+// flight and the descriptors of round c+2 are read), and contracted on the FP64 tensor pipe: the
+// band is a 16 x K x (16 TC) complex GEMM, 3M product (X = ArBr, Y = AiBi, W = (Ar+Ai)(Br+Bi)) on
+// DMMA.8x8x4 -- a tenth of the instructions of the DFMA formulation, which was issue/latency bound
+// (ncu: FP64 pipe 41 % active, long-scoreboard stalls).
+constexpr int BAND = 16, BT_THREADS = 64, AS_LDB = BAND + 2;
+
+__device__ __forceinline__ void hm_cp_async16(void *smem, const void *gmem, bool valid) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = valid ? 16 : 0;   // src-size 0: zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void hm_dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// CTA = 2 warps; warp w owns the right-hand sides [8 TC w, 8 TC (w+1)) of the pass (TC n-tiles of 8).
+// TMODE = false: CTA = band of 16 rows of y.   TMODE = true: CTA = low-rank leaf, rows = rank indices,
+// t = V^T x|cols written to the scratch ([rank index][rhs]); the rounds are 16 columns of the leaf.
+template <int TC, bool TMODE>
+__global__ void __launch_bounds__(BT_THREADS)
+k_hmv_gemm(const uint *__restrict__ band_ptr, const HMat::DRound *__restrict__ dround, const uint *__restrict__ bfar_ptr,
+           const HMat::FarItem *__restrict__ bfar, const uint *__restrict__ far_ids, const HLeafDev *__restrict__ leaves,
+           const unsigned long long *__restrict__ toff, const cplx *__restrict__ pool, cplx *T,
+           const cplx *__restrict__ xp, cplx *yp, uint ntot, uint nrhs) {
+  constexpr int RP = 16 * TC, XS_LD = RP + 2;   // leading dimensions == 2 (mod 8): conflict-free fragment loads
+  __shared__ cplx As[2][16][AS_LDB];      // [contraction index][row]
+  __shared__ cplx Xs[2][16][XS_LD];       // [contraction index][rhs]
+  __shared__ HMat::FarItem Is[3][16];     // per contraction index: U/A column, row range, x or t index
+  __shared__ uint s_cnt[3], s_far[3];
+  const uint tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint fr = lane >> 2, fc = lane & 3;
+  uint b0 = 0, db = 0, nd = 0, fb = 0, fe = 0, R = 0, lk = 0, ln = 0, lc0 = 0;
+  size_t voff = 0;
+  unsigned long long t0 = 0;
+  if (!TMODE) {
+    b0 = blockIdx.x * BAND;
+    db = band_ptr[blockIdx.x]; nd = band_ptr[blockIdx.x + 1] - db;
+    fb = bfar_ptr[blockIdx.x]; fe = bfar_ptr[blockIdx.x + 1];
+    R = nd + (fe - fb + 15) / 16;
+  } else {
+    const uint id = far_ids[blockIdx.x];
+    const HLeafDev L = leaves[id];
+    lk = L.k; ln = L.n; lc0 = L.c0;
+    voff = L.off + (size_t)L.m * L.kcap;
+    t0 = toff[id];
+    R = (ln + 15) / 16;
+    if (!lk) return;
+  }
+
+  for (uint l0 = 0; l0 < (TMODE ? lk : 1u); l0 += 16)    // rank indices 16 at a time (TMODE), once otherwise
+  for (uint r0 = 0; r0 < nrhs; r0 += RP) {
+    const uint kk = TMODE ? min(16u, lk - l0) : 16u;
+    // descriptors of round c -> registers of threads 0..15 (one contraction index each)
+    auto fetch_items = [&](uint c, HMat::FarItem &it, uint &cnt) {
+      if (TMODE) {
+        cnt = min(16u, ln - c * 16);
+        it.u_off = voff + (size_t)l0 * ln + c * 16 + tid;   // V[j, l0]: rows (rank indices) at stride n
+        it.t_idx = lc0 + c * 16 + tid;
+        it.r0 = 0; it.m = kk;
+      } else if (c < nd) {
+        const HMat::DRound D = dround[db + c];
+        cnt = D.cnt;
+        it.u_off = D.a_off + (size_t)tid * D.m;
+        it.t_idx = D.x_off + tid;
+        it.r0 = D.r0; it.m = D.m;
+      } else {
+        const uint f0 = fb + (c - nd) * 16;
+        cnt = min(16u, fe - f0);
+        if (tid < cnt) it = bfar[f0 + tid];
+      }
+    };
+    auto store_items = [&](uint c, const HMat::FarItem &it, uint cnt) {
+      if (tid < 16) Is[c % 3][tid] = it;
+      if (tid == 0) { s_cnt[c % 3] = cnt; s_far[c % 3] = (!TMODE && c >= nd) ? 1u : 0u; }
+    };
+    // operands of round c -> shared-memory buffers c & 1 (indices beyond cnt are zero-filled)
+    auto issue = [&](uint c) {
+      const uint ib = c % 3, buf = c & 1, cnt = s_cnt[ib];
+      const bool far = s_far[ib] != 0;
+      if (TMODE) {
+        for (uint e = tid; e < 16 * BAND; e += BT_THREADS) {
+          const uint j = e % 16, i = e / 16;   // consecutive threads walk a row of V^T (contiguous in j)
+          const bool ok = j < cnt && i < kk;
+          hm_cp_async16(&As[buf][j][i], ok ? pool + Is[ib][j].u_off + (size_t)i * ln : pool, ok);
+        }
+      } else {
+        for (uint e = tid; e < 16 * BAND; e += BT_THREADS) {
+          const uint i = e % BAND, j = e / BAND;
+          const HMat::FarItem it = Is[ib][j];
+          const long long row = (long long)b0 + i - (long long)it.r0;
+          const bool ok = j < cnt && row >= 0 && row < (long long)it.m;
+          hm_cp_async16(&As[buf][j][i], ok ? pool + it.u_off + row : pool, ok);
+        }
+      }
+      if (!far) {
+        for (uint e = tid; e < 16 * RP; e += BT_THREADS) {
+          const uint j = e % 16, r = e / 16;
+          const bool ok = j < cnt && r0 + r < nrhs;
+          hm_cp_async16(&Xs[buf][j][r], ok ? xp + (size_t)(r0 + r) * ntot + Is[ib][j].t_idx : xp, ok);
+        }
+      } else {
+        for (uint e = tid; e < 16 * RP; e += BT_THREADS) {
+          const uint r = e % RP, j = e / RP;
+          const bool ok = j < cnt && r0 + r < nrhs;
+          hm_cp_async16(&Xs[buf][j][r], ok ? T + (size_t)Is[ib][j].t_idx * nrhs + r0 + r : T, ok);
+        }
+      }
+    };
+    double X[2][TC][2], Y[2][TC][2], W[2][TC][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int q = 0; q < TC; q++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) X[a][q][e] = Y[a][q][e] = W[a][q][e] = 0.0;
+    HMat::FarItem it;
+    uint cnt = 0;
+    __syncthreads();   // previous pass is done with every buffer
+    if (R > 0) { fetch_items(0, it, cnt); store_items(0, it, cnt); }
+    if (R > 1) { fetch_items(1, it, cnt); store_items(1, it, cnt); }
+    __syncthreads();
+    if (R > 0) issue(0);
+    asm volatile("cp.async.commit_group;\n" ::);
+    for (uint c = 0; c < R; c++) {
+      __syncthreads();   // items of round c+1 visible; round c-1 contracted: its buffers are free
+      if (c + 1 < R) issue(c + 1);
+      asm volatile("cp.async.commit_group;\n" ::);
+      if (c + 2 < R) fetch_items(c + 2, it, cnt);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+      __syncthreads();   // operands of round c have landed
+      const uint buf = c & 1, jn = (s_cnt[c % 3] + 3) / 4;   // k4 steps (zero-filled tail)
+      const int nmi = (TMODE && kk <= 8) ? 1 : 2;             // ranks <= 8: the second row tile is all zero
+      for (uint ks = 0; ks < jn; ks++) {
+        double are[2], aim[2], asu[2], bre[TC], bim[TC], bsu[TC];
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+          const cplx v = As[buf][ks * 4 + fc][mi * 8 + fr];
+          are[mi] = v.x; aim[mi] = v.y; asu[mi] = v.x + v.y;
+        }
+#pragma unroll
+        for (int ni = 0; ni < TC; ni++) {
+          const cplx v = Xs[buf][ks * 4 + fc][(warp * TC + ni) * 8 + fr];
+          bre[ni] = v.x; bim[ni] = v.y; bsu[ni] = v.x + v.y;
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++)
+          if (mi < nmi)
+#pragma unroll
+            for (int ni = 0; ni < TC; ni++) {
+              hm_dmma(X[mi][ni][0], X[mi][ni][1], are[mi], bre[ni]);
+              hm_dmma(Y[mi][ni][0], Y[mi][ni][1], aim[mi], bim[ni]);
+              hm_dmma(W[mi][ni][0], W[mi][ni][1], asu[mi], bsu[ni]);
+            }
+      }
+      if (c + 2 < R) store_items(c + 2, it, cnt);   // slot (c+2) % 3 = (c-1) % 3: round c-1 is finished
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::);
+#pragma unroll
+    for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+      for (int ni = 0; ni < TC; ni++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const uint i = mi * 8 + fr, r = r0 + (warp * TC + ni) * 8 + fc * 2 + e;
+          const cplx v = make_double2(X[mi][ni][e] - Y[mi][ni][e], W[mi][ni][e] - X[mi][ni][e] - Y[mi][ni][e]);
+          if (TMODE) {
+            if (i < kk && r < nrhs) T[(size_t)(t0 + l0 + i) * nrhs + r] = v;
+          } else {
+            if (b0 + i < ntot && r < nrhs) yp[(size_t)r * ntot + b0 + i] = v;
+          }
+        }
+  }
+}
+
 __global__ void k_expand(const HLeafDev *__restrict__ leaves, const cplx *__restrict__ pool,
                          const uint *__restrict__ perm, cplx *Z, size_t ld) {
   const HLeafDev L = leaves[blockIdx.x];
@@ -469,7 +654,72 @@ int hmat_from_host(HMat &H, int device, uint n, const std::vector<uint> &perm, c
   return 0;
 }
 
+// band lists (structure) and rank offsets (after every assembly) of the batched matvec
+int hmat_prepare_batched(HMat &H, bool fetch) {
+  if (fetch && hmat_fetch_leaves(H)) return -1;
+  if (!H.d_band_ptr) {   // structure: bands x dense rounds, list of low-rank leaves
+    H.nband = (H.n + BAND - 1) / BAND;
+    std::vector<uint> ptr(H.nband + 1, 0), mvfar;
+    for (size_t id = 0; id < H.leaf.size(); id++) {
+      const HLeafDev &L = H.leaf[id];
+      if (!L.m || !L.n) continue;
+      if (L.adm) { mvfar.push_back((uint)id); continue; }
+      for (uint b = L.r0 / BAND; b <= (L.r0 + L.m - 1) / BAND; b++) ptr[b + 1] += (L.n + 15) / 16;
+    }
+    for (uint b = 0; b < H.nband; b++) ptr[b + 1] += ptr[b];
+    std::vector<HMat::DRound> rounds(ptr[H.nband]);
+    std::vector<uint> fill(ptr.begin(), ptr.end() - 1);
+    for (size_t id = 0; id < H.leaf.size(); id++) {
+      const HLeafDev &L = H.leaf[id];
+      if (!L.m || !L.n || L.adm) continue;
+      for (uint b = L.r0 / BAND; b <= (L.r0 + L.m - 1) / BAND; b++)
+        for (uint j0 = 0; j0 < L.n; j0 += 16)
+          rounds[fill[b]++] = {L.off + (size_t)j0 * L.m, L.r0, L.m, L.c0 + j0, std::min(16u, L.n - j0), {0, 0}};
+    }
+    H.nmvfar = (uint)mvfar.size();
+    if (to_device(H.d_band_ptr, ptr) || to_device(H.d_dround, rounds) || to_device(H.d_mvfar, mvfar)) return -1;
+    CNLD_CK(cudaMalloc(&H.d_toff, sizeof(unsigned long long) * (H.leaf.size() + 1)));
+    CNLD_CK(cudaMalloc(&H.d_bfar_ptr, sizeof(uint) * (H.nband + 1)));
+  }
+  // ranks: scratch offsets and the packed (leaf, rank index) items of every band
+  std::vector<unsigned long long> toff(H.leaf.size() + 1, 0);
+  std::vector<uint> fptr(H.nband + 1, 0);
+  unsigned long long sum = 0;
+  for (size_t id = 0; id < H.leaf.size(); id++) {
+    const HLeafDev &L = H.leaf[id];
+    toff[id] = sum;
+    if (!L.adm || !L.m || !L.n) continue;
+    sum += L.k;
+    for (uint b = L.r0 / BAND; b <= (L.r0 + L.m - 1) / BAND; b++) fptr[b + 1] += L.k;
+  }
+  H.ksum = sum;
+  for (uint b = 0; b < H.nband; b++) fptr[b + 1] += fptr[b];
+  std::vector<HMat::FarItem> items(fptr[H.nband]);
+  {
+    std::vector<uint> fill(fptr.begin(), fptr.end() - 1);
+    for (size_t id = 0; id < H.leaf.size(); id++) {
+      const HLeafDev &L = H.leaf[id];
+      if (!L.adm || !L.m || !L.n) continue;
+      for (uint b = L.r0 / BAND; b <= (L.r0 + L.m - 1) / BAND; b++)
+        for (uint l = 0; l < L.k; l++) items[fill[b]++] = {L.off + (size_t)l * L.m, toff[id] + l, L.r0, L.m};
+    }
+  }
+  if (H.bfar_cap < items.size()) {
+    cudaFree(H.d_bfar);
+    H.d_bfar = nullptr;
+    H.bfar_cap = items.size() + items.size() / 4 + 16;
+    CNLD_CK(cudaMalloc(&H.d_bfar, sizeof(HMat::FarItem) * H.bfar_cap));
+  }
+  CNLD_CK(cudaMemcpy(H.d_bfar, items.data(), sizeof(HMat::FarItem) * items.size(), cudaMemcpyHostToDevice));
+  CNLD_CK(cudaMemcpy(H.d_bfar_ptr, fptr.data(), sizeof(uint) * (H.nband + 1), cudaMemcpyHostToDevice));
+  CNLD_CK(cudaMemcpy(H.d_toff, toff.data(), sizeof(unsigned long long) * H.leaf.size(), cudaMemcpyHostToDevice));
+  H.mv_ready = true;
+  return 0;
+}
+
 void hmat_free(HMat &H) {
+  cudaFree(H.d_band_ptr); cudaFree(H.d_dround); cudaFree(H.d_mvfar); cudaFree(H.d_toff); cudaFree(H.d_T);
+  cudaFree(H.d_bfar_ptr); cudaFree(H.d_bfar);
   cudaFree(H.d_leaf); cudaFree(H.d_near); cudaFree(H.d_far); cudaFree(H.d_perm); cudaFree(H.d_pos);
   cudaFree(H.d_ctri_ptr); cudaFree(H.d_ctri); cudaFree(H.d_v2t_ptr); cudaFree(H.d_v2t); cudaFree(H.d_pool);
   cudaFree(H.d_flags); cudaFree(H.d_err); cudaFree(H.d_xp); cudaFree(H.d_yp); cudaFree(H.d_cpos);
@@ -518,6 +768,7 @@ int hmat_assemble(cudaStream_t st, HMat &H, double kr, double ki, double accur) 
   CNLD_CK(cudaStreamSynchronize(st));
   if (err) { set_error("H-matrix near-field: touching-pair queue overflow (leaf too large; raise NEAR_QCAP)"); return -1; }
   H.assembled = true;
+  H.mv_ready = false;   // ranks changed: the batched matvec refreshes its offsets on first use
   return 0;
 }
 
@@ -533,6 +784,47 @@ int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y
   }
   const size_t tot = (size_t)H.n * nrhs;
   const unsigned gb = (unsigned)((tot + 255) / 256);
+  if (nrhs >= 4) {
+    if (!H.mv_ready) {
+      CNLD_CK(cudaStreamSynchronize(st));
+      if (hmat_prepare_batched(H, H.bem != nullptr)) return -1;
+    }
+    const size_t need = (size_t)H.ksum * nrhs;
+    if (H.T_cap < need) {
+      CNLD_CK(cudaStreamSynchronize(st));
+      cudaFree(H.d_T);
+      H.d_T = nullptr;
+      CNLD_CK(cudaMalloc(&H.d_T, sizeof(cplx) * (need ? need : 1)));
+      H.T_cap = need;
+    }
+    k_permute_in<<<gb, 256, 0, st>>>(H.n, nrhs, H.d_perm, d_x, H.d_xp);
+    CNLD_CK_LAUNCH();
+    // right-hand sides per pass (16 * TC): the width that wastes the fewest columns, ties to the wider
+    int tc = 2;
+    uint best = ~0u;
+    for (int c : {2, 3, 4}) {
+      const uint rp = 16 * c, waste = (nrhs + rp - 1) / rp * rp - nrhs;
+      if (waste <= best) { best = waste; tc = c; }
+    }
+#define CNLD_HMV(TCV)                                                                                              \
+  do {                                                                                                             \
+    if (H.nmvfar) {                                                                                                \
+      k_hmv_gemm<TCV, true><<<H.nmvfar, BT_THREADS, 0, st>>>(H.d_band_ptr, H.d_dround, H.d_bfar_ptr, H.d_bfar,       \
+          H.d_mvfar, H.d_leaf, H.d_toff, H.d_pool, H.d_T, H.d_xp, H.d_yp, H.n, nrhs);                              \
+      CNLD_CK_LAUNCH();                                                                                            \
+    }                                                                                                              \
+    k_hmv_gemm<TCV, false><<<H.nband, BT_THREADS, 0, st>>>(H.d_band_ptr, H.d_dround, H.d_bfar_ptr, H.d_bfar,         \
+        H.d_mvfar, H.d_leaf, H.d_toff, H.d_pool, H.d_T, H.d_xp, H.d_yp, H.n, nrhs);                                \
+  } while (0)
+    if (tc == 2) CNLD_HMV(2);
+    else if (tc == 3) CNLD_HMV(3);
+    else CNLD_HMV(4);
+#undef CNLD_HMV
+    CNLD_CK_LAUNCH();
+    k_permute_out<<<gb, 256, 0, st>>>(H.n, nrhs, H.d_perm, alpha, H.d_yp, d_y);
+    CNLD_CK_LAUNCH();
+    return 0;
+  }
   k_permute_in<<<gb, 256, 0, st>>>(H.n, nrhs, H.d_perm, d_x, H.d_xp);
   CNLD_CK_LAUNCH();
   CNLD_CK(cudaMemsetAsync(H.d_yp, 0, sizeof(cplx) * tot, st));
