@@ -100,7 +100,7 @@ struct LuWork {
   uint inv_nbo = 0, inv_nfull = 0;   // geometry the buffers were allocated / filled for
   bool inv_ready = false;
   mutable cplx *ytmp = nullptr;      // nbo x nrhs scratch of lu_solve
-  mutable uint ytmp_cols = 0;
+  mutable size_t ytmp_elems = 0;
   cplx *linv = nullptr;  // [nblk][nb*nb]
   cplx *uinv = nullptr;  // [nblk][nb*nb]
   uint *info = nullptr;  // device flag: 0 ok else first failing pivot + 1

@@ -436,11 +436,11 @@ int lu_solve(cudaStream_t st, const LuWork &w, const cplx *a, size_t lda, cplx *
   const uint n = w.n;
   const bool inv = w.inv_ready && g_lu_outer_inverse;
   const uint NBO = inv ? w.inv_nbo : (uint)((g_lu_outer / NB) * NB > 0 ? (g_lu_outer / NB) * NB : NB);
-  if (inv && w.ytmp_cols < nrhs) {
+  if (inv && w.ytmp_elems < (size_t)NBO * nrhs) {
     cudaFree(w.ytmp);
     w.ytmp = nullptr;
     CNLD_CK(cudaMalloc(&w.ytmp, sizeof(cplx) * (size_t)NBO * nrhs));
-    w.ytmp_cols = nrhs;
+    w.ytmp_elems = (size_t)NBO * nrhs;
   }
   const uint nouter = (n + NBO - 1) / NBO;
   for (uint ob = 0; ob < nouter; ob++) {  // L y = b

@@ -5,16 +5,16 @@ from cnld import _lib as L
 from cnld import arrays
 from cnld.sweep import FrequencySweep, SweepSetup
 setup = SweepSetup.from_abstract(arrays.matrix_array(nelem=(4, 4)), 21)
-freqs = np.linspace(0.025e6, 50e6, 2000)[[417, 903, 1311, 1777]]
-for ns in (1, 2):
+freqs = np.linspace(0.025e6, 50e6, 2000)[[417, 903, 1311, 1777, 222, 1505]]
+for ns in (3,):
     sw = FrequencySweep(setup, nstreams=ns)
     sw.ctx.set_symmetric(1, 1)
     sw.ctx.run_device(freqs[:2]) if hasattr(sw.ctx, 'run_device') else sw.run(freqs[:2])
-    for outer in (256, 384, 512, 768):
-        for res in (4, 8, 12, 16, 24, 32):
+    for outer in (512, 1024):
+        for res in (12, 24):
             L.lib().cnld_b200_set_lu_outer(outer); L.lib().cnld_b200_set_lu_reserve(res)
             sw.run(freqs)
             t = sw.ctx.stage_times()
             print('streams', ns, 'outer', outer, 'reserve', res, 'asm %.1f fac %.1f sol %.1f ms/freq  -> %.3f freq/s' % (
-                t['assemble'] / 4 * 1e3, t['factor'] / 4 * 1e3, t['solve'] / 4 * 1e3, 4 / t['device_seconds']), flush=True)
+                t['assemble'] / 6 * 1e3, t['factor'] / 6 * 1e3, t['solve'] / 6 * 1e3, 6 / t['device_seconds']), flush=True)
     sw.close()
