@@ -2,7 +2,7 @@
 """
 bench.py -- frequencies solved per second on the 4x4 CMUT array (BASELINE.json metric).
 
-One "step" = one batch of frequencies (default 4 per GPU) pushed through the whole hot path:
+One "step" = one batch of frequencies (default 6 per GPU, 3 in flight) pushed through the whole hot path:
 init G = K - w^2 M - j w B, accumulate -2 rho w^2 Z(k) (Galerkin Helmholtz SLP assembly), unpivoted
 complex-FP64 LU, solve all P source patches, conj / boundary mask / patch average
 (cnld/scripts/generate_db.py:30-130).  Workload = BASELINE.json configs[2] ("4x4 CMUT array
@@ -24,6 +24,13 @@ import subprocess
 import sys
 import threading
 import time
+
+# The CPU arms (--impl reference, and the cpu_baseline leg) use every host core the process may run on.
+# torchrun exports OMP_NUM_THREADS=1 to its workers; undo that before numpy / OpenBLAS / libgomp read it.
+_NCORES = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+if 'reference' in sys.argv:
+    for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_v] = str(_NCORES)
 
 import numpy as np
 
@@ -107,6 +114,11 @@ def run_reference(args, rank, world):
     am = po.array_mesh(arr, refn)
     blocks = po.array_fem(arr, refn)
     cores = po.lib().orc_num_threads()
+    try:                                   # BLAS threads of the blocked LU follow the same count
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=_NCORES)
+    except Exception:
+        pass
     # each step = ONE full frequency of the workload (bounded sample of the per-GPU batch)
     freqs = workload_freqs(args.config, args.steps + args.warmup)
     for i in range(args.warmup):
