@@ -45,6 +45,7 @@ def lib():
         L.cnld_b200_create.argtypes = [C.c_int, u32, u32, vp, vp, u32, u32]
         L.cnld_b200_destroy.argtypes = [vp]
         L.cnld_b200_set_streams.argtypes = [vp, C.c_int]
+        L.cnld_b200_pin_host.argtypes = [vp, vp, C.c_size_t]
         L.cnld_b200_get_geometry.argtypes = [vp, vp, vp]
         L.cnld_b200_assemble_slp_ll.argtypes = [vp, f64, f64, vp, u32]
         L.cnld_b200_nearfield_slp_ll.argtypes = [vp, f64, f64, vp, u32, vp, u32, vp, u32]
@@ -119,6 +120,9 @@ class Context:
 
     def close(self):
         if getattr(self, '_h', None):
+            if getattr(self, '_pinned', None) is not None:
+                lib().cnld_b200_pin_host(self._h, None, 0)
+                self._pinned = None
             lib().cnld_b200_destroy(self._h)
             self._h = None
 
@@ -209,9 +213,29 @@ class Context:
         if want_nodes:
             xn = out_nodes if out_nodes is not None else np.empty((nf, P, self.nv), dtype=np.complex128)
             assert xn.shape == (nf, P, self.nv) and xn.dtype == np.complex128 and xn.flags.c_contiguous
+            if out_nodes is not None:
+                self.pin(out_nodes)        # caller-owned, reused buffer: D2H lands in it directly
         t = np.zeros(nf)
         check(lib().cnld_b200_sweep_run(self._h, ptr(freqs), nf, c, rho, ptr(xp), ptr(xn), ptr(t)))
         return xp, xn, t
+
+    def pin(self, arr):
+        """Page-lock `arr` in place (kept referenced here until replaced or close())."""
+        if arr is None:
+            if getattr(self, '_pinned', None) is not None:
+                lib().cnld_b200_pin_host(self._h, None, 0)
+                self._pinned = None
+            return
+        base = arr if arr.base is None else arr.base
+        cur = getattr(self, '_pinned', None)
+        if cur is not None and cur is base:
+            return
+        if not isinstance(base, np.ndarray) or not base.flags.c_contiguous:
+            return
+        if lib().cnld_b200_pin_host(self._h, ptr(base), base.nbytes) == 0:
+            self._pinned = base
+        else:
+            self._pinned = None
 
     def sweep_device(self, freqs, c=1500., rho=1000.):
         freqs = _c(freqs, np.float64)

@@ -29,6 +29,7 @@ void set_error(const char *fmt, ...) {
 
 #include "ctx.cuh"
 #include <algorithm>
+#include <map>
 using namespace cnld;
 using namespace cnld::sweep;
 
@@ -89,12 +90,38 @@ k_epilogue(uint nv, uint P, cplx *X, size_t ldx, const uint8_t *__restrict__ ob,
   }
 }
 
+// device copy of a host array; the allocation is kept when the new contents fit (no cudaFree /
+// cudaMalloc -- both synchronise the device -- when a sweep re-uploads operators of the same size)
+std::mutex g_cap_mu;
+std::map<const void *, size_t> g_cap;
 template <typename T>
 int upload(T *&d, const T *h, size_t n) {
-  if (d) { cudaFree(d); d = nullptr; }
-  CNLD_CK(cudaMalloc(&d, sizeof(T) * (n ? n : 1)));
+  const size_t bytes = sizeof(T) * (n ? n : 1);
+  {
+    std::lock_guard<std::mutex> lk(g_cap_mu);
+    auto it = d ? g_cap.find(d) : g_cap.end();
+    if (d && (it == g_cap.end() || it->second < bytes)) {
+      if (it != g_cap.end()) g_cap.erase(it);
+      cudaFree(d);
+      d = nullptr;
+    }
+    if (!d) {
+      CNLD_CK(cudaMalloc(&d, bytes));
+      g_cap[d] = bytes;
+    }
+  }
   if (n) CNLD_CK(cudaMemcpy(d, h, sizeof(T) * n, cudaMemcpyHostToDevice));
   return 0;
+}
+template <typename T>
+void dev_free(T *&d) {
+  if (!d) return;
+  {
+    std::lock_guard<std::mutex> lk(g_cap_mu);
+    g_cap.erase(d);
+  }
+  cudaFree(d);
+  d = nullptr;
 }
 
 int ensure_workspace(cnld_ctx *c, bool need_host_stage) {
@@ -280,7 +307,15 @@ int sweep_impl(cnld_ctx *c, const double *freqs, uint nf, double cs, double rho,
                cnld_field *x_node, double *t_freq, bool device_only) {
   if (check_ready(c)) return -1;
   const size_t nv = c->bem.nv, P = c->P;
-  if (ensure_workspace(c, x_node != nullptr)) return -1;
+  // Node displacements go straight into the caller's buffer when it lies inside the region the caller
+  // page-locked with cnld_b200_pin_host; otherwise through pinned staging + a host copy.
+  bool direct = false;
+  if (x_node && nf && c->reg_ptr) {
+    const char *lo = reinterpret_cast<const char *>(x_node), *hi = lo + sizeof(cplx) * (size_t)nf * P * nv;
+    const char *rlo = reinterpret_cast<const char *>(c->reg_ptr);
+    direct = lo >= rlo && hi <= rlo + c->reg_bytes;
+  }
+  if (ensure_workspace(c, x_node != nullptr && !direct)) return -1;
   if (c->xpatch_cap < nf) {
     cudaFree(c->d_xpatch);
     c->d_xpatch = nullptr;
@@ -312,7 +347,8 @@ int sweep_impl(cnld_ctx *c, const double *freqs, uint nf, double cs, double rho,
       if (remaining > c->sym_tol) {  // not converged: redo this frequency with the general elimination
         c->sym_redone++;
         if (enqueue_frequency(c, S, freqs[S.pending], cs, rho, c->d_xpatch + (size_t)S.pending * P * P, false)) return -1;
-        if (x_node) CNLD_CK(cudaMemcpyAsync(S.hX, S.X, sizeof(cplx) * P * nv, cudaMemcpyDeviceToHost, S.st));
+        if (x_node) CNLD_CK(cudaMemcpyAsync(direct ? (void *)(reinterpret_cast<cplx *>(x_node) + (size_t)S.pending * P * nv) : (void *)S.hX,
+                                            S.X, sizeof(cplx) * P * nv, cudaMemcpyDeviceToHost, S.st));
         if (x_node) CNLD_CK(cudaEventRecord(S.ev[3], S.st));
         if (end_recorded) CNLD_CK(cudaEventRecord(c->ev_end, S.st));
         CNLD_CK(cudaEventSynchronize(S.ev[3]));
@@ -321,7 +357,7 @@ int sweep_impl(cnld_ctx *c, const double *freqs, uint nf, double cs, double rho,
     float ms[3];
     for (int e = 0; e < 3; e++) { CNLD_CK(cudaEventElapsedTime(&ms[e], S.ev[e], S.ev[e + 1])); acc[e] += ms[e] * 1e-3; }
     if (t_freq) t_freq[S.pending] = (ms[0] + ms[1] + ms[2]) * 1e-3;
-    if (x_node) memcpy(reinterpret_cast<cplx *>(x_node) + (size_t)S.pending * P * nv, S.hX, sizeof(cplx) * P * nv);
+    if (x_node && !direct) memcpy(reinterpret_cast<cplx *>(x_node) + (size_t)S.pending * P * nv, S.hX, sizeof(cplx) * P * nv);
     if (c->profile) {
       double sec, fl, nl;
       if (lu_trailing_stats(S.lu, &sec, &fl, &nl)) return -1;
@@ -338,7 +374,8 @@ int sweep_impl(cnld_ctx *c, const double *freqs, uint nf, double cs, double rho,
     int rc = drain(S);
     if (rc) return rc;
     if (enqueue_frequency(c, S, freqs[i], cs, rho, c->d_xpatch + (size_t)i * P * P)) return -1;
-    if (x_node) CNLD_CK(cudaMemcpyAsync(S.hX, S.X, sizeof(cplx) * P * nv, cudaMemcpyDeviceToHost, S.st));
+    if (x_node) CNLD_CK(cudaMemcpyAsync(direct ? (void *)(reinterpret_cast<cplx *>(x_node) + (size_t)i * P * nv) : (void *)S.hX,
+                                        S.X, sizeof(cplx) * P * nv, cudaMemcpyDeviceToHost, S.st));
     if (x_node) CNLD_CK(cudaEventRecord(S.ev[3], S.st));
     S.pending = i;
   }
@@ -400,14 +437,30 @@ void cnld_b200_destroy(cnld_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->bem.device);
   free_workspace(c);
-  cudaFree(c->d_indptr); cudaFree(c->d_indices); cudaFree(c->d_K); cudaFree(c->d_M); cudaFree(c->d_B);
-  cudaFree(c->d_f_indptr); cudaFree(c->d_a_indptr); cudaFree(c->d_f_idx); cudaFree(c->d_a_idx);
-  cudaFree(c->d_f_val); cudaFree(c->d_a_val); cudaFree(c->d_ob); cudaFree(c->d_xpatch); cudaFree(c->d_xnode);
+  dev_free(c->d_indptr); dev_free(c->d_indices); dev_free(c->d_K); dev_free(c->d_M); dev_free(c->d_B);
+  dev_free(c->d_f_indptr); dev_free(c->d_a_indptr); dev_free(c->d_f_idx); dev_free(c->d_a_idx);
+  dev_free(c->d_f_val); dev_free(c->d_a_val); dev_free(c->d_ob); cudaFree(c->d_xpatch); cudaFree(c->d_xnode);
   cudaFree(c->d_sp);
-  cudaFree(c->d_m_rowptr); cudaFree(c->d_m_col); cudaFree(c->d_m_dK); cudaFree(c->d_m_dM); cudaFree(c->d_m_dB);
+  dev_free(c->d_m_rowptr); dev_free(c->d_m_col); dev_free(c->d_m_dK); dev_free(c->d_m_dM); dev_free(c->d_m_dB);
   if (c->ev_begin) { cudaEventDestroy(c->ev_begin); cudaEventDestroy(c->ev_end); }
+  if (c->reg_ptr) cudaHostUnregister(c->reg_ptr);
   bem_free(c->bem);
   delete c;
+}
+
+int cnld_b200_pin_host(cnld_ctx *c, void *ptr, size_t bytes) {
+  if (!c) { set_error("null context"); return -1; }
+  CNLD_CK(cudaSetDevice(c->bem.device));
+  if (c->reg_ptr) { cudaHostUnregister(c->reg_ptr); c->reg_ptr = nullptr; c->reg_bytes = 0; }
+  if (!ptr || !bytes) return 0;
+  if (cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaHostRegister failed for %zu bytes (the sweep falls back to pinned staging)", bytes);
+    return -1;
+  }
+  c->reg_ptr = ptr;
+  c->reg_bytes = bytes;
+  return 0;
 }
 
 int cnld_b200_set_streams(cnld_ctx *c, int n) {
@@ -577,9 +630,9 @@ int cnld_b200_set_mbk(cnld_ctx *c, const int64_t *indptr, const cnld_uint *indic
     for (const Trip &t : trips) { rp[t.r + 1]++; mc.push_back(t.c); dK.push_back(t.k); dM.push_back(t.m); dB.push_back(t.b); }
     for (size_t r = 0; r < nv; r++) rp[r + 1] += rp[r];
     c->m_nnz = (uint)mc.size();
-    cudaFree(c->d_m_rowptr); cudaFree(c->d_m_col); cudaFree(c->d_m_dK); cudaFree(c->d_m_dM); cudaFree(c->d_m_dB);
-    c->d_m_rowptr = nullptr; c->d_m_col = nullptr; c->d_m_dK = c->d_m_dM = c->d_m_dB = nullptr;
-    if (c->m_nnz) {
+    if (!c->m_nnz) {
+      dev_free(c->d_m_rowptr); dev_free(c->d_m_col); dev_free(c->d_m_dK); dev_free(c->d_m_dM); dev_free(c->d_m_dB);
+    } else {
       if (upload(c->d_m_rowptr, rp.data(), nv + 1) || upload(c->d_m_col, mc.data(), mc.size()) ||
           upload(c->d_m_dK, dK.data(), dK.size()) || upload(c->d_m_dM, dM.data(), dM.size()) ||
           upload(c->d_m_dB, dB.data(), dB.size())) return -1;

@@ -71,6 +71,9 @@ struct cnld_ctx {
   uint *d_m_rowptr = nullptr, *d_m_col = nullptr;
   double *d_m_dK = nullptr, *d_m_dM = nullptr, *d_m_dB = nullptr;
   double kstat[3] = {0, 0, 0};  // trailing ZGEMM: flops, seconds, launches (last sweep)
+  // caller's x_node buffer page-locked in place (direct D2H, no staging copy); re-used across calls
+  void *reg_ptr = nullptr;
+  size_t reg_bytes = 0;
   // pressure scratch
   double *d_sp = nullptr;
 };

@@ -133,6 +133,12 @@ int cnld_b200_sweep_fetch(cnld_ctx *ctx, cnld_uint nf, cnld_field *x_patch, cnld
  * sweep (begin/end events joined across all streams).  out must hold 5 doubles. */
 int cnld_b200_sweep_stage_times(cnld_ctx *ctx, double *out);
 
+/* Page-lock a caller-owned host region in place (cudaHostRegister).  A later sweep_run whose x_node
+ * buffer lies inside it copies node displacements straight into it (no staging buffer, no host
+ * memcpy).  One region per context; ptr = NULL (or destroy) releases it.  The caller must keep the
+ * memory alive until then. */
+int cnld_b200_pin_host(cnld_ctx *ctx, void *ptr, size_t bytes);
+
 /* Symmetric path (mode 1; default 0 = the reference's general elimination, solve_cholesky=False /
  * lrdecomp_amatrix in cnld/h2lib/factorizations_cy.pyx).  G = S + Delta, S = the complex symmetric
  * matrix given by G's lower triangle, Delta = the sparse strictly-upper asymmetry (the Sauter-Schwab
