@@ -38,7 +38,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, 'cnl-dyna_b200'))
 
 # dram bytes (read + write) of the first trailing update, ncu --set full: {general: ..., symmetric: ...}
-TRAFFIC_T2 = {True: 8.28e9, False: None}
+TRAFFIC_T2 = {True: 8.28e9, False: 8.06e9}
 METRIC = 'frequencies solved/s (Z assemble+factor+solve), 4x4 CMUT array'
 UNIT = 'frequencies/s'
 CONFIGS = {  # name: (nelem, refn, nfreq of the full sweep, fmin, fmax)
