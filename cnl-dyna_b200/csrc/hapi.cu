@@ -57,6 +57,10 @@ __global__ void k_block_dense(uint nb_, uint r0, const int64_t *__restrict__ ind
     if (j < nb_) D[(size_t)j * nb_ + i] = make_double2(K[p] - w2 * M[p], -omega * B[p]);
   }
 }
+__global__ void k_axpy_scaled(size_t n, double a, const cplx *__restrict__ x, cplx *y) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { y[i].x += a * x[i].x; y[i].y += a * x[i].y; }
+}
 __global__ void k_identity(uint n, cplx *D) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < (size_t)n * n) D[i] = make_double2((i % n) == (i / n) ? 1.0 : 0.0, 0.0);
@@ -190,12 +194,15 @@ void detect_blocks(const cnld_ctx *c, Blocks &B) {
   }
 }
 
+int g_hsweep_fluid_precond = 1;
+
 struct Gmres {
   cnld_ctx *c;
   HMat *H;
   cudaStream_t st;
   uint n, nb, restart;
-  double omega, coef;
+  double omega, coef, kwave = 0.0;
+  int fluid_precond = 1;   // add the membrane's own block of coef * Z to the block-Jacobi preconditioner
   Blocks blk;
   std::vector<cplx *> d_inv;  // per block type: dense inverse
   std::vector<cplx *> d_blk;  // per block type: the dense block K - w^2 M - j w B itself
@@ -240,6 +247,20 @@ struct Gmres {
       CNLD_CK_LAUNCH();
       k_identity<<<(unsigned)(((size_t)sz * sz + 255) / 256), 256, 0, st>>>(sz, I);
       CNLD_CK_LAUNCH();
+      if (fluid_precond && coef != 0.0) {
+        // self-radiation of the block: its own dense block of Z (exact near-field quadrature), so the
+        // preconditioner is (MBK + coef Z)_block^-1 -- the fluid loading a membrane puts on itself is
+        // the largest part of coef Z and costs one sz x sz assembly per block type and frequency
+        cplx *Zb = nullptr;
+        CNLD_CK(cudaMalloc(&Zb, sizeof(cplx) * (size_t)sz * sz));
+        std::vector<uint> idx(sz);
+        for (uint i = 0; i < sz; i++) idx[i] = blk.r0[b] + i;
+        if (nearfield_block(st, c->bem, c->h_t.data(), idx.data(), sz, idx.data(), sz, kwave, 0.0, Zb)) { cudaFree(Zb); return -1; }
+        k_axpy_scaled<<<(unsigned)(((size_t)sz * sz + 255) / 256), 256, 0, st>>>((size_t)sz * sz, coef, Zb, D);
+        CNLD_CK_LAUNCH();
+        CNLD_CK(cudaStreamSynchronize(st));
+        cudaFree(Zb);
+      }
       LuWork w;
       if (lu_work_alloc(w, sz) || lu_factor(st, w, D, sz) || lu_solve(st, w, D, sz, I, sz, sz)) return -1;
       // keep an unfactored copy of the block for apply_G
@@ -526,6 +547,8 @@ int cnld_b200_hsweep_run(cnld_ctx *c, cnld_hmat *h, const double *freqs, cnld_ui
     const double f = freqs[i], omega = H_TWO_PI * f;
     G.omega = omega;
     G.coef = -omega * omega * 2.0 * rho;
+    G.kwave = omega / cs;
+    G.fluid_precond = g_hsweep_fluid_precond;
     cudaEventRecord(e0, 0);
     if (f != 0.0 && hmat_assemble(0, h->H, omega / cs, 0.0, eps_aca)) { rc = -1; break; }
     if (G.setup_precond()) { rc = -1; break; }
