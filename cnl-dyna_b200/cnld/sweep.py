@@ -140,35 +140,62 @@ def broadcast_setup(setup, rank, device=None):
     return SweepSetup.unpack(out)
 
 
+def shard_cyclic(n, rank, world):
+    """Cyclic distribution of n jobs: indices rank, rank + world, ...  On the H-matrix path the cost
+    of a frequency grows with k (ACA ranks, GMRES iterations), so contiguous blocks of the sorted
+    frequency list would leave the rank with the highest block working long after the others."""
+    return np.arange(rank, n, world)
+
+
 def run_distributed(setup_or_none, freqs, rank, world, device=0, torch_device=None, nstreams=3,
-                    solver=None, symmetric=True):
-    """Block-distributed sweep: returns (x_patch[nf, P, P] on rank 0 else None, local seconds).
-    `solver(setup, freqs) -> x_patch[nf_local, P, P]` defaults to the GPU sweep; tests inject a
-    CPU stand-in to exercise the sharding / broadcast / gather logic under gloo."""
+                    solver=None, symmetric=True, method='dense', hmatrix=None, distribution=None):
+    """Distributed sweep: returns (x_patch[nf, P, P] on rank 0 else None, local seconds).
+    method 'dense' (LU, default) or 'hmatrix' (ACA H-matrix + GMRES, `hmatrix` = keyword arguments
+    of _lib.HMatrix / HMatrix.sweep).  distribution 'block' (default for dense) or 'cyclic' (default
+    for hmatrix).  No collective inside a frequency: one broadcast of the setup, one gather of the
+    patch responses.  `solver(setup, freqs) -> x_patch[nf_local, P, P]` replaces the GPU sweep; the
+    tests inject a CPU stand-in to exercise the sharding / broadcast / gather logic under gloo."""
     import torch
     import torch.distributed as dist
     freqs = np.asarray(freqs, dtype=np.float64)
     setup = broadcast_setup(setup_or_none, rank, torch_device) if world > 1 else setup_or_none
-    lo, hi = shard(len(freqs), rank, world)
-    if solver is None:
-        sw = FrequencySweep(setup, device=device, nstreams=nstreams, symmetric=symmetric)
-        xp, _, t = sw.run(freqs[lo:hi], want_nodes=False)
-        sw.close()
+    distribution = distribution or ('cyclic' if method == 'hmatrix' else 'block')
+    if distribution == 'cyclic':
+        owned = [shard_cyclic(len(freqs), r, world) for r in range(world)]
     else:
-        xp = solver(setup, freqs[lo:hi])
-        t = np.zeros(hi - lo)
+        owned = [np.arange(*shard(len(freqs), r, world)) for r in range(world)]
+    mine_idx = owned[rank]
+    if solver is not None:
+        xp = solver(setup, freqs[mine_idx])
+        t = np.zeros(len(mine_idx))
+    elif method == 'hmatrix':
+        kw = dict(hmatrix or {})
+        ctx = _lib.Context(setup.vertices, setup.triangles, q_reg=setup.q_reg, q_sing=setup.q_sing, device=device)
+        ctx.set_mbk(setup.K, setup.M, setup.B)
+        ctx.set_loads(setup.F, setup.AVG, setup.on_boundary)
+        H = _lib.HMatrix(ctx, **{k: kw.pop(k) for k in ('clf', 'eta', 'admis', 'strict', 'kmax') if k in kw})
+        xp, _, _, t = H.sweep(freqs[mine_idx], c=setup.c, rho=setup.rho, want_nodes=False, **kw)
+        H.close()
+        ctx.close()
+    else:
+        sw = FrequencySweep(setup, device=device, nstreams=nstreams, symmetric=symmetric)
+        xp, _, t = sw.run(freqs[mine_idx], want_nodes=False)
+        sw.close()
     if world == 1:
-        return xp, t
+        out = np.empty_like(xp)
+        out[mine_idx] = xp
+        return out, t
     P = setup.npatch
-    counts = [shard(len(freqs), r, world) for r in range(world)]
-    nmax = max(h - l for l, h in counts)
+    nmax = max(len(o) for o in owned)
     buf = np.zeros((nmax, P, P), dtype=np.complex128)
-    buf[:hi - lo] = xp
+    buf[:len(mine_idx)] = xp
     dev = torch_device if torch_device is not None else 'cpu'
     mine = torch.from_numpy(buf.view(np.float64)).to(dev)
     gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
     dist.gather(mine, gathered, dst=0)
     if rank != 0:
         return None, t
-    parts = [g.cpu().numpy().view(np.complex128)[:h - l] for g, (l, h) in zip(gathered, counts)]
-    return np.concatenate(parts, axis=0), t
+    out = np.empty((len(freqs), P, P), dtype=np.complex128)
+    for g, o in zip(gathered, owned):
+        out[o] = g.cpu().numpy().view(np.complex128)[:len(o)]
+    return out, t

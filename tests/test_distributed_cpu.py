@@ -47,9 +47,11 @@ def _worker(rank, world, port, q):
     freqs = np.array([0.5e6, 1e6, 3e6, 7e6, 11e6])
     setup = SweepSetup.from_abstract(arrays.matrix_array(nelem=(1, 1)), 3) if rank == 0 else None
     xp, _ = run_distributed(setup, freqs, rank, world, solver=_solver)
+    xc, _ = run_distributed(setup, freqs, rank, world, solver=_solver, distribution='cyclic')   # H-path default
     if rank == 0:
         ref = _solver(setup, freqs)
-        q.put((np.abs(xp - ref).max() / np.abs(ref).max(), xp.shape, [shard(5, r, world) for r in range(world)]))
+        err = max(np.abs(xp - ref).max(), np.abs(xc - ref).max()) / np.abs(ref).max()
+        q.put((err, xp.shape, [shard(5, r, world) for r in range(world)]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -63,6 +65,15 @@ def test_shard_is_a_block_partition():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
             sizes = [h - l for l, h in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_cyclic_shard_is_a_partition():
+    from cnld.sweep import shard_cyclic
+    for n in (0, 1, 5, 16, 501):
+        for w in (1, 2, 3, 8):
+            parts = [shard_cyclic(n, r, w) for r in range(w)]
+            assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
 
 
 def test_two_rank_gloo_sweep_matches_single_process():

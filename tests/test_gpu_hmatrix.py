@@ -120,3 +120,18 @@ def test_batched_matvec_equals_single_vector_and_dense(L, po, nrhs):
     assert _rel(H.matvec(X), H.todense() @ X) < 1e-13
     H.close()
     ctx.close()
+
+
+def test_run_distributed_hmatrix_method_single_rank():
+    """The sweep driver's H-matrix method (cyclic frequency distribution, ACA + GMRES per frequency)
+    against its dense-LU method on the same frequencies."""
+    from cnld import arrays
+    from cnld.sweep import SweepSetup, run_distributed
+    setup = SweepSetup.from_abstract(arrays.matrix_array(nelem=(2, 2)), 5)
+    freqs = np.array([0.0, 2e6, 9e6, 23e6, 41e6])
+    xd, _ = run_distributed(setup, freqs, 0, 1)
+    xh, _ = run_distributed(setup, freqs, 0, 1, method='hmatrix',
+                            hmatrix=dict(eps_aca=1e-7, tol=1e-10, batch=16, restart=60, maxiter=400))
+    assert xd.shape == xh.shape == (5, setup.npatch, setup.npatch)
+    for i in range(len(freqs)):
+        assert _rel(xh[i], xd[i]) < 1e-5, (freqs[i], _rel(xh[i], xd[i]))
