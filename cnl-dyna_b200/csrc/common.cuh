@@ -93,6 +93,9 @@ struct ZBatch {
 int zgemm_batched(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
                   const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, uint nbatch, const ZBatch &bt);
 
+int zgemm3m_batched(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
+                    const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, uint nbatch, const ZBatch &bt);
+
 struct LuWork {
   uint n = 0, nb = 0, nblk = 0, nouter = 0, nbo = 0;
   // inverses of the full nbo x nbo diagonal blocks of L and R (lu_invert_outer), used by lu_solve

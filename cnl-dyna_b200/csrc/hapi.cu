@@ -216,7 +216,7 @@ struct Gmres {
       ZBatch bt;
       bt.per = R.count;
       bt.sBj = sz; bt.sCj = sz;   // operand A (the block) is shared by the run
-      if (zgemm_batched(st, sz, nr, sz, 1.0, mats[blk.type[b]], sz, x + blk.r0[b], n, 0.0, y + blk.r0[b], n, R.count, bt))
+      if (zgemm3m_batched(st, sz, nr, sz, 1.0, mats[blk.type[b]], sz, x + blk.r0[b], n, 0.0, y + blk.r0[b], n, R.count, bt))
         return -1;
     }
     return 0;

@@ -177,9 +177,10 @@ constexpr int T3_A_STAGE = BK * T3_AS_LD, T3_B_STAGE = T3_BN * BS_LD;
 constexpr int T3_SMEM = T3_STAGES * (T3_A_STAGE + T3_B_STAGE) * (int)sizeof(cplx);
 
 __global__ void __launch_bounds__(T3_NT, 2)
-zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A, size_t lda,
-               const cplx *__restrict__ B, size_t ldb, double beta, cplx *C, size_t ldc, int lower_only,
-               uint ntiles) {
+zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A0, size_t lda,
+               const cplx *__restrict__ B0, size_t ldb, double beta, cplx *C0, size_t ldc, int lower_only,
+               uint ntiles1, uint nbatch, const ZBatch bt) {
+  const uint ntiles = ntiles1 * nbatch;   // batch item q owns tiles [q * ntiles1, (q + 1) * ntiles1)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx *As = reinterpret_cast<cplx *>(smem_raw);
   cplx *Bs = As + T3_STAGES * T3_A_STAGE;
@@ -197,6 +198,7 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
 
   // tile index -> (m0, n0); false for a tile that lies entirely above the diagonal (lower_only)
   auto coords = [&](uint tile, uint &m0, uint &n0) -> bool {
+    tile %= ntiles1;
     uint first, gm, within;
     if (!lower_only) {
       const uint grp = tile / gsz_full;
@@ -222,7 +224,11 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
     return !(lower_only && m0 + T3_BM <= n0);
   };
 
-  auto load_stage = [&](uint m0, uint n0, int kc, int stage) {
+  auto batch_off = [&](uint tile, long long sa, long long sb) -> long long {
+    const uint q = tile / ntiles1;
+    return (long long)(q / bt.per) * sa + (long long)(q % bt.per) * sb;
+  };
+  auto load_stage = [&](const cplx *__restrict__ A, const cplx *__restrict__ B, uint m0, uint n0, int kc, int stage) {
     const uint k0 = kc * BK;
     cplx *as = As + stage * T3_A_STAGE;
     cplx *bs = Bs + stage * T3_B_STAGE;
@@ -243,10 +249,10 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
       cp_async16(bs + j * BS_LD + kb, src, ok);
     }
   };
-  auto prologue = [&](uint m0, uint n0) {
+  auto prologue = [&](const cplx *A, const cplx *B, uint m0, uint n0) {
 #pragma unroll
     for (int s = 0; s < T3_STAGES - 1; s++) {
-      if (s < nk) load_stage(m0, n0, s, s);
+      if (s < nk) load_stage(A, B, m0, n0, s, s);
       cp_async_commit();
     }
   };
@@ -254,8 +260,10 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
   uint tile = blockIdx.x, m0 = 0, n0 = 0;
   while (tile < ntiles && !coords(tile, m0, n0)) tile += gridDim.x;
   if (tile >= ntiles) return;
-  prologue(m0, n0);
+  const cplx *A = A0 + batch_off(tile, bt.sAo, bt.sAj), *B = B0 + batch_off(tile, bt.sBo, bt.sBj);
+  prologue(A, B, m0, n0);
   for (;;) {
+  cplx *C = C0 + batch_off(tile, bt.sCo, bt.sCj);
   // the C tile is read ~70 us from now: pull its 384 lines into L2 while the main loop runs
   if (beta != 0.0) {
 #pragma unroll
@@ -277,7 +285,7 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
     __syncthreads();
     {
       int nx = kc + T3_STAGES - 1;
-      if (nx < nk) load_stage(m0, n0, nx, nx % T3_STAGES);
+      if (nx < nk) load_stage(A, B, m0, n0, nx, nx % T3_STAGES);
       cp_async_commit();
     }
     const cplx *as = As + (kc % T3_STAGES) * T3_A_STAGE + wm * 32 + fr;
@@ -314,7 +322,12 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
   uint ntile = tile + gridDim.x, nm0 = 0, nn0 = 0;
   while (ntile < ntiles && !coords(ntile, nm0, nn0)) ntile += gridDim.x;
   const bool more = ntile < ntiles;
-  if (more) prologue(nm0, nn0);
+  const cplx *An = A, *Bn = B;
+  if (more) {
+    An = A0 + batch_off(ntile, bt.sAo, bt.sAj);
+    Bn = B0 + batch_off(ntile, bt.sBo, bt.sBj);
+    prologue(An, Bn, nm0, nn0);
+  }
 #pragma unroll
   for (int mh = 0; mh < 2; mh++) {
     cplx old[2][3][2];
@@ -347,16 +360,16 @@ zgemm3m_kernel(uint M, uint N, uint K, double alpha, const cplx *__restrict__ A,
     }
   }
   if (!more) break;
-  tile = ntile; m0 = nm0; n0 = nn0;
+  tile = ntile; m0 = nm0; n0 = nn0; A = An; B = Bn;
   }  // tile loop
 }
 }  // namespace
 
 int g_zgemm_3m = 1;  // use the 3M kernel for non-aliased accumulating products
 
-int zgemm3m(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
-            const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, int reserve_sms, bool lower_only,
-            double *entries) {
+static int zgemm3m_impl(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
+                        const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, int reserve_sms, bool lower_only,
+                        double *entries, uint nbatch, const ZBatch &bt) {
   double cnt = (double)M * N;
   if (lower_only) {
     cnt = 0.0;
@@ -369,8 +382,8 @@ int zgemm3m(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A
   }
   if (entries) *entries = cnt;
   if (M == 0 || N == 0) return 0;
-  if (!g_zgemm_3m) return zgemm(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-  g_dmma_flops.fetch_add((unsigned long long)(6.0 * cnt * K), std::memory_order_relaxed);
+  if (!g_zgemm_3m) return zgemm_batched(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, nbatch, bt);
+  g_dmma_flops.fetch_add((unsigned long long)(6.0 * cnt * K * nbatch), std::memory_order_relaxed);
   static bool attr_set[64] = {false};
   int dev = 0;
   CNLD_CK(cudaGetDevice(&dev));
@@ -392,10 +405,24 @@ int zgemm3m(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A
   // reserve_sms: leave that many SMs without a CTA of this (persistent) kernel, for concurrent
   // latency-bound kernels on another stream
   const int use_sms = std::max(1, nsm[dev & 63] - std::max(0, reserve_sms));
-  dim3 grid(std::min(tiles, (uint)(2 * use_sms)));
-  zgemm3m_kernel<<<grid, T3_NT, T3_SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower_only ? 1 : 0, tiles);
+  dim3 grid(std::min(tiles * nbatch, (uint)(2 * use_sms)));
+  zgemm3m_kernel<<<grid, T3_NT, T3_SMEM, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower_only ? 1 : 0, tiles,
+                                               nbatch, bt);
   CNLD_CK_LAUNCH();
   return 0;
+}
+
+int zgemm3m(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
+            const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, int reserve_sms, bool lower_only,
+            double *entries) {
+  return zgemm3m_impl(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, reserve_sms, lower_only, entries, 1, ZBatch());
+}
+
+// batched 3M product (C must not alias A or B)
+int zgemm3m_batched(cudaStream_t st, uint M, uint N, uint K, double alpha, const cplx *A, size_t lda,
+                    const cplx *B, size_t ldb, double beta, cplx *C, size_t ldc, uint nbatch, const ZBatch &bt) {
+  if (!nbatch) return 0;
+  return zgemm3m_impl(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 0, false, nullptr, nbatch, bt);
 }
 
 namespace {
