@@ -272,7 +272,6 @@ k_aca(HLeafDev *leaves, const uint *__restrict__ far_ids, const __grid_constant_
 }
 
 // ---- matvec: y_perm += alpha * Z * x_perm over the leaves --------------------------------
-constexpr int MV_THREADS = 128;
 
 __global__ void k_permute_in(uint n, uint nrhs, const uint *__restrict__ perm, const cplx *__restrict__ x,
                              cplx *xp) {
@@ -290,50 +289,6 @@ __global__ void k_permute_out(uint n, uint nrhs, const uint *__restrict__ perm, 
   cplx *d = y + (size_t)r * n + perm[p];
   d->x += v.x;
   d->y += v.y;
-}
-
-// one CTA per leaf; vectors in cluster order, nrhs right-hand sides (stride n)
-__global__ void __launch_bounds__(MV_THREADS)
-k_hmv_leaf(const HLeafDev *__restrict__ leaves, uint ntot, const cplx *__restrict__ pool, const cplx *__restrict__ xp,
-           cplx *yp, uint nrhs) {
-  __shared__ cplx s_t[64];
-  const HLeafDev L = leaves[blockIdx.x];
-  const cplx *base = pool + L.off;
-  for (uint r = 0; r < nrhs; r++) {
-    const cplx *x = xp + (size_t)r * ntot + L.c0;
-    cplx *y = yp + (size_t)r * ntot + L.r0;
-    if (!L.adm) {
-      for (uint i = threadIdx.x; i < L.m; i += MV_THREADS) {
-        cplx s = make_double2(0.0, 0.0);
-        for (uint j = 0; j < L.n; j++) cfma(s, base[(size_t)j * L.m + i], x[j]);
-        red_add(y + i, s);
-      }
-    } else {
-      const cplx *U = base, *V = base + (size_t)L.m * L.kcap;
-      for (uint l0 = 0; l0 < L.k; l0 += 64) {
-        const uint kk = min(64u, L.k - l0);
-        __syncthreads();
-        // t[l] = V[:, l] . x  -- one warp per column l
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (uint l = warp; l < kk; l += MV_THREADS / 32) {
-          cplx s = make_double2(0.0, 0.0);
-          const cplx *v = V + (size_t)(l0 + l) * L.n;
-          for (uint j = lane; j < L.n; j += 32) cfma(s, v[j], x[j]);
-          for (int off = 16; off > 0; off >>= 1) {
-            s.x += __shfl_xor_sync(0xffffffffu, s.x, off);
-            s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
-          }
-          if (lane == 0) s_t[l] = s;
-        }
-        __syncthreads();
-        for (uint i = threadIdx.x; i < L.m; i += MV_THREADS) {
-          cplx s = make_double2(0.0, 0.0);
-          for (uint l = 0; l < kk; l++) cfma(s, U[(size_t)(l0 + l) * L.m + i], s_t[l]);
-          red_add(y + i, s);
-        }
-      }
-    }
-  }
 }
 
 // ---- batched matvec (several right-hand sides) ----------------------------------------------------
@@ -518,6 +473,83 @@ k_hmv_gemm(const uint *__restrict__ band_ptr, const HMat::DRound *__restrict__ d
             if (b0 + i < ntot && r < nrhs) yp[(size_t)r * ntot + b0 + i] = v;
           }
         }
+  }
+}
+
+// ---- matvec with 1-3 vectors: HBM-bound, so the kernels only have to read every leaf once, coalesced ----
+// t-pass: one warp per low-rank leaf, lanes along the columns (V[:, l] is contiguous), shuffle reduction.
+constexpr int V1_THREADS = 128;
+template <int NR>
+__global__ void __launch_bounds__(V1_THREADS)
+k_hmv1_t(uint nfar, const uint *__restrict__ far_ids, const HLeafDev *__restrict__ leaves,
+         const unsigned long long *__restrict__ toff, const cplx *__restrict__ pool, const cplx *__restrict__ xp,
+         cplx *T, uint ntot) {
+  const uint w = (blockIdx.x * V1_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= nfar) return;
+  const uint id = far_ids[w];
+  const HLeafDev L = leaves[id];
+  const cplx *V = pool + L.off + (size_t)L.m * L.kcap;
+  const cplx *x = xp + L.c0;
+  cplx *Tl = T + toff[id] * NR;
+  for (uint l = 0; l < L.k; l++) {
+    cplx s[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) s[r] = make_double2(0.0, 0.0);
+    const cplx *v = V + (size_t)l * L.n;
+    for (uint j = lane; j < L.n; j += 32) {
+      const cplx a = v[j];
+#pragma unroll
+      for (int r = 0; r < NR; r++) cfma(s[r], a, x[(size_t)r * ntot + j]);
+    }
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      for (int off = 16; off > 0; off >>= 1) {
+        s[r].x += __shfl_xor_sync(0xffffffffu, s[r].x, off);
+        s[r].y += __shfl_xor_sync(0xffffffffu, s[r].y, off);
+      }
+      if (lane == 0) Tl[(size_t)l * NR + r] = s[r];
+    }
+  }
+}
+
+// y-pass: one warp per band of 16 rows; lane = (row, parity of the contraction index): a column of a
+// leaf's 16 band rows is 256 contiguous bytes, two columns per warp load.
+template <int NR>
+__global__ void __launch_bounds__(V1_THREADS)
+k_hmv1_band(uint nband, const uint *__restrict__ band_ptr, const HMat::DRound *__restrict__ dround,
+            const uint *__restrict__ bfar_ptr, const HMat::FarItem *__restrict__ bfar, const cplx *__restrict__ pool,
+            const cplx *__restrict__ T, const cplx *__restrict__ xp, cplx *yp, uint ntot) {
+  const uint b = (blockIdx.x * V1_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= nband) return;
+  const uint i = lane & 15, h = lane >> 4;
+  const long long row = (long long)b * BAND + i;
+  cplx acc[NR];
+#pragma unroll
+  for (int r = 0; r < NR; r++) acc[r] = make_double2(0.0, 0.0);
+  for (uint d = band_ptr[b]; d < band_ptr[b + 1]; d++) {
+    const HMat::DRound D = dround[d];
+    const long long rl = row - (long long)D.r0;
+    const bool ok = rl >= 0 && rl < (long long)D.m;
+    const cplx *col = pool + D.a_off + (ok ? rl : 0);
+    const cplx *x = xp + D.x_off;
+    for (uint j = h; j < D.cnt; j += 2) {
+      const cplx a = ok ? col[(size_t)j * D.m] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int r = 0; r < NR; r++) cfma(acc[r], a, x[(size_t)r * ntot + j]);
+    }
+  }
+  for (uint f = bfar_ptr[b] + h; f < bfar_ptr[b + 1]; f += 2) {
+    const HMat::FarItem it = bfar[f];
+    const long long rl = row - (long long)it.r0;
+    const cplx a = (rl >= 0 && rl < (long long)it.m) ? pool[it.u_off + rl] : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int r = 0; r < NR; r++) cfma(acc[r], a, T[(size_t)it.t_idx * NR + r]);
+  }
+#pragma unroll
+  for (int r = 0; r < NR; r++) {
+    acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, 16);
+    acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, 16);
+    if (h == 0 && row < (long long)ntot) yp[(size_t)r * ntot + row] = acc[r];
   }
 }
 
@@ -825,11 +857,39 @@ int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y
     CNLD_CK_LAUNCH();
     return 0;
   }
+  // 1-3 vectors: every leaf is read once, coalesced (HBM-bound)
+  if (!H.mv_ready) {
+    CNLD_CK(cudaStreamSynchronize(st));
+    if (hmat_prepare_batched(H, H.bem != nullptr)) return -1;
+  }
+  {
+    const size_t need = (size_t)H.ksum * nrhs;
+    if (H.T_cap < need) {
+      CNLD_CK(cudaStreamSynchronize(st));
+      cudaFree(H.d_T);
+      H.d_T = nullptr;
+      CNLD_CK(cudaMalloc(&H.d_T, sizeof(cplx) * (need ? need : 1)));
+      H.T_cap = need;
+    }
+  }
   k_permute_in<<<gb, 256, 0, st>>>(H.n, nrhs, H.d_perm, d_x, H.d_xp);
   CNLD_CK_LAUNCH();
-  CNLD_CK(cudaMemsetAsync(H.d_yp, 0, sizeof(cplx) * tot, st));
-  k_hmv_leaf<<<(unsigned)H.leaf.size(), MV_THREADS, 0, st>>>(H.d_leaf, H.n, H.d_pool, H.d_xp, H.d_yp, nrhs);
-  CNLD_CK_LAUNCH();
+  const unsigned gt = (unsigned)(((size_t)H.nmvfar * 32 + V1_THREADS - 1) / V1_THREADS);
+  const unsigned gy = (unsigned)(((size_t)H.nband * 32 + V1_THREADS - 1) / V1_THREADS);
+#define CNLD_HMV1(NRV)                                                                                             \
+  do {                                                                                                             \
+    if (H.nmvfar) {                                                                                                \
+      k_hmv1_t<NRV><<<gt, V1_THREADS, 0, st>>>(H.nmvfar, H.d_mvfar, H.d_leaf, H.d_toff, H.d_pool, H.d_xp, H.d_T, H.n); \
+      CNLD_CK_LAUNCH();                                                                                            \
+    }                                                                                                              \
+    k_hmv1_band<NRV><<<gy, V1_THREADS, 0, st>>>(H.nband, H.d_band_ptr, H.d_dround, H.d_bfar_ptr, H.d_bfar, H.d_pool,  \
+                                                H.d_T, H.d_xp, H.d_yp, H.n);                                       \
+    CNLD_CK_LAUNCH();                                                                                              \
+  } while (0)
+  if (nrhs == 1) CNLD_HMV1(1);
+  else if (nrhs == 2) CNLD_HMV1(2);
+  else CNLD_HMV1(3);
+#undef CNLD_HMV1
   k_permute_out<<<gb, 256, 0, st>>>(H.n, nrhs, H.d_perm, alpha, H.d_yp, d_y);
   CNLD_CK_LAUNCH();
   return 0;
