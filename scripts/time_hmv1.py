@@ -6,7 +6,7 @@ nelem = (16, 16) if len(sys.argv) < 2 else (int(sys.argv[1]),) * 2
 am = mesh.Mesh.from_abstract(arrays.matrix_array(nelem=nelem), 19 if nelem[0] == 16 else 15)
 n = am.nvertices
 ctx = _lib.Context(np.array(am.vertices), np.array(am.triangles))
-H = _lib.HMatrix(ctx, clf=16, eta=0.8, strict=True, kmax=64)
+H = _lib.HMatrix(ctx, clf=16, eta=0.8, strict=True, kmax=int(sys.argv[2]) if len(sys.argv) > 2 else 64)
 H.assemble(2 * np.pi * 5e6 / 1500, 1e-2)
 info = H.info()
 rng = np.random.default_rng(0)
