@@ -303,6 +303,13 @@ class HMatrix:
         keys = ('clusters', 'leaves', 'admissible', 'inadmissible', 'capacity', 'stored', 'maxrank', 'n')
         return {k: int(v) for k, v in zip(keys, out)}
 
+    def sharing(self):
+        out = np.zeros(4)
+        f = lib().cnld_b200_hmat_sharing
+        f.argtypes = [vp, vp]
+        check(f(self._h, ptr(out)))
+        return dict(zip(('assembled_admissible', 'assembled_inadmissible', 'shared', 'pool_entries'), (int(v) for v in out)))
+
     def tree(self):
         i = self.info()
         ncl, nl, n = i['clusters'], i['leaves'], i['n']

@@ -453,8 +453,17 @@ int cnld_b200_hmat_info(cnld_hmat *h, double *out) {
     for (auto &L : H.leaf)
       if (L.adm) { used += (double)L.k * (L.m + L.n); maxrank = std::max(maxrank, (double)L.k); }
   }
-  out[0] = (double)H.tree.node.size(); out[1] = (double)H.leaf.size(); out[2] = H.nfar; out[3] = H.nnear;
+  double nadm = 0, ninadm = 0;
+  for (auto &L : H.leaf) (L.adm ? nadm : ninadm) += 1.0;
+  out[0] = (double)H.tree.node.size(); out[1] = (double)H.leaf.size(); out[2] = nadm; out[3] = ninadm;
   out[4] = (double)H.pool_size; out[5] = used; out[6] = maxrank; out[7] = H.n;
+  return 0;
+}
+
+int cnld_b200_hmat_sharing(cnld_hmat *h, double *out) {
+  if (!h) { set_error("null H-matrix"); return -1; }
+  HMat &H = h->H;
+  out[0] = H.nfar; out[1] = H.nnear; out[2] = (double)H.leaf.size() - H.nfar - H.nnear; out[3] = (double)H.pool_size;
   return 0;
 }
 

@@ -48,11 +48,17 @@ struct HMat {
   cplx *d_T = nullptr;
   size_t T_cap = 0;
   bool mv_ready = false;
+  // translation classes: leaf `dup[2i]` shares the pool data (and, after assembly, the rank) of leaf `dup[2i+1]`
+  uint ndup = 0;
+  uint *d_dup = nullptr;
+  size_t unique_entries = 0;   // pool entries actually stored / assembled
 };
 
 struct LeafRange { uint r0, m, c0, n; bool admissible; };
+// hx (optional): host vertex coordinates; with them, and a mesh that is translated copies of one
+// component (bem.periodic), leaves that are translates of an earlier leaf share its pool data
 int hmat_create_from_ranges(HMat &H, const BemDev &bem, const uint *htri, const std::vector<uint> &perm,
-                            const std::vector<LeafRange> &ranges, uint kmax);
+                            const std::vector<LeafRange> &ranges, uint kmax, const double *hx = nullptr);
 int hmat_from_host(HMat &H, int device, uint n, const std::vector<uint> &perm, const std::vector<HLeafDev> &leaf,
                    const std::vector<cplx> &pool);
 int hmat_create(HMat &H, const BemDev &bem, const double *hx, const uint *htri, uint clf, double eta, int admis,

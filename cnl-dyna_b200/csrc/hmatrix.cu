@@ -16,6 +16,8 @@
 //             entry, from the vertex -> triangle fans with the regular rule.
 //   k_hmv_* : leaf-parallel matvec, HBM-bound streaming of the pool.
 #include "hmat.cuh"
+#include <unordered_map>
+#include <cmath>
 
 #include <algorithm>
 #include <map>
@@ -593,12 +595,69 @@ int hmat_create(HMat &H, const BemDev &bem, const double *hx, const uint *htri, 
     const ClusterNode &Rn = H.tree.node[B.rc], &Cn = H.tree.node[B.cc];
     ranges.push_back({Rn.start, Rn.size, Cn.start, Cn.size, B.admissible});
   }
-  return hmat_create_from_ranges(H, bem, htri, H.tree.perm, ranges, kmax);
+  return hmat_create_from_ranges(H, bem, htri, H.tree.perm, ranges, kmax, hx);
 }
 
 // leaves given as (row range, column range) of the permutation `perm` (cluster order -> DOF)
+// Translation classes of the leaves.  The mesh is ncomp translated copies of one component (periodic.h) and
+// the kernel depends on x - y only, so a leaf whose row and column vertices are the translates -- by one
+// common lattice vector, in the same cluster order -- of another leaf's holds the same block.  Key of a
+// leaf: for every row and column vertex (local vertex id, quantised offset of its component relative to
+// the component of the first row vertex).  Leaves are matched by a 64-bit hash of the key and then
+// compared element by element; rep[b] = first leaf with the same key.
+static void leaf_translation_classes(const BemDev &bem, const double *hx, const std::vector<uint> &perm,
+                                     const std::vector<LeafRange> &ranges, std::vector<uint> &rep) {
+  rep.resize(ranges.size());
+  for (size_t b = 0; b < ranges.size(); b++) rep[b] = (uint)b;
+  if (!hx || !bem.periodic || !bem.use_periodic || bem.ncomp < 2) return;
+  const uint nvc = bem.plan[1].blk, nc = bem.ncomp;
+  double maxabs = 0.0;
+  for (size_t i = 0; i < 3 * (size_t)bem.nv; i++) maxabs = std::max(maxabs, std::fabs(hx[i]));
+  const double quantum = 1e-7 * (maxabs > 0.0 ? maxabs : 1.0);   // lattice offsets differ by far more, rounding by far less
+  std::vector<long long> q(3 * (size_t)nc);
+  for (uint c = 0; c < nc; c++)
+    for (int d = 0; d < 3; d++) q[3 * c + d] = std::llround((hx[3 * (size_t)(c * nvc) + d] - hx[d]) / quantum);
+  auto key_elem = [&](uint v, uint a0, int d) -> long long {   // d = 0..2: offset components, 3: local id
+    const uint c = v / nvc;
+    return d == 3 ? (long long)(v % nvc) : q[3 * c + d] - q[3 * a0 + d];
+  };
+  auto hash_leaf = [&](const LeafRange &B) -> unsigned long long {
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](long long x) { h = (h ^ (unsigned long long)x) * 1099511628211ull; };
+    mix(B.m); mix(B.n); mix(B.admissible ? 1 : 0);
+    const uint a0 = perm[B.r0] / nvc;
+    for (uint i = 0; i < B.m; i++) for (int d = 0; d < 4; d++) mix(key_elem(perm[B.r0 + i], a0, d));
+    for (uint i = 0; i < B.n; i++) for (int d = 0; d < 4; d++) mix(key_elem(perm[B.c0 + i], a0, d));
+    return h;
+  };
+  auto same = [&](const LeafRange &A, const LeafRange &B) -> bool {
+    if (A.m != B.m || A.n != B.n || A.admissible != B.admissible) return false;
+    const uint a0 = perm[A.r0] / nvc, b0 = perm[B.r0] / nvc;
+    for (uint i = 0; i < A.m; i++) for (int d = 0; d < 4; d++)
+      if (key_elem(perm[A.r0 + i], a0, d) != key_elem(perm[B.r0 + i], b0, d)) return false;
+    for (uint i = 0; i < A.n; i++) for (int d = 0; d < 4; d++)
+      if (key_elem(perm[A.c0 + i], a0, d) != key_elem(perm[B.c0 + i], b0, d)) return false;
+    return true;
+  };
+  std::unordered_map<unsigned long long, std::vector<uint>> seen;
+  seen.reserve(ranges.size() / 4 + 16);
+  for (size_t b = 0; b < ranges.size(); b++) {
+    if (!ranges[b].m || !ranges[b].n) continue;
+    std::vector<uint> &cand = seen[hash_leaf(ranges[b])];
+    bool found = false;
+    for (uint r : cand)
+      if (same(ranges[r], ranges[b])) { rep[b] = r; found = true; break; }
+    if (!found) cand.push_back((uint)b);
+  }
+}
+
+__global__ void k_copy_ranks(uint ndup, const uint *__restrict__ dup, HLeafDev *leaves) {
+  const uint i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ndup) leaves[dup[2 * i]].k = leaves[dup[2 * i + 1]].k;
+}
+
 int hmat_create_from_ranges(HMat &H, const BemDev &bem, const uint *htri, const std::vector<uint> &perm,
-                            const std::vector<LeafRange> &ranges, uint kmax) {
+                            const std::vector<LeafRange> &ranges, uint kmax, const double *hx) {
   H.bem = &bem;
   H.n = bem.nv;
   H.kmax = kmax;
@@ -633,7 +692,8 @@ int hmat_create_from_ranges(HMat &H, const BemDev &bem, const uint *htri, const 
     return id;
   };
   H.leaf.clear();
-  std::vector<uint> near_ids, far_ids;
+  std::vector<uint> near_ids, far_ids, rep, dup;
+  leaf_translation_classes(bem, hx, H.tree.perm, ranges, rep);
   size_t off = 0, foff = 0;
   for (size_t b = 0; b < ranges.size(); b++) {
     const LeafRange &B = ranges[b];
@@ -641,6 +701,13 @@ int hmat_create_from_ranges(HMat &H, const BemDev &bem, const uint *htri, const 
     memset(&L, 0, sizeof(L));
     L.r0 = B.r0; L.m = B.m; L.c0 = B.c0; L.n = B.n;
     L.adm = B.admissible ? 1 : 0;
+    if (rep[b] != b) {   // translate of an earlier leaf: same data, nothing to assemble
+      const HLeafDev &Rp = H.leaf[rep[b]];
+      L.off = Rp.off; L.kcap = Rp.kcap; L.foff = Rp.foff; L.rtl = Rp.rtl; L.ctl = Rp.ctl;
+      if (L.adm) { dup.push_back((uint)b); dup.push_back(rep[b]); }
+      H.leaf.push_back(L);
+      continue;
+    }
     L.off = off;
     if (B.admissible) {
       L.kcap = std::min(std::min(L.m, L.n), kmax);
@@ -659,8 +726,10 @@ int hmat_create_from_ranges(HMat &H, const BemDev &bem, const uint *htri, const 
   H.pool_size = off;
   H.nnear = (uint)near_ids.size();
   H.nfar = (uint)far_ids.size();
-  H.near_entries = 0;
-  for (uint b : near_ids) H.near_entries += (size_t)H.leaf[b].m * H.leaf[b].n;
+  H.near_entries = 0;   // logical entries (every leaf, shared or not)
+  for (const HLeafDev &L : H.leaf) if (!L.adm) H.near_entries += (size_t)L.m * L.n;
+  H.ndup = (uint)(dup.size() / 2);
+  if (to_device(H.d_dup, dup)) return -1;
   CNLD_CK(cudaSetDevice(bem.device));
   if (to_device(H.d_leaf, H.leaf) || to_device(H.d_near, near_ids) || to_device(H.d_far, far_ids) ||
       to_device(H.d_perm, H.tree.perm) || to_device(H.d_pos, H.tree.pos) || to_device(H.d_ctri_ptr, ctri_ptr) ||
@@ -751,7 +820,7 @@ int hmat_prepare_batched(HMat &H, bool fetch) {
 
 void hmat_free(HMat &H) {
   cudaFree(H.d_band_ptr); cudaFree(H.d_dround); cudaFree(H.d_mvfar); cudaFree(H.d_toff); cudaFree(H.d_T);
-  cudaFree(H.d_bfar_ptr); cudaFree(H.d_bfar);
+  cudaFree(H.d_bfar_ptr); cudaFree(H.d_bfar); cudaFree(H.d_dup);
   cudaFree(H.d_leaf); cudaFree(H.d_near); cudaFree(H.d_far); cudaFree(H.d_perm); cudaFree(H.d_pos);
   cudaFree(H.d_ctri_ptr); cudaFree(H.d_ctri); cudaFree(H.d_v2t_ptr); cudaFree(H.d_v2t); cudaFree(H.d_pool);
   cudaFree(H.d_flags); cudaFree(H.d_err); cudaFree(H.d_xp); cudaFree(H.d_yp); cudaFree(H.d_cpos);
@@ -795,6 +864,10 @@ int hmat_assemble(cudaStream_t st, HMat &H, double kr, double ki, double accur) 
   default: set_error("H-matrix path supports q_reg <= 3"); return -1;
   }
   if (rc) return rc;
+  if (H.ndup) {   // translates take the rank of the leaf whose data they share
+    k_copy_ranks<<<(H.ndup + 255) / 256, 256, 0, st>>>(H.ndup, H.d_dup, H.d_leaf);
+    CNLD_CK_LAUNCH();
+  }
   uint err = 0;
   CNLD_CK(cudaMemcpyAsync(&err, H.d_err, sizeof(uint), cudaMemcpyDeviceToHost, st));
   CNLD_CK(cudaStreamSynchronize(st));

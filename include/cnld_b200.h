@@ -206,6 +206,12 @@ void cnld_b200_hmat_destroy(cnld_hmat *h);
 /* out[8]: clusters, leaves, admissible leaves, inadmissible leaves, pool capacity (entries),
  * stored entries (dense + k(m+n), after assembly), max rank, n */
 int cnld_b200_hmat_info(cnld_hmat *h, double *out);
+/* Translation classes of the leaves (mesh = translated copies of one membrane, see
+ * cnld_b200_set_translation_classes): a leaf whose row and column vertices are the translates, by one
+ * common lattice vector and in the same cluster order, of an earlier leaf's shares that leaf's data and
+ * is not assembled.  out[4]: admissible leaves assembled, inadmissible leaves assembled, leaves sharing
+ * another leaf's data, pool capacity actually allocated (entries). */
+int cnld_b200_hmat_sharing(cnld_hmat *h, double *out);
 /* tree export (any pointer may be NULL): perm[n] (cluster order -> DOF), per cluster son0/son1
  * (-1 = leaf), start/size into perm, bmin/bmax[.][3]; per leaf row/col cluster, admissibility, rank */
 int cnld_b200_hmat_tree(cnld_hmat *h, cnld_uint *perm, int *son0, int *son1, cnld_uint *start,

@@ -55,6 +55,7 @@ def hscale(nelem, refn, eps=1e-2):
     H.assemble(k, eps)
     t_asm = time.perf_counter() - t0
     info = H.info()
+    info['sharing'] = H.sharing()
     rng = np.random.default_rng(0)
     x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
     H.matvec(x)
