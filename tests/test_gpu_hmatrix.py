@@ -135,3 +135,29 @@ def test_run_distributed_hmatrix_method_single_rank():
     assert xd.shape == xh.shape == (5, setup.npatch, setup.npatch)
     for i in range(len(freqs)):
         assert _rel(xh[i], xd[i]) < 1e-5, (freqs[i], _rel(xh[i], xd[i]))
+
+
+def test_leaf_translation_classes(L, po):
+    """Leaves that are translates of an earlier leaf share its data: the expanded matrix must equal the
+    one assembled leaf by leaf, and a real fraction of the leaves must be shared on a membrane array."""
+    arr = po.matrix_array(nelem=(4, 4))    # 2^k membranes per side: the bisection planes fall between membranes
+    am = po.array_mesh(arr, 5)
+    k = 2 * np.pi * 8e6 / 1500
+    dense = {}
+    for on in (False, True):
+        ctx = L.Context(am.vertices, am.triangles)
+        ctx.set_translation_classes(on)
+        H = L.HMatrix(ctx, clf=16, eta=0.8, strict=True, kmax=64)
+        H.assemble(k, 1e-9)
+        sh, info = H.sharing(), H.info()
+        assert sh['assembled_admissible'] + sh['assembled_inadmissible'] + sh['shared'] == info['leaves']
+        assert (sh['shared'] > info['leaves'] // 10) if on else (sh['shared'] == 0), (on, sh, info['leaves'])
+        dense[on] = H.todense()
+        if on:
+            x = np.random.default_rng(0).standard_normal((am.nvertices, 7)) + 0j
+            assert _rel(H.matvec(x), dense[on] @ x) < 1e-13
+        H.close()
+        ctx.close()
+    assert _rel(dense[True], dense[False]) < 1e-8
+    Z = po.assemble_z(am, k)
+    assert _rel(dense[True], Z) < 1e-7
