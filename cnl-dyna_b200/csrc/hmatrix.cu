@@ -308,6 +308,25 @@ __global__ void k_permute_out(uint n, uint nrhs, const uint *__restrict__ perm, 
 // (ncu: FP64 pipe 41 % active, long-scoreboard stalls).
 constexpr int BAND = 16, BT_THREADS = 64, AS_LDB = BAND + 2;
 
+// The batched kernels keep their work vectors DOF-major, [dof][rhs]: the 16 x (16 TC) operand tile of a
+// round is then 16 contiguous runs of 16 TC right-hand sides instead of 16 TC runs of 16 DOFs.
+__global__ void k_permute_in_t(uint n, uint nrhs, const uint *__restrict__ perm, const cplx *__restrict__ x, cplx *xp) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // i = pos * nrhs + r
+  if (i >= (size_t)n * nrhs) return;
+  const uint r = i % nrhs, p = i / nrhs;
+  xp[i] = x[(size_t)r * n + perm[p]];
+}
+__global__ void k_permute_out_t(uint n, uint nrhs, const uint *__restrict__ perm, cplx alpha, const cplx *__restrict__ yp,
+                                cplx *y) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * nrhs) return;
+  const uint r = i % nrhs, p = i / nrhs;
+  const cplx v = cmul(alpha, yp[i]);
+  cplx *d = y + (size_t)r * n + perm[p];
+  d->x += v.x;
+  d->y += v.y;
+}
+
 __device__ __forceinline__ void hm_cp_async16(void *smem, const void *gmem, bool valid) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   int sz = valid ? 16 : 0;   // src-size 0: zero fill
@@ -400,9 +419,9 @@ k_hmv_gemm(const uint *__restrict__ band_ptr, const HMat::DRound *__restrict__ d
       }
       if (!far) {
         for (uint e = tid; e < 16 * RP; e += BT_THREADS) {
-          const uint j = e % 16, r = e / 16;
+          const uint r = e % RP, j = e / RP;
           const bool ok = j < cnt && r0 + r < nrhs;
-          hm_cp_async16(&Xs[buf][j][r], ok ? xp + (size_t)(r0 + r) * ntot + Is[ib][j].t_idx : xp, ok);
+          hm_cp_async16(&Xs[buf][j][r], ok ? xp + (size_t)Is[ib][j].t_idx * nrhs + r0 + r : xp, ok);
         }
       } else {
         for (uint e = tid; e < 16 * RP; e += BT_THREADS) {
@@ -472,7 +491,7 @@ k_hmv_gemm(const uint *__restrict__ band_ptr, const HMat::DRound *__restrict__ d
           if (TMODE) {
             if (i < kk && r < nrhs) T[(size_t)(t0 + l0 + i) * nrhs + r] = v;
           } else {
-            if (b0 + i < ntot && r < nrhs) yp[(size_t)r * ntot + b0 + i] = v;
+            if (b0 + i < ntot && r < nrhs) yp[(size_t)(b0 + i) * nrhs + r] = v;
           }
         }
   }
@@ -902,7 +921,7 @@ int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y
       CNLD_CK(cudaMalloc(&H.d_T, sizeof(cplx) * (need ? need : 1)));
       H.T_cap = need;
     }
-    k_permute_in<<<gb, 256, 0, st>>>(H.n, nrhs, H.d_perm, d_x, H.d_xp);
+    k_permute_in_t<<<gb, 256, 0, st>>>(H.n, nrhs, H.d_perm, d_x, H.d_xp);
     CNLD_CK_LAUNCH();
     // right-hand sides per pass (16 * TC): the width that wastes the fewest columns, ties to the wider
     int tc = 2;
@@ -926,7 +945,7 @@ int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y
     else CNLD_HMV(4);
 #undef CNLD_HMV
     CNLD_CK_LAUNCH();
-    k_permute_out<<<gb, 256, 0, st>>>(H.n, nrhs, H.d_perm, alpha, H.d_yp, d_y);
+    k_permute_out_t<<<gb, 256, 0, st>>>(H.n, nrhs, H.d_perm, alpha, H.d_yp, d_y);
     CNLD_CK_LAUNCH();
     return 0;
   }
