@@ -83,6 +83,15 @@ k_diag(cplx *a0, size_t lda, uint n, uint b0, cplx *linv0, cplx *uinv0, uint *in
     __syncthreads();
   }
   for (uint j = g; j < NB; j += NG) linv[j * NB + r] = X[j * LD + r];
+  if (SYM) {
+    // symmetric block: R = D L^T, so inv(R) = inv(L)^T D^-1 -- a scaled transpose instead of a second elimination
+    for (uint j = g; j < NB; j += NG) {
+      cplx v = make_double2(r == j ? 1.0 : 0.0, 0.0);
+      if (r < nbk && j < nbk) v = cmul(X[r * LD + j], P[j]);
+      uinv[j * NB + r] = v;
+    }
+    return;
+  }
   __syncthreads();
   // X = inv(R), R upper: backward elimination on the identity; row kk is scaled by the reciprocal
   // pivot on the fly and in place only at the end (one barrier per step again)
