@@ -208,6 +208,8 @@ def main():
     for w in range(args.warmup):
         sweep.run_device(batch(w))
     fp64_peak = _lib.bench_dfma(3, device=local)         # measured FP64 FMA-pipe peak, TFLOP/s
+    # the same kernel alone on the GPU at the first trailing update's shape (conventional 8mnk rate)
+    alone_8mnk = _lib.bench_zgemm(N - 1024, N - 1024, 512, 3, device=local) if args.config == 'c3' else None
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -308,6 +310,9 @@ def main():
                          'whole_step_dmma_tflops': step_tflops,
                          'whole_step_frac': step_tflops / fp64_peak,
                          'achieved_conventional_8mnk': (ach * 4.0 / 3.0) if ach else None,
+                         # stand-alone rate of the same kernel (full grid, nothing co-running), executed flops
+                         'standalone_achieved': (alone_8mnk * 0.75) if alone_8mnk else None,
+                         'standalone_frac': (alone_8mnk * 0.75 / fp64_peak) if alone_8mnk else None,
                          'launches_timed': int(klaunch),
                          'peak_source': 'FP64 FMA-pipe peak measured live with cnld_b200_bench_dfma '
                                         '(MEASURED_PEAKS.json carries no FP64 figure; DMMA and DFMA share it)'},
