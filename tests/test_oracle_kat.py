@@ -136,3 +136,34 @@ def test_aca_block_accuracy(po):
         assert err < 3 * eps and U.shape[1] < 25
         assert prev is None or U.shape[1] >= prev
         prev = U.shape[1]
+
+
+def test_asymmetry_of_z_lives_on_touching_pairs_only(po):
+    """The assumption behind the GPU's symmetric path, checked on the oracle alone:
+    Z - Z^T is tiny and non-zero only at entries (i, j) whose vertices belong to touching triangles
+    (the Sauter-Schwab rules are not symmetric under swapping the two triangles; the regular tensor
+    rule is), and translated membranes give translated blocks."""
+    arr = po.matrix_array(nelem=(2, 1))
+    am = po.array_mesh(arr, 4)
+    k = 2 * np.pi * 7e6 / 1500
+    Z = po.assemble_z(am, k)
+    n = am.nvertices
+    A = Z - Z.T
+    scale = np.abs(Z).max()
+    assert 1e-12 < np.abs(A).max() / scale < 1e-5
+    # vertex pairs fed by touching triangle pairs
+    tri = np.asarray(am.triangles)
+    v2t = [set() for _ in range(n)]
+    for t, vs in enumerate(tri):
+        for v in vs:
+            v2t[v].add(t)
+    touch = np.zeros((n, n), dtype=bool)
+    for t, vs in enumerate(tri):
+        nb = set().union(*[v2t[v] for v in vs])          # triangles sharing a vertex with t
+        cols = np.unique(tri[sorted(nb)].ravel())
+        touch[np.ix_(vs, cols)] = True
+    assert np.abs(A[~touch]).max() <= 1e-15 * scale
+    # translation: the two membranes' diagonal blocks agree to rounding, and the off-diagonal blocks are transposes
+    h = n // 2
+    assert np.abs(Z[:h, :h] - Z[h:, h:]).max() <= 1e-12 * scale
+    assert np.abs(Z[h:, :h] - Z[:h, h:].T).max() <= 1e-12 * scale
