@@ -54,12 +54,41 @@ def main(cfg, file, write_over=False, array=None, device=0, block=8, store_nodes
                              z=setup.vertices[:, 2])
     todo = np.arange(len(freqs)) if done is None else np.nonzero(~done)[0]
     sw = FrequencySweep(setup, device=device, nstreams=nstreams)
+    # Single writer thread: block b is written (one transaction, then its progress
+    # rows) while block b+1 is on the GPU.  The queue holds one block, so at most two blocks of node
+    # displacements are alive; a writer failure stops the sweep at the next block.
+    import queue
+    import threading
+    q = queue.Queue(maxsize=1)
+    failure = []
+
+    def writer():
+        while True:
+            item = q.get()
+            if item is None:
+                return
+            if failure:
+                continue                 # drain after an error so the producer never blocks
+            try:
+                ids, xp, xn, t = item
+                database.append_frequency_block(file, freqs[ids], wavenums[ids], xp, xn, setup.vertices, t)
+                database.update_progress(file, ids + 1)      # job ids are 1-based like the reference's
+            except BaseException as e:   # noqa: BLE001 -- re-raised in the main thread
+                failure.append(e)
+
+    th = threading.Thread(target=writer, name='cnld-db-writer', daemon=True)
+    th.start()
     try:
         for b0 in range(0, len(todo), block):
+            if failure:
+                break
             ids = todo[b0:b0 + block]
             xp, xn, t = sw.run(freqs[ids], want_nodes=store_nodes)
-            database.append_frequency_block(file, freqs[ids], wavenums[ids], xp, xn, setup.vertices, t)
-            database.update_progress(file, ids + 1)      # job ids are 1-based like the reference's
+            q.put((ids, xp, xn, t))
     finally:
+        q.put(None)
+        th.join()
         sw.close()
+    if failure:
+        raise failure[0]
     postprocess(file, cfg.freq_interp)
