@@ -28,7 +28,7 @@ def postprocess(file, interp):
                                             time=times.ravel(), displacement=ppir.ravel())
 
 
-def main(cfg, file, write_over=False, array=None, device=0, block=8, store_nodes=True, nstreams=2):
+def main(cfg, file, write_over=False, array=None, device=0, block=12, store_nodes=True, nstreams=3):
     """Run (or resume) the sweep described by `cfg` and write `file`."""
     if not cfg.use_fluid:
         raise NotImplementedError("use_fluid=False is marked 'doesn't work right yet' in the reference "
