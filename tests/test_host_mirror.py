@@ -203,3 +203,40 @@ def test_translation_plan_covers_every_pair_once():
         assert not info2['periodic'] and len(copy2) == 0
         tot = sum(int((np.arange(sb, se)[None, :] < np.arange(tb, te)[:, None]).sum()) for tb, te, sb, se in work2.astype(np.int64))
         assert tot == nt * (nt - 1) // 2
+
+
+def test_translation_plan_falls_back_on_anything_irregular():
+    """Detection must be conservative: one component, permuted triangles, permuted vertices or a
+    scaled copy all take the integrate-everything list (one self rectangle, no copies)."""
+    from cnld import _lib, arrays, mesh
+    am1 = mesh.Mesh.from_abstract(arrays.matrix_array(nelem=(1, 1)), 3)
+    V1, T1 = np.array(am1.vertices), np.array(am1.triangles)
+    nv, nt = len(V1), len(T1)
+    shift = np.array([60e-6, 0.0, 0.0])
+
+    def plan(V, T):
+        info, work, copy = _lib.translation_plan(V, T)
+        tot = sum(int((np.arange(sb, se)[None, :] < np.arange(tb, te)[:, None]).sum()) for tb, te, sb, se in work.astype(np.int64))
+        return info, tot, len(copy)
+
+    # a clean pair of translated copies is detected ...
+    V2, T2 = np.vstack([V1, V1 + shift]), np.vstack([T1, T1 + nv]).astype(np.uint32)
+    info, tot, ncopy = plan(V2, T2)
+    assert info['periodic'] and info['components'] == 2 and info['offset_classes'] == 1 and ncopy == 1
+    assert tot == nt * (nt - 1) // 2 + nt * nt
+    full = (2 * nt) * (2 * nt - 1) // 2
+    # ... a single component is not
+    info, tot, ncopy = plan(V1, T1)
+    assert not info['periodic'] and ncopy == 0 and tot == nt * (nt - 1) // 2
+    # second copy with its triangles in another order
+    info, tot, ncopy = plan(V2, np.vstack([T1, (T1 + nv)[::-1]]).astype(np.uint32))
+    assert not info['periodic'] and ncopy == 0 and tot == full
+    # second copy with two vertices swapped (connectivity renumbered consistently: same geometry, other numbering)
+    perm = np.arange(nv); perm[[3, 5]] = perm[[5, 3]]
+    Vb = V1[perm] + shift
+    inv = np.argsort(perm)
+    info, tot, ncopy = plan(np.vstack([V1, Vb]), np.vstack([T1, inv[T1] + nv]).astype(np.uint32))
+    assert not info['periodic'] and ncopy == 0 and tot == full
+    # second copy scaled by 1 + 1e-9
+    info, tot, ncopy = plan(np.vstack([V1, V1 * (1 + 1e-9) + shift]), T2)
+    assert not info['periodic'] and ncopy == 0 and tot == full
