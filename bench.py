@@ -37,15 +37,61 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, 'cnl-dyna_b200'))
 
-# dram bytes (read + write) of the first trailing update, ncu --set full: {general: ..., symmetric: ...}
-TRAFFIC_T2 = {True: 8.28e9, False: 8.06e9}
 METRIC = 'frequencies solved/s (Z assemble+factor+solve), 4x4 CMUT array'
 UNIT = 'frequencies/s'
 CONFIGS = {  # name: (nelem, refn, nfreq of the full sweep, fmin, fmax)
     'c1': ((1, 1), 15, 500, 1e6, 50e6),
     'c2': ((2, 2), 15, 1000, 0.05e6, 50e6),
     'c3': ((4, 4), 21, 2000, 0.025e6, 50e6),
+    'c4': ((16, 16), 19, 500, 0.1e6, 50e6),      # ACA H-matrix + GMRES (bench_c4)
+    'c5': ((4, 4), 21, 2000, 0.025e6, 50e6),     # C3 mesh + 10^6 observation points (bench_c5)
 }
+OBS_GRID = (100, 100, 100)                       # x, y in [-1, 1] mm, z in [0.1, 2.1] mm
+
+
+def measured_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, taken from the
+    committed ncu --set full summary of THIS round (profiles/r2_traffic.json, written by
+    scripts/ncu_summary.py); None when that capture is absent."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')) as fh:
+            return json.load(fh).get(kernel_key)
+    except Exception:
+        return None
+
+
+def obs_grid():
+    nx, ny, nz = OBS_GRID
+    gx, gy, gz = np.meshgrid(np.linspace(-1e-3, 1e-3, nx), np.linspace(-1e-3, 1e-3, ny),
+                             np.linspace(0.1e-3, 2.1e-3, nz), indexing='ij')
+    return np.ascontiguousarray(np.c_[gx.ravel(), gy.ravel(), gz.ravel()])
+
+
+def cublas_yardstick(m, n, k, device):
+    """cuBLAS FP64 GEMM rates at the trailing update's shape -- an independent yardstick for the FP64
+    roofline denominator, measured with torch.matmul OUTSIDE the product path (TFLOP/s; the complex one
+    counted as 8 m n k)."""
+    import torch
+    out = {}
+    for name, dt, fl in (('dgemm_tflops', torch.float64, 2.0), ('zgemm_tflops_8mnk', torch.complex128, 8.0)):
+        try:
+            a = torch.randn(m, k, dtype=dt, device=device)
+            b = torch.randn(k, n, dtype=dt, device=device)
+            c = torch.matmul(a, b)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            out[name] = fl * m * n * k * 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+            del a, b, c
+        except Exception as exc:      # yardstick only: never fail the bench on it
+            out[name] = None
+            out[name + '_error'] = str(exc)[:80]
+    torch.cuda.empty_cache()
+    return out
 
 
 def workload_freqs(cfg, count, offset=0):
@@ -145,6 +191,188 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------
+# C5: field pressure of the 4x4 array on 10^6 observation points (BASELINE.json configs[4])
+# ---------------------------------------------------------------------------------------------------
+C5_METRIC = 'field-pressure frequencies/s (10^6 observation points x 144 source patches), 4x4 CMUT array'
+
+
+def _c5_oracle_sample(po, am, obs, k, disp, idx, block=2000):
+    """p[src, idx] by the oracle: disp . mesh_pres_vector(obs[idx], k) (bem_pressure.pyx:54-88, :110-112)."""
+    out = np.empty((disp.shape[0], len(idx)), dtype=np.complex128)
+    for b0 in range(0, len(idx), block):
+        pv = po.pres_vector(am, obs[idx[b0:b0 + block]], k)          # [nb, nv]
+        out[:, b0:b0 + block] = disp @ pv.T
+    return out
+
+
+def bench_c5_reference(args, rank):
+    """CPU arm of C5: the oracle's mesh_pres_vector + dot on a bounded sample of the 10^6 points."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import pyoracle as po
+    po.build()
+    nelem, refn = CONFIGS['c5'][:2]
+    arr = po.matrix_array(nelem=nelem)
+    am = po.array_mesh(arr, refn)
+    P = 9 * nelem[0] * nelem[1]
+    obs = obs_grid()
+    rng = np.random.default_rng(0)
+    disp = rng.standard_normal((P, am.nvertices)) + 1j * rng.standard_normal((P, am.nvertices))
+    nsample = 4000
+    freqs = workload_freqs('c5', args.steps + args.warmup)
+    steps = min(args.steps, 3)
+    idx = np.sort(rng.choice(len(obs), nsample, replace=False))
+    for f in freqs[:min(args.warmup, 1)]:
+        _c5_oracle_sample(po, am, obs, 2 * np.pi * f / 1500., disp, idx[:500])
+    t0 = time.perf_counter()
+    for f in freqs[args.warmup:args.warmup + steps]:
+        _c5_oracle_sample(po, am, obs, 2 * np.pi * f / 1500., disp, idx)
+    dt = (time.perf_counter() - t0) / steps
+    val = 1.0 / (dt * len(obs) / nsample)
+    print(json.dumps({
+        'impl': 'reference', 'metric': C5_METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'complex128 (f64)', 'data': 'synthetic',
+        'config': {'workload': f'c5: 4x4 CMUT array refn={refn} (N={am.nvertices}, T={am.ntriangles}), {len(obs)} observation points, P={P}'},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': po.lib().orc_num_threads(), 'kind': 'port',
+                         'sample': f'{nsample} of {len(obs)} observation points per step, extrapolated linearly'},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}), flush=True)
+
+
+def bench_c5(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    from cnld import _lib, arrays
+    from cnld.sweep import FrequencySweep, SweepSetup, broadcast_setup
+    if _lib.device_count() == 0:
+        raise SystemExit('bench.py: no CUDA device -- libcnld_b200 has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    nelem, refn = CONFIGS['c5'][:2]
+    setup = SweepSetup.from_abstract(arrays.matrix_array(nelem=nelem), refn) if rank == 0 else None
+    if world > 1:
+        setup = broadcast_setup(setup, rank, torch.device('cuda', local))
+    N, P, T = setup.nnodes, setup.npatch, len(setup.triangles)
+    obs = obs_grid()
+    nobs = len(obs)
+    nsteps = args.steps + args.warmup
+    # inputs: this rank's frequencies and their node displacements (C3's dense sweep, untimed)
+    freqs = workload_freqs('c5', nsteps, offset=rank)
+    sweep = FrequencySweep(setup, device=local, nstreams=1)
+    _, disp, _ = sweep.run(freqs, want_nodes=True)            # [nsteps, P, N]
+    ks = 2 * np.pi * freqs / setup.c
+    pf = _lib.PressureField(sweep.ctx, obs, P)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident: points and displacements in HBM, results stay in HBM ----------------------
+    pf.run(ks[0], disp[0], setup.c, setup.rho, fetch=False)
+    for w in range(args.warmup):
+        pf.run_device(ks[w], P, setup.c, setup.rho)
+    fp64_peak = _lib.bench_dfma(3, device=local)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    barrier()
+    dev_s = pv_s = ct_s = 0.0
+    for s_ in range(args.steps):
+        pf.run_device(ks[args.warmup + s_], P, setup.c, setup.rho)
+        inf = pf.info()
+        dev_s += inf['total_seconds']; pv_s += inf['pvec_seconds']; ct_s += inf['contract_seconds']
+    barrier()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.finish() if rank == 0 else None
+    dt = reduce_max(dev_s)
+    value = args.steps * world / dt
+
+    # ---- end to end: displacements from host memory, the whole field back to host memory ------------
+    out = np.empty((P, nobs), dtype=np.complex128)
+    pf.run(ks[0], disp[0], setup.c, setup.rho, out=out)        # untimed: page-locks `out`
+    barrier()
+    t0 = time.perf_counter()
+    for s_ in range(args.steps):
+        i = args.warmup + s_
+        pf.run(ks[i], disp[i], setup.c, setup.rho, out=out)
+    barrier()
+    dte = reduce_max(time.perf_counter() - t0)
+    e2e = args.steps * world / dte
+    assert np.isfinite(out).all() and np.abs(out).max() > 0
+    inf = pf.info()
+
+    line = None
+    if rank == 0:
+        flops = 6.0 * nobs * P * N * args.steps               # executed real flops of the 3M contraction
+        ach = flops / ct_s / 1e12
+        evals = 3.0 * T * nobs * args.steps
+        line = {
+            'metric': C5_METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'complex128 (f64)', 'data': 'synthetic',
+            'config': {'workload': f'c5: 4x4 CMUT array refn={refn} (N={N}, T={T}), {nobs} observation points on a '
+                                   f'{OBS_GRID[0]}x{OBS_GRID[1]}x{OBS_GRID[2]} grid, P={P} source patches, one frequency per step',
+                       'parallelism': f'freq-shard x{world}', 'obs_per_chunk': inf['obs_per_chunk'], 'chunks': inf['chunks'],
+                       'cache': 'node-space pressure vectors of one chunk = 9 GB >> 126 MB L2'},
+            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(disp[0].nbytes), 'd2h_bytes_per_step': int(out.nbytes)},
+            'gpu_launches': int(launches), 'clocks': clocks,
+            'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': ach / fp64_peak,
+                         'traffic': measured_traffic('zgemm3m_pfield'),
+                         'kernel': 'zgemm3m_kernel: p[src][obs] = PV[obs][node] . disp[src][node], 6 m n k executed flops '
+                                   '(3M); durations by CUDA events on the launch stream inside the timed region',
+                         'peak_source': 'FP64 FMA-pipe peak measured live (cnld_b200_bench_dfma)',
+                         'pvec_kernel': {'kernel': 'k_pvec_tiles (FP64 pipe: rsqrt + sincos per point pair)',
+                                         'kernel_evaluations_per_s': evals / pv_s, 'seconds_per_step': pv_s / args.steps},
+                         'contract_seconds_per_step': ct_s / args.steps},
+        }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import pyoracle as po
+        po.build()
+        am = po.array_mesh(po.matrix_array(nelem=nelem), refn)
+        rng = np.random.default_rng(0)
+        idx = np.sort(rng.choice(nobs, 10000, replace=False)).astype(np.uint32)
+        i = args.warmup + args.steps - 1                       # the last timed step's result is still on the device
+        got = pf.fetch(P, idx)
+        t0 = time.perf_counter()
+        ref = _c5_oracle_sample(po, am, obs, ks[i], disp[i], idx)
+        tc = time.perf_counter() - t0
+        rel = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+        line['parity'] = {'config': 'c5', 'sampled_points': len(idx), 'rel_l2': rel, 'tolerance': 1e-6,
+                          'against': 'oracle mesh_pres_vector . displacement'}
+        line['cpu_baseline'] = {'value': 1.0 / (tc * nobs / len(idx)), 'unit': UNIT, 'cores': po.lib().orc_num_threads(),
+                                'kind': 'port', 'sample': f'{len(idx)} of {nobs} observation points, extrapolated linearly'}
+        if not rel < 1e-6:
+            print(json.dumps(line), flush=True)
+            raise SystemExit('bench.py: c5 field pressure differs from the oracle by more than 1e-6')
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    pf.close()
+    sweep.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_c4(args, rank, world, local):
+    raise SystemExit('bench.py --config c4: not wired yet')
+
+
+def bench_c4_reference(args, rank):
+    raise SystemExit('bench.py --config c4 --impl reference: not wired yet')
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -165,10 +393,18 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', 0))
 
     if args.impl == 'reference':
+        if args.config == 'c5':
+            return bench_c5_reference(args, rank)
+        if args.config == 'c4':
+            return bench_c4_reference(args, rank)
         if args.steps > 2:
             args.steps, args.warmup = min(args.steps, 2), min(args.warmup, 1)
         run_reference(args, rank, world)
         return
+    if args.config == 'c5':
+        return bench_c5(args, rank, world, local)
+    if args.config == 'c4':
+        return bench_c4(args, rank, world, local)
 
     import torch
     import torch.distributed as dist
@@ -210,6 +446,8 @@ def main():
     fp64_peak = _lib.bench_dfma(3, device=local)         # measured FP64 FMA-pipe peak, TFLOP/s
     # the same kernel alone on the GPU at the first trailing update's shape (conventional 8mnk rate)
     alone_8mnk = _lib.bench_zgemm(N - 1024, N - 1024, 512, 3, device=local) if args.config == 'c3' else None
+    # independent yardstick for the FP64 peak: cuBLAS (through torch, outside the product) at the same shape
+    yard = cublas_yardstick(N - 1024, N - 1024, 512, torch.device('cuda', local)) if rank == 0 and N > 2048 else None
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -299,7 +537,10 @@ def main():
                          # profiles/r1_ncu_full_summary.txt.  General: 13776 x 13776 x 512, algorithmic bytes
                          # C read + write 6.07e9 + panels 0.45e9.  Symmetric: the same update restricted to the
                          # tiles on or below the diagonal, algorithmic C read + write 3.05e9 + panels 0.45e9.
-                         'traffic': (TRAFFIC_T2[bool(args.general)] if args.config == 'c3' else None),
+                         'traffic': (measured_traffic('zgemm3m_general_T2' if args.general else 'zgemm3m_lower_T2')
+                                     if args.config == 'c3' else None),
+                         'traffic_source': 'profiles/r2_traffic.json (ncu --set full of this round, first trailing update)',
+                         'cublas_yardstick': yard,
                          'kernel': 'zgemm3m_kernel (DMMA.8x8x4 rank-512 trailing updates of the LU'
                                    + ('' if args.general else ', tiles on or below the diagonal only')
                                    + '; 3M complex product = 6 m n k executed real flops per launch, i.e. 8 m n k '
@@ -315,11 +556,13 @@ def main():
                          'standalone_frac': (alone_8mnk * 0.75 / fp64_peak) if alone_8mnk else None,
                          'launches_timed': int(klaunch),
                          'peak_source': 'FP64 FMA-pipe peak measured live with cnld_b200_bench_dfma '
-                                        '(MEASURED_PEAKS.json carries no FP64 figure; DMMA and DFMA share it)'},
+                                        '(MEASURED_PEAKS.json carries no FP64 figure; DMMA and DFMA share it); '
+                                        'cublas_yardstick = torch.matmul float64 / complex128 at the same shape, same run'},
             'stage_seconds_per_frequency': dict(zip(('assemble', 'factor', 'solve'), (stage / (args.steps * nfb)).tolist())),
         }
 
-    # ---- CPU baseline beside it (rank 0, N=1 only, bounded sample) --------------------------
+    # ---- CPU baseline beside it (rank 0, N=1 only, bounded sample) + parity at THIS config -----
+    parity_fail = False
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, 'oracle'))
         import pyoracle as po
@@ -328,16 +571,30 @@ def main():
         am = po.array_mesh(arr, refn)
         blocks = po.array_fem(arr, refn)
         f = workload_freqs(args.config, 1)
+        tm = {}
         t0 = time.perf_counter()
-        cpu_reference_step(po, am, blocks, f, 1500., 1000.)
+        Xo, XPo = po.solve_frequency(am, blocks, float(f[0]), c=1500., rho=1000., blocked=True, timings=tm)
         tc = time.perf_counter() - t0
         line['cpu_baseline'] = {'value': 1.0 / tc, 'unit': UNIT, 'cores': po.lib().orc_num_threads(), 'kind': 'port',
-                                'sample': 'one full frequency of the same workload (oracle port of the H2Lib path)'}
+                                'sample': 'one full frequency of the same workload (oracle port of the H2Lib path)',
+                                'stage_seconds': tm}
+        # the same frequency through the product path (host buffers in/out), compared with the oracle's
+        # result (generate_db.py:82-99: x = conj(lusolve), x[ob] = 0, x_patch = AVG^T x)
+        sweep.ctx.set_streams(args.streams)
+        sweep.ctx.set_profile(False)
+        xp1, xn1, _ = sweep.run(f, want_nodes=True)
+        rn = float(np.linalg.norm(xn1[0].T - Xo) / np.linalg.norm(Xo))
+        rp = float(np.linalg.norm(xp1[0].T - XPo) / np.linalg.norm(XPo))
+        line['parity'] = {'config': args.config, 'frequency_hz': float(f[0]), 'rel_l2_node': rn, 'rel_l2_patch': rp,
+                          'tolerance': 1e-6, 'against': 'oracle port (full N x N assembly + blocked unpivoted LU on the host)'}
+        parity_fail = not (rn < 1e-6 and rp < 1e-6)
     if rank == 0:
         print(json.dumps(line), flush=True)
     sweep.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity_fail:
+        raise SystemExit('bench.py: GPU result differs from the oracle by more than 1e-6 at this config')
 
 
 if __name__ == '__main__':

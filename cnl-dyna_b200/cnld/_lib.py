@@ -68,6 +68,15 @@ def lib():
         L.cnld_b200_sweep_kernel_stats.argtypes = [vp, vp]
         L.cnld_b200_pres_vector.argtypes = [vp, vp, u32, f64, f64, f64, vp]
         L.cnld_b200_pressure.argtypes = [vp, vp, u32, vp, u32, f64, f64, vp, u32, vp]
+        L.cnld_b200_pfield_create.restype = vp
+        L.cnld_b200_pfield_create.argtypes = [vp, vp, u32, u32]
+        L.cnld_b200_pfield_destroy.argtypes = [vp]
+        L.cnld_b200_pfield_pin.argtypes = [vp, vp, C.c_size_t]
+        L.cnld_b200_pfield_run.argtypes = [vp, f64, f64, f64, vp, u32, vp]
+        L.cnld_b200_pfield_run_device.argtypes = [vp, f64, f64, f64, u32]
+        L.cnld_b200_pfield_fetch.argtypes = [vp, u32, vp, u32, vp]
+        L.cnld_b200_pfield_info.argtypes = [vp, vp]
+        L.cnld_b200_pres_plan_stats.argtypes = [u32, u32, vp, vp, vp, vp]
         L.cnld_b200_hmat_create.restype = vp
         L.cnld_b200_hmat_create.argtypes = [vp, u32, f64, C.c_int, C.c_int, u32]
         L.cnld_b200_hmat_destroy.argtypes = [vp]
@@ -276,6 +285,74 @@ class Context:
         check(lib().cnld_b200_pressure(self._h, ptr(obs), len(obs), ptr(ks), nk, c, rho, ptr(disp), nsrc,
                                        ptr(out)))
         return out
+
+
+class PressureField:
+    """Observation points resident on one GPU + workspace of the many-source field-pressure path
+    (opaque cnld_pfield): p[src, obs] = mesh_pres_vector(obs, k) . disp[src] for all points at once
+    (the loop of bem_pressure.pyx:103-112)."""
+
+    def __init__(self, ctx, obs, nsrc_max):
+        self.ctx = ctx
+        self.obs = _c(np.atleast_2d(obs), np.float64)
+        self.nobs, self.nsrc_max = len(self.obs), int(nsrc_max)
+        self._h = lib().cnld_b200_pfield_create(ctx._h, ptr(self.obs), self.nobs, self.nsrc_max)
+        if not self._h:
+            raise Cnldb200Error(lib().cnld_b200_last_error().decode())
+        self._pinned = None
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().cnld_b200_pfield_destroy(self._h)
+            self._h = None
+            self._pinned = None
+
+    __del__ = close
+
+    def run(self, k, disp, c=1500., rho=1000., out=None, fetch=True):
+        """disp[nsrc, N] (host) -> p[nsrc, nobs]; `out` = reusable host buffer (page-locked on first use)."""
+        disp = _c(disp, np.complex128)
+        nsrc = disp.shape[0]
+        assert disp.shape[1] == self.ctx.nv
+        p = None
+        if fetch:
+            p = out if out is not None else np.empty((nsrc, self.nobs), dtype=np.complex128)
+            assert p.shape == (nsrc, self.nobs) and p.dtype == np.complex128 and p.flags.c_contiguous
+            if out is not None and self._pinned is not out:
+                self._pinned = out if lib().cnld_b200_pfield_pin(self._h, ptr(out), out.nbytes) == 0 else None
+        check(lib().cnld_b200_pfield_run(self._h, float(k), c, rho, ptr(disp), nsrc, ptr(p)))
+        return p
+
+    def run_device(self, k, nsrc, c=1500., rho=1000.):
+        check(lib().cnld_b200_pfield_run_device(self._h, float(k), c, rho, int(nsrc)))
+
+    def fetch(self, nsrc, idx=None):
+        if idx is None:
+            p = np.empty((nsrc, self.nobs), dtype=np.complex128)
+            check(lib().cnld_b200_pfield_fetch(self._h, nsrc, None, 0, ptr(p)))
+            return p
+        idx = _c(idx, np.uint32)
+        p = np.empty((nsrc, len(idx)), dtype=np.complex128)
+        check(lib().cnld_b200_pfield_fetch(self._h, nsrc, ptr(idx), len(idx), ptr(p)))
+        return p
+
+    def info(self):
+        out = np.zeros(7)
+        check(lib().cnld_b200_pfield_info(self._h, ptr(out)))
+        keys = ('pvec_seconds', 'contract_seconds', 'total_seconds', 'chunks', 'obs_per_chunk', 'tri_chunks',
+                'node_entries')
+        return {k: (float(v) if i < 3 else int(v)) for i, (k, v) in enumerate(zip(keys, out))}
+
+
+def pres_plan_stats(vertices, triangles):
+    """Host-only: chunking of the mesh used by the pressure-vector kernel."""
+    x = _c(vertices, np.float64)
+    t = _c(triangles, np.uint32)
+    counts = np.zeros(6, dtype=np.uint32)
+    order = np.zeros(len(t), dtype=np.uint32)
+    check(lib().cnld_b200_pres_plan_stats(len(x), len(t), ptr(x), ptr(t), ptr(counts), ptr(order)))
+    keys = ('chunks', 'node_entries', 'max_triangles', 'max_nodes', 'accumulating_entries', 'untouched_vertices')
+    return dict(zip(keys, (int(v) for v in counts))), order
 
 
 ADMIS = {'2': 0, 'max': 1, 'sphere': 2, '2min': 3, '2_min': 3}

@@ -65,6 +65,22 @@ namespace cnld {
 int pres_vector(cudaStream_t st, const BemDev &b, const double *d_obs, uint nobs, double k, double c,
                 double rho, cplx *d_pvec);
 int pres_points(cudaStream_t st, const BemDev &b, double *d_sp);
+// many-source path: triangle chunks (host-built once per mesh) -> node-space pressure vectors of a
+// tile of observation points -> one ZGEMM against the displacements
+struct PresPlan {
+  uint nchunk = 0, nentries = 0;       // nentries = sum of chunk-local nodes (PV writes per observation point)
+  uint *tptr = nullptr, *nptr = nullptr, *node = nullptr;
+  double *tri = nullptr;
+  std::vector<uint> untouched;         // vertices no triangle references
+};
+int pres_plan_build(const BemDev &b, const double *hx, const uint *ht, PresPlan &p);
+void pres_plan_free(PresPlan &p);
+int pres_plan_stats(uint nv, uint nt, const double *hx, const uint *ht, uint *counts, uint *order);
+uint pres_tile_obs();
+int pres_pvec_tiles(cudaStream_t st, const PresPlan &p, const BemDev &b, const double *d_obs, uint mc, double k,
+                    double c, double rho, cplx *d_PV, size_t lda);
+int pres_contract(cudaStream_t st, const BemDev &b, const cplx *d_PV, size_t lda, uint mc, const cplx *d_disp,
+                  uint nsrc, cplx *d_out, size_t ldo);
 int pressure_field(cudaStream_t st, const BemDev &b, const double *d_obs, uint nobs, const double *d_sp,
                    double k, double c, double rho, const cplx *d_disp, uint nsrc, cplx *d_D, cplx *d_out);
 }  // namespace cnld

@@ -441,6 +441,7 @@ void cnld_b200_destroy(cnld_ctx *c) {
   dev_free(c->d_f_indptr); dev_free(c->d_a_indptr); dev_free(c->d_f_idx); dev_free(c->d_a_idx);
   dev_free(c->d_f_val); dev_free(c->d_a_val); dev_free(c->d_ob); cudaFree(c->d_xpatch); cudaFree(c->d_xnode);
   cudaFree(c->d_sp);
+  if (c->pplan_ready) pres_plan_free(c->pplan);
   dev_free(c->d_m_rowptr); dev_free(c->d_m_col); dev_free(c->d_m_dK); dev_free(c->d_m_dM); dev_free(c->d_m_dB);
   if (c->ev_begin) { cudaEventDestroy(c->ev_begin); cudaEventDestroy(c->ev_end); }
   if (c->reg_ptr) cudaHostUnregister(c->reg_ptr);
@@ -768,6 +769,16 @@ int cnld_b200_pressure(cnld_ctx *c, const double *obs, cnld_uint nobs, const dou
   if (!c) { set_error("null context"); return -1; }
   CNLD_CK(cudaSetDevice(c->bem.device));
   const size_t nv = c->bem.nv, nt = c->bem.nt;
+  if (nsrc > 4) {
+    // many sources: evaluate the kernel once per point pair, contract in node space on the DMMA ZGEMM
+    cnld_pfield *pf = cnld_b200_pfield_create(c, obs, nobs, nsrc);
+    if (!pf) return -1;
+    int rc = 0;
+    for (uint ik = 0; ik < nk && !rc; ik++)
+      rc = cnld_b200_pfield_run(pf, ks[ik], cs, rho, disp + (size_t)ik * nsrc * nv, nsrc, p + (size_t)ik * nsrc * nobs);
+    cnld_b200_pfield_destroy(pf);
+    return rc;
+  }
   double *d_obs = nullptr;
   cplx *d_disp = nullptr, *d_D = nullptr, *d_out = nullptr;
   if (!c->d_sp) {

@@ -76,5 +76,7 @@ struct cnld_ctx {
   size_t reg_bytes = 0;
   // pressure scratch
   double *d_sp = nullptr;
+  PresPlan pplan;            // triangle chunks of the many-source pressure path (pfield.cu)
+  bool pplan_ready = false;
 };
 

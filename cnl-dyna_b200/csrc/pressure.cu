@@ -9,8 +9,15 @@
 //   displacement is interpolated to the quadrature points once
 //   (D_g = scale * area/3/(4 pi) * sum_l N_l(xi_g) disp[v_l]) and every thread owns one
 //   observation point, streaming the 3*nt source points through shared memory:
-//   p(obs) = sum_g D_g * e^{-j k r}/r.  FP64 sincos/rsqrt bound.
+//   p(obs) = sum_g D_g * e^{-j k r}/r.  FP64 sincos/rsqrt bound.  Right for 1..4 sources.
+// k_pvec_tiles + zgemm3m: many sources (nsrc = P = 144 at C3).  e^{-j k r}/r is evaluated ONCE per
+//   (observation point, source point) and folded to node space on chip
+//   (PV[obs][node] = mesh_pres_vector of the reference, for a whole tile of observation points),
+//   then p[src][obs] = PV . disp[src] is one DMMA ZGEMM (K = nv instead of 3 nt source points).
 #include "pair.cuh"
+
+#include <algorithm>
+#include <numeric>
 
 namespace cnld {
 namespace {
@@ -119,6 +126,81 @@ k_pressure(uint nobs, const double *__restrict__ obs, uint npts, const double *_
     for (int s = 0; s < NS; s++) out[(size_t)s * ostride + o] = acc[s];
   }
 }
+
+// ---- node-space pressure vectors for a tile of observation points -----------------------------
+// The triangles are cut into spatially compact chunks (<= PV_TC triangles touching <= PV_NC nodes,
+// host-built once per mesh, PresPlan).  A CTA owns PV_OT observation points (one per thread) and
+// walks all chunks: per triangle three kernel evaluations, combined with the hat values of the
+// 3-point rule ((2/3,1/6,1/6) and its rotations: node l gets w (S/6 + E_l/2), S = E_0+E_1+E_2)
+// and accumulated into the chunk's [node][obs] tile in shared memory (a thread only touches its
+// own column: no atomics, no conflicts).  After the chunk the tile is written to PV (column-major
+// obs x node: coalesced along obs); a node that an earlier chunk already wrote is accumulated --
+// by the same thread that wrote it, so plain loads/stores are ordered.
+constexpr int PV_OT = 128, PV_NC = 48, PV_TC = 64;
+constexpr int PV_SMEM = PV_NC * PV_OT * (int)sizeof(cplx) + 2 * PV_TC * 8 * (int)sizeof(double);
+
+__global__ void __launch_bounds__(PV_OT, 2)
+k_pvec_tiles(uint nobs, const double *__restrict__ obs, uint nchunk, const uint *__restrict__ tptr,
+             const double *__restrict__ tri, const uint *__restrict__ nptr, const uint *__restrict__ node,
+             double k, double scale, cplx *PV, size_t lda) {
+  extern __shared__ __align__(16) unsigned char pv_smem[];
+  cplx *tile = reinterpret_cast<cplx *>(pv_smem);
+  double *stage = reinterpret_cast<double *>(tile + PV_NC * PV_OT);
+  const int tid = threadIdx.x;
+  const uint o = blockIdx.x * PV_OT + tid;
+  const bool live = o < nobs;
+  double ox = 0, oy = 0, oz2 = 1;
+  if (live) { ox = obs[3 * (size_t)o]; oy = obs[3 * (size_t)o + 1]; oz2 = obs[3 * (size_t)o + 2]; oz2 *= oz2; }
+  cplx *col = tile + tid;
+  const double w6 = scale * (1.0 / 6), w2 = scale * 0.5;
+  for (uint c = 0; c < nchunk; c++) {
+    const uint t0 = tptr[c], ntc = tptr[c + 1] - t0, n0 = nptr[c], nn = nptr[c + 1] - n0;
+    double *sg = stage + (c & 1) * (PV_TC * 8);
+    {
+      const double2 *src = reinterpret_cast<const double2 *>(tri + (size_t)t0 * 8);
+      double2 *dst = reinterpret_cast<double2 *>(sg);
+      for (uint i = tid; i < ntc * 4; i += PV_OT) dst[i] = src[i];
+    }
+    for (uint ln = 0; ln < nn; ln++) col[ln * PV_OT] = make_double2(0.0, 0.0);
+    __syncthreads();
+#pragma unroll 2
+    for (uint i = 0; i < ntc; i++) {
+      const double2 *e = reinterpret_cast<const double2 *>(sg + 8 * i);
+      const double2 p0 = e[0], p1 = e[1], p2 = e[2], ws = e[3];
+      double er[3], ei[3];
+      const double px[3] = {p0.x, p1.x, p2.x}, py[3] = {p0.y, p1.y, p2.y};
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        double dx = ox - px[q], dy = oy - py[q];
+        double r2 = fma(dx, dx, fma(dy, dy, oz2));
+        double rinv = rsqrt(r2), r = r2 * rinv, sn, cs;
+        sincos_fast(k * r, sn, cs);
+        er[q] = cs * rinv; ei[q] = -sn * rinv;
+      }
+      const double a6 = ws.x * w6, a2 = ws.x * w2;
+      const double sr = a6 * (er[0] + er[1] + er[2]), si = a6 * (ei[0] + ei[1] + ei[2]);
+      const unsigned long long sl = (unsigned long long)__double_as_longlong(ws.y);
+#pragma unroll
+      for (int l = 0; l < 3; l++) {
+        const uint s = (uint)(sl >> (8 * l)) & 0xffu;
+        cplx v = col[s * PV_OT];
+        v.x += fma(a2, er[l], sr);
+        v.y += fma(a2, ei[l], si);
+        col[s * PV_OT] = v;
+      }
+    }
+    if (live) {
+#pragma unroll 4
+      for (uint ln = 0; ln < nn; ln++) {
+        const uint nd = node[n0 + ln];
+        cplx *dst = PV + (size_t)(nd & 0x7fffffffu) * lda + o;
+        cplx v = col[ln * PV_OT];
+        if (nd >> 31) { cplx old = *dst; v.x += old.x; v.y += old.y; }
+        *dst = v;
+      }
+    }
+  }
+}
 }  // namespace
 
 int pres_vector(cudaStream_t st, const BemDev &b, const double *d_obs, uint nobs, double k, double c,
@@ -128,6 +210,160 @@ int pres_vector(cudaStream_t st, const BemDev &b, const double *d_obs, uint nobs
   k_pres_vector<<<nobs, 256, 0, st>>>(b.nt, b.x, b.t, b.g, d_obs, k, scale, b.nv, d_pvec);
   CNLD_CK_LAUNCH();
   return 0;
+}
+
+
+// ---- PresPlan: triangle chunks of k_pvec_tiles (host, once per mesh) ----------------------------
+namespace {
+struct PlanBuilder {
+  const double *x; const uint *t; uint nv;
+  std::vector<double> cen;           // centroids [nt][3]
+  std::vector<uint> order;           // triangle indices, permuted in place by the bisection
+  std::vector<uint> tptr, nptr, node;
+  std::vector<double> tri;
+  std::vector<uint8_t> touched;
+  std::vector<uint> scratch;
+  const double *g;
+  uint distinct_nodes(uint lo, uint hi) {
+    scratch.clear();
+    for (uint i = lo; i < hi; i++) for (int l = 0; l < 3; l++) scratch.push_back(t[3 * order[i] + l]);
+    std::sort(scratch.begin(), scratch.end());
+    scratch.erase(std::unique(scratch.begin(), scratch.end()), scratch.end());
+    return (uint)scratch.size();
+  }
+  void emit(uint lo, uint hi) {
+    distinct_nodes(lo, hi);                      // scratch = sorted unique node ids of the chunk
+    for (uint i = lo; i < hi; i++) {
+      const uint tt = order[i];
+      const uint v[3] = {t[3 * tt], t[3 * tt + 1], t[3 * tt + 2]};
+      static const double xi[3] = {1.0 / 6, 2.0 / 3, 1.0 / 6}, eta[3] = {1.0 / 6, 1.0 / 6, 2.0 / 3};
+      for (int q = 0; q < 3; q++) {              // bem_pressure.pyx:25-27, :75-80 (source z forced to 0)
+        const double n0 = 1.0 - xi[q] - eta[q];
+        tri.push_back(x[3 * v[0]] * n0 + x[3 * v[1]] * xi[q] + x[3 * v[2]] * eta[q]);
+        tri.push_back(x[3 * v[0] + 1] * n0 + x[3 * v[1] + 1] * xi[q] + x[3 * v[2] + 1] * eta[q]);
+      }
+      tri.push_back(0.5 * g[tt] * (1.0 / 3) * 0.0795774715459476678844418816863);
+      unsigned long long sl = 0;
+      for (int l = 0; l < 3; l++) {
+        const uint s = (uint)(std::lower_bound(scratch.begin(), scratch.end(), v[l]) - scratch.begin());
+        sl |= (unsigned long long)s << (8 * l);
+      }
+      double sd;
+      std::memcpy(&sd, &sl, sizeof(sd));
+      tri.push_back(sd);
+    }
+    for (uint nd : scratch) {
+      node.push_back(nd | (touched[nd] ? 0x80000000u : 0u));
+      touched[nd] = 1;
+    }
+    tptr.push_back((uint)(tri.size() / 8));
+    nptr.push_back((uint)node.size());
+  }
+  void split(uint lo, uint hi) {
+    if (hi - lo <= (uint)PV_TC && distinct_nodes(lo, hi) <= (uint)PV_NC) { emit(lo, hi); return; }
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (uint i = lo; i < hi; i++)
+      for (int d = 0; d < 3; d++) {
+        mn[d] = std::min(mn[d], cen[3 * order[i] + d]);
+        mx[d] = std::max(mx[d], cen[3 * order[i] + d]);
+      }
+    int ax = 0;
+    for (int d = 1; d < 3; d++) if (mx[d] - mn[d] > mx[ax] - mn[ax]) ax = d;
+    const uint mid = lo + (hi - lo) / 2;
+    std::nth_element(order.begin() + lo, order.begin() + mid, order.begin() + hi, [&](uint a, uint b) {
+      const double ca = cen[3 * a + ax], cb = cen[3 * b + ax];
+      return ca < cb || (ca == cb && a < b);
+    });
+    split(lo, mid);
+    split(mid, hi);
+  }
+};
+}  // namespace
+
+void pres_plan_free(PresPlan &p) {
+  cudaFree(p.tptr); cudaFree(p.tri); cudaFree(p.nptr); cudaFree(p.node);
+  p = PresPlan();
+}
+
+// host part: chunks of the mesh (x, t, g = 2 * area per triangle)
+static void pres_plan_host(uint nv, uint nt, const double *hx, const uint *ht, const double *hg, PlanBuilder &pb) {
+  pb.x = hx; pb.t = ht; pb.nv = nv; pb.g = hg;
+  pb.cen.resize(3 * (size_t)nt);
+  for (uint tt = 0; tt < nt; tt++)
+    for (int d = 0; d < 3; d++)
+      pb.cen[3 * (size_t)tt + d] = (hx[3 * ht[3 * tt] + d] + hx[3 * ht[3 * tt + 1] + d] + hx[3 * ht[3 * tt + 2] + d]) / 3.0;
+  pb.order.resize(nt);
+  std::iota(pb.order.begin(), pb.order.end(), 0u);
+  pb.touched.assign(nv, 0);
+  pb.tptr.push_back(0); pb.nptr.push_back(0);
+  if (nt) pb.split(0, nt);
+}
+
+// Host-only view of the plan (tests): counts = {chunks, node entries, max triangles per chunk, max
+// nodes per chunk, accumulate-flagged entries, vertices without a triangle}; order[nt] (nullable) =
+// the triangles in chunk order.
+int pres_plan_stats(uint nv, uint nt, const double *hx, const uint *ht, uint *counts, uint *order) {
+  std::vector<double> hg(nt, 1.0);
+  PlanBuilder pb;
+  pres_plan_host(nv, nt, hx, ht, hg.data(), pb);
+  uint mt = 0, mn = 0, acc = 0, unt = 0;
+  for (size_t c = 0; c + 1 < pb.tptr.size(); c++) {
+    mt = std::max(mt, pb.tptr[c + 1] - pb.tptr[c]);
+    mn = std::max(mn, pb.nptr[c + 1] - pb.nptr[c]);
+  }
+  for (uint nd : pb.node) acc += nd >> 31;
+  for (uint v = 0; v < nv; v++) unt += !pb.touched[v];
+  counts[0] = (uint)pb.tptr.size() - 1; counts[1] = (uint)pb.node.size(); counts[2] = mt; counts[3] = mn;
+  counts[4] = acc; counts[5] = unt;
+  if (order) std::copy(pb.order.begin(), pb.order.end(), order);
+  return 0;
+}
+
+int pres_plan_build(const BemDev &b, const double *hx, const uint *ht, PresPlan &p) {
+  PlanBuilder pb;
+  std::vector<double> hg(b.nt);
+  CNLD_CK(cudaMemcpy(hg.data(), b.g, sizeof(double) * b.nt, cudaMemcpyDeviceToHost));
+  pres_plan_host(b.nv, b.nt, hx, ht, hg.data(), pb);
+  p.nchunk = (uint)pb.tptr.size() - 1;
+  p.nentries = (uint)pb.node.size();
+  p.untouched.clear();
+  for (uint v = 0; v < b.nv; v++) if (!pb.touched[v]) p.untouched.push_back(v);
+  CNLD_CK(cudaMalloc(&p.tptr, sizeof(uint) * pb.tptr.size()));
+  CNLD_CK(cudaMalloc(&p.nptr, sizeof(uint) * pb.nptr.size()));
+  CNLD_CK(cudaMalloc(&p.tri, sizeof(double) * std::max<size_t>(pb.tri.size(), 8)));
+  CNLD_CK(cudaMalloc(&p.node, sizeof(uint) * std::max<size_t>(pb.node.size(), 1)));
+  CNLD_CK(cudaMemcpy(p.tptr, pb.tptr.data(), sizeof(uint) * pb.tptr.size(), cudaMemcpyHostToDevice));
+  CNLD_CK(cudaMemcpy(p.nptr, pb.nptr.data(), sizeof(uint) * pb.nptr.size(), cudaMemcpyHostToDevice));
+  CNLD_CK(cudaMemcpy(p.tri, pb.tri.data(), sizeof(double) * pb.tri.size(), cudaMemcpyHostToDevice));
+  CNLD_CK(cudaMemcpy(p.node, pb.node.data(), sizeof(uint) * pb.node.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+uint pres_tile_obs() { return PV_OT; }
+
+// PV (column-major mc x nv, leading dimension lda >= mc) = pressure vectors of mc observation points
+int pres_pvec_tiles(cudaStream_t st, const PresPlan &p, const BemDev &b, const double *d_obs, uint mc, double k,
+                    double c, double rho, cplx *d_PV, size_t lda) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  CNLD_CK(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    CNLD_CK(cudaFuncSetAttribute(k_pvec_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, PV_SMEM));
+    attr_set[dev & 63] = true;
+  }
+  // a vertex no triangle references never gets written by the kernel: its column must read as zero
+  for (uint v : p.untouched) CNLD_CK(cudaMemsetAsync(d_PV + (size_t)v * lda, 0, sizeof(cplx) * mc, st));
+  const double scale = -(k * c) * (k * c) * rho * 2.0;
+  k_pvec_tiles<<<(mc + PV_OT - 1) / PV_OT, PV_OT, PV_SMEM, st>>>(mc, d_obs, p.nchunk, p.tptr, p.tri, p.nptr, p.node, k,
+                                                                  scale, d_PV, lda);
+  CNLD_CK_LAUNCH();
+  return 0;
+}
+
+// out[src][obs0 .. obs0 + mc) (row stride ldo) = PV (mc x nv) . disp[src][:]   -- one DMMA ZGEMM
+int pres_contract(cudaStream_t st, const BemDev &b, const cplx *d_PV, size_t lda, uint mc, const cplx *d_disp,
+                  uint nsrc, cplx *d_out, size_t ldo) {
+  return zgemm3m(st, mc, nsrc, b.nv, 1.0, d_PV, lda, d_disp, b.nv, 0.0, d_out, ldo);
 }
 
 int pres_points(cudaStream_t st, const BemDev &b, double *d_sp) {

@@ -190,6 +190,34 @@ int cnld_b200_pressure(cnld_ctx *ctx, const double *obs, cnld_uint nobs, const d
                        cnld_uint nk, double c, double rho, const cnld_field *disp,
                        cnld_uint nsrc, cnld_field *p);
 
+/* Many sources (nsrc = P source patches) at 10^5..10^6 observation points: the loop of
+ * array_patch_pres_imp_resp (cnld/bem_pressure.pyx:103-112) for all points at once.  The observation
+ * points stay on the device; per wavenumber exp(-j k r)/r is evaluated once per (point, source point),
+ * folded to node space on chip and contracted with all displacement columns by one FP64 tensor-core
+ * ZGEMM per chunk of points.  cnld_b200_pressure takes this path by itself when nsrc > 4. */
+typedef struct cnld_pfield cnld_pfield;
+cnld_pfield *cnld_b200_pfield_create(cnld_ctx *ctx, const double *obs, cnld_uint nobs, cnld_uint nsrc_max);
+void cnld_b200_pfield_destroy(cnld_pfield *pf);
+/* page-lock the caller's result buffer in place (D2H of a chunk then overlaps the next chunk) */
+int cnld_b200_pfield_pin(cnld_pfield *pf, void *ptr, size_t bytes);
+/* p[isrc][iobs] (HOST, nullable: results stay on the device) for one wavenumber, disp[nsrc][nv] HOST */
+int cnld_b200_pfield_run(cnld_pfield *pf, double k, double c, double rho, const cnld_field *disp,
+                         cnld_uint nsrc, cnld_field *p);
+/* same, with the displacements of the previous run still on the device (device-resident timing) */
+int cnld_b200_pfield_run_device(cnld_pfield *pf, double k, double c, double rho, cnld_uint nsrc);
+/* results of the last run: all points (idx = NULL, p[nsrc][nobs]) or the listed ones (p[nsrc][nidx]) */
+int cnld_b200_pfield_fetch(cnld_pfield *pf, cnld_uint nsrc, const cnld_uint *idx, cnld_uint nidx,
+                           cnld_field *p);
+/* out[7]: seconds of the last run in the pressure-vector kernel, in the contraction, in total (CUDA
+ * events on the launch stream), chunks, observation points per chunk, triangle chunks of the mesh,
+ * node-space writes per observation point */
+int cnld_b200_pfield_info(cnld_pfield *pf, double *out);
+/* Host-only view of the triangle chunks the pressure-vector kernel walks (tests): counts[6] = {chunks,
+ * chunk-local node entries, max triangles per chunk, max nodes per chunk, entries that accumulate onto
+ * an earlier chunk's write, vertices without a triangle}; order[nt] (nullable) = triangles in chunk order. */
+int cnld_b200_pres_plan_stats(cnld_uint nv, cnld_uint nt, const double *x, const cnld_uint *t,
+                              cnld_uint *counts, cnld_uint *order);
+
 /* ---- H-matrix path (arrays too large to factor densely) ---------------------------------
  * Replaces build_bem3d_cluster(bem, clf, LINEAR) (include/bem3d.h:1493), build_strict_block /
  * build_nonstrict_block(root, root, &eta, admissible_*) (include/block.h:216-248, :78-140),

@@ -89,6 +89,49 @@ def test_c3_4x4_array_properties():
     sw.close()
 
 
+def test_c3_4x4_array_vs_oracle(po):
+    """configs[2] against the ORACLE at full size (N = 14 800): one frequency of the sweep grid, the
+    symmetric-part path and the reference's general elimination, node displacements and patch averages
+    (generate_db.py:82-99).  About a minute of host time for the oracle's N x N assembly + LU."""
+    oarr = po.matrix_array(nelem=(4, 4))
+    am, blocks = po.array_mesh(oarr, 21), po.array_fem(oarr, 21)
+    f = float(np.linspace(0.025e6, 50e6, 2000)[1131])
+    Xo, XPo = po.solve_frequency(am, blocks, f, blocked=True)
+    for symmetric in (True, False):
+        setup, sw = _sweep((4, 4), 21, nstreams=1, symmetric=symmetric)
+        xp, xn, _ = sw.run(np.array([f]))
+        assert _rel(xn[0].T, Xo) < 1e-6 and _rel(xp[0].T, XPo) < 1e-6, symmetric
+        sw.close()
+
+
+def test_c5_field_pressure_vs_oracle(po):
+    """configs[4] mesh (4x4, N = 14 800, T = 28 224), P = 144 sources, 10^5 points of the observation grid
+    (several chunks of the node-space path, last one ragged): sampled points against the oracle."""
+    from cnld import _lib
+    oarr = po.matrix_array(nelem=(4, 4))
+    am = po.array_mesh(oarr, 21)
+    ctx = _lib.Context(am.vertices, am.triangles)
+    rng = np.random.default_rng(3)
+    g = np.linspace(-1e-3, 1e-3, 100)
+    gx, gy, gz = np.meshgrid(g, g, np.linspace(0.1e-3, 2.1e-3, 10), indexing='ij')
+    obs = np.ascontiguousarray(np.c_[gx.ravel(), gy.ravel(), gz.ravel()])
+    disp = (rng.standard_normal((144, am.nvertices)) + 1j * rng.standard_normal((144, am.nvertices))) * 1e-9
+    k = 2 * np.pi * 23.7e6 / 1500.
+    pf = _lib.PressureField(ctx, obs, 144)
+    pf.run(k, disp, fetch=False)
+    info = pf.info()
+    assert info['chunks'] == -(-len(obs) // info['obs_per_chunk'])
+    idx = np.sort(rng.choice(len(obs), 3000, replace=False)).astype(np.uint32)
+    idx[-1] = len(obs) - 1
+    got = pf.fetch(144, idx)
+    ref = np.empty_like(got)
+    for b0 in range(0, len(idx), 1000):
+        ref[:, b0:b0 + 1000] = disp @ po.pres_vector(am, obs[idx[b0:b0 + 1000]], k).T
+    assert _rel(got, ref) < 1e-9
+    pf.close()
+    ctx.close()
+
+
 def test_empty_and_ragged_inputs():
     """Zero frequencies, one frequency, a frequency list not divisible by the stream count,
     matrix sizes that are not multiples of any tile size."""

@@ -203,6 +203,43 @@ def test_pressure_vs_oracle(L, po):
     ctx.close()
 
 
+def test_pressure_many_sources_vs_oracle(L, po):
+    """nsrc > 4 takes the node-space path (k_pvec_tiles + ZGEMM): ragged point counts (not a multiple of
+    the 128-point tile), one point, source counts that are not a multiple of the ZGEMM tile."""
+    arr, am, blocks, ctx = _setup_sweep(L, po, (2, 1), 4)
+    rng = np.random.default_rng(2)
+    for nobs, nsrc in [(1, 5), (300, 7), (1000, 18)]:
+        obs = np.c_[rng.uniform(-1e-3, 1e-3, nobs), rng.uniform(-1e-3, 1e-3, nobs), rng.uniform(1e-4, 2.1e-3, nobs)]
+        ks = np.array([0.0, 2 * np.pi * 3e6 / 1500, 2 * np.pi * 41e6 / 1500])
+        disp = rng.standard_normal((3, nsrc, am.nvertices)) + 1j * rng.standard_normal((3, nsrc, am.nvertices))
+        p = ctx.pressure(obs, ks, disp)
+        for ik, k in enumerate(ks):
+            ref = disp[ik] @ po.pres_vector(am, obs, k).T
+            if k == 0:
+                assert np.abs(p[ik]).max() == 0 and np.abs(ref).max() == 0      # scale -(k c)^2 2 rho = 0
+            else:
+                assert _rel(p[ik], ref) < 1e-11
+    # the resident-points object: reusable page-locked output, device-resident rerun, sampled fetch
+    obs = np.c_[rng.uniform(-1e-3, 1e-3, 777), rng.uniform(-1e-3, 1e-3, 777), rng.uniform(1e-4, 2.1e-3, 777)]
+    pf = L.PressureField(ctx, obs, 9)
+    disp = rng.standard_normal((9, am.nvertices)) + 1j * rng.standard_normal((9, am.nvertices))
+    k = 2 * np.pi * 11e6 / 1500
+    out = np.empty((9, 777), dtype=np.complex128)
+    p = pf.run(k, disp, out=out)
+    ref = disp @ po.pres_vector(am, obs, k).T
+    assert p is out and _rel(p, ref) < 1e-11
+    pf.run_device(k, 9)
+    idx = np.array([0, 5, 776, 5], dtype=np.uint32)
+    assert _rel(pf.fetch(9, idx), ref[:, idx]) < 1e-11
+    assert _rel(pf.fetch(9), ref) < 1e-11
+    # fewer sources than the capacity, and agreement with the few-source kernel (k_pressure)
+    assert _rel(pf.run(k, disp[:3]), ctx.pressure(obs, [k], disp[None, :3])[0]) < 1e-12
+    info = pf.info()
+    assert info['chunks'] == 1 and info['tri_chunks'] >= 1
+    pf.close()
+    ctx.close()
+
+
 def test_nearfield_subblock_vs_oracle_and_dense(L, po):
     am = po.array_mesh(po.matrix_array(nelem=(2, 1)), 5)
     k = 2 * np.pi * 9e6 / 1500
