@@ -68,6 +68,7 @@ int pres_points(cudaStream_t st, const BemDev &b, double *d_sp);
 // many-source path: triangle chunks (host-built once per mesh) -> node-space pressure vectors of a
 // tile of observation points -> one ZGEMM against the displacements
 struct PresPlan {
+  int variant = 0;                     // kernel geometry the chunks were cut for (PV_VARIANTS)
   uint nchunk = 0, nentries = 0;       // nentries = sum of chunk-local nodes (PV writes per observation point)
   uint *tptr = nullptr, *nptr = nullptr, *node = nullptr;
   double *tri = nullptr;
@@ -77,6 +78,9 @@ int pres_plan_build(const BemDev &b, const double *hx, const uint *ht, PresPlan 
 void pres_plan_free(PresPlan &p);
 int pres_plan_stats(uint nv, uint nt, const double *hx, const uint *ht, uint *counts, uint *order);
 uint pres_tile_obs();
+uint pres_tile_ctas();
+int pres_set_variant(int v);
+extern int g_pvec_variant;
 int pres_pvec_tiles(cudaStream_t st, const PresPlan &p, const BemDev &b, const double *d_obs, uint mc, double k,
                     double c, double rho, cplx *d_PV, size_t lda);
 int pres_contract(cudaStream_t st, const BemDev &b, const cplx *d_PV, size_t lda, uint mc, const cplx *d_disp,

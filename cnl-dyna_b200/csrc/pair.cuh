@@ -51,10 +51,23 @@ __device__ __forceinline__ void sincos_fast(double x, double &sn, double &cs) {
   cs = ((q + 1) & 2) ? -b : b;
 }
 
+// 1/sqrt(x) for positive, normal x (squared distances between distinct quadrature points: never
+// zero, denormal or infinite on this path).  MUFU.RSQ64H seed + one third-order step
+// y = y0 + y0 e (1/2 + 3/8 e), e = 1 - x y0^2 -- the same arithmetic as the library rsqrt() minus its
+// range check, whose branch (BSSY / BRA / BSYNC per call) keeps the compiler from interleaving
+// independent kernel evaluations (ncu: 'wait' stalls on every dependent DFMA of a serialised chain).
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double e = fma(x, -(y0 * y0), 1.0);
+  const double p = fma(e, 0.375, 0.5);
+  return fma(p, y0 * e, y0);
+}
+
 // exp(i kr r) * exp(-ki r) / r  for squared distance r2
 template <bool CPLXK>
 __device__ __forceinline__ cplx helmholtz(double r2, double kr, double ki) {
-  double rinv = rsqrt(r2);
+  double rinv = rsqrt_pos(r2);
   double r = r2 * rinv;
   if (CPLXK) rinv *= exp(-ki * r);
   double s, c;

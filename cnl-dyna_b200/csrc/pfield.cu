@@ -31,6 +31,7 @@ __global__ void k_pf_gather(uint nsrc, uint nidx, const uint *__restrict__ idx, 
 }
 
 int ensure_plan(cnld_ctx *c) {
+  if (c->pplan_ready && c->pplan.variant != g_pvec_variant) { pres_plan_free(c->pplan); c->pplan_ready = false; }
   if (c->pplan_ready) return 0;
   if (pres_plan_build(c->bem, c->h_x.data(), c->h_t.data(), c->pplan)) return -1;
   c->pplan_ready = true;
@@ -104,7 +105,7 @@ cnld_pfield *cnld_b200_pfield_create(cnld_ctx *c, const double *obs, cnld_uint n
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->bem.device);
   const uint tile = pres_tile_obs();
-  uint wave = (uint)nsm * 2 * tile;                         // one full wave of k_pvec_tiles (2 CTAs per SM)
+  uint wave = (uint)nsm * pres_tile_ctas() * tile;           // one full wave of k_pvec_tiles CTAs
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
   const size_t fixed = sizeof(cplx) * ((size_t)nsrc_max * nobs + (size_t)nsrc_max * nv) + 24 * (size_t)nobs;
@@ -202,6 +203,8 @@ int cnld_b200_pres_plan_stats(cnld_uint nv, cnld_uint nt, const double *x, const
     if (t[i] >= nv) { set_error("triangle vertex index out of range"); return -1; }
   return pres_plan_stats(nv, nt, x, t, counts, order);
 }
+
+int cnld_b200_set_pvec_variant(int v) { return pres_set_variant(v); }
 
 int cnld_b200_pfield_info(cnld_pfield *pf, double *out) {
   if (!pf || !out) { set_error("null argument"); return -1; }

@@ -39,7 +39,7 @@ __global__ void k_pres_vector(uint nt, const double *__restrict__ x, const uint 
       double xi = c_xi[q], eta = c_eta[q], n0 = 1.0 - xi - eta;
       double xs = x1 * n0 + x2 * xi + x3 * eta, ys = y1 * n0 + y2 * xi + y3 * eta;
       double r2 = (ox - xs) * (ox - xs) + (oy - ys) * (oy - ys) + oz * oz;
-      double rinv = rsqrt(r2), r = r2 * rinv, s, c;
+      double rinv = rsqrt_pos(r2), r = r2 * rinv, s, c;
       sincos_fast(k * r, s, c);
       double f = scale * (1.0 / 3) * INV4PI * rinv * da;
       double cr = f * c, ci = -f * s;
@@ -110,7 +110,7 @@ k_pressure(uint nobs, const double *__restrict__ obs, uint npts, const double *_
     for (uint i = 0; i < np; i++) {
       double dx = ox - s_xy[i][0], dy = oy - s_xy[i][1];
       double r2 = fma(dx, dx, fma(dy, dy, oz2));
-      double rinv = rsqrt(r2), r = r2 * rinv, sn, cs;
+      double rinv = rsqrt_pos(r2), r = r2 * rinv, sn, cs;
       sincos_fast(k * r, sn, cs);
       double er = cs * rinv, ei = -sn * rinv;
 #pragma unroll
@@ -136,18 +136,24 @@ k_pressure(uint nobs, const double *__restrict__ obs, uint npts, const double *_
 // own column: no atomics, no conflicts).  After the chunk the tile is written to PV (column-major
 // obs x node: coalesced along obs); a node that an earlier chunk already wrote is accumulated --
 // by the same thread that wrote it, so plain loads/stores are ordered.
-constexpr int PV_OT = 128, PV_NC = 48, PV_TC = 64;
-constexpr int PV_SMEM = PV_NC * PV_OT * (int)sizeof(cplx) + 2 * PV_TC * 8 * (int)sizeof(double);
+template <int OT, int NC, int TC, int TB>
+struct PvCfg {
+  static constexpr int SMEM = NC * OT * (int)sizeof(cplx);
+};
 
-__global__ void __launch_bounds__(PV_OT, 2)
+// TB triangles (3 TB independent kernel evaluations) are evaluated before their shared-memory updates;
+// the staged triangle records live in a separate static array, so the compiler knows the tile updates
+// do not alias them and can overlap the next batch's evaluations with this batch's updates.
+template <int OT, int NC, int TC, int TB, int MINB>
+__global__ void __launch_bounds__(OT, MINB)
 k_pvec_tiles(uint nobs, const double *__restrict__ obs, uint nchunk, const uint *__restrict__ tptr,
              const double *__restrict__ tri, const uint *__restrict__ nptr, const uint *__restrict__ node,
              double k, double scale, cplx *PV, size_t lda) {
   extern __shared__ __align__(16) unsigned char pv_smem[];
+  __shared__ __align__(16) double stage[2][(TC + TB) * 8];
   cplx *tile = reinterpret_cast<cplx *>(pv_smem);
-  double *stage = reinterpret_cast<double *>(tile + PV_NC * PV_OT);
   const int tid = threadIdx.x;
-  const uint o = blockIdx.x * PV_OT + tid;
+  const uint o = blockIdx.x * OT + tid;
   const bool live = o < nobs;
   double ox = 0, oy = 0, oz2 = 1;
   if (live) { ox = obs[3 * (size_t)o]; oy = obs[3 * (size_t)o + 1]; oz2 = obs[3 * (size_t)o + 2]; oz2 *= oz2; }
@@ -155,38 +161,51 @@ k_pvec_tiles(uint nobs, const double *__restrict__ obs, uint nchunk, const uint 
   const double w6 = scale * (1.0 / 6), w2 = scale * 0.5;
   for (uint c = 0; c < nchunk; c++) {
     const uint t0 = tptr[c], ntc = tptr[c + 1] - t0, n0 = nptr[c], nn = nptr[c + 1] - n0;
-    double *sg = stage + (c & 1) * (PV_TC * 8);
+    double *sg = stage[c & 1];
     {
       const double2 *src = reinterpret_cast<const double2 *>(tri + (size_t)t0 * 8);
       double2 *dst = reinterpret_cast<double2 *>(sg);
-      for (uint i = tid; i < ntc * 4; i += PV_OT) dst[i] = src[i];
-    }
-    for (uint ln = 0; ln < nn; ln++) col[ln * PV_OT] = make_double2(0.0, 0.0);
-    __syncthreads();
-#pragma unroll 2
-    for (uint i = 0; i < ntc; i++) {
-      const double2 *e = reinterpret_cast<const double2 *>(sg + 8 * i);
-      const double2 p0 = e[0], p1 = e[1], p2 = e[2], ws = e[3];
-      double er[3], ei[3];
-      const double px[3] = {p0.x, p1.x, p2.x}, py[3] = {p0.y, p1.y, p2.y};
-#pragma unroll
-      for (int q = 0; q < 3; q++) {
-        double dx = ox - px[q], dy = oy - py[q];
-        double r2 = fma(dx, dx, fma(dy, dy, oz2));
-        double rinv = rsqrt(r2), r = r2 * rinv, sn, cs;
-        sincos_fast(k * r, sn, cs);
-        er[q] = cs * rinv; ei[q] = -sn * rinv;
+      for (uint i = tid; i < ntc * 4; i += OT) dst[i] = src[i];
+      // pad to a multiple of TB with copies of the first record at weight 0
+      const uint npad = (ntc + TB - 1) / TB * TB;
+      for (uint i = ntc * 4 + tid; i < npad * 4; i += OT) {
+        double2 v = src[i & 3];
+        if ((i & 3) == 3) v.x = 0.0;
+        dst[i] = v;
       }
-      const double a6 = ws.x * w6, a2 = ws.x * w2;
-      const double sr = a6 * (er[0] + er[1] + er[2]), si = a6 * (ei[0] + ei[1] + ei[2]);
-      const unsigned long long sl = (unsigned long long)__double_as_longlong(ws.y);
+    }
+    for (uint ln = 0; ln < nn; ln++) col[ln * OT] = make_double2(0.0, 0.0);
+    __syncthreads();
+    for (uint i = 0; i < ntc; i += TB) {
+      double er[TB][3], ei[TB][3], a6[TB], a2[TB];
+      unsigned long long sl[TB];
 #pragma unroll
-      for (int l = 0; l < 3; l++) {
-        const uint s = (uint)(sl >> (8 * l)) & 0xffu;
-        cplx v = col[s * PV_OT];
-        v.x += fma(a2, er[l], sr);
-        v.y += fma(a2, ei[l], si);
-        col[s * PV_OT] = v;
+      for (int b = 0; b < TB; b++) {
+        const double2 *e = reinterpret_cast<const double2 *>(sg + 8 * (i + b));
+        const double2 p0 = e[0], p1 = e[1], p2 = e[2], ws = e[3];
+        const double px[3] = {p0.x, p1.x, p2.x}, py[3] = {p0.y, p1.y, p2.y};
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          double dx = ox - px[q], dy = oy - py[q];
+          double r2 = fma(dx, dx, fma(dy, dy, oz2));
+          double rinv = rsqrt_pos(r2), r = r2 * rinv, sn, cs;
+          sincos_fast(k * r, sn, cs);
+          er[b][q] = cs * rinv; ei[b][q] = -sn * rinv;
+        }
+        a6[b] = ws.x * w6; a2[b] = ws.x * w2;
+        sl[b] = (unsigned long long)__double_as_longlong(ws.y);
+      }
+#pragma unroll
+      for (int b = 0; b < TB; b++) {
+        const double sr = a6[b] * (er[b][0] + er[b][1] + er[b][2]), si = a6[b] * (ei[b][0] + ei[b][1] + ei[b][2]);
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+          const uint s = (uint)(sl[b] >> (8 * l)) & 0xffu;
+          cplx v = col[s * OT];
+          v.x += fma(a2[b], er[b][l], sr);
+          v.y += fma(a2[b], ei[b][l], si);
+          col[s * OT] = v;
+        }
       }
     }
     if (live) {
@@ -194,13 +213,20 @@ k_pvec_tiles(uint nobs, const double *__restrict__ obs, uint nchunk, const uint 
       for (uint ln = 0; ln < nn; ln++) {
         const uint nd = node[n0 + ln];
         cplx *dst = PV + (size_t)(nd & 0x7fffffffu) * lda + o;
-        cplx v = col[ln * PV_OT];
+        cplx v = col[ln * OT];
         if (nd >> 31) { cplx old = *dst; v.x += old.x; v.y += old.y; }
         *dst = v;
       }
     }
   }
 }
+
+// variants (cnld_b200_set_pvec_variant): {observation points per CTA, nodes per chunk, triangles per
+// chunk, triangles per batch, CTAs per SM}
+struct PvVariant { int ot, nc, tc, tb, ctas; };
+constexpr PvVariant PV_VARIANTS[] = {{128, 48, 64, 1, 2}, {128, 48, 64, 2, 2}, {128, 24, 32, 1, 4}, {128, 24, 32, 2, 4},
+                                     {64, 48, 64, 2, 3}, {128, 32, 40, 2, 3}, {128, 16, 20, 1, 6}, {128, 24, 32, 3, 4}};
+constexpr int PV_NVARIANTS = (int)(sizeof(PV_VARIANTS) / sizeof(PV_VARIANTS[0]));
 }  // namespace
 
 int pres_vector(cudaStream_t st, const BemDev &b, const double *d_obs, uint nobs, double k, double c,
@@ -213,6 +239,8 @@ int pres_vector(cudaStream_t st, const BemDev &b, const double *d_obs, uint nobs
 }
 
 
+int g_pvec_variant = 3;
+
 // ---- PresPlan: triangle chunks of k_pvec_tiles (host, once per mesh) ----------------------------
 namespace {
 struct PlanBuilder {
@@ -224,6 +252,7 @@ struct PlanBuilder {
   std::vector<uint8_t> touched;
   std::vector<uint> scratch;
   const double *g;
+  uint max_tc = 64, max_nc = 48;
   uint distinct_nodes(uint lo, uint hi) {
     scratch.clear();
     for (uint i = lo; i < hi; i++) for (int l = 0; l < 3; l++) scratch.push_back(t[3 * order[i] + l]);
@@ -260,7 +289,7 @@ struct PlanBuilder {
     nptr.push_back((uint)node.size());
   }
   void split(uint lo, uint hi) {
-    if (hi - lo <= (uint)PV_TC && distinct_nodes(lo, hi) <= (uint)PV_NC) { emit(lo, hi); return; }
+    if (hi - lo <= max_tc && distinct_nodes(lo, hi) <= max_nc) { emit(lo, hi); return; }
     double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
     for (uint i = lo; i < hi; i++)
       for (int d = 0; d < 3; d++) {
@@ -287,6 +316,7 @@ void pres_plan_free(PresPlan &p) {
 
 // host part: chunks of the mesh (x, t, g = 2 * area per triangle)
 static void pres_plan_host(uint nv, uint nt, const double *hx, const uint *ht, const double *hg, PlanBuilder &pb) {
+  pb.max_tc = PV_VARIANTS[g_pvec_variant].tc; pb.max_nc = PV_VARIANTS[g_pvec_variant].nc;
   pb.x = hx; pb.t = ht; pb.nv = nv; pb.g = hg;
   pb.cen.resize(3 * (size_t)nt);
   for (uint tt = 0; tt < nt; tt++)
@@ -324,6 +354,7 @@ int pres_plan_build(const BemDev &b, const double *hx, const uint *ht, PresPlan 
   std::vector<double> hg(b.nt);
   CNLD_CK(cudaMemcpy(hg.data(), b.g, sizeof(double) * b.nt, cudaMemcpyDeviceToHost));
   pres_plan_host(b.nv, b.nt, hx, ht, hg.data(), pb);
+  p.variant = g_pvec_variant;
   p.nchunk = (uint)pb.tptr.size() - 1;
   p.nentries = (uint)pb.node.size();
   p.untouched.clear();
@@ -339,25 +370,52 @@ int pres_plan_build(const BemDev &b, const double *hx, const uint *ht, PresPlan 
   return 0;
 }
 
-uint pres_tile_obs() { return PV_OT; }
+uint pres_tile_obs() { return PV_VARIANTS[g_pvec_variant].ot; }
+uint pres_tile_ctas() { return PV_VARIANTS[g_pvec_variant].ctas; }
+int pres_set_variant(int v) {
+  if (v < 0 || v >= PV_NVARIANTS) { set_error("pvec variant %d outside 0..%d", v, PV_NVARIANTS - 1); return -1; }
+  g_pvec_variant = v;
+  return 0;
+}
 
-// PV (column-major mc x nv, leading dimension lda >= mc) = pressure vectors of mc observation points
-int pres_pvec_tiles(cudaStream_t st, const PresPlan &p, const BemDev &b, const double *d_obs, uint mc, double k,
-                    double c, double rho, cplx *d_PV, size_t lda) {
+namespace {
+template <int V>
+int launch_pvec(cudaStream_t st, const PresPlan &p, const double *d_obs, uint mc, double k, double scale, cplx *d_PV,
+                size_t lda) {
+  constexpr PvVariant C = PV_VARIANTS[V];
+  auto kern = k_pvec_tiles<C.ot, C.nc, C.tc, C.tb, C.ctas>;
+  constexpr int SMEM = C.nc * C.ot * (int)sizeof(cplx);
   static bool attr_set[64] = {false};
   int dev = 0;
   CNLD_CK(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    CNLD_CK(cudaFuncSetAttribute(k_pvec_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, PV_SMEM));
+    CNLD_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set[dev & 63] = true;
   }
+  kern<<<(mc + C.ot - 1) / C.ot, C.ot, SMEM, st>>>(mc, d_obs, p.nchunk, p.tptr, p.tri, p.nptr, p.node, k, scale, d_PV, lda);
+  CNLD_CK_LAUNCH();
+  return 0;
+}
+}  // namespace
+
+// PV (column-major mc x nv, leading dimension lda >= mc) = pressure vectors of mc observation points
+int pres_pvec_tiles(cudaStream_t st, const PresPlan &p, const BemDev &b, const double *d_obs, uint mc, double k,
+                    double c, double rho, cplx *d_PV, size_t lda) {
   // a vertex no triangle references never gets written by the kernel: its column must read as zero
   for (uint v : p.untouched) CNLD_CK(cudaMemsetAsync(d_PV + (size_t)v * lda, 0, sizeof(cplx) * mc, st));
   const double scale = -(k * c) * (k * c) * rho * 2.0;
-  k_pvec_tiles<<<(mc + PV_OT - 1) / PV_OT, PV_OT, PV_SMEM, st>>>(mc, d_obs, p.nchunk, p.tptr, p.tri, p.nptr, p.node, k,
-                                                                  scale, d_PV, lda);
-  CNLD_CK_LAUNCH();
-  return 0;
+  switch (p.variant) {
+    case 0: return launch_pvec<0>(st, p, d_obs, mc, k, scale, d_PV, lda);
+    case 1: return launch_pvec<1>(st, p, d_obs, mc, k, scale, d_PV, lda);
+    case 2: return launch_pvec<2>(st, p, d_obs, mc, k, scale, d_PV, lda);
+    case 3: return launch_pvec<3>(st, p, d_obs, mc, k, scale, d_PV, lda);
+    case 4: return launch_pvec<4>(st, p, d_obs, mc, k, scale, d_PV, lda);
+    case 5: return launch_pvec<5>(st, p, d_obs, mc, k, scale, d_PV, lda);
+    case 6: return launch_pvec<6>(st, p, d_obs, mc, k, scale, d_PV, lda);
+    case 7: return launch_pvec<7>(st, p, d_obs, mc, k, scale, d_PV, lda);
+  }
+  set_error("pvec variant %d", p.variant);
+  return -1;
 }
 
 // out[src][obs0 .. obs0 + mc) (row stride ldo) = PV (mc x nv) . disp[src][:]   -- one DMMA ZGEMM
