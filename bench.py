@@ -365,12 +365,208 @@ def bench_c5(args, rank, world, local):
         dist.destroy_process_group()
 
 
-def bench_c4(args, rank, world, local):
-    raise SystemExit('bench.py --config c4: not wired yet')
+C4_METRIC = 'frequencies solved/s (ACA H-matrix assemble + GMRES, all 2304 source patches), 16x16 CMUT array'
+C4_H = dict(clf=16, eta=0.8, admis='2', strict=True, kmax=64)           # generate_db.py:264-275 defaults
+C4_SOLVE = dict(eps_aca=1e-2, tol=1e-6, restart=50, maxiter=300, batch=96)
+
+
+def _c4_cpu_sample(po, am, k, frac=64, seed=0):
+    """Oracle H-matrix work on every `frac`-th leaf: assemble (ACA / near field) and apply to one vector.
+    Returns (assemble seconds, matvec seconds, leaves sampled, leaves total)."""
+    ct = po.ClusterTree(am, C4_H['clf'])
+    rc, cc, adm = po.build_block(ct, C4_H['eta'], C4_H['strict'])
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(am.nvertices) + 1j * rng.standard_normal(am.nvertices)
+    pick = np.arange(seed % frac, len(rc), frac)
+    leaves = []
+    t0 = time.perf_counter()
+    for i in pick:
+        ri, ci = ct.idx(rc[i]), ct.idx(cc[i])
+        leaves.append((ri, ci, po.aca_block(am, k, ri, ci, C4_SOLVE['eps_aca']) if adm[i] else po.nearfield(am, k, ri, ci)))
+    ta = time.perf_counter() - t0
+    y = np.zeros(am.nvertices, dtype=np.complex128)
+    t0 = time.perf_counter()
+    for ri, ci, d in leaves:
+        y[ri] += d[0] @ (d[1].T @ x[ci]) if isinstance(d, tuple) else d @ x[ci]
+    tm = time.perf_counter() - t0
+    return ta, tm, len(pick), len(rc)
+
+
+def _c4_cpu_line(po, am, freqs, P, iters_mean):
+    """CPU estimate of one C4 frequency from a 1/64 sample of the leaves (assembly + one matvec),
+    extrapolated to all leaves, all P right-hand sides and the measured GMRES iteration count."""
+    ta = tm = 0.0
+    for f in freqs:
+        a, m, ns, nl = _c4_cpu_sample(po, am, 2 * np.pi * f / 1500.)
+        ta += a * nl / ns
+        tm += m * nl / ns
+    ta, tm = ta / len(freqs), tm / len(freqs)
+    sec = ta + tm * P * (iters_mean + 2)          # + initial residual and the final update
+    return sec, {'value': 1.0 / sec, 'unit': UNIT, 'cores': po.lib().orc_num_threads(), 'kind': 'port',
+                 'sample': f'every 64th H-matrix leaf assembled and applied to one vector by the oracle (per-leaf C calls from '
+                           f'Python), extrapolated x64 x {P} right-hand sides x {iters_mean + 2:.1f} matvecs per right-hand side; '
+                           f'assembly {ta:.1f} s + matvecs {tm * P * (iters_mean + 2):.0f} s per frequency'}
 
 
 def bench_c4_reference(args, rank):
-    raise SystemExit('bench.py --config c4 --impl reference: not wired yet')
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import pyoracle as po
+    po.build()
+    nelem, refn = CONFIGS['c4'][:2]
+    am = po.array_mesh(po.matrix_array(nelem=nelem), refn)
+    P = 9 * nelem[0] * nelem[1]
+    steps = min(args.steps, 2)
+    freqs = workload_freqs('c4', steps)
+    t0 = time.perf_counter()
+    sec, base = _c4_cpu_line(po, am, freqs, P, 15.0)
+    print(json.dumps({
+        'impl': 'reference', 'metric': C4_METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': 0, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'complex128 (f64)', 'data': 'synthetic',
+        'config': {'workload': f'c4: 16x16 CMUT array refn={refn} (N={am.nvertices}), P={P}, GMRES iterations assumed 15',
+                   'wall_seconds_sampled': time.perf_counter() - t0},
+        'cpu_baseline': base, 'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}), flush=True)
+
+
+def bench_c4(args, rank, world, local):
+    """configs[3]: 16x16 array (N = 194 816, P = 2 304), one frequency per step through the ACA H-matrix +
+    batched GMRES path; frequencies spread over [0.1, 50] MHz, dealt cyclically to the ranks."""
+    import torch
+    import torch.distributed as dist
+    from cnld import _lib, arrays
+    from cnld.sweep import SweepSetup, broadcast_setup
+    if _lib.device_count() == 0:
+        raise SystemExit('bench.py: no CUDA device -- libcnld_b200 has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    nelem, refn = CONFIGS['c4'][:2]
+    t_setup = time.perf_counter()
+    setup = SweepSetup.from_abstract(arrays.matrix_array(nelem=nelem), refn) if rank == 0 else None
+    if world > 1:
+        setup = broadcast_setup(setup, rank, torch.device('cuda', local))
+    ctx = _lib.Context(setup.vertices, setup.triangles, q_reg=setup.q_reg, q_sing=setup.q_sing, device=local)
+    ctx.set_mbk(setup.K, setup.M, setup.B)
+    ctx.set_loads(setup.F, setup.AVG, setup.on_boundary)
+    H = _lib.HMatrix(ctx, **C4_H)
+    t_setup = time.perf_counter() - t_setup
+    N, P, T = setup.nnodes, setup.npatch, len(setup.triangles)
+    nsteps = args.steps + args.warmup
+    # step s of rank r solves grid frequency (s * world + r): the cyclic deal of sweep.shard_cyclic
+    allf = workload_freqs('c4', 2 * nsteps * world)
+    mine = allf[rank::world]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for w in range(args.warmup):
+        H.sweep(mine[w:w + 1], c=setup.c, rho=setup.rho, want_nodes=False, **C4_SOLVE)
+    fp64_peak = _lib.bench_dfma(3, device=local)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0, fl0 = _lib.launch_count(), _lib.dmma_flop_count()
+    barrier()
+    dev_s, its, capped = 0.0, [], 0
+    for s_ in range(args.steps):
+        f = mine[args.warmup + s_:args.warmup + s_ + 1]
+        xp, _, it, t = H.sweep(f, c=setup.c, rho=setup.rho, want_nodes=False, **C4_SOLVE)
+        dev_s += float(t.sum())
+        its.append(float(it.mean()))
+        capped += H.capped()[1]
+    barrier()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.finish() if rank == 0 else None
+    dt = reduce_max(dev_s)
+    value = args.steps * world / dt
+    # ---- end to end: the same call by the wall clock (frequencies in, patch responses back on the host) --
+    barrier()
+    t0 = time.perf_counter()
+    for s_ in range(args.steps):
+        f = mine[nsteps + s_:nsteps + s_ + 1]
+        xp, _, it2, _ = H.sweep(f, c=setup.c, rho=setup.rho, want_nodes=False, **C4_SOLVE)
+    barrier()
+    dte = reduce_max(time.perf_counter() - t0)
+    e2e = args.steps * world / dte
+    assert np.isfinite(xp).all() and np.abs(xp).max() > 0
+    line = None
+    if rank == 0:
+        # ---- roofline leg: the H-matvec with the GMRES batch width, on the H-matrix of the last frequency ----
+        info = H.info()
+        nb = C4_SOLVE['batch']
+        mv_s = H.bench_matvec(nb, 5)
+        mv1_s = H.bench_matvec(1, 5)
+        ach = 6.0 * info['stored'] * nb / mv_s / 1e12
+        hbm = MEASURED_HBM()
+        # ---- parity: sampled rows of the matvec against exactly integrated rows ----------------------
+        f_last = float(mine[nsteps + args.steps - 1])
+        k_last = 2 * np.pi * f_last / setup.c
+        rng = np.random.default_rng(0)
+        x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+        rows = np.sort(rng.choice(N, 48, replace=False)).astype(np.uint32)
+        y = H.matvec(x)
+        exact = ctx.nearfield(k_last, rows, np.arange(N, dtype=np.uint32)) @ x
+        row_err = float(np.linalg.norm(y[rows] - exact) / np.linalg.norm(exact))
+        line = {
+            'metric': C4_METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'complex128 (f64)', 'data': 'synthetic',
+            'config': {'workload': f'c4: 16x16 CMUT array refn={refn} (N={N}, T={T}), P={P} right-hand sides per frequency, '
+                                   f'ACA H-matrix ({C4_H}) + batched GMRES ({C4_SOLVE}), one frequency per step per GPU',
+                       'frequencies_hz_rank0': [float(v) for v in mine[args.warmup:nsteps]],
+                       'parallelism': f'freq-shard (cyclic) x{world}', 'setup_seconds_once': t_setup,
+                       'hmatrix': info, 'gmres_mean_iterations': its, 'rank_capped_leaves': int(capped),
+                       'cache': 'leaf data 4.4 GB >> 126 MB L2'},
+            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': 8, 'd2h_bytes_per_step': int(xp.nbytes + it2.nbytes + 8)},
+            'gpu_launches': int(launches), 'clocks': clocks,
+            'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': ach / fp64_peak,
+                         'traffic': measured_traffic('hmv_batched'),
+                         'kernel': f'batched H-matvec ({nb} vectors: k_hmv_tstack + k_hmv_gemm on DMMA, 3M product: '
+                                   f'6 x stored entries x vectors executed flops), {mv_s * 1e3:.2f} ms per call, timed alone '
+                                   'with CUDA events after the timed region',
+                         'peak_source': 'FP64 FMA-pipe peak measured live (cnld_b200_bench_dfma)',
+                         'single_vector': {'bound': 'hbm', 'achieved': 16.0 * info['stored'] / mv1_s / 1e9, 'peak': hbm[0],
+                                           'unit': 'GB/s', 'frac': 16.0 * info['stored'] / mv1_s / 1e9 / hbm[0],
+                                           'peak_source': hbm[1], 'seconds': mv1_s}},
+            'parity': {'config': 'c4', 'frequency_hz': f_last, 'matvec_sampled_rows_rel_err_vs_exact': row_err,
+                       'tolerance': C4_SOLVE['eps_aca'], 'gmres_all_converged': True,
+                       'note': 'solution-level parity of the H path against the dense LU path: tests/test_gpu_fullsize.py'},
+        }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import pyoracle as po
+        po.build()
+        am = po.array_mesh(po.matrix_array(nelem=nelem), refn)
+        _, line['cpu_baseline'] = _c4_cpu_line(po, am, mine[args.warmup:args.warmup + 1], P, float(np.mean(its)))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    H.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    if line is not None and not line['parity']['matvec_sampled_rows_rel_err_vs_exact'] < C4_SOLVE['eps_aca']:
+        raise SystemExit('bench.py: c4 H-matvec differs from exactly integrated rows by more than eps_aca')
+
+
+def MEASURED_HBM():
+    """(GB/s, source) of the HBM roofline denominator: MEASURED_PEAKS.json if present, else the profiling guide's fallback."""
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md: 6.65 TB/s, an earlier measurement on this pool)'
 
 
 def main():

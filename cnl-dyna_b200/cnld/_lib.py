@@ -84,7 +84,9 @@ def lib():
         L.cnld_b200_hmat_tree.argtypes = [vp] * 12
         L.cnld_b200_hmat_assemble.argtypes = [vp, f64, f64, f64]
         L.cnld_b200_hmat_matvec.argtypes = [vp, cfield, vp, vp, u32]
+        L.cnld_b200_hmat_capped.argtypes = [vp, vp, vp]
         L.cnld_b200_hmat_todense.argtypes = [vp, vp, u32]
+        L.cnld_b200_hmat_bench_matvec.argtypes = [vp, u32, C.c_int, vp]
         L.cnld_b200_hsweep_run.argtypes = [vp, vp, vp, u32, f64, f64, f64, f64, u32, u32, u32, vp, vp, vp, vp]
         L.cnld_b200_bench_zgemm.argtypes = [C.c_int, u32, u32, u32, C.c_int, vp]
         L.cnld_b200_bench_dfma.argtypes = [C.c_int, C.c_int, vp]
@@ -400,6 +402,20 @@ class HMatrix:
     def assemble(self, k, eps_aca=1e-2):
         k = complex(k)
         check(lib().cnld_b200_hmat_assemble(self._h, k.real, k.imag, float(eps_aca)))
+        self._warn_capped(self.capped()[0])
+
+    def capped(self):
+        """(rank-capped low-rank leaves of the last assemble, summed over the last sweep)."""
+        a, b = C.c_uint(0), C.c_uint(0)
+        check(lib().cnld_b200_hmat_capped(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    @staticmethod
+    def _warn_capped(count):
+        if count:
+            import warnings
+            warnings.warn(f'H-matrix: ACA stopped at the rank capacity kmax in {count} low-rank leaves before reaching '
+                          'eps_aca; the approximation is less accurate than requested -- raise kmax', RuntimeWarning)
 
     def matvec(self, x, alpha=1.0):
         """alpha * Z @ x for x[n] or x[n, nrhs]."""
@@ -410,6 +426,12 @@ class HMatrix:
         check(lib().cnld_b200_hmat_matvec(self._h, cfield(a.real, a.imag), ptr(X), ptr(Y), X.shape[0]))
         return Y.T.reshape(x.shape)
 
+    def bench_matvec(self, nrhs, reps=5):
+        """Device-resident seconds per matvec with nrhs vectors."""
+        out = C.c_double(0)
+        check(lib().cnld_b200_hmat_bench_matvec(self._h, int(nrhs), int(reps), C.byref(out)))
+        return out.value
+
     def todense(self):
         n = self.ctx.nv
         buf = np.zeros((n, n), dtype=np.complex128)
@@ -417,16 +439,23 @@ class HMatrix:
         return buf.T
 
     def sweep(self, freqs, c=1500., rho=1000., eps_aca=1e-2, tol=1e-6, restart=50, maxiter=500, batch=32,
-              want_nodes=True):
-        """H-matrix + GMRES sweep -> x_patch[nf, P, P], x_node[nf, P, N] | None, iters[nf, P], t[nf]."""
+              want_nodes=True, allow_unconverged=False):
+        """H-matrix + GMRES sweep -> x_patch[nf, P, P], x_node[nf, P, N] | None, iters[nf, P], t[nf].
+        Raises if a right-hand side misses `tol` within `maxiter` steps (unless allow_unconverged)."""
         freqs = _c(freqs, np.float64)
         nf, P, n = len(freqs), self.ctx.npatch, self.ctx.nv
         xp = np.zeros((nf, P, P), dtype=np.complex128)
         xn = np.zeros((nf, P, n), dtype=np.complex128) if want_nodes else None
         it = np.zeros((nf, P), dtype=np.uint32)
         t = np.zeros(nf)
-        check(lib().cnld_b200_hsweep_run(self.ctx._h, self._h, ptr(freqs), nf, c, rho, eps_aca, tol, restart, maxiter,
-                                         batch, ptr(xp), ptr(xn), ptr(it), ptr(t)))
+        rc = lib().cnld_b200_hsweep_run(self.ctx._h, self._h, ptr(freqs), nf, c, rho, eps_aca, tol, restart, maxiter,
+                                        batch, ptr(xp), ptr(xn), ptr(it), ptr(t))
+        if rc == 2 and allow_unconverged:
+            import warnings
+            warnings.warn(lib().cnld_b200_last_error().decode(), RuntimeWarning)
+        else:
+            check(rc)
+        self._warn_capped(self.capped()[1])
         return xp, xn, it, t
 
 

@@ -18,6 +18,7 @@
 struct cnld_hmat {
   cnld_ctx *ctx = nullptr;
   HMat H;
+  unsigned last_capped = 0;   // rank-capped leaves summed over the assemblies of the last hsweep_run
 };
 
 namespace cnld_hapi {
@@ -25,25 +26,33 @@ typedef std::complex<double> zc;
 constexpr double H_TWO_PI = 6.283185307179586476925286766559;
 
 // ---- batched vector kernels; vectors are [r][n] with stride n --------------------------------
-__global__ void k_spmv_mbk(uint n, uint nb, const int64_t *__restrict__ indptr, const uint *__restrict__ indices,
-                           const double *__restrict__ K, const double *__restrict__ M, const double *__restrict__ B,
-                           double omega, const cplx *__restrict__ X, cplx *Y) {
-  // Y[r][i] = sum_j (K - w^2 M - j w B)[i,j] X[r][j]; one warp per (row, rhs)
-  const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint lane = threadIdx.x & 31;
-  if (w >= (size_t)n * nb) return;
-  const uint r = w / n, i = w % n;
+// Y[r][i] = sum_j (K - w^2 M - j w B)[i,j] X[r][j]: the sparse FEM operator (about 20 entries per row)
+// applied to all right-hand sides.  Thread = (row, chunk of RC right-hand sides): the row's pattern and
+// values are read once per chunk; consecutive threads take consecutive rows, so the gathers of one
+// right-hand side fall into neighbouring sectors.
+template <int RC>
+__global__ void __launch_bounds__(256)
+k_spmm_mbk(uint n, uint nb, const int64_t *__restrict__ indptr, const uint *__restrict__ indices,
+           const double *__restrict__ K, const double *__restrict__ M, const double *__restrict__ B,
+           double omega, const cplx *__restrict__ X, cplx *Y) {
+  const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint nch = (nb + RC - 1) / RC;
+  if (id >= (size_t)n * nch) return;
+  const uint i = id % n, r0 = (uint)(id / n) * RC;
   const double w2 = omega * omega;
-  cplx s = make_double2(0.0, 0.0);
-  for (int64_t p = indptr[i] + lane; p < indptr[i + 1]; p += 32) {
-    cplx a = make_double2(K[p] - w2 * M[p], -omega * B[p]);
-    cfma(s, a, X[(size_t)r * n + indices[p]]);
+  cplx acc[RC];
+#pragma unroll
+  for (int q = 0; q < RC; q++) acc[q] = make_double2(0.0, 0.0);
+  for (int64_t p = indptr[i]; p < indptr[i + 1]; p++) {
+    const cplx a = make_double2(K[p] - w2 * M[p], -omega * B[p]);
+    const cplx *x = X + (size_t)r0 * n + indices[p];
+#pragma unroll
+    for (int q = 0; q < RC; q++)
+      if (r0 + q < nb) cfma(acc[q], a, x[(size_t)q * n]);
   }
-  for (int off = 16; off > 0; off >>= 1) {
-    s.x += __shfl_xor_sync(0xffffffffu, s.x, off);
-    s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
-  }
-  if (lane == 0) Y[(size_t)r * n + i] = s;
+#pragma unroll
+  for (int q = 0; q < RC; q++)
+    if (r0 + q < nb) Y[(size_t)(r0 + q) * n + i] = acc[q];
 }
 
 __global__ void k_block_dense(uint nb_, uint r0, const int64_t *__restrict__ indptr, const uint *__restrict__ indices,
@@ -147,6 +156,23 @@ k_epilogue_batch(uint nv, uint P, uint s0, cplx *X, const uint8_t *__restrict__ 
   }
 }
 
+// device buffer released on every exit path
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  int alloc(size_t count) {
+    if (cudaMalloc(&p, sizeof(T) * (count ? count : 1)) != cudaSuccess) {
+      p = nullptr;
+      set_error("out of device memory (%zu bytes)", sizeof(T) * count);
+      cudaGetLastError();
+      return -1;
+    }
+    return 0;
+  }
+  T *release() { T *q = p; p = nullptr; return q; }
+};
+
 struct Blocks {  // diagonal blocks of the FEM operator and their types (identical membranes share one)
   std::vector<uint> r0, sz, type;
   std::vector<uint> rep;  // representative block of each type
@@ -205,7 +231,6 @@ struct Gmres {
   int fluid_precond = 1;   // add the membrane's own block of coef * Z to the block-Jacobi preconditioner
   Blocks blk;
   std::vector<cplx *> d_inv;  // per block type: dense inverse
-  std::vector<cplx *> d_blk;  // per block type: the dense block K - w^2 M - j w B itself
   cplx *Vb = nullptr, *W = nullptr, *T = nullptr, *X = nullptr, *Bp = nullptr, *Hd = nullptr, *yd = nullptr;
   double *sd = nullptr;
 
@@ -222,13 +247,13 @@ struct Gmres {
     return 0;
   }
   int apply_G(const cplx *x, cplx *y, uint nr) {  // y = MBK x + coef Z x
-    if (blk.exact) {   // the FEM operator is its block diagonal: dense blocks on the tensor pipe
-      if (apply_blockdiag(d_blk, x, y, nr)) return -1;
-    } else {
-      k_spmv_mbk<<<(unsigned)(((size_t)n * nr * 32 + 255) / 256), 256, 0, st>>>(n, nr, c->d_indptr, c->d_indices, c->d_K,
-                                                                              c->d_M, c->d_B, omega, x, y);
-      CNLD_CK_LAUNCH();
-    }
+    // the FEM operator as the sparse matrix it is (round 1 applied it as one dense 761 x 761 block per
+    // membrane: 38 times its flops)
+    constexpr int RC = 8;
+    const size_t work = (size_t)n * ((nr + RC - 1) / RC);
+    k_spmm_mbk<RC><<<(unsigned)((work + 255) / 256), 256, 0, st>>>(n, nr, c->d_indptr, c->d_indices, c->d_K, c->d_M, c->d_B,
+                                                                  omega, x, y);
+    CNLD_CK_LAUNCH();
     if (coef != 0.0 && hmat_matvec(st, *H, make_double2(coef, 0.0), x, y, nr)) return -1;
     return 0;
   }
@@ -239,41 +264,33 @@ struct Gmres {
     for (uint t = 0; t < blk.rep.size(); t++) {
       const uint b = blk.rep[t], sz = blk.sz[b];
       if (sz > 8192) { set_error("FEM diagonal block of %u DOFs is too large for the block preconditioner", sz); return -1; }
-      cplx *D = nullptr, *I = nullptr;
-      CNLD_CK(cudaMalloc(&D, sizeof(cplx) * (size_t)sz * sz));
-      CNLD_CK(cudaMalloc(&I, sizeof(cplx) * (size_t)sz * sz));
-      CNLD_CK(cudaMemsetAsync(D, 0, sizeof(cplx) * (size_t)sz * sz, st));
-      k_block_dense<<<sz, 128, 0, st>>>(sz, blk.r0[b], c->d_indptr, c->d_indices, c->d_K, c->d_M, c->d_B, omega, D);
+      DevBuf<cplx> D, I;
+      if (D.alloc((size_t)sz * sz) || I.alloc((size_t)sz * sz)) return -1;
+      CNLD_CK(cudaMemsetAsync(D.p, 0, sizeof(cplx) * (size_t)sz * sz, st));
+      k_block_dense<<<sz, 128, 0, st>>>(sz, blk.r0[b], c->d_indptr, c->d_indices, c->d_K, c->d_M, c->d_B, omega, D.p);
       CNLD_CK_LAUNCH();
-      k_identity<<<(unsigned)(((size_t)sz * sz + 255) / 256), 256, 0, st>>>(sz, I);
+      k_identity<<<(unsigned)(((size_t)sz * sz + 255) / 256), 256, 0, st>>>(sz, I.p);
       CNLD_CK_LAUNCH();
       if (fluid_precond && coef != 0.0) {
         // self-radiation of the block: its own dense block of Z (exact near-field quadrature), so the
         // preconditioner is (MBK + coef Z)_block^-1 -- the fluid loading a membrane puts on itself is
         // the largest part of coef Z and costs one sz x sz assembly per block type and frequency
-        cplx *Zb = nullptr;
-        CNLD_CK(cudaMalloc(&Zb, sizeof(cplx) * (size_t)sz * sz));
+        DevBuf<cplx> Zb;
+        if (Zb.alloc((size_t)sz * sz)) return -1;
         std::vector<uint> idx(sz);
         for (uint i = 0; i < sz; i++) idx[i] = blk.r0[b] + i;
-        if (nearfield_block(st, c->bem, c->h_t.data(), idx.data(), sz, idx.data(), sz, kwave, 0.0, Zb)) { cudaFree(Zb); return -1; }
-        k_axpy_scaled<<<(unsigned)(((size_t)sz * sz + 255) / 256), 256, 0, st>>>((size_t)sz * sz, coef, Zb, D);
+        if (nearfield_block(st, c->bem, c->h_t.data(), idx.data(), sz, idx.data(), sz, kwave, 0.0, Zb.p)) return -1;
+        k_axpy_scaled<<<(unsigned)(((size_t)sz * sz + 255) / 256), 256, 0, st>>>((size_t)sz * sz, coef, Zb.p, D.p);
         CNLD_CK_LAUNCH();
         CNLD_CK(cudaStreamSynchronize(st));
-        cudaFree(Zb);
       }
       LuWork w;
-      if (lu_work_alloc(w, sz) || lu_factor(st, w, D, sz) || lu_solve(st, w, D, sz, I, sz, sz)) return -1;
-      // keep an unfactored copy of the block for apply_G
-      cplx *Dc = nullptr;
-      CNLD_CK(cudaMalloc(&Dc, sizeof(cplx) * (size_t)sz * sz));
-      CNLD_CK(cudaMemsetAsync(Dc, 0, sizeof(cplx) * (size_t)sz * sz, st));
-      k_block_dense<<<sz, 128, 0, st>>>(sz, blk.r0[b], c->d_indptr, c->d_indices, c->d_K, c->d_M, c->d_B, omega, Dc);
-      CNLD_CK_LAUNCH();
-      CNLD_CK(cudaStreamSynchronize(st));
+      const int lrc = (lu_work_alloc(w, sz) || lu_factor(st, w, D.p, sz) || lu_solve(st, w, D.p, sz, I.p, sz, sz)) ? -1 : 0;
+      cudaStreamSynchronize(st);
       lu_work_free(w);
-      cudaFree(D);
-      if (t < d_inv.size()) { cudaFree(d_inv[t]); d_inv[t] = I; } else d_inv.push_back(I);
-      if (t < d_blk.size()) { cudaFree(d_blk[t]); d_blk[t] = Dc; } else d_blk.push_back(Dc);
+      if (lrc) return -1;
+      cplx *Iq = I.release();
+      if (t < d_inv.size()) { cudaFree(d_inv[t]); d_inv[t] = Iq; } else d_inv.push_back(Iq);
     }
     return 0;
   }
@@ -293,8 +310,6 @@ struct Gmres {
     cudaFree(Vb); cudaFree(W); cudaFree(T); cudaFree(X); cudaFree(Bp); cudaFree(Hd); cudaFree(yd); cudaFree(sd);
     for (auto p : d_inv) cudaFree(p);
     d_inv.clear();
-    for (auto p : d_blk) cudaFree(p);
-    d_blk.clear();
   }
 
   // Solve P G X = P B for nr right-hand sides held in B (device, [r][n]); result in X.
@@ -417,8 +432,25 @@ struct Gmres {
       CNLD_CK(cudaStreamSynchronize(st));
     }
     if (iters) for (uint r = 0; r < nr; r++) iters[r] = it[r];
+    // Right-hand sides that ran out of iterations: measure the true preconditioned residual of what is
+    // returned, so the caller gets a status instead of a silently unconverged solution (the reference's
+    // lu() raises on a failed factorisation, compressed_formats.py:247-252).
+    bool pending = false;
+    for (uint r = 0; r < nr; r++) pending |= !done[r];
+    if (pending) {
+      if (apply_G(X, T, nr) || apply_P(T, W, nr)) return -1;
+      k_sub<<<gv, 256, 0, st>>>(v, Bp, W, W);
+      CNLD_CK_LAUNCH();
+      if (norms(W, resid)) return -1;
+      for (uint r = 0; r < nr; r++) {
+        const double rel = bnorm[r] > 0.0 ? resid[r] / bnorm[r] : 0.0;
+        if (!done[r] && rel > tol) { unconverged++; worst = std::max(worst, rel); }
+      }
+    }
     return 0;
   }
+  unsigned unconverged = 0;   // right-hand sides above the tolerance after maxiter steps (whole sweep)
+  double worst = 0.0;         // their largest relative residual
 };
 }  // namespace cnld_hapi
 using namespace cnld_hapi;
@@ -516,6 +548,45 @@ int cnld_b200_hmat_matvec(cnld_hmat *h, cnld_field alpha, const cnld_field *x, c
   return rc;
 }
 
+// device-resident timing of the matvec (seconds per call, CUDA events on the launch stream, after one
+// untimed call); the vectors hold a fixed pseudo-random pattern
+int cnld_b200_hmat_bench_matvec(cnld_hmat *h, cnld_uint nrhs, int reps, double *seconds) {
+  if (!h || !seconds || !nrhs || reps < 1) { set_error("bench_matvec: bad arguments"); return -1; }
+  CNLD_CK(cudaSetDevice(h->ctx->bem.device));
+  const size_t tot = (size_t)h->H.n * nrhs;
+  std::vector<cplx> hx(tot);
+  unsigned long long sd = 88172645463325252ull;
+  for (size_t i = 0; i < tot; i++) {
+    sd ^= sd << 13; sd ^= sd >> 7; sd ^= sd << 17;
+    hx[i] = make_double2((double)(sd & 0xffff) / 65536.0 - 0.5, (double)((sd >> 16) & 0xffff) / 65536.0 - 0.5);
+  }
+  cplx *dx = nullptr, *dy = nullptr;
+  CNLD_CK(cudaMalloc(&dx, sizeof(cplx) * tot));
+  CNLD_CK(cudaMalloc(&dy, sizeof(cplx) * tot));
+  cudaEvent_t e0, e1;
+  CNLD_CK(cudaEventCreate(&e0));
+  CNLD_CK(cudaEventCreate(&e1));
+  int rc = -1;
+  do {
+    if (cudaMemcpy(dx, hx.data(), sizeof(cplx) * tot, cudaMemcpyHostToDevice) != cudaSuccess) break;
+    if (cudaMemset(dy, 0, sizeof(cplx) * tot) != cudaSuccess) break;
+    if (hmat_matvec(0, h->H, make_double2(1.0, 0.0), dx, dy, nrhs)) break;
+    cudaEventRecord(e0, 0);
+    bool ok = true;
+    for (int r = 0; r < reps && ok; r++) ok = hmat_matvec(0, h->H, make_double2(1.0, 0.0), dx, dy, nrhs) == 0;
+    cudaEventRecord(e1, 0);
+    if (!ok || cudaEventSynchronize(e1) != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *seconds = ms * 1e-3 / reps;
+    rc = 0;
+  } while (0);
+  if (rc) set_error("bench_matvec: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(dx); cudaFree(dy);
+  return rc;
+}
+
 int cnld_b200_hmat_todense(cnld_hmat *h, cnld_field *Z, cnld_uint ld) {
   if (!h) { set_error("null H-matrix"); return -1; }
   CNLD_CK(cudaSetDevice(h->ctx->bem.device));
@@ -539,50 +610,72 @@ int cnld_b200_hsweep_run(cnld_ctx *c, cnld_hmat *h, const double *freqs, cnld_ui
   if (!c->d_indptr || !c->d_f_indptr) { set_error("cnld_b200_set_mbk / set_loads have not been called"); return -1; }
   CNLD_CK(cudaSetDevice(c->bem.device));
   const uint n = c->bem.nv, P = c->P;
-  Gmres G;
+  struct GmresGuard {
+    Gmres G;
+    ~GmresGuard() { G.release(); }
+  } guard;
+  Gmres &G = guard.G;
   G.c = c; G.H = &h->H; G.st = 0; G.n = n;
   G.nb = std::min(batch ? batch : 32u, P);
   G.restart = restart ? restart : 50;
   detect_blocks(c, G.blk);
   if (G.alloc()) return -1;
-  cplx *dB = nullptr, *dxp = nullptr;
-  CNLD_CK(cudaMalloc(&dB, sizeof(cplx) * (size_t)n * G.nb));
-  CNLD_CK(cudaMalloc(&dxp, sizeof(cplx) * (size_t)P * P));
-  cudaEvent_t e0, e1;
-  CNLD_CK(cudaEventCreate(&e0));
-  CNLD_CK(cudaEventCreate(&e1));
+  DevBuf<cplx> dB, dxp;
+  if (dB.alloc((size_t)n * G.nb) || dxp.alloc((size_t)P * P)) return -1;
+  struct Events {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Events() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+  } ev;
+  CNLD_CK(cudaEventCreate(&ev.e0));
+  CNLD_CK(cudaEventCreate(&ev.e1));
   int rc = 0;
+  h->last_capped = 0;
   for (uint i = 0; i < nf && !rc; i++) {
     const double f = freqs[i], omega = H_TWO_PI * f;
     G.omega = omega;
     G.coef = -omega * omega * 2.0 * rho;
     G.kwave = omega / cs;
     G.fluid_precond = g_hsweep_fluid_precond;
-    cudaEventRecord(e0, 0);
-    if (f != 0.0 && hmat_assemble(0, h->H, omega / cs, 0.0, eps_aca)) { rc = -1; break; }
+    cudaEventRecord(ev.e0, 0);
+    if (f != 0.0) {
+      if (hmat_assemble(0, h->H, omega / cs, 0.0, eps_aca)) { rc = -1; break; }
+      h->last_capped += h->H.capped_leaves;
+    }
     if (G.setup_precond()) { rc = -1; break; }
     for (uint s0 = 0; s0 < P && !rc; s0 += G.nb) {
       const uint nr = std::min(G.nb, P - s0);
-      cudaMemsetAsync(dB, 0, sizeof(cplx) * (size_t)n * nr, 0);
-      k_rhs_batch<<<nr, 128>>>(n, s0, c->d_f_indptr, c->d_f_idx, c->d_f_val, dB);
+      cudaMemsetAsync(dB.p, 0, sizeof(cplx) * (size_t)n * nr, 0);
+      k_rhs_batch<<<nr, 128>>>(n, s0, c->d_f_indptr, c->d_f_idx, c->d_f_val, dB.p);
       cnld::count_launch();
-      if (G.solve(dB, nr, tol, maxiter ? maxiter : 500, iters ? iters + (size_t)i * P + s0 : nullptr)) { rc = -1; break; }
-      k_epilogue_batch<<<nr, 256>>>(n, P, s0, G.X, c->d_ob, c->d_a_indptr, c->d_a_idx, c->d_a_val, dxp);
+      if (G.solve(dB.p, nr, tol, maxiter ? maxiter : 500, iters ? iters + (size_t)i * P + s0 : nullptr)) { rc = -1; break; }
+      k_epilogue_batch<<<nr, 256>>>(n, P, s0, G.X, c->d_ob, c->d_a_indptr, c->d_a_idx, c->d_a_val, dxp.p);
       cnld::count_launch();
       if (x_node && cudaMemcpy(reinterpret_cast<cplx *>(x_node) + ((size_t)i * P + s0) * n, G.X, sizeof(cplx) * (size_t)n * nr,
                                cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); rc = -1; }
     }
-    cudaEventRecord(e1, 0);
-    if (cudaMemcpy(reinterpret_cast<cplx *>(x_patch) + (size_t)i * P * P, dxp, sizeof(cplx) * (size_t)P * P,
-                   cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); rc = -1; }
+    cudaEventRecord(ev.e1, 0);
+    if (x_patch && cudaMemcpy(reinterpret_cast<cplx *>(x_patch) + (size_t)i * P * P, dxp.p, sizeof(cplx) * (size_t)P * P,
+                              cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("D2H failed"); rc = -1; }
+    if (cudaEventSynchronize(ev.e1) != cudaSuccess) { set_error("hsweep: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventElapsedTime(&ms, ev.e0, ev.e1);
     if (t_freq) t_freq[i] = ms * 1e-3;
   }
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(dB); cudaFree(dxp);
-  G.release();
-  return rc;
+  if (rc) { cudaDeviceSynchronize(); return rc; }
+  if (G.unconverged) {
+    // results are in the output buffers; the caller decides (rc 2 = "not converged", not a CUDA failure)
+    set_error("GMRES: %u right-hand side(s) did not reach tol %.1e within %u iterations (largest relative residual %.2e)",
+              G.unconverged, tol, maxiter ? maxiter : 500u, G.worst);
+    return 2;
+  }
+  return 0;
+}
+
+int cnld_b200_hmat_capped(cnld_hmat *h, unsigned *last_assembly, unsigned *last_sweep) {
+  if (!h) { set_error("null H-matrix"); return -1; }
+  if (last_assembly) *last_assembly = h->H.capped_leaves;
+  if (last_sweep) *last_sweep = h->last_capped;
+  return 0;
 }
 
 }  // extern "C"

@@ -23,6 +23,7 @@ struct HMat {
   std::vector<HLeafDev> leaf;
   size_t pool_size = 0, near_entries = 0;
   bool assembled = false;
+  uint capped_leaves = 0;   // low-rank leaves of the last assembly whose ACA stopped at the rank capacity, eps_aca not met
   HLeafDev *d_leaf = nullptr;
   uint *d_near = nullptr, *d_far = nullptr, *d_perm = nullptr, *d_pos = nullptr, *d_cpos = nullptr;
   uint *d_ctri_ptr = nullptr, *d_ctri = nullptr, *d_v2t_ptr = nullptr, *d_v2t = nullptr;
@@ -44,7 +45,17 @@ struct HMat {
   FarItem *d_bfar = nullptr;
   size_t bfar_cap = 0;
   unsigned long long *d_toff = nullptr;   // per leaf: offset (in rank indices) into the scratch
-  unsigned long long ksum = 0;
+  unsigned long long ksum = 0;            // rows of the scratch (rank indices, padded per column cluster to 16)
+  // stacked t-pass: the low-rank leaves of one column cluster contract the same x|cols, so their rank
+  // indices are laid out consecutively in the scratch (padded to a multiple of 16 per column cluster) and
+  // a CTA owns a band of 16 scratch rows: t|band = [V_1 .. V_q]^T|band x|cols -- full 16-row DMMA tiles
+  // instead of one CTA per leaf with k (3..10) useful rows
+  struct TBand { uint c0, n, rows, pad; };
+  TBand *d_tband = nullptr;
+  unsigned long long *d_vrow = nullptr;   // per scratch row: pool offset of its V column (~0: padding row)
+  size_t tband_cap = 0, vrow_cap = 0;
+  uint ntband = 0;
+  std::vector<uint> far_by_col;           // low-rank leaf ids sorted by column cluster (structure, built once)
   cplx *d_T = nullptr;
   size_t T_cap = 0;
   bool mv_ready = false;

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(ACA_THREADS)
 k_aca(HLeafDev *leaves, const uint *__restrict__ far_ids, const __grid_constant__ RegRule R,
       const double *__restrict__ qp, const double *__restrict__ g, const uint *__restrict__ perm,
       const uint *__restrict__ v2t_ptr, const uint *__restrict__ v2t, double kr, double ki, double accur,
-      cplx *pool, unsigned char *flags) {
+      cplx *pool, unsigned char *flags, uint *capped) {
   __shared__ double s_val[ACA_THREADS / 32];
   __shared__ uint s_idx[ACA_THREADS / 32];
   const uint lid = far_ids[blockIdx.x];
@@ -209,6 +209,7 @@ k_aca(HLeafDev *leaves, const uint *__restrict__ far_ids, const __grid_constant_
   __syncthreads();
   uint k = 0, ik = 0;
   double start = 0.0;
+  bool met = false;   // the loop ended because the accuracy was reached or the block was exhausted
   while (k < kcap) {
     // residual row ik -> V[:, k]
     const uint vi = ridx[ik];
@@ -231,7 +232,7 @@ k_aca(HLeafDev *leaves, const uint *__restrict__ far_ids, const __grid_constant_
         if (!rused[i] && i < nx) { nx = i; nb = 1.0; }
       // argmax breaks ties towards the smaller index -> picks the smallest unused row
       block_argmax(nb, nx, s_val, s_idx);
-      if (!(nb > 0.0)) break;
+      if (!(nb > 0.0)) { met = true; break; }
       ik = nx;
       continue;
     }
@@ -265,12 +266,17 @@ k_aca(HLeafDev *leaves, const uint *__restrict__ far_ids, const __grid_constant_
     const double e = sqrt(nu2) * sqrt(nv2);
     if (k == 0) start = e;
     k++;
-    if (e <= accur * start) break;
-    if (bi == 0xffffffffu) break;
+    if (e <= accur * start) { met = true; break; }
+    if (bi == 0xffffffffu) { met = true; break; }
     ik = bi;
   }
   __syncthreads();
-  if (threadIdx.x == 0) leaves[lid].k = k;
+  if (threadIdx.x == 0) {
+    leaves[lid].k = k;
+    // rank capacity reached before eps_aca was: H2Lib's ACA would have kept growing the rank.  A full-rank
+    // factorisation (k == min(m, n)) is exact, not capped.
+    if (!met && k == kcap && kcap < min(m, n)) atomicAdd(capped, 1u);
+  }
 }
 
 // ---- matvec: y_perm += alpha * Z * x_perm over the leaves --------------------------------
@@ -495,6 +501,102 @@ k_hmv_gemm(const uint *__restrict__ band_ptr, const HMat::DRound *__restrict__ d
           }
         }
   }
+}
+
+
+// ---- stacked t-pass -----------------------------------------------------------------------------
+// CTA = band of 16 rows of the scratch (consecutive rank indices of the low-rank leaves of ONE column
+// cluster), NW warps x TC n-tiles of 8 right-hand sides per pass.  Round = 16 columns of the cluster.
+// All (pass, round) pairs form one software pipeline (the next pair's operands are in flight while the
+// current one is contracted), so column clusters of 16..32 columns -- most of them -- do not drain it
+// after every pass.  No descriptors are read inside the loop: a row's operand address is its V column
+// plus the column index.
+constexpr int TS_LDA = 20;   // As[row][col]: conflict-free for the cp.async writes and the fragment loads
+template <int NW, int TC>
+__global__ void __launch_bounds__(32 * NW)
+k_hmv_tstack(const HMat::TBand *__restrict__ tband, const unsigned long long *__restrict__ vrow,
+             const cplx *__restrict__ pool, cplx *T, const cplx *__restrict__ xp, uint nrhs) {
+  constexpr int NT = 32 * NW, RP = 8 * TC * NW, XS_LD = RP + 2;
+  extern __shared__ __align__(16) unsigned char ts_smem[];
+  cplx (*As)[16][TS_LDA] = reinterpret_cast<cplx (*)[16][TS_LDA]>(ts_smem);                                  // [buf][row][col]
+  cplx (*Xs)[16][XS_LD] = reinterpret_cast<cplx (*)[16][XS_LD]>(ts_smem + sizeof(cplx) * 2 * 16 * TS_LDA);   // [buf][col][rhs]
+  __shared__ unsigned long long s_row[16];
+  const uint tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint fr = lane >> 2, fc = lane & 3;
+  const HMat::TBand B = tband[blockIdx.x];
+  if (tid < 16) s_row[tid] = vrow[(size_t)blockIdx.x * 16 + tid];
+  __syncthreads();
+  const uint R = (B.n + 15) / 16, npass = (nrhs + RP - 1) / RP, total = R * npass;
+  const int nmi = B.rows <= 8 ? 1 : 2;
+  auto issue = [&](uint s) {
+    const uint c = s % R, r0 = (s / R) * RP, buf = s & 1, cnt = min(16u, B.n - c * 16);
+    for (uint e = tid; e < 256; e += NT) {
+      const uint j = e & 15, i = e >> 4;
+      const unsigned long long base = s_row[i];
+      const bool ok = j < cnt && base != ~0ull;
+      hm_cp_async16(&As[buf][i][j], ok ? pool + base + c * 16 + j : pool, ok);
+    }
+    for (uint e = tid; e < 16 * RP; e += NT) {
+      const uint r = e % RP, j = e / RP;
+      const bool ok = j < cnt && r0 + r < nrhs;
+      hm_cp_async16(&Xs[buf][j][r], ok ? xp + (size_t)(B.c0 + c * 16 + j) * nrhs + r0 + r : xp, ok);
+    }
+  };
+  double X[2][TC][2], Y[2][TC][2], W[2][TC][2];
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int q = 0; q < TC; q++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) X[a][q][e] = Y[a][q][e] = W[a][q][e] = 0.0;
+  issue(0);
+  asm volatile("cp.async.commit_group;\n" ::);
+  for (uint s = 0; s < total; s++) {
+    __syncthreads();   // pair s-1 is contracted: its buffers are free
+    if (s + 1 < total) issue(s + 1);
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 1;\n" ::);
+    __syncthreads();   // operands of pair s have landed
+    const uint c = s % R, buf = s & 1, jn = (min(16u, B.n - c * 16) + 3) / 4;
+    for (uint ks = 0; ks < jn; ks++) {
+      double are[2], aim[2], asu[2], bre[TC], bim[TC], bsu[TC];
+#pragma unroll
+      for (int mi = 0; mi < 2; mi++) {
+        const cplx v = As[buf][mi * 8 + fr][ks * 4 + fc];
+        are[mi] = v.x; aim[mi] = v.y; asu[mi] = v.x + v.y;
+      }
+#pragma unroll
+      for (int ni = 0; ni < TC; ni++) {
+        const cplx v = Xs[buf][ks * 4 + fc][(warp * TC + ni) * 8 + fr];
+        bre[ni] = v.x; bim[ni] = v.y; bsu[ni] = v.x + v.y;
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; mi++)
+        if (mi < nmi)
+#pragma unroll
+          for (int ni = 0; ni < TC; ni++) {
+            hm_dmma(X[mi][ni][0], X[mi][ni][1], are[mi], bre[ni]);
+            hm_dmma(Y[mi][ni][0], Y[mi][ni][1], aim[mi], bim[ni]);
+            hm_dmma(W[mi][ni][0], W[mi][ni][1], asu[mi], bsu[ni]);
+          }
+    }
+    if (c + 1 == R) {   // last round of this pass: write the band's t rows, restart the accumulators
+      const uint r0 = (s / R) * RP;
+#pragma unroll
+      for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+        for (int ni = 0; ni < TC; ni++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const uint i = mi * 8 + fr, r = r0 + (warp * TC + ni) * 8 + fc * 2 + e;
+            if (i < B.rows && r < nrhs)
+              T[((size_t)blockIdx.x * 16 + i) * nrhs + r] =
+                  make_double2(X[mi][ni][e] - Y[mi][ni][e], W[mi][ni][e] - X[mi][ni][e] - Y[mi][ni][e]);
+            X[mi][ni][e] = Y[mi][ni][e] = W[mi][ni][e] = 0.0;
+          }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
 // ---- matvec with 1-3 vectors: HBM-bound, so the kernels only have to read every leaf once, coalesced ----
@@ -756,7 +858,7 @@ int hmat_create_from_ranges(HMat &H, const BemDev &bem, const uint *htri, const 
     return -1;
   CNLD_CK(cudaMalloc(&H.d_pool, sizeof(cplx) * (off ? off : 1)));
   CNLD_CK(cudaMalloc(&H.d_flags, foff ? foff : 1));
-  CNLD_CK(cudaMalloc(&H.d_err, sizeof(uint)));
+  CNLD_CK(cudaMalloc(&H.d_err, 2 * sizeof(uint)));
   return 0;
 }
 
@@ -797,22 +899,64 @@ int hmat_prepare_batched(HMat &H, bool fetch) {
           rounds[fill[b]++] = {L.off + (size_t)j0 * L.m, L.r0, L.m, L.c0 + j0, std::min(16u, L.n - j0), {0, 0}};
     }
     H.nmvfar = (uint)mvfar.size();
+    H.far_by_col = mvfar;   // grouped by column cluster for the stacked t-pass
+    std::stable_sort(H.far_by_col.begin(), H.far_by_col.end(), [&](uint a, uint b) {
+      const HLeafDev &A = H.leaf[a], &B = H.leaf[b];
+      return A.c0 != B.c0 ? A.c0 < B.c0 : A.n < B.n;
+    });
     if (to_device(H.d_band_ptr, ptr) || to_device(H.d_dround, rounds) || to_device(H.d_mvfar, mvfar)) return -1;
     CNLD_CK(cudaMalloc(&H.d_toff, sizeof(unsigned long long) * (H.leaf.size() + 1)));
     CNLD_CK(cudaMalloc(&H.d_bfar_ptr, sizeof(uint) * (H.nband + 1)));
   }
-  // ranks: scratch offsets and the packed (leaf, rank index) items of every band
+  // ranks: scratch offsets and the packed (leaf, rank index) items of every band.  The scratch rows of
+  // the low-rank leaves of one column cluster are consecutive and padded to a multiple of 16 (stacked
+  // t-pass: one CTA per 16 scratch rows).
   std::vector<unsigned long long> toff(H.leaf.size() + 1, 0);
   std::vector<uint> fptr(H.nband + 1, 0);
+  std::vector<HMat::TBand> tbands;
+  std::vector<unsigned long long> vrow;
   unsigned long long sum = 0;
+  for (size_t q = 0; q < H.far_by_col.size();) {
+    const HLeafDev &L0 = H.leaf[H.far_by_col[q]];
+    const unsigned long long base = sum;
+    size_t e = q;
+    for (; e < H.far_by_col.size(); e++) {
+      const uint id = H.far_by_col[e];
+      const HLeafDev &L = H.leaf[id];
+      if (L.c0 != L0.c0 || L.n != L0.n) break;
+      toff[id] = sum;
+      const size_t voff = L.off + (size_t)L.m * L.kcap;
+      for (uint l = 0; l < L.k; l++) vrow.push_back(voff + (size_t)l * L.n);
+      sum += L.k;
+    }
+    const unsigned long long rows = sum - base;
+    for (unsigned long long r = 0; r < rows; r += 16)
+      tbands.push_back({L0.c0, L0.n, (uint)std::min<unsigned long long>(16, rows - r), 0});
+    sum = base + (rows + 15) / 16 * 16;
+    vrow.resize(sum, ~0ull);
+    q = e;
+  }
   for (size_t id = 0; id < H.leaf.size(); id++) {
     const HLeafDev &L = H.leaf[id];
-    toff[id] = sum;
     if (!L.adm || !L.m || !L.n) continue;
-    sum += L.k;
     for (uint b = L.r0 / BAND; b <= (L.r0 + L.m - 1) / BAND; b++) fptr[b + 1] += L.k;
   }
   H.ksum = sum;
+  H.ntband = (uint)tbands.size();
+  if (H.tband_cap < tbands.size()) {
+    cudaFree(H.d_tband);
+    H.d_tband = nullptr;
+    H.tband_cap = tbands.size() + tbands.size() / 4 + 16;
+    CNLD_CK(cudaMalloc(&H.d_tband, sizeof(HMat::TBand) * H.tband_cap));
+  }
+  if (H.vrow_cap < vrow.size()) {
+    cudaFree(H.d_vrow);
+    H.d_vrow = nullptr;
+    H.vrow_cap = vrow.size() + vrow.size() / 4 + 16;
+    CNLD_CK(cudaMalloc(&H.d_vrow, sizeof(unsigned long long) * H.vrow_cap));
+  }
+  CNLD_CK(cudaMemcpy(H.d_tband, tbands.data(), sizeof(HMat::TBand) * tbands.size(), cudaMemcpyHostToDevice));
+  CNLD_CK(cudaMemcpy(H.d_vrow, vrow.data(), sizeof(unsigned long long) * vrow.size(), cudaMemcpyHostToDevice));
   for (uint b = 0; b < H.nband; b++) fptr[b + 1] += fptr[b];
   std::vector<HMat::FarItem> items(fptr[H.nband]);
   {
@@ -839,7 +983,7 @@ int hmat_prepare_batched(HMat &H, bool fetch) {
 
 void hmat_free(HMat &H) {
   cudaFree(H.d_band_ptr); cudaFree(H.d_dround); cudaFree(H.d_mvfar); cudaFree(H.d_toff); cudaFree(H.d_T);
-  cudaFree(H.d_bfar_ptr); cudaFree(H.d_bfar); cudaFree(H.d_dup);
+  cudaFree(H.d_bfar_ptr); cudaFree(H.d_bfar); cudaFree(H.d_dup); cudaFree(H.d_tband); cudaFree(H.d_vrow);
   cudaFree(H.d_leaf); cudaFree(H.d_near); cudaFree(H.d_far); cudaFree(H.d_perm); cudaFree(H.d_pos);
   cudaFree(H.d_ctri_ptr); cudaFree(H.d_ctri); cudaFree(H.d_v2t_ptr); cudaFree(H.d_v2t); cudaFree(H.d_pool);
   cudaFree(H.d_flags); cudaFree(H.d_err); cudaFree(H.d_xp); cudaFree(H.d_yp); cudaFree(H.d_cpos);
@@ -863,10 +1007,10 @@ static int assemble_nq(cudaStream_t st, HMat &H, double kr, double ki, double ac
   if (H.nfar) {
     if (ki != 0.0)
       k_aca<NQ, true><<<H.nfar, ACA_THREADS, 0, st>>>(H.d_leaf, H.d_far, b.rule, b.qp, b.g, H.d_perm, H.d_v2t_ptr,
-                                                       H.d_v2t, kr, ki, accur, H.d_pool, H.d_flags);
+                                                       H.d_v2t, kr, ki, accur, H.d_pool, H.d_flags, H.d_err + 1);
     else
       k_aca<NQ, false><<<H.nfar, ACA_THREADS, 0, st>>>(H.d_leaf, H.d_far, b.rule, b.qp, b.g, H.d_perm, H.d_v2t_ptr,
-                                                        H.d_v2t, kr, ki, accur, H.d_pool, H.d_flags);
+                                                        H.d_v2t, kr, ki, accur, H.d_pool, H.d_flags, H.d_err + 1);
     CNLD_CK_LAUNCH();
   }
   return 0;
@@ -874,7 +1018,7 @@ static int assemble_nq(cudaStream_t st, HMat &H, double kr, double ki, double ac
 
 int hmat_assemble(cudaStream_t st, HMat &H, double kr, double ki, double accur) {
   CNLD_CK(cudaMemsetAsync(H.d_pool, 0, sizeof(cplx) * H.pool_size, st));
-  CNLD_CK(cudaMemsetAsync(H.d_err, 0, sizeof(uint), st));
+  CNLD_CK(cudaMemsetAsync(H.d_err, 0, 2 * sizeof(uint), st));
   int rc;
   switch (H.bem->nq) {
   case 1: rc = assemble_nq<1>(st, H, kr, ki, accur); break;
@@ -887,14 +1031,18 @@ int hmat_assemble(cudaStream_t st, HMat &H, double kr, double ki, double accur) 
     k_copy_ranks<<<(H.ndup + 255) / 256, 256, 0, st>>>(H.ndup, H.d_dup, H.d_leaf);
     CNLD_CK_LAUNCH();
   }
-  uint err = 0;
-  CNLD_CK(cudaMemcpyAsync(&err, H.d_err, sizeof(uint), cudaMemcpyDeviceToHost, st));
+  uint errs[2] = {0, 0};
+  CNLD_CK(cudaMemcpyAsync(errs, H.d_err, 2 * sizeof(uint), cudaMemcpyDeviceToHost, st));
   CNLD_CK(cudaStreamSynchronize(st));
+  const uint err = errs[0];
+  H.capped_leaves = errs[1];
   if (err) { set_error("H-matrix near-field: touching-pair queue overflow (leaf too large; raise NEAR_QCAP)"); return -1; }
   H.assembled = true;
   H.mv_ready = false;   // ranks changed: the batched matvec refreshes its offsets on first use
   return 0;
 }
+
+int g_hmv_tstack = 1;
 
 // device vectors in ORIGINAL DOF order, nrhs of them with stride n:  y += alpha * Z x
 int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y, uint nrhs) {
@@ -923,7 +1071,37 @@ int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y
     }
     k_permute_in_t<<<gb, 256, 0, st>>>(H.n, nrhs, H.d_perm, d_x, H.d_xp);
     CNLD_CK_LAUNCH();
-    // right-hand sides per pass (16 * TC): the width that wastes the fewest columns, ties to the wider
+    // t-pass: right-hand sides per pass = 8 TC NW; the width that wastes the fewest columns, ties to the wider
+    if (!g_hmv_tstack && H.nmvfar) {   // debug: one CTA per low-rank leaf (round-1 kernel)
+      k_hmv_gemm<4, true><<<H.nmvfar, BT_THREADS, 0, st>>>(H.d_band_ptr, H.d_dround, H.d_bfar_ptr, H.d_bfar, H.d_mvfar,
+                                                           H.d_leaf, H.d_toff, H.d_pool, H.d_T, H.d_xp, H.d_yp, H.n, nrhs);
+      CNLD_CK_LAUNCH();
+    } else if (H.ntband) {
+      int bw = 2, bt = 2;
+      uint bestw = ~0u;
+      for (int w : {2, 4})
+        for (int c : {2, 3, 4}) {
+          const uint rp = 8 * c * w, waste = (nrhs + rp - 1) / rp * rp - nrhs;
+          if (waste < bestw || (waste == bestw && 8 * c * w > 8 * bt * bw)) { bestw = waste; bw = w; bt = c; }
+        }
+#define CNLD_TS(NWV, TCV)                                                                                          \
+  do {                                                                                                             \
+    constexpr int SM = (int)sizeof(cplx) * 2 * 16 * (TS_LDA + 8 * TCV * NWV + 2);                                  \
+    static bool attr[64] = {false};                                                                                \
+    int dev = 0;                                                                                                   \
+    CNLD_CK(cudaGetDevice(&dev));                                                                                  \
+    if (!attr[dev & 63]) {                                                                                         \
+      CNLD_CK(cudaFuncSetAttribute(k_hmv_tstack<NWV, TCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));      \
+      attr[dev & 63] = true;                                                                                       \
+    }                                                                                                              \
+    k_hmv_tstack<NWV, TCV><<<H.ntband, 32 * NWV, SM, st>>>(H.d_tband, H.d_vrow, H.d_pool, H.d_T, H.d_xp, nrhs);    \
+  } while (0)
+      if (bw == 2) { if (bt == 2) CNLD_TS(2, 2); else if (bt == 3) CNLD_TS(2, 3); else CNLD_TS(2, 4); }
+      else { if (bt == 2) CNLD_TS(4, 2); else if (bt == 3) CNLD_TS(4, 3); else CNLD_TS(4, 4); }
+#undef CNLD_TS
+      CNLD_CK_LAUNCH();
+    }
+    // y-pass: right-hand sides per pass (16 * TC)
     int tc = 2;
     uint best = ~0u;
     for (int c : {2, 3, 4}) {
@@ -931,15 +1109,8 @@ int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y
       if (waste <= best) { best = waste; tc = c; }
     }
 #define CNLD_HMV(TCV)                                                                                              \
-  do {                                                                                                             \
-    if (H.nmvfar) {                                                                                                \
-      k_hmv_gemm<TCV, true><<<H.nmvfar, BT_THREADS, 0, st>>>(H.d_band_ptr, H.d_dround, H.d_bfar_ptr, H.d_bfar,       \
-          H.d_mvfar, H.d_leaf, H.d_toff, H.d_pool, H.d_T, H.d_xp, H.d_yp, H.n, nrhs);                              \
-      CNLD_CK_LAUNCH();                                                                                            \
-    }                                                                                                              \
-    k_hmv_gemm<TCV, false><<<H.nband, BT_THREADS, 0, st>>>(H.d_band_ptr, H.d_dround, H.d_bfar_ptr, H.d_bfar,         \
-        H.d_mvfar, H.d_leaf, H.d_toff, H.d_pool, H.d_T, H.d_xp, H.d_yp, H.n, nrhs);                                \
-  } while (0)
+  k_hmv_gemm<TCV, false><<<H.nband, BT_THREADS, 0, st>>>(H.d_band_ptr, H.d_dround, H.d_bfar_ptr, H.d_bfar,           \
+      H.d_mvfar, H.d_leaf, H.d_toff, H.d_pool, H.d_T, H.d_xp, H.d_yp, H.n, nrhs)
     if (tc == 2) CNLD_HMV(2);
     else if (tc == 3) CNLD_HMV(3);
     else CNLD_HMV(4);
@@ -1059,7 +1230,7 @@ int nearfield_block(cudaStream_t st, const BemDev &bem, const uint *htri, const 
   if (to_device(H.d_leaf, H.leaf) || to_device(H.d_near, near_ids) || to_device(H.d_pos, rpos) || to_device(H.d_cpos, cpos) ||
       to_device(H.d_ctri_ptr, ctri_ptr) || to_device(H.d_ctri, ctri) || to_device(H.d_perm, perm)) rc = -1;
   if (!rc && cudaMalloc(&H.d_pool, sizeof(cplx) * (off ? off : 1)) != cudaSuccess) { set_error("nearfield: out of memory"); rc = -1; }
-  if (!rc && cudaMalloc(&H.d_err, sizeof(uint)) != cudaSuccess) { set_error("nearfield: out of memory"); rc = -1; }
+  if (!rc && cudaMalloc(&H.d_err, 2 * sizeof(uint)) != cudaSuccess) { set_error("nearfield: out of memory"); rc = -1; }
   if (!rc) rc = hmat_assemble(st, H, kr, ki, 0.0);
   if (!rc) {
     k_untile<<<(unsigned)H.leaf.size(), 256, 0, st>>>(H.d_leaf, H.d_pool, d_out, rows);

@@ -250,7 +250,13 @@ int cnld_b200_hmat_assemble(cnld_hmat *h, double k_re, double k_im, double eps_a
 /* y[r][:] += alpha * Z x[r][:] for nrhs host vectors of length n (original DOF order) */
 int cnld_b200_hmat_matvec(cnld_hmat *h, cnld_field alpha, const cnld_field *x, cnld_field *y,
                           cnld_uint nrhs);
+/* Low-rank leaves whose ACA stopped at the rank capacity kmax before reaching eps_aca (H2Lib's ACA keeps
+ * growing the rank): count of the last assemble call, and summed over the last hsweep_run.  Non-zero
+ * means the H-matrix is less accurate than eps_aca asks for -- raise kmax. */
+int cnld_b200_hmat_capped(cnld_hmat *h, unsigned *last_assembly, unsigned *last_sweep);
 int cnld_b200_hmat_todense(cnld_hmat *h, cnld_field *Z, cnld_uint ld);
+/* device-resident timing of the matvec with nrhs vectors: seconds per call (CUDA events) */
+int cnld_b200_hmat_bench_matvec(cnld_hmat *h, cnld_uint nrhs, int reps, double *seconds);
 /* generate_db.process with the H-matrix + GMRES path: per frequency assemble Z_H(k), then solve
  * (MBK + (-2 rho w^2) Z_H) x = F[:, s] for all source patches by left-preconditioned restarted
  * GMRES (block-diagonal MBK^-1), `batch` right-hand sides in lock-step; residual tolerance tol.
