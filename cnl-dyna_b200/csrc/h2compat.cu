@@ -13,6 +13,7 @@
 
 #include "../../include/cnld_b200.h"
 #include "common.cuh"
+#include "densedev.cuh"
 
 using cnld::set_error;
 
@@ -82,6 +83,7 @@ pamatrix new_zero_amatrix(uint rows, uint cols) {
 }
 void del_amatrix(pamatrix a) {
   if (!a) return;
+  cnld::dd::drop(a->a);
   if (!a->owner) free(a->a);
   free(a);
 }
@@ -92,26 +94,32 @@ pamatrix clone_amatrix(pcamatrix src) {
   return a;
 }
 void scale_amatrix(field alpha, pamatrix a) {
+  cnld::dd::drop(a->a);
   for (uint j = 0; j < a->cols; j++) {
     field *c = a->a + (size_t)j * a->ld;
     for (uint i = 0; i < a->rows; i++) c[i] = fmul(alpha, c[i]);
   }
 }
 void conjugate_amatrix(pamatrix a) {
+  cnld::dd::drop(a->a);
   for (uint j = 0; j < a->cols; j++) {
     field *c = a->a + (size_t)j * a->ld;
     for (uint i = 0; i < a->rows; i++) c[i].im = -c[i].im;
   }
 }
 void addeval_amatrix_avector(field alpha, pcamatrix a, pcavector src, pavector trg) {
+  // trg += alpha * A src on the GPU; the device copy of A is kept for the next call (densedev.cu)
   if (src->dim != a->cols || trg->dim != a->rows) { set_error("addeval_amatrix_avector: dimension mismatch"); die("addeval"); }
-  for (uint j = 0; j < a->cols; j++) {
-    field s = fmul(alpha, src->v[j]);
-    const field *c = a->a + (size_t)j * a->ld;
-    for (uint i = 0; i < a->rows; i++) trg->v[i] = fadd(trg->v[i], fmul(c[i], s));
-  }
+  cnld::dd::Resident *R = cnld::dd::resident(a->a, a->rows, a->cols, a->ld);
+  if (!R) die("addeval_amatrix_avector");
+  const cplx al = make_double2(alpha.re, alpha.im);
+  if (cnld::dd::with_vectors(src->dim, (const cplx *)src->v, trg->dim, (cplx *)trg->v, true, [&](const cplx *dx, cplx *dy) {
+        return cnld::dd::gemv(0, R->d, R->rows, R->rows, R->cols, cnld::dd::TRI_FULL, 0, al, dx, dy);
+      }))
+    die("addeval_amatrix_avector");
 }
 void add_amatrix(field alpha, bool atrans, pcamatrix a, pamatrix b) {
+  cnld::dd::drop(b->a);
   for (uint j = 0; j < b->cols; j++)
     for (uint i = 0; i < b->rows; i++) {
       field v = atrans ? fconj(a->a[(size_t)i * a->ld + j]) : a->a[(size_t)j * a->ld + i];
@@ -492,11 +500,22 @@ pbem3d new_slp_helmholtz_bem3d(field k, pcsurface3d gr, uint q_regular, uint q_s
   b->k = k;
   b->q_regular = q_regular;
   b->q_singular = q_singular;
-  b->priv = cnld_b200_create(0, gr->vertices, gr->triangles, &gr->x[0][0], &gr->t[0][0], q_regular, q_singular);
+  b->priv = cnld_b200_create(cnld::dd::device_id(), gr->vertices, gr->triangles, &gr->x[0][0], &gr->t[0][0], q_regular, q_singular);
   if (!b->priv) { free(b); return nullptr; }
   return b;
 }
+/* The double-layer operator is bound by cnld/h2lib/_helmholtzbem3d.pxd:13 but never constructed by
+ * cnl-dyna (ZFullMatrix / ZHMatrix build the single-layer operator only, compressed_formats.py:629,675);
+ * it is outside the hot path and has no kernel here.  The symbol exists so that the
+ * reference's extension modules link; calling it reports that and returns NULL. */
+pbem3d new_dlp_helmholtz_bem3d(field, pcsurface3d, uint, uint, basisfunctionbem3d, basisfunctionbem3d, field) {
+  set_error("new_dlp_helmholtz_bem3d: the double-layer potential operator is not implemented in libcnld_b200 "
+            "(cnl-dyna's frequency-response path only uses new_slp_helmholtz_bem3d)");
+  fprintf(stderr, "libcnld_b200: %s\n", cnld_b200_last_error());
+  return nullptr;
+}
 void assemble_bem3d_amatrix(pbem3d bem, pamatrix G) {
+  cnld::dd::drop(G->a);
   if (!bem || !bem->priv) { set_error("assemble_bem3d_amatrix: bem object has no device state"); die("assemble_bem3d_amatrix"); }
   if (G->rows != bem->gr->vertices || G->cols != bem->gr->vertices) { set_error("assemble_bem3d_amatrix: matrix must be vertices x vertices"); die("assemble_bem3d_amatrix"); }
   if (cnld_b200_assemble_slp_ll((cnld_ctx *)bem->priv, bem->k.re, bem->k.im, (cnld_field *)G->a, G->ld))
@@ -505,36 +524,99 @@ void assemble_bem3d_amatrix(pbem3d bem, pamatrix G) {
 
 /* ------------------------------------------------------- factorizations ---- */
 uint lrdecomp_amatrix(pamatrix a) {
-  uint info = 0;
+  // unpivoted LU on the GPU; the factors stay resident so that the per-source-patch lrsolve calls of
+  // generate_db.process (cnld/scripts/generate_db.py:82-91) do not re-upload them
   if (a->rows != a->cols) { set_error("lrdecomp_amatrix: matrix must be square"); die("lrdecomp_amatrix"); }
-  if (cnld_b200_lrdecomp(0, a->rows, (cnld_field *)a->a, a->ld, &info)) die("lrdecomp_amatrix");
-  return info;
+  const uint n = a->rows;
+  if (cnld_b200_device_count() <= cnld::dd::device_id()) { set_error("no CUDA device %d (libcnld_b200 has no CPU fallback)", cnld::dd::device_id()); die("lrdecomp_amatrix"); }
+  cnld::dd::drop(a->a);
+  cudaSetDevice(cnld::dd::device_id());
+  cplx *dA = nullptr;
+  cnld::LuWork w;
+  uint info = 0;
+  bool ok = cudaMalloc(&dA, sizeof(cplx) * std::max<size_t>((size_t)n * n, 1)) == cudaSuccess;
+  if (!ok) { cnld::dd::drop_all(); ok = cudaMalloc(&dA, sizeof(cplx) * std::max<size_t>((size_t)n * n, 1)) == cudaSuccess; }
+  ok = ok && (!n || cudaMemcpy2D(dA, sizeof(cplx) * n, a->a, sizeof(cplx) * a->ld, sizeof(cplx) * n, n, cudaMemcpyHostToDevice) == cudaSuccess);
+  ok = ok && !cnld::lu_work_alloc(w, n) && !cnld::lu_factor(0, w, dA, n);
+  ok = ok && cudaMemcpy(&info, w.info, sizeof(uint), cudaMemcpyDeviceToHost) == cudaSuccess;
+  ok = ok && (!n || cudaMemcpy2D(a->a, sizeof(cplx) * a->ld, dA, sizeof(cplx) * n, sizeof(cplx) * n, n, cudaMemcpyDeviceToHost) == cudaSuccess);
+  if (!ok) {
+    if (cudaGetLastError() != cudaSuccess) set_error("lrdecomp_amatrix: CUDA failure");
+    cnld::lu_work_free(w);
+    cudaFree(dA);
+    die("lrdecomp_amatrix");
+  }
+  if (info) { cnld::lu_work_free(w); cudaFree(dA); return info; }
+  cnld::dd::Resident *R = cnld::dd::adopt(a->a, n, n, a->ld, dA, cnld::dd::KIND_LU);
+  R->w = w;
+  R->w_ready = true;
+  return 0;
+}
+static cnld::dd::Resident *resident_lu(pcamatrix a, const char *who) {
+  cnld::dd::Resident *R = cnld::dd::resident(a->a, a->rows, a->cols, a->ld, cnld::dd::KIND_LU);
+  if (!R) die(who);
+  if (!R->w_ready) {   // factors that were not computed in this process' cache: rebuild the block inverses once
+    if (cnld::lu_work_alloc(R->w, a->rows) || cnld::lu_invert_diag(0, R->w, R->d, R->rows)) die(who);
+    R->w_ready = true;
+    R->kind = cnld::dd::KIND_LU;
+  }
+  return R;
 }
 void lrsolve_amatrix_avector(bool atrans, pcamatrix a, pavector x) {
-  if (atrans) { set_error("lrsolve_amatrix_avector: atrans is not used on the cnl-dyna path"); die("lrsolve_amatrix_avector"); }
-  if (cnld_b200_lrsolve(0, a->rows, (const cnld_field *)a->a, a->ld, (cnld_field *)x->v, 1, x->dim))
-    die("lrsolve_amatrix_avector");
+  if (a->rows != a->cols || x->dim != a->rows) { set_error("lrsolve_amatrix_avector: dimension mismatch"); die("lrsolve_amatrix_avector"); }
+  cnld::dd::Resident *R = resident_lu(a, "lrsolve_amatrix_avector");
+  const uint n = a->rows;
+  int rc;
+  if (!atrans) {
+    rc = cnld::dd::with_vectors(0, nullptr, n, (cplx *)x->v, true,
+                                [&](const cplx *, cplx *dx) { return cnld::lu_solve(0, R->w, R->d, n, dx, 1, n); });
+  } else {   // (L R)^H x = b:  R^H y = b, L^H x = y
+    rc = cnld::dd::with_vectors(0, nullptr, n, (cplx *)x->v, true, [&](const cplx *, cplx *dx) {
+      return cnld::dd::trsv(0, R->d, n, n, false, false, true, dx) || cnld::dd::trsv(0, R->d, n, n, true, true, true, dx);
+    });
+  }
+  if (rc) die("lrsolve_amatrix_avector");
 }
 void triangularsolve_amatrix_avector(bool alower, bool aunit, bool atrans, pcamatrix a, pavector x) {
-  // small host substitution (used by the reference only in commented-out code,
-  // compressed_formats.py:269-270); kept for API completeness
+  if (a->rows != a->cols || x->dim != a->rows) { set_error("triangularsolve_amatrix_avector: dimension mismatch"); die("triangularsolve_amatrix_avector"); }
+  cnld::dd::Resident *R = cnld::dd::resident(a->a, a->rows, a->cols, a->ld);
+  if (!R) die("triangularsolve_amatrix_avector");
   const uint n = a->rows;
-  auto A = [&](uint i, uint j) { return atrans ? fconj(a->a[(size_t)i * a->ld + j]) : a->a[(size_t)j * a->ld + i]; };
-  bool lower = atrans ? !alower : alower;
-  auto divf = [](field p, field q) { double d = q.re * q.re + q.im * q.im; return mk((p.re * q.re + p.im * q.im) / d, (p.im * q.re - p.re * q.im) / d); };
-  if (lower) {
-    for (uint i = 0; i < n; i++) {
-      field s = x->v[i];
-      for (uint j = 0; j < i; j++) { field p = fmul(A(i, j), x->v[j]); s = mk(s.re - p.re, s.im - p.im); }
-      x->v[i] = aunit ? s : divf(s, A(i, i));
-    }
-  } else {
-    for (uint ii = n; ii-- > 0;) {
-      field s = x->v[ii];
-      for (uint j = ii + 1; j < n; j++) { field p = fmul(A(ii, j), x->v[j]); s = mk(s.re - p.re, s.im - p.im); }
-      x->v[ii] = aunit ? s : divf(s, A(ii, ii));
-    }
-  }
+  if (cnld::dd::with_vectors(0, nullptr, n, (cplx *)x->v, true,
+                             [&](const cplx *, cplx *dx) { return cnld::dd::trsv(0, R->d, n, n, alower, aunit, atrans, dx); }))
+    die("triangularsolve_amatrix_avector");
+}
+/* Cholesky A = L L^H of a Hermitian positive definite matrix, lower triangle in place (upper part
+ * zeroed); returns 0 or the index (+1) of the first non-positive pivot (include/factorizations.h:281). */
+uint choldecomp_amatrix(pamatrix a) {
+  if (a->rows != a->cols) { set_error("choldecomp_amatrix: matrix must be square"); die("choldecomp_amatrix"); }
+  const uint n = a->rows;
+  cnld::dd::drop(a->a);
+  cnld::dd::Resident *R = cnld::dd::resident(a->a, n, n, a->ld, cnld::dd::KIND_CHOL);
+  if (!R) die("choldecomp_amatrix");
+  uint *d_info = nullptr, info = 0;
+  bool ok = cudaMalloc(&d_info, sizeof(uint)) == cudaSuccess && cudaMemset(d_info, 0, sizeof(uint)) == cudaSuccess;
+  ok = ok && !cnld::dd::potrf(0, R->d, n, n, d_info);
+  ok = ok && cudaMemcpy(&info, d_info, sizeof(uint), cudaMemcpyDeviceToHost) == cudaSuccess;
+  ok = ok && (!n || cudaMemcpy2D(a->a, sizeof(cplx) * a->ld, R->d, sizeof(cplx) * n, sizeof(cplx) * n, n, cudaMemcpyDeviceToHost) == cudaSuccess);
+  cudaFree(d_info);
+  if (!ok) { set_error("choldecomp_amatrix: CUDA failure: %s", cudaGetErrorString(cudaGetLastError())); die("choldecomp_amatrix"); }
+  cplx *keep = R->d;
+  R->d = nullptr;                       // re-register under the new host content (the factor)
+  cnld::dd::drop(a->a);
+  if (info) { cudaFree(keep); return info; }
+  cnld::dd::adopt(a->a, n, n, a->ld, keep, cnld::dd::KIND_CHOL);
+  return 0;
+}
+void cholsolve_amatrix_avector(pcamatrix a, pavector x) {
+  if (a->rows != a->cols || x->dim != a->rows) { set_error("cholsolve_amatrix_avector: dimension mismatch"); die("cholsolve_amatrix_avector"); }
+  cnld::dd::Resident *R = cnld::dd::resident(a->a, a->rows, a->cols, a->ld, cnld::dd::KIND_CHOL);
+  if (!R) die("cholsolve_amatrix_avector");
+  const uint n = a->rows;
+  if (cnld::dd::with_vectors(0, nullptr, n, (cplx *)x->v, true, [&](const cplx *, cplx *dx) {
+        return cnld::dd::trsv(0, R->d, n, n, true, false, false, dx) || cnld::dd::trsv(0, R->d, n, n, true, false, true, dx);
+      }))
+    die("cholsolve_amatrix_avector");
 }
 
 }  // extern "C"

@@ -78,6 +78,7 @@ void hmat_free(HMat &H);
 int hmat_assemble(cudaStream_t st, HMat &H, double kr, double ki, double accur);
 int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y, uint nrhs);
 int hmat_expand(cudaStream_t st, HMat &H, cplx *d_Z, size_t ld);
+int hmat_compress_dense(cudaStream_t st, HMat &H, const cplx *d_Z, size_t ld, double accur);
 int hmat_fetch_leaves(HMat &H);
 // (re)build the band lists and rank offsets of the batched matvec from H.leaf (after the ranks changed)
 int hmat_prepare_batched(HMat &H, bool fetch);

@@ -191,15 +191,15 @@ __device__ double block_sum(double v, double *sv) {
   return s;
 }
 
-template <int NQ, bool CPLXK>
-__global__ void __launch_bounds__(ACA_THREADS)
-k_aca(HLeafDev *leaves, const uint *__restrict__ far_ids, const __grid_constant__ RegRule R,
-      const double *__restrict__ qp, const double *__restrict__ g, const uint *__restrict__ perm,
-      const uint *__restrict__ v2t_ptr, const uint *__restrict__ v2t, double kr, double ki, double accur,
-      cplx *pool, unsigned char *flags, uint *capped) {
+// Partial-pivot ACA of one admissible leaf by a CTA (aca.h:114-117 decomp_partialaca_rkmatrix); the matrix
+// entries come from `entry(row vertex, column vertex)`: the far-field quadrature (k_aca) or an explicit
+// dense matrix (k_aca_dense: re-compression after dense-expansion H-arithmetic, h2compat_h.cu).
+template <class Entry>
+__device__ __forceinline__ void aca_leaf(HLeafDev *leaves, const uint lid, const Entry &entry,
+                                         const uint *__restrict__ perm, double accur, cplx *pool, unsigned char *flags,
+                                         uint *capped) {
   __shared__ double s_val[ACA_THREADS / 32];
   __shared__ uint s_idx[ACA_THREADS / 32];
-  const uint lid = far_ids[blockIdx.x];
   const HLeafDev L = leaves[lid];
   const uint m = L.m, n = L.n, kcap = L.kcap;
   cplx *U = pool + L.off, *V = U + (size_t)m * kcap;
@@ -216,7 +216,7 @@ k_aca(HLeafDev *leaves, const uint *__restrict__ far_ids, const __grid_constant_
     double best = -1.0;
     uint bj = 0xffffffffu;
     for (uint j = threadIdx.x; j < n; j += ACA_THREADS) {
-      cplx r = far_entry<NQ, CPLXK>(vi, cidx[j], R, qp, g, v2t_ptr, v2t, kr, ki);
+      cplx r = entry(vi, cidx[j]);
       for (uint l = 0; l < k; l++) cfms(r, U[(size_t)l * m + ik], V[(size_t)l * n + j]);
       V[(size_t)k * n + j] = r;
       double a = r.x * r.x + r.y * r.y;
@@ -253,7 +253,7 @@ k_aca(HLeafDev *leaves, const uint *__restrict__ far_ids, const __grid_constant_
     uint bi = 0xffffffffu;
     __syncthreads();
     for (uint i = threadIdx.x; i < m; i += ACA_THREADS) {
-      cplx c = far_entry<NQ, CPLXK>(ridx[i], vj, R, qp, g, v2t_ptr, v2t, kr, ki);
+      cplx c = entry(ridx[i], vj);
       for (uint l = 0; l < k; l++) cfms(c, U[(size_t)l * m + i], V[(size_t)l * n + jk]);
       U[(size_t)k * m + i] = c;
       double a = c.x * c.x + c.y * c.y;
@@ -277,6 +277,45 @@ k_aca(HLeafDev *leaves, const uint *__restrict__ far_ids, const __grid_constant_
     // factorisation (k == min(m, n)) is exact, not capped.
     if (!met && k == kcap && kcap < min(m, n)) atomicAdd(capped, 1u);
   }
+}
+
+template <int NQ, bool CPLXK>
+struct QuadEntry {
+  const RegRule &R;
+  const double *__restrict__ qp, *__restrict__ g;
+  const uint *__restrict__ v2t_ptr, *__restrict__ v2t;
+  double kr, ki;
+  __device__ __forceinline__ cplx operator()(uint vi, uint vj) const {
+    return far_entry<NQ, CPLXK>(vi, vj, R, qp, g, v2t_ptr, v2t, kr, ki);
+  }
+};
+template <int NQ, bool CPLXK>
+__global__ void __launch_bounds__(ACA_THREADS)
+k_aca(HLeafDev *leaves, const uint *__restrict__ far_ids, const __grid_constant__ RegRule R,
+      const double *__restrict__ qp, const double *__restrict__ g, const uint *__restrict__ perm,
+      const uint *__restrict__ v2t_ptr, const uint *__restrict__ v2t, double kr, double ki, double accur,
+      cplx *pool, unsigned char *flags, uint *capped) {
+  const QuadEntry<NQ, CPLXK> entry{R, qp, g, v2t_ptr, v2t, kr, ki};
+  aca_leaf(leaves, far_ids[blockIdx.x], entry, perm, accur, pool, flags, capped);
+}
+
+struct DenseEntry {
+  const cplx *__restrict__ Z;
+  size_t ld;
+  __device__ __forceinline__ cplx operator()(uint vi, uint vj) const { return Z[(size_t)vj * ld + vi]; }
+};
+__global__ void __launch_bounds__(ACA_THREADS)
+k_aca_dense(HLeafDev *leaves, const uint *__restrict__ far_ids, const cplx *__restrict__ Z, size_t ld,
+            const uint *__restrict__ perm, double accur, cplx *pool, unsigned char *flags, uint *capped) {
+  const DenseEntry entry{Z, ld};
+  aca_leaf(leaves, far_ids[blockIdx.x], entry, perm, accur, pool, flags, capped);
+}
+// inadmissible leaves of the re-compression: the sub-block itself
+__global__ void k_gather_dense(const HLeafDev *__restrict__ leaves, const uint *__restrict__ near_ids,
+                               const cplx *__restrict__ Z, size_t ld, const uint *__restrict__ perm, cplx *pool) {
+  const HLeafDev L = leaves[near_ids[blockIdx.x]];
+  for (size_t e = threadIdx.x; e < (size_t)L.m * L.n; e += blockDim.x)
+    pool[L.off + e] = Z[(size_t)perm[L.c0 + e / L.m] * ld + perm[L.r0 + e % L.m]];
 }
 
 // ---- matvec: y_perm += alpha * Z * x_perm over the leaves --------------------------------
@@ -1043,6 +1082,28 @@ int hmat_assemble(cudaStream_t st, HMat &H, double kr, double ki, double accur) 
 }
 
 int g_hmv_tstack = 1;
+
+// Fill every leaf of H from an explicit dense matrix on the device (original DOF order, column-major):
+// inadmissible leaves take their sub-block, admissible leaves its partial-pivot ACA to `accur`.
+int hmat_compress_dense(cudaStream_t st, HMat &H, const cplx *d_Z, size_t ld, double accur) {
+  CNLD_CK(cudaMemsetAsync(H.d_pool, 0, sizeof(cplx) * H.pool_size, st));
+  CNLD_CK(cudaMemsetAsync(H.d_err, 0, 2 * sizeof(uint), st));
+  if (H.nnear) {
+    k_gather_dense<<<H.nnear, 256, 0, st>>>(H.d_leaf, H.d_near, d_Z, ld, H.d_perm, H.d_pool);
+    CNLD_CK_LAUNCH();
+  }
+  if (H.nfar) {
+    k_aca_dense<<<H.nfar, ACA_THREADS, 0, st>>>(H.d_leaf, H.d_far, d_Z, ld, H.d_perm, accur, H.d_pool, H.d_flags, H.d_err + 1);
+    CNLD_CK_LAUNCH();
+  }
+  uint errs[2] = {0, 0};
+  CNLD_CK(cudaMemcpyAsync(errs, H.d_err, 2 * sizeof(uint), cudaMemcpyDeviceToHost, st));
+  CNLD_CK(cudaStreamSynchronize(st));
+  H.capped_leaves = errs[1];
+  H.assembled = true;
+  H.mv_ready = false;
+  return 0;
+}
 
 // device vectors in ORIGINAL DOF order, nrhs of them with stride n:  y += alpha * Z x
 int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y, uint nrhs) {

@@ -34,6 +34,14 @@ typedef real *preal;
 void init_h2lib(int *argc, char ***argv);
 void uninit_h2lib(void);
 void freemem(void *ptr);
+/* macros in H2Lib (include/basic.h:181,298,302), used by the Cython parametrizations
+ * (cnld/h2lib/macrosurface3d.pyx:83-172) */
+#include <math.h>
+#ifndef REAL_ABS
+#define REAL_ABS(x) fabs(x)
+#define REAL_NORM2(x, y) sqrt((x) * (x) + (y) * (y))
+#define REAL_NORM3(x, y, z) sqrt((x) * (x) + (y) * (y) + (z) * (z))
+#endif
 
 /* ---- avector (cnld/h2lib/_avector.pxd:8-23; include/avector.h:39-48) ------- */
 typedef struct _avector {
@@ -162,6 +170,10 @@ pbem3d new_bem3d(pcsurface3d gr, basisfunctionbem3d row_basis, basisfunctionbem3
 void del_bem3d(pbem3d bem);
 pbem3d new_slp_helmholtz_bem3d(field k, pcsurface3d gr, uint q_regular, uint q_singular,
                                basisfunctionbem3d row_basis, basisfunctionbem3d col_basis);
+/* bound by _helmholtzbem3d.pxd:13 (helmholtzbem3d.h:113) but never constructed by cnl-dyna: no kernel here,
+ * the call reports that and returns NULL ("what links and what does not") */
+pbem3d new_dlp_helmholtz_bem3d(field k, pcsurface3d gr, uint q_regular, uint q_singular,
+                               basisfunctionbem3d row_basis, basisfunctionbem3d col_basis, field alpha);
 void assemble_bem3d_amatrix(pbem3d bem, pamatrix G);
 
 /* ---- cluster / block trees (_cluster.pxd:7-23, _block.pxd:8-31; cluster.h:40-70, block.h:48-69) */
@@ -261,6 +273,9 @@ void del_truncmode(ptruncmode tm);
 ptruncmode new_releucl_truncmode(void);
 
 /* ---- krylovsolvers (_krylovsolvers.pxd:10-13; krylovsolvers.h:283) -------------------------- */
+/* conjugate gradients for Hermitian positive definite operators; the matvec runs on the GPU */
+uint solve_cg_amatrix_avector(pcamatrix A, pcavector b, pavector x, real eps, uint maxiter);
+uint solve_cg_hmatrix_avector(pchmatrix A, pcavector b, pavector x, real eps, uint maxiter);
 uint solve_gmres_amatrix_avector(pcamatrix A, pcavector b, pavector x, real eps, uint maxiter, uint kmax);
 uint solve_gmres_hmatrix_avector(pchmatrix A, pcavector b, pavector x, real eps, uint maxiter, uint kmax);
 
@@ -268,6 +283,40 @@ uint solve_gmres_hmatrix_avector(pchmatrix A, pcavector b, pavector x, real eps,
 uint lrdecomp_amatrix(pamatrix a);
 void lrsolve_amatrix_avector(bool atrans, pcamatrix a, pavector x);
 void triangularsolve_amatrix_avector(bool alower, bool aunit, bool atrans, pcamatrix a, pavector x);
+/* Cholesky A = L L^H (factorizations.h:281, :315): lower triangle in place; returns 0 or the failing pivot + 1 */
+uint choldecomp_amatrix(pamatrix a);
+void cholsolve_amatrix_avector(pcamatrix a, pavector x);
+
+/* ---- matrixnorms (_matrixnorms.pxd:11-19; matrixnorms.h): spectral norm of a difference by 20 power
+ * iteration steps, every operator applied on the GPU; the *_lr_* variants compare with the product L R of
+ * a factorisation held in one matrix --------------------------------------------------------------- */
+real norm2diff_amatrix_sparsematrix(pcsparsematrix a, pcamatrix b);
+real norm2diff_amatrix_hmatrix(pchmatrix a, pcamatrix b);
+real norm2diff_sparsematrix_hmatrix(pchmatrix a, pcsparsematrix b);
+real norm2diff_lr_amatrix(pcamatrix A, pcamatrix LR);
+real norm2diff_lr_hmatrix(pchmatrix A, pchmatrix LR);
+real norm2diff_lr_amatrix_hmatrix(pcamatrix A, pchmatrix LR);
+real norm2diff_lr_hmatrix_amatrix(pchmatrix A, pcamatrix LR);
+real norm2diff_lr_sparsematrix_amatrix(pcsparsematrix A, pcamatrix LR);
+real norm2diff_lr_sparsematrix_hmatrix(pcsparsematrix A, pchmatrix LR);
+
+/* ---- harith (_harith.pxd:13-23; harith.h:88-630).  Dense-expansion H-arithmetic on the GPU: operands are
+ * expanded to dense device matrices, the operation runs on the sweep's dense kernels (ZGEMM, unpivoted LU,
+ * Cholesky) and an H-matrix result is re-compressed into the target's block structure (partial-pivot ACA
+ * of the explicit block to `eps`; the truncation mode is accepted and ignored).  Factorisations stay dense
+ * on the device, attached to the hmatrix they were computed from.  Limited to sizes whose dense expansion
+ * fits the device (tens of thousands of DOFs on a B200); larger arrays take the GMRES path. ------------ */
+void lrdecomp_hmatrix(phmatrix a, pctruncmode tm, real eps);
+void lrsolve_hmatrix_avector(bool atrans, pchmatrix a, pavector x);
+void lreval_hmatrix_avector(bool atrans, pchmatrix a, pavector x);
+void choldecomp_hmatrix(phmatrix a, pctruncmode tm, real eps);
+void cholsolve_hmatrix_avector(pchmatrix a, pavector x);
+void choleval_hmatrix_avector(pchmatrix a, pavector x);
+void addmul_hmatrix(field alpha, bool xtrans, pchmatrix x, bool ytrans, pchmatrix y, pctruncmode tm, real eps,
+                    phmatrix z);
+void add_hmatrix(field alpha, pchmatrix a, pctruncmode tm, real eps, phmatrix b);
+void add_amatrix_hmatrix(field alpha, bool atrans, pcamatrix a, pctruncmode tm, real eps, phmatrix b);
+void triangularsolve_hmatrix_avector(bool alower, bool aunit, bool atrans, pchmatrix a, pavector x);
 
 #ifdef __cplusplus
 }
