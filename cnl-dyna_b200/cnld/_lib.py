@@ -77,6 +77,9 @@ def lib():
         L.cnld_b200_pfield_fetch.argtypes = [vp, u32, vp, u32, vp]
         L.cnld_b200_pfield_info.argtypes = [vp, vp]
         L.cnld_b200_pres_plan_stats.argtypes = [u32, u32, vp, vp, vp, vp]
+        L.cnld_b200_db_append_block.argtypes = [C.c_char_p, u32, vp, vp, u32, vp, vp, u32, vp, vp, vp, C.c_int]
+        L.cnld_b200_db_begin_bulk.argtypes = [C.c_char_p]
+        L.cnld_b200_db_finish.argtypes = [C.c_char_p]
         L.cnld_b200_hmat_create.restype = vp
         L.cnld_b200_hmat_create.argtypes = [vp, u32, f64, C.c_int, C.c_int, u32]
         L.cnld_b200_hmat_destroy.argtypes = [vp]
@@ -355,6 +358,31 @@ def pres_plan_stats(vertices, triangles):
     check(lib().cnld_b200_pres_plan_stats(len(x), len(t), ptr(x), ptr(t), ptr(counts), ptr(order)))
     keys = ('chunks', 'node_entries', 'max_triangles', 'max_nodes', 'accumulating_entries', 'untouched_vertices')
     return dict(zip(keys, (int(v) for v in counts))), order
+
+
+def db_append_block(file, freqs, wavenums, x_patch, x_node=None, nodes=None, times=None, job_ids=None, fast=True):
+    """One transaction: the rows generate_db.process writes for a block of frequencies (C writer)."""
+    freqs, wavenums = _c(freqs, np.float64), _c(wavenums, np.float64)
+    x_patch = _c(x_patch, np.complex128)
+    nf, P, _ = x_patch.shape
+    N = 0
+    if x_node is not None:
+        x_node = _c(x_node, np.complex128)
+        N = x_node.shape[2]
+        nodes = _c(nodes, np.float64)
+        assert x_node.shape[:2] == (nf, P) and nodes.shape == (N, 3)
+    times = _c(times, np.float64) if times is not None else None
+    job_ids = _c(job_ids, np.uint32) if job_ids is not None else None
+    check(lib().cnld_b200_db_append_block(os.fsencode(file), nf, ptr(freqs), ptr(wavenums), P, ptr(x_patch), ptr(times), N,
+                                          ptr(x_node), ptr(nodes), ptr(job_ids), int(fast)))
+
+
+def db_begin_bulk(file):
+    check(lib().cnld_b200_db_begin_bulk(os.fsencode(file)))
+
+
+def db_finish(file):
+    check(lib().cnld_b200_db_finish(os.fsencode(file)))
 
 
 ADMIS = {'2': 0, 'max': 1, 'sphere': 2, '2min': 3, '2_min': 3}

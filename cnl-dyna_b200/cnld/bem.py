@@ -24,29 +24,27 @@ def array_z_matrix(array, refn, k, format='HFormat', *args, **kwargs):
     return ZFullMatrix(amesh, k, *args, **kwargs)
 
 
+class _MaskedFluidOperator:
+    """x -> -w^2 2 rho M A M x with M the projector that zeroes the clamped boundary nodes: the fluid
+    loading operator of the Krylov formulation (bem.py:40-72, scratch/freq_resp_db_krylov.py:38-79).
+    `apply` is the H-/dense matvec on the GPU or the LU solve with the factored impedance matrix."""
+
+    def __init__(self, apply, free, scale):
+        self.apply, self.free, self.scale = apply, free, scale
+
+    def __call__(self, x):
+        v = np.where(self.free, np.asarray(x, dtype=np.complex128).ravel(), 0.0)
+        return self.scale * np.where(self.free, self.apply(v), 0.0)
+
+
 def array_z_linop(array, refn, f, c, rho, *args, **kwargs):
-    """Linear operators x -> -w^2 2 rho Z x (boundary rows/cols masked) and its LU-based inverse
-    (bem.py:40-72)."""
+    """(Gbe, Gbe_inv) as scipy LinearOperators, like bem.array_z_linop (bem.py:40-72)."""
     from scipy.sparse.linalg import LinearOperator
-    k, omg = 2 * np.pi * f / c, 2 * np.pi * f
-    Z = array_z_matrix(array, refn, k, *args, **kwargs)
-    Z_LU = Z.lu()
+    omega = 2 * np.pi * f
+    Z = array_z_matrix(array, refn, omega / c, *args, **kwargs)
+    Zlu = Z.lu()
     amesh = mesh.Mesh.from_abstract(array, refn)
-    ob, n = amesh.on_boundary, len(amesh.vertices)
-
-    def mv(x):
-        x = np.array(x, dtype=np.complex128).ravel()
-        x[ob] = 0
-        p = Z * x
-        p[ob] = 0
-        return -omg**2 * rho * 2 * p
-
-    def inv_mv(x):
-        x = np.array(x, dtype=np.complex128).ravel()
-        x[ob] = 0
-        p = Z_LU._triangularsolve(x)
-        p[ob] = 0
-        return -omg**2 * rho * 2 * p
-
-    return (LinearOperator((n, n), dtype=np.complex128, matvec=mv),
-            LinearOperator((n, n), dtype=np.complex128, matvec=inv_mv))
+    free = ~np.asarray(amesh.on_boundary, dtype=bool)
+    n, scale = len(free), -omega**2 * rho * 2
+    ops = [_MaskedFluidOperator(fn, free, scale) for fn in (Z._matvec, Zlu._triangularsolve)]
+    return tuple(LinearOperator((n, n), dtype=np.complex128, matvec=op) for op in ops)

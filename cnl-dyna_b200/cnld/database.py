@@ -116,11 +116,26 @@ def append_patch_to_patch_imp_resp(con, **kwargs):
                         _rows(kwargs, ['source_patch', 'dest_patch', 'time', 'displacement']))
 
 
-@read_db
-def append_frequency_block(con, freqs, wavenums, x_patch, x_node=None, nodes=None, times=None):
+def append_frequency_block(file, freqs, wavenums, x_patch, x_node=None, nodes=None, times=None, job_ids=None,
+                           threads=None):
     """One transaction for a block of frequencies: x_patch[nf, P(src), P(dst)] and optionally
-    x_node[nf, P(src), N] (same rows the reference writes one source patch at a time,
-    generate_db.py:101-127)."""
+    x_node[nf, P(src), N] -- the rows the reference writes one source patch at a time through Python
+    (generate_db.py:101-127, database.py:144-194) -- plus the progress rows `job_ids`, written by the C
+    bulk writer (prepared statements on libsqlite3, node rows staged by `threads` threads and appended by
+    raw record copy; csrc/dbwriter.cpp).  Same tables, columns, values and row order."""
+    from . import _lib
+    if not os.path.isfile(file):
+        raise IOError('File does not exist')
+    if threads is None:
+        threads = min(8, len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1))
+    if index_exists(file, 'patch_to_node_freq_resp_index'):
+        threads = 1          # the staged raw-copy append needs a target without indexes (begin_bulk)
+    _lib.db_append_block(file, freqs, wavenums, x_patch, x_node, nodes, times, job_ids, fast=max(1, int(threads)))
+
+
+@read_db
+def append_frequency_block_py(con, freqs, wavenums, x_patch, x_node=None, nodes=None, times=None):
+    """The same rows through sqlite3.executemany (kept as the cross-check of the C writer)."""
     nf, P, _ = x_patch.shape
     with con:
         for i in range(nf):
@@ -138,6 +153,23 @@ def append_frequency_block(con, freqs, wavenums, x_patch, x_node=None, nodes=Non
                     con.executemany('INSERT INTO patch_to_node_freq_resp VALUES (?,?,?,?,?,?,?,?,?)',
                                     zip(repeat(s), ids, xs, ys, zs, repeat(float(freqs[i])), repeat(float(wavenums[i])),
                                         x_node[i, s].real.tolist(), x_node[i, s].imag.tolist()))
+
+
+@open_db
+def index_exists(con, name):
+    return con.execute("SELECT count(*) FROM sqlite_master WHERE type='index' and name=?", (name,)).fetchone()[0] != 0
+
+
+def begin_bulk(file):
+    """Drop the two frequency-response indexes for the duration of a sweep (a bulk load maintains them
+    row by row otherwise); finish_bulk rebuilds them, leaving the reference's schema (database.py:31-45)."""
+    from . import _lib
+    _lib.db_begin_bulk(file)
+
+
+def finish_bulk(file):
+    from . import _lib
+    _lib.db_finish(file)
 
 
 @read_db

@@ -183,6 +183,29 @@ def _lib_h2():
         'new_releucl_truncmode': (P(_truncmode), []),
         'solve_gmres_amatrix_avector': (uint, [P(_amatrix), P(_avector), P(_avector), real, uint, uint]),
         'solve_gmres_hmatrix_avector': (uint, [P(_hmatrix), P(_avector), P(_avector), real, uint, uint]),
+        'solve_cg_amatrix_avector': (uint, [P(_amatrix), P(_avector), P(_avector), real, uint]),
+        'solve_cg_hmatrix_avector': (uint, [P(_hmatrix), P(_avector), P(_avector), real, uint]),
+        'choldecomp_amatrix': (uint, [P(_amatrix)]), 'cholsolve_amatrix_avector': (None, [P(_amatrix), P(_avector)]),
+        'new_dlp_helmholtz_bem3d': (P(_bem3d), [field, P(_surface3d), uint, uint, C.c_int, C.c_int, field]),
+        'norm2diff_amatrix_sparsematrix': (real, [P(_sparsematrix), P(_amatrix)]),
+        'norm2diff_amatrix_hmatrix': (real, [P(_hmatrix), P(_amatrix)]),
+        'norm2diff_sparsematrix_hmatrix': (real, [P(_hmatrix), P(_sparsematrix)]),
+        'norm2diff_lr_amatrix': (real, [P(_amatrix), P(_amatrix)]),
+        'norm2diff_lr_hmatrix': (real, [P(_hmatrix), P(_hmatrix)]),
+        'norm2diff_lr_amatrix_hmatrix': (real, [P(_amatrix), P(_hmatrix)]),
+        'norm2diff_lr_hmatrix_amatrix': (real, [P(_hmatrix), P(_amatrix)]),
+        'norm2diff_lr_sparsematrix_amatrix': (real, [P(_sparsematrix), P(_amatrix)]),
+        'norm2diff_lr_sparsematrix_hmatrix': (real, [P(_sparsematrix), P(_hmatrix)]),
+        'lrdecomp_hmatrix': (None, [P(_hmatrix), P(_truncmode), real]),
+        'lrsolve_hmatrix_avector': (None, [C.c_bool, P(_hmatrix), P(_avector)]),
+        'lreval_hmatrix_avector': (None, [C.c_bool, P(_hmatrix), P(_avector)]),
+        'choldecomp_hmatrix': (None, [P(_hmatrix), P(_truncmode), real]),
+        'cholsolve_hmatrix_avector': (None, [P(_hmatrix), P(_avector)]),
+        'choleval_hmatrix_avector': (None, [P(_hmatrix), P(_avector)]),
+        'addmul_hmatrix': (None, [field, C.c_bool, P(_hmatrix), C.c_bool, P(_hmatrix), P(_truncmode), real, P(_hmatrix)]),
+        'add_hmatrix': (None, [field, P(_hmatrix), P(_truncmode), real, P(_hmatrix)]),
+        'add_amatrix_hmatrix': (None, [field, C.c_bool, P(_amatrix), P(_truncmode), real, P(_hmatrix)]),
+        'triangularsolve_hmatrix_avector': (None, [C.c_bool, C.c_bool, C.c_bool, P(_hmatrix), P(_avector)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -791,6 +814,83 @@ def lrsolve_amatrix_avector(atrans, a, x):
 
 def triangularsolve_amatrix_avector(alower, aunit, atrans, a, x):
     _lib_h2().triangularsolve_amatrix_avector(bool(alower), bool(aunit), bool(atrans), a.ptr, x.ptr)
+
+
+# ---- the rest of the surface cnld/h2lib/*.pyx exposes (krylovsolvers / factorizations / matrixnorms / harith)
+def solve_cg_amatrix_avector(A, b, x, eps, maxiter):
+    return _lib_h2().solve_cg_amatrix_avector(A.ptr, b.ptr, x.ptr, eps, maxiter)
+
+
+def solve_cg_hmatrix_avector(A, b, x, eps, maxiter):
+    return _lib_h2().solve_cg_hmatrix_avector(A.ptr, b.ptr, x.ptr, eps, maxiter)
+
+
+def choldecomp_amatrix(a):
+    return _lib_h2().choldecomp_amatrix(a.ptr)
+
+
+def cholsolve_amatrix_avector(a, x):
+    _lib_h2().cholsolve_amatrix_avector(a.ptr, x.ptr)
+
+
+def new_dlp_helmholtz_bem3d(k, surf, q_regular, q_singular, row_basis, col_basis, alpha):
+    """Not on cnl-dyna's path and not implemented by libcnld_b200: raises with the library's message."""
+    ptr = _lib_h2().new_dlp_helmholtz_bem3d(_f(k), surf.ptr, q_regular, q_singular, int(row_basis), int(col_basis), _f(alpha))
+    if not ptr:
+        raise NotImplementedError(_lib.lib().cnld_b200_last_error().decode())
+    return Bem3d.wrap(ptr, True)
+
+
+def _norm(name):
+    def fn(a, b):
+        return getattr(_lib_h2(), name)(a.ptr, b.ptr)
+    fn.__name__ = name
+    return fn
+
+
+for _n in ('amatrix_sparsematrix', 'amatrix_hmatrix', 'sparsematrix_hmatrix', 'lr_amatrix', 'lr_hmatrix',
+           'lr_amatrix_hmatrix', 'lr_hmatrix_amatrix', 'lr_sparsematrix_amatrix', 'lr_sparsematrix_hmatrix'):
+    globals()['norm2diff_' + _n] = _norm('norm2diff_' + _n)
+
+
+def lrdecomp_hmatrix(a, tm, eps):
+    _lib_h2().lrdecomp_hmatrix(a.ptr, tm.ptr, eps)
+
+
+def lrsolve_hmatrix_avector(atrans, a, x):
+    _lib_h2().lrsolve_hmatrix_avector(bool(atrans), a.ptr, x.ptr)
+
+
+def lreval_hmatrix_avector(atrans, a, x):
+    _lib_h2().lreval_hmatrix_avector(bool(atrans), a.ptr, x.ptr)
+
+
+def choldecomp_hmatrix(a, tm, eps):
+    _lib_h2().choldecomp_hmatrix(a.ptr, tm.ptr, eps)
+
+
+def cholsolve_hmatrix_avector(a, x):
+    _lib_h2().cholsolve_hmatrix_avector(a.ptr, x.ptr)
+
+
+def choleval_hmatrix_avector(a, x):
+    _lib_h2().choleval_hmatrix_avector(a.ptr, x.ptr)
+
+
+def addmul_hmatrix(alpha, xtrans, x, ytrans, y, tm, eps, z):
+    _lib_h2().addmul_hmatrix(_f(alpha), bool(xtrans), x.ptr, bool(ytrans), y.ptr, tm.ptr, eps, z.ptr)
+
+
+def add_hmatrix(alpha, a, tm, eps, b):
+    _lib_h2().add_hmatrix(_f(alpha), a.ptr, tm.ptr, eps, b.ptr)
+
+
+def add_amatrix_hmatrix(alpha, atrans, a, tm, eps, b):
+    _lib_h2().add_amatrix_hmatrix(_f(alpha), bool(atrans), a.ptr, tm.ptr, eps, b.ptr)
+
+
+def triangularsolve_hmatrix_avector(alower, aunit, atrans, a, x):
+    _lib_h2().triangularsolve_hmatrix_avector(bool(alower), bool(aunit), bool(atrans), a.ptr, x.ptr)
 
 
 __all__ = [n for n in dir() if not n.startswith('_') and n not in ('C', 'np', 'enum', 'atexit', 'real', 'uint')]

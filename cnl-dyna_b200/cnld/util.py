@@ -5,35 +5,48 @@ from copy import deepcopy
 import numpy as np
 
 
-def memoize(func, maxsize=20):
-    """Mirror of util.memoize (util.py:549-588): objects with `_memoize()` contribute that key,
-    ndarrays their bytes, floats are rounded to 18 digits; results are deep-copied."""
-    def make_hashable(obj):
-        if hasattr(obj, '_memoize'):
-            return obj._memoize()
-        try:
-            hash(obj)
-        except TypeError:
-            if isinstance(obj, np.ndarray):
-                return obj.tobytes()
-            return str(obj)
-        if isinstance(obj, float):
-            return round(obj, 18)
-        return obj
+class _Memo:
+    """Call cache behind `memoize`.  Same observable contract as the reference's decorator
+    (util.py:549-588) -- a bounded `memo` dict on the wrapped function, argument keys built from
+    `_memoize()` of abstract objects / array bytes / floats rounded to 18 digits, every hit returned as a
+    deep copy -- written as a small class around one key function."""
 
-    func.memo = {}
+    def __init__(self, func, maxsize):
+        self.func, self.maxsize, self.memo = func, maxsize, {}
+        func.memo = self.memo                      # the reference exposes the cache as func.memo
+
+    @staticmethod
+    def key_of(value):
+        memo_key = getattr(value, '_memoize', None)
+        if callable(memo_key):
+            return memo_key()
+        if isinstance(value, np.ndarray):
+            return (value.shape, value.dtype.str, value.tobytes())
+        if isinstance(value, float):
+            return round(value, 18)
+        try:
+            hash(value)
+            return value
+        except TypeError:
+            return str(value)
+
+    def __call__(self, *args, **kwargs):
+        key = (tuple(map(self.key_of, args)), tuple(sorted((k, self.key_of(v)) for k, v in kwargs.items())))
+        hit = self.memo.get(key)
+        if hit is None:
+            hit = self.func(*args, **kwargs)
+            if len(self.memo) <= self.maxsize:     # a full cache computes without storing
+                self.memo[key] = hit
+        return deepcopy(hit)
+
+
+def memoize(func, maxsize=20):
+    cache = _Memo(func, maxsize)
 
     @functools.wraps(func)
-    def decorator(*args, **kwargs):
-        key = (tuple(make_hashable(a) for a in args),
-               tuple((k, make_hashable(v)) for k, v in sorted(kwargs.items())))
-        if key not in func.memo:
-            if len(func.memo) > maxsize:
-                return func(*args, **kwargs)
-            func.memo[key] = func(*args, **kwargs)
-        return deepcopy(func.memo[key])
-
-    return decorator
+    def cached(*args, **kwargs):
+        return cache(*args, **kwargs)
+    return cached
 
 
 def meshview(v1, v2, v3, mode='cartesian', as_list=True):

@@ -266,6 +266,19 @@ int cnld_b200_hsweep_run(cnld_ctx *ctx, cnld_hmat *h, const double *freqs, cnld_
                          cnld_uint maxiter, cnld_uint batch, cnld_field *x_patch,
                          cnld_field *x_node, cnld_uint *iters, double *t_freq);
 
+/* ---- database writer ---------------------------------------------------
+ * Bulk appends to cnl-dyna's sqlite database (cnld/database.py:22-92 schema, :144-194 append_*;
+ * cnld/scripts/generate_db.py:101-130 writes the same rows one source patch at a time through Python):
+ * prepared statements on libsqlite3, one transaction per block of frequencies, straight from the arrays
+ * cnld_b200_sweep_run returned.  x_patch[nf][P(src)][P(dst)], x_node[nf][P(src)][N] (nullable),
+ * nodes[N][3], times[nf] (nullable), job_ids[nf] (nullable: progress rows marked complete, 1-based). */
+int cnld_b200_db_append_block(const char *file, cnld_uint nf, const double *freqs, const double *wavenums,
+                              cnld_uint P, const cnld_field *x_patch, const double *times, cnld_uint N,
+                              const cnld_field *x_node, const double *nodes, const cnld_uint *job_ids, int fast);
+/* drop the two frequency-response indexes before a bulk load / (re)build them after it */
+int cnld_b200_db_begin_bulk(const char *file);
+int cnld_b200_db_finish(const char *file);
+
 /* ---- microbenchmarks used for roofline denominators ----------------------- */
 /* FP64 DMMA ZGEMM C(m x n) -= A(m x k) B(k x n) on device-resident random data;
  * returns achieved TFLOP/s (8 m n k flop) averaged over reps. */

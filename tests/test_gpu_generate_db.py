@@ -6,15 +6,19 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def test_generate_db_end_to_end_and_resume(tmp_path, po):
+@pytest.mark.parametrize('fmt,devices,tol', [('FullFormat', 1, 1e-6), ('FullFormat', [0, 0], 1e-6), ('HFormat', 1, 2e-2),
+                                             ('HFormat', [0, 0], 2e-2)])
+def test_generate_db_end_to_end_and_resume(tmp_path, po, fmt, devices, tol):
+    """cfg.format picks the solver (dense LU / ACA H-matrix + GMRES, tolerance = the reference's eps_aca for the
+    latter); devices = [0, 0] runs the multi-process driver (one worker per entry) with both workers on GPU 0."""
     from cnld import abstract, arrays, database
     from cnld.scripts import generate_db
     arr = arrays.matrix_array(nelem=(2, 1))
     cfg_file = str(tmp_path / 'array.json')
     abstract.dump(arr, cfg_file)
-    cfg = generate_db.Config(freqs=(0, 8e6, 2e6), mesh_refn=3, array_config=cfg_file)
+    cfg = generate_db.Config(freqs=(0, 8e6, 2e6), mesh_refn=3, array_config=cfg_file, format=fmt)
     db = str(tmp_path / 'out' / 'resp.db')
-    generate_db.main(cfg, db, block=2)
+    generate_db.main(cfg, db, block=2, devices=devices)
     freqs, ppfr = database.read_patch_to_patch_freq_resp(db)
     assert np.allclose(freqs, [0, 2e6, 4e6, 6e6, 8e6]) and ppfr.shape == (18, 18, 5)
     f2, pnfr, nodes = database.read_patch_to_node_freq_resp(db)
@@ -24,8 +28,8 @@ def test_generate_db_end_to_end_and_resume(tmp_path, po):
     assert np.allclose(nodes, am.vertices)
     for i, f in enumerate(freqs):
         Xo, XPo = po.solve_frequency(am, blocks, f)
-        assert np.linalg.norm(pnfr[:, :, i].T - Xo) / np.linalg.norm(Xo) < 1e-6
-        assert np.linalg.norm(ppfr[:, :, i].T - XPo) / np.linalg.norm(XPo) < 1e-6
+        assert np.linalg.norm(pnfr[:, :, i].T - Xo) / np.linalg.norm(Xo) < tol
+        assert np.linalg.norm(ppfr[:, :, i].T - XPo) / np.linalg.norm(XPo) < tol
     t, ppir = database.read_patch_to_patch_imp_resp(db)
     to, ho = po.fft_to_fir(freqs, ppfr, interp=cfg.freq_interp, use_kkr=True)
     assert ppir.shape == ho.shape and np.linalg.norm(ppir - ho) / np.linalg.norm(ho) < 1e-9

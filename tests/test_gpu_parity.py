@@ -256,3 +256,67 @@ def test_nearfield_subblock_vs_oracle_and_dense(L, po):
     with pytest.raises(L.Cnldb200Error):
         ctx.nearfield(k, [1, 1], [2])          # repeated index
     ctx.close()
+
+
+def test_compat_dense_entry_points(L):
+    """The H2Lib-named dense entry points that used to loop on the host now run on the GPU behind a
+    device-resident copy (densedev.cu): matvec, unpivoted LU + repeated solves with the cached factors,
+    adjoint solve, triangular solves, Cholesky, CG, GMRES, spectral-norm estimates."""
+    from cnld import h2lib as h
+    rng = np.random.default_rng(11)
+    n = 300
+    a = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)) + n * 0.8 * np.eye(n)
+    A = h.AMatrix.from_array(np.ascontiguousarray(a.T))           # numpy view is the transpose of the stored matrix
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    y = h.AVector(n)
+    y.v[:] = 1.0
+    h.addeval_amatrix_avector(2.0 - 1j, A, h.AVector.from_array(x), y)
+    assert _rel(y.v, 1.0 + (2.0 - 1j) * (a @ x)) < 1e-13
+    LU = h.clone_amatrix(A)
+    assert h.lrdecomp_amatrix(LU) == 0
+    for _ in range(3):                                             # same factors, no re-upload
+        b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        v = h.AVector.from_array(b.copy())
+        h.lrsolve_amatrix_avector(False, LU, v)
+        assert _rel(a @ v.v, b) < 1e-11
+    v = h.AVector.from_array(b.copy())
+    h.lrsolve_amatrix_avector(True, LU, v)                         # adjoint system
+    assert _rel(a.conj().T @ v.v, b) < 1e-11
+    assert h.norm2diff_lr_amatrix(A, LU) < 1e-10 * np.linalg.norm(a, 2)
+    LU.a[0, 0] += 1.0                                              # host copy rewritten: the cached factors are stale
+    v = h.AVector.from_array(b.copy())
+    h.lrsolve_amatrix_avector(False, LU, v)
+    assert _rel(a @ v.v, b) > 1e-6
+    # triangular solves with the factors of a fresh factorisation
+    LU = h.clone_amatrix(A)
+    h.lrdecomp_amatrix(LU)
+    lu = np.array(LU.a).T
+    Lm, Um = np.tril(lu, -1) + np.eye(n), np.triu(lu)
+    for lower, unit, trans, M in [(True, True, False, Lm), (False, False, False, Um), (True, True, True, Lm.conj().T),
+                                  (False, False, True, Um.conj().T)]:
+        v = h.AVector.from_array(b.copy())
+        h.triangularsolve_amatrix_avector(lower, unit, trans, LU, v)
+        assert _rel(M @ v.v, b) < 1e-10
+    # Hermitian positive definite: Cholesky, CG
+    hp = a.conj().T @ a
+    Hm = h.AMatrix.from_array(np.ascontiguousarray(hp.T))
+    CH = h.clone_amatrix(Hm)
+    assert h.choldecomp_amatrix(CH) == 0
+    lc = np.tril(np.array(CH.a).T)
+    assert _rel(lc @ lc.conj().T, hp) < 1e-12
+    v = h.AVector.from_array(b.copy())
+    h.cholsolve_amatrix_avector(CH, v)
+    assert _rel(hp @ v.v, b) < 1e-9
+    bad = h.AMatrix.from_array(np.ascontiguousarray((hp - 2 * np.linalg.eigvalsh(hp)[5] * np.eye(n)).T))
+    assert h.choldecomp_amatrix(bad) != 0                          # indefinite: reports the failing pivot
+    w = h.AVector(n)
+    w.v[:] = 0
+    assert 0 < h.solve_cg_amatrix_avector(Hm, h.AVector.from_array(b.copy()), w, 1e-12, 2000) < 2000
+    assert _rel(hp @ w.v, b) < 1e-9
+    w.v[:] = 0
+    assert h.solve_gmres_amatrix_avector(A, h.AVector.from_array(b.copy()), w, 1e-11, 500, 50) < 500
+    assert _rel(a @ w.v, b) < 1e-9
+    Bm = h.AMatrix.from_array(np.ascontiguousarray((a + 0.01 * rng.standard_normal((n, n))).T))
+    est = h.norm2diff_lr_amatrix(Bm, LU)
+    exact = np.linalg.norm(np.array(Bm.a).T - a, 2)
+    assert 0.7 * exact < est <= exact * (1 + 1e-9)
