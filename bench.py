@@ -13,8 +13,11 @@ frequencies taken from the 2000-point grid in [0.025, 50] MHz.
   python bench.py [--gpus N] [--steps K] [--warmup W]         this repo's CUDA path
   python bench.py --impl reference ...                        CPU arm: the oracle port of the
                                                               reference's H2Lib path on host cores
-Multi-GPU (torchrun, one rank per GPU): frequencies are sharded, no collective inside a
-frequency ("weak" scaling: per-GPU batch fixed); setup broadcast once, results gathered.
+Multi-GPU (torchrun as the launcher, one rank per GPU): frequencies are sharded, no collective inside a
+frequency ("weak" scaling: per-GPU batch fixed); setup broadcast once, patch responses gathered, both with
+NCCL through the library's own C ABI (cnld_b200_comm_*, no torch.distributed).
+  --config c4   16x16 array, ACA H-matrix + GMRES (BASELINE.json configs[3])
+  --config c5   field pressure on 10^6 observation points (configs[4])
 """
 import argparse
 import ctypes as C
@@ -243,18 +246,16 @@ def bench_c5_reference(args, rank):
 
 def bench_c5(args, rank, world, local):
     import torch
-    import torch.distributed as dist
     from cnld import _lib, arrays
     from cnld.sweep import FrequencySweep, SweepSetup, broadcast_setup
     if _lib.device_count() == 0:
         raise SystemExit('bench.py: no CUDA device -- libcnld_b200 has no CPU fallback')
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    comm = _lib.Comm(rank, world, local)
     nelem, refn = CONFIGS['c5'][:2]
     setup = SweepSetup.from_abstract(arrays.matrix_array(nelem=nelem), refn) if rank == 0 else None
     if world > 1:
-        setup = broadcast_setup(setup, rank, torch.device('cuda', local))
+        setup = broadcast_setup(setup, rank, comm=comm)
     N, P, T = setup.nnodes, setup.npatch, len(setup.triangles)
     obs = obs_grid()
     nobs = len(obs)
@@ -268,15 +269,11 @@ def bench_c5(args, rank, world, local):
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        comm.barrier()
         torch.cuda.synchronize()
 
     def reduce_max(x):
-        t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return comm.max(x)
 
     # ---- device-resident: points and displacements in HBM, results stay in HBM ----------------------
     pf.run(ks[0], disp[0], setup.c, setup.rho, fetch=False)
@@ -361,8 +358,7 @@ def bench_c5(args, rank, world, local):
         print(json.dumps(line), flush=True)
     pf.close()
     sweep.close()
-    if world > 1:
-        dist.destroy_process_group()
+    comm.close()
 
 
 C4_METRIC = 'frequencies solved/s (ACA H-matrix assemble + GMRES, all 2304 source patches), 16x16 CMUT array'
@@ -435,19 +431,17 @@ def bench_c4(args, rank, world, local):
     """configs[3]: 16x16 array (N = 194 816, P = 2 304), one frequency per step through the ACA H-matrix +
     batched GMRES path; frequencies spread over [0.1, 50] MHz, dealt cyclically to the ranks."""
     import torch
-    import torch.distributed as dist
     from cnld import _lib, arrays
     from cnld.sweep import SweepSetup, broadcast_setup
     if _lib.device_count() == 0:
         raise SystemExit('bench.py: no CUDA device -- libcnld_b200 has no CPU fallback')
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    comm = _lib.Comm(rank, world, local)
     nelem, refn = CONFIGS['c4'][:2]
     t_setup = time.perf_counter()
     setup = SweepSetup.from_abstract(arrays.matrix_array(nelem=nelem), refn) if rank == 0 else None
     if world > 1:
-        setup = broadcast_setup(setup, rank, torch.device('cuda', local))
+        setup = broadcast_setup(setup, rank, comm=comm)
     ctx = _lib.Context(setup.vertices, setup.triangles, q_reg=setup.q_reg, q_sing=setup.q_sing, device=local)
     ctx.set_mbk(setup.K, setup.M, setup.B)
     ctx.set_loads(setup.F, setup.AVG, setup.on_boundary)
@@ -461,15 +455,11 @@ def bench_c4(args, rank, world, local):
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        comm.barrier()
         torch.cuda.synchronize()
 
     def reduce_max(x):
-        t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return comm.max(x)
 
     for w in range(args.warmup):
         H.sweep(mine[w:w + 1], c=setup.c, rho=setup.rho, want_nodes=False, **C4_SOLVE)
@@ -497,6 +487,7 @@ def bench_c4(args, rank, world, local):
     for s_ in range(args.steps):
         f = mine[nsteps + s_:nsteps + s_ + 1]
         xp, _, it2, _ = H.sweep(f, c=setup.c, rho=setup.rho, want_nodes=False, **C4_SOLVE)
+        comm.gather(xp)                     # patch responses to rank 0 (NCCL, NVLink)
     barrier()
     dte = reduce_max(time.perf_counter() - t0)
     e2e = args.steps * world / dte
@@ -554,8 +545,7 @@ def bench_c4(args, rank, world, local):
         print(json.dumps(line), flush=True)
     H.close()
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    comm.close()
     if line is not None and not line['parity']['matvec_sampled_rows_rel_err_vs_exact'] < C4_SOLVE['eps_aca']:
         raise SystemExit('bench.py: c4 H-matvec differs from exactly integrated rows by more than eps_aca')
 
@@ -603,21 +593,20 @@ def main():
         return bench_c4(args, rank, world, local)
 
     import torch
-    import torch.distributed as dist
     from cnld import _lib, arrays
     from cnld.sweep import FrequencySweep, SweepSetup, broadcast_setup
 
     if _lib.device_count() == 0:
         raise SystemExit('bench.py: no CUDA device -- libcnld_b200 has no CPU fallback')
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    # multi-GPU plumbing: NCCL through the library's own C ABI (cnld_b200_comm_*); torchrun is only the launcher
+    comm = _lib.Comm(rank, world, local)
 
     nelem, refn = CONFIGS[args.config][:2]
     t_setup = time.perf_counter()
     setup = SweepSetup.from_abstract(arrays.matrix_array(nelem=nelem), refn) if rank == 0 else None
     if world > 1:
-        setup = broadcast_setup(setup, rank, torch.device('cuda', local))
+        setup = broadcast_setup(setup, rank, comm=comm)
     if args.lu_outer:
         _lib.lib().cnld_b200_set_lu_outer(args.lu_outer)
     if args.lu_reserve >= 0:
@@ -629,8 +618,7 @@ def main():
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        comm.barrier()
         torch.cuda.synchronize()
 
     def batch(step):
@@ -666,10 +654,7 @@ def main():
     step_flops = _lib.dmma_flop_count() - fl0      # executed DMMA flops of this rank's timed steps
     step_tflops = step_flops / dev_s / 1e12
     clocks = sampler.finish() if rank == 0 else None
-    tt = torch.tensor([dt], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dt = float(tt.item())
+    dt = comm.max(dt)
     value = args.steps * nfb * world / dt
 
     # ---- end to end through the public API (host buffers in, host buffers out) -------------
@@ -683,13 +668,12 @@ def main():
         h2d = sweep.upload() + 8 * nfb
         xp, xn, _ = sweep.run(batch(args.warmup + s), want_nodes=True, out_nodes=out_nodes)
         d2h = xp.nbytes + xn.nbytes
+        gathered = comm.gather(xp)          # the sweep's one exchange: patch responses to rank 0 (NCCL, NVLink)
     barrier()
-    dte = time.perf_counter() - t0
-    tt = torch.tensor([dte], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dte = float(tt.item())
+    dte = comm.max(time.perf_counter() - t0)
     e2e = args.steps * nfb * world / dte
+    if rank == 0:
+        assert gathered.shape == (world,) + xp.shape and np.isfinite(gathered).all()
     assert np.isfinite(xp).all() and np.abs(xp).max() > 0
 
     sym_stats = sweep.ctx.symmetric_stats()
@@ -723,7 +707,9 @@ def main():
                        'symmetric_stats': sym_stats,
                        'frequencies_per_step_per_gpu': nfb, 'streams': args.streams, 'parallelism': f'freq-shard x{world}',
                        'cache': 'per-frequency working set 3.5 GB >> 126 MB L2 (inputs larger than L2)',
-                       'setup_seconds_once': t_setup},
+                       'setup_seconds_once': t_setup,
+                       'comm': dict(comm.stats(), backend='NCCL via cnld_b200_comm_* (C ABI); setup broadcast once, '
+                                                          'patch responses gathered to rank 0 every e2e step')},
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'gpu_launches': int(launches), 'wall_seconds_timed_region': wall,
             'clocks': clocks,
@@ -787,8 +773,7 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     sweep.close()
-    if world > 1:
-        dist.destroy_process_group()
+    comm.close()
     if parity_fail:
         raise SystemExit('bench.py: GPU result differs from the oracle by more than 1e-6 at this config')
 

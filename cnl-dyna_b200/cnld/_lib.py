@@ -77,6 +77,16 @@ def lib():
         L.cnld_b200_pfield_fetch.argtypes = [vp, u32, vp, u32, vp]
         L.cnld_b200_pfield_info.argtypes = [vp, vp]
         L.cnld_b200_pres_plan_stats.argtypes = [u32, u32, vp, vp, vp, vp]
+        L.cnld_b200_comm_create.restype = vp
+        L.cnld_b200_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        L.cnld_b200_comm_destroy.argtypes = [vp]
+        L.cnld_b200_comm_rank.argtypes = [vp]
+        L.cnld_b200_comm_world.argtypes = [vp]
+        L.cnld_b200_comm_bcast.argtypes = [vp, vp, C.c_size_t, C.c_int]
+        L.cnld_b200_comm_gather.argtypes = [vp, vp, C.c_size_t, vp, C.c_int]
+        L.cnld_b200_comm_allreduce_max.argtypes = [vp, vp, C.c_int]
+        L.cnld_b200_comm_barrier.argtypes = [vp]
+        L.cnld_b200_comm_stats.argtypes = [vp, vp]
         L.cnld_b200_db_append_block.argtypes = [C.c_char_p, u32, vp, vp, u32, vp, vp, u32, vp, vp, vp, C.c_int]
         L.cnld_b200_db_begin_bulk.argtypes = [C.c_char_p]
         L.cnld_b200_db_finish.argtypes = [C.c_char_p]
@@ -358,6 +368,68 @@ def pres_plan_stats(vertices, triangles):
     check(lib().cnld_b200_pres_plan_stats(len(x), len(t), ptr(x), ptr(t), ptr(counts), ptr(order)))
     keys = ('chunks', 'node_entries', 'max_triangles', 'max_nodes', 'accumulating_entries', 'untouched_vertices')
     return dict(zip(keys, (int(v) for v in counts))), order
+
+
+class Comm:
+    """One rank of the sweep's communicator (opaque cnld_comm): NCCL over NVLink through the C ABI, no
+    torch.distributed.  Rank / world / rendezvous default to the launcher's environment (torchrun: RANK,
+    WORLD_SIZE, LOCAL_RANK, MASTER_ADDR, MASTER_PORT; the id exchange uses CNLD_B200_COMM_PORT or
+    MASTER_PORT + 17)."""
+
+    def __init__(self, rank=None, world=None, device=None, addr=None, port=None):
+        env = os.environ
+        self.rank = int(env.get('RANK', 0)) if rank is None else int(rank)
+        self.world = int(env.get('WORLD_SIZE', 1)) if world is None else int(world)
+        self.device = int(env.get('LOCAL_RANK', 0)) if device is None else int(device)
+        addr = addr or env.get('MASTER_ADDR', '127.0.0.1')
+        port = int(port or env.get('CNLD_B200_COMM_PORT', 0) or int(env.get('MASTER_PORT', 29500)) + 17)
+        self._h = lib().cnld_b200_comm_create(self.rank, self.world, self.device, addr.encode(), port)
+        if not self._h:
+            raise Cnldb200Error(lib().cnld_b200_last_error().decode())
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().cnld_b200_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def bcast(self, arr, root=0):
+        """In place: every rank's `arr` (same shape / dtype, C-contiguous) becomes root's."""
+        assert arr.flags.c_contiguous
+        check(lib().cnld_b200_comm_bcast(self._h, ptr(arr), arr.nbytes, root))
+        return arr
+
+    def bcast_object(self, obj, root=0):
+        """Small Python object (pickled) from root to every rank."""
+        import pickle
+        payload = np.frombuffer(pickle.dumps(obj), dtype=np.uint8).copy() if self.rank == root else None
+        n = np.array([len(payload) if payload is not None else 0], dtype=np.int64)
+        self.bcast(n, root)
+        if payload is None:
+            payload = np.empty(int(n[0]), dtype=np.uint8)
+        self.bcast(payload, root)
+        return pickle.loads(payload.tobytes())
+
+    def gather(self, arr, root=0):
+        """Equal-shaped arrays of all ranks stacked along a new first axis on root; None elsewhere."""
+        arr = np.ascontiguousarray(arr)
+        out = np.empty((self.world,) + arr.shape, dtype=arr.dtype) if self.rank == root else None
+        check(lib().cnld_b200_comm_gather(self._h, ptr(arr), arr.nbytes, ptr(out), root))
+        return out
+
+    def max(self, *vals):
+        v = np.array(vals, dtype=np.float64)
+        check(lib().cnld_b200_comm_allreduce_max(self._h, ptr(v), len(v)))
+        return v.tolist() if len(v) != 1 else float(v[0])
+
+    def barrier(self):
+        check(lib().cnld_b200_comm_barrier(self._h))
+
+    def stats(self):
+        out = np.zeros(3)
+        check(lib().cnld_b200_comm_stats(self._h, ptr(out)))
+        return dict(nccl_bytes=float(out[0]), nccl_seconds=float(out[1]), nccl_version=int(out[2]))
 
 
 def db_append_block(file, freqs, wavenums, x_patch, x_node=None, nodes=None, times=None, job_ids=None, fast=True):

@@ -220,9 +220,10 @@ def _run_workers(cfg, setup, freqs, todo, dev_ids, block, store_nodes, nstreams,
                 if any(p.exitcode not in (None, 0) for p in procs):
                     raise RuntimeError('a generate_db worker process died')
                 continue
-            if item[0] == 'done':
+            tag = item[0] if isinstance(item[0], str) else None
+            if tag == 'done':
                 alive -= 1
-            elif item[0] == 'error':
+            elif tag == 'error':
                 raise RuntimeError(f'generate_db worker {item[1]} failed: {item[2]}')
             else:
                 if failure:

@@ -117,26 +117,65 @@ def shard(n, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def broadcast_setup(setup, rank, device=None):
-    """Rank 0's SweepSetup to every rank through torch.distributed (NCCL over NVLink on GPUs,
-    gloo on CPU).  One collective per array, once per sweep."""
-    import torch
-    import torch.distributed as dist
-    dev = device if device is not None else 'cpu'
+class TorchComm:
+    """The communicator interface of `_lib.Comm` (bcast / bcast_object / gather / max / barrier) on top of an
+    initialised torch.distributed process group -- what the CPU tests use (gloo, world_size 2); on GPUs the
+    sweep uses `_lib.Comm` (NCCL through the C ABI, no torch)."""
+
+    def __init__(self, device=None):
+        import torch.distributed as dist
+        self.dist, self.device = dist, device if device is not None else 'cpu'
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def bcast(self, arr, root=0):
+        import torch
+        t = torch.from_numpy(arr.view(np.uint8).reshape(-1)).to(self.device)
+        self.dist.broadcast(t, src=root)
+        if self.rank != root:
+            arr.view(np.uint8).reshape(-1)[:] = t.cpu().numpy()
+        return arr
+
+    def bcast_object(self, obj, root=0):
+        box = [obj if self.rank == root else None]
+        self.dist.broadcast_object_list(box, src=root)
+        return box[0]
+
+    def gather(self, arr, root=0):
+        import torch
+        mine = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()).to(self.device)
+        parts = [torch.empty_like(mine) for _ in range(self.world)] if self.rank == root else None
+        self.dist.gather(mine, parts, dst=root)
+        if self.rank != root:
+            return None
+        return np.stack([p.cpu().numpy().view(arr.dtype).reshape(arr.shape) for p in parts])
+
+    def max(self, *vals):
+        import torch
+        t = torch.tensor(vals, dtype=torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist() if len(vals) != 1 else float(t[0])
+
+    def barrier(self):
+        self.dist.barrier()
+
+
+def _as_comm(comm, device=None):
+    return comm if comm is not None else TorchComm(device)
+
+
+def broadcast_setup(setup, rank, device=None, comm=None):
+    """Rank 0's SweepSetup to every rank: one collective per array, once per sweep.  `comm` is a
+    `_lib.Comm` (NCCL over NVLink through the C ABI) or None for the torch.distributed adapter (gloo on
+    CPU, nccl on GPUs) bound to `device`."""
+    comm = _as_comm(comm, device)
     names = ['vertices', 'triangles', 'on_boundary', 'scalars'] + [
         f'{m}_{p}' for m in ('K', 'M', 'B', 'F', 'AVG') for p in ('indptr', 'indices', 'data')]
     packed = setup.pack() if rank == 0 else None
-    meta = [[(k, packed[k].shape, str(packed[k].dtype)) for k in names]] if rank == 0 else [None]
-    dist.broadcast_object_list(meta, src=0)
+    meta = comm.bcast_object([(k, packed[k].shape, str(packed[k].dtype)) for k in names] if rank == 0 else None)
     out = {}
-    for k, shape, dtype in meta[0]:
-        if rank == 0:
-            t = torch.from_numpy(np.ascontiguousarray(packed[k]).view(np.uint8).reshape(-1).copy()).to(dev)
-        else:
-            nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-            t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        dist.broadcast(t, src=0)
-        out[k] = t.cpu().numpy().view(np.dtype(dtype)).reshape(shape)
+    for k, shape, dtype in meta:
+        a = np.ascontiguousarray(packed[k]) if rank == 0 else np.empty(shape, dtype=np.dtype(dtype))
+        out[k] = comm.bcast(a)
     return SweepSetup.unpack(out)
 
 
@@ -148,17 +187,18 @@ def shard_cyclic(n, rank, world):
 
 
 def run_distributed(setup_or_none, freqs, rank, world, device=0, torch_device=None, nstreams=3,
-                    solver=None, symmetric=True, method='dense', hmatrix=None, distribution=None):
+                    solver=None, symmetric=True, method='dense', hmatrix=None, distribution=None, comm=None):
     """Distributed sweep: returns (x_patch[nf, P, P] on rank 0 else None, local seconds).
     method 'dense' (LU, default) or 'hmatrix' (ACA H-matrix + GMRES, `hmatrix` = keyword arguments
     of _lib.HMatrix / HMatrix.sweep).  distribution 'block' (default for dense) or 'cyclic' (default
     for hmatrix).  No collective inside a frequency: one broadcast of the setup, one gather of the
     patch responses.  `solver(setup, freqs) -> x_patch[nf_local, P, P]` replaces the GPU sweep; the
-    tests inject a CPU stand-in to exercise the sharding / broadcast / gather logic under gloo."""
-    import torch
-    import torch.distributed as dist
+    tests inject a CPU stand-in to exercise the sharding / broadcast / gather logic under gloo.
+    `comm`: `_lib.Comm` (NCCL through the C ABI) or None = torch.distributed adapter on `torch_device`."""
     freqs = np.asarray(freqs, dtype=np.float64)
-    setup = broadcast_setup(setup_or_none, rank, torch_device) if world > 1 else setup_or_none
+    if world > 1:
+        comm = _as_comm(comm, torch_device)
+    setup = broadcast_setup(setup_or_none, rank, comm=comm) if world > 1 else setup_or_none
     distribution = distribution or ('cyclic' if method == 'hmatrix' else 'block')
     if distribution == 'cyclic':
         owned = [shard_cyclic(len(freqs), r, world) for r in range(world)]
@@ -189,13 +229,10 @@ def run_distributed(setup_or_none, freqs, rank, world, device=0, torch_device=No
     nmax = max(len(o) for o in owned)
     buf = np.zeros((nmax, P, P), dtype=np.complex128)
     buf[:len(mine_idx)] = xp
-    dev = torch_device if torch_device is not None else 'cpu'
-    mine = torch.from_numpy(buf.view(np.float64)).to(dev)
-    gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-    dist.gather(mine, gathered, dst=0)
+    gathered = comm.gather(buf)            # the one exchange of the sweep: patch responses to rank 0
     if rank != 0:
         return None, t
     out = np.empty((len(freqs), P, P), dtype=np.complex128)
     for g, o in zip(gathered, owned):
-        out[o] = g.cpu().numpy().view(np.complex128)[:len(o)]
+        out[o] = g[:len(o)]
     return out, t

@@ -266,6 +266,28 @@ int cnld_b200_hsweep_run(cnld_ctx *ctx, cnld_hmat *h, const double *freqs, cnld_
                          cnld_uint maxiter, cnld_uint batch, cnld_field *x_patch,
                          cnld_field *x_node, cnld_uint *iters, double *t_freq);
 
+/* ---- multi-GPU plumbing (one process per GPU) ------------------------------------------------------------
+ * Replaces the reference's process pool + write lock (cnld/scripts/generate_db.py:229-242): frequencies are
+ * sharded over ranks, nothing is exchanged inside a frequency; rank 0's frequency-independent setup is
+ * broadcast once and the patch responses are gathered once, with NCCL over NVLink (libnccl.so.2 loaded at
+ * run time, no PyTorch).  rank / world / addr / port come from the launcher (torchrun exports RANK,
+ * WORLD_SIZE, LOCAL_RANK, MASTER_ADDR, MASTER_PORT; the port must be free on rank 0's host -- it carries the
+ * NCCL unique id, one TCP connection per rank).  world = 1 needs neither NCCL nor a GPU: every call is a no-op.
+ * All buffers are HOST buffers. */
+typedef struct cnld_comm cnld_comm;
+cnld_comm *cnld_b200_comm_create(int rank, int world, int device, const char *addr, int port);
+void cnld_b200_comm_destroy(cnld_comm *comm);
+int cnld_b200_comm_rank(const cnld_comm *comm);
+int cnld_b200_comm_world(const cnld_comm *comm);
+int cnld_b200_comm_bcast(cnld_comm *comm, void *buf, size_t bytes, int root);
+/* every rank contributes `bytes` bytes; root receives world * bytes in rank order (recv may be NULL elsewhere) */
+int cnld_b200_comm_gather(cnld_comm *comm, const void *send, size_t bytes, void *recv, int root);
+/* element-wise maximum over the ranks, in place (timing: max over ranks); n = 0 is a barrier */
+int cnld_b200_comm_allreduce_max(cnld_comm *comm, double *vals, int n);
+int cnld_b200_comm_barrier(cnld_comm *comm);
+/* out[3]: payload bytes this rank moved through NCCL, device seconds of those collectives, NCCL version */
+int cnld_b200_comm_stats(cnld_comm *comm, double *out);
+
 /* ---- database writer ---------------------------------------------------
  * Bulk appends to cnl-dyna's sqlite database (cnld/database.py:22-92 schema, :144-194 append_*;
  * cnld/scripts/generate_db.py:101-130 writes the same rows one source patch at a time through Python):
