@@ -26,6 +26,9 @@ class SweepSetup:
         self.on_boundary = np.ascontiguousarray(on_boundary, dtype=np.uint8)
         self.K, self.M, self.B = (sps.csr_matrix(a) for a in (K, M, B))
         self.F, self.AVG = sps.csc_matrix(F), sps.csc_matrix(AVG)
+        for m in (self.K, self.M, self.B, self.F, self.AVG):
+            m.eliminate_zeros()       # block_diag of dense membrane blocks stores every zero: 16 x 925^2 entries at C3
+            m.sort_indices()
         self.c, self.rho, self.q_reg, self.q_sing = float(c), float(rho), int(q_reg), int(q_sing)
 
     @classmethod
