@@ -77,6 +77,15 @@ def lib():
         L.cnld_b200_pfield_fetch.argtypes = [vp, u32, vp, u32, vp]
         L.cnld_b200_pfield_info.argtypes = [vp, vp]
         L.cnld_b200_pres_plan_stats.argtypes = [u32, u32, vp, vp, vp, vp]
+        L.cnld_b200_fir_create.restype = vp
+        L.cnld_b200_fir_create.argtypes = [C.c_int, u32, u32, u32, vp]
+        L.cnld_b200_fir_destroy.argtypes = [vp]
+        L.cnld_b200_fir_conv.argtypes = [vp, vp, u32, f64, C.c_int, vp]
+        L.cnld_b200_fir_reset.argtypes = [vp]
+        L.cnld_b200_fir_push.argtypes = [vp, vp]
+        L.cnld_b200_fir_base.argtypes = [vp, f64, vp]
+        L.cnld_b200_fir_add.argtypes = [vp, vp, f64, vp]
+        L.cnld_b200_fft_to_fir.argtypes = [C.c_int, u32, vp, u32, vp, u32, C.c_int, vp, vp]
         L.cnld_b200_comm_create.restype = vp
         L.cnld_b200_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
         L.cnld_b200_comm_destroy.argtypes = [vp]
@@ -368,6 +377,63 @@ def pres_plan_stats(vertices, triangles):
     check(lib().cnld_b200_pres_plan_stats(len(x), len(t), ptr(x), ptr(t), ptr(counts), ptr(order)))
     keys = ('chunks', 'node_entries', 'max_triangles', 'max_nodes', 'accumulating_entries', 'untouched_vertices')
     return dict(zip(keys, (int(v) for v in counts))), order
+
+
+class FirTable:
+    """Patch-to-patch impulse responses fir[nsrc, ndest, nfir] resident on one GPU (opaque cnld_fir): the
+    convolution of the time-domain solver (simulation.pyx:51-77 fir_conv_cy, :400-410)."""
+
+    def __init__(self, fir, device=0):
+        fir = _c(fir, np.float64)
+        assert fir.ndim == 3
+        self.nsrc, self.ndest, self.nfir = fir.shape
+        self._h = lib().cnld_b200_fir_create(device, self.nsrc, self.ndest, self.nfir, ptr(fir))
+        if not self._h:
+            raise Cnldb200Error(lib().cnld_b200_last_error().decode())
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().cnld_b200_fir_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def conv(self, p, dt, offset):
+        """fir_conv_cy(fir, p, dt, offset) for p[nsample, nsrc] -> x[ndest]."""
+        p = _c(np.asarray(p).reshape(-1, self.nsrc), np.float64)
+        x = np.empty(self.ndest)
+        check(lib().cnld_b200_fir_conv(self._h, ptr(p), len(p), float(dt), int(offset), ptr(x)))
+        return x
+
+    def reset(self):
+        check(lib().cnld_b200_fir_reset(self._h))
+
+    def push(self, p_row):
+        check(lib().cnld_b200_fir_push(self._h, ptr(_c(p_row, np.float64))))
+
+    def base(self, dt):
+        x = np.empty(self.ndest)
+        check(lib().cnld_b200_fir_base(self._h, float(dt), ptr(x)))
+        return x
+
+    def add(self, p_row, dt):
+        x = np.empty(self.ndest)
+        check(lib().cnld_b200_fir_add(self._h, ptr(_c(p_row, np.float64)), float(dt), ptr(x)))
+        return x
+
+
+def fft_to_fir(freqs, s, interp=1, use_kkr=True, device=0):
+    """One-sided spectra s[..., nf] -> (t[nfft], h[..., nfft]) on the GPU (impulse_response.py:191-224)."""
+    freqs = _c(freqs, np.float64)
+    s = np.asarray(s, dtype=np.complex128)
+    lead = s.shape[:-1]
+    flat = _c(s.reshape(-1, s.shape[-1]), np.complex128)
+    nfft = 2 * ((len(freqs) - 1) * int(interp) + 1) - 1
+    t = np.empty(nfft)
+    h = np.empty((flat.shape[0], nfft))
+    check(lib().cnld_b200_fft_to_fir(device, len(freqs), ptr(freqs), flat.shape[0], ptr(flat), int(interp), int(bool(use_kkr)),
+                                     ptr(t), ptr(h)))
+    return t, h.reshape(lead + (nfft,))
 
 
 class Comm:

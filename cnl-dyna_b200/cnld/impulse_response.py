@@ -1,8 +1,10 @@
 """
 cnld.impulse_response -- frequency response -> impulse response (mirror of
 /root/reference/cnld/impulse_response.py: interp_fft :161-175, one_to_two :11-46,
-kramers_kronig2 :115-125, fft_to_fir :191-206, fft_to_sir :209-224).  Host-side numpy: the stage
-is O(P^2 nfft log nfft) on a few MB and sits after the device sweep.
+kramers_kronig2 :115-125, fft_to_fir :191-206, fft_to_sir :209-224).  Two engines with the same
+results: 'device' = libcnld_b200 (cnld_b200_fft_to_fir: interpolation kernel + one exactly-twiddled DFT
+GEMM on the FP64 tensor cores, used by generate_db.postprocess and the field-pressure path whenever a GPU
+is present) and 'host' = the numpy / scipy.fft restatement of the reference's own module below.
 """
 import numpy as np
 from scipy.fft import fftfreq, ifft
@@ -57,11 +59,28 @@ def _to_time(f, s, interp, use_kkr, axis):
     return np.arange(nfft) / fs, np.real(ifft(s2s, axis=axis)) * fs
 
 
-def fft_to_fir(f, s, interp=1, use_kkr=True, axis=-1):
+def _engine(engine):
+    if engine in ('host', 'device'):
+        return engine
+    from . import _lib
+    return 'device' if _lib.device_count() > 0 else 'host'
+
+
+def _device_to_time(f, s, interp, use_kkr, axis, device):
+    from . import _lib
+    t, h = _lib.fft_to_fir(f, np.moveaxis(np.asarray(s), axis, -1), interp=interp, use_kkr=use_kkr, device=device)
+    return t, np.moveaxis(h, -1, axis)
+
+
+def fft_to_fir(f, s, interp=1, use_kkr=True, axis=-1, engine=None, device=0):
     """One-sided FFT -> impulse response of a causal LTI system."""
+    if _engine(engine) == 'device':
+        return _device_to_time(f, s, interp, use_kkr, axis, device)
     return _to_time(f, s, interp, use_kkr, axis)
 
 
-def fft_to_sir(f, s, interp=1, use_kkr=False, axis=-1):
+def fft_to_sir(f, s, interp=1, use_kkr=False, axis=-1, engine=None, device=0):
     """One-sided FFT -> spatial impulse response."""
+    if _engine(engine) == 'device':
+        return _device_to_time(f, s, interp, use_kkr, axis, device)
     return _to_time(f, s, interp, use_kkr, axis)

@@ -266,6 +266,31 @@ int cnld_b200_hsweep_run(cnld_ctx *ctx, cnld_hmat *h, const double *freqs, cnld_
                          cnld_uint maxiter, cnld_uint batch, cnld_field *x_patch,
                          cnld_field *x_node, cnld_uint *iters, double *t_freq);
 
+/* ---- impulse responses -------------------------------------------------
+ * impulse_response.fft_to_fir / fft_to_sir (cnld/impulse_response.py:191-224) for nbatch one-sided spectra
+ * s[nbatch][nf] on the frequency grid freqs[nf]: magnitude / unwrapped-phase interpolation by `interp`
+ * (:161-175), conjugate mirror to nfft = 2 ((nf - 1) interp + 1) - 1 bins (:11-46), optional Kramers-Kronig
+ * reconstruction (:115-125), real(ifft) * fs.  Outputs t[nfft] (nullable) and h[nbatch][nfft] (HOST).
+ * Evaluated as one exactly-twiddled DFT GEMM on the FP64 tensor cores (csrc/impresp.cu). */
+int cnld_b200_fft_to_fir(int device, cnld_uint nf, const double *freqs, cnld_uint nbatch, const cnld_field *s,
+                         cnld_uint interp, int use_kkr, double *t, double *h);
+
+/* ---- time-domain FIR convolution ----------------------------------------------
+ * fir_conv_cy (cnld/simulation.pyx:51-77): x[j] = dt * sum_i sum_k fir[i][j][k + offset] p[nsample-1-k][i],
+ * the convolution of FixedStepSolver (:400-410, :459-503).  The table fir[nsrc][ndest][nfir] stays on the
+ * device; every convolution streams it once (HBM-bound). */
+typedef struct cnld_fir cnld_fir;
+cnld_fir *cnld_b200_fir_create(int device, cnld_uint nsrc, cnld_uint ndest, cnld_uint nfir, const double *fir);
+void cnld_b200_fir_destroy(cnld_fir *f);
+/* fir_conv_cy(fir, p, dt, offset): p[nsample][nsrc], x[ndest] (HOST) */
+int cnld_b200_fir_conv(cnld_fir *f, const double *p, cnld_uint nsample, double dt, int offset, double *x);
+/* resident stepping: push the finished step's pressures p_row[nsrc] into the device history; base = the
+ * history convolved with offset 1 (`_fir_conv_base`); add = the current sample with offset 0 (`_fir_conv_add`) */
+int cnld_b200_fir_reset(cnld_fir *f);
+int cnld_b200_fir_push(cnld_fir *f, const double *p_row);
+int cnld_b200_fir_base(cnld_fir *f, double dt, double *x);
+int cnld_b200_fir_add(cnld_fir *f, const double *p_row, double dt, double *x);
+
 /* ---- multi-GPU plumbing (one process per GPU) ------------------------------------------------------------
  * Replaces the reference's process pool + write lock (cnld/scripts/generate_db.py:229-242): frequencies are
  * sharded over ranks, nothing is exchanged inside a frequency; rank 0's frequency-independent setup is

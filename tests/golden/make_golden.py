@@ -225,9 +225,45 @@ def golden_pressure():
     print('pressure', pv.shape, np.abs(pv).max())
 
 
+def golden_fir_conv():
+    """cnld/simulation.pyx:51-77 fir_conv_cy (the convolution the time-domain solver calls every step,
+    :400-410): the function body is taken from the reference source and executed as plain Python after
+    stripping the C declarations; the loop arithmetic is untouched."""
+    import re
+    src = open(os.path.join(REF, 'cnld', 'simulation.pyx')).read()
+    m = re.search(r'cpdef np\.ndarray fir_conv_cy\(.*?\n    return np\.asarray\(x\)\n', src, flags=re.S)
+    body = m.group(0)
+    body = re.sub(r'cpdef np\.ndarray fir_conv_cy\([^)]*\):', 'def fir_conv_cy(fir, p, dt, offset):', body, flags=re.S)
+    body = body.replace('    cdef int nsrc = fir.shape[0]', '    nsrc = fir.shape[0]').replace(
+        '    cdef int ndest = fir.shape[1]', '    ndest = fir.shape[1]').replace(
+        '    cdef int nfir = fir.shape[2]', '    nfir = fir.shape[2]').replace(
+        '    cdef int nsample = p.shape[0]', '    nsample = p.shape[0]').replace(
+        '    cdef double[:] x = np.zeros(ndest, dtype=np.float64)', '    x = np.zeros(ndest, dtype=np.float64)')
+    body = re.sub(r'^\s*cdef .*\n', '', body, flags=re.M)
+    ns = {'np': np}
+    exec(compile(body, 'simulation.pyx:fir_conv_cy', 'exec'), ns)
+    rng = np.random.default_rng(7)
+    out = {}
+    cases = [(3, 4, 16, 5, 0), (3, 4, 16, 5, 1), (3, 4, 16, 16, 1), (3, 4, 16, 40, 1), (3, 4, 16, 1, 0), (5, 2, 9, 9, 0),
+             (2, 2, 8, 30, 0)]
+    for c, (nsrc, ndest, nfir, nsample, offset) in enumerate(cases):
+        fir = rng.standard_normal((nsrc, ndest, nfir))
+        pp = rng.standard_normal((nsample, nsrc))
+        out[f'fir{c}'], out[f'p{c}'] = fir, pp
+        out[f'arg{c}'] = np.array([2.5e-9, offset])
+        out[f'x{c}'] = ns['fir_conv_cy'](fir, pp, 2.5e-9, offset)
+    out['ncases'] = np.array(len(cases))
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), 'fir_conv.npz'), **out)
+    print('fir_conv', len(cases), 'cases')
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'fir_conv':
+        golden_fir_conv()
+        sys.exit(0)
     golden_fem('1x1_r3', (1, 1), 3)
     golden_fem('2x1_r4', (2, 1), 4)
     golden_fem('1x1_r6', (1, 1), 6)
     golden_fir()
     golden_pressure()
+    golden_fir_conv()

@@ -45,6 +45,15 @@ def test_fir_matches_reference(po):
     assert _rel(h, g['sir_h']) < 1e-11
 
 
+def test_fir_conv_matches_reference(po):
+    """oracle fir_conv == the reference's fir_conv_cy loop (simulation.pyx:51-77) on the golden cases."""
+    g = np.load(os.path.join(GOLDEN, 'fir_conv.npz'))
+    for c in range(int(g['ncases'])):
+        dt, offset = g[f'arg{c}']
+        x = po.fir_conv(g[f'fir{c}'], g[f'p{c}'], dt, int(offset))
+        assert _rel(x, g[f'x{c}']) < 1e-13
+
+
 def test_pressure_matches_reference(po):
     g = np.load(os.path.join(GOLDEN, 'pressure.npz'))
     am = po.Mesh(g['vertices'], np.zeros((1, 2), np.uint32), g['triangles'],
