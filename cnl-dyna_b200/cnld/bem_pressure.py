@@ -65,6 +65,28 @@ def array_patch_pres_imp_resp(array, refn, db_file, r, c, rho, use_kkr=False, in
     return impulse_response.fft_to_sir(freqs, sfr, interp=interp, axis=1, use_kkr=use_kkr)
 
 
+def field_patch_pres_imp_resp(vertices, triangles, freqs, disp, points, c, rho, use_kkr=False, interp=2):
+    """array_patch_pres_imp_resp for MANY field points at once (BASELINE.json configs[4]): the spatial impulse
+    response of every patch at every point, sir[patch, point, nfft].  disp[freq, patch, node] are the node
+    displacements of the sweep; per frequency the whole field is one pass of the many-source pressure path
+    (observation points resident on the GPU), the spectra then go through the device impulse response."""
+    from . import _lib
+    ctx = _context(vertices, triangles)
+    freqs = np.asarray(freqs, dtype=np.float64)
+    disp = np.asarray(disp, dtype=np.complex128)
+    nf, P, _ = disp.shape
+    points = np.atleast_2d(np.asarray(points, dtype=np.float64))
+    pf = _lib.PressureField(ctx, points, P)
+    try:
+        sfr = np.empty((P, len(points), nf), dtype=np.complex128)
+        buf = np.empty((P, len(points)), dtype=np.complex128)
+        for i, f in enumerate(freqs):
+            sfr[:, :, i] = pf.run(2 * np.pi * f / c, disp[i], c, rho, out=buf)
+    finally:
+        pf.close()
+    return impulse_response.fft_to_sir(freqs, sfr, interp=interp, axis=-1, use_kkr=use_kkr)
+
+
 def press_resp(array, refn, db_file, pes, r, c, rho, use_kkr=False, interp=2):
     """Field pressure for patch pressures pes[:, patch] (bem_pressure.pyx:120-134)."""
     sir_t, sir = array_patch_pres_imp_resp(array, refn, db_file, r, c, rho, interp=interp, use_kkr=use_kkr)

@@ -416,30 +416,35 @@ void identity_hmatrix(phmatrix hm) {
   }
 }
 void copy_sparsematrix_hmatrix(psparsematrix sp, phmatrix hm) {
-  // entries that fall into dense leaves are copied; the (block-diagonal FEM) operators of cnl-dyna
-  // can also reach admissible leaves -- those are reported, not silently dropped
+  // Entries that fall into inadmissible leaves are copied into the dense blocks.  Entries inside an
+  // admissible leaf become an exact low-rank block: q entries v_t at (i_t, j_t) are the sum of q rank-one
+  // terms v_t e_i e_j^T, i.e. A = [e_i1 .. e_iq], B = [conj(v_1) e_j1 .. conj(v_q) e_jq]  (block = A B^*).
   clear_hmatrix(hm);
   std::vector<hmatrix *> L;
   collect(hm, L);
-  size_t placed = 0;
   for (hmatrix *l : L) {
-    if (!l->f) continue;
     std::unordered_map<uint, uint> cpos;
     for (uint j = 0; j < l->cc->size; j++) cpos[l->cc->idx[j]] = j;
+    std::vector<std::pair<std::pair<uint, uint>, field>> hits;   // admissible leaves: (local row, local col), value
     for (uint i = 0; i < l->rc->size; i++) {
       uint row = l->rc->idx[i];
       for (uint p = sp->row[row]; p < sp->row[row + 1]; p++) {
         auto it = cpos.find(sp->col[p]);
-        if (it != cpos.end()) { l->f->a[(size_t)it->second * l->f->ld + i] = sp->coeff[p]; placed++; }
+        if (it == cpos.end()) continue;
+        if (l->f) l->f->a[(size_t)it->second * l->f->ld + i] = sp->coeff[p];
+        else if (l->r && (sp->coeff[p].re != 0.0 || sp->coeff[p].im != 0.0)) hits.push_back({{i, it->second}, sp->coeff[p]});
+      }
+    }
+    if (l->r && !hits.empty()) {
+      resize_rk(l->r, (uint)hits.size());
+      for (size_t t = 0; t < hits.size(); t++) {
+        l->r->A.a[t * l->r->A.rows + hits[t].first.first] = mk(1.0, 0.0);
+        l->r->B.a[t * l->r->B.rows + hits[t].first.second] = mk(hits[t].second.re, -hits[t].second.im);
       }
     }
   }
-  size_t nzv = 0;
-  for (uint p = 0; p < sp->nz; p++) if (sp->coeff[p].re != 0.0 || sp->coeff[p].im != 0.0) nzv++;
-  if (placed < nzv)
-    fprintf(stderr, "libcnld_b200: copy_sparsematrix_hmatrix: %zu non-zero entries lie in admissible leaves and "
-                    "were not copied (keep the sparse operator separate: cnld.compressed_formats.HSumFormat)\n",
-            nzv - placed);
+  std::lock_guard<std::mutex> lk(g_mu);
+  invalidate(hm);
 }
 void add_hmatrix_amatrix(field alpha, bool atrans, pchmatrix a, pamatrix b) {
   std::vector<hmatrix *> L;

@@ -67,3 +67,26 @@ def test_fir_convolution_vs_reference_golden_and_oracle(po):
     # deterministic: the same call twice gives the same bits
     assert np.array_equal(tab.base(dt), tab.base(dt))
     tab.close()
+
+
+def test_field_spatial_impulse_responses_vs_reference_loop(po):
+    """configs[4] in small: SIR of every patch at many field points through the many-source pressure path +
+    device impulse response, against the reference's loop (bem_pressure.pyx:91-117: one point, one
+    frequency at a time) restated with the oracle's pressure vector and fft_to_sir."""
+    from cnld import arrays, bem_pressure
+    from cnld.sweep import FrequencySweep, SweepSetup
+    setup = SweepSetup.from_abstract(arrays.matrix_array(nelem=(2, 1)), 3)
+    sw = FrequencySweep(setup, nstreams=2)
+    freqs = np.arange(1e6, 12.1e6, 1e6)
+    _, xn, _ = sw.run(freqs)                                   # [freq, patch, node]
+    sw.close()
+    rng = np.random.default_rng(9)
+    pts = np.c_[rng.uniform(-3e-4, 3e-4, 7), rng.uniform(-3e-4, 3e-4, 7), rng.uniform(1e-4, 1e-3, 7)]
+    t, sir = bem_pressure.field_patch_pres_imp_resp(setup.vertices, setup.triangles, freqs, xn, pts, setup.c, setup.rho)
+    oarr = po.matrix_array(nelem=(2, 1))
+    am = po.array_mesh(oarr, 3)
+    sfr = np.empty((xn.shape[1], len(pts), len(freqs)), dtype=np.complex128)
+    for i, f in enumerate(freqs):
+        sfr[:, :, i] = xn[i] @ po.pres_vector(am, pts, 2 * np.pi * f / setup.c).T
+    to, ho = po.fft_to_fir(freqs, sfr, interp=2, use_kkr=False)
+    assert sir.shape == ho.shape and np.allclose(t, to, rtol=1e-13, atol=0) and _rel(sir, ho) < 1e-9
