@@ -96,5 +96,6 @@ extern "C" int cnld_b200_set_lu_outer_inverse(int v) { cnld::g_lu_outer_inverse 
 namespace cnld_hapi { extern int g_hsweep_fluid_precond; }
 extern "C" int cnld_b200_set_hsweep_fluid_precond(int v) { cnld_hapi::g_hsweep_fluid_precond = v; return 0; }
 extern "C" int cnld_b200_set_lu_reserve(int v) { cnld::g_lu_reserve_sms = v; return 0; }
-namespace cnld { extern int g_hmv_tstack; }
+namespace cnld { extern int g_hmv_tstack; extern int g_hmv_ywarps; }
+extern "C" int cnld_b200_set_hmv_ywarps(int v) { cnld::g_hmv_ywarps = v; return 0; }
 extern "C" int cnld_b200_set_hmv_tstack(int v) { cnld::g_hmv_tstack = v; return 0; }

@@ -351,7 +351,7 @@ __global__ void k_permute_out(uint n, uint nrhs, const uint *__restrict__ perm, 
 // band is a 16 x K x (16 TC) complex GEMM, 3M product (X = ArBr, Y = AiBi, W = (Ar+Ai)(Br+Bi)) on
 // DMMA.8x8x4 -- a tenth of the instructions of the DFMA formulation, which was issue/latency bound
 // (ncu: FP64 pipe 41 % active, long-scoreboard stalls).
-constexpr int BAND = 16, BT_THREADS = 64, AS_LDB = BAND + 2;
+constexpr int BAND = 16, AS_LDB = BAND + 2;
 
 // The batched kernels keep their work vectors DOF-major, [dof][rhs]: the 16 x (16 TC) operand tile of a
 // round is then 16 contiguous runs of 16 TC right-hand sides instead of 16 TC runs of 16 DOFs.
@@ -386,15 +386,17 @@ __device__ __forceinline__ void hm_dmma(double &c0, double &c1, double a, double
 // CTA = 2 warps; warp w owns the right-hand sides [8 TC w, 8 TC (w+1)) of the pass (TC n-tiles of 8).
 // TMODE = false: CTA = band of 16 rows of y.   TMODE = true: CTA = low-rank leaf, rows = rank indices,
 // t = V^T x|cols written to the scratch ([rank index][rhs]); the rounds are 16 columns of the leaf.
-template <int TC, bool TMODE>
-__global__ void __launch_bounds__(BT_THREADS)
+template <int TC, bool TMODE, int NW = 2>
+__global__ void __launch_bounds__(32 * NW)
 k_hmv_gemm(const uint *__restrict__ band_ptr, const HMat::DRound *__restrict__ dround, const uint *__restrict__ bfar_ptr,
            const HMat::FarItem *__restrict__ bfar, const uint *__restrict__ far_ids, const HLeafDev *__restrict__ leaves,
            const unsigned long long *__restrict__ toff, const cplx *__restrict__ pool, cplx *T,
            const cplx *__restrict__ xp, cplx *yp, uint ntot, uint nrhs) {
-  constexpr int RP = 16 * TC, XS_LD = RP + 2;   // leading dimensions == 2 (mod 8): conflict-free fragment loads
-  __shared__ cplx As[2][16][AS_LDB];      // [contraction index][row]
-  __shared__ cplx Xs[2][16][XS_LD];       // [contraction index][rhs]
+  constexpr int BT_THREADS = 32 * NW;        // NW warps, each TC n-tiles of 8 right-hand sides
+  constexpr int RP = 8 * TC * NW, XS_LD = RP + 2;   // leading dimensions == 2 (mod 8): conflict-free fragment loads
+  extern __shared__ __align__(16) unsigned char hg_smem[];
+  cplx (*As)[16][AS_LDB] = reinterpret_cast<cplx (*)[16][AS_LDB]>(hg_smem);                                  // [buf][contraction index][row]
+  cplx (*Xs)[16][XS_LD] = reinterpret_cast<cplx (*)[16][XS_LD]>(hg_smem + sizeof(cplx) * 2 * 16 * AS_LDB);   // [buf][contraction index][rhs]
   __shared__ HMat::FarItem Is[3][16];     // per contraction index: U/A column, row range, x or t index
   __shared__ uint s_cnt[3], s_far[3];
   const uint tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1082,6 +1084,7 @@ int hmat_assemble(cudaStream_t st, HMat &H, double kr, double ki, double accur) 
 }
 
 int g_hmv_tstack = 1;
+int g_hmv_ywarps = 0;   // 0: pick by the batch width
 
 // Fill every leaf of H from an explicit dense matrix on the device (original DOF order, column-major):
 // inadmissible leaves take their sub-block, admissible leaves its partial-pivot ACA to `accur`.
@@ -1134,7 +1137,7 @@ int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y
     CNLD_CK_LAUNCH();
     // t-pass: right-hand sides per pass = 8 TC NW; the width that wastes the fewest columns, ties to the wider
     if (!g_hmv_tstack && H.nmvfar) {   // debug: one CTA per low-rank leaf (round-1 kernel)
-      k_hmv_gemm<4, true><<<H.nmvfar, BT_THREADS, 0, st>>>(H.d_band_ptr, H.d_dround, H.d_bfar_ptr, H.d_bfar, H.d_mvfar,
+      k_hmv_gemm<4, true><<<H.nmvfar, 64, (int)sizeof(cplx) * 2 * 16 * (AS_LDB + 16 * 4 + 2), st>>>(H.d_band_ptr, H.d_dround, H.d_bfar_ptr, H.d_bfar, H.d_mvfar,
                                                            H.d_leaf, H.d_toff, H.d_pool, H.d_T, H.d_xp, H.d_yp, H.n, nrhs);
       CNLD_CK_LAUNCH();
     } else if (H.ntband) {
@@ -1162,21 +1165,42 @@ int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y
 #undef CNLD_TS
       CNLD_CK_LAUNCH();
     }
-    // y-pass: right-hand sides per pass (16 * TC)
-    int tc = 2;
-    uint best = ~0u;
-    for (int c : {2, 3, 4}) {
-      const uint rp = 16 * c, waste = (nrhs + rp - 1) / rp * rp - nrhs;
-      if (waste <= best) { best = waste; tc = c; }
-    }
-#define CNLD_HMV(TCV)                                                                                              \
-  k_hmv_gemm<TCV, false><<<H.nband, BT_THREADS, 0, st>>>(H.d_band_ptr, H.d_dround, H.d_bfar_ptr, H.d_bfar,           \
-      H.d_mvfar, H.d_leaf, H.d_toff, H.d_pool, H.d_T, H.d_xp, H.d_yp, H.n, nrhs)
-    if (tc == 2) CNLD_HMV(2);
-    else if (tc == 3) CNLD_HMV(3);
-    else CNLD_HMV(4);
+    // y-pass: right-hand sides per pass = 8 TC NW, chosen like the t-pass (fewest wasted columns, ties to the wider:
+    // a wider pass re-reads the leaf data and the round descriptors fewer times)
+    {
+      int bw = 2, bt = 2;
+      uint bestw = ~0u;
+      for (int w : {2, 4})
+        for (int c : {2, 3, 4}) {
+          const uint rp = 8 * c * w, waste = (nrhs + rp - 1) / rp * rp - nrhs;
+          if (waste < bestw || (waste == bestw && 8 * c * w > 8 * bt * bw)) { bestw = waste; bw = w; bt = c; }
+        }
+      if (g_hmv_ywarps == 2 || g_hmv_ywarps == 4) {   // debug override of the warp count
+        bw = g_hmv_ywarps;
+        bestw = ~0u;
+        for (int c : {2, 3, 4}) {
+          const uint rp = 8 * c * bw, waste = (nrhs + rp - 1) / rp * rp - nrhs;
+          if (waste <= bestw) { bestw = waste; bt = c; }
+        }
+      }
+#define CNLD_HMV(NWV, TCV)                                                                                         \
+  do {                                                                                                             \
+    constexpr int SM = (int)sizeof(cplx) * 2 * 16 * (AS_LDB + 8 * TCV * NWV + 2);                                  \
+    static bool attr[64] = {false};                                                                                \
+    int dev = 0;                                                                                                   \
+    CNLD_CK(cudaGetDevice(&dev));                                                                                  \
+    if (!attr[dev & 63]) {                                                                                         \
+      CNLD_CK(cudaFuncSetAttribute(k_hmv_gemm<TCV, false, NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); \
+      attr[dev & 63] = true;                                                                                       \
+    }                                                                                                              \
+    k_hmv_gemm<TCV, false, NWV><<<H.nband, 32 * NWV, SM, st>>>(H.d_band_ptr, H.d_dround, H.d_bfar_ptr, H.d_bfar,     \
+        H.d_mvfar, H.d_leaf, H.d_toff, H.d_pool, H.d_T, H.d_xp, H.d_yp, H.n, nrhs);                                \
+  } while (0)
+      if (bw == 2) { if (bt == 2) CNLD_HMV(2, 2); else if (bt == 3) CNLD_HMV(2, 3); else CNLD_HMV(2, 4); }
+      else { if (bt == 2) CNLD_HMV(4, 2); else if (bt == 3) CNLD_HMV(4, 3); else CNLD_HMV(4, 4); }
 #undef CNLD_HMV
-    CNLD_CK_LAUNCH();
+      CNLD_CK_LAUNCH();
+    }
     k_permute_out_t<<<gb, 256, 0, st>>>(H.n, nrhs, H.d_perm, alpha, H.d_yp, d_y);
     CNLD_CK_LAUNCH();
     return 0;

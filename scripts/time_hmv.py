@@ -16,9 +16,9 @@ t0 = time.perf_counter()
 H.assemble(2 * np.pi * f / 1500, 1e-2)
 ta = time.perf_counter() - t0
 info = H.info()
-for nrhs in [(v, m) for m in (0, 1) for v in nrhs_list]:
+for nrhs in [(v, m) for m in (2, 4) for v in nrhs_list]:
     nrhs, mode = nrhs
-    _lib.lib().cnld_b200_set_hmv_tstack(mode)
+    _lib.lib().cnld_b200_set_hmv_ywarps(mode)
     s = H.bench_matvec(nrhs, 3)
-    print(json.dumps(dict(tstack=mode, n=n, f=f, nrhs=nrhs, seconds=s, stored=info['stored'], maxrank=info['maxrank'], assemble_s=ta,
+    print(json.dumps(dict(ywarps=mode, n=n, f=f, nrhs=nrhs, seconds=s, stored=info['stored'], maxrank=info['maxrank'], assemble_s=ta,
                           tflops_8=8.0 * info['stored'] * nrhs / s / 1e12, gbs_leafdata=16.0 * info['stored'] / s / 1e9)), flush=True)
