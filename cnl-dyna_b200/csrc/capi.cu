@@ -272,7 +272,7 @@ int enqueue_frequency(cnld_ctx *c, Slot &S, double f, double cs, double rho, cpl
   CNLD_CK(cudaMemsetAsync(S.X, 0, sizeof(cplx) * (size_t)nv * P, S.st));
   k_build_rhs<<<P, 128, 0, S.st>>>(P, c->d_f_indptr, c->d_f_idx, c->d_f_val, S.X, nv);
   CNLD_CK_LAUNCH();
-  if (lu_solve(S.st, S.lu, S.G, nv, S.X, P, nv)) return -1;
+  if (lu_solve(S.st, S.lu, S.G, nv, S.X, P, nv, c->f_first_row.empty() ? nullptr : c->f_first_row.data())) return -1;
   {
     const cplx *src = S.X;
     cplx *dst = S.E, *other = S.E2;
@@ -700,6 +700,12 @@ int cnld_b200_set_loads(cnld_ctx *c, cnld_uint P, const int64_t *f_indptr, const
   for (int64_t i = 0; i < a_indptr[P]; i++) if (a_idx[i] >= nv) { set_error("AVG row index out of range"); return -1; }
   if (P != c->P) { free_workspace(c); c->xpatch_cap = 0; }
   c->P = P;
+  // first loaded row of every source patch: lets the forward substitution skip columns that are still zero
+  c->f_first_row.assign(P, (uint)nv);
+  for (cnld_uint s = 0; s < P; s++)
+    for (int64_t q = f_indptr[s]; q < f_indptr[s + 1]; q++) c->f_first_row[s] = std::min<uint>(c->f_first_row[s], f_idx[q]);
+  for (cnld_uint s = 1; s < P; s++)
+    if (c->f_first_row[s] < c->f_first_row[s - 1]) { c->f_first_row.clear(); break; }   // not ordered: no skipping
   if (upload(c->d_f_indptr, f_indptr, (size_t)P + 1) || upload(c->d_f_idx, f_idx, (size_t)f_indptr[P]) ||
       upload(c->d_f_val, f_val, (size_t)f_indptr[P]) || upload(c->d_a_indptr, a_indptr, (size_t)P + 1) ||
       upload(c->d_a_idx, a_idx, (size_t)a_indptr[P]) || upload(c->d_a_val, a_val, (size_t)a_indptr[P]) ||

@@ -128,6 +128,6 @@ int lu_factor(cudaStream_t st, LuWork &w, cplx *a, size_t lda);
 int lu_factor_sym(cudaStream_t st, LuWork &w, cplx *a, size_t lda);
 // X (n x nrhs, ldx) <- (LU)^-1 X
 int lu_solve(cudaStream_t st, const LuWork &w, const cplx *a, size_t lda, cplx *x, uint nrhs,
-             size_t ldx);
+             size_t ldx, const uint *col_first_row = nullptr);
 
 }  // namespace cnld

@@ -54,6 +54,7 @@ struct cnld_ctx {
   uint *d_f_idx = nullptr, *d_a_idx = nullptr;
   double *d_f_val = nullptr, *d_a_val = nullptr;
   uint8_t *d_ob = nullptr;
+  std::vector<uint> f_first_row;   // per source patch: first loaded row (empty: columns not ordered by row)
   // results of the last sweep
   cplx *d_xpatch = nullptr;
   size_t xpatch_cap = 0;

@@ -440,9 +440,19 @@ int lu_invert_outer(cudaStream_t st, LuWork &w, const cplx *a, size_t lda) {
 // whose inverse is available (lu_invert_outer) take one product with the inverse and one rank-nbo
 // update of everything beyond; the others (a ragged last block, stand-alone lrsolve) go through
 // block steps with the inverted nb x nb diagonal blocks.
+// col_first_row (optional, host, nrhs entries, non-decreasing): row of the first non-zero of every
+// right-hand side.  The forward substitution then skips, per outer block, the columns that are still
+// zero there (patch loads: column s is non-zero only on its own membrane, generate_db.py:84) -- at the
+// 4x4 array half of the (block, column) pairs.
 int lu_solve(cudaStream_t st, const LuWork &w, const cplx *a, size_t lda, cplx *x, uint nrhs,
-             size_t ldx) {
+             size_t ldx, const uint *col_first_row) {
   const uint n = w.n;
+  auto active = [&](uint row_end) -> uint {   // columns whose first non-zero row is below row_end
+    if (!col_first_row) return nrhs;
+    uint c = 0;
+    while (c < nrhs && col_first_row[c] < row_end) c++;
+    return c;
+  };
   const bool inv = w.inv_ready && g_lu_outer_inverse;
   const uint NBO = inv ? w.inv_nbo : (uint)((g_lu_outer / NB) * NB > 0 ? (g_lu_outer / NB) * NB : NB);
   if (inv && w.ytmp_elems < (size_t)NBO * nrhs) {
@@ -454,22 +464,24 @@ int lu_solve(cudaStream_t st, const LuWork &w, const cplx *a, size_t lda, cplx *
   const uint nouter = (n + NBO - 1) / NBO;
   for (uint ob = 0; ob < nouter; ob++) {  // L y = b
     const uint O = ob * NBO, OE = (n - O < NBO) ? n : O + NBO;
+    const uint na = active(OE);     // the other columns are zero in rows [0, OE) and stay zero
+    if (!na) continue;
     if (inv && ob < w.inv_nfull) {
-      if (zgemm3m(st, NBO, nrhs, NBO, 1.0, w.linvO + (size_t)ob * NBO * NBO, NBO, x + O, ldx, 0.0, w.ytmp, NBO)) return -1;
-      CNLD_CK(cudaMemcpy2DAsync(x + O, sizeof(cplx) * ldx, w.ytmp, sizeof(cplx) * NBO, sizeof(cplx) * NBO, nrhs,
+      if (zgemm3m(st, NBO, na, NBO, 1.0, w.linvO + (size_t)ob * NBO * NBO, NBO, x + O, ldx, 0.0, w.ytmp, NBO)) return -1;
+      CNLD_CK(cudaMemcpy2DAsync(x + O, sizeof(cplx) * ldx, w.ytmp, sizeof(cplx) * NBO, sizeof(cplx) * NBO, na,
                                 cudaMemcpyDeviceToDevice, st));
-      if (n > OE && zgemm3m(st, n - OE, nrhs, NBO, -1.0, a + (size_t)O * lda + OE, lda, w.ytmp, NBO, 1.0, x + OE, ldx))
+      if (n > OE && zgemm3m(st, n - OE, na, NBO, -1.0, a + (size_t)O * lda + OE, lda, w.ytmp, NBO, 1.0, x + OE, ldx))
         return -1;
       continue;
     }
     for (uint o = O; o < OE; o += NB) {
       const uint b = o / NB, nbk = (OE - o < (uint)NB) ? OE - o : NB, in_rows = OE - o - nbk;
       cplx *xb = x + o;
-      if (zgemm(st, nbk, nrhs, nbk, 1.0, w.linv + (size_t)b * NB * NB, NB, xb, ldx, 0.0, xb, ldx)) return -1;
-      if (in_rows && zgemm3m(st, in_rows, nrhs, nbk, -1.0, a + (size_t)o * lda + o + nbk, lda, xb, ldx, 1.0,
+      if (zgemm(st, nbk, na, nbk, 1.0, w.linv + (size_t)b * NB * NB, NB, xb, ldx, 0.0, xb, ldx)) return -1;
+      if (in_rows && zgemm3m(st, in_rows, na, nbk, -1.0, a + (size_t)o * lda + o + nbk, lda, xb, ldx, 1.0,
                              xb + nbk, ldx)) return -1;
     }
-    if (n > OE && zgemm3m(st, n - OE, nrhs, OE - O, -1.0, a + (size_t)O * lda + OE, lda, x + O, ldx, 1.0, x + OE, ldx))
+    if (n > OE && zgemm3m(st, n - OE, na, OE - O, -1.0, a + (size_t)O * lda + OE, lda, x + O, ldx, 1.0, x + OE, ldx))
       return -1;
   }
   for (uint ob = nouter; ob-- > 0;) {  // R x = y
