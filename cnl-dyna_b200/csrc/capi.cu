@@ -704,8 +704,8 @@ int cnld_b200_set_loads(cnld_ctx *c, cnld_uint P, const int64_t *f_indptr, const
   c->f_first_row.assign(P, (uint)nv);
   for (cnld_uint s = 0; s < P; s++)
     for (int64_t q = f_indptr[s]; q < f_indptr[s + 1]; q++) c->f_first_row[s] = std::min<uint>(c->f_first_row[s], f_idx[q]);
-  for (cnld_uint s = 1; s < P; s++)
-    if (c->f_first_row[s] < c->f_first_row[s - 1]) { c->f_first_row.clear(); break; }   // not ordered: no skipping
+  // non-decreasing lower envelope (suffix minimum): column s and every later one are zero above f_first_row[s]
+  for (cnld_uint s = P; s-- > 1;) c->f_first_row[s - 1] = std::min(c->f_first_row[s - 1], c->f_first_row[s]);
   if (upload(c->d_f_indptr, f_indptr, (size_t)P + 1) || upload(c->d_f_idx, f_idx, (size_t)f_indptr[P]) ||
       upload(c->d_f_val, f_val, (size_t)f_indptr[P]) || upload(c->d_a_indptr, a_indptr, (size_t)P + 1) ||
       upload(c->d_a_idx, a_idx, (size_t)a_indptr[P]) || upload(c->d_a_val, a_val, (size_t)a_indptr[P]) ||

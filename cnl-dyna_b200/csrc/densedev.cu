@@ -23,17 +23,27 @@ std::list<Resident *> g_cache;   // most recently used first
 constexpr size_t MAX_RESIDENT = 3;
 constexpr uint NSAMPLE = 4096;
 
+// Fingerprint = the whole diagonal + NSAMPLE entries spread evenly over the matrix.  It catches the host
+// array being reused for another matrix or rescaled / refactored in place; a write that touches none of the
+// sampled entries is NOT detected (cnl-dyna never writes into a matrix between its lrsolve calls;
+// CNLD_B200_NO_RESIDENT=1 turns the cache off and every call uploads again).
 size_t sample_index(uint s, uint rows, uint cols, size_t ldh) {
+  const uint nd = std::min(rows, cols);
+  if (s < nd) return (size_t)s * ldh + s;
+  s -= nd;
   const unsigned long long tot = (unsigned long long)rows * cols;
   const unsigned long long e = (tot * (2ull * s + 1)) / (2ull * NSAMPLE) % (tot ? tot : 1);
   return (size_t)(e / rows) * ldh + (size_t)(e % rows);
 }
+uint sample_count(const Resident &R) { return NSAMPLE + std::min(R.rows, R.cols); }
 void take_fingerprint(Resident &R, const cplx *host) {
-  R.finger.resize(NSAMPLE);
-  for (uint s = 0; s < NSAMPLE; s++) R.finger[s] = host[sample_index(s, R.rows, R.cols, R.ldh)];
+  R.finger.resize(sample_count(R));
+  for (uint s = 0; s < R.finger.size(); s++) R.finger[s] = host[sample_index(s, R.rows, R.cols, R.ldh)];
 }
 bool fingerprint_ok(const Resident &R, const cplx *host) {
-  for (uint s = 0; s < NSAMPLE; s++) {
+  static const bool off = getenv("CNLD_B200_NO_RESIDENT") != nullptr;
+  if (off) return false;
+  for (uint s = 0; s < R.finger.size(); s++) {
     const cplx v = host[sample_index(s, R.rows, R.cols, R.ldh)];
     if (memcmp(&v, &R.finger[s], sizeof(cplx)) != 0) return false;
   }
