@@ -6,9 +6,9 @@
 // whole history with offset 1, once per step, and `_fir_conv_add` for the current sample with offset 0 in
 // every fixed-point iteration, :459-503).  The patch-to-patch impulse-response table fir[P][P][nfir]
 // (663 MB at the 4x4 array) stays on the device; one convolution reads it once -- an HBM-bound kernel
-// (2 flops per 8 bytes).  Thread block = (destination j, slice of the sources), threads along the lag k
-// (contiguous in the table and, with the history stored source-major, contiguous in time as well);
-// per-block partial sums are reduced in a fixed order, so results do not depend on scheduling.
+// (2 flops per 8 bytes).  Thread block = (source i, slice of the destinations): the source's history window
+// sits in shared memory and every warp streams whole contiguous table rows against it; the per-(j, i)
+// partial sums are reduced over i in a fixed order, so results do not depend on scheduling.
 // The stepping entry points keep the pressure history on the device too: a step uploads one row of P values.
 #include <algorithm>
 
@@ -29,36 +29,48 @@ struct cnld_fir {
 };
 
 namespace {
-constexpr int FC_THREADS = 256;
+constexpr int FC_THREADS = 256, FC_KTILE = 4096;
 
-// partial[j][g] = sum over sources i in group g, lags k < K of fir[i][j][k + offset] * h[i][last - k];
-// h is source-major with row stride hs, `last` = index of the newest sample
+// CTA = (source i, slice of the destinations); the source's history window is staged once in shared memory
+// (reversed, so lag k pairs with table entry k) and every warp streams whole table rows fir[i][j][offset ..
+// offset + K) -- 32 KB of contiguous doubles per row at 4000 taps -- against it.  partial[j][i] = row dot window.
 __global__ void __launch_bounds__(FC_THREADS)
 k_fir_conv(uint nsrc, uint ndest, uint nfir, uint per, uint K, uint offset, const double *__restrict__ fir,
            const double *__restrict__ h, size_t hs, size_t last, double *partial, uint ngroup) {
-  __shared__ double red[FC_THREADS / 32];
-  const uint j = blockIdx.x, g = blockIdx.y;
-  const uint i0 = g * per, i1 = min(nsrc, i0 + per);
-  double acc = 0.0;
-  for (uint i = i0; i < i1; i++) {
-    const double *f = fir + ((size_t)i * ndest + j) * nfir + offset;
-    const double *hp = h + (size_t)i * hs + last;
-    for (uint k = threadIdx.x; k < K; k += FC_THREADS) acc = fma(f[k], hp[-(long long)k], acc);
-  }
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int w = 0; w < FC_THREADS / 32; w++) s += red[w];
-    partial[(size_t)j * ngroup + g] = s;
+  __shared__ double win[FC_KTILE];
+  const uint i = blockIdx.x, g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint j0 = g * per, j1 = min(ndest, j0 + per);
+  const double *hp = h + (size_t)i * hs + last;
+  for (uint k0 = 0; k0 < K; k0 += FC_KTILE) {
+    const uint kt = min((uint)FC_KTILE, K - k0);
+    __syncthreads();
+    for (uint k = threadIdx.x; k < kt; k += FC_THREADS) win[k] = hp[-(long long)(k0 + k)];
+    __syncthreads();
+    for (uint j = j0 + warp; j < j1; j += FC_THREADS / 32) {
+      const double *f = fir + ((size_t)i * ndest + j) * nfir + offset + k0;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      uint k = lane;
+      for (; k + 96 < kt; k += 128) {
+        a0 = fma(__ldcs(f + k), win[k], a0);
+        a1 = fma(__ldcs(f + k + 32), win[k + 32], a1);
+        a2 = fma(__ldcs(f + k + 64), win[k + 64], a2);
+        a3 = fma(__ldcs(f + k + 96), win[k + 96], a3);
+      }
+      for (; k < kt; k += 32) a0 = fma(__ldcs(f + k), win[k], a0);
+      double acc = (a0 + a1) + (a2 + a3);
+      for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (lane == 0) {
+        double *dst = partial + (size_t)j * nsrc + i;
+        *dst = k0 ? *dst + acc : acc;
+      }
+    }
   }
 }
-__global__ void k_fir_finish(uint ndest, uint ngroup, const double *__restrict__ partial, double dt, double *x) {
+__global__ void k_fir_finish(uint ndest, uint nsrc, const double *__restrict__ partial, double dt, double *x) {
   const uint j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= ndest) return;
   double s = 0.0;
-  for (uint g = 0; g < ngroup; g++) s += partial[(size_t)j * ngroup + g];
+  for (uint i = 0; i < nsrc; i++) s += partial[(size_t)j * nsrc + i];
   x[j] = s * dt;
 }
 // p[t][i] (time-major, as the caller holds it) -> h[i][t]
@@ -76,13 +88,13 @@ __global__ void k_fir_push(uint nsrc, size_t cap, size_t pos, const double *__re
 
 int run_conv(cnld_fir *f, const double *d_h, size_t hs, size_t last, uint K, uint offset, double dt, double *x_host) {
   if (K) {
-    k_fir_conv<<<dim3(f->ndest, f->ngroup), FC_THREADS, 0, f->st>>>(f->nsrc, f->ndest, f->nfir, f->per, K, offset, f->d_fir, d_h,
-                                                                   hs, last, f->d_part, f->ngroup);
+    k_fir_conv<<<dim3(f->nsrc, f->ngroup), FC_THREADS, 0, f->st>>>(f->nsrc, f->ndest, f->nfir, f->per, K, offset, f->d_fir, d_h,
+                                                                  hs, last, f->d_part, f->ngroup);
     CNLD_CK_LAUNCH();
   } else {
-    CNLD_CK(cudaMemsetAsync(f->d_part, 0, sizeof(double) * (size_t)f->ndest * f->ngroup, f->st));
+    CNLD_CK(cudaMemsetAsync(f->d_part, 0, sizeof(double) * (size_t)f->ndest * f->nsrc, f->st));
   }
-  k_fir_finish<<<(f->ndest + 127) / 128, 128, 0, f->st>>>(f->ndest, f->ngroup, f->d_part, dt, f->d_x);
+  k_fir_finish<<<(f->ndest + 127) / 128, 128, 0, f->st>>>(f->ndest, f->nsrc, f->d_part, dt, f->d_x);
   CNLD_CK_LAUNCH();
   CNLD_CK(cudaMemcpyAsync(x_host, f->d_x, sizeof(double) * f->ndest, cudaMemcpyDeviceToHost, f->st));
   CNLD_CK(cudaStreamSynchronize(f->st));
@@ -99,13 +111,13 @@ cnld_fir *cnld_b200_fir_create(int device, cnld_uint nsrc, cnld_uint ndest, cnld
   f->device = device; f->nsrc = nsrc; f->ndest = ndest; f->nfir = nfir;
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
-  // enough blocks to fill the GPU a few times over: ndest x ngroup >= 8 x SMs where the sources allow it
-  f->ngroup = std::max(1u, std::min(nsrc, (uint)((8 * nsm + ndest - 1) / ndest)));
-  f->per = (nsrc + f->ngroup - 1) / f->ngroup;
-  f->ngroup = (nsrc + f->per - 1) / f->per;
+  // CTAs = sources x destination slices: about four per SM, at least 8 destinations (one per warp) per slice
+  f->ngroup = std::max(1u, std::min((ndest + 7) / 8, (uint)((4 * nsm + nsrc - 1) / nsrc)));
+  f->per = (ndest + f->ngroup - 1) / f->ngroup;
+  f->ngroup = (ndest + f->per - 1) / f->per;
   const size_t tab = (size_t)nsrc * ndest * nfir;
   bool ok = cudaSetDevice(device) == cudaSuccess && cudaMalloc(&f->d_fir, sizeof(double) * tab) == cudaSuccess &&
-            cudaMalloc(&f->d_part, sizeof(double) * (size_t)ndest * f->ngroup) == cudaSuccess &&
+            cudaMalloc(&f->d_part, sizeof(double) * (size_t)ndest * nsrc) == cudaSuccess &&
             cudaMalloc(&f->d_x, sizeof(double) * ndest) == cudaSuccess && cudaMalloc(&f->d_row, sizeof(double) * nsrc) == cudaSuccess &&
             cudaMemcpy(f->d_fir, fir, sizeof(double) * tab, cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaStreamCreateWithFlags(&f->st, cudaStreamNonBlocking) == cudaSuccess;
