@@ -366,41 +366,34 @@ C4_H = dict(clf=16, eta=0.8, admis='2', strict=True, kmax=64)           # genera
 C4_SOLVE = dict(eps_aca=1e-2, tol=1e-6, restart=50, maxiter=300, batch=96)
 
 
-def _c4_cpu_sample(po, am, k, frac=64, seed=0):
-    """Oracle H-matrix work on every `frac`-th leaf: assemble (ACA / near field) and apply to one vector.
+def _c4_cpu_sample(po, am, k, tree, frac=64, seed=0):
+    """Oracle H-matrix work on every `frac`-th leaf of the block tree: assemble (ACA / near field) and apply to
+    one vector, in C with OpenMP over the leaves (oracle: orc_hleaves_sample).
     Returns (assemble seconds, matvec seconds, leaves sampled, leaves total)."""
-    ct = po.ClusterTree(am, C4_H['clf'])
-    rc, cc, adm = po.build_block(ct, C4_H['eta'], C4_H['strict'])
+    ct, rc, cc, adm = tree
     rng = np.random.default_rng(seed)
     x = rng.standard_normal(am.nvertices) + 1j * rng.standard_normal(am.nvertices)
     pick = np.arange(seed % frac, len(rc), frac)
-    leaves = []
-    t0 = time.perf_counter()
-    for i in pick:
-        ri, ci = ct.idx(rc[i]), ct.idx(cc[i])
-        leaves.append((ri, ci, po.aca_block(am, k, ri, ci, C4_SOLVE['eps_aca']) if adm[i] else po.nearfield(am, k, ri, ci)))
-    ta = time.perf_counter() - t0
-    y = np.zeros(am.nvertices, dtype=np.complex128)
-    t0 = time.perf_counter()
-    for ri, ci, d in leaves:
-        y[ri] += d[0] @ (d[1].T @ x[ci]) if isinstance(d, tuple) else d @ x[ci]
-    tm = time.perf_counter() - t0
-    return ta, tm, len(pick), len(rc)
+    _, info = po.hleaves_sample(am, k, ct, rc, cc, adm, pick, x, eps_aca=C4_SOLVE['eps_aca'], kmax=C4_H['kmax'])
+    return info['assemble_seconds'], info['matvec_seconds'], len(pick), len(rc)
 
 
 def _c4_cpu_line(po, am, freqs, P, iters_mean):
     """CPU estimate of one C4 frequency from a 1/64 sample of the leaves (assembly + one matvec),
     extrapolated to all leaves, all P right-hand sides and the measured GMRES iteration count."""
     ta = tm = 0.0
+    ct = po.ClusterTree(am, C4_H['clf'])
+    tree = (ct,) + tuple(po.build_block(ct, C4_H['eta'], C4_H['strict']))
     for f in freqs:
-        a, m, ns, nl = _c4_cpu_sample(po, am, 2 * np.pi * f / 1500.)
+        a, m, ns, nl = _c4_cpu_sample(po, am, 2 * np.pi * f / 1500., tree)
         ta += a * nl / ns
         tm += m * nl / ns
     ta, tm = ta / len(freqs), tm / len(freqs)
     sec = ta + tm * P * (iters_mean + 2)          # + initial residual and the final update
     return sec, {'value': 1.0 / sec, 'unit': UNIT, 'cores': po.lib().orc_num_threads(), 'kind': 'port',
-                 'sample': f'every 64th H-matrix leaf assembled and applied to one vector by the oracle (per-leaf C calls from '
-                           f'Python), extrapolated x64 x {P} right-hand sides x {iters_mean + 2:.1f} matvecs per right-hand side; '
+                 'sample': f'every 64th H-matrix leaf assembled (OpenMP over the leaves) and applied to one vector by the oracle, '
+                           f'extrapolated x64 x {P} right-hand sides x {iters_mean + 2:.1f} matvecs per right-hand side (single-vector, '
+                           f'serial matvec: an upper bound on the CPU matvec time); '
                            f'assembly {ta:.1f} s + matvecs {tm * P * (iters_mean + 2):.0f} s per frequency'}
 
 

@@ -107,6 +107,8 @@ def lib():
         L.cnld_b200_hmat_assemble.argtypes = [vp, f64, f64, f64]
         L.cnld_b200_hmat_matvec.argtypes = [vp, cfield, vp, vp, u32]
         L.cnld_b200_hmat_capped.argtypes = [vp, vp, vp]
+        L.cnld_b200_hmat_set_coarse.argtypes = [vp, u32, vp, vp]
+        L.cnld_b200_hmat_coarse_used.argtypes = [vp]
         L.cnld_b200_hmat_todense.argtypes = [vp, vp, u32]
         L.cnld_b200_hmat_bench_matvec.argtypes = [vp, u32, C.c_int, vp]
         L.cnld_b200_hsweep_run.argtypes = [vp, vp, vp, u32, f64, f64, f64, f64, u32, u32, u32, vp, vp, vp, vp]
@@ -604,12 +606,38 @@ class HMatrix:
         check(lib().cnld_b200_hmat_todense(self._h, ptr(buf), n))
         return buf.T
 
+    def set_coarse(self, W, fmode):
+        """Coarse space of the two-level GMRES preconditioner: W[n, m] (m <= 16), fmode[m] in Hz."""
+        if W is None:
+            check(lib().cnld_b200_hmat_set_coarse(self._h, 0, None, None))
+            self._coarse = 0
+            return
+        W, fmode = _c(W, np.float64), _c(fmode, np.float64)
+        assert W.shape == (self.ctx.nv, len(fmode))
+        check(lib().cnld_b200_hmat_set_coarse(self._h, W.shape[1], ptr(W), ptr(fmode)))
+        self._coarse = W.shape[1]
+
+    def enable_coarse(self, m=16):
+        """Build the coarse space from the context's FEM operators: the first m in-vacuo eigenmodes
+        (K v = lambda M v on the free nodes) of every membrane = connected component of the mesh."""
+        W, fmode = membrane_modes(self.ctx, m)
+        self.set_coarse(W, fmode)
+        return fmode
+
+    def coarse_used(self):
+        return int(lib().cnld_b200_hmat_coarse_used(self._h))
+
     def sweep(self, freqs, c=1500., rho=1000., eps_aca=1e-2, tol=1e-6, restart=50, maxiter=500, batch=32,
-              want_nodes=True, allow_unconverged=False):
+              want_nodes=True, allow_unconverged=False, coarse=16):
         """H-matrix + GMRES sweep -> x_patch[nf, P, P], x_node[nf, P, N] | None, iters[nf, P], t[nf].
         Raises if a right-hand side misses `tol` within `maxiter` steps (unless allow_unconverged)."""
         freqs = _c(freqs, np.float64)
         nf, P, n = len(freqs), self.ctx.npatch, self.ctx.nv
+        if coarse and getattr(self, '_coarse', None) is None:
+            self.enable_coarse(int(coarse))       # once per H-matrix (frequency independent)
+        elif not coarse and getattr(self, '_coarse', 0):
+            self.set_coarse(None, None)
+            self._coarse = None
         xp = np.zeros((nf, P, P), dtype=np.complex128)
         xn = np.zeros((nf, P, n), dtype=np.complex128) if want_nodes else None
         it = np.zeros((nf, P), dtype=np.uint32)
@@ -623,6 +651,46 @@ class HMatrix:
             check(rc)
         self._warn_capped(self.capped()[1])
         return xp, xn, it, t
+
+
+def membrane_modes(ctx, m=16):
+    """(W[n, m], fmode[m]): per membrane (connected component of the mesh) the first m eigenmodes of the
+    in-vacuo plate problem K v = lambda M v on its unclamped nodes, zero elsewhere; identical membranes share
+    one eigen-decomposition.  fmode = resonance frequencies (Hz) of the first membrane's modes."""
+    from scipy import sparse as sps
+    from scipy.linalg import eigh
+    from scipy.sparse.csgraph import connected_components
+    n = ctx.nv
+    indptr, cols, Kv, Mv, _ = ctx._mbk
+    K = sps.csr_matrix((Kv, cols, indptr), shape=(n, n))
+    M = sps.csr_matrix((Mv, cols, indptr), shape=(n, n))
+    free = ~np.asarray(ctx._loads[-1], dtype=bool)
+    t = ctx.triangles.astype(np.int64)
+    adj = sps.coo_matrix((np.ones(3 * len(t)), (np.r_[t[:, 0], t[:, 1], t[:, 2]], np.r_[t[:, 1], t[:, 2], t[:, 0]])), shape=(n, n))
+    ncomp, lab = connected_components(adj, directed=False)
+    W = np.zeros((n, m))
+    fmode, cache = None, []
+    for c in range(ncomp):
+        idx = np.nonzero((lab == c) & free)[0]
+        if len(idx) == 0:
+            continue
+        Kf = K[idx][:, idx].toarray()
+        Mf = M[idx][:, idx].toarray()
+        hit = next((v for kf, mf, v, _ in cache if kf.shape == Kf.shape and np.array_equal(kf, Kf) and np.array_equal(mf, Mf)), None)
+        if hit is None:
+            mm = min(m, len(idx))
+            lam, V = eigh(0.5 * (Kf + Kf.T), 0.5 * (Mf + Mf.T), subset_by_index=[0, mm - 1])
+            V = V / np.abs(V).max(axis=0)
+            f = np.sqrt(np.maximum(lam, 0.0)) / (2 * np.pi)
+            cache.append((Kf, Mf, V, f))
+            hit = V
+            if fmode is None:
+                fmode = np.full(m, np.inf)
+                fmode[:mm] = f
+        W[idx, :hit.shape[1]] = hit
+    if fmode is None:
+        fmode = np.full(m, np.inf)
+    return W, fmode
 
 
 def lrdecomp(G, device=0):

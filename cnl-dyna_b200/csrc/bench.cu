@@ -93,7 +93,8 @@ extern "C" int cnld_b200_set_lu_outer(int v) { cnld::g_lu_outer = v; return 0; }
 extern "C" int cnld_b200_set_zgemm_3m(int v) { cnld::g_zgemm_3m = v; return 0; }
 
 extern "C" int cnld_b200_set_lu_outer_inverse(int v) { cnld::g_lu_outer_inverse = v; return 0; }
-namespace cnld_hapi { extern int g_hsweep_fluid_precond; }
+namespace cnld_hapi { extern int g_hsweep_fluid_precond; extern int g_hsweep_coarse; }
+extern "C" int cnld_b200_set_hsweep_coarse(int v) { cnld_hapi::g_hsweep_coarse = v; return 0; }
 extern "C" int cnld_b200_set_hsweep_fluid_precond(int v) { cnld_hapi::g_hsweep_fluid_precond = v; return 0; }
 extern "C" int cnld_b200_set_lu_reserve(int v) { cnld::g_lu_reserve_sms = v; return 0; }
 namespace cnld { extern int g_hmv_tstack; extern int g_hmv_ywarps; }

@@ -19,6 +19,10 @@ struct cnld_hmat {
   cnld_ctx *ctx = nullptr;
   HMat H;
   unsigned last_capped = 0;   // rank-capped leaves summed over the assemblies of the last hsweep_run
+  // coarse space of the two-level GMRES preconditioner (cnld_b200_hmat_set_coarse): m functions per node
+  // (membrane eigenmodes, zero on clamped nodes), W[n][m], and their in-vacuo resonance frequencies
+  uint coarse_m = 0, last_coarse_m = 0;
+  std::vector<double> coarse_W, coarse_f;
 };
 
 namespace cnld_hapi {
@@ -173,6 +177,47 @@ struct DevBuf {
   T *release() { T *q = p; p = nullptr; return q; }
 };
 
+// ---- coarse space kernels: coarse DOF (b, j) = mode j restricted to diagonal block b ------------------------
+// C[(b, j)][r] = sum_{i in block b} W[i][j] X[r][i]   (W real); grid (nblocks, nr), block 128 threads
+__global__ void __launch_bounds__(128)
+k_coarse_restrict(uint n, uint m, uint mtot, const uint *__restrict__ r0, const uint *__restrict__ sz,
+                  const double *__restrict__ W, const cplx *__restrict__ X, cplx *C, size_t ldc) {
+  __shared__ double sr[4][16], si[4][16];
+  const uint b = blockIdx.x, r = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const cplx *x = X + (size_t)r * n + r0[b];
+  const double *w = W + (size_t)r0[b] * mtot;
+  double ar[16], ai[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) ar[j] = ai[j] = 0.0;
+  for (uint i = threadIdx.x; i < sz[b]; i += 128) {
+    const cplx v = x[i];
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+      if (j < (int)m) { const double wj = w[(size_t)i * mtot + j]; ar[j] = fma(wj, v.x, ar[j]); ai[j] = fma(wj, v.y, ai[j]); }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    for (int off = 16; off > 0; off >>= 1) { ar[j] += __shfl_xor_sync(0xffffffffu, ar[j], off); ai[j] += __shfl_xor_sync(0xffffffffu, ai[j], off); }
+    if (lane == 0) { sr[warp][j] = ar[j]; si[warp][j] = ai[j]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < m) {
+    const uint j = threadIdx.x;
+    C[(size_t)r * ldc + (size_t)b * m + j] = make_double2(sr[0][j] + sr[1][j] + sr[2][j] + sr[3][j], si[0][j] + si[1][j] + si[2][j] + si[3][j]);
+  }
+}
+// Y[r][i] (+)= sum_j W[i][j] C[(block of i, j)][r]
+__global__ void k_coarse_prolong(uint n, uint m, uint mtot, const uint *__restrict__ blk_of, const double *__restrict__ W,
+                                 const cplx *__restrict__ C, size_t ldc, cplx *Y, int accumulate) {
+  const uint i = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (i >= n) return;
+  const cplx *c = C + (size_t)r * ldc + (size_t)blk_of[i] * m;
+  const double *w = W + (size_t)i * mtot;
+  cplx s = accumulate ? Y[(size_t)r * n + i] : make_double2(0.0, 0.0);
+  for (uint j = 0; j < m; j++) { s.x = fma(w[j], c[j].x, s.x); s.y = fma(w[j], c[j].y, s.y); }
+  Y[(size_t)r * n + i] = s;
+}
+
 struct Blocks {  // diagonal blocks of the FEM operator and their types (identical membranes share one)
   std::vector<uint> r0, sz, type;
   std::vector<uint> rep;  // representative block of each type
@@ -221,6 +266,7 @@ void detect_blocks(const cnld_ctx *c, Blocks &B) {
 }
 
 int g_hsweep_fluid_precond = 1;
+int g_hsweep_coarse = 1;   // 0: ignore the coarse space; n > 1: use exactly n functions per membrane
 
 struct Gmres {
   cnld_ctx *c;
@@ -257,8 +303,92 @@ struct Gmres {
     if (coef != 0.0 && hmat_matvec(st, *H, make_double2(coef, 0.0), x, y, nr)) return -1;
     return 0;
   }
-  int apply_P(const cplx *x, cplx *y, uint nr) {  // y = blockdiag(MBK)^-1 x
-    return apply_blockdiag(d_inv, x, y, nr);
+  int apply_P(const cplx *x, cplx *y, uint nr) {  // y = M^-1 x
+    if (!cm) return apply_blockdiag(d_inv, x, y, nr);   // one level: blockdiag(MBK + own fluid block)^-1
+    // Two-level (A-DEF2): q = W E^-1 W^H x (coarse correction in the span of the membranes' first cm
+    // eigenmodes, E = W^H G W), then the block-Jacobi smoother on what the coarse space did not explain,
+    // y = q + P (x - G q), with G q = (G W) c from the stored G W: no extra H-matvec.  The acoustic
+    // crosstalk between membranes acts mostly through their low modes; with those handled exactly the
+    // iteration count no longer grows with the array size or near the immersed resonances.
+    const uint nc = nblk * cm;
+    dim3 gr(nblk, nr);
+    k_coarse_restrict<<<gr, 128, 0, st>>>(n, cm, cmtot, d_r0, d_sz, d_Wc, x, Cc, nc);
+    CNLD_CK_LAUNCH();
+    if (zgemm3m(st, nc, nr, nc, 1.0, Einv, nc, Cc, nc, 0.0, Cc2, nc)) return -1;
+    CNLD_CK(cudaMemcpyAsync(Tm, x, sizeof(cplx) * (size_t)n * nr, cudaMemcpyDeviceToDevice, st));
+    if (zgemm3m(st, n, nr, nc, -1.0, GW, n, Cc2, nc, 1.0, Tm, n)) return -1;
+    if (apply_blockdiag(d_inv, Tm, y, nr)) return -1;
+    dim3 gp((n + 127) / 128, nr);
+    k_coarse_prolong<<<gp, 128, 0, st>>>(n, cm, cmtot, d_blk_of, d_Wc, Cc2, nc, y, 1);
+    CNLD_CK_LAUNCH();
+    return 0;
+  }
+  // coarse space (optional): cm of the cmtot functions per node are in use at this frequency
+  uint cm = 0, cmtot = 0, nblk = 0;
+  double *d_Wc = nullptr;
+  uint *d_r0 = nullptr, *d_sz = nullptr, *d_blk_of = nullptr;
+  cplx *GW = nullptr, *Einv = nullptr, *Cc = nullptr, *Cc2 = nullptr, *Tm = nullptr;
+  size_t gw_cap = 0;
+  int alloc_coarse(const std::vector<double> &Wh, uint mtot) {
+    cmtot = mtot;
+    nblk = (uint)blk.r0.size();
+    std::vector<uint> blk_of(n, 0);
+    for (uint b = 0; b < nblk; b++) for (uint i = 0; i < blk.sz[b]; i++) blk_of[blk.r0[b] + i] = b;
+    const size_t ncmax = (size_t)nblk * mtot;
+    CNLD_CK(cudaMalloc(&d_Wc, sizeof(double) * Wh.size()));
+    CNLD_CK(cudaMemcpy(d_Wc, Wh.data(), sizeof(double) * Wh.size(), cudaMemcpyHostToDevice));
+    CNLD_CK(cudaMalloc(&d_r0, sizeof(uint) * nblk));
+    CNLD_CK(cudaMalloc(&d_sz, sizeof(uint) * nblk));
+    CNLD_CK(cudaMalloc(&d_blk_of, sizeof(uint) * n));
+    CNLD_CK(cudaMemcpy(d_r0, blk.r0.data(), sizeof(uint) * nblk, cudaMemcpyHostToDevice));
+    CNLD_CK(cudaMemcpy(d_sz, blk.sz.data(), sizeof(uint) * nblk, cudaMemcpyHostToDevice));
+    CNLD_CK(cudaMemcpy(d_blk_of, blk_of.data(), sizeof(uint) * n, cudaMemcpyHostToDevice));
+    CNLD_CK(cudaMalloc(&GW, sizeof(cplx) * (size_t)n * ncmax));
+    CNLD_CK(cudaMalloc(&Einv, sizeof(cplx) * ncmax * ncmax));
+    CNLD_CK(cudaMalloc(&Cc, sizeof(cplx) * ncmax * std::max<size_t>(nb, 1)));
+    CNLD_CK(cudaMalloc(&Cc2, sizeof(cplx) * ncmax * std::max<size_t>(nb, 1)));
+    CNLD_CK(cudaMalloc(&Tm, sizeof(cplx) * (size_t)n * nb));
+    return 0;
+  }
+  // per frequency: G W (through the H-matvec, nb columns at a time), E = W^H G W and its inverse
+  int setup_coarse(uint m_use) {
+    cm = 0;
+    if (!cmtot || !m_use) return 0;
+    const uint m = std::min(m_use, cmtot), nc = nblk * m;
+    for (uint c0 = 0; c0 < nc; c0 += nb) {
+      const uint nr = std::min(nb, nc - c0);
+      // columns c0 .. c0 + nr of W: unit coarse vectors prolonged (X as scratch)
+      CNLD_CK(cudaMemsetAsync(Cc, 0, sizeof(cplx) * (size_t)nc * nr, st));
+      std::vector<cplx> unit((size_t)nc * nr, make_double2(0.0, 0.0));
+      for (uint r = 0; r < nr; r++) unit[(size_t)r * nc + c0 + r] = make_double2(1.0, 0.0);
+      CNLD_CK(cudaMemcpyAsync(Cc, unit.data(), sizeof(cplx) * unit.size(), cudaMemcpyHostToDevice, st));
+      CNLD_CK(cudaStreamSynchronize(st));
+      dim3 gp((n + 127) / 128, nr);
+      k_coarse_prolong<<<gp, 128, 0, st>>>(n, m, cmtot, d_blk_of, d_Wc, Cc, nc, Tm, 0);
+      CNLD_CK_LAUNCH();
+      if (apply_G(Tm, GW + (size_t)c0 * n, nr)) return -1;
+    }
+    // E (nc x nc, column major) = W^H (G W), then E^-1 by LU against the identity
+    DevBuf<cplx> E;
+    if (E.alloc((size_t)nc * nc)) return -1;
+    for (uint c0 = 0; c0 < nc; c0 += 4096) {
+      const uint nr = std::min(4096u, nc - c0);
+      dim3 gr(nblk, nr);
+      k_coarse_restrict<<<gr, 128, 0, st>>>(n, m, cmtot, d_r0, d_sz, d_Wc, GW + (size_t)c0 * n, E.p + (size_t)c0 * nc, nc);
+      CNLD_CK_LAUNCH();
+    }
+    k_identity<<<(unsigned)(((size_t)nc * nc + 255) / 256), 256, 0, st>>>(nc, Einv);
+    CNLD_CK_LAUNCH();
+    LuWork w;
+    uint info = 0;
+    const int lrc = (lu_work_alloc(w, nc) || lu_factor(st, w, E.p, nc) || lu_solve(st, w, E.p, nc, Einv, nc, nc) ||
+                     cudaMemcpyAsync(&info, w.info, sizeof(uint), cudaMemcpyDeviceToHost, st) != cudaSuccess) ? -1 : 0;
+    cudaStreamSynchronize(st);
+    lu_work_free(w);
+    if (lrc) return -1;
+    if (info) return 0;      // singular coarse operator (e.g. f = 0 with a degenerate space): stay one-level
+    cm = m;
+    return 0;
   }
   int setup_precond() {
     for (uint t = 0; t < blk.rep.size(); t++) {
@@ -308,6 +438,7 @@ struct Gmres {
   }
   void release() {
     cudaFree(Vb); cudaFree(W); cudaFree(T); cudaFree(X); cudaFree(Bp); cudaFree(Hd); cudaFree(yd); cudaFree(sd);
+    cudaFree(d_Wc); cudaFree(d_r0); cudaFree(d_sz); cudaFree(d_blk_of); cudaFree(GW); cudaFree(Einv); cudaFree(Cc); cudaFree(Cc2); cudaFree(Tm);
     for (auto p : d_inv) cudaFree(p);
     d_inv.clear();
   }
@@ -620,6 +751,11 @@ int cnld_b200_hsweep_run(cnld_ctx *c, cnld_hmat *h, const double *freqs, cnld_ui
   G.restart = restart ? restart : 50;
   detect_blocks(c, G.blk);
   if (G.alloc()) return -1;
+  if (h->coarse_m && g_hsweep_coarse) {
+    if (h->coarse_W.size() != (size_t)n * h->coarse_m) { set_error("hsweep: coarse space does not match the mesh"); return -1; }
+    if (h->coarse_m > 16) { set_error("hsweep: at most 16 coarse functions per node"); return -1; }
+    if (G.alloc_coarse(h->coarse_W, h->coarse_m)) return -1;
+  }
   DevBuf<cplx> dB, dxp;
   if (dB.alloc((size_t)n * G.nb) || dxp.alloc((size_t)P * P)) return -1;
   struct Events {
@@ -642,6 +778,16 @@ int cnld_b200_hsweep_run(cnld_ctx *c, cnld_hmat *h, const double *freqs, cnld_ui
       h->last_capped += h->H.capped_leaves;
     }
     if (G.setup_precond()) { rc = -1; break; }
+    if (G.cmtot) {
+      // modes whose in-vacuo resonance lies below ~1.6 f matter at f (immersion lowers them); at least 4
+      uint m_use = 0;
+      for (uint j = 0; j < h->coarse_m; j++) if (h->coarse_f[j] <= 1.6 * f) m_use = j + 1;
+      m_use = std::max(m_use, std::min(4u, h->coarse_m));
+      if (g_hsweep_coarse > 1) m_use = std::min<uint>(g_hsweep_coarse, h->coarse_m);   // debug: fixed count
+      if (f == 0.0) m_use = 0;
+      if (G.setup_coarse(m_use)) { rc = -1; break; }
+      h->last_coarse_m = G.cm;
+    }
     for (uint s0 = 0; s0 < P && !rc; s0 += G.nb) {
       const uint nr = std::min(G.nb, P - s0);
       cudaMemsetAsync(dB.p, 0, sizeof(cplx) * (size_t)n * nr, 0);
@@ -670,6 +816,18 @@ int cnld_b200_hsweep_run(cnld_ctx *c, cnld_hmat *h, const double *freqs, cnld_ui
   }
   return 0;
 }
+
+/* Coarse space of the two-level preconditioner: W[n][m] (node major, m <= 16) = the first m eigenmodes of
+ * every membrane's in-vacuo plate problem K v = lambda M v on its own nodes (zero on clamped nodes and on
+ * every other membrane), fmode[m] = their resonance frequencies in Hz.  m = 0 removes it. */
+int cnld_b200_hmat_set_coarse(cnld_hmat *h, cnld_uint m, const double *W, const double *fmode) {
+  if (!h || (m && (!W || !fmode)) || m > 16) { set_error("hmat_set_coarse: bad arguments (m <= 16)"); return -1; }
+  h->coarse_m = m;
+  h->coarse_W.assign(W, W + (size_t)h->H.n * m);
+  h->coarse_f.assign(fmode, fmode + m);
+  return 0;
+}
+int cnld_b200_hmat_coarse_used(cnld_hmat *h) { return h ? (int)h->last_coarse_m : -1; }
 
 int cnld_b200_hmat_capped(cnld_hmat *h, unsigned *last_assembly, unsigned *last_sweep) {
   if (!h) { set_error("null H-matrix"); return -1; }

@@ -250,6 +250,15 @@ int cnld_b200_hmat_assemble(cnld_hmat *h, double k_re, double k_im, double eps_a
 /* y[r][:] += alpha * Z x[r][:] for nrhs host vectors of length n (original DOF order) */
 int cnld_b200_hmat_matvec(cnld_hmat *h, cnld_field alpha, const cnld_field *x, cnld_field *y,
                           cnld_uint nrhs);
+/* Coarse space of the two-level GMRES preconditioner (optional; without it: block Jacobi).  W[n][m]
+ * (node major, m <= 16): the first m in-vacuo eigenmodes of every membrane on its own nodes (zero on
+ * clamped nodes); fmode[m]: their resonance frequencies (Hz), used to pick how many are needed at a
+ * frequency.  The preconditioner is then  M^-1 = Q + P (I - G Q),  Q = W (W^H G W)^-1 W^H  with G W kept
+ * on the device (one extra dense product per iteration, no extra H-matvec): the inter-membrane crosstalk
+ * through the low modes is solved exactly, and the iteration count stops growing with the array size and
+ * near the immersed resonances.  cnld_b200_hmat_coarse_used: functions per membrane in the last sweep. */
+int cnld_b200_hmat_set_coarse(cnld_hmat *h, cnld_uint m, const double *W, const double *fmode);
+int cnld_b200_hmat_coarse_used(cnld_hmat *h);
 /* Low-rank leaves whose ACA stopped at the rank capacity kmax before reaching eps_aca (H2Lib's ACA keeps
  * growing the rank): count of the last assemble call, and summed over the last hsweep_run.  Non-zero
  * means the H-matrix is less accurate than eps_aca asks for -- raise kmax. */

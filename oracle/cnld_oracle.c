@@ -621,3 +621,171 @@ ORC_API int orc_num_threads(void)
   return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------
+ * Timing helper for large arrays (bench.py --config c4, CPU baseline): assemble a LIST of H-matrix
+ * leaves -- inadmissible: the dense Galerkin block, admissible: partial-pivot ACA exactly as
+ * orc_aca_block -- and apply them to one vector, with vertex -> triangle adjacency built once
+ * (orc_nearfield_slp_ll scans all T^2 triangle pairs per call, which is fine for the parity cases
+ * and useless at T = 3.7e5), OpenMP over the leaves.  Same entries, same ACA, same stopping rule.
+ * leaf l: rows ridx[rptr[l] .. rptr[l+1]), columns cidx[cptr[l] .. cptr[l+1]), adm[l].
+ * out[0] = assembly seconds, out[1] = matvec seconds, out[2] = stored entries, out[3] = largest rank;
+ * y (nv) += sum over the listed leaves of leaf * x.
+ * ---------------------------------------------------------------------- */
+#include <omp.h>
+typedef struct { uint *tl; uint n; } orc_trilist;
+static void orc_collect_tris(const uint *idx, uint cnt, const uint *vptr, const uint *vadj, int *stamp, int mark, orc_trilist *out)
+{
+  out->n = 0;
+  for (uint i = 0; i < cnt; i++)
+    for (uint e = vptr[idx[i]]; e < vptr[idx[i] + 1]; e++)
+      if (stamp[vadj[e]] != mark) { stamp[vadj[e]] = mark; out->tl[out->n++] = vadj[e]; }
+}
+ORC_API void orc_hleaves_sample(uint nv, uint nt, const real *x_, const uint *t_, const real *g, real kr, real ki,
+                                uint q, uint q2, uint nleaf, const uint *rptr, const uint *ridx, const uint *cptr,
+                                const uint *cidx, const int *adm, real accur, uint kmax, const field *xin, field *y,
+                                real *out)
+{
+  const real(*x)[3] = (const real(*)[3])x_;
+  const uint(*t)[3] = (const uint(*)[3])t_;
+  uint *vptr = calloc(nv + 1, sizeof(uint)), *vadj = malloc(sizeof(uint) * 3 * (size_t)nt), *fill = malloc(sizeof(uint) * nv);
+  for (uint tt = 0; tt < nt; tt++) for (int d = 0; d < 3; d++) vptr[t[tt][d] + 1]++;
+  for (uint v = 0; v < nv; v++) vptr[v + 1] += vptr[v];
+  memcpy(fill, vptr, sizeof(uint) * nv);
+  for (uint tt = 0; tt < nt; tt++) for (int d = 0; d < 3; d++) vadj[fill[t[tt][d]]++] = tt;
+  free(fill);
+  field **data = calloc(nleaf, sizeof(field *));
+  uint *rank = calloc(nleaf, sizeof(uint));
+  double stored = 0.0, maxrank = 0.0;
+  double t0 = omp_get_wtime();
+#pragma omp parallel
+  {
+    orc_rules R;
+    orc_rules_init(&R, q, q2);
+    int *rmap = malloc(sizeof(int) * nv), *cmap = malloc(sizeof(int) * nv), *stamp = malloc(sizeof(int) * nt);
+    for (uint i = 0; i < nv; i++) rmap[i] = cmap[i] = -1;
+    for (uint i = 0; i < nt; i++) stamp[i] = -1;
+    orc_trilist rt = {malloc(sizeof(uint) * nt), 0}, ct = {malloc(sizeof(uint) * nt), 0};
+    int mark = 0;
+#pragma omp for schedule(dynamic, 4) reduction(+ : stored) reduction(max : maxrank)
+    for (uint l = 0; l < nleaf; l++) {
+      const uint *ri = ridx + rptr[l], *ci = cidx + cptr[l];
+      const uint m = rptr[l + 1] - rptr[l], n = cptr[l + 1] - cptr[l];
+      for (uint i = 0; i < m; i++) rmap[ri[i]] = (int)i;
+      for (uint j = 0; j < n; j++) cmap[ci[j]] = (int)j;
+      orc_collect_tris(ri, m, vptr, vadj, stamp, mark++, &rt);
+      orc_collect_tris(ci, n, vptr, vadj, stamp, mark++, &ct);
+      if (!adm[l]) {
+        field *N = calloc((size_t)m * n, sizeof(field));
+        for (uint a = 0; a < rt.n; a++)
+          for (uint b = 0; b < ct.n; b++) {
+            const uint tt = rt.tl[a], ss = ct.tl[b];
+            field loc[3][3];
+            orc_pair_ll(&R, x, t[tt], t[ss], g[tt], g[ss], kr, ki, loc);
+            for (int i = 0; i < 3; i++) {
+              const int r = rmap[t[tt][i]];
+              if (r < 0) continue;
+              for (int j = 0; j < 3; j++) { const int c = cmap[t[ss][j]]; if (c >= 0) N[(size_t)c * m + r] += loc[i][j]; }
+            }
+          }
+        data[l] = N;
+        stored += (double)m * n;
+      } else {
+        uint kc = kmax < m ? kmax : m;
+        if (kc > n) kc = n;
+        field *U = calloc((size_t)(m + n) * kc, sizeof(field)), *V = U + (size_t)m * kc;
+        field *row = malloc(sizeof(field) * n), *col = malloc(sizeof(field) * m);
+        char *rused = calloc(m, 1), *cused = calloc(n, 1);
+        uint k = 0, ik = 0;
+        real start = 0.0;
+        while (k < kc) {
+          memset(row, 0, sizeof(field) * n);            /* residual row ik: triangles of that vertex x column triangles */
+          for (uint e = vptr[ri[ik]]; e < vptr[ri[ik] + 1]; e++) {
+            const uint tt = vadj[e];
+            int li = 0;
+            for (int d = 0; d < 3; d++) if (t[tt][d] == ri[ik]) li = d;
+            for (uint b = 0; b < ct.n; b++) {
+              const uint ss = ct.tl[b];
+              field loc[3][3];
+              orc_pair_ll(&R, x, t[tt], t[ss], g[tt], g[ss], kr, ki, loc);
+              for (int j = 0; j < 3; j++) { const int c = cmap[t[ss][j]]; if (c >= 0) row[c] += loc[li][j]; }
+            }
+          }
+          for (uint p = 0; p < k; p++) for (uint j = 0; j < n; j++) row[j] -= U[(size_t)p * m + ik] * V[(size_t)p * n + j];
+          rused[ik] = 1;
+          uint jk = 0;
+          real best = -1.0;
+          for (uint j = 0; j < n; j++) if (!cused[j] && cabs(row[j]) > best) { best = cabs(row[j]); jk = j; }
+          if (!(best > 0.0)) {
+            uint nx = m;
+            for (uint i = 0; i < m; i++) if (!rused[i]) { nx = i; break; }
+            if (nx == m) break;
+            ik = nx;
+            continue;
+          }
+          cused[jk] = 1;
+          const field piv = 1.0 / row[jk];
+          for (uint j = 0; j < n; j++) V[(size_t)k * n + j] = row[j] * piv;
+          memset(col, 0, sizeof(field) * m);             /* residual column jk */
+          for (uint e = vptr[ci[jk]]; e < vptr[ci[jk] + 1]; e++) {
+            const uint ss = vadj[e];
+            int lj = 0;
+            for (int d = 0; d < 3; d++) if (t[ss][d] == ci[jk]) lj = d;
+            for (uint a = 0; a < rt.n; a++) {
+              const uint tt = rt.tl[a];
+              field loc[3][3];
+              orc_pair_ll(&R, x, t[tt], t[ss], g[tt], g[ss], kr, ki, loc);
+              for (int i = 0; i < 3; i++) { const int r = rmap[t[tt][i]]; if (r >= 0) col[r] += loc[i][lj]; }
+            }
+          }
+          for (uint p = 0; p < k; p++) for (uint i = 0; i < m; i++) col[i] -= U[(size_t)p * m + i] * V[(size_t)p * n + jk];
+          real nu = 0.0, nvv = 0.0;
+          for (uint i = 0; i < m; i++) { U[(size_t)k * m + i] = col[i]; nu += creal(col[i]) * creal(col[i]) + cimag(col[i]) * cimag(col[i]); }
+          for (uint j = 0; j < n; j++) { const field v = V[(size_t)k * n + j]; nvv += creal(v) * creal(v) + cimag(v) * cimag(v); }
+          const real err = sqrt(nu) * sqrt(nvv);
+          if (k == 0) start = err;
+          k++;
+          if (err <= accur * start) break;
+          uint nx = m;
+          best = -1.0;
+          for (uint i = 0; i < m; i++) if (!rused[i] && cabs(col[i]) > best) { best = cabs(col[i]); nx = i; }
+          if (nx == m) break;
+          ik = nx;
+        }
+        free(row); free(col); free(rused); free(cused);
+        data[l] = U;
+        rank[l] = k;
+        stored += (double)k * (m + n);
+        if ((double)k > maxrank) maxrank = (double)k;
+      }
+      for (uint i = 0; i < m; i++) rmap[ri[i]] = -1;
+      for (uint j = 0; j < n; j++) cmap[ci[j]] = -1;
+    }
+    free(rmap); free(cmap); free(stamp); free(rt.tl); free(ct.tl);
+    orc_rules_free(&R);
+  }
+  double t1 = omp_get_wtime();
+  /* matvec over the sampled leaves: disjoint row sets are not guaranteed, so accumulate per leaf under a lock-free
+     per-thread buffer would need nv * threads; leaves are few here: serialise the scatter, parallelise the products */
+  for (uint l = 0; l < nleaf; l++) {
+    const uint *ri = ridx + rptr[l], *ci = cidx + cptr[l];
+    const uint m = rptr[l + 1] - rptr[l], n = cptr[l + 1] - cptr[l];
+    if (!adm[l]) {
+      const field *N = data[l];
+      for (uint j = 0; j < n; j++) { const field xj = xin[ci[j]]; for (uint i = 0; i < m; i++) y[ri[i]] += N[(size_t)j * m + i] * xj; }
+    } else {
+      uint kc = kmax < m ? kmax : m;
+      if (kc > n) kc = n;
+      const field *U = data[l], *V = U + (size_t)m * kc;
+      for (uint p = 0; p < rank[l]; p++) {
+        field s = 0.0;
+        for (uint j = 0; j < n; j++) s += V[(size_t)p * n + j] * xin[ci[j]];
+        for (uint i = 0; i < m; i++) y[ri[i]] += U[(size_t)p * m + i] * s;
+      }
+    }
+  }
+  double t2 = omp_get_wtime();
+  for (uint l = 0; l < nleaf; l++) free(data[l]);
+  free(data); free(rank); free(vptr); free(vadj);
+  out[0] = t1 - t0; out[1] = t2 - t1; out[2] = stored; out[3] = maxrank;
+}
