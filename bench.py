@@ -101,7 +101,8 @@ def workload_freqs(cfg, count, offset=0):
     """`count` frequencies spread over the config's sweep grid (deterministic)."""
     _, _, nf, f0, f1 = CONFIGS[cfg]
     grid = np.linspace(f0, f1, nf)
-    idx = (np.arange(count) * 37 + offset * 101 + 11) % nf
+    stride = 137 if cfg == 'c4' else 37      # c4: few, expensive steps -- spread them over the whole band (high k too)
+    idx = (np.arange(count) * stride + offset * 101 + 11) % nf
     return grid[idx]
 
 

@@ -561,6 +561,13 @@ struct Gmres {
       k_combine<<<ge, 256, 0, st>>>(n, nb, j, Vb, yd, X);
       CNLD_CK_LAUNCH();
       CNLD_CK(cudaStreamSynchronize(st));
+      // Every right-hand side converged inside this cycle by the Arnoldi residual estimate, and no restart has
+      // happened: the estimate is the residual of X up to rounding (CGS2 keeps the basis orthogonal to 1e-15),
+      // so the explicit residual of the next cycle -- a full operator application, a fifth of the work at 4
+      // iterations -- is skipped.  After a restart the explicit residual is always formed.
+      bool finished = true;
+      for (uint r = 0; r < nr; r++) finished &= (done[r] == 1);
+      if (finished && total <= m) break;
     }
     if (iters) for (uint r = 0; r < nr; r++) iters[r] = it[r];
     // Right-hand sides that ran out of iterations: measure the true preconditioned residual of what is
