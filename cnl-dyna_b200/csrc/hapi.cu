@@ -786,9 +786,12 @@ int cnld_b200_hsweep_run(cnld_ctx *c, cnld_hmat *h, const double *freqs, cnld_ui
     }
     if (G.setup_precond()) { rc = -1; break; }
     if (G.cmtot) {
-      // modes whose in-vacuo resonance lies below ~1.6 f matter at f (immersion lowers them); at least 4
+      // modes whose in-vacuo resonance lies below ~2.2 f matter at f (immersion lowers the resonances); at least 4.
+      // Measured at the 16x16 array (scripts/time_hsweep.py): 8.6 MHz m = 2 / 4 / 6 -> 2.73 / 2.56 / 2.76 s,
+      // 28.6 MHz m = 4 / 6 / 10 -> 5.1 / 3.6 / 5.2 s, 42.3 MHz m = 6 / 10 / 16 -> 7.8 / 4.5 / 5.4 s: too few modes cost
+      // iterations, too many cost the dense G W product of every application.
       uint m_use = 0;
-      for (uint j = 0; j < h->coarse_m; j++) if (h->coarse_f[j] <= 1.6 * f) m_use = j + 1;
+      for (uint j = 0; j < h->coarse_m; j++) if (h->coarse_f[j] <= 2.2 * f) m_use = j + 1;
       m_use = std::max(m_use, std::min(4u, h->coarse_m));
       if (g_hsweep_coarse > 1) m_use = std::min<uint>(g_hsweep_coarse, h->coarse_m);   // debug: fixed count
       if (f == 0.0) m_use = 0;
