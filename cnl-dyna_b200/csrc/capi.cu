@@ -303,8 +303,31 @@ int check_ready(cnld_ctx *c) {
   return 0;
 }
 
+int sweep_inner(cnld_ctx *c, const double *freqs, uint nf, double cs, double rho, cnld_field *x_patch,
+                cnld_field *x_node, double *t_freq, bool device_only);
+// On any failure the other slots may still have kernels and asynchronous copies in flight that target
+// the caller's buffers: wait for every stream before the error is returned (the caller is then free to
+// drop its arrays), and forget the half-finished frequencies.
 int sweep_impl(cnld_ctx *c, const double *freqs, uint nf, double cs, double rho, cnld_field *x_patch,
                cnld_field *x_node, double *t_freq, bool device_only) {
+  const int rc = sweep_inner(c, freqs, nf, cs, rho, x_patch, x_node, t_freq, device_only);
+  if (rc && c) {
+    const std::string msg = cnld_b200_last_error();
+    for (int s = 0; s < c->nslots; s++) {
+      Slot &S = c->slots[s];
+      if (S.st) cudaStreamSynchronize(S.st);
+      if (S.st_lo) cudaStreamSynchronize(S.st_lo);
+      if (S.st_asm) cudaStreamSynchronize(S.st_asm);
+      S.pending = -1;
+    }
+    cudaGetLastError();
+    set_error("%s", msg.c_str());
+  }
+  return rc;
+}
+
+int sweep_inner(cnld_ctx *c, const double *freqs, uint nf, double cs, double rho, cnld_field *x_patch,
+                cnld_field *x_node, double *t_freq, bool device_only) {
   if (check_ready(c)) return -1;
   const size_t nv = c->bem.nv, P = c->P;
   // Node displacements go straight into the caller's buffer when it lies inside the region the caller
@@ -756,8 +779,13 @@ int cnld_b200_pres_vector(cnld_ctx *c, const double *obs, cnld_uint nobs, double
   CNLD_CK(cudaSetDevice(c->bem.device));
   double *d_obs = nullptr;
   cplx *d_p = nullptr;
-  CNLD_CK(cudaMalloc(&d_obs, sizeof(double) * 3 * (size_t)nobs));
-  CNLD_CK(cudaMalloc(&d_p, sizeof(cplx) * (size_t)nobs * c->bem.nv));
+  if (cudaMalloc(&d_obs, sizeof(double) * 3 * (size_t)nobs) != cudaSuccess ||
+      cudaMalloc(&d_p, sizeof(cplx) * (size_t)nobs * c->bem.nv) != cudaSuccess) {
+    set_error("pres_vector: out of device memory (%u points)", nobs);
+    cudaGetLastError();
+    cudaFree(d_obs); cudaFree(d_p);
+    return -1;
+  }
   int rc = 0;
   do {
     if (cudaMemcpy(d_obs, obs, sizeof(double) * 3 * (size_t)nobs, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); rc = -1; break; }
@@ -791,10 +819,13 @@ int cnld_b200_pressure(cnld_ctx *c, const double *obs, cnld_uint nobs, const dou
     CNLD_CK(cudaMalloc(&c->d_sp, sizeof(double) * 2 * 3 * nt));
     if (pres_points(0, c->bem, c->d_sp)) return -1;
   }
-  CNLD_CK(cudaMalloc(&d_obs, sizeof(double) * 3 * (size_t)nobs));
-  CNLD_CK(cudaMalloc(&d_disp, sizeof(cplx) * nsrc * nv));
-  CNLD_CK(cudaMalloc(&d_D, sizeof(cplx) * nsrc * 3 * nt));
-  CNLD_CK(cudaMalloc(&d_out, sizeof(cplx) * (size_t)nsrc * nobs));
+  if (cudaMalloc(&d_obs, sizeof(double) * 3 * (size_t)nobs) != cudaSuccess || cudaMalloc(&d_disp, sizeof(cplx) * nsrc * nv) != cudaSuccess ||
+      cudaMalloc(&d_D, sizeof(cplx) * nsrc * 3 * nt) != cudaSuccess || cudaMalloc(&d_out, sizeof(cplx) * (size_t)nsrc * nobs) != cudaSuccess) {
+    set_error("pressure: out of device memory (%u points, %u sources)", nobs, nsrc);
+    cudaGetLastError();
+    cudaFree(d_obs); cudaFree(d_disp); cudaFree(d_D); cudaFree(d_out);
+    return -1;
+  }
   int rc = 0;
   do {
     if (cudaMemcpy(d_obs, obs, sizeof(double) * 3 * (size_t)nobs, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("H2D failed"); rc = -1; break; }
