@@ -2,7 +2,7 @@
 """
 bench.py -- frequencies solved per second on the 4x4 CMUT array (BASELINE.json metric).
 
-One "step" = one batch of frequencies (default 6 per GPU, 3 in flight) pushed through the whole hot path:
+One "step" = one batch of frequencies (default 12 per GPU, 6 in flight) pushed through the whole hot path:
 init G = K - w^2 M - j w B, accumulate -2 rho w^2 Z(k) (Galerkin Helmholtz SLP assembly), unpivoted
 complex-FP64 LU, solve all P source patches, conj / boundary mask / patch average
 (cnld/scripts/generate_db.py:30-130).  Workload = BASELINE.json configs[2] ("4x4 CMUT array
@@ -561,8 +561,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default='c3', choices=sorted(CONFIGS))
-    ap.add_argument('--freqs-per-step', type=int, default=6)
-    ap.add_argument('--streams', type=int, default=3)
+    ap.add_argument('--freqs-per-step', type=int, default=12)
+    ap.add_argument('--streams', type=int, default=6)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--general', action='store_true', help='general unpivoted LU of G instead of the symmetric-part path')
     ap.add_argument('--lu-outer', type=int, default=0, help='debug: outer LU block (multiple of 64)')
