@@ -99,6 +99,8 @@ def lib():
         L.cnld_b200_db_append_block.argtypes = [C.c_char_p, u32, vp, vp, u32, vp, vp, u32, vp, vp, vp, C.c_int]
         L.cnld_b200_db_begin_bulk.argtypes = [C.c_char_p]
         L.cnld_b200_db_finish.argtypes = [C.c_char_p]
+        L.cnld_b200_db_counters.argtypes = [vp]
+        L.cnld_b200_db_append_imp_resp.argtypes = [C.c_char_p, u32, u32, vp, vp, C.c_int]
         L.cnld_b200_hmat_create.restype = vp
         L.cnld_b200_hmat_create.argtypes = [vp, u32, f64, C.c_int, C.c_int, u32]
         L.cnld_b200_hmat_destroy.argtypes = [vp]
@@ -523,6 +525,21 @@ def db_begin_bulk(file):
 
 def db_finish(file):
     check(lib().cnld_b200_db_finish(os.fsencode(file)))
+
+
+def db_append_imp_resp(file, times, h, threads=8):
+    """patch_to_patch_imp_resp rows from h[P, P, nt] (C writer; pages into an empty table, SQL otherwise)."""
+    times, h = _c(times, np.float64), _c(h, np.float64)
+    P, P2, nt = h.shape
+    assert P == P2 and times.shape == (nt,)
+    check(lib().cnld_b200_db_append_imp_resp(os.fsencode(file), P, nt, ptr(times), ptr(h), int(threads)))
+
+
+def db_counters():
+    """Node rows written as pages / through SQL, node indexes generated directly / by CREATE INDEX (this process)."""
+    out = np.zeros(6, np.uint64)
+    check(lib().cnld_b200_db_counters(ptr(out)))
+    return dict(zip(('rows_paged', 'rows_sql', 'index_direct', 'index_sql', 'imp_rows_paged', 'imp_rows_sql'), (int(v) for v in out)))
 
 
 ADMIS = {'2': 0, 'max': 1, 'sphere': 2, '2min': 3, '2_min': 3}

@@ -116,6 +116,15 @@ def append_patch_to_patch_imp_resp(con, **kwargs):
                         _rows(kwargs, ['source_patch', 'dest_patch', 'time', 'displacement']))
 
 
+def append_patch_to_patch_imp_resp_block(file, times, ppir, threads=None):
+    """All rows of patch_to_patch_imp_resp from ppir[P(src), P(dst), nt] -- the rows generate_db.py:143-164
+    builds with meshgrid and appends through pandas -- by the C writer (csrc/dbwriter.cpp)."""
+    from . import _lib
+    if threads is None:
+        threads = min(16, len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1))
+    _lib.db_append_imp_resp(file, times, np.ascontiguousarray(ppir, dtype=np.float64), threads=max(1, int(threads)))
+
+
 def append_frequency_block(file, freqs, wavenums, x_patch, x_node=None, nodes=None, times=None, job_ids=None,
                            threads=None):
     """One transaction for a block of frequencies: x_patch[nf, P(src), P(dst)] and optionally

@@ -33,15 +33,18 @@ _Config = dict(freqs=(0, 50e6, 200e3), sound_speed=1500., fluid_rho=1000., array
 Config = abstract.register_type('Config', _Config)
 
 GMRES = dict(tol=1e-6, restart=50, maxiter=500, batch=96)     # the Krylov stand-in for the reference's H-LU
+LAST_TIMING = {}      # wall seconds of the stages of the last main() call (setup, sweep + writer, finish, postprocess)
 
 
-def postprocess(file, interp):
-    """Frequency responses -> patch-to-patch impulse responses (generate_db.py:143-164)."""
-    freqs, ppfr = database.read_patch_to_patch_freq_resp(file)
+def postprocess(file, interp, freqs=None, ppfr=None):
+    """Frequency responses -> patch-to-patch impulse responses (generate_db.py:143-164).  `freqs`, `ppfr`
+    [P(src), P(dst), nf]: the responses of a sweep that ran in this process (the same doubles the database
+    holds); without them they are read back from the file, as the reference does."""
+    if ppfr is None:
+        freqs, ppfr = database.read_patch_to_patch_freq_resp(file)
     t, ppir = impulse_response.fft_to_fir(freqs, ppfr, interp=interp, axis=-1, use_kkr=True)
-    src, dst, times = np.meshgrid(np.arange(ppir.shape[0]), np.arange(ppir.shape[1]), t, indexing='ij')
-    database.append_patch_to_patch_imp_resp(file, source_patch=src.ravel(), dest_patch=dst.ravel(),
-                                            time=times.ravel(), displacement=ppir.ravel())
+    # the rows the reference builds with meshgrid(source, dest, time) and appends through pandas
+    database.append_patch_to_patch_imp_resp_block(file, t, ppir)
 
 
 def _solver_kind(cfg):
@@ -60,8 +63,9 @@ def _solver_kind(cfg):
 class _Solver:
     """One GPU: blocks of frequencies -> (x_patch, x_node | None, seconds)."""
 
-    def __init__(self, setup, cfg, device, nstreams):
+    def __init__(self, setup, cfg, device, nstreams, ring=False):
         self.kind = _solver_kind(cfg)
+        self._ring, self._turn, self._use_ring = None, 0, ring      # ring: the consumer is done with a block before the third next one
         if self.kind == 'dense':
             self.sw = FrequencySweep(setup, device=device, nstreams=nstreams)
         else:
@@ -75,7 +79,16 @@ class _Solver:
 
     def run(self, freqs, want_nodes):
         if self.kind == 'dense':
-            return self.sw.run(freqs, want_nodes=want_nodes)
+            out = None
+            if want_nodes and self._use_ring:
+                # three page-locked result buffers in rotation (one being filled, one queued, one with the
+                # writer): the node displacements land in them straight from the device
+                nf, P, N = len(freqs), self.sw.setup.npatch, self.sw.setup.nnodes
+                if self._ring is None or self._ring.shape[1] < nf:
+                    self._ring = np.empty((3, nf, P, N), np.complex128)
+                out = self._ring[self._turn % 3][:nf]
+                self._turn += 1
+            return self.sw.run(freqs, want_nodes=want_nodes, out_nodes=out)
         xp, xn, _, t = self.H.sweep(freqs, c=self.setup.c, rho=self.setup.rho, eps_aca=self.eps_aca,
                                     want_nodes=want_nodes, **GMRES)
         return xp, xn, t
@@ -120,6 +133,9 @@ def main(cfg, args, write_over=None, array=None, device=0, block=12, store_nodes
         raise NotImplementedError("use_fluid=False is marked 'doesn't work right yet' in the reference "
                                   "(generate_db.py:93) and is not on the accelerated path")
     kind = _solver_kind(cfg)
+    import time
+    t_start = time.perf_counter()
+    LAST_TIMING.clear()
     f_start, f_stop, f_step = cfg.freqs
     freqs = np.arange(f_start, f_stop + f_step, f_step)
     wavenums = 2 * np.pi * freqs / cfg.sound_speed
@@ -149,6 +165,11 @@ def main(cfg, args, write_over=None, array=None, device=0, block=12, store_nodes
     if kind == 'h':
         block = min(block, 2)        # an H-path frequency takes seconds: small blocks keep the resume points close
     database.begin_bulk(file)        # the freq-resp indexes are rebuilt once, after the load (database.finish_bulk)
+    LAST_TIMING['setup'] = time.perf_counter() - t_start
+    t_sweep = time.perf_counter()
+    writer_busy = [0.0]
+    # a sweep that computes every frequency in this process keeps the patch responses for the post-processing
+    xp_all = np.zeros((len(freqs), setup.npatch, setup.npatch), np.complex128) if len(todo) == len(freqs) else None
 
     # Single writer: block b is written -- one transaction, data and progress rows --
     # while block b+1 is being computed.  The queue holds one block per producer; a writer failure stops
@@ -165,8 +186,12 @@ def main(cfg, args, write_over=None, array=None, device=0, block=12, store_nodes
                 continue                 # drain after an error so the producers never block
             try:
                 ids, xp, xn, t = item
+                t_w = time.perf_counter()
                 database.append_frequency_block(file, freqs[ids], wavenums[ids], xp, xn, setup.vertices, t,
                                                 job_ids=ids + 1)     # job ids are 1-based like the reference's
+                if xp_all is not None:
+                    xp_all[ids] = xp
+                writer_busy[0] += time.perf_counter() - t_w
             except BaseException as e:   # noqa: BLE001 -- re-raised in the main thread
                 failure.append(e)
 
@@ -174,7 +199,7 @@ def main(cfg, args, write_over=None, array=None, device=0, block=12, store_nodes
     th.start()
     try:
         if ndev == 1:
-            solver = _Solver(setup, cfg, dev_ids[0] if devices != 1 else device, nstreams)
+            solver = _Solver(setup, cfg, dev_ids[0] if devices != 1 else device, nstreams, ring=True)
             try:
                 for b0 in range(0, len(todo), block):
                     if failure:
@@ -191,8 +216,18 @@ def main(cfg, args, write_over=None, array=None, device=0, block=12, store_nodes
         th.join()
     if failure:
         raise failure[0]
+    LAST_TIMING['sweep_and_writer'] = time.perf_counter() - t_sweep
+    LAST_TIMING['writer_busy'] = writer_busy[0]
+    t_fin = time.perf_counter()
     database.finish_bulk(file)
-    postprocess(file, cfg.freq_interp)
+    LAST_TIMING['finish_indexes'] = time.perf_counter() - t_fin
+    t_pp = time.perf_counter()
+    if xp_all is not None:
+        postprocess(file, cfg.freq_interp, freqs, np.ascontiguousarray(np.transpose(xp_all, (1, 2, 0))))
+    else:
+        postprocess(file, cfg.freq_interp)
+    LAST_TIMING['postprocess'] = time.perf_counter() - t_pp
+    LAST_TIMING['frequencies'] = int(len(todo))
 
 
 def _run_workers(cfg, setup, freqs, todo, dev_ids, block, store_nodes, nstreams, q, failure, cyclic):

@@ -14,16 +14,21 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <climits>
+#include <cstdlib>
+#include <map>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <algorithm>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../../include/cnld_b200.h"
+#include "dbpages.h"
 
 namespace cnld {
 void set_error(const char *fmt, ...);
@@ -46,8 +51,9 @@ struct Api {
   int (*finalize)(sqlite3_stmt *) = nullptr;
   const char *(*errmsg)(sqlite3 *) = nullptr;
   int (*busy_timeout)(sqlite3 *, int) = nullptr;
+  long long (*column_int64)(sqlite3_stmt *, int) = nullptr;
 };
-constexpr int SQLITE_OK = 0, SQLITE_DONE = 101;
+constexpr int SQLITE_OK = 0, SQLITE_ROW = 100, SQLITE_DONE = 101;
 
 Api *api() {
   static Api a;
@@ -70,8 +76,9 @@ Api *api() {
     a.finalize = (decltype(a.finalize))sym("sqlite3_finalize");
     a.errmsg = (decltype(a.errmsg))sym("sqlite3_errmsg");
     a.busy_timeout = (decltype(a.busy_timeout))sym("sqlite3_busy_timeout");
+    a.column_int64 = (decltype(a.column_int64))sym("sqlite3_column_int64");
     if (!a.open || !a.close || !a.exec || !a.prepare || !a.bind_int64 || !a.bind_double || !a.step || !a.reset ||
-        !a.finalize || !a.errmsg) {
+        !a.finalize || !a.errmsg || !a.column_int64) {
       dlclose(a.lib);
       a.lib = nullptr;
     }
@@ -96,6 +103,16 @@ struct Db {
     return 0;
   }
 };
+// first column of the first row of `sql` as an integer (SQL NULL / no row: 0)
+int query_int(Db &db, const char *sql, long long *out) {
+  sqlite3_stmt *st = nullptr;
+  if (db.A->prepare(db.con, sql, -1, &st, nullptr) != SQLITE_OK) { set_error("sqlite: %s: %s", sql, db.A->errmsg(db.con)); return -1; }
+  const int rc = db.A->step(st);
+  *out = rc == SQLITE_ROW ? db.A->column_int64(st, 0) : 0;
+  db.A->finalize(st);
+  if (rc != SQLITE_ROW && rc != SQLITE_DONE) { set_error("sqlite: %s: %s", sql, db.A->errmsg(db.con)); return -1; }
+  return 0;
+}
 struct Stmt {
   Api *A;
   sqlite3_stmt *s = nullptr;
@@ -152,6 +169,72 @@ std::string scratch_dir(const char *file) {
   const size_t p = f.find_last_of('/');
   return p == std::string::npos ? "." : f.substr(0, p);
 }
+
+// Page path (dbpages.cpp): between cnld_b200_db_begin_bulk and cnld_b200_db_finish this process remembers
+// which rowid ranges of patch_to_node_freq_resp it wrote as pages; if they cover the whole table, finish
+// generates the index from the descriptors instead of letting SQLite scan and sort the table.
+struct BulkState {
+  bool covered = false;                              // every row of the node table is described by `blocks`
+  std::vector<cnld::dbpages::NodeBlock> blocks;
+};
+std::mutex g_bulk_mutex;
+std::atomic<unsigned long long> g_rows_paged{0}, g_rows_sql{0}, g_index_direct{0}, g_index_sql{0}, g_imp_paged{0}, g_imp_sql{0};
+std::map<std::string, BulkState> g_bulk;
+std::string canonical(const char *file) {
+  char buf[PATH_MAX];
+  return realpath(file, buf) ? std::string(buf) : std::string(file);
+}
+bool sql_only() {
+  const char *m = getenv("CNLD_B200_DB_MODE");       // "sql": never write pages directly (tests, debugging)
+  return m && strcmp(m, "sql") == 0;
+}
+const char *NODE_ROOT_SQL = "SELECT rootpage FROM sqlite_master WHERE type='table' AND name='patch_to_node_freq_resp'";
+const char *NODE_NINDEX_SQL = "SELECT count(*) FROM sqlite_master WHERE type='index' AND tbl_name='patch_to_node_freq_resp'";
+
+// node rows of a block as b-tree pages, under SQLite's exclusive lock.  0 done, 1 not applicable, -1 error
+int append_node_pages(const char *file, cnld_uint nf, const double *freqs, const double *wavenums, cnld_uint P, cnld_uint N,
+                      const cnld_field *x_node, const double *nodes, int threads) {
+  if (sql_only()) return 1;
+  Db lock;
+  if (lock.open(file)) return -1;
+  if (lock.exec("BEGIN EXCLUSIVE")) return -1;
+  long long root = 0, nindex = 0;
+  if (query_int(lock, NODE_ROOT_SQL, &root) || query_int(lock, NODE_NINDEX_SQL, &nindex)) return -1;
+  int rc = 1;
+  uint64_t first = 0;
+  if (root >= 2 && nindex == 0)
+    rc = cnld::dbpages::append_node_rows(file, (uint32_t)root, nf, freqs, wavenums, P, N, (const double *)x_node, nodes,
+                                         threads, &first);
+  lock.exec("ROLLBACK");      // nothing was written through this connection; its cache dies with it
+  if (rc == 0) g_rows_paged += (unsigned long long)nf * P * N;
+  std::lock_guard<std::mutex> g(g_bulk_mutex);
+  auto it = g_bulk.find(canonical(file));
+  if (it != g_bulk.end()) {
+    if (rc == 0) {
+      cnld::dbpages::NodeBlock b;
+      b.first_rowid = first; b.nf = nf; b.P = P; b.N = N;
+      b.freqs.assign(freqs, freqs + nf);
+      it->second.blocks.push_back(std::move(b));
+    } else {
+      it->second.covered = false;                    // these rows go in through SQL
+    }
+  }
+  return rc;
+}
+
+// the schema row CREATE INDEX would have written for a b-tree that already exists, and a new schema cookie
+int register_index(const char *file, const char *name, const char *table, uint32_t root, const char *create_sql) {
+  Db db;
+  if (db.open(file)) return -1;
+  long long cookie = 0;
+  if (query_int(db, "PRAGMA schema_version", &cookie)) return -1;
+  char sql[800], bump[64];
+  snprintf(sql, sizeof(sql), "INSERT INTO sqlite_master (type, name, tbl_name, rootpage, sql) VALUES ('index', '%s', '%s', %u, '%s')",
+           name, table, root, create_sql);
+  snprintf(bump, sizeof(bump), "PRAGMA schema_version=%lld", cookie + 1);
+  return (db.exec("PRAGMA writable_schema=ON") || db.exec("BEGIN IMMEDIATE") || db.exec(sql) || db.exec(bump) || db.exec("COMMIT") ||
+          db.exec("PRAGMA writable_schema=OFF")) ? -1 : 0;
+}
 }  // namespace
 
 extern "C" {
@@ -166,6 +249,18 @@ int cnld_b200_db_append_block(const char *file, cnld_uint nf, const double *freq
                               const cnld_field *x_patch, const double *times, cnld_uint N, const cnld_field *x_node,
                               const double *nodes, const cnld_uint *job_ids, int fast) {
   if (!file || !freqs || !wavenums || !x_patch) { set_error("db_append_block: null argument"); return -1; }
+  if (x_node && !nodes) { set_error("db_append_block: node coordinates are needed with x_node"); return -1; }
+  if (x_node && fast > 1) {
+    // node rows first, as pages; the patch rows and the progress marks follow in the SQL transaction below, so
+    // a frequency is marked complete only when its node rows are in the file
+    const int rc = append_node_pages(file, nf, freqs, wavenums, P, N, x_node, nodes, fast);
+    if (rc < 0) return -1;
+    if (rc == 0) x_node = nullptr;
+  } else if (x_node) {
+    std::lock_guard<std::mutex> g(g_bulk_mutex);
+    auto it = g_bulk.find(canonical(file));
+    if (it != g_bulk.end()) it->second.covered = false;
+  }
   Db db;
   if (db.open(file)) return -1;
   Api *A = db.A;
@@ -231,7 +326,7 @@ int cnld_b200_db_append_block(const char *file, cnld_uint nf, const double *freq
     }
     if (rc) break;
     if (x_node) {
-      if (!nodes) { set_error("db_append_block: node coordinates are needed with x_node"); rc = -2; break; }
+      g_rows_sql += (unsigned long long)nf * P * N;
       if (stages.empty()) {
         if (insert_node_rows(db, "", 0, (size_t)nf * P, P, N, freqs, wavenums, x_node, nodes)) { rc = -2; break; }
       } else {
@@ -262,15 +357,139 @@ int cnld_b200_db_append_block(const char *file, cnld_uint nf, const double *freq
 int cnld_b200_db_begin_bulk(const char *file) {
   Db db;
   if (db.open(file)) return -1;
-  return (db.exec("DROP INDEX IF EXISTS patch_to_patch_freq_resp_index") || db.exec("DROP INDEX IF EXISTS patch_to_node_freq_resp_index")) ? -1 : 0;
+  if (db.exec("DROP INDEX IF EXISTS patch_to_patch_freq_resp_index") || db.exec("DROP INDEX IF EXISTS patch_to_node_freq_resp_index")) return -1;
+  long long maxrow = 0;
+  if (query_int(db, "SELECT max(rowid) FROM patch_to_node_freq_resp", &maxrow)) return -1;
+  std::lock_guard<std::mutex> g(g_bulk_mutex);
+  BulkState &st = g_bulk[canonical(file)];
+  st.blocks.clear();
+  st.covered = maxrow == 0;          // rows of an earlier run are not described: finish indexes through SQL then
+  return 0;
 }
 int cnld_b200_db_finish(const char *file) {
+  BulkState st;
+  {
+    std::lock_guard<std::mutex> g(g_bulk_mutex);
+    auto it = g_bulk.find(canonical(file));
+    if (it != g_bulk.end()) { st = std::move(it->second); g_bulk.erase(it); }
+  }
+  const char *node_index_sql = "CREATE INDEX patch_to_node_freq_resp_index ON patch_to_node_freq_resp (source_patch, node_id, frequency)";
+  // the node index straight from the block descriptors when they describe the whole table
+  bool direct = st.covered && !st.blocks.empty() && !sql_only();
+  if (direct) {
+    std::sort(st.blocks.begin(), st.blocks.end(), [](const cnld::dbpages::NodeBlock &a, const cnld::dbpages::NodeBlock &b) { return a.first_rowid < b.first_rowid; });
+    uint64_t next = 1;
+    for (const auto &b : st.blocks) {
+      if (b.first_rowid != next) { direct = false; break; }
+      next += (uint64_t)b.nf * b.P * b.N;
+    }
+    if (direct) {
+      Db lock;
+      if (lock.open(file) || lock.exec("BEGIN EXCLUSIVE")) return -1;
+      long long maxrow = 0, nindex = 0, count_ok = 0;
+      if (query_int(lock, "SELECT max(rowid) FROM patch_to_node_freq_resp", &maxrow) || query_int(lock, NODE_NINDEX_SQL, &nindex)) return -1;
+      (void)count_ok;
+      uint32_t root = 0;
+      int rc = 1;
+      if ((uint64_t)maxrow + 1 == next && nindex == 0) {
+        int threads = (int)std::thread::hardware_concurrency();
+        if (threads > 32) threads = 32;
+        rc = cnld::dbpages::build_node_index(file, st.blocks, threads, &root);
+      }
+      lock.exec("ROLLBACK");
+      if (rc < 0) return -1;
+      direct = rc == 0;
+      if (direct) {
+        g_index_direct++;
+        if (register_index(file, "patch_to_node_freq_resp_index", "patch_to_node_freq_resp", root, node_index_sql)) return -1;
+      }
+    }
+  }
   Db db;
   if (db.open(file)) return -1;
   if (db.exec("PRAGMA cache_size=-1048576")) return -1;
-  return (db.exec("CREATE INDEX IF NOT EXISTS patch_to_patch_freq_resp_index ON patch_to_patch_freq_resp (source_patch, dest_patch, frequency)") ||
-          db.exec("CREATE INDEX IF NOT EXISTS patch_to_node_freq_resp_index ON patch_to_node_freq_resp (source_patch, node_id, frequency)"))
-             ? -1 : 0;
+  if (db.exec("CREATE INDEX IF NOT EXISTS patch_to_patch_freq_resp_index ON patch_to_patch_freq_resp (source_patch, dest_patch, frequency)")) return -1;
+  if (!direct) {
+    if (db.exec("CREATE INDEX IF NOT EXISTS patch_to_node_freq_resp_index ON patch_to_node_freq_resp (source_patch, node_id, frequency)")) return -1;
+    g_index_sql++;
+  }
+  return 0;
+}
+/* Rows (source_patch, dest_patch, time, displacement) of patch_to_patch_imp_resp from h[P][P][nt] -- what
+ * generate_db.py:143-164 appends through pandas after the sweep.  Into an empty table of a plain database the
+ * rows and their index go in as pages (dbpages.cpp); otherwise prepared statements in one transaction. */
+int cnld_b200_db_append_imp_resp(const char *file, cnld_uint P, cnld_uint nt, const double *times, const double *h, int threads) {
+  if (!file || !times || !h || !P || !nt) { set_error("db_append_imp_resp: null argument"); return -1; }
+  const char *index_sql = "CREATE INDEX patch_to_patch_imp_resp_index ON patch_to_patch_imp_resp (source_patch, dest_patch, time)";
+  bool paged = false;
+  if (!sql_only() && threads > 0) {
+    long long root = 0, maxrow = 0, other = 0;
+    {
+      Db db;
+      if (db.open(file)) return -1;
+      if (query_int(db, "SELECT rootpage FROM sqlite_master WHERE type='table' AND name='patch_to_patch_imp_resp'", &root) ||
+          query_int(db, "SELECT max(rowid) FROM patch_to_patch_imp_resp", &maxrow) ||
+          query_int(db, "SELECT count(*) FROM sqlite_master WHERE type='index' AND tbl_name='patch_to_patch_imp_resp' AND "
+                        "name<>'patch_to_patch_imp_resp_index'", &other))
+        return -1;
+      bool ascending = true;
+      for (cnld_uint k = 1; k < nt; k++) ascending = ascending && times[k] > times[k - 1];
+      if (root >= 2 && maxrow == 0 && other == 0 && ascending && times[0] == times[0]) {
+        if (db.exec("DROP INDEX IF EXISTS patch_to_patch_imp_resp_index")) return -1;
+      } else {
+        root = 0;
+      }
+    }
+    if (root >= 2) {
+      Db lock;
+      if (lock.open(file) || lock.exec("BEGIN EXCLUSIVE")) return -1;
+      if (query_int(lock, "SELECT rootpage FROM sqlite_master WHERE type='table' AND name='patch_to_patch_imp_resp'", &root)) return -1;
+      uint64_t first = 0;
+      uint32_t iroot = 0;
+      int rc = cnld::dbpages::append_imp_resp_rows(file, (uint32_t)root, P, nt, times, h, threads, &first);
+      int rci = rc == 0 ? cnld::dbpages::build_imp_resp_index(file, first, P, nt, times, threads, &iroot) : 1;
+      lock.exec("ROLLBACK");
+      if (rc < 0 || rci < 0) return -1;
+      paged = rc == 0;
+      if (paged) g_imp_paged += (unsigned long long)P * P * nt;
+      if (rci == 0 && register_index(file, "patch_to_patch_imp_resp_index", "patch_to_patch_imp_resp", iroot, index_sql)) return -1;
+    }
+  }
+  Db db;
+  if (db.open(file)) return -1;
+  Api *A = db.A;
+  if (!paged) {
+    if (db.exec("PRAGMA synchronous=OFF") || db.exec("PRAGMA journal_mode=MEMORY") || db.exec("PRAGMA cache_size=-262144") || db.exec("BEGIN IMMEDIATE")) return -1;
+    Stmt st(A);
+    int rc = 0;
+    if (A->prepare(db.con, "INSERT INTO patch_to_patch_imp_resp VALUES (?,?,?,?)", -1, &st.s, nullptr) != SQLITE_OK) rc = -1;
+    for (cnld_uint s = 0; s < P && !rc; s++)
+      for (cnld_uint d = 0; d < P && !rc; d++) {
+        const double *hh = h + ((size_t)s * P + d) * nt;
+        A->bind_int64(st.s, 1, s);
+        A->bind_int64(st.s, 2, d);
+        for (cnld_uint k = 0; k < nt; k++) {
+          A->bind_double(st.s, 3, times[k]);
+          A->bind_double(st.s, 4, hh[k]);
+          if (A->step(st.s) != SQLITE_DONE) { rc = -1; break; }
+          A->reset(st.s);
+        }
+      }
+    if (rc) { set_error("sqlite: %s", A->errmsg(db.con)); db.exec("ROLLBACK"); return -1; }
+    if (db.exec("COMMIT")) return -1;
+    g_imp_sql += (unsigned long long)P * P * nt;
+  }
+  char sql[300];
+  snprintf(sql, sizeof(sql), "CREATE INDEX IF NOT EXISTS %s", index_sql + strlen("CREATE INDEX "));
+  return db.exec(sql) ? -1 : 0;
+}
+/* out[6]: node rows written as pages / through SQL, node indexes generated from descriptors / by CREATE INDEX,
+ * impulse-response rows written as pages / through SQL (this process, since load) */
+int cnld_b200_db_counters(unsigned long long *out) {
+  if (!out) { set_error("db_counters: null argument"); return -1; }
+  out[0] = g_rows_paged; out[1] = g_rows_sql; out[2] = g_index_direct; out[3] = g_index_sql;
+  out[4] = g_imp_paged; out[5] = g_imp_sql;
+  return 0;
 }
 
 }  // extern "C"

@@ -331,9 +331,26 @@ int cnld_b200_comm_stats(cnld_comm *comm, double *out);
 int cnld_b200_db_append_block(const char *file, cnld_uint nf, const double *freqs, const double *wavenums,
                               cnld_uint P, const cnld_field *x_patch, const double *times, cnld_uint N,
                               const cnld_field *x_node, const double *nodes, const cnld_uint *job_ids, int fast);
-/* drop the two frequency-response indexes before a bulk load / (re)build them after it */
+/* drop the two frequency-response indexes before a bulk load / (re)build them after it.
+ * With fast > 1, cnld_b200_db_append_block writes the node rows (cnld/database.py:38-45, 2.13 M per
+ * frequency at the 4x4 array) as b-tree pages in SQLite's file format instead of through SQL
+ * (csrc/dbpages.cpp: records encoded by `fast` threads, pages appended to the file, interior levels
+ * rebuilt; applies when the table has no index, i.e. inside the bulk bracket, and the file is a plain
+ * rollback-journal database); cnld_b200_db_finish then generates the node index, already sorted, from the
+ * descriptors of those appends when they cover the whole table, and lets SQLite build it otherwise.
+ * Environment CNLD_B200_DB_MODE=sql disables the page path. */
 int cnld_b200_db_begin_bulk(const char *file);
 int cnld_b200_db_finish(const char *file);
+/* Rows (source_patch, dest_patch, time, displacement) of patch_to_patch_imp_resp (cnld/database.py:47-53) from
+ * h[P][P][nt] and times[nt] -- what cnld/scripts/generate_db.py:143-164 appends through pandas after the sweep.
+ * Into an empty table of a plain rollback-journal database the rows and their (source_patch, dest_patch, time)
+ * index are written as pages by `threads` threads; otherwise prepared statements in one transaction. */
+int cnld_b200_db_append_imp_resp(const char *file, cnld_uint P, cnld_uint nt, const double *times, const double *h,
+                                 int threads);
+/* out[6]: node rows written as pages, node rows written through SQL, node indexes generated from
+ * descriptors, node indexes built by CREATE INDEX, impulse-response rows written as pages / through SQL
+ * (this process) */
+int cnld_b200_db_counters(unsigned long long *out);
 
 /* ---- microbenchmarks used for roofline denominators ----------------------- */
 /* FP64 DMMA ZGEMM C(m x n) -= A(m x k) B(k x n) on device-resident random data;
