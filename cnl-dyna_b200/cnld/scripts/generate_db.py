@@ -168,6 +168,7 @@ def main(cfg, args, write_over=None, array=None, device=0, block=12, store_nodes
     LAST_TIMING['setup'] = time.perf_counter() - t_start
     t_sweep = time.perf_counter()
     writer_busy = [0.0]
+    block_done = []       # single-process path: seconds since the start of the sweep stage at which each block was queued
     # a sweep that computes every frequency in this process keeps the patch responses for the post-processing
     xp_all = np.zeros((len(freqs), setup.npatch, setup.npatch), np.complex128) if len(todo) == len(freqs) else None
 
@@ -206,6 +207,7 @@ def main(cfg, args, write_over=None, array=None, device=0, block=12, store_nodes
                         break
                     ids = todo[b0:b0 + block]
                     q.put((ids,) + tuple(solver.run(freqs[ids], store_nodes)))
+                    block_done.append(time.perf_counter() - t_sweep)
             finally:
                 solver.close()
         else:
@@ -218,6 +220,9 @@ def main(cfg, args, write_over=None, array=None, device=0, block=12, store_nodes
         raise failure[0]
     LAST_TIMING['sweep_and_writer'] = time.perf_counter() - t_sweep
     LAST_TIMING['writer_busy'] = writer_busy[0]
+    if len(block_done) > 1:
+        LAST_TIMING['first_block'] = block_done[0]       # includes creating the device context and its workspaces
+        LAST_TIMING['steady_frequencies_per_s'] = (len(todo) - min(block, len(todo))) / (block_done[-1] - block_done[0])
     t_fin = time.perf_counter()
     database.finish_bulk(file)
     LAST_TIMING['finish_indexes'] = time.perf_counter() - t_fin
