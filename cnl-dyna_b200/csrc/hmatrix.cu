@@ -640,14 +640,29 @@ k_hmv_tstack(const HMat::TBand *__restrict__ tband, const unsigned long long *__
   asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
-// ---- matvec with 1-3 vectors: HBM-bound, so the kernels only have to read every leaf once, coalesced ----
-// t-pass: one warp per low-rank leaf, lanes along the columns (V[:, l] is contiguous), shuffle reduction.
+// ---- matvec with 1-3 vectors: HBM-bound, so the kernels only have to read every leaf once, coalesced, with
+// enough independent loads in flight per warp to cover the DRAM latency ----
+// t-pass: one warp per low-rank leaf, lanes along the columns (V[:, l] is contiguous).  LC rank indices are
+// contracted together: LC independent 16-byte loads per lane before the first use (a leaf is only k x n =
+// 5..10 x 16..64 entries, so one load per lane and rank index would leave the warp waiting for DRAM k times),
+// then LC interleaved shuffle reductions.
 constexpr int V1_THREADS = 128;
+// Compiler fence for values: everything that produced v[] (the loads) is scheduled before this point and every
+// use after it (one asm statement: separate ones would let a use slip between them).  Without it ptxas sinks
+// each load next to its first use, which leaves two loads in flight per lane.
+__device__ __forceinline__ void loads_done(cplx (&v)[4]) {
+  asm volatile("" : "+d"(v[0].x), "+d"(v[0].y), "+d"(v[1].x), "+d"(v[1].y), "+d"(v[2].x), "+d"(v[2].y), "+d"(v[3].x), "+d"(v[3].y));
+}
+__device__ __forceinline__ void loads_done(cplx (&v)[8]) {
+  asm volatile("" : "+d"(v[0].x), "+d"(v[0].y), "+d"(v[1].x), "+d"(v[1].y), "+d"(v[2].x), "+d"(v[2].y), "+d"(v[3].x), "+d"(v[3].y),
+                    "+d"(v[4].x), "+d"(v[4].y), "+d"(v[5].x), "+d"(v[5].y), "+d"(v[6].x), "+d"(v[6].y), "+d"(v[7].x), "+d"(v[7].y));
+}
 template <int NR>
-__global__ void __launch_bounds__(V1_THREADS)
+__global__ void __launch_bounds__(V1_THREADS, 4)
 k_hmv1_t(uint nfar, const uint *__restrict__ far_ids, const HLeafDev *__restrict__ leaves,
          const unsigned long long *__restrict__ toff, const cplx *__restrict__ pool, const cplx *__restrict__ xp,
          cplx *T, uint ntot) {
+  constexpr int LC = NR == 1 ? 8 : 4;
   const uint w = (blockIdx.x * V1_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= nfar) return;
   const uint id = far_ids[w];
@@ -655,65 +670,262 @@ k_hmv1_t(uint nfar, const uint *__restrict__ far_ids, const HLeafDev *__restrict
   const cplx *V = pool + L.off + (size_t)L.m * L.kcap;
   const cplx *x = xp + L.c0;
   cplx *Tl = T + toff[id] * NR;
-  for (uint l = 0; l < L.k; l++) {
-    cplx s[NR];
+  for (uint l0 = 0; l0 < L.k; l0 += LC) {
+    cplx s[LC][NR];
 #pragma unroll
-    for (int r = 0; r < NR; r++) s[r] = make_double2(0.0, 0.0);
-    const cplx *v = V + (size_t)l * L.n;
+    for (int c = 0; c < LC; c++)
+#pragma unroll
+      for (int r = 0; r < NR; r++) s[c][r] = make_double2(0.0, 0.0);
     for (uint j = lane; j < L.n; j += 32) {
-      const cplx a = v[j];
+      cplx a[LC], xv[NR];
 #pragma unroll
-      for (int r = 0; r < NR; r++) cfma(s[r], a, x[(size_t)r * ntot + j]);
+      for (int c = 0; c < LC; c++)       // clamped row: rows beyond the rank repeat the last one and are not stored
+        a[c] = __ldg(V + (size_t)min(l0 + c, L.k - 1) * L.n + j);
+#pragma unroll
+      for (int r = 0; r < NR; r++) xv[r] = x[(size_t)r * ntot + j];
+      loads_done(a);
+#pragma unroll
+      for (int c = 0; c < LC; c++)
+#pragma unroll
+        for (int r = 0; r < NR; r++) cfma(s[c][r], a[c], xv[r]);
     }
 #pragma unroll
-    for (int r = 0; r < NR; r++) {
-      for (int off = 16; off > 0; off >>= 1) {
-        s[r].x += __shfl_xor_sync(0xffffffffu, s[r].x, off);
-        s[r].y += __shfl_xor_sync(0xffffffffu, s[r].y, off);
-      }
-      if (lane == 0) Tl[(size_t)l * NR + r] = s[r];
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int c = 0; c < LC; c++)
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          s[c][r].x += __shfl_xor_sync(0xffffffffu, s[c][r].x, off);
+          s[c][r].y += __shfl_xor_sync(0xffffffffu, s[c][r].y, off);
+        }
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < LC; c++)
+        if (l0 + c < L.k) {
+#pragma unroll
+          for (int r = 0; r < NR; r++) Tl[(size_t)(l0 + c) * NR + r] = s[c][r];
+        }
     }
   }
 }
 
-// y-pass: one warp per band of 16 rows; lane = (row, parity of the contraction index): a column of a
-// leaf's 16 band rows is 256 contiguous bytes, two columns per warp load.
+// t-pass over the stacked layout (the batched t-pass's own descriptors): the scratch rows of one column
+// cluster are consecutive, 16 per band, and vrow[] holds the pool offset of every row's V column -- so a warp
+// needs no leaf record at all: one band descriptor + 16 row offsets, then the columns as independent 16-byte
+// loads (half-warp = one row: a row's n entries are contiguous; 8 rows x 2 column steps = 16 loads per lane
+// in flight), 4-step reductions, 16 consecutive results.  Warps walk the bands with a grid stride and fetch
+// the next band's descriptors before they contract the current one.
+__device__ __forceinline__ void loads_done(cplx (&p)[8], cplx (&q)[8]) {
+  // the real parts only: a 16-byte load delivers both parts, so ordering x orders the load
+  asm volatile("" : "+d"(p[0].x), "+d"(p[1].x), "+d"(p[2].x), "+d"(p[3].x), "+d"(p[4].x), "+d"(p[5].x), "+d"(p[6].x), "+d"(p[7].x),
+                    "+d"(q[0].x), "+d"(q[1].x), "+d"(q[2].x), "+d"(q[3].x), "+d"(q[4].x), "+d"(q[5].x), "+d"(q[6].x), "+d"(q[7].x));
+}
+__device__ __forceinline__ void loads_done(cplx (&p)[4], cplx (&q)[4]) {
+  asm volatile("" : "+d"(p[0].x), "+d"(p[1].x), "+d"(p[2].x), "+d"(p[3].x), "+d"(q[0].x), "+d"(q[1].x), "+d"(q[2].x), "+d"(q[3].x));
+}
 template <int NR>
-__global__ void __launch_bounds__(V1_THREADS)
+__global__ void __launch_bounds__(V1_THREADS, 3)
+k_hmv1_tb(uint ntband, const HMat::TBand *__restrict__ tband, const unsigned long long *__restrict__ vrow,
+          const cplx *__restrict__ pool, const cplx *__restrict__ xp, cplx *T, uint ntot) {
+  constexpr int RU = NR == 1 ? 8 : 4;        // rows per lane and pass (register budget: RU x NR accumulators)
+  const uint W = gridDim.x * (V1_THREADS / 32), lane = threadIdx.x & 31;
+  uint w = (blockIdx.x * V1_THREADS + threadIdx.x) >> 5;
+  if (w >= ntband) return;
+  const uint i = lane & 15, h = lane >> 4;
+  HMat::TBand B = tband[w];
+  unsigned long long off[8];
+#pragma unroll
+  for (int u = 0; u < 8; u++) off[u] = __ldg(vrow + (size_t)w * 16 + h + 2 * u);
+  while (true) {
+    const uint wn = w + W, wc = wn < ntband ? wn : w;
+    const HMat::TBand Bn = tband[wc];
+    unsigned long long offn[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) offn[u] = __ldg(vrow + (size_t)wc * 16 + h + 2 * u);
+    // padding rows read row 0 of the band (always present, a valid address) and are masked out at the end
+    const unsigned long long off0 = __shfl_sync(0xffffffffu, off[0], 0);
+    double msk[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      msk[u] = off[u] != ~0ull ? 1.0 : 0.0;
+      if (off[u] == ~0ull) off[u] = off0;
+    }
+    const cplx *x = xp + B.c0;
+#pragma unroll
+    for (int pass = 0; pass < 8 / RU; pass++) {
+      if (pass * 2 * RU >= (int)B.rows) break;
+      cplx s[RU][NR];
+#pragma unroll
+      for (int u = 0; u < RU; u++)
+#pragma unroll
+        for (int r = 0; r < NR; r++) s[u][r] = make_double2(0.0, 0.0);
+      for (uint j = i; j < B.n; j += 32) {
+        const bool two = j + 16 < B.n;
+        const uint j2 = two ? j + 16 : j;
+        const double m2 = two ? 1.0 : 0.0;
+        cplx a[RU], a2[RU], xv[NR], xv2[NR];
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+          a[u] = __ldg(pool + off[pass * RU + u] + j);
+          a2[u] = __ldg(pool + off[pass * RU + u] + j2);
+        }
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          xv[r] = x[(size_t)r * ntot + j];
+          const cplx t2 = x[(size_t)r * ntot + j2];
+          xv2[r] = make_double2(t2.x * m2, t2.y * m2);
+        }
+        loads_done(a, a2);
+#pragma unroll
+        for (int u = 0; u < RU; u++)
+#pragma unroll
+          for (int r = 0; r < NR; r++) {
+            cfma(s[u][r], a[u], xv[r]);
+            cfma(s[u][r], a2[u], xv2[r]);
+          }
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int u = 0; u < RU; u++)
+#pragma unroll
+          for (int r = 0; r < NR; r++) {
+            s[u][r].x += __shfl_xor_sync(0xffffffffu, s[u][r].x, o);
+            s[u][r].y += __shfl_xor_sync(0xffffffffu, s[u][r].y, o);
+          }
+      if (i == 0) {
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+          const uint row = h + 2 * (pass * RU + u);
+          if (row < B.rows) {
+#pragma unroll
+            for (int r = 0; r < NR; r++)
+              T[((size_t)w * 16 + row) * NR + r] =
+                  make_double2(s[u][r].x * msk[pass * RU + u], s[u][r].y * msk[pass * RU + u]);
+          }
+        }
+      }
+    }
+    if (wn >= ntband) break;
+    w = wn;
+    B = Bn;
+#pragma unroll
+    for (int u = 0; u < 8; u++) off[u] = offn[u];
+  }
+}
+
+// y-pass: one CTA per band of 16 rows, its dense rounds and low-rank items dealt round-robin to the four
+// warps (12 176 bands at the 16x16 array are not enough warps to fill the chip one warp per band); lane =
+// (row, parity of the contraction index): a column of a leaf's 16 band rows is 256 contiguous bytes, two
+// columns per warp load.  All loads of a round (8 per lane) and of four low-rank items are issued before
+// the first use, and the next round's descriptor is fetched while the current one is contracted.
+template <int NR>
+__global__ void __launch_bounds__(V1_THREADS, 6)
 k_hmv1_band(uint nband, const uint *__restrict__ band_ptr, const HMat::DRound *__restrict__ dround,
             const uint *__restrict__ bfar_ptr, const HMat::FarItem *__restrict__ bfar, const cplx *__restrict__ pool,
             const cplx *__restrict__ T, const cplx *__restrict__ xp, cplx *yp, uint ntot) {
-  const uint b = (blockIdx.x * V1_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (b >= nband) return;
+  constexpr int NW = V1_THREADS / 32;
+  __shared__ cplx red[NW][BAND][NR];
+  const uint b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint i = lane & 15, h = lane >> 4;
   const long long row = (long long)b * BAND + i;
+  const cplx zero = make_double2(0.0, 0.0);
   cplx acc[NR];
 #pragma unroll
-  for (int r = 0; r < NR; r++) acc[r] = make_double2(0.0, 0.0);
-  for (uint d = band_ptr[b]; d < band_ptr[b + 1]; d++) {
-    const HMat::DRound D = dround[d];
-    const long long rl = row - (long long)D.r0;
-    const bool ok = rl >= 0 && rl < (long long)D.m;
-    const cplx *col = pool + D.a_off + (ok ? rl : 0);
-    const cplx *x = xp + D.x_off;
-    for (uint j = h; j < D.cnt; j += 2) {
-      const cplx a = ok ? col[(size_t)j * D.m] : make_double2(0.0, 0.0);
+  for (int r = 0; r < NR; r++) acc[r] = zero;
+  {
+    const uint d1 = band_ptr[b + 1];
+    uint d = band_ptr[b] + warp;
+    HMat::DRound D{};
+    if (d < d1) D = dround[d];
+    while (d < d1) {
+      const uint dn = d + NW;
+      HMat::DRound Dn{};
+      if (dn < d1) Dn = dround[dn];
+      const long long rl = row - (long long)D.r0;
+      const bool ok = rl >= 0 && rl < (long long)D.m;
+      const cplx *col = pool + D.a_off + (ok ? rl : 0);
+      const cplx *x = xp + D.x_off;
+      // unconditional loads from clamped (always valid) addresses, masked afterwards: predicated loads are
+      // scheduled next to their uses, two at a time
+      cplx a[8], xv[NR][8];
+      const uint jmax = D.cnt - 1;
 #pragma unroll
-      for (int r = 0; r < NR; r++) cfma(acc[r], a, x[(size_t)r * ntot + j]);
+      for (int u = 0; u < 8; u++) {
+        const uint j = min(h + 2 * u, jmax);
+        a[u] = __ldg(col + (size_t)j * D.m);
+#pragma unroll
+        for (int r = 0; r < NR; r++) xv[r][u] = __ldg(x + (size_t)r * ntot + j);
+      }
+      loads_done(a);
+#pragma unroll
+      for (int r = 0; r < NR; r++) loads_done(xv[r]);
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const double msk = ok && h + 2 * u <= jmax ? 1.0 : 0.0;
+        const cplx am = make_double2(a[u].x * msk, a[u].y * msk);
+#pragma unroll
+        for (int r = 0; r < NR; r++) cfma(acc[r], am, xv[r][u]);
+      }
+      D = Dn;
+      d = dn;
     }
   }
-  for (uint f = bfar_ptr[b] + h; f < bfar_ptr[b + 1]; f += 2) {
-    const HMat::FarItem it = bfar[f];
-    const long long rl = row - (long long)it.r0;
-    const cplx a = (rl >= 0 && rl < (long long)it.m) ? pool[it.u_off + rl] : make_double2(0.0, 0.0);
+  {
+    // four items (stride 2 NW) per trip; the next trip's item records are fetched before this trip's data
+    const uint f1 = bfar_ptr[b + 1];
+    uint f = bfar_ptr[b] + warp * 2 + h;
+    HMat::FarItem it[4], itn[4];
+    if (f < f1) {
 #pragma unroll
-    for (int r = 0; r < NR; r++) cfma(acc[r], a, T[(size_t)it.t_idx * NR + r]);
+      for (int u = 0; u < 4; u++) it[u] = bfar[min(f + 2 * NW * u, f1 - 1)];
+    }
+    while (f < f1) {
+      const uint fn = f + 8 * NW;
+      if (fn < f1) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) itn[u] = bfar[min(fn + 2 * NW * u, f1 - 1)];
+      }
+      cplx a[4], t[NR][4];
+      double msk[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const long long rl = row - (long long)it[u].r0;
+        const bool ok = f + 2 * NW * u < f1 && rl >= 0 && rl < (long long)it[u].m;
+        msk[u] = ok ? 1.0 : 0.0;
+        a[u] = __ldg(pool + it[u].u_off + (ok ? rl : 0));
+#pragma unroll
+        for (int r = 0; r < NR; r++) t[r][u] = __ldg(T + (size_t)it[u].t_idx * NR + r);
+      }
+      loads_done(a);
+#pragma unroll
+      for (int r = 0; r < NR; r++) loads_done(t[r]);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const cplx am = make_double2(a[u].x * msk[u], a[u].y * msk[u]);
+#pragma unroll
+        for (int r = 0; r < NR; r++) cfma(acc[r], am, t[r][u]);
+      }
+      f = fn;
+#pragma unroll
+      for (int u = 0; u < 4; u++) it[u] = itn[u];
+    }
   }
 #pragma unroll
   for (int r = 0; r < NR; r++) {
     acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, 16);
     acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, 16);
-    if (h == 0 && row < (long long)ntot) yp[(size_t)r * ntot + row] = acc[r];
+    if (h == 0) red[warp][i][r] = acc[r];
+  }
+  __syncthreads();
+  if (warp == 0 && h == 0 && row < (long long)ntot) {
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      cplx sum = red[0][i][r];
+#pragma unroll
+      for (int q = 1; q < NW; q++) { sum.x += red[q][i][r].x; sum.y += red[q][i][r].y; }
+      yp[(size_t)r * ntot + row] = sum;
+    }
   }
 }
 
@@ -1223,11 +1435,16 @@ int hmat_matvec(cudaStream_t st, HMat &H, cplx alpha, const cplx *d_x, cplx *d_y
   k_permute_in<<<gb, 256, 0, st>>>(H.n, nrhs, H.d_perm, d_x, H.d_xp);
   CNLD_CK_LAUNCH();
   const unsigned gt = (unsigned)(((size_t)H.nmvfar * 32 + V1_THREADS - 1) / V1_THREADS);
-  const unsigned gy = (unsigned)(((size_t)H.nband * 32 + V1_THREADS - 1) / V1_THREADS);
+  const unsigned gy = H.nband;          // one CTA per band
+  // grid-stride t-pass: 3 CTAs per SM resident, 8 rounds of CTAs (tail balance), never more warps than bands
+  const unsigned gtb = (unsigned)std::min<size_t>(((size_t)H.ntband * 32 + V1_THREADS - 1) / V1_THREADS, (size_t)148 * 3 * 8);
 #define CNLD_HMV1(NRV)                                                                                             \
   do {                                                                                                             \
-    if (H.nmvfar) {                                                                                                \
+    if (H.nmvfar && !g_hmv_tstack) {                                                                                \
       k_hmv1_t<NRV><<<gt, V1_THREADS, 0, st>>>(H.nmvfar, H.d_mvfar, H.d_leaf, H.d_toff, H.d_pool, H.d_xp, H.d_T, H.n); \
+      CNLD_CK_LAUNCH();                                                                                            \
+    } else if (H.ntband) {                                                                                         \
+      k_hmv1_tb<NRV><<<gtb, V1_THREADS, 0, st>>>(H.ntband, H.d_tband, H.d_vrow, H.d_pool, H.d_xp, H.d_T, H.n);    \
       CNLD_CK_LAUNCH();                                                                                            \
     }                                                                                                              \
     k_hmv1_band<NRV><<<gy, V1_THREADS, 0, st>>>(H.nband, H.d_band_ptr, H.d_dround, H.d_bfar_ptr, H.d_bfar, H.d_pool,  \
