@@ -537,9 +537,10 @@ def db_append_imp_resp(file, times, h, threads=8):
 
 def db_counters():
     """Node rows written as pages / through SQL, node indexes generated directly / by CREATE INDEX (this process)."""
-    out = np.zeros(6, np.uint64)
+    out = np.zeros(8, np.uint64)
     check(lib().cnld_b200_db_counters(ptr(out)))
-    return dict(zip(('rows_paged', 'rows_sql', 'index_direct', 'index_sql', 'imp_rows_paged', 'imp_rows_sql'), (int(v) for v in out)))
+    return dict(zip(('rows_paged', 'rows_sql', 'index_direct', 'index_sql', 'imp_rows_paged', 'imp_rows_sql', 'patch_rows_paged',
+                     'patch_rows_sql'), (int(v) for v in out)))
 
 
 ADMIS = {'2': 0, 'max': 1, 'sphere': 2, '2min': 3, '2_min': 3}

@@ -627,6 +627,39 @@ int build_node_index(const char *file, const std::vector<NodeBlock> &blocks, int
   });
 }
 
+// patch_to_patch_freq_resp (database.py:22-29): rows (source_patch, dest_patch, frequency, wavenumber,
+// displacement_real, displacement_imag, time_solve) in (frequency, source, dest) order; one task per
+// frequency.  Its index (source_patch, dest_patch, frequency) has the shape of the node index with the
+// destination patch in the place of the node: build_node_index with N = P.
+int append_patch_rows(const char *file, uint32_t root, uint32_t nf, const double *freqs, const double *wavenums, uint32_t P,
+                      const double *x_patch, const double *times, int threads, uint64_t *first_rowid) {
+  if (!nf || !P) return 1;
+  bool fmt4 = false;
+  if (int rc = file_format4(file, &fmt4)) return rc;
+  std::vector<Enc> ep(P), ef((size_t)nf * 3);
+  for (uint32_t s = 0; s < P; s++) ep[s].len = (uint8_t)enc_int(s, fmt4, &ep[s].type, ep[s].data);
+  for (uint32_t i = 0; i < nf; i++) {
+    ef[3 * i].len = (uint8_t)enc_real(freqs[i], fmt4, &ef[3 * i].type, ef[3 * i].data);
+    ef[3 * i + 1].len = (uint8_t)enc_real(wavenums[i], fmt4, &ef[3 * i + 1].type, ef[3 * i + 1].data);
+    ef[3 * i + 2].len = (uint8_t)enc_real(times ? times[i] : 0.0, fmt4, &ef[3 * i + 2].type, ef[3 * i + 2].data);
+  }
+  const size_t per = (size_t)P * P;
+  return append_rows_impl(file, root, nf, per, threads, first_rowid, [&](size_t i, size_t j, uint8_t *out) -> size_t {
+    const Enc &e_s = ep[j / P], &e_d = ep[j % P], &e_f = ef[3 * i], &e_w = ef[3 * i + 1], &e_t = ef[3 * i + 2];
+    const double *x = x_patch + 2 * (i * per + j);
+    out[0] = 8; out[1] = e_s.type; out[2] = e_d.type; out[3] = e_f.type; out[4] = e_w.type; out[7] = e_t.type;
+    uint8_t *b = out + 8;
+    memcpy(b, e_s.data, e_s.len); b += e_s.len;
+    memcpy(b, e_d.data, e_d.len); b += e_d.len;
+    memcpy(b, e_f.data, e_f.len); b += e_f.len;
+    memcpy(b, e_w.data, e_w.len); b += e_w.len;
+    b += enc_real(x[0], fmt4, &out[5], b);
+    b += enc_real(x[1], fmt4, &out[6], b);
+    memcpy(b, e_t.data, e_t.len); b += e_t.len;
+    return (size_t)(b - out);
+  });
+}
+
 // patch_to_patch_imp_resp (database.py:47-53): rows (source_patch, dest_patch, time, displacement) in
 // (source, dest, time) order -- which is also the order of its index (source_patch, dest_patch, time) when
 // the times ascend, so the index entries are the rows' keys with their rowids.

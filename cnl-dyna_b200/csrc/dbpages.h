@@ -23,6 +23,11 @@ int append_node_rows(const char *file, uint32_t root_page, uint32_t nf, const do
 // index on (source_patch, node_id, frequency) of the rows the blocks describe; *root_page = root of the new b-tree
 int build_node_index(const char *file, const std::vector<NodeBlock> &blocks, int threads, uint32_t *root_page);
 
+// rows of patch_to_patch_freq_resp from x_patch[nf][P][P] (re, im), times[nf] (nullable: 0); its index
+// (source_patch, dest_patch, frequency) = build_node_index with blocks whose N is P
+int append_patch_rows(const char *file, uint32_t root_page, uint32_t nf, const double *freqs, const double *wavenums,
+                      uint32_t P, const double *x_patch, const double *times, int threads, uint64_t *first_rowid);
+
 // rows (source_patch, dest_patch, time, displacement) of patch_to_patch_imp_resp from h[P][P][nt], and the
 // index on (source_patch, dest_patch, time) of exactly those rows (times strictly ascending)
 int append_imp_resp_rows(const char *file, uint32_t root_page, uint32_t P, uint32_t nt, const double *times, const double *h,

@@ -176,9 +176,12 @@ std::string scratch_dir(const char *file) {
 struct BulkState {
   bool covered = false;                              // every row of the node table is described by `blocks`
   std::vector<cnld::dbpages::NodeBlock> blocks;
+  bool pcovered = false;                             // the same for patch_to_patch_freq_resp (blocks with N = P)
+  std::vector<cnld::dbpages::NodeBlock> pblocks;
 };
 std::mutex g_bulk_mutex;
-std::atomic<unsigned long long> g_rows_paged{0}, g_rows_sql{0}, g_index_direct{0}, g_index_sql{0}, g_imp_paged{0}, g_imp_sql{0};
+std::atomic<unsigned long long> g_rows_paged{0}, g_rows_sql{0}, g_index_direct{0}, g_index_sql{0}, g_imp_paged{0}, g_imp_sql{0},
+    g_patch_paged{0}, g_patch_sql{0};
 std::map<std::string, BulkState> g_bulk;
 std::string canonical(const char *file) {
   char buf[PATH_MAX];
@@ -190,36 +193,91 @@ bool sql_only() {
 }
 const char *NODE_ROOT_SQL = "SELECT rootpage FROM sqlite_master WHERE type='table' AND name='patch_to_node_freq_resp'";
 const char *NODE_NINDEX_SQL = "SELECT count(*) FROM sqlite_master WHERE type='index' AND tbl_name='patch_to_node_freq_resp'";
+const char *PATCH_ROOT_SQL = "SELECT rootpage FROM sqlite_master WHERE type='table' AND name='patch_to_patch_freq_resp'";
+const char *PATCH_NINDEX_SQL = "SELECT count(*) FROM sqlite_master WHERE type='index' AND tbl_name='patch_to_patch_freq_resp'";
 
-// node rows of a block as b-tree pages, under SQLite's exclusive lock.  0 done, 1 not applicable, -1 error
-int append_node_pages(const char *file, cnld_uint nf, const double *freqs, const double *wavenums, cnld_uint P, cnld_uint N,
-                      const cnld_field *x_node, const double *nodes, int threads) {
-  if (sql_only()) return 1;
+int register_index(const char *file, const char *name, const char *table, uint32_t root, const char *create_sql);
+
+// node rows (x_node may be null) and patch rows of a block as b-tree pages, under SQLite's exclusive lock.
+// *node_done / *patch_done: written as pages; otherwise the caller inserts them through SQL.  -1 error
+int append_block_pages(const char *file, cnld_uint nf, const double *freqs, const double *wavenums, cnld_uint P, cnld_uint N,
+                       const cnld_field *x_node, const double *nodes, const cnld_field *x_patch, const double *times, int threads,
+                       bool *node_done, bool *patch_done) {
+  *node_done = *patch_done = false;
+  if (sql_only()) return 0;
   Db lock;
   if (lock.open(file)) return -1;
   if (lock.exec("BEGIN EXCLUSIVE")) return -1;
-  long long root = 0, nindex = 0;
-  if (query_int(lock, NODE_ROOT_SQL, &root) || query_int(lock, NODE_NINDEX_SQL, &nindex)) return -1;
-  int rc = 1;
-  uint64_t first = 0;
-  if (root >= 2 && nindex == 0)
+  long long root = 0, nindex = 0, proot = 0, pnindex = 0;
+  if (query_int(lock, NODE_ROOT_SQL, &root) || query_int(lock, NODE_NINDEX_SQL, &nindex) || query_int(lock, PATCH_ROOT_SQL, &proot) ||
+      query_int(lock, PATCH_NINDEX_SQL, &pnindex))
+    return -1;
+  int rc = 1, prc = 1;
+  uint64_t first = 0, pfirst = 0;
+  if (x_node && root >= 2 && nindex == 0)
     rc = cnld::dbpages::append_node_rows(file, (uint32_t)root, nf, freqs, wavenums, P, N, (const double *)x_node, nodes,
                                          threads, &first);
+  if (rc >= 0 && proot >= 2 && pnindex == 0)
+    prc = cnld::dbpages::append_patch_rows(file, (uint32_t)proot, nf, freqs, wavenums, P, (const double *)x_patch, times, threads, &pfirst);
   lock.exec("ROLLBACK");      // nothing was written through this connection; its cache dies with it
-  if (rc == 0) g_rows_paged += (unsigned long long)nf * P * N;
+  if (rc < 0 || prc < 0) return -1;
+  *node_done = rc == 0;
+  *patch_done = prc == 0;
+  if (*node_done) g_rows_paged += (unsigned long long)nf * P * N;
+  if (*patch_done) g_patch_paged += (unsigned long long)nf * P * P;
   std::lock_guard<std::mutex> g(g_bulk_mutex);
   auto it = g_bulk.find(canonical(file));
   if (it != g_bulk.end()) {
-    if (rc == 0) {
-      cnld::dbpages::NodeBlock b;
-      b.first_rowid = first; b.nf = nf; b.P = P; b.N = N;
-      b.freqs.assign(freqs, freqs + nf);
-      it->second.blocks.push_back(std::move(b));
-    } else {
+    cnld::dbpages::NodeBlock b;
+    b.nf = nf; b.P = P;
+    b.freqs.assign(freqs, freqs + nf);
+    if (*node_done) {
+      b.first_rowid = first; b.N = N;
+      it->second.blocks.push_back(b);
+    } else if (x_node) {
       it->second.covered = false;                    // these rows go in through SQL
     }
+    if (*patch_done) {
+      b.first_rowid = pfirst; b.N = P;
+      it->second.pblocks.push_back(b);
+    } else {
+      it->second.pcovered = false;
+    }
   }
-  return rc;
+  return 0;
+}
+
+// index (first two integer columns, frequency) of a table whose rows the blocks describe completely, generated
+// from the descriptors and registered under `name`.  1: done, 0: not applicable (caller uses CREATE INDEX), -1 error
+int direct_index(const char *file, std::vector<cnld::dbpages::NodeBlock> &blocks, const char *table, const char *name,
+                 const char *create_sql) {
+  if (blocks.empty() || sql_only()) return 0;
+  std::sort(blocks.begin(), blocks.end(), [](const cnld::dbpages::NodeBlock &a, const cnld::dbpages::NodeBlock &b) { return a.first_rowid < b.first_rowid; });
+  uint64_t next = 1;
+  for (const auto &b : blocks) {
+    if (b.first_rowid != next) return 0;
+    next += (uint64_t)b.nf * b.P * b.N;
+  }
+  uint32_t root = 0;
+  {
+    Db lock;
+    if (lock.open(file) || lock.exec("BEGIN EXCLUSIVE")) return -1;
+    char q1[200], q2[200];
+    snprintf(q1, sizeof(q1), "SELECT max(rowid) FROM %s", table);
+    snprintf(q2, sizeof(q2), "SELECT count(*) FROM sqlite_master WHERE type='index' AND tbl_name='%s'", table);
+    long long maxrow = 0, nindex = 0;
+    if (query_int(lock, q1, &maxrow) || query_int(lock, q2, &nindex)) return -1;
+    int rc = 1;
+    if ((uint64_t)maxrow + 1 == next && nindex == 0) {
+      int threads = (int)std::thread::hardware_concurrency();
+      if (threads > 32) threads = 32;
+      rc = cnld::dbpages::build_node_index(file, blocks, threads, &root);
+    }
+    lock.exec("ROLLBACK");
+    if (rc < 0) return -1;
+    if (rc != 0) return 0;
+  }
+  return register_index(file, name, table, root, create_sql) ? -1 : 1;
 }
 
 // the schema row CREATE INDEX would have written for a b-tree that already exists, and a new schema cookie
@@ -250,16 +308,20 @@ int cnld_b200_db_append_block(const char *file, cnld_uint nf, const double *freq
                               const double *nodes, const cnld_uint *job_ids, int fast) {
   if (!file || !freqs || !wavenums || !x_patch) { set_error("db_append_block: null argument"); return -1; }
   if (x_node && !nodes) { set_error("db_append_block: node coordinates are needed with x_node"); return -1; }
-  if (x_node && fast > 1) {
-    // node rows first, as pages; the patch rows and the progress marks follow in the SQL transaction below, so
-    // a frequency is marked complete only when its node rows are in the file
-    const int rc = append_node_pages(file, nf, freqs, wavenums, P, N, x_node, nodes, fast);
-    if (rc < 0) return -1;
-    if (rc == 0) x_node = nullptr;
-  } else if (x_node) {
+  bool patch_paged = false;
+  if (fast > 1) {
+    // node and patch rows first, as pages; the progress marks (and whatever the page path could not take)
+    // follow in the SQL transaction below, so a frequency is marked complete only when its rows are in the file
+    bool node_paged = false;
+    if (append_block_pages(file, nf, freqs, wavenums, P, N, x_node, nodes, x_patch, times, fast, &node_paged, &patch_paged)) return -1;
+    if (node_paged) x_node = nullptr;
+  } else {
     std::lock_guard<std::mutex> g(g_bulk_mutex);
     auto it = g_bulk.find(canonical(file));
-    if (it != g_bulk.end()) it->second.covered = false;
+    if (it != g_bulk.end()) {
+      if (x_node) it->second.covered = false;
+      it->second.pcovered = false;
+    }
   }
   Db db;
   if (db.open(file)) return -1;
@@ -309,7 +371,8 @@ int cnld_b200_db_append_block(const char *file, cnld_uint nf, const double *freq
   int rc = 0;
   do {
     if (A->prepare(db.con, "INSERT INTO patch_to_patch_freq_resp VALUES (?,?,?,?,?,?,?)", -1, &pp.s, nullptr) != SQLITE_OK) { rc = -1; break; }
-    for (cnld_uint i = 0; i < nf && !rc; i++) {
+    if (!patch_paged) g_patch_sql += (unsigned long long)nf * P * P;
+    for (cnld_uint i = 0; i < nf && !rc && !patch_paged; i++) {
       const cnld_field *xp = x_patch + (size_t)i * P * P;
       for (cnld_uint s = 0; s < P && !rc; s++)
         for (cnld_uint d = 0; d < P; d++) {
@@ -358,12 +421,16 @@ int cnld_b200_db_begin_bulk(const char *file) {
   Db db;
   if (db.open(file)) return -1;
   if (db.exec("DROP INDEX IF EXISTS patch_to_patch_freq_resp_index") || db.exec("DROP INDEX IF EXISTS patch_to_node_freq_resp_index")) return -1;
-  long long maxrow = 0;
-  if (query_int(db, "SELECT max(rowid) FROM patch_to_node_freq_resp", &maxrow)) return -1;
+  long long maxrow = 0, pmaxrow = 0;
+  if (query_int(db, "SELECT max(rowid) FROM patch_to_node_freq_resp", &maxrow) ||
+      query_int(db, "SELECT max(rowid) FROM patch_to_patch_freq_resp", &pmaxrow))
+    return -1;
   std::lock_guard<std::mutex> g(g_bulk_mutex);
   BulkState &st = g_bulk[canonical(file)];
   st.blocks.clear();
+  st.pblocks.clear();
   st.covered = maxrow == 0;          // rows of an earlier run are not described: finish indexes through SQL then
+  st.pcovered = pmaxrow == 0;
   return 0;
 }
 int cnld_b200_db_finish(const char *file) {
@@ -374,41 +441,17 @@ int cnld_b200_db_finish(const char *file) {
     if (it != g_bulk.end()) { st = std::move(it->second); g_bulk.erase(it); }
   }
   const char *node_index_sql = "CREATE INDEX patch_to_node_freq_resp_index ON patch_to_node_freq_resp (source_patch, node_id, frequency)";
-  // the node index straight from the block descriptors when they describe the whole table
-  bool direct = st.covered && !st.blocks.empty() && !sql_only();
-  if (direct) {
-    std::sort(st.blocks.begin(), st.blocks.end(), [](const cnld::dbpages::NodeBlock &a, const cnld::dbpages::NodeBlock &b) { return a.first_rowid < b.first_rowid; });
-    uint64_t next = 1;
-    for (const auto &b : st.blocks) {
-      if (b.first_rowid != next) { direct = false; break; }
-      next += (uint64_t)b.nf * b.P * b.N;
-    }
-    if (direct) {
-      Db lock;
-      if (lock.open(file) || lock.exec("BEGIN EXCLUSIVE")) return -1;
-      long long maxrow = 0, nindex = 0, count_ok = 0;
-      if (query_int(lock, "SELECT max(rowid) FROM patch_to_node_freq_resp", &maxrow) || query_int(lock, NODE_NINDEX_SQL, &nindex)) return -1;
-      (void)count_ok;
-      uint32_t root = 0;
-      int rc = 1;
-      if ((uint64_t)maxrow + 1 == next && nindex == 0) {
-        int threads = (int)std::thread::hardware_concurrency();
-        if (threads > 32) threads = 32;
-        rc = cnld::dbpages::build_node_index(file, st.blocks, threads, &root);
-      }
-      lock.exec("ROLLBACK");
-      if (rc < 0) return -1;
-      direct = rc == 0;
-      if (direct) {
-        g_index_direct++;
-        if (register_index(file, "patch_to_node_freq_resp_index", "patch_to_node_freq_resp", root, node_index_sql)) return -1;
-      }
-    }
-  }
+  const char *patch_index_sql = "CREATE INDEX patch_to_patch_freq_resp_index ON patch_to_patch_freq_resp (source_patch, dest_patch, frequency)";
+  // the indexes straight from the block descriptors when they describe the whole table
+  int direct = st.covered ? direct_index(file, st.blocks, "patch_to_node_freq_resp", "patch_to_node_freq_resp_index", node_index_sql) : 0;
+  if (direct < 0) return -1;
+  int pdirect = st.pcovered ? direct_index(file, st.pblocks, "patch_to_patch_freq_resp", "patch_to_patch_freq_resp_index", patch_index_sql) : 0;
+  if (pdirect < 0) return -1;
+  if (direct) g_index_direct++;
   Db db;
   if (db.open(file)) return -1;
   if (db.exec("PRAGMA cache_size=-1048576")) return -1;
-  if (db.exec("CREATE INDEX IF NOT EXISTS patch_to_patch_freq_resp_index ON patch_to_patch_freq_resp (source_patch, dest_patch, frequency)")) return -1;
+  if (!pdirect && db.exec("CREATE INDEX IF NOT EXISTS patch_to_patch_freq_resp_index ON patch_to_patch_freq_resp (source_patch, dest_patch, frequency)")) return -1;
   if (!direct) {
     if (db.exec("CREATE INDEX IF NOT EXISTS patch_to_node_freq_resp_index ON patch_to_node_freq_resp (source_patch, node_id, frequency)")) return -1;
     g_index_sql++;
@@ -483,12 +526,14 @@ int cnld_b200_db_append_imp_resp(const char *file, cnld_uint P, cnld_uint nt, co
   snprintf(sql, sizeof(sql), "CREATE INDEX IF NOT EXISTS %s", index_sql + strlen("CREATE INDEX "));
   return db.exec(sql) ? -1 : 0;
 }
-/* out[6]: node rows written as pages / through SQL, node indexes generated from descriptors / by CREATE INDEX,
- * impulse-response rows written as pages / through SQL (this process, since load) */
+/* out[8]: node rows written as pages / through SQL, node indexes generated from descriptors / by CREATE INDEX,
+ * impulse-response rows written as pages / through SQL, patch rows written as pages / through SQL (this
+ * process, since load) */
 int cnld_b200_db_counters(unsigned long long *out) {
   if (!out) { set_error("db_counters: null argument"); return -1; }
   out[0] = g_rows_paged; out[1] = g_rows_sql; out[2] = g_index_direct; out[3] = g_index_sql;
   out[4] = g_imp_paged; out[5] = g_imp_sql;
+  out[6] = g_patch_paged; out[7] = g_patch_sql;
   return 0;
 }
 

@@ -333,7 +333,7 @@ int cnld_b200_db_append_block(const char *file, cnld_uint nf, const double *freq
                               const cnld_field *x_node, const double *nodes, const cnld_uint *job_ids, int fast);
 /* drop the two frequency-response indexes before a bulk load / (re)build them after it.
  * With fast > 1, cnld_b200_db_append_block writes the node rows (cnld/database.py:38-45, 2.13 M per
- * frequency at the 4x4 array) as b-tree pages in SQLite's file format instead of through SQL
+ * frequency at the 4x4 array) and the patch rows (database.py:22-29) as b-tree pages in SQLite's file format instead of through SQL
  * (csrc/dbpages.cpp: records encoded by `fast` threads, pages appended to the file, interior levels
  * rebuilt; applies when the table has no index, i.e. inside the bulk bracket, and the file is a plain
  * rollback-journal database); cnld_b200_db_finish then generates the node index, already sorted, from the
@@ -347,9 +347,9 @@ int cnld_b200_db_finish(const char *file);
  * index are written as pages by `threads` threads; otherwise prepared statements in one transaction. */
 int cnld_b200_db_append_imp_resp(const char *file, cnld_uint P, cnld_uint nt, const double *times, const double *h,
                                  int threads);
-/* out[6]: node rows written as pages, node rows written through SQL, node indexes generated from
- * descriptors, node indexes built by CREATE INDEX, impulse-response rows written as pages / through SQL
- * (this process) */
+/* out[8]: node rows written as pages, node rows written through SQL, node indexes generated from
+ * descriptors, node indexes built by CREATE INDEX, impulse-response rows written as pages / through SQL,
+ * patch rows written as pages / through SQL (this process) */
 int cnld_b200_db_counters(unsigned long long *out);
 
 /* ---- microbenchmarks used for roofline denominators ----------------------- */

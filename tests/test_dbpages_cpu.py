@@ -50,7 +50,10 @@ def _dump(path):
         plan=con.execute('EXPLAIN QUERY PLAN SELECT rowid FROM patch_to_node_freq_resp WHERE source_patch=0 AND '
                          'node_id=2 ORDER BY frequency').fetchall(),
         ordered=con.execute('SELECT rowid FROM patch_to_node_freq_resp ORDER BY source_patch, node_id, frequency').fetchall(),
-        patch=con.execute('SELECT * FROM patch_to_patch_freq_resp ORDER BY rowid').fetchall(),
+        patch=con.execute('SELECT rowid, * FROM patch_to_patch_freq_resp ORDER BY rowid').fetchall(),
+        patch_ordered=con.execute('SELECT rowid FROM patch_to_patch_freq_resp ORDER BY source_patch, dest_patch, frequency').fetchall(),
+        patch_plan=con.execute('EXPLAIN QUERY PLAN SELECT displacement_real FROM patch_to_patch_freq_resp WHERE source_patch=0 AND '
+                               'dest_patch=0 ORDER BY frequency').fetchall(),
         progress=con.execute('SELECT * FROM progress ORDER BY job_id').fetchall(),
         types=con.execute('SELECT typeof(frequency), typeof(z), typeof(displacement_real), count(*) FROM '
                           'patch_to_node_freq_resp GROUP BY 1, 2, 3 ORDER BY 1, 2, 3').fetchall())
@@ -97,8 +100,11 @@ def test_pages_equal_sql_path(tmp_path, monkeypatch, page_size, shape):
         out[mode] = _dump(f)
     rows = 2 * nf * P * N
     # the page path was really taken (no silent fallback), and the SQL path is really SQL
-    assert used['pages'] == dict(rows_paged=rows, rows_sql=0, index_direct=1, index_sql=0, imp_rows_paged=0, imp_rows_sql=0)
-    assert used['sql'] == dict(rows_paged=0, rows_sql=rows, index_direct=0, index_sql=1, imp_rows_paged=0, imp_rows_sql=0)
+    prow = 2 * nf * P * P
+    assert used['pages'] == dict(rows_paged=rows, rows_sql=0, index_direct=1, index_sql=0, imp_rows_paged=0, imp_rows_sql=0,
+                                 patch_rows_paged=prow, patch_rows_sql=0)
+    assert used['sql'] == dict(rows_paged=0, rows_sql=rows, index_direct=0, index_sql=1, imp_rows_paged=0, imp_rows_sql=0,
+                               patch_rows_paged=0, patch_rows_sql=prow)
     a, b = out['pages'], out['sql']
     assert a['check'] == [('ok',)] and b['check'] == [('ok',)]
     assert len(a['rows']) == 2 * nf * P * N and _same_rows(a['rows'], b['rows'])
@@ -109,6 +115,7 @@ def test_pages_equal_sql_path(tmp_path, monkeypatch, page_size, shape):
     assert a['ordered'] == b['ordered']
     assert a['types'] == b['types']           # integral REALs read back as 'real' in both
     assert _same_rows(a['patch'], b['patch']) and a['progress'] == b['progress']
+    assert a['patch_ordered'] == b['patch_ordered'] and 'patch_to_patch_freq_resp_index' in a['patch_plan'][0][-1]
 
 
 def test_pages_after_sql_rows_and_resume(tmp_path, monkeypatch):
@@ -125,11 +132,12 @@ def test_pages_after_sql_rows_and_resume(tmp_path, monkeypatch):
     _write(fa, blocks[3:], 'pages', monkeypatch)
     c1 = _lib.db_counters()
     assert {k: c1[k] - c0[k] for k in c0} == dict(rows_paged=3 * nf * P * N, rows_sql=0, index_direct=0, index_sql=2, imp_rows_paged=0,
-                                                  imp_rows_sql=0)
+                                                  imp_rows_sql=0, patch_rows_paged=3 * nf * P * P, patch_rows_sql=0)
     _write(fb, blocks, 'sql', monkeypatch)
     a, b = _dump(fa), _dump(fb)
     assert a['check'] == [('ok',)]
     assert _same_rows(a['rows'], b['rows']) and a['ordered'] == b['ordered'] and a['index'] == b['index']
+    assert _same_rows(a['patch'], b['patch']) and a['patch_ordered'] == b['patch_ordered']
     # a root that is still a leaf with cells when the page writer arrives
     fc, fd = _make(str(tmp_path / 'c.db')), _make(str(tmp_path / 'd.db'))
     tiny = [_block(1, 1, 3, 9)]
