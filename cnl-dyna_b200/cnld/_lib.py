@@ -85,6 +85,17 @@ def lib():
         L.cnld_b200_fir_push.argtypes = [vp, vp]
         L.cnld_b200_fir_base.argtypes = [vp, f64, vp]
         L.cnld_b200_fir_add.argtypes = [vp, vp, f64, vp]
+        L.cnld_b200_td_create.restype = vp
+        L.cnld_b200_td_create.argtypes = [C.c_int, u32, u32, vp, u32, vp, vp] + [f64] * 7 + [C.c_int]
+        L.cnld_b200_td_destroy.argtypes = [vp]
+        L.cnld_b200_td_reset.argtypes = [vp]
+        L.cnld_b200_td_step.argtypes = [vp, u32]
+        L.cnld_b200_td_current_step.argtypes = [vp]
+        L.cnld_b200_td_current_step.restype = u32
+        L.cnld_b200_td_taps.argtypes = [vp]
+        L.cnld_b200_td_taps.restype = u32
+        L.cnld_b200_td_state.argtypes = [vp, u32, u32] + [vp] * 6
+        L.cnld_b200_td_info.argtypes = [vp, u32, u32, vp, vp]
         L.cnld_b200_fft_to_fir.argtypes = [C.c_int, u32, vp, u32, vp, u32, C.c_int, vp, vp]
         L.cnld_b200_comm_create.restype = vp
         L.cnld_b200_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
@@ -424,6 +435,64 @@ class FirTable:
         x = np.empty(self.ndest)
         check(lib().cnld_b200_fir_add(self._h, ptr(_c(p_row, np.float64)), float(dt), ptr(x)))
         return x
+
+
+class TimeDomainSolver:
+    """FixedStepSolver's arithmetic on one GPU (opaque cnld_td; simulation.pyx:297-555): fir[P, P, nfir] on the
+    step dt, v[nt, P] on the solver's time grid.  `step(n)` advances n samples without a host round trip."""
+    STATE = ('x', 'u', 'p_es', 'p_cont_spr', 'p_cont_dmp', 'p_tot')
+
+    def __init__(self, fir, v, gap_eff, dt, k, n, x0, lmbd, atol=1e-10, maxiter=5, e0=None, device=0):
+        if e0 is None:
+            from scipy.constants import epsilon_0 as e0
+        fir = _c(fir, np.float64)
+        v = _c(v, np.float64)
+        gap_eff = _c(gap_eff, np.float64)
+        assert fir.ndim == 3 and fir.shape[0] == fir.shape[1] and v.ndim == 2 and v.shape[1] == fir.shape[0] == len(gap_eff)
+        self.npatch, self.nfir, self.nt = fir.shape[0], fir.shape[2], v.shape[0]
+        self._h = lib().cnld_b200_td_create(device, self.npatch, self.nfir, ptr(fir), self.nt, ptr(v), ptr(gap_eff), float(dt),
+                                            float(e0), float(k), float(n), float(x0), float(lmbd), float(atol), int(maxiter))
+        if not self._h:
+            raise Cnldb200Error(lib().cnld_b200_last_error().decode())
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().cnld_b200_td_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def current_step(self):
+        return int(lib().cnld_b200_td_current_step(self._h))
+
+    @property
+    def taps(self):
+        """Taps a step streams: trailing taps that are zero for every patch pair are skipped."""
+        return int(lib().cnld_b200_td_taps(self._h))
+
+    def reset(self):
+        check(lib().cnld_b200_td_reset(self._h))
+
+    def step(self, nsteps=1):
+        check(lib().cnld_b200_td_step(self._h, int(nsteps)))
+
+    def state(self, i0=0, i1=None, into=None):
+        """Samples [i0, i1) of every state array -> dict of [i1 - i0, P] arrays (or written into `into`'s rows)."""
+        i1 = self.current_step if i1 is None else i1
+        out = {}
+        for key in self.STATE:
+            out[key] = into[key][i0:i1] if into is not None else np.empty((i1 - i0, self.npatch))
+            assert out[key].flags.c_contiguous
+        check(lib().cnld_b200_td_state(self._h, i0, i1, *[ptr(out[key]) for key in self.STATE]))
+        return out
+
+    def info(self, s0=1, s1=None):
+        s1 = self.current_step if s1 is None else s1
+        err = np.empty(max(s1 - s0, 0))
+        it = np.empty(max(s1 - s0, 0), dtype=np.int32)
+        check(lib().cnld_b200_td_info(self._h, s0, s1, ptr(err), ptr(it)))
+        return err, it
 
 
 def fft_to_fir(freqs, s, interp=1, use_kkr=True, device=0):

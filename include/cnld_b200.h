@@ -300,6 +300,36 @@ int cnld_b200_fir_push(cnld_fir *f, const double *p_row);
 int cnld_b200_fir_base(cnld_fir *f, double dt, double *x);
 int cnld_b200_fir_add(cnld_fir *f, const double *p_row, double dt, double *x);
 
+/* ---- fixed-step time-domain solver (simulation.pyx:459-503) ---------------------
+ * FixedStepSolver (cnld/simulation.pyx:297-555) with the table, the total-pressure history and all state arrays
+ * resident on the device: a step is one pass over the table (the blind estimate = `_fir_conv_base`, :447-457 /
+ * :400-404) followed by the fixed-point iterations on the current sample (:430-445, :466-498) in one CTA; no host
+ * round trip between steps.
+ *   fir[npatch][npatch][nfir]  table already resampled to the step dt (the constructor's interp1d, :311-314)
+ *   v[nt][npatch]              drive on the solver's time grid (StateDB, :108-126); gap_eff[npatch]
+ *   e0 = vacuum permittivity (scipy.constants.epsilon_0 of the caller), electrostatic pressure p_es_pp (:17-21)
+ *   k, n, x0 contact spring (:80-88), lmbd contact damper (:91-99), atol / maxiter of the fixed point (:303)
+ * create() sets the initial state (:335, current_step = 1).  The contact pressures reproduce np.vectorize's
+ * output-type rule (truncation toward zero whenever patch 0 is out of contact), see csrc/firconv.cu. */
+typedef struct cnld_td cnld_td;
+cnld_td *cnld_b200_td_create(int device, cnld_uint npatch, cnld_uint nfir, const double *fir, cnld_uint nt, const double *v,
+                             const double *gap_eff, double dt, double e0, double k, double n, double x0, double lmbd,
+                             double atol, int maxiter);
+void cnld_b200_td_destroy(cnld_td *t);
+/* FixedStepSolver.reset (:516-527) */
+int cnld_b200_td_reset(cnld_td *t);
+/* nsteps x FixedStepSolver.step (:459-503); error if the time grid ends first */
+int cnld_b200_td_step(cnld_td *t, cnld_uint nsteps);
+cnld_uint cnld_b200_td_current_step(const cnld_td *t);
+/* taps a step's convolution reads: 1 + the last tap that is nonzero in any patch pair (a causal, Kramers-Kronig
+ * table is exactly zero in its second half; those taps are never streamed) */
+cnld_uint cnld_b200_td_taps(const cnld_td *t);
+/* samples [i0, i1) of x, u, p_es, p_cont_spr, p_cont_dmp, p_tot -> HOST [i1 - i0][npatch] each (nullable) */
+int cnld_b200_td_state(cnld_td *t, cnld_uint i0, cnld_uint i1, double *x, double *u, double *p_es, double *p_cont_spr,
+                       double *p_cont_dmp, double *p_tot);
+/* FixedStepSolver.error / .iters (:383-389) of the steps that produced samples [s0, s1), s0 >= 1 (HOST, nullable) */
+int cnld_b200_td_info(cnld_td *t, cnld_uint s0, cnld_uint s1, double *error, int *iters);
+
 /* ---- multi-GPU plumbing (one process per GPU) ------------------------------------------------------------
  * Replaces the reference's process pool + write lock (cnld/scripts/generate_db.py:229-242): frequencies are
  * sharded over ranks, nothing is exchanged inside a frequency; rank 0's frequency-independent setup is

@@ -35,6 +35,8 @@ class _Factory:
 
 
 def _namedlist(typename, fields, **kw):
+    if isinstance(fields, str):                          # 'a b c' with one common default (simulation.pyx:105)
+        fields = OrderedDict((n, kw.get('default')) for n in fields.replace(',', ' ').split())
     fields = OrderedDict(fields) if not isinstance(fields, OrderedDict) else fields
 
     def __init__(self, *args, **kwargs):
@@ -257,9 +259,98 @@ def golden_fir_conv():
     print('fir_conv', len(cases), 'cases')
 
 
+def _reference_simulation_module():
+    """cnld/simulation.pyx executed as plain Python: the two `cimport` lines dropped and the typed signature /
+    C declarations of fir_conv_cy stripped (as in golden_fir_conv); every class and function body -- StateDB,
+    FixedStepSolver, the contact closures with their np.vectorize wrappers -- is the reference's own text."""
+    import re
+    src = open(os.path.join(REF, 'cnld', 'simulation.pyx')).read()
+    src = re.sub(r'^cimport .*\n', '', src, flags=re.M)
+    src = re.sub(r'cpdef np\.ndarray fir_conv_cy\([^)]*\):', 'def fir_conv_cy(fir, p, dt, offset):', src, flags=re.S)
+    for name in ('nsrc = fir.shape[0]', 'ndest = fir.shape[1]', 'nfir = fir.shape[2]', 'nsample = p.shape[0]'):
+        src = src.replace('    cdef int ' + name, '    ' + name)
+    src = src.replace('    cdef double[:] x = np.zeros(ndest, dtype=np.float64)', '    x = np.zeros(ndest, dtype=np.float64)')
+    src = re.sub(r'^\s*cdef .*\n', '', src, flags=re.M)
+    for name in ('cnld.compensation', 'cnld.database'):   # imported at module level, not used by FixedStepSolver.step
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+            setattr(cnld, name.split('.')[1], sys.modules[name])
+    mod = types.ModuleType('cnld.simulation')
+    exec(compile(src, os.path.join(REF, 'cnld', 'simulation.pyx'), 'exec'), mod.__dict__)
+    return mod
+
+
+def td_case(case):
+    """Inputs of the time-domain golden cases: P patches, a table of damped oscillators (strong self terms,
+    weak coupling falling off with the patch distance) sampled on its own grid fir_t, a DC ramp + pulse drive
+    that takes most patches into contact; case 1 keeps patch 0 out of contact (the int64 truncation of
+    np.vectorize then applies to everybody else), case 2 uses a quadratic contact law and maxiter 3."""
+    rng = np.random.default_rng(100 + case)
+    P, nfir_in, dt_in = (6, 90, 4e-9) if case < 2 else (4, 60, 5e-9)
+    t_step = 2e-9 if case < 2 else 5e-9
+    fir_t = np.arange(nfir_in) * dt_in
+    pos = np.arange(P)
+    amp = 9e-7 / (1 + 6 * np.abs(pos[:, None] - pos[None, :]))**2 * (1 + 0.1 * rng.standard_normal((P, P)))
+    w0 = 2 * np.pi * 6e6 * (1 + 0.05 * rng.standard_normal((P, P)))
+    fir = amp[:, :, None] * np.exp(-fir_t / 60e-9) * np.sin(w0[:, :, None] * fir_t + 0.35)
+    nt = 140 if case < 2 else 90
+    t_lim = (0.0, (nt - 1) * t_step, t_step)
+    v_t = np.arange(0, nt * t_step, 4 * t_step)
+    ramp = 1 / (1 + np.exp(-(v_t - 40e-9) / 8e-9))
+    v = np.outer(ramp, 18.5 + 1.5 * rng.random(P)) + 2 * np.outer(np.sin(2 * np.pi * 9e6 * v_t) * (v_t > 120e-9), np.ones(P))
+    if case == 0:
+        v *= 1.09
+    if case == 1:
+        v[:, 0] *= 0.3
+    if case == 2:
+        v = v[:, 0] * 1.02                                # one drive for all patches (StateDB tiles it)
+    gap = np.full(P, 50e-9)
+    gap_eff = gap + 100e-9 / 6.3
+    kw = dict(k=(2.5e14, 2.5e14, 4e22)[case], n=(1, 1, 2)[case], x0=-30e-9, lmbd=(2e13, 2e13, 4e21)[case],
+              atol=(1e-12, 1e-10, 1e-12)[case], maxiter=5 if case < 2 else 3)
+    return dict(fir_t=fir_t, fir=fir, v_t=v_t, v=v, gap=gap, gap_eff=gap_eff, t_lim=np.array(t_lim), **kw)
+
+
+def golden_td_solver():
+    """FixedStepSolver (cnld/simulation.pyx:297-555): constructed and stepped through the reference's own class."""
+    sim = _reference_simulation_module()
+    out = {}
+    ncases = 3
+    for c in range(ncases):
+        a = td_case(c)
+        s = sim.FixedStepSolver((a['fir_t'], a['fir']), (a['v_t'], a['v']), a['gap'], a['gap_eff'], tuple(a['t_lim']),
+                                a['k'], a['n'], a['x0'], a['lmbd'], atol=a['atol'], maxiter=a['maxiter'])
+        nsteps = len(s._db.t) - 2
+        for _ in range(nsteps):
+            s.step()
+        for key, val in a.items():
+            out[f'{key}{c}'] = np.asarray(val)
+        out[f'nsteps{c}'] = np.array(nsteps)
+        out[f'firi{c}'] = s._fir
+        out[f't{c}'], out[f'vi{c}'] = s._db.t, s._db.v
+        for key in ('x', 'u', 'p_es', 'p_cont_spr', 'p_cont_dmp', 'p_tot'):
+            out[f'{key}{c}'] = getattr(s._db, key).copy()
+        out[f'error{c}'], out[f'iters{c}'] = s.error, s.iters
+        pen = (s._db.x < a['x0'])
+        print('td case', c, 'steps', nsteps, 'iters', np.bincount(s.iters), 'contact samples', pen.sum(axis=0),
+              'xmin', s._db.x.min(), 'max err', s.error.max())
+    out['ncases'] = np.array(ncases)
+    # drive-signal generators (:640-712), arguments in tests/test_host_mirror.py::test_simulation_signals
+    sigs = [sim.gaussian_pulse(5e6, 0.8, 100e6, td=1e-7), sim.gaussian_pulse(3e6, 0.5, 80e6, antisym=False),
+            sim.logistic_ramp(2e-7, 1e-8), sim.logistic_ramp(2e-7, 1e-8, td=3e-7, tstop=1e-6),
+            sim.linear_ramp(2e-7, 1e-8), sim.linear_ramp(2e-7, 1e-8, td=1e-7, tstop=6e-7), sim.winsin(5e6, 3, 1e-8, td=2e-7)]
+    sigs.append(sim.sigadd(sigs[2], sigs[6], sigs[4]))
+    for q, (ts, vs) in enumerate(sigs):
+        out[f'sig_t{q}'], out[f'sig_v{q}'] = ts, vs
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), 'td_solver.npz'), **out)
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'fir_conv':
         golden_fir_conv()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'td_solver':
+        golden_td_solver()
         sys.exit(0)
     golden_fem('1x1_r3', (1, 1), 3)
     golden_fem('2x1_r4', (2, 1), 4)
@@ -267,3 +358,4 @@ if __name__ == '__main__':
     golden_fir()
     golden_pressure()
     golden_fir_conv()
+    golden_td_solver()

@@ -69,6 +69,85 @@ def test_fir_convolution_vs_reference_golden_and_oracle(po):
     tab.close()
 
 
+def test_fixed_step_solver_vs_reference_golden(po):
+    """FixedStepSolver on the device against the reference's own class (tests/golden/td_solver.npz: three drives
+    into contact, linear and quadratic contact laws, maxiter 5 / 3, steps with patch 0 in and out of contact --
+    np.vectorize's integer truncation included), stepping one sample at a time, many at a time and after reset."""
+    from cnld import simulation as sim
+    g = np.load(os.path.join(GOLDEN, 'td_solver.npz'))
+    for c in range(int(g['ncases'])):
+        nsteps = int(g[f'nsteps{c}'])
+        n = int(g[f'n{c}'])
+        s = sim.FixedStepSolver((g[f'fir_t{c}'], g[f'fir{c}']), (g[f'v_t{c}'], g[f'v{c}']), g[f'gap{c}'], g[f'gap_eff{c}'],
+                                tuple(g[f't_lim{c}']), float(g[f'k{c}']), n, float(g[f'x0{c}']), float(g[f'lmbd{c}']),
+                                atol=float(g[f'atol{c}']), maxiter=int(g[f'maxiter{c}']))
+        assert np.array_equal(s._fir, g[f'firi{c}']) and s.current_step == 1
+        assert np.array_equal(s.pressure_electrostatic[0], g[f'p_es{c}'][0])      # initial state, bit for bit
+
+        def check():
+            assert s.current_step == nsteps + 1 and np.array_equal(s.time, g[f't{c}'][:nsteps + 1])
+            assert np.array_equal(s.iters, g[f'iters{c}'])
+            for key, view in (('x', s.displacement), ('u', s.velocity), ('p_es', s.pressure_electrostatic),
+                              ('p_cont_spr', s.pressure_contact_spring), ('p_cont_dmp', s.pressure_contact_damper),
+                              ('p_tot', s.pressure_total)):
+                assert view.shape == (nsteps + 1, s.npatch) and _rel(view, g[f'{key}{c}'][:nsteps + 1]) < 1e-9, (c, key)
+            assert np.abs(s.error - g[f'error{c}']).max() < 1e-9 * np.abs(g[f'x{c}']).max()
+            free = s.displacement[:, 0] >= float(g[f'x0{c}'])
+            assert np.array_equal(s.pressure_contact_spring[free], np.trunc(s.pressure_contact_spring[free]))
+
+        for _ in range(10):
+            s.step()
+        assert s.current_step == 11 and _rel(s.displacement, g[f'x{c}'][:11]) < 1e-9
+        s.step(nsteps - 10)
+        check()
+        x_first = s.displacement.copy()
+        s.reset()
+        assert s.current_step == 1 and not s._db.x.any() and len(s.error) == 0
+        assert sum(1 for _ in s) == nsteps                                          # iterator protocol = solve()
+        check()
+        assert np.array_equal(x_first, s.displacement)                              # deterministic
+        with pytest.raises(Exception):
+            s.step(2)                                                               # past the time grid
+        s.close()
+
+
+def test_fixed_step_solver_vs_oracle_larger(po):
+    """36 patches, 700-tap table, 400 steps (history shorter and longer than the table), against the oracle's
+    restatement of the solver; and the module-level fir_conv_cy / fir_conv_py against the oracle."""
+    from cnld import _lib, simulation as sim
+    rng = np.random.default_rng(11)
+    P, nfir, dt, nt = 36, 700, 2e-9, 402
+    tt = np.arange(nfir) * dt
+    px = np.arange(P) % 6
+    py = np.arange(P) // 6
+    dist = np.hypot(px[:, None] - px[None, :], py[:, None] - py[None, :])
+    amp = 7e-7 / (1 + 5 * dist)**2 * (1 + 0.1 * rng.standard_normal((P, P)))
+    fir = amp[:, :, None] * np.exp(-tt / 70e-9) * np.sin(2 * np.pi * 5.5e6 * (1 + 0.03 * rng.standard_normal((P, P, 1))) * tt + 0.3)
+    fir[:, :, 300:] = 0                         # causal (Kramers-Kronig) tables end in exact zeros: never streamed
+    t = np.arange(nt) * dt
+    v = np.outer(1 / (1 + np.exp(-(t - 60e-9) / 10e-9)), 19.5 + 1.5 * rng.random(P)) + 1.5 * np.outer(np.sin(2 * np.pi * 8e6 * t), np.ones(P))
+    gap_eff = np.full(P, 50e-9 + 100e-9 / 6.3)
+    # contact threshold inside the stable electrostatic range (|x0| < gap_eff / 3): a rounding-level perturbation of
+    # the table stays at rounding level over the 400 steps (checked with the oracle; with x0 = -30 nm it grows to 10 %)
+    kw = dict(k=1e14 * 15e-9**-0.5, n=1.5, x0=-15e-9, lmbd=2e13 * 15e-9**-0.5, atol=1e-13, maxiter=4)
+    ref = po.td_solve(fir, v, gap_eff, dt, kw['k'], kw['n'], kw['x0'], kw['lmbd'], kw['atol'], kw['maxiter'], nsteps=nt - 1)
+    dev = _lib.TimeDomainSolver(fir, v, gap_eff, dt, kw['k'], kw['n'], kw['x0'], kw['lmbd'], atol=kw['atol'], maxiter=kw['maxiter'])
+    assert dev.taps == 300 and dev.nfir == nfir
+    dev.step(nt - 1)
+    got = dev.state(0, nt)
+    err, it = dev.info(1, nt)
+    assert (ref['x'] < kw['x0']).sum() > 500 and ref['iters'].max() > 4          # contact engaged, iterations vary
+    assert ((ref['x'][:, 1:] < kw['x0']).any(axis=1) & (ref['x'][:, 0] >= kw['x0'])).sum() > 50   # truncation rule exercised
+    assert np.array_equal(it, ref['iters'])
+    for key in got:
+        assert _rel(got[key], ref[key]) < 1e-9, key
+    assert np.abs(err - ref['error']).max() < 1e-9 * np.abs(ref['x']).max()
+    dev.close()
+    p = rng.standard_normal((50, P))
+    assert _rel(sim.fir_conv_cy(fir, p, dt, 1), po.fir_conv(fir, p, dt, 1)) < 1e-12
+    assert _rel(sim.fir_conv_py(fir, p, 1 / dt, 0), po.fir_conv(fir, p, dt, 0)) < 1e-12
+
+
 def test_field_spatial_impulse_responses_vs_reference_loop(po):
     """configs[4] in small: SIR of every patch at many field points through the many-source pressure path +
     device impulse response, against the reference's loop (bem_pressure.pyx:91-117: one point, one

@@ -126,6 +126,40 @@ def test_fir_mirror_matches_reference_golden():
     assert _rel(np.moveaxis(h0, 0, -1), g['h_2_1']) < 1e-11
 
 
+def test_simulation_signals_and_statedb_match_reference_golden():
+    """cnld.simulation's drive signals (simulation.pyx:640-712) and StateDB's time grid / drive interpolation
+    (:108-126) against the vectors the reference's own module produced; without a GPU the solver itself must
+    refuse to construct (no CPU fallback)."""
+    from cnld import _lib, simulation as sim
+    g = np.load(os.path.join(GOLDEN, 'td_solver.npz'))
+    sigs = [sim.gaussian_pulse(5e6, 0.8, 100e6, td=1e-7), sim.gaussian_pulse(3e6, 0.5, 80e6, antisym=False),
+            sim.logistic_ramp(2e-7, 1e-8), sim.logistic_ramp(2e-7, 1e-8, td=3e-7, tstop=1e-6),
+            sim.linear_ramp(2e-7, 1e-8), sim.linear_ramp(2e-7, 1e-8, td=1e-7, tstop=6e-7), sim.winsin(5e6, 3, 1e-8, td=2e-7)]
+    sigs.append(sim.sigadd(sigs[2], sigs[6], sigs[4]))
+    for q, (t, v) in enumerate(sigs):
+        assert t.shape == g[f'sig_t{q}'].shape and np.allclose(t, g[f'sig_t{q}'], rtol=1e-13, atol=1e-20), q
+        assert np.allclose(v, g[f'sig_v{q}'], rtol=1e-12, atol=1e-15), q
+    for c in range(int(g['ncases'])):
+        db = sim.StateDB(tuple(g[f't_lim{c}']), (g[f'v_t{c}'], g[f'v{c}']), g[f'fir{c}'].shape[0])
+        assert np.array_equal(db.t, g[f't{c}']) and np.array_equal(db.v, g[f'vi{c}'])
+        assert db.x.shape == g[f'x{c}'].shape and not db.x.any()
+        st = db.get_state_i(3)
+        st.x = np.full(db.x.shape[1], 2.0)
+        db.set_state_i(st)
+        assert np.all(db.x[3] == 2.0) and not db.x[2].any() and db.get_state_t(db.t[3] * 1.01).i == 3
+    x = np.array([-5e-8, 0.0, -3.5e-8])
+    assert np.allclose(sim.make_p_cont_spr(2e14, 1, -3e-8)(x), [4e6, 0, 1e6])
+    assert np.allclose(sim.make_p_cont_dmp(1e13, 1, -3e-8)(x, np.array([1.0, 1.0, -2.0])), [-2e5, 0, 1e5])
+    assert np.allclose(sim.p_es_pp(10.0, -1e-8, 6e-8), -8.8541878188e-12 / 2 * 100 / 25e-16, rtol=1e-9)
+    if _lib.device_count() == 0:
+        a = g
+        with pytest.raises(_lib.Cnldb200Error):
+            sim.FixedStepSolver((a['fir_t2'], a['fir2']), (a['v_t2'], a['v2']), a['gap2'], a['gap_eff2'], tuple(a['t_lim2']),
+                                float(a['k2']), 2, float(a['x02']), float(a['lmbd2']))
+    with pytest.raises(NotImplementedError):
+        sim.CompensationSolver()
+
+
 def test_database_roundtrip(tmp_path):
     from cnld import database
     from cnld.scripts.generate_db import Config
