@@ -364,7 +364,7 @@ def bench_c5(args, rank, world, local):
 
 C4_METRIC = 'frequencies solved/s (ACA H-matrix assemble + GMRES, all 2304 source patches), 16x16 CMUT array'
 C4_H = dict(clf=16, eta=0.8, admis='2', strict=True, kmax=64)           # generate_db.py:264-275 defaults
-C4_SOLVE = dict(eps_aca=1e-2, tol=1e-6, restart=50, maxiter=300, batch=96)
+C4_SOLVE = dict(eps_aca=1e-2, tol=1e-6, restart=50, maxiter=300, batch=192)
 
 
 def _c4_cpu_sample(po, am, k, tree, frac=64, seed=0):

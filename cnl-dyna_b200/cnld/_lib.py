@@ -96,6 +96,7 @@ def lib():
         L.cnld_b200_td_taps.restype = u32
         L.cnld_b200_td_state.argtypes = [vp, u32, u32] + [vp] * 6
         L.cnld_b200_td_info.argtypes = [vp, u32, u32, vp, vp]
+        L.cnld_b200_td_trace.argtypes = [vp, u32, u32, vp]
         L.cnld_b200_fft_to_fir.argtypes = [C.c_int, u32, vp, u32, vp, u32, C.c_int, vp, vp]
         L.cnld_b200_comm_create.restype = vp
         L.cnld_b200_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
@@ -485,6 +486,12 @@ class TimeDomainSolver:
             out[key] = into[key][i0:i1] if into is not None else np.empty((i1 - i0, self.npatch))
             assert out[key].flags.c_contiguous
         check(lib().cnld_b200_td_state(self._h, i0, i1, *[ptr(out[key]) for key in self.STATE]))
+        return out
+
+    def trace(self, s0, s1):
+        """%globaltimer marks [ns] of the step kernels (solver created with CNLD_B200_TD_TRACE=1), [s1 - s0, 8]."""
+        out = np.zeros((s1 - s0, 8), dtype=np.uint64)
+        check(lib().cnld_b200_td_trace(self._h, s0, s1, ptr(out)))
         return out
 
     def info(self, s0=1, s1=None):

@@ -237,39 +237,58 @@ int cnld_b200_fir_add(cnld_fir *f, const double *p_row, double dt, double *x) {
 struct cnld_td {
   int device = 0;
   uint P = 0, nfir = 0, nt = 0, ngroup = 1, per = 0, cur = 1;
+  uint ngroup_far = 1, per_far = 0;      // k_fir_far: destination slices sized to one wave of its own occupancy
   uint ntap = 0;                 // taps that matter: 1 + the last tap that is nonzero anywhere (<= nfir)
   double dt = 0, e0 = 0, k = 0, n = 0, x0 = 0, lmbd = 0, atol = 0;
   int maxiter = 0;
   bool pdl = true;               // step kernel launched as a programmatic dependent of the convolution (CNLD_B200_TD_PDL=0: plain)
+  uint block = 8;                // samples per pass over the table (CNLD_B200_TD_BLOCK=1: one pass per sample)
+  size_t ld = 0;                 // row stride of the device table: rows padded so that tap 1 sits on a 32-byte boundary
+  double *tab = nullptr;         // tap 0 of row 0 (= d_fir + 3)
+  double *d_firn = nullptr;      // fir[:, :, 1 .. TD_B - 1] as [lag - 1][source][destination]
   double *d_fir = nullptr, *d_fir0 = nullptr, *d_v = nullptr, *d_geff = nullptr, *d_hist = nullptr, *d_state = nullptr,
          *d_part = nullptr, *d_err = nullptr;
   int *d_iters = nullptr;
+  unsigned long long *d_trace = nullptr;
   cudaStream_t st = nullptr;
 };
 
 namespace {
 constexpr int TD_THREADS = 1024;
+constexpr int TD_B = 8;        // blocked stepping: samples served by one pass over the table
 enum { TD_X = 0, TD_U, TD_PES, TD_SPR, TD_DMP, TD_PTOT, TD_NSTATE };
 
 struct TdArgs {
   uint P, nt, s;
   double dt, e0h, k, n, x0, lmbd, atol;   // e0h = -e_0 / 2
   int maxiter, stage;                     // stage: fir[:, :, 0] fits in shared memory next to the work vectors
+  uint near;                              // blocked stepping: lags 1 .. near are added from the block's own samples
+  uint early;                             // the history pass and the samples up to s - 2 are complete when this kernel starts
+  const double *firn;                     // fir[:, :, 1 .. TD_B - 1] as [lag - 1][source][destination]
   const double *fir0, *v, *geff, *part;
   double *hist, *state, *err;
   int *iters;
+  unsigned long long *trace;              // optional [nt][8] %globaltimer marks of the kernel's phases (CNLD_B200_TD_TRACE=1)
 };
 
-__global__ void k_td_gather_fir0(uint P, uint nfir, const double *__restrict__ fir, double *fir0) {
+__device__ __forceinline__ void td_mark(const TdArgs &a, int k) {
+  if (a.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[(size_t)a.s * 8 + k] = t;
+  }
+}
+
+__global__ void k_td_gather_fir0(uint P, size_t ld, const double *__restrict__ tab, double *fir0) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < (size_t)P * P) fir0[e] = fir[e * nfir];
+  if (e < (size_t)P * P) fir0[e] = tab[e * ld];
 }
 // 1 + the largest tap index that is nonzero in any (source, destination) pair: a Kramers-Kronig (causal) table is
 // exactly zero in its second half (impulse_response.py:115-125), and taps that are zero everywhere add nothing
-__global__ void k_td_last_tap(size_t rows, uint nfir, const double *__restrict__ fir, uint *last) {
+__global__ void k_td_last_tap(size_t rows, uint nfir, size_t ld, const double *__restrict__ tab, uint *last) {
   const size_t r = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
-  const double *f = fir + r * nfir;
+  const double *f = tab + r * ld;
   uint best = 0;
   for (uint k = threadIdx.x & 31; k < nfir; k += 32)
     if (f[k] != 0.0) best = k + 1;
@@ -277,30 +296,133 @@ __global__ void k_td_last_tap(size_t rows, uint nfir, const double *__restrict__
   if ((threadIdx.x & 31) == 0 && best) atomicMax(last, best);
 }
 
-__device__ __forceinline__ double td_pow(double a, double n) {
-  return n == 1.0 ? a : n == 2.0 ? a * a : pow(a, n);
+// firn[lag - 1][i][j] = fir[i][j][lag], lag = 1 .. TD_B - 1 (zero beyond the table)
+__global__ void k_td_gather_near(uint P, uint nfir, size_t ld, const double *__restrict__ tab, double *firn) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x, PP = (size_t)P * P;
+  if (e >= PP * (TD_B - 1)) return;
+  const uint lag = (uint)(e / PP) + 1;
+  firn[e] = lag < nfir ? tab[(e % PP) * ld + lag] : 0.0;
+}
+
+// Blocked stepping, the part of the next TD_B samples' convolutions that the finished history already fixes:
+//   part[b][i][j] = sum_{tau > b} fir[i][j][tau] * h_i[s0 + b - tau],   b = 0 .. TD_B - 1,
+// (h_i = total pressure of source i, rows < s0 known).  Every table entry is loaded once and feeds TD_B lags: the
+// pass costs what one convolution costs and serves TD_B samples.  Same CTA shape as k_fir_conv.  The solver stores
+// its table with 32-byte aligned rows starting at tap 1, so a lane takes four consecutive taps (one sector, two
+// 16-byte loads) against twelve window values.  Window: logical[q] = W(k0 + q - B), W(m) = h_i[s0 - 1 - m] (zero
+// outside 0 <= m < s0: lags that reach into the block or before the first sample drop out by themselves).  A lane
+// reads its twelve window values as six 16-byte chunks at a lane stride of 32 bytes; adjacent chunks are swapped in
+// every other 128-byte row so that the eight lanes of a quarter warp hit all 32 banks whatever the chunk offset.
+__device__ __forceinline__ uint fw_phys(uint m) {
+  const uint c = m >> 1;
+  return ((c ^ ((c >> 3) & 1u)) << 1) | (m & 1u);
+}
+__device__ __forceinline__ double2 fw_lds128(const double *p) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return v;
+}
+
+template <int B>
+__global__ void __launch_bounds__(FC_THREADS, 3)
+k_fir_far(uint P, size_t ld, uint per, uint K, uint s0, const double *__restrict__ tab, const double *__restrict__ h, size_t hs,
+          double *part) {
+  constexpr uint WLEN = FC_KTILE + B + 8;
+  __shared__ __align__(16) double wbuf[(WLEN + 15) & ~15u];
+  asm volatile("griddepcontrol.launch_dependents;");
+  const uint i = blockIdx.x, g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint j0 = g * per, j1 = min(P, j0 + per);
+  const double *hp = h + (size_t)i * hs;
+  const size_t PP = (size_t)P * P;
+  for (uint k0 = 0; k0 < K; k0 += FC_KTILE) {           // taps tau = 1 + k0 + t, t < kt
+    const uint kt = min((uint)FC_KTILE, K - k0), nq = kt >> 2;
+    __syncthreads();
+    for (uint q = threadIdx.x; q < kt + B + 4; q += FC_THREADS) {
+      const long long m = (long long)k0 + (long long)q - B;
+      wbuf[fw_phys(q)] = (m >= 0 && m < (long long)s0) ? hp[s0 - 1 - m] : 0.0;
+    }
+    __syncthreads();
+    for (uint j = j0 + warp; j < j1; j += FC_THREADS / 32) {
+      const double *f = tab + ((size_t)i * P + j) * ld + 1 + k0;      // 32-byte aligned (ld % 4 == 0, tap 1 on a boundary)
+      double acc[B];
+#pragma unroll
+      for (int b = 0; b < B; b++) acc[b] = 0.0;
+      const double2 *f2 = reinterpret_cast<const double2 *>(f);
+      // three groups of four taps per lane in flight: a buffer is refilled right after it has been used and is
+      // needed again two groups later (rotation by unrolling, no register copies that would wait for the load)
+      constexpr int NBUF = 3;
+      double2 bu[NBUF][2];
+#pragma unroll
+      for (int k = 0; k < NBUF; k++)
+        if (lane + 32 * k < nq) { bu[k][0] = __ldcs(f2 + 2 * (lane + 32 * k)); bu[k][1] = __ldcs(f2 + 2 * (lane + 32 * k) + 1); }
+      for (uint qb = lane; qb < nq; qb += 32 * NBUF) {
+#pragma unroll
+        for (int k = 0; k < NBUF; k++) {
+          const uint q = qb + 32 * k;
+          if (q < nq) {
+            double wv[12];                              // logical[4 q + x]
+#pragma unroll
+            for (int x = 0; x < 12; x += 2) {
+              const double2 w2 = fw_lds128(wbuf + fw_phys(4 * q + x));
+              wv[x] = w2.x;
+              wv[x + 1] = w2.y;
+            }
+            const double2 u0 = bu[k][0], u1 = bu[k][1];
+#pragma unroll
+            for (int b = 0; b < B; b++) {               // tap 4 q + u, lag b -> logical[4 q + u - b + B]
+              acc[b] = fma(u0.x, wv[B - b], acc[b]);
+              acc[b] = fma(u0.y, wv[B + 1 - b], acc[b]);
+              acc[b] = fma(u1.x, wv[B + 2 - b], acc[b]);
+              acc[b] = fma(u1.y, wv[B + 3 - b], acc[b]);
+            }
+            if (q + 32 * NBUF < nq) {
+              bu[k][0] = __ldcs(f2 + 2 * (q + 32 * NBUF));
+              bu[k][1] = __ldcs(f2 + 2 * (q + 32 * NBUF) + 1);
+            }
+          }
+        }
+      }
+      const uint t = 4 * nq + lane;                     // up to three taps after the last full group
+      if (t < kt) {
+        const double fv = f[t];
+#pragma unroll
+        for (int b = 0; b < B; b++) acc[b] = fma(fv, wbuf[fw_phys(t - b + B)], acc[b]);
+      }
+#pragma unroll
+      for (int b = 0; b < B; b++) {
+        double a = acc[b];
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (lane == 0) {
+          double *dst = part + (size_t)b * PP + (size_t)i * P + j;
+          *dst = k0 ? *dst + a : a;
+        }
+      }
+    }
+  }
 }
 
 // out[j] = sum_i M[i * P + j] * (W ? w[i] : 1): the sources are dealt to G thread groups, the group sums are added
 // in group order (fixed association, independent of timing)
-template <bool W>
-__device__ void td_colsum(uint P, const double *__restrict__ M, const double *w, double *gsum, double *out) {
+// CG: M is global memory another kernel wrote -- read it through L2 (ld.global.cg), M in shared memory otherwise
+template <bool W, bool CG = false>
+__device__ void td_colsum(uint nsrc, uint P, const double *M, const double *w, double *gsum, double *out) {
+  auto ld = [&](size_t e) { return CG ? __ldcg(M + e) : M[e]; };
   const uint T = TD_THREADS, Pp = min((P + 31u) & ~31u, T), G = T / Pp, g = threadIdx.x / Pp, jj = threadIdx.x % Pp;
-  const uint chunk = (P + G - 1) / G;
+  const uint chunk = (nsrc + G - 1) / G;
   if (g < G) {
-    const uint i0 = g * chunk, i1 = min(P, i0 + chunk);
+    const uint i0 = min(nsrc, g * chunk), i1 = min(nsrc, i0 + chunk);
     for (uint j = jj; j < P; j += Pp) {
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
       uint i = i0;
       for (; i + 3 < i1; i += 4) {
-        const double m0 = M[(size_t)i * P + j], m1 = M[(size_t)(i + 1) * P + j], m2 = M[(size_t)(i + 2) * P + j],
-                     m3 = M[(size_t)(i + 3) * P + j];
+        const double m0 = ld((size_t)i * P + j), m1 = ld((size_t)(i + 1) * P + j), m2 = ld((size_t)(i + 2) * P + j),
+                     m3 = ld((size_t)(i + 3) * P + j);
         a0 = W ? fma(m0, w[i], a0) : a0 + m0;
         a1 = W ? fma(m1, w[i + 1], a1) : a1 + m1;
         a2 = W ? fma(m2, w[i + 2], a2) : a2 + m2;
         a3 = W ? fma(m3, w[i + 3], a3) : a3 + m3;
       }
-      for (; i < i1; i++) a0 = W ? fma(M[(size_t)i * P + j], w[i], a0) : a0 + M[(size_t)i * P + j];
+      for (; i < i1; i++) a0 = W ? fma(ld((size_t)i * P + j), w[i], a0) : a0 + ld((size_t)i * P + j);
       gsum[(size_t)g * P + j] = (a0 + a1) + (a2 + a3);
     }
   }
@@ -313,142 +435,194 @@ __device__ void td_colsum(uint P, const double *__restrict__ M, const double *w,
   __syncthreads();
 }
 
+// The step kernel is ONE CTA executing a long, mostly serial program; every helper exists once in the code
+// (noinline functions, loops that are not unrolled): with the reference's control flow written out call by call the
+// kernel had 26 000 instructions, each executed once or twice, and ran at the speed of its instruction fetches.
+struct TdSm {
+  double *base, *x, *xp, *u, *pes, *spr, *dmp, *pt, *v, *ge, *tmp, *wn, *red, *gsum;
+  const double *fir0;
+  bool fir0_shared;
+};
+
+__device__ __noinline__ void td_far_sum(const TdArgs &a, const TdSm &m) {       // sum over the sources of the history pass
+  td_colsum<false, true>(a.P, a.P, a.part, nullptr, m.gsum, m.tmp);
+}
+// tmp += sum over lags lo .. hi of fir[:, :, lag]^T p_tot[s - lag] (lags and sources flattened into one column sum)
+__device__ __noinline__ void td_near_sum(const TdArgs &a, const TdSm &m, uint lo, uint hi) {
+  const uint P = a.P, T = TD_THREADS, tid = threadIdx.x, n = (hi - lo + 1) * P;
+  const double *pt_rows = a.state + (size_t)TD_PTOT * a.nt * P;
+  for (uint e = tid; e < n; e += T) m.wn[e] = __ldcg(pt_rows + (size_t)(a.s - lo - e / P) * P + e % P);
+  __syncthreads();
+  td_colsum<true, true>(n, P, a.firn + (size_t)(lo - 1) * P * P, m.wn, m.gsum, m.base);
+  for (uint j = tid; j < P; j += T) m.tmp[j] += m.base[j];
+  __syncthreads();
+}
+__device__ __noinline__ double td_pow_general(double a, double n) { return pow(a, n); }
+__device__ __forceinline__ double td_pow(double a, double n) { return n == 1.0 ? a : n == 2.0 ? a * a : td_pow_general(a, n); }
+
+__device__ __noinline__ void td_update_all(const TdArgs &a, const TdSm &m) {    // _update_all, simulation.pyx:412-421
+  const uint P = a.P, T = TD_THREADS, tid = threadIdx.x;
+  const bool first_free = m.x[0] >= a.x0;
+  for (uint j = tid; j < P; j += T) {
+    const double xj = m.x[j], d = xj + m.ge[j];
+    m.u[j] = a.s ? (xj - m.xp[j]) / a.dt : 0.0;
+    m.pes[j] = (a.e0h * (m.v[j] * m.v[j])) / (d * d);
+    double c = xj >= a.x0 ? 0.0 : a.k * td_pow(a.x0 - xj, a.n);
+    if (first_free) c = trunc(c);
+    m.spr[j] = c;
+    m.pt[j] = (c + m.dmp[j]) + m.pes[j];
+  }
+  __syncthreads();
+}
+__device__ __noinline__ void td_update_dmp(const TdArgs &a, const TdSm &m) {    // _update_cont_dmp, :423-428
+  const uint P = a.P, T = TD_THREADS, tid = threadIdx.x;
+  const bool first_free = m.x[0] >= a.x0;
+  for (uint j = tid; j < P; j += T) {
+    double c = m.x[j] >= a.x0 ? 0.0 : -(a.lmbd * td_pow(a.x0 - m.x[j], a.n)) * m.u[j];
+    if (first_free) c = trunc(c);
+    m.dmp[j] = c;
+  }
+  __syncthreads();
+}
+__device__ __noinline__ double td_update_x(const TdArgs &a, const TdSm &m) {    // _update_x, :430-445
+  const uint P = a.P, T = TD_THREADS, tid = threadIdx.x;
+  if (m.fir0_shared) td_colsum<true, false>(P, P, m.fir0, m.pt, m.gsum, m.tmp);
+  else td_colsum<true, true>(P, P, m.fir0, m.pt, m.gsum, m.tmp);
+  double e = 0.0;
+  for (uint j = tid; j < P; j += T) {
+    const double xn = __dadd_rn(m.base[j], __dmul_rn(m.tmp[j], a.dt));
+    const double dj = fabs(m.x[j] - xn);
+    e = (dj > e || dj != dj) ? dj : e;                // NaN sticks, like np.max
+    m.x[j] = xn;
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    const double o = __shfl_xor_sync(0xffffffffu, e, off);
+    e = (o > e || o != o) ? o : e;
+  }
+  if ((tid & 31) == 0) m.red[tid >> 5] = e;
+  __syncthreads();
+  e = (tid & 31) < T / 32 ? m.red[tid & 31] : 0.0;    // every warp reduces the 32 warp maxima again
+  for (int off = 16; off > 0; off >>= 1) {
+    const double o = __shfl_xor_sync(0xffffffffu, e, off);
+    e = (o > e || o != o) ? o : e;
+  }
+  __syncthreads();
+  return e;
+}
+
 __global__ void __launch_bounds__(TD_THREADS) k_td_step(TdArgs a) {
   extern __shared__ double sm[];
   const uint P = a.P, T = TD_THREADS, tid = threadIdx.x, s = a.s;
-  double *base = sm, *x = base + P, *xp = x + P, *u = xp + P, *pes = u + P, *spr = pes + P, *dmp = spr + P, *pt = dmp + P,
-         *v = pt + P, *ge = v + P, *tmp = ge + P, *red = tmp + P, *gsum = red + 32;
+  TdSm m;
+  m.base = sm; m.x = m.base + P; m.xp = m.x + P; m.u = m.xp + P; m.pes = m.u + P; m.spr = m.pes + P; m.dmp = m.spr + P;
+  m.pt = m.dmp + P; m.v = m.pt + P; m.ge = m.v + P; m.tmp = m.ge + P; m.wn = m.tmp + P; m.red = m.wn + (size_t)(TD_B - 1) * P;
+  m.gsum = m.red + 32;
+  m.fir0 = a.fir0;
+  m.fir0_shared = a.stage != 0;
   double *S = a.state;
-  const size_t plane = (size_t)a.nt * P;
-  // prologue on data no earlier kernel of the step writes: drive, gaps and the zero-lag slice of the table
-  const double *fir0 = a.fir0;
+  const size_t plane = (size_t)a.nt * P, PP = (size_t)P * P;
+  td_mark(a, 0);
+  // Prologue, overlapped with the previous kernel of the stream (programmatic dependent launch): the drive, the
+  // gaps and the zero-lag slice of the table are constants of the run.  In a block of samples a kernel releases
+  // its dependent only after its own dependency is met, so when sample s starts, everything up to sample s - 2 and
+  // the history pass of the block are complete: their part of the convolution (all of it except lag 1) is summed
+  // before the wait as well, through L2.
   if (a.stage) {
     const uint Pp = min((P + 31u) & ~31u, T), G = T / Pp;
-    double *f0s = sm + (((size_t)11 * P + 32 + (size_t)G * P + 1) & ~(size_t)1);   // 16-byte aligned
-    const size_t n2 = (size_t)P * P / 2;
+    double *f0s = sm + (((size_t)(10 + TD_B) * P + 32 + (size_t)G * P + 1) & ~(size_t)1);   // 16-byte aligned
+    const size_t n2 = PP / 2;
     const double2 *src = reinterpret_cast<const double2 *>(a.fir0);
     double2 *dst = reinterpret_cast<double2 *>(f0s);
     for (size_t e = tid; e < n2; e += T) dst[e] = src[e];
-    if (tid == 0 && (P & 1)) f0s[(size_t)P * P - 1] = a.fir0[(size_t)P * P - 1];
-    fir0 = f0s;
+    if (tid == 0 && (P & 1)) f0s[PP - 1] = a.fir0[PP - 1];
+    m.fir0 = f0s;
   }
   for (uint j = tid; j < P; j += T) {
-    v[j] = a.v[(size_t)s * P + j];
-    ge[j] = a.geff[j];
-    dmp[j] = 0.0;
-    x[j] = 0.0;
+    m.v[j] = a.v[(size_t)s * P + j];
+    m.ge[j] = a.geff[j];
+    m.dmp[j] = 0.0;
+    m.x[j] = 0.0;
+    m.tmp[j] = 0.0;
   }
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // the convolution (and with it every earlier step) is complete
-  for (uint j = tid; j < P; j += T) xp[j] = s ? S[TD_X * plane + (size_t)(s - 1) * P + j] : 0.0;
   __syncthreads();
-
-  auto update_all = [&]() {                           // _update_all, simulation.pyx:412-421
-    const bool first_free = x[0] >= a.x0;
-    for (uint j = tid; j < P; j += T) {
-      const double xj = x[j], d = xj + ge[j];
-      u[j] = s ? (xj - xp[j]) / a.dt : 0.0;
-      pes[j] = (a.e0h * (v[j] * v[j])) / (d * d);
-      double c = xj >= a.x0 ? 0.0 : a.k * td_pow(a.x0 - xj, a.n);
-      if (first_free) c = trunc(c);
-      spr[j] = c;
-      pt[j] = (c + dmp[j]) + pes[j];
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {              // 0: before the dependency is met, 1: after
+    if (pass) {
+      td_mark(a, 1);
+      asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous kernel of the stream is complete
+      asm volatile("griddepcontrol.launch_dependents;");   // the next sample's kernel may run its prologue now
+      td_mark(a, 2);
+      for (uint j = tid; j < P; j += T) m.xp[j] = s ? S[TD_X * plane + (size_t)(s - 1) * P + j] : 0.0;
     }
-    __syncthreads();
-  };
-  auto update_x = [&]() -> double {                   // _update_x, :430-445
-    td_colsum<true>(P, fir0, pt, gsum, tmp);
-    double e = 0.0;
-    for (uint j = tid; j < P; j += T) {
-      const double xn = __dadd_rn(base[j], __dmul_rn(tmp[j], a.dt));
-      const double dj = fabs(x[j] - xn);
-      e = (dj > e || dj != dj) ? dj : e;              // NaN sticks, like np.max
-      x[j] = xn;
-    }
-    for (int off = 16; off > 0; off >>= 1) {
-      const double o = __shfl_xor_sync(0xffffffffu, e, off);
-      e = (o > e || o != o) ? o : e;
-    }
-    if ((tid & 31) == 0) red[tid >> 5] = e;
-    __syncthreads();
-    e = red[0];
-    for (uint w = 1; w < T / 32; w++) e = (red[w] > e || red[w] != red[w]) ? red[w] : e;
-    __syncthreads();
-    return e;
-  };
-
+    if (s && (pass == 0) == (a.early != 0)) td_far_sum(a, m);
+    // lags into the block's own samples: 2 .. near early, lag 1 (or all of them) once the previous sample is final
+    const uint lo = pass ? 1u : 2u, hi = pass ? (a.early ? min(a.near, 1u) : a.near) : (a.early ? a.near : 0u);
+    if (s && hi >= lo) td_near_sum(a, m, lo, hi);
+  }
   if (s == 0) {                                       // initial state (:335)
-    update_all();
+    td_update_all(a, m);
   } else {
-    td_colsum<false>(P, a.part, nullptr, gsum, tmp);  // finish the convolution: sum over the sources, times dt
-    for (uint j = tid; j < P; j += T) x[j] = base[j] = tmp[j] * a.dt;      // _blind_x
+    for (uint j = tid; j < P; j += T) m.x[j] = m.base[j] = m.tmp[j] * a.dt;      // _blind_x (:447-457)
     __syncthreads();
-    update_all();
-    double err = update_x();
-    update_all();
-    int it = 2;
-    for (int q = 0; q < a.maxiter - 1; q++) {
-      if (err <= a.atol) break;
-      err = update_x();
-      update_all();
-      it++;
-    }
-    {                                                 // _update_cont_dmp (:423-428)
-      const bool first_free = x[0] >= a.x0;
-      for (uint j = tid; j < P; j += T) {
-        double c = x[j] >= a.x0 ? 0.0 : -(a.lmbd * td_pow(a.x0 - x[j], a.n)) * u[j];
-        if (first_free) c = trunc(c);
-        tmp[j] = c;
+    td_mark(a, 3);
+    // step (:459-503) as one loop: [damper update] -> _update_all -> decide -> _update_x.  Phase 0 iterates without
+    // the contact damper, phase 1 with the damper frozen at phase 0's estimate; the first _update_x of a phase is
+    // unconditional, up to maxiter - 1 more follow while max|dx| > atol; `it` counts like the reference's `i`
+    int phase = 0, q = 0, it = 2;
+    bool need_dmp = false;
+    double err = 0.0;
+#pragma unroll 1
+    for (;;) {
+      if (need_dmp) {
+        td_update_dmp(a, m);
+        need_dmp = false;
       }
-      __syncthreads();
-      for (uint j = tid; j < P; j += T) dmp[j] = tmp[j];
-      __syncthreads();
-    }
-    update_all();
-    err = update_x();
-    update_all();
-    for (int q = 0; q < a.maxiter - 1; q++) {
-      if (err <= a.atol) break;
-      err = update_x();
-      update_all();
-      it++;
+      td_update_all(a, m);
+      if (q == 0 || (q < a.maxiter && !(err <= a.atol))) {
+        err = td_update_x(a, m);
+        if (q > 0) it++;
+        q++;
+        continue;
+      }
+      if (phase == 0) {
+        td_mark(a, 4);
+        phase = 1;
+        q = 0;
+        need_dmp = true;
+        continue;
+      }
+      break;
     }
     if (tid == 0) {
       a.err[s] = err;
       a.iters[s] = it;
     }
+    td_mark(a, 5);
   }
   for (uint j = tid; j < P; j += T) {
     const size_t r = (size_t)s * P + j;
-    S[TD_X * plane + r] = x[j];
-    S[TD_U * plane + r] = u[j];
-    S[TD_PES * plane + r] = pes[j];
-    S[TD_SPR * plane + r] = spr[j];
-    S[TD_DMP * plane + r] = dmp[j];
-    S[TD_PTOT * plane + r] = pt[j];
-    a.hist[(size_t)j * a.nt + s] = pt[j];             // the next steps' convolution input
+    S[TD_X * plane + r] = m.x[j];
+    S[TD_U * plane + r] = m.u[j];
+    S[TD_PES * plane + r] = m.pes[j];
+    S[TD_SPR * plane + r] = m.spr[j];
+    S[TD_DMP * plane + r] = m.dmp[j];
+    S[TD_PTOT * plane + r] = m.pt[j];
+    a.hist[(size_t)j * a.nt + s] = m.pt[j];           // the next steps' convolution input
   }
+  td_mark(a, 6);
 }
 
 size_t td_smem_base(uint P) {
   const uint Pp = std::min((P + 31u) & ~31u, (uint)TD_THREADS), G = TD_THREADS / Pp;
-  return sizeof(double) * (((size_t)11 * P + 32 + (size_t)G * P + 1) & ~(size_t)1);
+  return sizeof(double) * (((size_t)(10 + TD_B) * P + 32 + (size_t)G * P + 1) & ~(size_t)1);
 }
 bool td_stage(uint P) { return td_smem_base(P) + sizeof(double) * P * P <= 224 * 1024; }
 size_t td_smem(uint P) { return td_smem_base(P) + (td_stage(P) ? sizeof(double) * P * P : 0); }
 
-int td_launch_step(cnld_td *t, uint s) {
-  if (s) {
-    const uint K = t->ntap > 1 ? std::min(s, t->ntap - 1) : 0u;
-    if (K) {
-      k_fir_conv<<<dim3(t->P, t->ngroup), FC_THREADS, 0, t->st>>>(t->P, t->P, t->nfir, t->per, K, 1, t->d_fir, t->d_hist, t->nt,
-                                                                   s - 1, t->d_part, 1, t->P);
-      CNLD_CK_LAUNCH();
-    } else {
-      CNLD_CK(cudaMemsetAsync(t->d_part, 0, sizeof(double) * (size_t)t->P * t->P, t->st));
-    }
-  }
-  TdArgs a{t->P, t->nt, s, t->dt, -t->e0 / 2, t->k, t->n, t->x0, t->lmbd, t->atol, t->maxiter, td_stage(t->P) ? 1 : 0, t->d_fir0,
-           t->d_v, t->d_geff, t->d_part, t->d_hist, t->d_state, t->d_err, t->d_iters};
+int td_launch_kernel(cnld_td *t, uint s, uint near, uint early, const double *part) {
+  TdArgs a{t->P, t->nt, s, t->dt, -t->e0 / 2, t->k, t->n, t->x0, t->lmbd, t->atol, t->maxiter, td_stage(t->P) ? 1 : 0, near,
+           t->pdl ? early : 0u, t->d_firn, t->d_fir0, t->d_v, t->d_geff, part, t->d_hist, t->d_state, t->d_err, t->d_iters,
+           t->d_trace};
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(1);
   cfg.blockDim = dim3(TD_THREADS);
@@ -461,6 +635,37 @@ int td_launch_step(cnld_td *t, uint s) {
   cfg.numAttrs = t->pdl ? 1 : 0;
   CNLD_CK(cudaLaunchKernelEx(&cfg, k_td_step, a));
   CNLD_CK_LAUNCH();
+  return 0;
+}
+
+// one sample: one pass over the table (k_fir_conv, lags 1 .. min(s, taps - 1)), then the step kernel
+int td_launch_step(cnld_td *t, uint s) {
+  if (s) {
+    const uint K = t->ntap > 1 ? std::min(s, t->ntap - 1) : 0u;
+    if (K) {
+      k_fir_conv<<<dim3(t->P, t->ngroup), FC_THREADS, 0, t->st>>>(t->P, t->P, (uint)t->ld, t->per, K, 1, t->tab, t->d_hist, t->nt,
+                                                                   s - 1, t->d_part, 1, t->P);
+      CNLD_CK_LAUNCH();
+    } else {
+      CNLD_CK(cudaMemsetAsync(t->d_part, 0, sizeof(double) * (size_t)t->P * t->P, t->st));
+    }
+  }
+  return td_launch_kernel(t, s, 0, 0, t->d_part);
+}
+
+// nb <= TD_B samples starting at s0 >= 1: one pass over the table for what the history before s0 contributes to all of
+// them (k_fir_far), then the step kernels, each adding the lags that reach into the block from fir[:, :, 1 .. nb - 1]
+int td_launch_block(cnld_td *t, uint s0, uint nb) {
+  const size_t PP = (size_t)t->P * t->P;
+  const uint K = t->ntap > 1 ? std::min(s0 + nb - 1, t->ntap - 1) : 0u;
+  if (K) {
+    k_fir_far<TD_B><<<dim3(t->P, t->ngroup_far), FC_THREADS, 0, t->st>>>(t->P, t->ld, t->per_far, K, s0, t->tab, t->d_hist, t->nt, t->d_part);
+    CNLD_CK_LAUNCH();
+  } else {
+    CNLD_CK(cudaMemsetAsync(t->d_part, 0, sizeof(double) * PP * TD_B, t->st));
+  }
+  for (uint b = 0; b < nb; b++)
+    if (td_launch_kernel(t, s0 + b, t->ntap > 1 ? std::min(b, t->ntap - 1) : 0u, b >= 1, t->d_part + (size_t)b * PP)) return -1;
   return 0;
 }
 }  // namespace
@@ -478,29 +683,43 @@ cnld_td *cnld_b200_td_create(int device, cnld_uint npatch, cnld_uint nfir, const
   t->device = device; t->P = npatch; t->nfir = nfir; t->nt = nt;
   t->dt = dt; t->e0 = e0; t->k = k; t->n = n; t->x0 = x0; t->lmbd = lmbd; t->atol = atol; t->maxiter = maxiter;
   if (const char *e = getenv("CNLD_B200_TD_PDL")) t->pdl = atoi(e) != 0;
+  if (const char *e = getenv("CNLD_B200_TD_BLOCK")) t->block = (uint)std::min(std::max(atoi(e), 1), TD_B);
+  t->ld = ((size_t)nfir + 3 + 3) & ~(size_t)3;
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
   t->ngroup = std::max(1u, std::min((npatch + 7) / 8, (uint)((4 * nsm + npatch - 1) / npatch)));
   t->per = (npatch + t->ngroup - 1) / t->ngroup;
   t->ngroup = (npatch + t->per - 1) / t->per;
-  const size_t PP = (size_t)npatch * npatch, tab = PP * nfir, rows = (size_t)nt * npatch;
+  int occ_far = 4;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_far, k_fir_far<TD_B>, FC_THREADS, 0);
+  t->ngroup_far = std::max(1u, std::min((npatch + 7) / 8, (uint)(std::max(occ_far, 1) * nsm) / npatch));
+  t->per_far = (npatch + t->ngroup_far - 1) / t->ngroup_far;
+  t->ngroup_far = (npatch + t->per_far - 1) / t->per_far;
+  const size_t PP = (size_t)npatch * npatch, tab = PP * t->ld + 4, rows = (size_t)nt * npatch;
   bool ok = cudaSetDevice(device) == cudaSuccess && cudaMalloc(&t->d_fir, sizeof(double) * tab) == cudaSuccess &&
-            cudaMalloc(&t->d_fir0, sizeof(double) * PP) == cudaSuccess && cudaMalloc(&t->d_part, sizeof(double) * PP) == cudaSuccess &&
+            cudaMemset(t->d_fir, 0, sizeof(double) * tab) == cudaSuccess &&
+            cudaMalloc(&t->d_fir0, sizeof(double) * PP) == cudaSuccess && cudaMalloc(&t->d_part, sizeof(double) * PP * TD_B) == cudaSuccess &&
+            cudaMalloc(&t->d_firn, sizeof(double) * PP * (TD_B - 1)) == cudaSuccess &&
             cudaMalloc(&t->d_v, sizeof(double) * rows) == cudaSuccess && cudaMalloc(&t->d_geff, sizeof(double) * npatch) == cudaSuccess &&
             cudaMalloc(&t->d_hist, sizeof(double) * rows) == cudaSuccess &&
             cudaMalloc(&t->d_state, sizeof(double) * rows * TD_NSTATE) == cudaSuccess &&
             cudaMalloc(&t->d_err, sizeof(double) * nt) == cudaSuccess && cudaMalloc(&t->d_iters, sizeof(int) * nt) == cudaSuccess &&
-            cudaMemcpy(t->d_fir, fir, sizeof(double) * tab, cudaMemcpyHostToDevice) == cudaSuccess &&
+            (!getenv("CNLD_B200_TD_TRACE") || (cudaMalloc(&t->d_trace, sizeof(unsigned long long) * nt * 8) == cudaSuccess &&
+                                                cudaMemset(t->d_trace, 0, sizeof(unsigned long long) * nt * 8) == cudaSuccess)) &&
+            cudaMemcpy2D(t->d_fir + 3, sizeof(double) * t->ld, fir, sizeof(double) * nfir, sizeof(double) * nfir, PP,
+                         cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaMemcpy(t->d_v, v, sizeof(double) * rows, cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaMemcpy(t->d_geff, gap_eff, sizeof(double) * npatch, cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking) == cudaSuccess &&
             cudaFuncSetAttribute(k_td_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
   if (ok) {
-    k_td_gather_fir0<<<(unsigned)((PP + 255) / 256), 256, 0, t->st>>>(npatch, nfir, t->d_fir, t->d_fir0);
+    t->tab = t->d_fir + 3;
+    k_td_gather_fir0<<<(unsigned)((PP + 255) / 256), 256, 0, t->st>>>(npatch, t->ld, t->tab, t->d_fir0);
+    k_td_gather_near<<<(unsigned)((PP * (TD_B - 1) + 255) / 256), 256, 0, t->st>>>(npatch, nfir, t->ld, t->tab, t->d_firn);
     uint *d_last = reinterpret_cast<uint *>(t->d_iters);        // scratch until reset() clears it
     ok = cudaMemsetAsync(d_last, 0, sizeof(uint), t->st) == cudaSuccess;
-    k_td_last_tap<<<(unsigned)((PP + 7) / 8), 256, 0, t->st>>>(PP, nfir, t->d_fir, d_last);
-    count_launch(2);
+    k_td_last_tap<<<(unsigned)((PP + 7) / 8), 256, 0, t->st>>>(PP, nfir, t->ld, t->tab, d_last);
+    count_launch(3);
     ok = ok && cudaMemcpyAsync(&t->ntap, d_last, sizeof(uint), cudaMemcpyDeviceToHost, t->st) == cudaSuccess &&
          cudaStreamSynchronize(t->st) == cudaSuccess && cudaGetLastError() == cudaSuccess && cnld_b200_td_reset(t) == 0;
   }
@@ -515,8 +734,8 @@ cnld_td *cnld_b200_td_create(int device, cnld_uint npatch, cnld_uint nfir, const
 void cnld_b200_td_destroy(cnld_td *t) {
   if (!t) return;
   cudaSetDevice(t->device);
-  cudaFree(t->d_fir); cudaFree(t->d_fir0); cudaFree(t->d_part); cudaFree(t->d_v); cudaFree(t->d_geff); cudaFree(t->d_hist);
-  cudaFree(t->d_state); cudaFree(t->d_err); cudaFree(t->d_iters);
+  cudaFree(t->d_fir); cudaFree(t->d_fir0); cudaFree(t->d_firn); cudaFree(t->d_part); cudaFree(t->d_v); cudaFree(t->d_geff); cudaFree(t->d_hist);
+  cudaFree(t->d_state); cudaFree(t->d_err); cudaFree(t->d_iters); cudaFree(t->d_trace);
   if (t->st) cudaStreamDestroy(t->st);
   delete t;
 }
@@ -541,11 +760,23 @@ int cnld_b200_td_step(cnld_td *t, cnld_uint nsteps) {
   if (!t) { set_error("null td solver"); return -1; }
   if ((size_t)t->cur + nsteps > t->nt) { set_error("td_step: %u steps from sample %u run past the %u samples of the time grid", nsteps, t->cur, t->nt); return -1; }
   CNLD_CK(cudaSetDevice(t->device));
-  for (uint q = 0; q < nsteps; q++) {
-    if (td_launch_step(t, t->cur)) return -1;
-    t->cur++;
+  for (uint left = nsteps; left;) {
+    const uint nb = std::min(left, t->block);
+    if (nb > 1 ? td_launch_block(t, t->cur, nb) : td_launch_step(t, t->cur)) return -1;
+    t->cur += nb;
+    left -= nb;
   }
   CNLD_CK(cudaStreamSynchronize(t->st));
+  return 0;
+}
+
+/* diagnostic (CNLD_B200_TD_TRACE=1 at create): %globaltimer marks [ns] of the step kernels of samples [s0, s1), 8 per
+ * sample: kernel start, prologue done, dependency met, base ready, first fixed point done, second done, rows written */
+int cnld_b200_td_trace(cnld_td *t, cnld_uint s0, cnld_uint s1, unsigned long long *marks) {
+  if (!t || s0 > s1 || s1 > t->nt || !marks) { set_error("td_trace: bad arguments"); return -1; }
+  if (!t->d_trace) { set_error("td_trace: create the solver with CNLD_B200_TD_TRACE=1"); return -1; }
+  CNLD_CK(cudaSetDevice(t->device));
+  CNLD_CK(cudaMemcpy(marks, t->d_trace + (size_t)s0 * 8, sizeof(unsigned long long) * 8 * (s1 - s0), cudaMemcpyDeviceToHost));
   return 0;
 }
 

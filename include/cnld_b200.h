@@ -327,6 +327,10 @@ cnld_uint cnld_b200_td_taps(const cnld_td *t);
 /* samples [i0, i1) of x, u, p_es, p_cont_spr, p_cont_dmp, p_tot -> HOST [i1 - i0][npatch] each (nullable) */
 int cnld_b200_td_state(cnld_td *t, cnld_uint i0, cnld_uint i1, double *x, double *u, double *p_es, double *p_cont_spr,
                        double *p_cont_dmp, double *p_tot);
+/* diagnostic, needs CNLD_B200_TD_TRACE=1 in the environment at create: %globaltimer marks [ns] of the step kernels of
+ * samples [s0, s1), marks[s1 - s0][8]: kernel start, prologue done, dependency met, base ready, first fixed point done,
+ * second fixed point done, state rows written, (unused) */
+int cnld_b200_td_trace(cnld_td *t, cnld_uint s0, cnld_uint s1, unsigned long long *marks);
 /* FixedStepSolver.error / .iters (:383-389) of the steps that produced samples [s0, s1), s0 >= 1 (HOST, nullable) */
 int cnld_b200_td_info(cnld_td *t, cnld_uint s0, cnld_uint s1, double *error, int *iters);
 

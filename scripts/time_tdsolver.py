@@ -46,6 +46,12 @@ out = dict(config='FixedStepSolver on the device', P=P, nfir=nfir, steps=a.steps
            warm_steps=warm, warm_seconds=t_warm, seconds_per_step=per, steps_per_s=1 / per, table_gbs=fir.nbytes * (nfir - 1) / nfir / per / 1e9,
            convolutions_per_step_mean=float(it[warm:].mean()), contact_samples=int((st['x'] < kw['x0']).sum()),
            gpu_launches=_lib.launch_count() - l0, xmin=float(st['x'].min()))
+if os.environ.get('CNLD_B200_TD_TRACE'):
+    tr = s.trace(warm + 16, warm + 16 + 24).astype(np.int64)
+    rel = tr[:, :7] - tr[:, :1]
+    out['trace_us_from_kernel_start'] = (rel / 1e3).round(1).tolist()
+    out['trace_start_to_start_us'] = (np.diff(tr[:, 0]) / 1e3).round(1).tolist()
+    out['trace_wait_return_minus_prev_end_us'] = ((tr[1:, 2] - tr[:-1, 6]) / 1e3).round(1).tolist()
 if not a.no_cpu:
     import pyoracle as po
     n_cpu = 20                       # the oracle redoes the same samples from the device's history: ~10-30 s of host work

@@ -95,17 +95,24 @@ def test_fixed_step_solver_vs_reference_golden(po):
             free = s.displacement[:, 0] >= float(g[f'x0{c}'])
             assert np.array_equal(s.pressure_contact_spring[free], np.trunc(s.pressure_contact_spring[free]))
 
-        for _ in range(10):
+        for _ in range(10):                      # one table pass per sample ...
             s.step()
         assert s.current_step == 11 and _rel(s.displacement, g[f'x{c}'][:11]) < 1e-9
-        s.step(nsteps - 10)
+        s.step(nsteps - 10)                      # ... then blocks of 8 samples per pass (history / in-block lags split)
         check()
-        x_first = s.displacement.copy()
+        x_mixed = s.displacement.copy()
         s.reset()
         assert s.current_step == 1 and not s._db.x.any() and len(s.error) == 0
-        assert sum(1 for _ in s) == nsteps                                          # iterator protocol = solve()
+        assert sum(1 for _ in s) == nsteps                                          # iterator protocol, sample by sample
         check()
-        assert np.array_equal(x_first, s.displacement)                              # deterministic
+        assert _rel(s.displacement, x_mixed) < 1e-11                                # same sums, different association
+        s.reset()
+        s.solve()                                                                   # everything in one device call
+        check()
+        x_solve = s.displacement.copy()
+        s.reset()
+        s.solve()
+        assert np.array_equal(x_solve, s.displacement)                              # deterministic, bit for bit
         with pytest.raises(Exception):
             s.step(2)                                                               # past the time grid
         s.close()
@@ -142,6 +149,13 @@ def test_fixed_step_solver_vs_oracle_larger(po):
     for key in got:
         assert _rel(got[key], ref[key]) < 1e-9, key
     assert np.abs(err - ref['error']).max() < 1e-9 * np.abs(ref['x']).max()
+    dev.reset()                                  # sample by sample (one table pass each) against the blocked passes
+    for _ in range(nt - 1):
+        dev.step(1)
+    single = dev.state(0, nt)
+    assert np.array_equal(dev.info(1, nt)[1], it)
+    for key in got:
+        assert _rel(single[key], got[key]) < 1e-11, key
     dev.close()
     p = rng.standard_normal((50, P))
     assert _rel(sim.fir_conv_cy(fir, p, dt, 1), po.fir_conv(fir, p, dt, 1)) < 1e-12
