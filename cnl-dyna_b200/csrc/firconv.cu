@@ -403,33 +403,58 @@ k_fir_far(uint P, size_t ld, uint per, uint K, uint s0, const double *__restrict
 
 // out[j] = sum_i M[i * P + j] * (W ? w[i] : 1): the sources are dealt to G thread groups, the group sums are added
 // in group order (fixed association, independent of timing)
-// CG: M is global memory another kernel wrote -- read it through L2 (ld.global.cg), M in shared memory otherwise
+// CG: M is global memory another kernel wrote -- read it through L2 (ld.global.cg); otherwise M is in shared memory.
+// w (W only) is always in shared memory.  Pointer increments and 32-bit shared addresses: this loop is most of what
+// the single CTA of the step kernel executes.
+__device__ __forceinline__ double td_lds(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
 template <bool W, bool CG = false>
-__device__ void td_colsum(uint nsrc, uint P, const double *M, const double *w, double *gsum, double *out) {
-  auto ld = [&](size_t e) { return CG ? __ldcg(M + e) : M[e]; };
-  const uint T = TD_THREADS, Pp = min((P + 31u) & ~31u, T), G = T / Pp, g = threadIdx.x / Pp, jj = threadIdx.x % Pp;
+__device__ __forceinline__ void td_colsum(uint nsrc, uint P, const double *M, const double *w, double *gsum, double *out) {
+  const uint T = TD_THREADS, Pp = min((P + 31u) & ~31u, T), G = T / Pp, g = threadIdx.x / Pp, jj = threadIdx.x - g * Pp;
   const uint chunk = (nsrc + G - 1) / G;
   if (g < G) {
-    const uint i0 = min(nsrc, g * chunk), i1 = min(nsrc, i0 + chunk);
+    const uint i0 = min(nsrc, g * chunk), i1 = min(nsrc, i0 + chunk), n = i1 - i0;
+    const unsigned wb = W ? (unsigned)__cvta_generic_to_shared(w) + i0 * 8u : 0u;
     for (uint j = jj; j < P; j += Pp) {
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      uint i = i0;
-      for (; i + 3 < i1; i += 4) {
-        const double m0 = ld((size_t)i * P + j), m1 = ld((size_t)(i + 1) * P + j), m2 = ld((size_t)(i + 2) * P + j),
-                     m3 = ld((size_t)(i + 3) * P + j);
-        a0 = W ? fma(m0, w[i], a0) : a0 + m0;
-        a1 = W ? fma(m1, w[i + 1], a1) : a1 + m1;
-        a2 = W ? fma(m2, w[i + 2], a2) : a2 + m2;
-        a3 = W ? fma(m3, w[i + 3], a3) : a3 + m3;
+      const double *pg = M + (size_t)i0 * P + j;      // CG
+      unsigned ps = CG ? 0u : (unsigned)__cvta_generic_to_shared(M) + (i0 * P + j) * 8u, pw = wb;
+      const unsigned st = P * 8u;
+      uint i = 0;
+      for (; i + 3 < n; i += 4) {
+        double m0, m1, m2, m3;
+        if (CG) {
+          m0 = __ldcg(pg); m1 = __ldcg(pg + P); m2 = __ldcg(pg + 2 * (size_t)P); m3 = __ldcg(pg + 3 * (size_t)P);
+          pg += 4 * (size_t)P;
+        } else {
+          m0 = td_lds(ps); m1 = td_lds(ps + st); m2 = td_lds(ps + 2 * st); m3 = td_lds(ps + 3 * st);
+          ps += 4 * st;
+        }
+        if (W) {
+          a0 = fma(m0, td_lds(pw), a0);
+          a1 = fma(m1, td_lds(pw + 8), a1);
+          a2 = fma(m2, td_lds(pw + 16), a2);
+          a3 = fma(m3, td_lds(pw + 24), a3);
+          pw += 32;
+        } else {
+          a0 += m0; a1 += m1; a2 += m2; a3 += m3;
+        }
       }
-      for (; i < i1; i++) a0 = W ? fma(ld((size_t)i * P + j), w[i], a0) : a0 + ld((size_t)i * P + j);
+      for (; i < n; i++) {
+        double m0;
+        if (CG) { m0 = __ldcg(pg); pg += P; } else { m0 = td_lds(ps); ps += st; }
+        if (W) { a0 = fma(m0, td_lds(pw), a0); pw += 8; } else a0 += m0;
+      }
       gsum[(size_t)g * P + j] = (a0 + a1) + (a2 + a3);
     }
   }
   __syncthreads();
   for (uint j = threadIdx.x; j < P; j += T) {
     double s = 0.0;
-    for (uint q = 0; q < G; q++) s += gsum[(size_t)q * P + j];
+    for (uint q = 0; q < G; q++) s += gsum[q * P + j];
     out[j] = s;
   }
   __syncthreads();
@@ -444,14 +469,15 @@ struct TdSm {
   bool fir0_shared;
 };
 
-__device__ __noinline__ void td_far_sum(const TdArgs &a, const TdSm &m) {       // sum over the sources of the history pass
+__device__ __forceinline__ void td_far_sum(const TdArgs &a, const TdSm &m) {       // sum over the sources of the history pass
   td_colsum<false, true>(a.P, a.P, a.part, nullptr, m.gsum, m.tmp);
 }
 // tmp += sum over lags lo .. hi of fir[:, :, lag]^T p_tot[s - lag] (lags and sources flattened into one column sum)
-__device__ __noinline__ void td_near_sum(const TdArgs &a, const TdSm &m, uint lo, uint hi) {
+__device__ __forceinline__ void td_near_sum(const TdArgs &a, const TdSm &m, uint lo, uint hi) {
   const uint P = a.P, T = TD_THREADS, tid = threadIdx.x, n = (hi - lo + 1) * P;
   const double *pt_rows = a.state + (size_t)TD_PTOT * a.nt * P;
-  for (uint e = tid; e < n; e += T) m.wn[e] = __ldcg(pt_rows + (size_t)(a.s - lo - e / P) * P + e % P);
+  for (uint r = 0; r <= hi - lo; r++)
+    for (uint j = tid; j < P; j += T) m.wn[r * P + j] = __ldcg(pt_rows + (size_t)(a.s - lo - r) * P + j);
   __syncthreads();
   td_colsum<true, true>(n, P, a.firn + (size_t)(lo - 1) * P * P, m.wn, m.gsum, m.base);
   for (uint j = tid; j < P; j += T) m.tmp[j] += m.base[j];
@@ -460,7 +486,7 @@ __device__ __noinline__ void td_near_sum(const TdArgs &a, const TdSm &m, uint lo
 __device__ __noinline__ double td_pow_general(double a, double n) { return pow(a, n); }
 __device__ __forceinline__ double td_pow(double a, double n) { return n == 1.0 ? a : n == 2.0 ? a * a : td_pow_general(a, n); }
 
-__device__ __noinline__ void td_update_all(const TdArgs &a, const TdSm &m) {    // _update_all, simulation.pyx:412-421
+__device__ __forceinline__ void td_update_all(const TdArgs &a, const TdSm &m) {    // _update_all, simulation.pyx:412-421
   const uint P = a.P, T = TD_THREADS, tid = threadIdx.x;
   const bool first_free = m.x[0] >= a.x0;
   for (uint j = tid; j < P; j += T) {
@@ -474,7 +500,7 @@ __device__ __noinline__ void td_update_all(const TdArgs &a, const TdSm &m) {    
   }
   __syncthreads();
 }
-__device__ __noinline__ void td_update_dmp(const TdArgs &a, const TdSm &m) {    // _update_cont_dmp, :423-428
+__device__ __forceinline__ void td_update_dmp(const TdArgs &a, const TdSm &m) {    // _update_cont_dmp, :423-428
   const uint P = a.P, T = TD_THREADS, tid = threadIdx.x;
   const bool first_free = m.x[0] >= a.x0;
   for (uint j = tid; j < P; j += T) {
@@ -484,7 +510,7 @@ __device__ __noinline__ void td_update_dmp(const TdArgs &a, const TdSm &m) {    
   }
   __syncthreads();
 }
-__device__ __noinline__ double td_update_x(const TdArgs &a, const TdSm &m) {    // _update_x, :430-445
+__device__ __forceinline__ double td_update_x(const TdArgs &a, const TdSm &m) {    // _update_x, :430-445
   const uint P = a.P, T = TD_THREADS, tid = threadIdx.x;
   if (m.fir0_shared) td_colsum<true, false>(P, P, m.fir0, m.pt, m.gsum, m.tmp);
   else td_colsum<true, true>(P, P, m.fir0, m.pt, m.gsum, m.tmp);
