@@ -364,7 +364,7 @@ def bench_c5(args, rank, world, local):
 
 C4_METRIC = 'frequencies solved/s (ACA H-matrix assemble + GMRES, all 2304 source patches), 16x16 CMUT array'
 C4_H = dict(clf=16, eta=0.8, admis='2', strict=True, kmax=64)           # generate_db.py:264-275 defaults
-C4_SOLVE = dict(eps_aca=1e-2, tol=1e-6, restart=50, maxiter=300, batch=192)
+C4_SOLVE = dict(eps_aca=1e-2, tol=1e-6, restart=50, maxiter=300, batch=96)
 
 
 def _c4_cpu_sample(po, am, k, tree, frac=64, seed=0):
@@ -565,9 +565,15 @@ def main():
     ap.add_argument('--streams', type=int, default=6)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--general', action='store_true', help='general unpivoted LU of G instead of the symmetric-part path')
+    ap.add_argument('--c4-batch', type=int, default=0, help='c4: right-hand sides per GMRES batch (default: C4_SOLVE)')
+    ap.add_argument('--c4-restart', type=int, default=0, help='c4: GMRES restart length (default: C4_SOLVE)')
     ap.add_argument('--lu-outer', type=int, default=0, help='debug: outer LU block (multiple of 64)')
     ap.add_argument('--lu-reserve', type=int, default=-1, help='debug: SMs left free by the look-ahead trailing update')
     args = ap.parse_args()
+    if args.c4_batch:
+        C4_SOLVE['batch'] = args.c4_batch
+    if args.c4_restart:
+        C4_SOLVE['restart'] = args.c4_restart
 
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

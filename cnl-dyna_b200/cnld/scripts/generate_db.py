@@ -32,7 +32,7 @@ _Config = dict(freqs=(0, 50e6, 200e3), sound_speed=1500., fluid_rho=1000., array
                freq_interp=2)
 Config = abstract.register_type('Config', _Config)
 
-GMRES = dict(tol=1e-6, restart=50, maxiter=500, batch=192)    # the Krylov stand-in for the reference's H-LU
+GMRES = dict(tol=1e-6, restart=50, maxiter=500, batch=96)  # the Krylov stand-in for the reference's H-LU
 LAST_TIMING = {}      # wall seconds of the stages of the last main() call (setup, sweep + writer, finish, postprocess)
 
 
