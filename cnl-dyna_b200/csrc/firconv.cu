@@ -242,10 +242,14 @@ struct cnld_td {
   double dt = 0, e0 = 0, k = 0, n = 0, x0 = 0, lmbd = 0, atol = 0;
   int maxiter = 0;
   bool pdl = true;               // step kernel launched as a programmatic dependent of the convolution (CNLD_B200_TD_PDL=0: plain)
-  uint block = 8;                // samples per pass over the table (CNLD_B200_TD_BLOCK=1: one pass per sample)
+  uint block = 16;               // samples per pass over the table (CNLD_B200_TD_BLOCK=1: one pass per sample)
+  int mma = 1;                   // history pass on the FP64 tensor pipe over an interleaved second copy of the table;
+                                 // CNLD_B200_TD_MMA=0: the DFMA kernel on the row layout, blocks of 8, no second copy
   size_t ld = 0;                 // row stride of the device table: rows padded so that tap 1 sits on a 32-byte boundary
   double *tab = nullptr;         // tap 0 of row 0 (= d_fir + 3)
   double *d_firn = nullptr;      // fir[:, :, 1 .. TD_B - 1] as [lag - 1][source][destination]
+  double *d_tab8 = nullptr;      // mma == 1: second copy of the table, interleaved by tiles of 8 destinations (k_td_interleave)
+  size_t ng4 = 0;                // groups of 4 taps per row in that copy
   double *d_fir = nullptr, *d_fir0 = nullptr, *d_v = nullptr, *d_geff = nullptr, *d_hist = nullptr, *d_state = nullptr,
          *d_part = nullptr, *d_err = nullptr;
   int *d_iters = nullptr;
@@ -255,7 +259,7 @@ struct cnld_td {
 
 namespace {
 constexpr int TD_THREADS = 1024;
-constexpr int TD_B = 8;        // blocked stepping: samples served by one pass over the table
+constexpr int TD_B = 16;       // blocked stepping: at most this many samples are served by one pass over the table
 enum { TD_X = 0, TD_U, TD_PES, TD_SPR, TD_DMP, TD_PTOT, TD_NSTATE };
 
 struct TdArgs {
@@ -403,6 +407,116 @@ k_fir_far(uint P, size_t ld, uint per, uint K, uint s0, const double *__restrict
 
 // out[j] = sum_i M[i * P + j] * (W ? w[i] : 1): the sources are dealt to G thread groups, the group sums are added
 // in group order (fixed association, independent of timing)
+// The same history pass on the FP64 tensor pipe.  For one source i the pass is a product of the table rows with a
+// Toeplitz matrix of the window: part[n][i][j] = sum_t fir[i][j][1 + t] * W(t - n), an (8 destinations) x (taps) x
+// (8 lags) GEMM per row tile -- DMMA.8x8x4 with A = table entries straight from global memory (lane = (row, four taps):
+// two 16-byte loads of one sector give the A operands of four DMMAs), B = window values from shared memory (one
+// wavefront: the 32 lanes read 15 consecutive doubles), C = the 8 x 8 block of `part` (no shuffles, no reduction
+// over lanes).  Per KB of table: 2 LDG.128 + 4 NB LDS.64 + 4 NB DMMA instead of 2 + 12 + 64 DFMA per 128 taps -- the
+// L1TEX unit no longer limits the pass, and 16 lags (NB = 2) cost the same table traffic as 8.  The eight warps of a
+// CTA split the taps of a row tile; their C blocks are added in warp order.
+// Walking eight table rows at once, 128 bytes at a time in each, thrashes the DRAM pages (3.2 TB/s measured on the row
+// layout), so the pass reads a second copy of the table interleaved by row tiles (k_td_interleave): a warp request is
+// 1 KB contiguous.  Measured on the way: taps in the M dimension instead (one row per warp, n' = lag - m as columns)
+// needs no copy but NB + 1 column blocks, 184 us at 16 lags against 152 us here.
+__device__ __forceinline__ void fw_dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// tab8[((i * tiles + jt) * ng4 + g4) * 32 + r * 4 + u] = fir[i][8 jt + r][1 + 4 g4 + u]  (zero outside the table)
+__global__ void k_td_interleave(uint P, uint nfir, size_t ld, size_t ng4, const double *__restrict__ tab, double *tab8) {
+  const size_t tiles = (P + 7) >> 3, total = (size_t)P * tiles * ng4 * 32;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const uint u = e & 3, r = (e >> 2) & 7;
+    const size_t g4 = (e >> 5) % ng4, it = (e >> 5) / ng4, jt = it % tiles, i = it / tiles;
+    const size_t j = 8 * jt + r, tau = 1 + 4 * g4 + u;
+    tab8[e] = (j < P && tau < nfir) ? tab[(i * P + j) * ld + tau] : 0.0;
+  }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(FC_THREADS)
+k_fir_far_mma(uint P, size_t ng4, uint per, uint K, uint s0, const double *__restrict__ tab8, const double *__restrict__ h, size_t hs,
+              double *part) {
+  constexpr uint B = 8 * NB, NW = FC_THREADS / 32;
+  __shared__ __align__(16) double wbuf[FC_KTILE + B + 32];    // logical[q] = W(k0 + q - B)
+  __shared__ double red[NW][NB][64];
+  asm volatile("griddepcontrol.launch_dependents;");
+  const uint i = blockIdx.x, g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint j0 = g * per, j1 = min(P, j0 + per), r = lane >> 2, kq = lane & 3;
+  const double *hp = h + (size_t)i * hs;
+  const size_t PP = (size_t)P * P;
+  for (uint k0 = 0; k0 < K; k0 += FC_KTILE) {           // taps tau = 1 + k0 + t, t < kt
+    // a chunk = 16 taps: lane (row r, kq) takes the four taps 16 ch + 4 kq .. + 3 of its row (one 32-byte sector, the
+    // warp's request covers a 128-byte line in each of its eight rows) = the A operands of four DMMAs
+    const uint kt = min((uint)FC_KTILE, K - k0), nchunk = (kt + 15) >> 4, cpw = (nchunk + NW - 1) / NW;
+    __syncthreads();
+    for (uint q = threadIdx.x; q < 16 * nchunk + B + 1; q += FC_THREADS) {
+      const long long m = (long long)k0 + (long long)q - B;
+      wbuf[q] = (m >= 0 && m < (long long)s0) ? hp[s0 - 1 - m] : 0.0;
+    }
+    __syncthreads();
+    const uint c0 = min(nchunk, warp * cpw), c1 = min(nchunk, c0 + cpw);
+    for (uint jt = j0; jt < j1; jt += 8) {
+      // interleaved copy: [source][row tile][group of 4 taps][row 0..7][4 taps] -- the warp's request is 1 KB contiguous
+      const double *f = tab8 + ((((size_t)i * ((P + 7) >> 3) + (jt >> 3)) * ng4 + (k0 >> 2) + kq) * 8 + r) * 4;
+      double acc[NB][2];
+#pragma unroll
+      for (int nb = 0; nb < NB; nb++) acc[nb][0] = acc[nb][1] = 0.0;
+      auto load = [&](uint ch, double (&v)[4]) {        // zero past the end of the tile
+        const uint t = 16 * ch + 4 * kq;
+        if (t + 3 < kt) {
+          const double2 lo = __ldcs(reinterpret_cast<const double2 *>(f + 128 * ch)), hi = __ldcs(reinterpret_cast<const double2 *>(f + 128 * ch) + 1);
+          v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; u++) v[u] = t + u < kt ? f[128 * ch + u] : 0.0;
+        }
+      };
+      auto mma = [&](uint ch, const double (&v)[4]) {
+        const double *w = wbuf + 16 * ch + 4 * kq + B - r;         // lag n = 8 nb + r: logical[t - n + B]
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int nb = 0; nb < NB; nb++) fw_dmma(acc[nb][0], acc[nb][1], v[u], w[u - 8 * nb]);
+      };
+      // two pairs of chunks in rotation: a pair is reloaded right after its DMMAs and used again one pair later, so four
+      // to eight 16-byte loads per lane are in flight under the DMMAs of the other pair (no register copies)
+      double va[4], vb[4], vc[4], vd[4];
+      if (c0 < c1) load(c0, va);
+      if (c0 + 1 < c1) load(c0 + 1, vb);
+      for (uint ch = c0; ch < c1; ch += 4) {
+        if (ch + 2 < c1) load(ch + 2, vc);
+        if (ch + 3 < c1) load(ch + 3, vd);
+        mma(ch, va);
+        if (ch + 1 < c1) mma(ch + 1, vb);
+        if (ch + 4 < c1) load(ch + 4, va);
+        if (ch + 5 < c1) load(ch + 5, vb);
+        if (ch + 2 < c1) mma(ch + 2, vc);
+        if (ch + 3 < c1) mma(ch + 3, vd);
+      }
+#pragma unroll
+      for (int nb = 0; nb < NB; nb++) {
+        red[warp][nb][2 * lane] = acc[nb][0];
+        red[warp][nb][2 * lane + 1] = acc[nb][1];
+      }
+      __syncthreads();
+      // C fragment element e of lane l: row l / 4, lag 8 nb + 2 (l % 4) + e; the warps' blocks are added in warp order
+      for (uint e = threadIdx.x; e < NB * 64; e += FC_THREADS) {
+        const uint nb = e >> 6, x = e & 63, l = x >> 1, row = jt + (l >> 2), n = 8 * nb + 2 * (l & 3) + (x & 1);
+        double sum = 0.0;
+#pragma unroll
+        for (uint w = 0; w < NW; w++) sum += red[w][nb][x];
+        if (row < j1) {
+          double *dst = part + (size_t)n * PP + (size_t)i * P + row;
+          *dst = k0 ? *dst + sum : sum;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // CG: M is global memory another kernel wrote -- read it through L2 (ld.global.cg); otherwise M is in shared memory.
 // w (W only) is always in shared memory.  Pointer increments and 32-bit shared addresses: this loop is most of what
 // the single CTA of the step kernel executes.
@@ -685,7 +799,10 @@ int td_launch_block(cnld_td *t, uint s0, uint nb) {
   const size_t PP = (size_t)t->P * t->P;
   const uint K = t->ntap > 1 ? std::min(s0 + nb - 1, t->ntap - 1) : 0u;
   if (K) {
-    k_fir_far<TD_B><<<dim3(t->P, t->ngroup_far), FC_THREADS, 0, t->st>>>(t->P, t->ld, t->per_far, K, s0, t->tab, t->d_hist, t->nt, t->d_part);
+    const dim3 grid(t->P, t->ngroup_far);
+    if (!t->mma) k_fir_far<8><<<grid, FC_THREADS, 0, t->st>>>(t->P, t->ld, t->per_far, K, s0, t->tab, t->d_hist, t->nt, t->d_part);
+    else if (nb <= 8) k_fir_far_mma<1><<<grid, FC_THREADS, 0, t->st>>>(t->P, t->ng4, t->per_far, K, s0, t->d_tab8, t->d_hist, t->nt, t->d_part);
+    else k_fir_far_mma<2><<<grid, FC_THREADS, 0, t->st>>>(t->P, t->ng4, t->per_far, K, s0, t->d_tab8, t->d_hist, t->nt, t->d_part);
     CNLD_CK_LAUNCH();
   } else {
     CNLD_CK(cudaMemsetAsync(t->d_part, 0, sizeof(double) * PP * TD_B, t->st));
@@ -709,7 +826,9 @@ cnld_td *cnld_b200_td_create(int device, cnld_uint npatch, cnld_uint nfir, const
   t->device = device; t->P = npatch; t->nfir = nfir; t->nt = nt;
   t->dt = dt; t->e0 = e0; t->k = k; t->n = n; t->x0 = x0; t->lmbd = lmbd; t->atol = atol; t->maxiter = maxiter;
   if (const char *e = getenv("CNLD_B200_TD_PDL")) t->pdl = atoi(e) != 0;
+  if (const char *e = getenv("CNLD_B200_TD_MMA")) t->mma = atoi(e) != 0;
   if (const char *e = getenv("CNLD_B200_TD_BLOCK")) t->block = (uint)std::min(std::max(atoi(e), 1), TD_B);
+  if (!t->mma) t->block = std::min(t->block, 8u);
   t->ld = ((size_t)nfir + 3 + 3) & ~(size_t)3;
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
@@ -717,9 +836,11 @@ cnld_td *cnld_b200_td_create(int device, cnld_uint npatch, cnld_uint nfir, const
   t->per = (npatch + t->ngroup - 1) / t->ngroup;
   t->ngroup = (npatch + t->per - 1) / t->per;
   int occ_far = 4;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_far, k_fir_far<TD_B>, FC_THREADS, 0);
+  if (t->mma) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_far, k_fir_far_mma<2>, FC_THREADS, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_far, k_fir_far<8>, FC_THREADS, 0);
   t->ngroup_far = std::max(1u, std::min((npatch + 7) / 8, (uint)(std::max(occ_far, 1) * nsm) / npatch));
   t->per_far = (npatch + t->ngroup_far - 1) / t->ngroup_far;
+  if (t->mma == 1) t->per_far = (t->per_far + 7) & ~7u;          // whole tiles of 8 destinations per CTA
   t->ngroup_far = (npatch + t->per_far - 1) / t->per_far;
   const size_t PP = (size_t)npatch * npatch, tab = PP * t->ld + 4, rows = (size_t)nt * npatch;
   bool ok = cudaSetDevice(device) == cudaSuccess && cudaMalloc(&t->d_fir, sizeof(double) * tab) == cudaSuccess &&
@@ -742,8 +863,15 @@ cnld_td *cnld_b200_td_create(int device, cnld_uint npatch, cnld_uint nfir, const
     t->tab = t->d_fir + 3;
     k_td_gather_fir0<<<(unsigned)((PP + 255) / 256), 256, 0, t->st>>>(npatch, t->ld, t->tab, t->d_fir0);
     k_td_gather_near<<<(unsigned)((PP * (TD_B - 1) + 255) / 256), 256, 0, t->st>>>(npatch, nfir, t->ld, t->tab, t->d_firn);
+    if (t->mma == 1) {
+      t->ng4 = (((size_t)nfir + 3) / 4 + 3) & ~(size_t)3;       // whole chunks of 16 taps
+      const size_t n8 = (size_t)npatch * ((npatch + 7) / 8) * t->ng4 * 32;
+      ok = ok && cudaMalloc(&t->d_tab8, sizeof(double) * n8) == cudaSuccess;
+      if (ok) k_td_interleave<<<(unsigned)std::min<size_t>((n8 + 255) / 256, 1u << 20), 256, 0, t->st>>>(npatch, nfir, t->ld, t->ng4, t->tab, t->d_tab8);
+      count_launch();
+    }
     uint *d_last = reinterpret_cast<uint *>(t->d_iters);        // scratch until reset() clears it
-    ok = cudaMemsetAsync(d_last, 0, sizeof(uint), t->st) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(d_last, 0, sizeof(uint), t->st) == cudaSuccess;
     k_td_last_tap<<<(unsigned)((PP + 7) / 8), 256, 0, t->st>>>(PP, nfir, t->ld, t->tab, d_last);
     count_launch(3);
     ok = ok && cudaMemcpyAsync(&t->ntap, d_last, sizeof(uint), cudaMemcpyDeviceToHost, t->st) == cudaSuccess &&
@@ -760,7 +888,7 @@ cnld_td *cnld_b200_td_create(int device, cnld_uint npatch, cnld_uint nfir, const
 void cnld_b200_td_destroy(cnld_td *t) {
   if (!t) return;
   cudaSetDevice(t->device);
-  cudaFree(t->d_fir); cudaFree(t->d_fir0); cudaFree(t->d_firn); cudaFree(t->d_part); cudaFree(t->d_v); cudaFree(t->d_geff); cudaFree(t->d_hist);
+  cudaFree(t->d_fir); cudaFree(t->d_fir0); cudaFree(t->d_firn); cudaFree(t->d_tab8); cudaFree(t->d_part); cudaFree(t->d_v); cudaFree(t->d_geff); cudaFree(t->d_hist);
   cudaFree(t->d_state); cudaFree(t->d_err); cudaFree(t->d_iters); cudaFree(t->d_trace);
   if (t->st) cudaStreamDestroy(t->st);
   delete t;
