@@ -10,6 +10,8 @@
 // sits in shared memory and every warp streams whole contiguous table rows against it; the per-(j, i)
 // partial sums are reduced over i in a fixed order, so results do not depend on scheduling.
 // The stepping entry points keep the pressure history on the device too: a step uploads one row of P values.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -242,6 +244,7 @@ struct cnld_td {
   double dt = 0, e0 = 0, k = 0, n = 0, x0 = 0, lmbd = 0, atol = 0;
   int maxiter = 0;
   bool pdl = true;               // step kernel launched as a programmatic dependent of the convolution (CNLD_B200_TD_PDL=0: plain)
+  bool cluster = true;           // step kernel on a cluster of TD_CL CTAs (CNLD_B200_TD_CLUSTER=0: one CTA)
   uint block = 16;               // samples per pass over the table (CNLD_B200_TD_BLOCK=1: one pass per sample)
   int mma = 1;                   // history pass on the FP64 tensor pipe over an interleaved second copy of the table;
                                  // CNLD_B200_TD_MMA=0: the DFMA kernel on the row layout, blocks of 8, no second copy
@@ -600,12 +603,17 @@ __device__ __forceinline__ void td_near_sum(const TdArgs &a, const TdSm &m, uint
 __device__ __noinline__ double td_pow_general(double a, double n) { return pow(a, n); }
 __device__ __forceinline__ double td_pow(double a, double n) { return n == 1.0 ? a : n == 2.0 ? a * a : td_pow_general(a, n); }
 
-__device__ __forceinline__ void td_update_all(const TdArgs &a, const TdSm &m) {    // _update_all, simulation.pyx:412-421
+// the velocity of _update_all (:415) enters nothing inside the fixed point: it is evaluated where it is read, by the
+// damper update and for the stored row
+__device__ __forceinline__ void td_update_u(const TdArgs &a, const TdSm &m) {
+  for (uint j = threadIdx.x; j < a.P; j += TD_THREADS) m.u[j] = a.s ? (m.x[j] - m.xp[j]) / a.dt : 0.0;
+  __syncthreads();
+}
+__device__ __forceinline__ void td_update_all(const TdArgs &a, const TdSm &m) {    // _update_all, simulation.pyx:412-421 (without u)
   const uint P = a.P, T = TD_THREADS, tid = threadIdx.x;
   const bool first_free = m.x[0] >= a.x0;
   for (uint j = tid; j < P; j += T) {
     const double xj = m.x[j], d = xj + m.ge[j];
-    m.u[j] = a.s ? (xj - m.xp[j]) / a.dt : 0.0;
     m.pes[j] = (a.e0h * (m.v[j] * m.v[j])) / (d * d);
     double c = xj >= a.x0 ? 0.0 : a.k * td_pow(a.x0 - xj, a.n);
     if (first_free) c = trunc(c);
@@ -624,10 +632,9 @@ __device__ __forceinline__ void td_update_dmp(const TdArgs &a, const TdSm &m) { 
   }
   __syncthreads();
 }
-__device__ __forceinline__ double td_update_x(const TdArgs &a, const TdSm &m) {    // _update_x, :430-445
+// second half of _update_x (:436-443): x <- base + dt * tmp, returns max|dx|
+__device__ __forceinline__ double td_finish_x(const TdArgs &a, const TdSm &m) {
   const uint P = a.P, T = TD_THREADS, tid = threadIdx.x;
-  if (m.fir0_shared) td_colsum<true, false>(P, P, m.fir0, m.pt, m.gsum, m.tmp);
-  else td_colsum<true, true>(P, P, m.fir0, m.pt, m.gsum, m.tmp);
   double e = 0.0;
   for (uint j = tid; j < P; j += T) {
     const double xn = __dadd_rn(m.base[j], __dmul_rn(m.tmp[j], a.dt));
@@ -648,6 +655,11 @@ __device__ __forceinline__ double td_update_x(const TdArgs &a, const TdSm &m) { 
   }
   __syncthreads();
   return e;
+}
+__device__ __forceinline__ double td_update_x(const TdArgs &a, const TdSm &m) {    // _update_x, :430-445
+  if (m.fir0_shared) td_colsum<true, false>(a.P, a.P, m.fir0, m.pt, m.gsum, m.tmp);
+  else td_colsum<true, true>(a.P, a.P, m.fir0, m.pt, m.gsum, m.tmp);
+  return td_finish_x(a, m);
 }
 
 __global__ void __launch_bounds__(TD_THREADS) k_td_step(TdArgs a) {
@@ -714,6 +726,7 @@ __global__ void __launch_bounds__(TD_THREADS) k_td_step(TdArgs a) {
 #pragma unroll 1
     for (;;) {
       if (need_dmp) {
+        td_update_u(a, m);
         td_update_dmp(a, m);
         need_dmp = false;
       }
@@ -739,6 +752,7 @@ __global__ void __launch_bounds__(TD_THREADS) k_td_step(TdArgs a) {
     }
     td_mark(a, 5);
   }
+  td_update_u(a, m);
   for (uint j = tid; j < P; j += T) {
     const size_t r = (size_t)s * P + j;
     S[TD_X * plane + r] = m.x[j];
@@ -752,6 +766,208 @@ __global__ void __launch_bounds__(TD_THREADS) k_td_step(TdArgs a) {
   td_mark(a, 6);
 }
 
+// ---- the step kernel on a cluster of TD_CL CTAs ----------------------------------------------------------------
+// Same program, but the products over the sources are dealt to the CTAs of a thread-block cluster: CTA c owns a slice
+// of the sources, keeps its rows of fir[:, :, 0] in REGISTERS for the whole kernel (6 doubles per thread at P = 144:
+// the single-CTA kernel re-reads 166 KB of shared memory per fixed-point iteration and is bound by that), sums its
+// slice, writes the partial sums into every CTA's shared memory (distributed shared memory) and, after one cluster
+// barrier, every CTA adds the TD_CL partial vectors in rank order.  Everything else -- electrostatic and contact
+// pressures, the error norm, the control flow -- is computed redundantly by every CTA from identical inputs with
+// identical instructions, so all CTAs take the same branches and meet at the same barriers.  Rank 0 writes the rows.
+constexpr int TD_CL = 4, TD_MR = 8;       // cluster size; fir[:, :, 0] rows per thread kept in registers (at most)
+namespace cg = cooperative_groups;
+
+struct TdCl {
+  double *gsum, *gpart;                   // [G][P] group sums of this CTA; [2][TD_CL][P] partial vectors of all CTAs
+  uint rank, buf;
+};
+
+// out[j] = sum over ALL sources i < nsrc of M[i * P + j] * (W ? w[i] : 1); REG: this thread's entries of M are in mreg
+template <bool W, bool REG>
+__device__ __forceinline__ void td_cl_colsum(cg::cluster_group &cl, TdCl &c, uint nsrc, uint P, const double *M, const double *w,
+                                             const double (&mreg)[TD_MR], double *out) {
+  const uint T = TD_THREADS, Pp = min((P + 31u) & ~31u, T), G = T / Pp, g = threadIdx.x / Pp, jj = threadIdx.x - g * Pp;
+  const uint per = (nsrc + TD_CL - 1) / TD_CL, lo = min(nsrc, c.rank * per), nc = min(nsrc, lo + per) - lo;
+  const uint chunk = (nc + G - 1) / G;
+  if (g < G) {
+    const uint o0 = min(nc, g * chunk), n = min(nc, o0 + chunk) - o0, i0 = lo + o0;
+    const unsigned wb = W ? (unsigned)__cvta_generic_to_shared(w) + i0 * 8u : 0u;
+    for (uint j = jj; j < P; j += Pp) {
+      double a0 = 0.0, a1 = 0.0;
+      if (REG) {
+#pragma unroll
+        for (int q = 0; q < TD_MR; q += 2) {
+          if (q < (int)n) a0 = fma(mreg[q], td_lds(wb + 8 * q), a0);
+          if (q + 1 < (int)n) a1 = fma(mreg[q + 1], td_lds(wb + 8 * q + 8), a1);
+        }
+      } else {
+        const double *pg = M + (size_t)i0 * P + j;
+        unsigned pw = wb;
+        uint i = 0;
+        for (; i + 1 < n; i += 2) {
+          const double m0 = __ldcg(pg), m1 = __ldcg(pg + P);
+          pg += 2 * (size_t)P;
+          if (W) {
+            a0 = fma(m0, td_lds(pw), a0);
+            a1 = fma(m1, td_lds(pw + 8), a1);
+            pw += 16;
+          } else {
+            a0 += m0;
+            a1 += m1;
+          }
+        }
+        if (i < n) a0 = W ? fma(__ldcg(pg), td_lds(pw), a0) : a0 + __ldcg(pg);
+      }
+      c.gsum[(size_t)g * P + j] = a0 + a1;
+    }
+  }
+  __syncthreads();
+  double *mine = c.gpart + ((size_t)c.buf * TD_CL + c.rank) * P;
+  for (uint j = threadIdx.x; j < P; j += T) {
+    double sum = 0.0;
+    for (uint q = 0; q < G; q++) sum += c.gsum[q * P + j];
+#pragma unroll
+    for (uint r = 0; r < TD_CL; r++) cl.map_shared_rank(mine, r)[j] = sum;
+  }
+  cl.sync();
+  const double *all = c.gpart + (size_t)c.buf * TD_CL * P;
+  for (uint j = threadIdx.x; j < P; j += T) {
+    double sum = 0.0;
+#pragma unroll
+    for (uint r = 0; r < TD_CL; r++) sum += all[r * P + j];
+    out[j] = sum;
+  }
+  c.buf ^= 1u;          // the next product writes the other buffer: a CTA one barrier ahead cannot overwrite what a slower one still reads
+  __syncthreads();
+}
+
+__global__ void __cluster_dims__(TD_CL, 1, 1) __launch_bounds__(TD_THREADS) k_td_step_cl(TdArgs a) {
+  extern __shared__ double sm[];
+  cg::cluster_group cl = cg::this_cluster();
+  const uint P = a.P, T = TD_THREADS, tid = threadIdx.x, s = a.s;
+  const uint Pp = min((P + 31u) & ~31u, T), G = T / Pp;
+  TdSm m;
+  m.base = sm; m.x = m.base + P; m.xp = m.x + P; m.u = m.xp + P; m.pes = m.u + P; m.spr = m.pes + P; m.dmp = m.spr + P;
+  m.pt = m.dmp + P; m.v = m.pt + P; m.ge = m.v + P; m.tmp = m.ge + P; m.wn = m.tmp + P; m.red = m.wn + (size_t)(TD_B - 1) * P;
+  m.gsum = m.red + 32;
+  m.fir0 = a.fir0;
+  m.fir0_shared = false;
+  TdCl c;
+  c.gsum = m.gsum;
+  c.gpart = m.gsum + (size_t)G * P;
+  c.rank = cl.block_rank();
+  c.buf = 0;
+  double *S = a.state;
+  const size_t plane = (size_t)a.nt * P, PP = (size_t)P * P;
+  const bool lead = c.rank == 0;
+  if (lead) td_mark(a, 0);
+  // this thread's entries of fir[:, :, 0]: sources of this CTA's slice, group g, destination jj (constants of the run)
+  double mreg[TD_MR];
+  {
+    const uint g = tid / Pp, jj = tid - g * Pp, per = (P + TD_CL - 1) / TD_CL, lo = min(P, c.rank * per), nc = min(P, lo + per) - lo;
+    const uint chunk = (nc + G - 1) / G, o0 = min(nc, g * chunk), n = g < G ? min(nc, o0 + chunk) - o0 : 0u;
+#pragma unroll
+    for (int q = 0; q < TD_MR; q++) mreg[q] = (q < (int)n && jj < P) ? a.fir0[(size_t)(lo + o0 + q) * P + jj] : 0.0;
+  }
+  const bool reg = a.stage != 0;          // host: P <= TD_THREADS and at most TD_MR rows per thread
+  for (uint j = tid; j < P; j += T) {
+    m.v[j] = a.v[(size_t)s * P + j];
+    m.ge[j] = a.geff[j];
+    m.dmp[j] = 0.0;
+    m.x[j] = 0.0;
+    m.tmp[j] = 0.0;
+  }
+  __syncthreads();
+  cl.sync();                               // every CTA of the cluster is resident before the first remote store
+  const double *pt_rows = S + (size_t)TD_PTOT * plane;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {              // 0: before the dependency is met, 1: after (see k_td_step)
+    if (pass) {
+      if (lead) td_mark(a, 1);
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      asm volatile("griddepcontrol.launch_dependents;");
+      if (lead) td_mark(a, 2);
+      for (uint j = tid; j < P; j += T) m.xp[j] = s ? S[TD_X * plane + (size_t)(s - 1) * P + j] : 0.0;
+    }
+    if (s && (pass == 0) == (a.early != 0)) td_cl_colsum<false, false>(cl, c, P, P, a.part, nullptr, mreg, m.tmp);
+    const uint lo = pass ? 1u : 2u, hi = pass ? (a.early ? min(a.near, 1u) : a.near) : (a.early ? a.near : 0u);
+    if (s && hi >= lo) {
+      for (uint r = 0; r <= hi - lo; r++)
+        for (uint j = tid; j < P; j += T) m.wn[r * P + j] = __ldcg(pt_rows + (size_t)(s - lo - r) * P + j);
+      __syncthreads();
+      td_cl_colsum<true, false>(cl, c, (hi - lo + 1) * P, P, a.firn + (size_t)(lo - 1) * PP, m.wn, mreg, m.base);
+      for (uint j = tid; j < P; j += T) m.tmp[j] += m.base[j];
+      __syncthreads();
+    }
+  }
+  if (s == 0) {
+    td_update_all(a, m);
+  } else {
+    for (uint j = tid; j < P; j += T) m.x[j] = m.base[j] = m.tmp[j] * a.dt;
+    __syncthreads();
+    if (lead) td_mark(a, 3);
+    int phase = 0, q = 0, it = 2;
+    bool need_dmp = false;
+    double err = 0.0;
+#pragma unroll 1
+    for (;;) {
+      if (need_dmp) {
+        td_update_u(a, m);
+        td_update_dmp(a, m);
+        need_dmp = false;
+      }
+      td_update_all(a, m);
+      if (q == 0 || (q < a.maxiter && !(err <= a.atol))) {
+        if (reg) td_cl_colsum<true, true>(cl, c, P, P, a.fir0, m.pt, mreg, m.tmp);
+        else td_cl_colsum<true, false>(cl, c, P, P, a.fir0, m.pt, mreg, m.tmp);
+        err = td_finish_x(a, m);
+        if (q > 0) it++;
+        q++;
+        continue;
+      }
+      if (phase == 0) {
+        if (lead) td_mark(a, 4);
+        phase = 1;
+        q = 0;
+        need_dmp = true;
+        continue;
+      }
+      break;
+    }
+    if (lead && tid == 0) {
+      a.err[s] = err;
+      a.iters[s] = it;
+    }
+    if (lead) td_mark(a, 5);
+  }
+  td_update_u(a, m);
+  if (lead) {
+    for (uint j = tid; j < P; j += T) {
+      const size_t r = (size_t)s * P + j;
+      S[TD_X * plane + r] = m.x[j];
+      S[TD_U * plane + r] = m.u[j];
+      S[TD_PES * plane + r] = m.pes[j];
+      S[TD_SPR * plane + r] = m.spr[j];
+      S[TD_DMP * plane + r] = m.dmp[j];
+      S[TD_PTOT * plane + r] = m.pt[j];
+      a.hist[(size_t)j * a.nt + s] = m.pt[j];
+    }
+    td_mark(a, 6);
+  }
+  cl.sync();                               // no CTA leaves while another may still address its shared memory
+}
+
+size_t td_smem_cl(uint P) {
+  const uint Pp = std::min((P + 31u) & ~31u, (uint)TD_THREADS), G = TD_THREADS / Pp;
+  return sizeof(double) * ((size_t)(10 + TD_B) * P + 32 + (size_t)G * P + (size_t)2 * TD_CL * P);
+}
+// the register path of the cluster kernel: every destination has its own thread and a thread holds at most TD_MR rows
+bool td_cl_reg(uint P) {
+  if (P > (uint)TD_THREADS) return false;
+  const uint Pp = std::min((P + 31u) & ~31u, (uint)TD_THREADS), G = TD_THREADS / Pp, nc = (P + TD_CL - 1) / TD_CL;
+  return (nc + G - 1) / G <= (uint)TD_MR;
+}
+
 size_t td_smem_base(uint P) {
   const uint Pp = std::min((P + 31u) & ~31u, (uint)TD_THREADS), G = TD_THREADS / Pp;
   return sizeof(double) * (((size_t)(10 + TD_B) * P + 32 + (size_t)G * P + 1) & ~(size_t)1);
@@ -760,20 +976,22 @@ bool td_stage(uint P) { return td_smem_base(P) + sizeof(double) * P * P <= 224 *
 size_t td_smem(uint P) { return td_smem_base(P) + (td_stage(P) ? sizeof(double) * P * P : 0); }
 
 int td_launch_kernel(cnld_td *t, uint s, uint near, uint early, const double *part) {
-  TdArgs a{t->P, t->nt, s, t->dt, -t->e0 / 2, t->k, t->n, t->x0, t->lmbd, t->atol, t->maxiter, td_stage(t->P) ? 1 : 0, near,
+  const int stage = t->cluster ? (td_cl_reg(t->P) ? 1 : 0) : (td_stage(t->P) ? 1 : 0);
+  TdArgs a{t->P, t->nt, s, t->dt, -t->e0 / 2, t->k, t->n, t->x0, t->lmbd, t->atol, t->maxiter, stage, near,
            t->pdl ? early : 0u, t->d_firn, t->d_fir0, t->d_v, t->d_geff, part, t->d_hist, t->d_state, t->d_err, t->d_iters,
            t->d_trace};
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(1);
+  cfg.gridDim = dim3(t->cluster ? TD_CL : 1);
   cfg.blockDim = dim3(TD_THREADS);
-  cfg.dynamicSmemBytes = td_smem(t->P);
+  cfg.dynamicSmemBytes = t->cluster ? td_smem_cl(t->P) : td_smem(t->P);
   cfg.stream = t->st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = t->pdl ? 1 : 0;
-  CNLD_CK(cudaLaunchKernelEx(&cfg, k_td_step, a));
+  if (t->cluster) CNLD_CK(cudaLaunchKernelEx(&cfg, k_td_step_cl, a));
+  else CNLD_CK(cudaLaunchKernelEx(&cfg, k_td_step, a));
   CNLD_CK_LAUNCH();
   return 0;
 }
@@ -826,6 +1044,8 @@ cnld_td *cnld_b200_td_create(int device, cnld_uint npatch, cnld_uint nfir, const
   t->device = device; t->P = npatch; t->nfir = nfir; t->nt = nt;
   t->dt = dt; t->e0 = e0; t->k = k; t->n = n; t->x0 = x0; t->lmbd = lmbd; t->atol = atol; t->maxiter = maxiter;
   if (const char *e = getenv("CNLD_B200_TD_PDL")) t->pdl = atoi(e) != 0;
+  if (const char *e = getenv("CNLD_B200_TD_CLUSTER")) t->cluster = atoi(e) != 0;
+  if (td_smem_cl(npatch) > 200 * 1024) t->cluster = false;
   if (const char *e = getenv("CNLD_B200_TD_MMA")) t->mma = atoi(e) != 0;
   if (const char *e = getenv("CNLD_B200_TD_BLOCK")) t->block = (uint)std::min(std::max(atoi(e), 1), TD_B);
   if (!t->mma) t->block = std::min(t->block, 8u);
@@ -858,7 +1078,9 @@ cnld_td *cnld_b200_td_create(int device, cnld_uint npatch, cnld_uint nfir, const
             cudaMemcpy(t->d_v, v, sizeof(double) * rows, cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaMemcpy(t->d_geff, gap_eff, sizeof(double) * npatch, cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaFuncSetAttribute(k_td_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+            cudaFuncSetAttribute(k_td_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+            (!t->cluster ||
+             cudaFuncSetAttribute(k_td_step_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)td_smem_cl(npatch)) == cudaSuccess);
   if (ok) {
     t->tab = t->d_fir + 3;
     k_td_gather_fir0<<<(unsigned)((PP + 255) / 256), 256, 0, t->st>>>(npatch, t->ld, t->tab, t->d_fir0);
