@@ -250,19 +250,25 @@ struct cnld_td {
                                  // CNLD_B200_TD_MMA=0: the DFMA kernel on the row layout, blocks of 8, no second copy
   size_t ld = 0;                 // row stride of the device table: rows padded so that tap 1 sits on a 32-byte boundary
   double *tab = nullptr;         // tap 0 of row 0 (= d_fir + 3)
-  double *d_firn = nullptr;      // fir[:, :, 1 .. TD_B - 1] as [lag - 1][source][destination]
+  double *d_firn = nullptr;      // fir[:, :, 1 .. TD_NL] as [lag - 1][source][destination]
   double *d_tab8 = nullptr;      // mma == 1: second copy of the table, interleaved by tiles of 8 destinations (k_td_interleave)
   size_t ng4 = 0;                // groups of 4 taps per row in that copy
   double *d_fir = nullptr, *d_fir0 = nullptr, *d_v = nullptr, *d_geff = nullptr, *d_hist = nullptr, *d_state = nullptr,
          *d_part = nullptr, *d_err = nullptr;
   int *d_iters = nullptr;
   unsigned long long *d_trace = nullptr;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr, st2 = nullptr;       // st2: run-ahead history passes (lower priority)
+  cudaEvent_t ev_hist = nullptr, ev_far = nullptr;
+  bool overlap = true;           // history pass of block k + 1 under the samples of block k (CNLD_B200_TD_OVERLAP=0: in line)
+  uint pbuf = 0;                 // plane buffer (of two) the current block reads
+  uint ngroup_narrow = 1, per_narrow = 0;
 };
 
 namespace {
 constexpr int TD_THREADS = 1024;
 constexpr int TD_B = 16;       // blocked stepping: at most this many samples are served by one pass over the table
+constexpr int TD_NL = 2 * TD_B - 1;   // lags the step kernels add themselves: the block's own samples and, when the history
+                                      // pass ran ahead under the previous block, that block's samples too
 enum { TD_X = 0, TD_U, TD_PES, TD_SPR, TD_DMP, TD_PTOT, TD_NSTATE };
 
 struct TdArgs {
@@ -271,7 +277,7 @@ struct TdArgs {
   int maxiter, stage;                     // stage: fir[:, :, 0] fits in shared memory next to the work vectors
   uint near;                              // blocked stepping: lags 1 .. near are added from the block's own samples
   uint early;                             // the history pass and the samples up to s - 2 are complete when this kernel starts
-  const double *firn;                     // fir[:, :, 1 .. TD_B - 1] as [lag - 1][source][destination]
+  const double *firn;                     // fir[:, :, 1 .. TD_NL] as [lag - 1][source][destination]
   const double *fir0, *v, *geff, *part;
   double *hist, *state, *err;
   int *iters;
@@ -303,10 +309,10 @@ __global__ void k_td_last_tap(size_t rows, uint nfir, size_t ld, const double *_
   if ((threadIdx.x & 31) == 0 && best) atomicMax(last, best);
 }
 
-// firn[lag - 1][i][j] = fir[i][j][lag], lag = 1 .. TD_B - 1 (zero beyond the table)
+// firn[lag - 1][i][j] = fir[i][j][lag], lag = 1 .. TD_NL (zero beyond the table)
 __global__ void k_td_gather_near(uint P, uint nfir, size_t ld, const double *__restrict__ tab, double *firn) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x, PP = (size_t)P * P;
-  if (e >= PP * (TD_B - 1)) return;
+  if (e >= PP * TD_NL) return;
   const uint lag = (uint)(e / PP) + 1;
   firn[e] = lag < nfir ? tab[(e % PP) * ld + lag] : 0.0;
 }
@@ -439,10 +445,12 @@ __global__ void k_td_interleave(uint P, uint nfir, size_t ld, size_t ng4, const 
 
 template <int NB>
 __global__ void __launch_bounds__(FC_THREADS)
-k_fir_far_mma(uint P, size_t ng4, uint per, uint K, uint s0, const double *__restrict__ tab8, const double *__restrict__ h, size_t hs,
-              double *part) {
+k_fir_far_mma(uint P, size_t ng4, uint per, uint K, uint s0, uint lag0, const double *__restrict__ tab8, const double *__restrict__ h,
+              size_t hs, double *part) {
+  // lag0 > 0: the pass runs ahead -- s0 is the first sample of the block BEFORE the one it serves, the lags are
+  // lag0 + n (rows >= s0 are not known yet; the step kernels add them)
   constexpr uint B = 8 * NB, NW = FC_THREADS / 32;
-  __shared__ __align__(16) double wbuf[FC_KTILE + B + 32];    // logical[q] = W(k0 + q - B)
+  __shared__ __align__(16) double wbuf[FC_KTILE + B + 32];    // logical[q] = W(k0 + q - B - lag0)
   __shared__ double red[NW][NB][64];
   asm volatile("griddepcontrol.launch_dependents;");
   const uint i = blockIdx.x, g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -455,7 +463,7 @@ k_fir_far_mma(uint P, size_t ng4, uint per, uint K, uint s0, const double *__res
     const uint kt = min((uint)FC_KTILE, K - k0), nchunk = (kt + 15) >> 4, cpw = (nchunk + NW - 1) / NW;
     __syncthreads();
     for (uint q = threadIdx.x; q < 16 * nchunk + B + 1; q += FC_THREADS) {
-      const long long m = (long long)k0 + (long long)q - B;
+      const long long m = (long long)k0 + (long long)q - B - lag0;
       wbuf[q] = (m >= 0 && m < (long long)s0) ? hp[s0 - 1 - m] : 0.0;
     }
     __syncthreads();
@@ -667,7 +675,7 @@ __global__ void __launch_bounds__(TD_THREADS) k_td_step(TdArgs a) {
   const uint P = a.P, T = TD_THREADS, tid = threadIdx.x, s = a.s;
   TdSm m;
   m.base = sm; m.x = m.base + P; m.xp = m.x + P; m.u = m.xp + P; m.pes = m.u + P; m.spr = m.pes + P; m.dmp = m.spr + P;
-  m.pt = m.dmp + P; m.v = m.pt + P; m.ge = m.v + P; m.tmp = m.ge + P; m.wn = m.tmp + P; m.red = m.wn + (size_t)(TD_B - 1) * P;
+  m.pt = m.dmp + P; m.v = m.pt + P; m.ge = m.v + P; m.tmp = m.ge + P; m.wn = m.tmp + P; m.red = m.wn + (size_t)TD_NL * P;
   m.gsum = m.red + 32;
   m.fir0 = a.fir0;
   m.fir0_shared = a.stage != 0;
@@ -681,7 +689,7 @@ __global__ void __launch_bounds__(TD_THREADS) k_td_step(TdArgs a) {
   // before the wait as well, through L2.
   if (a.stage) {
     const uint Pp = min((P + 31u) & ~31u, T), G = T / Pp;
-    double *f0s = sm + (((size_t)(10 + TD_B) * P + 32 + (size_t)G * P + 1) & ~(size_t)1);   // 16-byte aligned
+    double *f0s = sm + (((size_t)(11 + TD_NL) * P + 32 + (size_t)G * P + 1) & ~(size_t)1);   // 16-byte aligned
     const size_t n2 = PP / 2;
     const double2 *src = reinterpret_cast<const double2 *>(a.fir0);
     double2 *dst = reinterpret_cast<double2 *>(f0s);
@@ -848,7 +856,7 @@ __global__ void __cluster_dims__(TD_CL, 1, 1) __launch_bounds__(TD_THREADS) k_td
   const uint Pp = min((P + 31u) & ~31u, T), G = T / Pp;
   TdSm m;
   m.base = sm; m.x = m.base + P; m.xp = m.x + P; m.u = m.xp + P; m.pes = m.u + P; m.spr = m.pes + P; m.dmp = m.spr + P;
-  m.pt = m.dmp + P; m.v = m.pt + P; m.ge = m.v + P; m.tmp = m.ge + P; m.wn = m.tmp + P; m.red = m.wn + (size_t)(TD_B - 1) * P;
+  m.pt = m.dmp + P; m.v = m.pt + P; m.ge = m.v + P; m.tmp = m.ge + P; m.wn = m.tmp + P; m.red = m.wn + (size_t)TD_NL * P;
   m.gsum = m.red + 32;
   m.fir0 = a.fir0;
   m.fir0_shared = false;
@@ -959,7 +967,7 @@ __global__ void __cluster_dims__(TD_CL, 1, 1) __launch_bounds__(TD_THREADS) k_td
 
 size_t td_smem_cl(uint P) {
   const uint Pp = std::min((P + 31u) & ~31u, (uint)TD_THREADS), G = TD_THREADS / Pp;
-  return sizeof(double) * ((size_t)(10 + TD_B) * P + 32 + (size_t)G * P + (size_t)2 * TD_CL * P);
+  return sizeof(double) * ((size_t)(11 + TD_NL) * P + 32 + (size_t)G * P + (size_t)2 * TD_CL * P);
 }
 // the register path of the cluster kernel: every destination has its own thread and a thread holds at most TD_MR rows
 bool td_cl_reg(uint P) {
@@ -970,7 +978,7 @@ bool td_cl_reg(uint P) {
 
 size_t td_smem_base(uint P) {
   const uint Pp = std::min((P + 31u) & ~31u, (uint)TD_THREADS), G = TD_THREADS / Pp;
-  return sizeof(double) * (((size_t)(10 + TD_B) * P + 32 + (size_t)G * P + 1) & ~(size_t)1);
+  return sizeof(double) * (((size_t)(11 + TD_NL) * P + 32 + (size_t)G * P + 1) & ~(size_t)1);
 }
 bool td_stage(uint P) { return td_smem_base(P) + sizeof(double) * P * P <= 224 * 1024; }
 size_t td_smem(uint P) { return td_smem_base(P) + (td_stage(P) ? sizeof(double) * P * P : 0); }
@@ -1011,22 +1019,76 @@ int td_launch_step(cnld_td *t, uint s) {
   return td_launch_kernel(t, s, 0, 0, t->d_part);
 }
 
-// nb <= TD_B samples starting at s0 >= 1: one pass over the table for what the history before s0 contributes to all of
-// them (k_fir_far), then the step kernels, each adding the lags that reach into the block from fir[:, :, 1 .. nb - 1]
-int td_launch_block(cnld_td *t, uint s0, uint nb) {
-  const size_t PP = (size_t)t->P * t->P;
-  const uint K = t->ntap > 1 ? std::min(s0 + nb - 1, t->ntap - 1) : 0u;
-  if (K) {
-    const dim3 grid(t->P, t->ngroup_far);
-    if (!t->mma) k_fir_far<8><<<grid, FC_THREADS, 0, t->st>>>(t->P, t->ld, t->per_far, K, s0, t->tab, t->d_hist, t->nt, t->d_part);
-    else if (nb <= 8) k_fir_far_mma<1><<<grid, FC_THREADS, 0, t->st>>>(t->P, t->ng4, t->per_far, K, s0, t->d_tab8, t->d_hist, t->nt, t->d_part);
-    else k_fir_far_mma<2><<<grid, FC_THREADS, 0, t->st>>>(t->P, t->ng4, t->per_far, K, s0, t->d_tab8, t->d_hist, t->nt, t->d_part);
-    CNLD_CK_LAUNCH();
-  } else {
-    CNLD_CK(cudaMemsetAsync(t->d_part, 0, sizeof(double) * PP * TD_B, t->st));
+// What a run-ahead history pass could not know: the TD_B samples of the block before the one it serves.
+//   part[n][i][j] += sum_{r < TD_B} fir[i][j][n + TD_B - r] * p_tot[s0 - TD_B + r][i],   n = 0 .. TD_B - 1
+// from the compact copy of the first TD_NL lags (5 MB at C3, L2): CTA = source i, thread = destination j holds its
+// 31 lags in registers.  Runs once per block between the previous block's last sample and this block's first.
+__global__ void __launch_bounds__(256) k_fir_mid(uint P, uint s0, const double *__restrict__ firn, const double *__restrict__ pt_rows,
+                                                 double *part) {
+  __shared__ double pv[TD_B];
+  asm volatile("griddepcontrol.launch_dependents;");
+  const uint i = blockIdx.x;
+  const size_t PP = (size_t)P * P;
+  if (threadIdx.x < TD_B) pv[threadIdx.x] = pt_rows[(size_t)(s0 - TD_B + threadIdx.x) * P + i];
+  __syncthreads();
+  for (uint j = threadIdx.x; j < P; j += blockDim.x) {
+    double f[TD_NL];
+#pragma unroll
+    for (int l = 0; l < TD_NL; l++) f[l] = __ldcg(firn + (size_t)l * PP + (size_t)i * P + j);     // lag l + 1
+#pragma unroll
+    for (int n = 0; n < TD_B; n++) {
+      double acc = 0.0;
+#pragma unroll
+      for (int r = 0; r < TD_B; r++) acc = fma(f[n + TD_B - r - 1], pv[r], acc);
+      part[(size_t)n * PP + (size_t)i * P + j] += acc;
+    }
   }
-  for (uint b = 0; b < nb; b++)
-    if (td_launch_kernel(t, s0 + b, t->ntap > 1 ? std::min(b, t->ntap - 1) : 0u, b >= 1, t->d_part + (size_t)b * PP)) return -1;
+}
+
+// history pass for the nb <= TD_B samples of a block: into plane buffer `buf`, on stream st.  lag0 = 0: the history before
+// s0 for the block starting at s0.  lag0 = TD_B (run-ahead): the history before s0 for the block starting at s0 + TD_B.
+int td_launch_far(cnld_td *t, cudaStream_t st, uint s0, uint nb, uint lag0, uint buf, bool narrow) {
+  const size_t PP = (size_t)t->P * t->P;
+  double *part = t->d_part + (size_t)buf * TD_B * PP;
+  const uint K = t->ntap > 1 ? std::min(s0 + lag0 + nb - 1, t->ntap - 1) : 0u;
+  if (!K) {
+    CNLD_CK(cudaMemsetAsync(part, 0, sizeof(double) * PP * TD_B, st));
+    return 0;
+  }
+  // narrow: about two CTAs per SM, so that the step kernels of the running block find room next to the pass
+  const uint ng = narrow ? t->ngroup_narrow : t->ngroup_far, per = narrow ? t->per_narrow : t->per_far;
+  const dim3 grid(t->P, ng);
+  if (!t->mma) k_fir_far<8><<<grid, FC_THREADS, 0, st>>>(t->P, t->ld, per, K, s0, t->tab, t->d_hist, t->nt, part);
+  else if (nb <= 8) k_fir_far_mma<1><<<grid, FC_THREADS, 0, st>>>(t->P, t->ng4, per, K, s0, lag0, t->d_tab8, t->d_hist, t->nt, part);
+  else k_fir_far_mma<2><<<grid, FC_THREADS, 0, st>>>(t->P, t->ng4, per, K, s0, lag0, t->d_tab8, t->d_hist, t->nt, part);
+  CNLD_CK_LAUNCH();
+  return 0;
+}
+
+// nb <= TD_B samples starting at s0 >= 1.  The history before the block is convolved once for all of them
+// (td_launch_far), the step kernels add the lags that reach into the block itself from fir[:, :, 1 .. nb - 1].
+// ahead: the pass for this block already ran under the previous block (stream st2, rows before the PREVIOUS block
+// only, plane buffer t->pbuf); k_fir_mid adds the previous block's samples.
+// prefetch: start the run-ahead pass for the next block now.
+int td_launch_block(cnld_td *t, uint s0, uint nb, bool ahead, bool prefetch) {
+  const size_t PP = (size_t)t->P * t->P;
+  if (ahead) {
+    CNLD_CK(cudaStreamWaitEvent(t->st, t->ev_far, 0));
+    k_fir_mid<<<t->P, 256, 0, t->st>>>(t->P, s0, t->d_firn, t->d_state + (size_t)TD_PTOT * t->nt * t->P,
+                                      t->d_part + (size_t)t->pbuf * TD_B * PP);
+    CNLD_CK_LAUNCH();
+  } else if (td_launch_far(t, t->st, s0, nb, 0, t->pbuf, false)) return -1;
+  if (prefetch) {                       // everything before s0 is final once the work queued on st so far is done
+    CNLD_CK(cudaEventRecord(t->ev_hist, t->st));
+    CNLD_CK(cudaStreamWaitEvent(t->st2, t->ev_hist, 0));
+    if (td_launch_far(t, t->st2, s0, TD_B, TD_B, t->pbuf ^ 1u, true)) return -1;
+    CNLD_CK(cudaEventRecord(t->ev_far, t->st2));
+  }
+  const double *part = t->d_part + (size_t)t->pbuf * TD_B * PP;
+  for (uint b = 0; b < nb; b++) {
+    if (td_launch_kernel(t, s0 + b, t->ntap > 1 ? std::min(b, t->ntap - 1) : 0u, b >= 1, part + (size_t)b * PP)) return -1;
+  }
+  if (prefetch) t->pbuf ^= 1u;
   return 0;
 }
 }  // namespace
@@ -1045,6 +1107,7 @@ cnld_td *cnld_b200_td_create(int device, cnld_uint npatch, cnld_uint nfir, const
   t->dt = dt; t->e0 = e0; t->k = k; t->n = n; t->x0 = x0; t->lmbd = lmbd; t->atol = atol; t->maxiter = maxiter;
   if (const char *e = getenv("CNLD_B200_TD_PDL")) t->pdl = atoi(e) != 0;
   if (const char *e = getenv("CNLD_B200_TD_CLUSTER")) t->cluster = atoi(e) != 0;
+  if (const char *e = getenv("CNLD_B200_TD_OVERLAP")) t->overlap = atoi(e) != 0;
   if (td_smem_cl(npatch) > 200 * 1024) t->cluster = false;
   if (const char *e = getenv("CNLD_B200_TD_MMA")) t->mma = atoi(e) != 0;
   if (const char *e = getenv("CNLD_B200_TD_BLOCK")) t->block = (uint)std::min(std::max(atoi(e), 1), TD_B);
@@ -1062,11 +1125,16 @@ cnld_td *cnld_b200_td_create(int device, cnld_uint npatch, cnld_uint nfir, const
   t->per_far = (npatch + t->ngroup_far - 1) / t->ngroup_far;
   if (t->mma == 1) t->per_far = (t->per_far + 7) & ~7u;          // whole tiles of 8 destinations per CTA
   t->ngroup_far = (npatch + t->per_far - 1) / t->per_far;
+  t->ngroup_narrow = std::max(1u, std::min((npatch + 7) / 8, (uint)(2 * nsm) / npatch));
+  t->per_narrow = ((npatch + t->ngroup_narrow - 1) / t->ngroup_narrow + 7) & ~7u;
+  t->ngroup_narrow = (npatch + t->per_narrow - 1) / t->per_narrow;
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   const size_t PP = (size_t)npatch * npatch, tab = PP * t->ld + 4, rows = (size_t)nt * npatch;
   bool ok = cudaSetDevice(device) == cudaSuccess && cudaMalloc(&t->d_fir, sizeof(double) * tab) == cudaSuccess &&
             cudaMemset(t->d_fir, 0, sizeof(double) * tab) == cudaSuccess &&
-            cudaMalloc(&t->d_fir0, sizeof(double) * PP) == cudaSuccess && cudaMalloc(&t->d_part, sizeof(double) * PP * TD_B) == cudaSuccess &&
-            cudaMalloc(&t->d_firn, sizeof(double) * PP * (TD_B - 1)) == cudaSuccess &&
+            cudaMalloc(&t->d_fir0, sizeof(double) * PP) == cudaSuccess && cudaMalloc(&t->d_part, sizeof(double) * PP * TD_B * 2) == cudaSuccess &&
+            cudaMalloc(&t->d_firn, sizeof(double) * PP * TD_NL) == cudaSuccess &&
             cudaMalloc(&t->d_v, sizeof(double) * rows) == cudaSuccess && cudaMalloc(&t->d_geff, sizeof(double) * npatch) == cudaSuccess &&
             cudaMalloc(&t->d_hist, sizeof(double) * rows) == cudaSuccess &&
             cudaMalloc(&t->d_state, sizeof(double) * rows * TD_NSTATE) == cudaSuccess &&
@@ -1077,14 +1145,17 @@ cnld_td *cnld_b200_td_create(int device, cnld_uint npatch, cnld_uint nfir, const
                          cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaMemcpy(t->d_v, v, sizeof(double) * rows, cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaMemcpy(t->d_geff, gap_eff, sizeof(double) * npatch, cudaMemcpyHostToDevice) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&t->st, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&t->st2, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+            cudaEventCreateWithFlags(&t->ev_hist, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&t->ev_far, cudaEventDisableTiming) == cudaSuccess &&
             cudaFuncSetAttribute(k_td_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
             (!t->cluster ||
              cudaFuncSetAttribute(k_td_step_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)td_smem_cl(npatch)) == cudaSuccess);
   if (ok) {
     t->tab = t->d_fir + 3;
     k_td_gather_fir0<<<(unsigned)((PP + 255) / 256), 256, 0, t->st>>>(npatch, t->ld, t->tab, t->d_fir0);
-    k_td_gather_near<<<(unsigned)((PP * (TD_B - 1) + 255) / 256), 256, 0, t->st>>>(npatch, nfir, t->ld, t->tab, t->d_firn);
+    k_td_gather_near<<<(unsigned)((PP * TD_NL + 255) / 256), 256, 0, t->st>>>(npatch, nfir, t->ld, t->tab, t->d_firn);
     if (t->mma == 1) {
       t->ng4 = (((size_t)nfir + 3) / 4 + 3) & ~(size_t)3;       // whole chunks of 16 taps
       const size_t n8 = (size_t)npatch * ((npatch + 7) / 8) * t->ng4 * 32;
@@ -1113,6 +1184,9 @@ void cnld_b200_td_destroy(cnld_td *t) {
   cudaFree(t->d_fir); cudaFree(t->d_fir0); cudaFree(t->d_firn); cudaFree(t->d_tab8); cudaFree(t->d_part); cudaFree(t->d_v); cudaFree(t->d_geff); cudaFree(t->d_hist);
   cudaFree(t->d_state); cudaFree(t->d_err); cudaFree(t->d_iters); cudaFree(t->d_trace);
   if (t->st) cudaStreamDestroy(t->st);
+  if (t->st2) cudaStreamDestroy(t->st2);
+  if (t->ev_hist) cudaEventDestroy(t->ev_hist);
+  if (t->ev_far) cudaEventDestroy(t->ev_far);
   delete t;
 }
 
@@ -1128,6 +1202,7 @@ int cnld_b200_td_reset(cnld_td *t) {
   if (td_launch_step(t, 0)) return -1;
   CNLD_CK(cudaStreamSynchronize(t->st));
   t->cur = 1;
+  t->pbuf = 0;
   return 0;
 }
 
@@ -1136,12 +1211,22 @@ int cnld_b200_td_step(cnld_td *t, cnld_uint nsteps) {
   if (!t) { set_error("null td solver"); return -1; }
   if ((size_t)t->cur + nsteps > t->nt) { set_error("td_step: %u steps from sample %u run past the %u samples of the time grid", nsteps, t->cur, t->nt); return -1; }
   CNLD_CK(cudaSetDevice(t->device));
+  bool ahead = false;                   // the history pass of the next block to launch has run ahead
   for (uint left = nsteps; left;) {
     const uint nb = std::min(left, t->block);
-    if (nb > 1 ? td_launch_block(t, t->cur, nb) : td_launch_step(t, t->cur)) return -1;
+    if (nb > 1) {
+      // run ahead for the next block if this one is a full block of TD_B samples and a next block exists
+      const bool prefetch = t->overlap && t->mma && t->block == (uint)TD_B && nb == (uint)TD_B && left - nb > 1;
+      if (td_launch_block(t, t->cur, nb, ahead, prefetch)) return -1;
+      ahead = prefetch;
+    } else {
+      if (td_launch_step(t, t->cur)) return -1;
+      ahead = false;
+    }
     t->cur += nb;
     left -= nb;
   }
+  CNLD_CK(cudaStreamSynchronize(t->st2));
   CNLD_CK(cudaStreamSynchronize(t->st));
   return 0;
 }
