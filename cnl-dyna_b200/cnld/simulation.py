@@ -7,7 +7,8 @@ The arithmetic runs in libcnld_b200 (csrc/firconv.cu): the patch-to-patch table,
 every state array stay on one GPU.  Stepped one sample at a time, a step is one pass over the table plus the
 fixed-point iterations of the current sample in a single CTA (`cnld_b200_td_*`); `step(n)` / `solve()` advance in
 blocks of 16 samples per table pass (the history before the block is convolved once for all 16, the lags inside
-the block are added per sample) and never return to the host in between.  This module keeps the reference's
+the block are added per sample; the pass for the next block runs under the current block's samples) and never
+return to the host in between.  This module keeps the reference's
 objects and names around it: the constructor resamples the table and the drive exactly as the reference does
 (scipy interp1d, host, once), `StateDB` holds the host copies the properties hand out.
 

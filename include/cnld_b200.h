@@ -322,7 +322,9 @@ int cnld_b200_td_reset(cnld_td *t);
  * per pass over the table (the history before the block is convolved once for the whole block, the lags inside it per
  * sample); nsteps = 1 is the reference's scheme, one pass per sample.  Environment at create: CNLD_B200_TD_BLOCK=n
  * (1..16) block size, CNLD_B200_TD_MMA=0 history pass without the interleaved second copy of the table (blocks of 8),
- * CNLD_B200_TD_PDL=0 no programmatic dependent launches, CNLD_B200_TD_TRACE=1 phase marks for cnld_b200_td_trace. */
+ * CNLD_B200_TD_PDL=0 no programmatic dependent launches, CNLD_B200_TD_CLUSTER=0 step kernel on one CTA,
+ * CNLD_B200_TD_OVERLAP=0 history passes in line instead of running ahead on a second stream,
+ * CNLD_B200_TD_TRACE=1 phase marks for cnld_b200_td_trace. */
 int cnld_b200_td_step(cnld_td *t, cnld_uint nsteps);
 cnld_uint cnld_b200_td_current_step(const cnld_td *t);
 /* taps a step's convolution reads: 1 + the last tap that is nonzero in any patch pair (a causal, Kramers-Kronig
