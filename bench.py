@@ -545,6 +545,187 @@ def bench_c4(args, rank, world, local):
         raise SystemExit('bench.py: c4 H-matvec differs from exactly integrated rows by more than eps_aca')
 
 
+TD_METRIC = 'time steps/s (FixedStepSolver: contact simulation on the patch-to-patch impulse responses), 4x4 CMUT array table'
+TD_KW = dict(k=3e14, n=1, x0=-15e-9, lmbd=3e13, atol=1e-12, maxiter=5)
+
+
+def td_scenario(P=144, nfir=4000, nt=400, seed=3):
+    """Synthetic table of the 4x4 array's size (P x P damped oscillators, coupling falling off with the patch distance),
+    a DC ramp + tone drive that takes the patches into contact; contact threshold inside the stable electrostatic range."""
+    dt = 2e-9
+    side = int(round(P**0.5))
+    rng = np.random.default_rng(seed)
+    tt = np.arange(nfir) * dt
+    px, py = np.arange(P) % side, np.arange(P) // side
+    dist = np.hypot(px[:, None] - px[None, :], py[:, None] - py[None, :])
+    amp = 7e-7 / (1 + 5 * dist)**2 * (1 + 0.1 * rng.standard_normal((P, P)))
+    fir = amp[:, :, None] * np.exp(-tt / 70e-9) * np.sin(2 * np.pi * 5.5e6 * tt + 0.3)
+    t = np.arange(nt) * dt
+    v = np.outer(1 / (1 + np.exp(-(t - 60e-9) / 10e-9)), 19.5 + 1.5 * rng.random(P)) + \
+        1.5 * np.outer(np.sin(2 * np.pi * 8e6 * t), np.ones(P))
+    return fir, t, v, np.full(P, 50e-9 + 100e-9 / 6.3), dt
+
+
+def bench_td_reference(args, rank):
+    """--impl reference --config td: the oracle's restatement of FixedStepSolver.step (numpy on the host's BLAS threads)
+    on a bounded sample of the same samples: a history longer than the table, 8 samples per step."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import pyoracle as po
+    per = 8
+    fir, t, v, gap_eff, dt = td_scenario(nt=4100)
+    rng = np.random.default_rng(1)
+    hist = -1e6 * rng.random((4050, fir.shape[0]))           # a pressure history of the right size and magnitude
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for s_ in range(steps * per):
+        base = po.fir_conv(fir, hist, dt, 1)
+        for _ in range(6):                                    # the fixed point's products on the current sample
+            base + dt * (hist[-1] @ fir[:, :, 0])
+    dts = (time.perf_counter() - t0) / steps
+    val = per / dts
+    print(json.dumps({
+        'impl': 'reference', 'metric': TD_METRIC, 'value': val, 'unit': 'steps/s', 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': 0, 'ms_per_step': dts * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': {'workload': 'td: P=144 patches, 4000-tap table, history longer than the table'},
+        'cpu_baseline': {'value': val, 'unit': 'steps/s', 'cores': os.cpu_count(), 'kind': 'port',
+                         'sample': f'{per} samples per step: one base convolution over the whole table + 6 zero-lag products each '
+                                   '(oracle restatement, numpy einsum)'},
+        'e2e': {'value': val, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}), flush=True)
+
+
+def bench_td(args, rank, world, local):
+    """--config td: the time-domain consumer of the sweep's database.  One bench step =
+    `--td-samples` time steps of FixedStepSolver on one GPU; N > 1 = independent replicas (a simulation does not shard)."""
+    os.environ['CNLD_B200_DEVICE'] = str(local)
+    from cnld import _lib, simulation
+    if _lib.device_count() == 0:
+        raise SystemExit('bench.py: no CUDA device -- libcnld_b200 has no CPU fallback')
+    comm = _lib.Comm(rank, world, local) if world > 1 else None
+    ns = args.td_samples
+    warm = 4000 + 64
+    nt = warm + ns * (args.steps + args.warmup) + 2
+    fir, t, v, gap_eff, dt = td_scenario(nt=nt, seed=3 + rank)
+    P, nfir = fir.shape[0], fir.shape[2]
+    sol = _lib.TimeDomainSolver(fir, v, gap_eff, dt, TD_KW['k'], TD_KW['n'], TD_KW['x0'], TD_KW['lmbd'], atol=TD_KW['atol'],
+                                maxiter=TD_KW['maxiter'], device=local)
+    sol.step(warm)                                            # history longer than the table from here on
+    for _ in range(args.warmup):
+        sol.step(ns)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if comm:
+        comm.barrier()
+    l0 = _lib.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sol.step(ns)                                          # synchronous: returns when the samples are final on the device
+    dts = time.perf_counter() - t0
+    launches = _lib.launch_count() - l0
+    if comm:
+        dts = comm.max(dts)
+    clocks = sampler.finish() if rank == 0 else None
+    value = ns * args.steps * world / dts
+    err, it = sol.info(1, sol.current_step)
+    st = sol.state(0, 321)
+    contact = int((sol.state(warm, sol.current_step)['x'] < TD_KW['x0']).sum())
+    sol.close()
+
+    # ---- end to end through the reference-facing class: every bench step brings all six state arrays of its samples back
+    # to the host (StateDB); the table and the drive go to the device once, in the constructor (reported, not timed --
+    # like the sweep's setup; most of it is the reference's own cubic resampling of the table with scipy on the host)
+    t0 = time.perf_counter()
+    fs = simulation.FixedStepSolver((np.arange(nfir + 1) * dt, np.concatenate([fir, fir[:, :, -1:]], axis=2)), (t, v), gap_eff,
+                                    gap_eff, (0.0, (nt - 1) * dt, dt), TD_KW['k'], TD_KW['n'], TD_KW['x0'], TD_KW['lmbd'],
+                                    atol=TD_KW['atol'], maxiter=TD_KW['maxiter'], device=local)
+    t_setup = time.perf_counter() - t0
+    fs.step(warm)
+    for _ in range(args.warmup):
+        fs.step(ns)
+    if comm:
+        comm.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fs.step(ns)
+    dte = time.perf_counter() - t0
+    if comm:
+        dte = comm.max(dte)
+    e2e = ns * args.steps * world / dte
+    h2d, d2h = 0, 6 * ns * P * 8 + ns * 12
+    x_e2e = fs.displacement
+    assert np.isfinite(x_e2e).all() and x_e2e.shape[0] == fs.current_step
+    fs.close()
+
+    line = None
+    if rank == 0:
+        # the history pass alone: in line (no run-ahead), from the phase marks of the step kernels around it
+        os.environ['CNLD_B200_TD_TRACE'] = '1'
+        os.environ['CNLD_B200_TD_OVERLAP'] = '0'
+        s2 = _lib.TimeDomainSolver(fir, v, gap_eff, dt, TD_KW['k'], TD_KW['n'], TD_KW['x0'], TD_KW['lmbd'], atol=TD_KW['atol'],
+                                   maxiter=TD_KW['maxiter'], device=local)
+        s2.step(warm + 64)
+        tr = s2.trace(warm, warm + 64).astype(np.int64)
+        s2.close()
+        del os.environ['CNLD_B200_TD_TRACE'], os.environ['CNLD_B200_TD_OVERLAP']
+        gaps = (tr[1:, 2] - tr[:-1, 6]) / 1e9                 # previous kernel's last store -> this kernel's dependency met
+        t_pass = float(np.median(np.sort(gaps)[-3:]))         # the block boundaries (16 samples apart) hold the pass
+        t_step = float(np.median(np.diff(tr[:, 0]))) / 1e9
+        hbm, hbm_src = MEASURED_HBM()
+        ach = fir.nbytes * (nfir - 1) / nfir / t_pass / 1e9
+        line = {
+            'metric': TD_METRIC, 'value': value, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': dts / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'td: FixedStepSolver, P={P} patches, {nfir}-tap table ({fir.nbytes / 1e6:.0f} MB), history longer '
+                                   f'than the table, contact engaged ({contact} patch samples in contact), {ns} time steps per bench step',
+                       'solver': TD_KW, 'parallelism': f'replicas x{world}', 'convolutions_per_sample_mean': float(it[warm:].mean()),
+                       'cache': 'table 663 MB >> 126 MB L2'},
+            'e2e': {'value': e2e, 'unit': 'steps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                    'note': 'cnld.simulation.FixedStepSolver.step(n): the six state arrays, errors and iteration counts of the n samples '
+                            'copied back into the host StateDB inside the timed region; table and drive uploaded once by the constructor',
+                    'setup_seconds_once': t_setup},
+            'gpu_launches': int(launches), 'clocks': clocks,
+            'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None,
+                         'kernel': 'k_fir_far_mma<2>: the history pass (one read of the table, 16 lags per entry on DMMA) timed in '
+                                   'line from the step kernels\' phase marks; in the timed region it runs ahead on a second stream '
+                                   'under the previous block and serves 16 samples',
+                         'peak_source': hbm_src, 'seconds_per_pass': t_pass, 'table_bytes_per_sample': fir.nbytes / 16,
+                         'step_kernel_seconds': t_step,
+                         'note': 'a sample costs one cluster step kernel (latency bound: ~6 fixed-point iterations of scalar '
+                                 'code between barriers) + 1/16 of a hidden pass'},
+        }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import pyoracle as po
+        ref = po.td_solve(fir, v[:322], gap_eff, dt, TD_KW['k'], TD_KW['n'], TD_KW['x0'], TD_KW['lmbd'], TD_KW['atol'],
+                          TD_KW['maxiter'], nsteps=320)
+        rel = {key: float(np.linalg.norm(st[key] - ref[key][:321]) / max(np.linalg.norm(ref[key][:321]), 1e-300))
+               for key in ('x', 'u', 'p_tot', 'p_cont_spr')}
+        same_it = bool(np.array_equal(it[:320], ref['iters']))
+        line['parity'] = {'config': 'td', 'samples': 320, 'rel_l2': rel, 'iteration_counts_equal': same_it, 'tolerance': 1e-9,
+                          'against': 'oracle restatement of FixedStepSolver (pinned to the reference class by tests/golden/td_solver.npz)'}
+        rng = np.random.default_rng(1)
+        hist = -1e6 * rng.random((4050, P))
+        t0 = time.perf_counter()
+        for _ in range(16):
+            base = po.fir_conv(fir, hist, dt, 1)
+            for _ in range(6):
+                base + dt * (hist[-1] @ fir[:, :, 0])
+        tc = (time.perf_counter() - t0) / 16
+        line['cpu_baseline'] = {'value': 1.0 / tc, 'unit': 'steps/s', 'cores': os.cpu_count(), 'kind': 'port',
+                                'sample': '16 samples with a history longer than the table: one base convolution + 6 zero-lag '
+                                          'products each (oracle restatement, numpy einsum)'}
+        if not (max(rel.values()) < 1e-9 and same_it):
+            print(json.dumps(line), flush=True)
+            raise SystemExit('bench.py: td solver differs from the oracle')
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if comm:
+        comm.close()
+
+
 def MEASURED_HBM():
     """(GB/s, source) of the HBM roofline denominator: MEASURED_PEAKS.json if present, else the profiling guide's fallback."""
     try:
@@ -560,7 +741,8 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--config', default='c3', choices=sorted(CONFIGS))
+    ap.add_argument('--config', default='c3', choices=sorted(CONFIGS) + ['td'])
+    ap.add_argument('--td-samples', type=int, default=2048, help='td: time steps per bench step')
     ap.add_argument('--freqs-per-step', type=int, default=12)
     ap.add_argument('--streams', type=int, default=6)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -584,6 +766,8 @@ def main():
             return bench_c5_reference(args, rank)
         if args.config == 'c4':
             return bench_c4_reference(args, rank)
+        if args.config == 'td':
+            return bench_td_reference(args, rank)
         if args.steps > 2:
             args.steps, args.warmup = min(args.steps, 2), min(args.warmup, 1)
         run_reference(args, rank, world)
@@ -592,6 +776,8 @@ def main():
         return bench_c5(args, rank, world, local)
     if args.config == 'c4':
         return bench_c4(args, rank, world, local)
+    if args.config == 'td':
+        return bench_td(args, rank, world, local)
 
     import torch
     from cnld import _lib, arrays
