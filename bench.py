@@ -18,6 +18,8 @@ frequency ("weak" scaling: per-GPU batch fixed); setup broadcast once, patch res
 NCCL through the library's own C ABI (cnld_b200_comm_*, no torch.distributed).
   --config c4   16x16 array, ACA H-matrix + GMRES (BASELINE.json configs[3])
   --config c5   field pressure on 10^6 observation points (configs[4])
+  --config td   time steps/s of the time-domain contact solver (FixedStepSolver) on a table
+                of the 4x4 array's size; a simulation does not shard: --gpus N runs N independent replicas
 """
 import argparse
 import ctypes as C
