@@ -1111,6 +1111,11 @@ cnld_td *cnld_b200_td_create(int device, cnld_uint npatch, cnld_uint nfir, const
   if (td_smem_cl(npatch) > 200 * 1024) t->cluster = false;
   if (const char *e = getenv("CNLD_B200_TD_MMA")) t->mma = atoi(e) != 0;
   if (const char *e = getenv("CNLD_B200_TD_BLOCK")) t->block = (uint)std::min(std::max(atoi(e), 1), TD_B);
+  if (t->mma) {                         // the DMMA pass reads a second, interleaved copy of the table: only if both fit
+    size_t fr = 0, tot = 0;
+    const size_t one = sizeof(double) * (size_t)npatch * (((size_t)npatch + 7) & ~(size_t)7) * ((size_t)nfir + 16);
+    if (cudaSetDevice(device) == cudaSuccess && cudaMemGetInfo(&fr, &tot) == cudaSuccess && 2 * one + ((size_t)1 << 30) > fr) t->mma = 0;
+  }
   if (!t->mma) t->block = std::min(t->block, 8u);
   t->ld = ((size_t)nfir + 3 + 3) & ~(size_t)3;
   int nsm = 148;
