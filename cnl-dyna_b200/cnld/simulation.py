@@ -8,7 +8,7 @@ every state array stay on one GPU.  Stepped one sample at a time, a step is one 
 fixed-point iterations of the current sample in a single CTA (`cnld_b200_td_*`); `step(n)` / `solve()` advance in
 blocks of 16 samples per table pass (the history before the block is convolved once for all 16, the lags inside
 the block are added per sample; the pass for the next block runs under the current block's samples) and never
-return to the host in between.  This module keeps the reference's
+return to the host in between; `step()` called sample by sample is served from a look-ahead of whole blocks.  This module keeps the reference's
 objects and names around it: the constructor resamples the table and the drive exactly as the reference does
 (scipy interp1d, host, once), `StateDB` holds the host copies the properties hand out.
 
@@ -144,10 +144,7 @@ class FixedStepSolver:
         self._p_cont_dmp = make_p_cont_dmp(lmbd, n, x0)
         self._dev = _lib.TimeDomainSolver(self._fir, self._db.v, self._gap_eff, t_step, k, n, x0, lmbd, atol=atol,
                                           maxiter=maxiter, e0=e_0, device=device)
-        self._error = np.zeros(0)
-        self._iters = np.zeros(0, dtype=np.int32)
-        self.current_step = 1
-        self._pull(0, 1)
+        self._start()
 
     @classmethod
     def from_array_and_db(cls, array, dbfile, t_v, t_lim, k, n, x0, lmbd, atol=1e-10, maxiter=5, calc_fir=False,
@@ -168,13 +165,37 @@ class FixedStepSolver:
         return cls((fir_t, fir), t_v, gap, gap_eff, t_lim, k, n, x0, lmbd, atol, maxiter, device=device)
 
     # -- device -> host -------------------------------------------------------------------------------------
-    def _pull(self, i0, i1):
-        db = self._db
-        self._dev.state(i0, i1, into={name: getattr(db, '_' + name) for name in _FIELDS})
-        if i1 > max(i0, 1):
-            err, it = self._dev.info(max(i0, 1), i1)
-            self._error = np.concatenate([self._error[:max(i0, 1) - 1], err])
-            self._iters = np.concatenate([self._iters[:max(i0, 1) - 1], it])
+    # The device runs ahead of `current_step`: the drive is fixed at construction, so a call that needs one more
+    # sample advances the device by LOOKAHEAD samples (whole blocks of 16 per table pass instead of one pass per
+    # sample) into private arrays; rows become visible in the StateDB only when `step()` reaches them, exactly when
+    # the reference would have computed them.
+    LOOKAHEAD = 64
+
+    def _start(self):
+        nt = len(self._db.t)
+        self._ahead = {name: np.zeros((nt, self.npatch)) for name in _FIELDS}
+        self._error_all = np.zeros(nt)
+        self._iters_all = np.zeros(nt, dtype=np.int32)
+        self._done = 1                                   # samples final on the device (its current_step)
+        self.current_step = 1
+        self._dev.state(0, 1, into=self._ahead)
+        self._reveal(0, 1)
+
+    def _advance(self, upto):
+        nt = len(self._db.t)
+        need = upto - self._done
+        if need <= 0:
+            return
+        n = need if self._done + need > nt else min(max(need, self.LOOKAHEAD), nt - self._done)
+        self._dev.step(n)                                # raises past the end of the time grid, like the library
+        lo, hi = self._done, self._done + n
+        self._dev.state(lo, hi, into=self._ahead)
+        self._error_all[lo:hi], self._iters_all[lo:hi] = self._dev.info(lo, hi)
+        self._done = hi
+
+    def _reveal(self, i0, i1):
+        for name in _FIELDS:
+            getattr(self._db, '_' + name)[i0:i1] = self._ahead[name][i0:i1]
 
     # -- the reference's read-only views ----------------------------------------------------------------------
     time = property(lambda self: self._db.t[:self.current_step])
@@ -185,8 +206,8 @@ class FixedStepSolver:
     pressure_contact_spring = property(lambda self: self._db.p_cont_spr[:self.current_step, :])
     pressure_contact_damper = property(lambda self: self._db.p_cont_dmp[:self.current_step, :])
     pressure_total = property(lambda self: self._db.p_tot[:self.current_step, :])
-    error = property(lambda self: np.array(self._error[:self.current_step]))
-    iters = property(lambda self: np.array(self._iters[:self.current_step]))
+    error = property(lambda self: np.array(self._error_all[1:self.current_step]))
+    iters = property(lambda self: np.array(self._iters_all[1:self.current_step]))
     props = property(lambda self: self.Properties(gap=self._gap, gap_eff=self._gap_eff))
 
     def get_current_state(self):
@@ -206,11 +227,11 @@ class FixedStepSolver:
 
     # -- stepping ----------------------------------------------------------------------------------------------
     def step(self, nsteps=1):
-        """Advance by one sample (:459-503), or by `nsteps` samples in one device call."""
+        """Advance by one sample (:459-503), or by `nsteps` samples."""
         first = self.current_step
-        self._dev.step(nsteps)
+        self._advance(first + nsteps)
         self.current_step = first + nsteps
-        self._pull(first, self.current_step)
+        self._reveal(first, self.current_step)
 
     def solve(self):
         """All remaining samples (:505-514; the reference's loop refers to a `_time` attribute that does not
@@ -222,10 +243,7 @@ class FixedStepSolver:
     def reset(self):
         self._db.clear()
         self._dev.reset()
-        self._error = np.zeros(0)
-        self._iters = np.zeros(0, dtype=np.int32)
-        self.current_step = 1
-        self._pull(0, 1)
+        self._start()
 
     def close(self):
         self._dev.close()

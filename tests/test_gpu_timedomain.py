@@ -98,6 +98,8 @@ def test_fixed_step_solver_vs_reference_golden(po):
         for _ in range(10):                      # one table pass per sample ...
             s.step()
         assert s.current_step == 11 and _rel(s.displacement, g[f'x{c}'][:11]) < 1e-9
+        # the device runs ahead in whole blocks; the StateDB shows a sample only when step() has reached it
+        assert s._done > 11 and not s._db.x[11:].any() and not s.get_current_state().x.any() and len(s.iters) == 10
         s.step(nsteps - 10)                      # ... then blocks of 8 samples per pass (history / in-block lags split)
         check()
         x_mixed = s.displacement.copy()
