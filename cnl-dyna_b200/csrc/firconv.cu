@@ -230,9 +230,16 @@ int cnld_b200_fir_add(cnld_fir *f, const double *p_row, double dt, double *x) {
 //                   (zero), then with the damper frozen at the converged estimate   (:412-445, :466-498)
 // The reference recomputes `_fir_conv_base` in the first `_update_x`; it is the blind estimate's convolution of
 // the same rows, so one pass over the table per step is all the HBM traffic a step needs.  Here nothing leaves
-// the device between steps: the total-pressure history IS the convolution's input (source-major rows), the
-// step's scalar logic runs in one CTA right behind the convolution on the same stream, and the state arrays are
-// downloaded when the caller asks for them.
+// the device between steps: the total-pressure history IS the convolution's input (source-major rows) and the
+// state arrays are downloaded when the caller asks for them.  How a run of samples is scheduled:
+//   * one sample (nsteps = 1):   k_fir_conv over the whole history, then the step kernel;
+//   * a block of up to TD_B = 16 samples: the history BEFORE the block is convolved once for all of them
+//     (k_fir_far_mma: every table entry loaded once, 16 lags each, on DMMA), the step kernel of sample s adds the
+//     lags that reach into the block's own samples (compact copy of the first lags, L2);
+//   * consecutive full blocks: the pass for block k + 1 runs ahead on a second stream under the samples of block k
+//     over the rows older than block k, k_fir_mid adds block k's samples at the boundary;
+//   * the step kernel (k_td_step_cl, a cluster of 4 CTAs, or k_td_step on one CTA) is a programmatic dependent of
+//     the kernel before it and does everything that does not depend on the previous sample before its wait.
 // np.vectorize quirk kept on purpose (results identical to the reference's): the contact closures return the
 // Python int 0 outside contact and np.vectorize derives its output dtype from the first element, so whenever
 // patch 0 is out of contact the contact pressures of all patches are truncated toward zero (int64).
@@ -267,8 +274,8 @@ struct cnld_td {
 namespace {
 constexpr int TD_THREADS = 1024;
 constexpr int TD_B = 16;       // blocked stepping: at most this many samples are served by one pass over the table
-constexpr int TD_NL = 2 * TD_B - 1;   // lags the step kernels add themselves: the block's own samples and, when the history
-                                      // pass ran ahead under the previous block, that block's samples too
+constexpr int TD_NL = 2 * TD_B - 1;   // lags of the compact copy: the step kernels add the block's own samples (lags < TD_B),
+                                      // k_fir_mid the previous block's when the history pass ran ahead (lags <= TD_NL)
 enum { TD_X = 0, TD_U, TD_PES, TD_SPR, TD_DMP, TD_PTOT, TD_NSTATE };
 
 struct TdArgs {
