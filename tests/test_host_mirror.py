@@ -160,6 +160,67 @@ def test_simulation_signals_and_statedb_match_reference_golden():
         sim.CompensationSolver()
 
 
+def test_fixed_step_solver_host_logic_with_oracle_standin(po, monkeypatch):
+    """The host side of cnld.simulation.FixedStepSolver (constructor resampling, look-ahead stepping with samples
+    revealed only when step() reaches them, iterator, reset, solve, the error past the time grid) with the device
+    object replaced by a stand-in that serves the oracle's solution; compared with the reference-generated golden."""
+    from cnld import _lib, simulation as sim
+    g = np.load(os.path.join(GOLDEN, 'td_solver.npz'))
+    c = 1
+
+    class StandIn:
+        STATE = _lib.TimeDomainSolver.STATE
+
+        def __init__(self, fir, v, gap_eff, dt, k, n, x0, lmbd, atol=1e-10, maxiter=5, e0=None, device=0):
+            self.nt, self.npatch = v.shape
+            self.sol = po.td_solve(fir, v, gap_eff, dt, k, n, x0, lmbd, atol, maxiter, nsteps=self.nt - 1)
+            self.current_step, self.calls = 1, []
+
+        def step(self, nsteps=1):
+            if self.current_step + nsteps > self.nt:
+                raise _lib.Cnldb200Error('td_step: past the time grid')
+            self.calls.append(nsteps)
+            self.current_step += nsteps
+
+        def reset(self):
+            self.current_step = 1
+
+        def state(self, i0, i1, into=None):
+            assert i1 <= self.current_step
+            for key in self.STATE:
+                into[key][i0:i1] = self.sol[key][i0:i1]
+
+        def info(self, s0, s1):
+            return self.sol['error'][s0 - 1:s1 - 1], self.sol['iters'][s0 - 1:s1 - 1]
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(_lib, 'TimeDomainSolver', StandIn)
+    nsteps = int(g[f'nsteps{c}'])
+    s = sim.FixedStepSolver((g[f'fir_t{c}'], g[f'fir{c}']), (g[f'v_t{c}'], g[f'v{c}']), g[f'gap{c}'], g[f'gap_eff{c}'],
+                            tuple(g[f't_lim{c}']), float(g[f'k{c}']), int(g[f'n{c}']), float(g[f'x0{c}']), float(g[f'lmbd{c}']),
+                            atol=float(g[f'atol{c}']), maxiter=int(g[f'maxiter{c}']))
+    assert np.array_equal(s._fir, g[f'firi{c}']) and s.current_step == 1 and len(s.error) == 0
+    assert np.allclose(s.pressure_electrostatic[0], g[f'p_es{c}'][0], rtol=1e-12)
+    for _ in range(5):
+        s.step()
+    assert s._dev.calls == [sim.FixedStepSolver.LOOKAHEAD]                     # one device call served five samples
+    assert s.current_step == 6 and not s._db.x[6:].any() and np.allclose(s.displacement, g[f'x{c}'][:6], rtol=1e-9, atol=1e-20)
+    assert np.array_equal(s.iters, g[f'iters{c}'][:5]) and s.get_previous_state().i == 5
+    s.step(80)                                                                  # beyond the look-ahead: one more call
+    assert s._dev.calls == [64, 64] and s.current_step == 86
+    assert sum(1 for _ in s) == nsteps - 85 and s.current_step == nsteps + 1   # iterator = step until len(t) - 1
+    assert np.allclose(s.pressure_total, g[f'p_tot{c}'][:nsteps + 1], rtol=1e-9, atol=1e-9)
+    assert np.array_equal(s.iters, g[f'iters{c}']) and np.allclose(s.error, g[f'error{c}'], atol=1e-18)
+    with pytest.raises(_lib.Cnldb200Error):
+        s.step(2)
+    s.reset()
+    assert s.current_step == 1 and not s._db.x.any() and len(s.iters) == 0
+    s.solve()
+    assert s.current_step == nsteps + 1 and np.allclose(s.velocity, g[f'u{c}'][:nsteps + 1], rtol=1e-8, atol=1e-12)
+
+
 def test_database_roundtrip(tmp_path):
     from cnld import database
     from cnld.scripts.generate_db import Config
