@@ -789,7 +789,11 @@ __global__ void __launch_bounds__(TD_THREADS) k_td_step(TdArgs a) {
 // barrier, every CTA adds the TD_CL partial vectors in rank order.  Everything else -- electrostatic and contact
 // pressures, the error norm, the control flow -- is computed redundantly by every CTA from identical inputs with
 // identical instructions, so all CTAs take the same branches and meet at the same barriers.  Rank 0 writes the rows.
-constexpr int TD_CL = 4, TD_MR = 8;       // cluster size; fir[:, :, 0] rows per thread kept in registers (at most)
+#ifndef CNLD_TD_CL
+#define CNLD_TD_CL 4                      // step kernel to step kernel at P = 144: 2 CTAs 24.7 us, 4 CTAs 19.7 us, 8 CTAs 20.3 us
+#endif
+constexpr int TD_CL = CNLD_TD_CL;         // cluster size
+constexpr int TD_MR = 32 / CNLD_TD_CL;    // fir[:, :, 0] rows per thread kept in registers (at most)
 namespace cg = cooperative_groups;
 
 struct TdCl {
